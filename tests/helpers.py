@@ -1,0 +1,122 @@
+"""ctypes bindings used by the tests: the index builder and the CPU oracle.
+
+The oracle (oracle/veloci_oracle.cpp) is test infrastructure: it is only ever
+loaded from tests/, __graft_entry__.smoke() and bench.py's CPU baseline.
+"""
+import ctypes
+import json
+import os
+import tempfile
+
+from veloci_b200 import build
+
+_ERRLEN = 4096
+
+
+class OracleError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(message)
+        self.status = status
+        self.message = message
+
+
+def _index_lib():
+    lib = ctypes.CDLL(build.build_index_lib())
+    lib.vidx_create_from_jsonl.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+    lib.vidx_create_synthetic.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+    lib.vidx_write_synthetic_requests.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+    return lib
+
+
+def create_index(directory, docs, config=None):
+    """docs: list of JSON-able documents (or a JSON-lines string); config: dict of field configs."""
+    lib = _index_lib()
+    text = docs if isinstance(docs, str) else "\n".join(json.dumps(d, ensure_ascii=False) for d in docs)
+    err = ctypes.create_string_buffer(_ERRLEN)
+    rc = lib.vidx_create_from_jsonl(directory.encode(), text.encode("utf-8"), json.dumps(config or {}).encode(), err, _ERRLEN)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return directory
+
+
+def create_synthetic_index(directory, **params):
+    lib = _index_lib()
+    err = ctypes.create_string_buffer(_ERRLEN)
+    rc = lib.vidx_create_synthetic(directory.encode(), json.dumps(params).encode(), err, _ERRLEN)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return directory
+
+
+def synthetic_requests(**params):
+    lib = _index_lib()
+    err = ctypes.create_string_buffer(_ERRLEN)
+    with tempfile.NamedTemporaryFile(suffix=".jsonl", delete=False) as f:
+        path = f.name
+    try:
+        rc = lib.vidx_write_synthetic_requests(path.encode(), json.dumps(params).encode(), err, _ERRLEN)
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        with open(path) as f:
+            return [line for line in f.read().split("\n") if line]
+    finally:
+        os.unlink(path)
+
+
+class Oracle:
+    def __init__(self, directory=None):
+        self.lib = ctypes.CDLL(build.build_oracle())
+        L = self.lib
+        L.vo_open.restype = ctypes.c_void_p
+        L.vo_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+        L.vo_close.argtypes = [ctypes.c_void_p]
+        L.vo_free.argtypes = [ctypes.c_void_p]
+        L.vo_search.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
+        L.vo_call.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
+        L.vo_search_batch.restype = ctypes.c_double
+        L.vo_search_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        self.h = None
+        if directory is not None:
+            err = ctypes.create_string_buffer(_ERRLEN)
+            self.h = L.vo_open(directory.encode(), err, _ERRLEN)
+            if not self.h:
+                raise OracleError(4, err.value.decode())
+
+    def close(self):
+        if self.h:
+            self.lib.vo_close(self.h)
+            self.h = None
+
+    def _take(self, rc, out, err):
+        if rc != 0:
+            raise OracleError(rc, err.value.decode())
+        s = ctypes.string_at(out.value).decode("utf-8")
+        self.lib.vo_free(out)
+        return s
+
+    def search(self, request):
+        """request: dict or JSON string -> {"num_hits", "data": [[id, score, score_bits]...], "facets"}"""
+        text = request if isinstance(request, str) else json.dumps(request, ensure_ascii=False)
+        out = ctypes.c_void_p()
+        err = ctypes.create_string_buffer(_ERRLEN)
+        rc = self.lib.vo_search(self.h, text.encode("utf-8"), ctypes.byref(out), err, _ERRLEN)
+        return json.loads(self._take(rc, out, err))
+
+    def call(self, fn, **args):
+        out = ctypes.c_void_p()
+        err = ctypes.create_string_buffer(_ERRLEN)
+        rc = self.lib.vo_call(self.h, fn.encode(), json.dumps(args, ensure_ascii=False).encode("utf-8"), ctypes.byref(out), err, _ERRLEN)
+        return json.loads(self._take(rc, out, err))
+
+    def search_batch(self, requests, threads=1, k=10):
+        import numpy as np
+
+        n = len(requests)
+        arr = (ctypes.c_char_p * n)(*[r.encode("utf-8") if isinstance(r, str) else json.dumps(r).encode("utf-8") for r in requests])
+        ids = np.zeros((n, k), dtype=np.uint32)
+        scores = np.zeros((n, k), dtype=np.float32)
+        num_hits = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        secs = self.lib.vo_search_batch(self.h, arr, n, threads, k, ids.ctypes.data, scores.ctypes.data, num_hits.ctypes.data, status.ctypes.data)
+        return {"seconds": secs, "ids": ids, "scores": scores, "num_hits": num_hits, "status": status}
