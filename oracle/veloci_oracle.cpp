@@ -1215,6 +1215,136 @@ static std::string call(const Persistence* p, const std::string& fn, const vjson
         }
         return s + "]";
     }
+    // ---- codec round trips (writer -> bytes -> reader) for the reference's codec unit tests
+    auto u32s = [](const vjson::Value& arr) {
+        std::vector<uint32_t> v;
+        for (auto& x : arr.arr) v.push_back((uint32_t)x.num);
+        return v;
+    };
+    if (fn == "codec_indirect") {
+        vfmt::IndirectWriter w;
+        for (auto& e : a.get("adds")->arr) w.add((uint32_t)e.arr[0].num, u32s(e.arr[1]));
+        vfmt::IndirectView v;
+        v.start_pos = (const uint8_t*)w.ids.data();
+        v.n_ids = w.ids.size();
+        v.data = w.data.data();
+        v.data_len = w.data.size();
+        std::string s = "{\"values\":[";
+        std::vector<uint32_t> out;
+        bool first = true;
+        std::map<uint32_t, uint32_t> counts;
+        for (auto& q : a.get("queries")->arr) {
+            s += first ? "" : ",";
+            first = false;
+            if (v.get_values((uint64_t)q.num, out)) {
+                s += ids_to_json(out);
+                for (uint32_t x : out) counts[x]++;
+            } else s += "null";
+        }
+        s += "],\"counts\":{";
+        first = true;
+        for (auto& kv : counts) {
+            s += (first ? "\"" : ",\"") + std::to_string(kv.first) + "\":" + std::to_string(kv.second);
+            first = false;
+        }
+        return s + "},\"data_len\":" + std::to_string(w.data.size()) + "}";
+    }
+    if (fn == "codec_packed") {
+        std::vector<uint32_t> vals = u32s(*a.get("stored"));  // already value+1, like encode_vals' input
+        uint32_t mx = 0;
+        for (uint32_t x : vals) mx = std::max(mx, x);
+        int width = vfmt::packed_bytes_required(mx);
+        std::vector<uint8_t> bytes(vals.size() * (size_t)width);
+        for (size_t i = 0; i < vals.size(); ++i) memcpy(&bytes[i * width], &vals[i], (size_t)width);
+        vfmt::PackedView v;
+        v.bytes = bytes.data();
+        v.len = bytes.size();
+        v.width = width;
+        std::string s = "{\"width\":" + std::to_string(width) + ",\"values\":[";
+        bool first = true;
+        for (auto& q : a.get("queries")->arr) {
+            uint32_t out;
+            s += first ? "" : ",";
+            first = false;
+            s += v.get_value((uint64_t)q.num, out) ? std::to_string(out) : "null";
+        }
+        return s + "]}";
+    }
+    if (fn == "codec_phrase") {
+        vfmt::PhrasePairWriter w;
+        for (auto& e : a.get("adds")->arr) {
+            std::vector<uint32_t> vals = u32s(e.arr[2]);
+            w.add((uint32_t)e.arr[0].num, (uint32_t)e.arr[1].num, vals.data(), vals.size());
+        }
+        vfmt::PhrasePairView v;
+        v.recs = w.recs.data();
+        v.n = w.recs.size() / 12;
+        v.data = w.data.data();
+        v.data_len = w.data.size();
+        std::string s = "{\"size\":" + std::to_string(v.n) + ",\"offsets\":[";
+        for (size_t i = 0; i < v.n; ++i) s += (i ? "," : "") + std::to_string(vfmt::load_u32(v.recs + i * 12 + 8));
+        s += "],\"values\":[";
+        bool first = true;
+        for (auto& q : a.get("queries")->arr) {
+            std::vector<uint32_t> out;
+            s += first ? "" : ",";
+            first = false;
+            s += v.get_values((uint32_t)q.arr[0].num, (uint32_t)q.arr[1].num, out) ? ids_to_json(out) : "null";
+        }
+        return s + "]}";
+    }
+    if (fn == "codec_anchor_score") {
+        vfmt::AnchorScoreWriter w;
+        for (auto& e : a.get("adds")->arr) {
+            std::vector<uint32_t> pairs = u32s(e.arr[1]);
+            w.set_scores((uint32_t)e.arr[0].num, pairs.data(), pairs.size());
+        }
+        std::vector<uint8_t> sp = w.encode_start_pos();
+        vfmt::AnchorScoreView v;
+        v.start_pos = sp.data();
+        v.start_len = sp.size();
+        v.data = w.data.data();
+        v.data_len = w.data.size();
+        std::string s = "[";
+        bool first = true;
+        for (auto& q : a.get("queries")->arr) {
+            s += first ? "[" : ",[";
+            first = false;
+            bool f2 = true;
+            v.for_each((uint32_t)q.num, [&](uint32_t anchor, uint32_t score) {
+                s += (f2 ? "[" : ",[") + std::to_string(anchor) + "," + std::to_string(score) + "]";
+                f2 = false;
+            });
+            s += "]";
+        }
+        return s + "]";
+    }
+    if (fn == "fst_roundtrip") {
+        vfmt::FstWriter w;
+        uint64_t i = 0;
+        for (auto& k : a.get("keys")->arr) w.insert(k.str, a.get("values") ? (uint64_t)a.get("values")->arr[i].num : i), ++i;
+        std::vector<uint8_t> bytes = w.finish();
+        vfmt::FstReader r(bytes.data(), bytes.size());
+        std::string s = "{\"len\":" + std::to_string(r.len()) + ",\"bytes\":" + std::to_string(bytes.size()) + ",\"items\":[";
+        bool first = true;
+        r.for_each([&](const std::string& k, uint64_t v) {
+            s += first ? "[" : ",[";
+            first = false;
+            vjson::write_string(s, k);
+            s += "," + std::to_string(v) + "]";
+        });
+        s += "],\"ord_to_term\":[";
+        first = true;
+        if (a.get("ords"))
+            for (auto& o : a.get("ords")->arr) {
+                std::string t;
+                s += first ? "" : ",";
+                first = false;
+                if (r.ord_to_term((uint64_t)o.num, t)) vjson::write_string(s, t);
+                else s += "null";
+            }
+        return s + "]}";
+    }
     if (!p) throw InvalidRequest("call needs an index: " + fn);
     if (fn == "field_search") {  // get_term_ids_in_field
         PlanRequestSearchPart pr;

@@ -1,0 +1,384 @@
+"""Pins the CPU oracle against the reference's own integration fixtures.
+
+Every test cites the reference test it ports (file:line).  The reference asserts
+on hit counts, ranking order, document fields and facet vectors; documents are
+addressed here through the anchor id (= position in the corpus list), since
+fetching documents from the doc store is outside the hot path.
+"""
+import tempfile
+
+import pytest
+
+import helpers
+import ref_fixtures as fx
+
+
+def _make(docs, config):
+    d = tempfile.mkdtemp(prefix="vb200_idx_")
+    helpers.create_index(d, docs, config)
+    return helpers.Oracle(d)
+
+
+@pytest.fixture(scope="module")
+def test_all(native_libs):
+    return _make(fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG)
+
+
+@pytest.fixture(scope="module")
+def test_score(native_libs):
+    return _make(fx.TEST_SCORE_DOCS, fx.TEST_SCORE_CONFIG)
+
+
+@pytest.fixture(scope="module")
+def test_phrase(native_libs):
+    return _make(fx.TEST_PHRASE_DOCS, fx.TEST_PHRASE_CONFIG)
+
+
+@pytest.fixture(scope="module")
+def test_facet(native_libs):
+    return _make(fx.TEST_FACET_DOCS, fx.TEST_FACET_CONFIG)
+
+
+def docs_of(res, corpus):
+    return [corpus[h[0]] for h in res["data"]]
+
+
+def search_req(o, search_request, **extra):
+    return o.search({"search_req": search_request, **extra})
+
+
+A = fx.TEST_ALL_DOCS
+
+
+def test_simple_search(test_all):  # tests.rs:262-276
+    hits = docs_of(search_req(test_all, {"search": {"terms": ["urge"], "path": "meanings.eng[]"}}), A)
+    assert len(hits) == 1
+    assert hits[0]["ent_seq"] == "1587690"
+    assert hits[0]["commonness"] == 20
+    assert hits[0]["tags"] == ["nice"]
+
+
+def test_simple_search_skip_far(test_all):  # tests.rs:307-321
+    res = search_req(test_all, {"search": {"terms": ["urge"], "path": "meanings.eng[]"}}, skip=1000)
+    assert len(res["data"]) == 0
+
+
+def test_simple_search_case_sensitive(test_all):  # tests.rs:323-346
+    assert len(search_req(test_all, {"search": {"ignore_case": True, "terms": ["Urge"], "path": "meanings.eng[]"}})["data"]) == 1
+    assert len(search_req(test_all, {"search": {"ignore_case": False, "terms": ["Urge"], "path": "meanings.eng[]"}})["data"]) == 0
+
+
+def test_or_query(test_all):  # tests.rs:366-391 (explain part dropped)
+    res = search_req(test_all, {"or": {"queries": [{"search": {"terms": ["majestät"], "path": "meanings.ger[]"}}, {"search": {"terms": ["urge"], "path": "meanings.eng[]"}}]}})
+    hits = docs_of(res, A)
+    assert len(hits) == 2
+    assert hits[0]["ent_seq"] == "1587690"
+
+
+def test_float_and_bool(test_all):  # tests.rs:393-419
+    hits = docs_of(search_req(test_all, {"search": {"terms": ["5.123"], "path": "float_value"}}), A)
+    assert len(hits) == 1 and hits[0]["float_value"] == 5.123
+    hits = docs_of(search_req(test_all, {"search": {"terms": ["true"], "path": "my_bool"}}), A)
+    assert len(hits) == 1 and hits[0]["my_bool"] is True
+
+
+def test_invalid_field_error(test_all):  # tests.rs:421-436
+    with pytest.raises(helpers.OracleError) as e:
+        search_req(test_all, {"search": {"terms": ["test"], "path": "notexisting"}})
+    assert e.value.message == "field does not exist notexisting.textindex (fst not found)"
+    assert e.value.status == 2
+
+
+def test_missing_search_req_is_invalid(test_all):  # search.rs:151-155
+    with pytest.raises(helpers.OracleError) as e:
+        test_all.search({"top": 3})
+    assert e.value.status == 1
+
+
+def test_two_tokens_hit_the_same_anchor(test_all):  # tests.rs:455-468
+    hits = docs_of(search_req(test_all, {"search": {"terms": ["majestätischer"], "path": "meanings.ger[]", "levenshtein_distance": 1}}), A)
+    assert len(hits) == 1 and hits[0]["ent_seq"] == "1587680"
+
+
+def test_deep_structured_objects(test_all):  # tests.rs:470-483
+    hits = docs_of(search_req(test_all, {"search": {"terms": ["brook"], "path": "address[].line[]", "levenshtein_distance": 1}}), A)
+    assert len(hits) == 1 and hits[0]["id"] == 123456
+
+
+def test_search_without_first_char_exact_match(test_all):  # tests.rs:485-497
+    hits = docs_of(search_req(test_all, {"search": {"terms": ["najestätischer"], "path": "meanings.ger[]", "levenshtein_distance": 1}}), A)
+    assert len(hits) == 1 and hits[0]["ent_seq"] == "1587680"
+
+
+def test_prefer_exact_matches_to_tokenmatches(test_all):  # tests.rs:499-510
+    hits = docs_of(search_req(test_all, {"search": {"terms": ["will"], "path": "meanings.eng[]", "levenshtein_distance": 1}}), A)
+    assert hits[0]["meanings"]["eng"][0] == "will"
+
+
+def test_prefer_exact_match_over_multi_hit(native_libs):  # tests.rs:512-538
+    docs = [
+        {"definition": ["home"], "traditional": "家"},
+        {"definition": ["to live at home", "to stay at home", "home (schooling etc)", "le home", "ok home", "so much home"], "traditional": "居家"},
+    ]
+    o = _make(docs, {})
+    hits = docs_of(o.search({"search_req": {"search": {"terms": ["home"], "path": "definition[]", "levenshtein_distance": 0, "firstCharExactMatch": True}}}), docs)
+    assert [h["traditional"] for h in hits] == ["家", "居家"]
+
+
+def test_exact_match_with_boost(native_libs):  # tests.rs:540-572
+    docs = [
+        {"definition": ["home", "family"], "traditional": "家", "commonness": 5.5318},
+        {"definition": ["place to return to", "home", "final destination", "ending"], "traditional": "歸宿", "commonness": 3.1294},
+    ]
+    o = _make(docs, {"commonness": fx.BOOST})
+    req = {
+        "search_req": {"search": {"terms": ["home"], "path": "definition[]", "levenshtein_distance": 0, "firstCharExactMatch": True}},
+        "boost": [{"path": "commonness", "boost_fun": "Log10", "param": 1}],
+    }
+    assert [h["traditional"] for h in docs_of(o.search(req), docs)] == ["家", "歸宿"]
+
+
+def test_prefer_exact_tokenmatches_to_fuzzy_text_hits(test_all):  # tests.rs:574-587
+    hits = docs_of(search_req(test_all, {"search": {"terms": ["karl"], "path": "meanings.eng[]", "levenshtein_distance": 1}}), A)
+    assert hits[0]["meanings"]["eng"][0] == "karl der große"
+
+
+def test_search_word_non_tokenized(test_all):  # tests.rs:599-611
+    hits = docs_of(search_req(test_all, {"search": {"terms": ["偉容"], "path": "kanji[].text"}}), A)
+    assert len(hits) == 1 and hits[0]["ent_seq"] == "1587680"
+
+
+def test_disabled_tokenization(test_all):  # tests.rs:613-624
+    assert len(search_req(test_all, {"search": {"terms": ["tokens"], "path": "nofulltext"}})["data"]) == 0
+
+
+def test_search_on_non_subobject(test_all):  # tests.rs:626-637
+    assert len(search_req(test_all, {"search": {"terms": ["1587690"], "path": "ent_seq"}})["data"]) == 1
+
+
+def test_and_connect_hits_same_field(test_all):  # tests.rs:639-653
+    req = {"and": {"queries": [{"search": {"terms": ["aussehen"], "path": "meanings.ger[]"}}, {"search": {"terms": ["majestätisches"], "path": "meanings.ger[]"}}]}}
+    hits = docs_of(search_req(test_all, req), A)
+    assert len(hits) == 1 and hits[0]["ent_seq"] == "1587680"
+
+
+def test_and_connect_hits_different_fields(test_all):  # tests.rs:655-669
+    req = {"and": {"queries": [{"search": {"terms": ["majestät"], "path": "meanings.ger[]"}}, {"search": {"terms": ["majestic"], "path": "meanings.eng[]"}}]}}
+    hits = docs_of(search_req(test_all, req), A)
+    assert len(hits) == 1 and hits[0]["ent_seq"] == "1587680"
+
+
+def test_and_connect_hits_different_fields_no_hit(test_all):  # tests.rs:671-689
+    req = {"and": {"queries": [{"search": {"terms": ["majestät"], "path": "meanings.ger[]"}}, {"search": {"terms": ["urge"], "path": "meanings.eng[]"}}]}}
+    assert len(search_req(test_all, req)["data"]) == 0
+
+
+def test_and_connect_alle_meine_words(test_all):  # tests.rs:691-710
+    req = {"and": {"queries": [{"search": {"terms": ["words"], "path": "meanings.ger[]"}}, {"search": {"terms": ["1000"], "path": "ent_seq"}}]}}
+    hits = docs_of(search_req(test_all, req), A)
+    assert len(hits) == 1 and hits[0]["ent_seq"] == "1000"
+
+
+OR_MAJ_URGE = {"or": {"queries": [{"search": {"terms": ["majestät"], "path": "meanings.ger[]"}}, {"search": {"terms": ["urge"], "path": "meanings.eng[]"}}]}}
+
+
+def test_or_connect_hits_with_top(test_all):  # tests.rs:712-733
+    hits = docs_of(search_req(test_all, OR_MAJ_URGE, top=1), A)
+    assert len(hits) == 1 and hits[0]["ent_seq"] == "1587690"
+
+
+def test_or_connect_hits(test_all):  # tests.rs:735-753
+    res = search_req(test_all, OR_MAJ_URGE)
+    assert res["num_hits"] == 2 and docs_of(res, A)[0]["ent_seq"] == "1587690"
+
+
+def test_simple_search_with_filter(test_all):  # tests.rs:755-771
+    res = search_req(test_all, {"search": {"terms": ["urge"], "path": "meanings.eng[]"}}, filter={"search": {"terms": ["1587690"], "path": "ent_seq"}})
+    assert len(res["data"]) == 1
+
+
+def test_or_connect_hits_with_filter(test_all):  # tests.rs:773-800
+    res = search_req(test_all, OR_MAJ_URGE, filter={"search": {"terms": ["1587690"], "path": "ent_seq"}})
+    assert len(res["data"]) == 1
+
+
+def test_or_connect_hits_with_filter_reuse_query(test_all):  # tests.rs:802-824
+    res = search_req(test_all, OR_MAJ_URGE, filter={"search": {"terms": ["urge"], "path": "meanings.eng[]"}})
+    assert len(res["data"]) == 1
+
+
+def test_find_2_values_from_token(test_all):  # tests.rs:826-837
+    assert len(search_req(test_all, {"search": {"terms": ["意慾"], "path": "kanji[].text"}})["data"]) == 2
+
+
+def test_search_and_boosto(test_all):  # tests.rs:839-855
+    res = search_req(test_all, {"search": {"terms": ["意慾"], "path": "kanji[].text"}}, boost=[{"path": "kanji[].commonness", "boost_fun": "Log10", "param": 1}])
+    assert len(res["data"]) == 2
+
+
+def test_search_and_double_boost(test_all):  # tests.rs:857-878
+    res = search_req(
+        test_all,
+        {"search": {"terms": ["awesome"], "path": "field1[].text"}},
+        boost=[{"path": "commonness", "boost_fun": "Log10", "param": 1}, {"path": "field1[].rank", "expression": "10 / $SCORE", "skip_when_score": [0]}],
+    )
+    assert len(res["data"]) == 2
+
+
+def test_search_and_boost_anchor(test_all):  # tests.rs:880-898
+    req = {"search": {"terms": ["意慾"], "path": "kanji[].text", "levenshtein_distance": 0, "firstCharExactMatch": True}}
+    hits = docs_of(search_req(test_all, req, boost=[{"path": "commonness", "boost_fun": "Log10", "param": 1}]), A)
+    assert hits[0]["commonness"] == 500
+
+
+def test_or_connect_search_and_boost_anchor(test_all):  # tests.rs:900-931
+    req = {
+        "or": {
+            "queries": [
+                {"search": {"terms": ["awesome"], "path": "field1[].text", "options": {"boost": [{"path": "field1[].rank", "boost_fun": "Log10", "param": 1}]}}},
+                {"search": {"terms": ["urge"], "path": "meanings.eng[]", "options": {"boost": [{"path": "commonness", "boost_fun": "Log10", "param": 1}]}}},
+            ]
+        }
+    }
+    assert docs_of(search_req(test_all, req), A)[0]["commonness"] == 20
+
+
+def test_or_connect_same_search(test_all):  # tests.rs:933-957
+    req = {"or": {"queries": [{"search": {"terms": ["awesome"], "path": "field1[].text"}}, {"search": {"terms": ["awesome"], "path": "field1[].text"}}]}}
+    hits = docs_of(search_req(test_all, req), A)
+    assert hits[0]["commonness"] == 551 and len(hits) == 2
+
+
+def test_starts_with_terms(test_all):  # tests.rs:959-990
+    r = test_all.call("field_search", part={"terms": ["majes"], "path": "meanings.ger[]", "levenshtein_distance": 0, "starts_with": True})
+    assert sorted(r["terms"]) == ["Majestät", "Majestät (f)", "majestätischer", "majestätischer Anblick (m)", "majestätisches", "majestätisches Aussehen (n)"]
+
+
+def test_rank_boost_on_anchor_higher(test_all):  # tests.rs:1160-1208
+    for part in ({"terms": ["COllectif"], "path": "title"}, {"terms": ["boostemich"], "path": "meanings.ger[]"}):
+        boosted = search_req(test_all, {"search": part}, boost=[{"path": "commonness", "boost_fun": "Log2", "param": 2}])["data"]
+        plain = search_req(test_all, {"search": part})["data"]
+        assert boosted[0][1] > plain[0][1]
+
+
+def test_boost_terms(test_all):  # tests.rs:1232-1256
+    req = {
+        "search_req": {"search": {"terms": ["weich"], "path": "meanings.ger[]", "levenshtein_distance": 1, "firstCharExactMatch": True}},
+        "boost_term": [{"terms": ["9555"], "path": "ent_seq", "boost": 5.0}],
+    }
+    for _ in range(3):
+        assert docs_of(test_all.search(req), A)[0]["meanings"]["ger"][0] == "(1) 2 3 super nice weich"
+
+
+def test_or_connect_hits_but_boost_one_term(test_all):  # tests.rs:1276-1288
+    req = {"or": {"queries": [{"search": {"terms": ["majestät (f)"], "path": "meanings.ger[]", "boost": 2}}, {"search": {"terms": ["urge"], "path": "meanings.eng[]"}}]}}
+    hits = docs_of(search_req(test_all, req), A)
+    assert len(hits) == 2 and hits[0]["meanings"]["ger"][0] == "majestätischer Anblick (m)"
+
+
+def test_boost_text_localitaet(test_all):  # tests.rs:1296-1313
+    req = {"or": {"queries": [{"search": {"terms": ["text"], "path": "meanings.ger[]"}}, {"search": {"terms": ["localität"], "path": "meanings.ger[]"}}]}}
+    hits = docs_of(search_req(test_all, req, text_locality=True), A)
+    assert hits[0]["meanings"]["ger"][0] == "text localität"
+
+
+# ------------------------------------------------------------------ scores --
+S = fx.TEST_SCORE_DOCS
+
+
+def test_boost_simple(native_libs):  # test_scores.rs:68-104
+    docs = [{"commonness": 10, "name": "product"}, {"commonness": 99, "name": "product"}, {"commonness": 33, "name": "product"}]
+    o = _make(docs, {"name": {}, "commonness": fx.BOOST})
+    req = {
+        "search_req": {"search": {"terms": ["product"], "path": "name", "levenshtein_distance": 0, "firstCharExactMatch": True}},
+        "boost": [{"path": "commonness", "boost_fun": "Log10", "param": 1}],
+    }
+    assert [h["commonness"] for h in docs_of(o.search(req), docs)] == [99, 33, 10]
+
+
+def test_check_score_regarding_to_length(test_score):  # test_scores.rs:106-126
+    req = {
+        "search_req": {"or": {"queries": [{"search": {"terms": [t], "path": "title"}} for t in ("greg", "tagebuch", "05")]}},
+        "phrase_boosts": [{"path": "title", "search1": {"terms": ["greg"], "path": "title"}, "search2": {"terms": ["tagebuch"], "path": "title"}}],
+    }
+    titles = [d["title"] for d in docs_of(test_score.search(req), S)]
+    assert titles == ["greg tagebuch 05", "greg tagebuch", "and some some text 05 this is not relevant let tagebuch greg"]
+
+
+def test_add_and_multiply_boost_relations(test_score):  # test_scores.rs:185-237 (query-generator requests restated as plain requests)
+    base = {"search": {"terms": ["weich"], "path": "meanings.ger[]"}}
+    plain = search_req(test_score, base)["data"][0][1]
+    added = search_req(test_score, base, boost=[{"path": "commonness", "boost_fun": "Add"}])["data"][0][1]
+    mult = search_req(test_score, base, boost=[{"path": "commonness", "boost_fun": "Multiply"}])["data"][0][1]
+    assert plain + 2.0 == added
+    assert plain * 2.0 == mult
+
+
+def test_rank_exact_matches_pretty_good(test_score):  # test_scores.rs:239-259
+    req = {"search": {"terms": ["weich"], "path": "meanings.ger[]", "levenshtein_distance": 1, "explain": True, "firstCharExactMatch": True}}
+    hits = docs_of(search_req(test_score, req, boost=[{"path": "commonness", "boost_fun": "Log2", "param": 2}]), S)
+    assert hits[0]["meanings"]["ger"][0] == "weich"
+
+
+# ------------------------------------------------------------------ phrase --
+P = fx.TEST_PHRASE_DOCS
+
+
+def _pb(path):
+    return {"path": path, "search1": {"terms": ["die"], "path": path}, "search2": {"terms": ["erbin"], "path": path}}
+
+
+def test_should_boost_phrase(test_phrase):  # test_phrase.rs:39-52
+    req = {"search_req": {"search": {"terms": ["erbin"], "path": "title"}}, "phrase_boosts": [_pb("title")]}
+    assert docs_of(test_phrase.search(req), P)[0]["title"] == "die erbin"
+
+
+def test_should_boost_phrase_search_multifield(test_phrase):  # test_phrase.rs:54-79
+    req = {
+        "search_req": {"or": {"queries": [{"search": {"terms": [t], "path": p}} for p in ("title", "tags[]") for t in ("die", "erbin")]}},
+        "phrase_boosts": [_pb("title"), _pb("tags[]")],
+    }
+    assert docs_of(test_phrase.search(req), P)[0]["title"] == "die erbin"
+
+
+def test_should_and_boost_phrase_search(test_phrase):  # test_phrase.rs:81-99
+    req = {"search_req": {"and": {"queries": [{"search": {"terms": ["die"], "path": "title"}}, {"search": {"terms": ["erbin"], "path": "title"}}]}}, "phrase_boosts": [_pb("title")]}
+    assert docs_of(test_phrase.search(req), P)[0]["title"] == "die erbin"
+
+
+# ------------------------------------------------------------------ facets --
+def test_facet_with_facet_index(test_facet):  # tests_facet.rs:60-72
+    res = test_facet.search({"search_req": {"search": {"terms": ["will"], "path": "meanings.eng[]"}}, "facets": [{"field": "tags[]"}, {"field": "commonness"}]})
+    assert len(res["data"]) == 2
+    assert [f[:2] for f in res["facets"]["tags[]"]] == [["nice", 2], ["cool", 1]]
+    assert [f[:2] for f in res["facets"]["commonness"]] == [["20", 2]]
+
+
+def test_facet_without_facet_index(test_facet):  # tests_facet.rs:88-99
+    res = test_facet.search({"search_req": {"search": {"terms": ["test"], "path": "meanings.ger[]"}}, "facets": [{"field": "meanings.eng[]"}]})
+    assert len(res["data"]) == 1
+    assert [f[:2] for f in res["facets"]["meanings.eng[]"]] == [["test1", 1]]
+
+
+# ----------------------------------------------------------------- minimal --
+def test_minimal_identity_column(native_libs):  # tests_minimal.rs:21-105
+    docs = [{"field": "test", "field2": "test2"}]
+    o = _make(docs, {})
+    assert len(o.search({"search_req": {"search": {"terms": ["test"], "path": "field"}}})["data"]) == 1
+    res = o.search({"search_req": {"search": {"terms": ["test"], "path": "field"}}, "filter": {"search": {"terms": ["test"], "path": "field"}}})
+    assert len(res["data"]) == 1
+    res = o.search({"search_req": {"or": {"queries": [{"search": {"terms": ["test"], "path": "field"}}, {"search": {"terms": ["test2"], "path": "field"}}]}}})
+    assert len(res["data"]) == 1
+
+
+# ------------------------------------------------------------------- large --
+def test_large(native_libs):  # tests_large.rs:10-112
+    docs = [{"category": "superb", "tags": ["nice", "cool"]}] * 300 + [{"category": "awesome", "tags": ["is", "cool"]}] * 300
+    docs.append({"text": "a long text with more than 64 characters so that the option do_not_store_text_longer_than is active. then the whole text won't be store in the fst, only its tokens"})
+    o = _make(docs, {"*GLOBAL*": {"features": ["All"]}, "tags[]": {"facet": True}})
+    assert o.search({"search_req": {"search": {"terms": ["superb"], "path": "category"}}})["num_hits"] == 300
+    assert len(o.search({"search_req": {"search": {"terms": ["long"], "path": "text"}}})["data"]) == 1
+    res = o.search({"search_req": {"or": {"queries": [{"search": {"terms": ["superb"], "path": "category"}}, {"search": {"terms": ["awesome"], "path": "category"}}]}}})
+    assert res["num_hits"] == 600
+    res = o.search({"search_req": {"search": {"terms": ["superb"], "path": "category"}}, "facets": [{"field": "tags[]"}]})
+    assert sorted(f[:2] for f in res["facets"]["tags[]"]) == sorted([["nice", 300], ["cool", 300]])
