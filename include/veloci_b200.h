@@ -1,0 +1,155 @@
+/* veloci_b200 -- C ABI of the B200-native query-time hit pipeline for Veloci indices.
+ *
+ * This is the drop-in boundary: a Rust `-sys` crate binds exactly these symbols
+ * (see INTEGRATION.md).  Plain pointers and sizes only; no C++/torch types.
+ * Every entry point cites the reference interface it replaces (paths relative to
+ * the veloci repository).
+ *
+ * Conventions
+ *   - every function returns an int32 status (VGPU_OK == 0); the message of the last
+ *     failure on the calling thread is read with vgpu_last_error().  Status codes
+ *     mirror `VelociError` (src/error.rs:5-43).
+ *   - handles are opaque.  The caller owns inputs; the library owns outputs until
+ *     the matching *_free / *_close.
+ *   - an index handle is immutable after open (like `&Persistence`, Sync); batches
+ *     carry all mutable state, one batch per host thread at a time.
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry
+ *     point fails with VGPU_ERR_CUDA.
+ */
+#ifndef VELOCI_B200_H
+#define VELOCI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    VGPU_OK = 0,
+    VGPU_ERR_INVALID_REQUEST = 1, /* VelociError::InvalidRequest (src/search.rs:151-155) */
+    VGPU_ERR_FIELD_NOT_FOUND = 2, /* VelociError::FstNotFound: "field does not exist {path} (fst not found)" */
+    VGPU_ERR_PATH_NOT_FOUND = 3,  /* VelociError::StringError("Did not found path in indices ...") (src/persistence.rs:454-458) */
+    VGPU_ERR_IO = 4,              /* VelociError::Io / metaData.json problems */
+    VGPU_ERR_JSON = 5,            /* VelociError::JsonError (serde) */
+    VGPU_ERR_CUDA = 6,
+    VGPU_ERR_NCCL = 7,
+    VGPU_ERR_UNSUPPORTED = 8,     /* valid veloci request outside the accelerated path (regex, per-part top, ...) */
+    VGPU_ERR_INTERNAL = 9
+};
+
+typedef struct vgpu_index vgpu_index;
+typedef struct vgpu_batch vgpu_batch;
+
+/* Hit{id: u32, score: f32} (src/search.rs:53-57) */
+typedef struct vgpu_hit {
+    uint32_t id;
+    float score;
+} vgpu_hit;
+
+/* Message of the last failed call on this thread (never NULL). */
+const char* vgpu_last_error(void);
+
+/* Number of CUDA devices visible to the library (0 when none / no driver). */
+int32_t vgpu_device_count(void);
+
+/* ---- index ----------------------------------------------------------------
+ * Persistence::load(dir) (src/persistence.rs:393-409, 206-305): reads metaData.json,
+ * every index file it lists and every FST, then builds the device layout in the HBM
+ * of `device`.  With n_shards > 1 the handle owns the anchor range
+ * [rank*num_docs/n_shards, (rank+1)*num_docs/n_shards): postings, anchor-keyed
+ * stores and boost columns are cut to it; term-keyed structures are replicated. */
+int32_t vgpu_index_open(const char* dir, int32_t device, uint32_t shard_rank, uint32_t n_shards, vgpu_index** out);
+void vgpu_index_close(vgpu_index* idx);
+/* num_docs of metaData.json and the anchor range this handle owns. */
+int32_t vgpu_index_info(const vgpu_index* idx, uint64_t* num_docs, uint64_t* anchor_lo, uint64_t* anchor_hi, uint64_t* device_bytes);
+
+/* ---- whole-query seam (batched) -------------------------------------------
+ * search::search(request, &persistence) (src/search.rs:143-228) for `n` requests at
+ * once.  `request_json[i]` is the reference's `search::Request` JSON, verbatim.
+ *
+ *   prepare : parse + plan (plan_creator, src/plan_creator/execution_plan.rs:132) on
+ *             the host and upload the batch programs            (host -> device)
+ *   execute : run every plan step of every request as batched kernels; results stay
+ *             on the device; returns after the stream is idle
+ *   fetch_* : copy results to the host                           (device -> host)
+ * A request that fails (invalid, unknown field, unsupported) gets its status set and
+ * an empty result; the other requests of the batch are unaffected. */
+int32_t vgpu_batch_prepare(vgpu_index* idx, const char* const* request_json, uint32_t n, vgpu_batch** out);
+int32_t vgpu_batch_execute(vgpu_batch* batch);
+void vgpu_batch_free(vgpu_batch* batch);
+
+/* Per-request status (VGPU_OK or the error of that request) and message. */
+int32_t vgpu_batch_status(const vgpu_batch* batch, uint32_t q);
+const char* vgpu_batch_message(const vgpu_batch* batch, uint32_t q);
+
+/* SearchResult.num_hits and .data (src/search/result/search_result.rs:8-26) of request
+ * q after top/skip: hits sorted by (score desc, id desc) (src/search.rs:123-130).
+ * `hits` may be NULL to query the count only; at most `cap` hits are written. */
+int32_t vgpu_batch_result(const vgpu_batch* batch, uint32_t q, uint64_t* num_hits, vgpu_hit* hits, uint32_t cap, uint32_t* n_hits);
+
+/* All requests at once into row-major [n][k] arrays (rows padded with id 0xFFFFFFFF,
+ * score 0).  Any output pointer may be NULL. */
+int32_t vgpu_batch_results_flat(const vgpu_batch* batch, uint32_t k, uint32_t* ids, float* scores, uint64_t* num_hits, int32_t* status);
+
+/* facets of request q (src/facet.rs:31-73): number of facet fields, then per field
+ * the (value id, count) groups sorted by count desc (ties: value id asc) and the
+ * group's text (FST ord_to_term, src/search/search_field.rs:36-51). */
+int32_t vgpu_batch_facet_count(const vgpu_batch* batch, uint32_t q, uint32_t* n_fields);
+int32_t vgpu_batch_facet(const vgpu_batch* batch, uint32_t q, uint32_t field, const char** field_name, uint32_t* n_groups);
+int32_t vgpu_batch_facet_group(const vgpu_batch* batch, uint32_t q, uint32_t field, uint32_t group, uint32_t* value_id, uint32_t* count, const char** text);
+
+/* One-call form: prepare + execute + results_flat + free.  The e2e path of bench.py. */
+int32_t vgpu_search_batch(vgpu_index* idx, const char* const* request_json, uint32_t n, uint32_t k, uint32_t* ids, float* scores, uint64_t* num_hits, int32_t* status);
+
+/* ---- multi-GPU merge (anchor-range shards) ----------------------
+ * After execute, every shard holds the local top-(top+skip) of each request as
+ * device rows of `stride` 64-bit keys ((orderable score << 32) | anchor id, 0 = no
+ * hit) plus its local num_hits.  The host all-gathers those buffers (NCCL) and calls
+ * vgpu_batch_merge_gathered on every rank: final top-k of n_shards * stride
+ * candidates, num_hits summed.  Pointers are device pointers. */
+int32_t vgpu_batch_local_topk(const vgpu_batch* batch, uint64_t** keys_dev, uint64_t** num_hits_dev, uint32_t* stride);
+int32_t vgpu_batch_merge_gathered(vgpu_batch* batch, const uint64_t* gathered_keys_dev, const uint64_t* gathered_num_hits_dev, uint32_t n_shards);
+
+/* ---- step seam -------------------------------------------------------------
+ * One symbol per PlanStep kind (src/plan_creator/plan_steps.rs:18-74), each over host
+ * hit lists; used by the step-level parity tests.  Outputs are malloc'd by the
+ * library and released with vgpu_free. */
+typedef struct vgpu_hitlist {
+    vgpu_hit* hits;   /* hits_scores */
+    uint32_t n_hits;
+    uint32_t* ids;    /* hits_ids */
+    uint32_t n_ids;
+} vgpu_hitlist;
+void vgpu_free(void* p);
+void vgpu_hitlist_free(vgpu_hitlist* l);
+
+/* get_term_ids_in_field (src/search/search_field.rs:277-398): `part_json` is one
+ * RequestSearchPart; fills hits_scores (term id, score) and/or hits_ids. */
+int32_t vgpu_field_search(vgpu_index* idx, const char* part_json, int32_t get_scores, int32_t get_ids, vgpu_hitlist* out);
+/* resolve_token_to_anchor (src/search/search_field.rs:400-504) for the term hits of `in`. */
+int32_t vgpu_resolve_to_anchor(vgpu_index* idx, const char* part_json, const vgpu_hitlist* in, vgpu_hitlist* out);
+/* union_hits_score (src/search/set_op.rs:87-220); terms[i] = request.terms[0] of input i. */
+int32_t vgpu_union_hits_score(vgpu_index* idx, const vgpu_hitlist* inputs, const char* const* terms, uint32_t n, vgpu_hitlist* out);
+/* intersect_hits_score (src/search/set_op.rs:368-446). */
+int32_t vgpu_intersect_hits_score(vgpu_index* idx, const vgpu_hitlist* inputs, uint32_t n, vgpu_hitlist* out);
+/* add_boost (src/search/boost.rs:470-504): `boost_json` is one RequestBoostPart. */
+int32_t vgpu_add_boost(vgpu_index* idx, const char* boost_json, vgpu_hitlist* inout);
+/* top_n_sort + apply_top_skip (src/search/sort.rs:5-22, src/search.rs:230-239). */
+int32_t vgpu_top_n(vgpu_index* idx, const vgpu_hitlist* in, uint32_t top, uint32_t skip, vgpu_hitlist* out);
+
+/* ---- instrumentation ---------------------------------------------------------
+ * Kernel launches issued by this library since process start, and per-phase device
+ * time (CUDA events on the library's stream) of the last vgpu_batch_execute:
+ * phase 0 fuzzy match, 1 match grouping + scoring, 2 posting slicing, 3 tile
+ * evaluation (expand + merge + boost + tile top-k), 4 final top-k.  Also the
+ * algorithmic byte counts of the last execute. */
+uint64_t vgpu_launch_count(void);
+int32_t vgpu_batch_phase_ms(const vgpu_batch* batch, float* ms, uint32_t n_phases);
+int32_t vgpu_batch_traffic_model(const vgpu_batch* batch, uint64_t* posting_bytes, uint64_t* boost_bytes, uint64_t* postings, uint64_t* union_hits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VELOCI_B200_H */

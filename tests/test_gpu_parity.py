@@ -1,0 +1,221 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same
+index directories and the same request JSON.
+
+Bar (BASELINE.json north_star): term matches, hit-id sets and counts bit-exact;
+f32 scores within 1e-5 relative; top-k order identical except among ties within
+that tolerance.
+"""
+import json
+import tempfile
+
+import numpy as np
+import pytest
+
+import helpers
+import ref_fixtures as fx
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+def close(a, b):
+    a, b = float(a), float(b)
+    return abs(a - b) <= REL * max(abs(a), abs(b), 1e-30)
+
+
+def assert_same_topk(gpu, cpu, ctx=""):
+    """gpu/cpu: lists of (id, score) in rank order."""
+    assert len(gpu) == len(cpu), f"{ctx}: {len(gpu)} hits vs {len(cpu)}"
+    cpu_scores = {i: s for i, s in cpu}
+    for pos, ((gi, gs), (ci, cs)) in enumerate(zip(gpu, cpu)):
+        assert close(gs, cs), f"{ctx}: score at rank {pos}: gpu {gs!r} cpu {cs!r}"
+        if gi != ci:
+            # only a tie (within tolerance) may reorder or swap the boundary element
+            if gi in cpu_scores:
+                assert close(cpu_scores[gi], cs), f"{ctx}: id {gi} at rank {pos} is not a tie with {ci}"
+            else:
+                assert close(gs, cpu[-1][1]), f"{ctx}: id {gi} at rank {pos} missing from the oracle's top-k and not a boundary tie"
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import veloci_b200
+
+    assert veloci_b200.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return veloci_b200
+
+
+def _pair(gpu, docs=None, config=None, synth=None):
+    d = tempfile.mkdtemp(prefix="vb200_gpu_")
+    if synth is not None:
+        helpers.create_synthetic_index(d, **synth)
+    else:
+        helpers.create_index(d, docs, config)
+    return gpu.Index(d), helpers.Oracle(d), d
+
+
+def compare_batch(index, oracle, requests, k=10, expect_ok=True):
+    out = index.search_batch(requests, k=k)
+    ref = oracle.search_batch(requests, threads=4, k=k)
+    for q, r in enumerate(requests):
+        if expect_ok:
+            assert out["status"][q] == 0, f"request {q} failed on the GPU path: {r}"
+        if out["status"][q] != 0:
+            continue
+        assert ref["status"][q] == 0, f"oracle failed on request {q}"
+        assert int(out["num_hits"][q]) == int(ref["num_hits"][q]), f"num_hits of request {q}: gpu {out['num_hits'][q]} cpu {ref['num_hits'][q]}: {r}"
+        g = [(int(i), s) for i, s in zip(out["ids"][q], out["scores"][q]) if i != 0xFFFFFFFF]
+        c = [(int(i), s) for i, s in zip(ref["ids"][q], ref["scores"][q]) if i != 0xFFFFFFFF]
+        assert_same_topk(g, c, ctx=f"request {q} {r}")
+    return out, ref
+
+
+SMALL = dict(num_docs=60000, vocab=5000, seed=7)
+
+
+@pytest.fixture(scope="module")
+def small(gpu, native_libs):
+    return _pair(gpu, synth=SMALL)
+
+
+def test_or3_fuzzy_boost(small):  # BASELINE config 2 shape
+    index, oracle, _ = small
+    reqs = helpers.synthetic_requests(num_queries=400, query_kind="or3", levenshtein=1, **SMALL)
+    out, _ = compare_batch(index, oracle, reqs)
+    assert out["num_hits"].sum() > 0
+
+
+def test_single_term_lev2(small):  # BASELINE config 4 shape
+    index, oracle, _ = small
+    reqs = helpers.synthetic_requests(num_queries=300, query_kind="single", levenshtein=2, query_seed=5, **SMALL)
+    compare_batch(index, oracle, reqs)
+
+
+def test_and_queries(small):  # BASELINE config 3 core (intersection)
+    index, oracle, _ = small
+    reqs = helpers.synthetic_requests(num_queries=300, query_kind="and", levenshtein=1, query_seed=9, **SMALL)
+    compare_batch(index, oracle, reqs)
+
+
+def test_exact_no_boost_top_skip(small):
+    index, oracle, _ = small
+    base = [json.loads(r) for r in helpers.synthetic_requests(num_queries=60, query_kind="or3", levenshtein=0, query_seed=11, **SMALL)]
+    reqs = []
+    for i, r in enumerate(base):
+        r.pop("boost", None)
+        r["top"] = [1, 3, 10, 25][i % 4]
+        if i % 3 == 0:
+            r["skip"] = [0, 2, 7][(i // 3) % 3]
+        reqs.append(json.dumps(r))
+    index_out = index.prepare(reqs).execute()
+    for q, r in enumerate(reqs):
+        g = index_out.result(q)
+        c = oracle.search(r)
+        assert g["num_hits"] == c["num_hits"]
+        assert_same_topk(g["data"], [(h[0], np.float32(h[1])) for h in c["data"]], ctx=r)
+
+
+def test_field_search_matches_term_sets(small):  # get_term_ids_in_field, exact term-id sets and scores
+    index, oracle, _ = small
+    words = [json.loads(r)["search_req"]["search"]["terms"][0] for r in helpers.synthetic_requests(num_queries=120, query_kind="single", query_seed=3, **SMALL)]
+    for i, w in enumerate(words):
+        part = {"terms": [w], "path": "body", "levenshtein_distance": i % 3}
+        if i % 7 == 0:
+            part["starts_with"] = True
+            part["terms"] = [w[:3]]
+        if i % 5 == 0:
+            part["ignore_case"] = i % 10 == 0
+        if i % 11 == 0:
+            part["boost"] = 2.5
+        hits, _ = index.field_search(part)
+        ref = oracle.call("field_search", part=part)["hits_scores"]
+        assert [h[0] for h in hits] == [h[0] for h in ref], part
+        for (_, gs), (_, cs) in zip(hits, ref):
+            assert close(gs, cs), (part, gs, cs)
+
+
+def test_errors_per_request(small):
+    index, _, _ = small
+    reqs = [
+        json.dumps({"search_req": {"search": {"terms": ["abc"], "path": "nope"}}}),
+        json.dumps({"top": 3}),
+        "{not json",
+        json.dumps({"search_req": {"search": {"terms": ["abc"], "path": "body"}}, "boost": [{"path": "missing", "boost_fun": "Log10"}]}),
+        json.dumps({"search_req": {"search": {"terms": ["abc"], "path": "body"}}}),
+    ]
+    b = index.prepare(reqs).execute()
+    assert [b.status(i) for i in range(5)] == [2, 1, 5, 3, 0]
+    assert "field does not exist nope.textindex (fst not found)" in b.message(0)  # tests/all/tests.rs:435
+
+
+# ---- the reference's own integration fixtures ----------------------------------
+
+def _requests_test_all():
+    S = lambda terms, path, **kw: {"search": {"terms": [terms], "path": path, **kw}}
+    return [
+        {"search_req": S("urge", "meanings.eng[]")},
+        {"search_req": S("majestätischer", "meanings.ger[]", levenshtein_distance=1)},
+        {"search_req": S("Majestätischer", "meanings.ger[]", ignore_case=False)},
+        {"search_req": {"or": {"queries": [S("majestät", "meanings.ger[]"), S("urge", "meanings.eng[]")]}}},
+        {"search_req": {"or": {"queries": [S("majestät", "meanings.ger[]"), S("urge", "meanings.eng[]")]}}, "top": 1},
+        {"search_req": {"and": {"queries": [S("alle", "meanings.ger[]"), S("meine", "meanings.ger[]"), S("words", "meanings.ger[]")]}}},
+        {"search_req": {"and": {"queries": [S("majestät", "meanings.ger[]"), S("majestätischer", "meanings.ger[]")]}}},
+        {"search_req": {"and": {"queries": [S("majestät", "meanings.ger[]"), S("urge", "meanings.eng[]")]}}},
+        {"search_req": S("awesome", "field1[].text"), "boost": [{"path": "commonness", "boost_fun": "Log10", "param": 1}]},
+        {"search_req": S("意慾", "kanji[].text"), "boost": [{"path": "commonness", "boost_fun": "Log10", "param": 1}]},
+        {"search_req": {"or": {"queries": [S("awesome", "field1[].text"), S("awesome", "field1[].text")]}}},
+        {"search_req": S("COllectif", "title"), "boost": [{"path": "commonness", "boost_fun": "Log2", "param": 2}]},
+        {"search_req": S("boostemich", "meanings.ger[]"), "boost": [{"path": "commonness", "boost_fun": "Log2", "param": 2}]},
+        {"search_req": S("weich", "meanings.ger[]", levenshtein_distance=1)},
+        {"search_req": S("ein", "meanings.ger[]", starts_with=True)},
+        {"search_req": {"or": {"queries": [{"and": {"queries": [S("alle", "meanings.ger[]"), S("meine", "meanings.ger[]")]}}, S("urge", "meanings.eng[]")]}}},
+        {"search_req": S("will", "meanings.eng[]", boost=3.0)},
+    ]
+
+
+def test_reference_fixture_corpus(gpu, native_libs):  # tests/all/tests.rs corpus
+    index, oracle, _ = _pair(gpu, fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG)
+    reqs = [json.dumps(r, ensure_ascii=False) for r in _requests_test_all()]
+    b = index.prepare(reqs).execute()
+    for q, r in enumerate(reqs):
+        assert b.status(q) == 0, (r, b.message(q))
+        g = b.result(q)
+        c = oracle.search(r)
+        assert g["num_hits"] == c["num_hits"], r
+        assert_same_topk(g["data"], [(h[0], np.float32(h[1])) for h in c["data"]], ctx=r)
+
+
+def test_set_op_step_seam(small):  # set_op.rs:532-551 vector + random lists
+    index, oracle, _ = small
+    got = index.intersect_hits_score([[(0, 20.0), (10, 20.0)], [(0, 20.0), (3, 20.0), (10, 30.0), (20, 30.0)]])
+    assert got == [(0, np.float32(40.0)), (10, np.float32(50.0))]
+    rng = np.random.default_rng(3)
+    lists, terms = [], ["b", "a", "b", "c"]
+    for _ in range(4):
+        ids = np.unique(rng.integers(0, SMALL["num_docs"], 500))
+        lists.append([(int(i), float(np.float32(rng.random() * 10))) for i in ids])
+    inputs = [{"hits_scores": [[i, s] for i, s in l], "term": t} for l, t in zip(lists, terms)]
+    ref = oracle.call("union_hits_score", inputs=inputs)
+    got = index.union_hits_score(lists, terms)
+    assert [g[0] for g in got] == [r[0] for r in ref]
+    assert all(close(g[1], r[1]) for g, r in zip(got, ref))
+    ref = oracle.call("intersect_hits_score", inputs=inputs[:3])
+    got = index.intersect_hits_score(lists[:3])
+    assert [g[0] for g in got] == [r[0] for r in ref]
+    assert all(close(g[1], r[1]) for g, r in zip(got, ref))
+
+
+def test_resolve_and_boost_and_topn_step_seam(small):
+    index, oracle, _ = small
+    part = {"terms": ["abcd"], "path": "body", "levenshtein_distance": 2}
+    hits, _ = index.field_search(part)
+    ref = oracle.call("resolve_token_to_anchor", part=part)["hits_scores"]
+    got, _ = index.resolve_to_anchor(part, hits)
+    assert [g[0] for g in got] == [r[0] for r in ref]
+    assert all(close(g[1], r[1]) for g, r in zip(got, ref))
+    boosted = index.add_boost({"path": "commonness", "boost_fun": "Log10", "param": 1}, got)
+    assert len(boosted) == len(got) and any(b[1] != g[1] for b, g in zip(boosted, got)) or not got
+    top = index.top_n(got, 7, 2)
+    ref_top = oracle.call("top_n_sort", hits=[[i, float(s)] for i, s in got], top=9)[2:9]
+    assert_same_topk(top, [(r[0], np.float32(r[1])) for r in ref_top])

@@ -1,0 +1,290 @@
+"""ctypes binding of include/veloci_b200.h (the calls a Rust `-sys` crate would make)."""
+import ctypes
+import json
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+STATUS_NAMES = {
+    0: "ok", 1: "InvalidRequest", 2: "FieldNotFound", 3: "PathNotFound", 4: "Io", 5: "Json",
+    6: "Cuda", 7: "Nccl", 8: "Unsupported", 9: "Internal",
+}
+
+
+class VelociGpuError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"[{STATUS_NAMES.get(status, status)}] {message}")
+        self.status = status
+        self.message = message
+
+
+class _Hit(ctypes.Structure):
+    _fields_ = [("id", ctypes.c_uint32), ("score", ctypes.c_float)]
+
+
+class _HitList(ctypes.Structure):
+    _fields_ = [("hits", ctypes.POINTER(_Hit)), ("n_hits", ctypes.c_uint32), ("ids", ctypes.POINTER(ctypes.c_uint32)), ("n_ids", ctypes.c_uint32)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libveloci_b200.so")
+
+
+def load_library():
+    """Loads the CUDA library; raises if it has not been built (there is no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise VelociGpuError(6, f"{path} is missing: build it with `python -m veloci_b200.build` (nvcc, sm_100a)")
+    L = ctypes.CDLL(path)
+    vp, u32, u64, i32, cp = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int32, ctypes.c_char_p
+    P = ctypes.POINTER
+    L.vgpu_last_error.restype = cp
+    L.vgpu_device_count.restype = i32
+    L.vgpu_index_open.argtypes = [cp, i32, u32, u32, P(vp)]
+    L.vgpu_index_close.argtypes = [vp]
+    L.vgpu_index_close.restype = None
+    L.vgpu_index_info.argtypes = [vp, P(u64), P(u64), P(u64), P(u64)]
+    L.vgpu_batch_prepare.argtypes = [vp, P(cp), u32, P(vp)]
+    L.vgpu_batch_execute.argtypes = [vp]
+    L.vgpu_batch_free.argtypes = [vp]
+    L.vgpu_batch_free.restype = None
+    L.vgpu_batch_status.argtypes = [vp, u32]
+    L.vgpu_batch_message.argtypes = [vp, u32]
+    L.vgpu_batch_message.restype = cp
+    L.vgpu_batch_result.argtypes = [vp, u32, P(u64), P(_Hit), u32, P(u32)]
+    L.vgpu_batch_results_flat.argtypes = [vp, u32, vp, vp, vp, vp]
+    L.vgpu_search_batch.argtypes = [vp, P(cp), u32, u32, vp, vp, vp, vp]
+    L.vgpu_batch_facet_count.argtypes = [vp, u32, P(u32)]
+    L.vgpu_batch_facet.argtypes = [vp, u32, u32, P(cp), P(u32)]
+    L.vgpu_batch_facet_group.argtypes = [vp, u32, u32, u32, P(u32), P(u32), P(cp)]
+    L.vgpu_batch_local_topk.argtypes = [vp, P(vp), P(vp), P(u32)]
+    L.vgpu_batch_merge_gathered.argtypes = [vp, vp, vp, u32]
+    L.vgpu_free.argtypes = [vp]
+    L.vgpu_free.restype = None
+    L.vgpu_hitlist_free.argtypes = [P(_HitList)]
+    L.vgpu_hitlist_free.restype = None
+    L.vgpu_field_search.argtypes = [vp, cp, i32, i32, P(_HitList)]
+    L.vgpu_resolve_to_anchor.argtypes = [vp, cp, P(_HitList), P(_HitList)]
+    L.vgpu_union_hits_score.argtypes = [vp, P(_HitList), P(cp), u32, P(_HitList)]
+    L.vgpu_intersect_hits_score.argtypes = [vp, P(_HitList), u32, P(_HitList)]
+    L.vgpu_add_boost.argtypes = [vp, cp, P(_HitList)]
+    L.vgpu_top_n.argtypes = [vp, P(_HitList), u32, u32, P(_HitList)]
+    L.vgpu_launch_count.restype = u64
+    L.vgpu_batch_phase_ms.argtypes = [vp, P(ctypes.c_float), u32]
+    L.vgpu_batch_traffic_model.argtypes = [vp, P(u64), P(u64), P(u64), P(u64)]
+    _LIB = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise VelociGpuError(rc, load_library().vgpu_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    return int(load_library().vgpu_device_count())
+
+
+def launch_count():
+    return int(load_library().vgpu_launch_count())
+
+
+def _encode_requests(requests):
+    enc = [r.encode("utf-8") if isinstance(r, str) else (r if isinstance(r, bytes) else json.dumps(r, ensure_ascii=False).encode("utf-8")) for r in requests]
+    return (ctypes.c_char_p * len(enc))(*enc), enc
+
+
+def _to_hitlist(hits=None, ids=None):
+    hits = list(hits or [])
+    ids = list(ids or [])
+    hl = _HitList()
+    harr = (_Hit * max(1, len(hits)))()
+    for i, (a, s) in enumerate(hits):
+        harr[i].id, harr[i].score = int(a), float(s)
+    iarr = (ctypes.c_uint32 * max(1, len(ids)))(*ids)
+    hl.hits, hl.n_hits = ctypes.cast(harr, ctypes.POINTER(_Hit)), len(hits)
+    hl.ids, hl.n_ids = ctypes.cast(iarr, ctypes.POINTER(ctypes.c_uint32)), len(ids)
+    hl._keep = (harr, iarr)
+    return hl
+
+
+def _from_hitlist(L, hl):
+    hits = [(hl.hits[i].id, np.float32(hl.hits[i].score)) for i in range(hl.n_hits)]
+    ids = [hl.ids[i] for i in range(hl.n_ids)]
+    L.vgpu_hitlist_free(ctypes.byref(hl))
+    return hits, ids
+
+
+class Batch:
+    """A prepared batch of requests (vgpu_batch_prepare / execute / fetch)."""
+
+    def __init__(self, index, requests):
+        self.L = load_library()
+        self.index = index
+        self.n = len(requests)
+        arr, self._keep = _encode_requests(requests)
+        self.h = ctypes.c_void_p()
+        _check(self.L.vgpu_batch_prepare(index.h, arr, self.n, ctypes.byref(self.h)))
+
+    def execute(self):
+        _check(self.L.vgpu_batch_execute(self.h))
+        return self
+
+    def status(self, q):
+        return int(self.L.vgpu_batch_status(self.h, q))
+
+    def message(self, q):
+        return self.L.vgpu_batch_message(self.h, q).decode("utf-8", "replace")
+
+    def result(self, q, cap=256):
+        """-> {"num_hits", "data": [(id, score)], "facets": {...}} of request q (raises for a failed request)."""
+        st = self.status(q)
+        if st != 0:
+            raise VelociGpuError(st, self.message(q))
+        nh, n = ctypes.c_uint64(), ctypes.c_uint32()
+        hits = (_Hit * cap)()
+        _check(self.L.vgpu_batch_result(self.h, q, ctypes.byref(nh), hits, cap, ctypes.byref(n)))
+        out = {"num_hits": int(nh.value), "data": [(hits[i].id, np.float32(hits[i].score)) for i in range(n.value)]}
+        nf = ctypes.c_uint32()
+        _check(self.L.vgpu_batch_facet_count(self.h, q, ctypes.byref(nf)))
+        if nf.value:
+            facets = {}
+            for f in range(nf.value):
+                name, ng = ctypes.c_char_p(), ctypes.c_uint32()
+                _check(self.L.vgpu_batch_facet(self.h, q, f, ctypes.byref(name), ctypes.byref(ng)))
+                groups = []
+                for g in range(ng.value):
+                    vid, cnt, text = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_char_p()
+                    _check(self.L.vgpu_batch_facet_group(self.h, q, f, g, ctypes.byref(vid), ctypes.byref(cnt), ctypes.byref(text)))
+                    groups.append((text.value.decode("utf-8", "replace"), int(cnt.value), int(vid.value)))
+                facets[name.value.decode("utf-8")] = groups
+            out["facets"] = facets
+        return out
+
+    def results_flat(self, k=10):
+        ids = np.zeros((self.n, k), dtype=np.uint32)
+        scores = np.zeros((self.n, k), dtype=np.float32)
+        num_hits = np.zeros(self.n, dtype=np.uint64)
+        status = np.zeros(self.n, dtype=np.int32)
+        _check(self.L.vgpu_batch_results_flat(self.h, k, ids.ctypes.data, scores.ctypes.data, num_hits.ctypes.data, status.ctypes.data))
+        return {"ids": ids, "scores": scores, "num_hits": num_hits, "status": status}
+
+    def local_topk(self):
+        """Device pointers of the shard-local result rows: (keys_ptr, num_hits_ptr, stride)."""
+        keys, hits, stride = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint32()
+        _check(self.L.vgpu_batch_local_topk(self.h, ctypes.byref(keys), ctypes.byref(hits), ctypes.byref(stride)))
+        return keys.value, hits.value, int(stride.value)
+
+    def merge_gathered(self, keys_ptr, hits_ptr, n_shards):
+        _check(self.L.vgpu_batch_merge_gathered(self.h, ctypes.c_void_p(keys_ptr), ctypes.c_void_p(hits_ptr), n_shards))
+
+    def phase_ms(self):
+        ms = (ctypes.c_float * 5)()
+        _check(self.L.vgpu_batch_phase_ms(self.h, ms, 5))
+        return [float(x) for x in ms]
+
+    def traffic_model(self):
+        a, b, c, d = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        _check(self.L.vgpu_batch_traffic_model(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
+        return {"posting_bytes": a.value, "boost_bytes": b.value, "postings": c.value, "union_hits": d.value}
+
+    def close(self):
+        if self.h:
+            self.L.vgpu_batch_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Index:
+    """An index directory loaded into the HBM of one GPU (one anchor-range shard of it)."""
+
+    def __init__(self, directory, device=0, shard_rank=0, n_shards=1):
+        self.L = load_library()
+        self.h = ctypes.c_void_p()
+        _check(self.L.vgpu_index_open(os.fsencode(directory), device, shard_rank, n_shards, ctypes.byref(self.h)))
+
+    def info(self):
+        a, b, c, d = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        _check(self.L.vgpu_index_info(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
+        return {"num_docs": a.value, "anchor_lo": b.value, "anchor_hi": c.value, "device_bytes": d.value}
+
+    def prepare(self, requests):
+        return Batch(self, requests)
+
+    def search(self, request):
+        b = Batch(self, [request]).execute()
+        try:
+            return b.result(0)
+        finally:
+            b.close()
+
+    def search_batch(self, requests, k=10):
+        """One vgpu_search_batch call: host JSON in, host arrays out."""
+        n = len(requests)
+        arr, keep = _encode_requests(requests)
+        ids = np.zeros((n, k), dtype=np.uint32)
+        scores = np.zeros((n, k), dtype=np.float32)
+        num_hits = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        _check(self.L.vgpu_search_batch(self.h, arr, n, k, ids.ctypes.data, scores.ctypes.data, num_hits.ctypes.data, status.ctypes.data))
+        return {"ids": ids, "scores": scores, "num_hits": num_hits, "status": status}
+
+    # ---- step seam
+    def field_search(self, part, get_scores=True, get_ids=False):
+        out = _HitList()
+        _check(self.L.vgpu_field_search(self.h, json.dumps(part, ensure_ascii=False).encode("utf-8"), int(get_scores), int(get_ids), ctypes.byref(out)))
+        return _from_hitlist(self.L, out)
+
+    def resolve_to_anchor(self, part, hits, ids=None):
+        inp, out = _to_hitlist(hits, ids), _HitList()
+        _check(self.L.vgpu_resolve_to_anchor(self.h, json.dumps(part, ensure_ascii=False).encode("utf-8"), ctypes.byref(inp), ctypes.byref(out)))
+        return _from_hitlist(self.L, out)
+
+    def union_hits_score(self, lists, terms):
+        n = len(lists)
+        keep = [_to_hitlist(l) for l in lists]
+        arr = (_HitList * max(1, n))(*keep)
+        tarr = (ctypes.c_char_p * max(1, n))(*[t.encode("utf-8") for t in terms])
+        out = _HitList()
+        _check(self.L.vgpu_union_hits_score(self.h, arr, tarr, n, ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[0]
+
+    def intersect_hits_score(self, lists):
+        n = len(lists)
+        keep = [_to_hitlist(l) for l in lists]
+        arr = (_HitList * max(1, n))(*keep)
+        out = _HitList()
+        _check(self.L.vgpu_intersect_hits_score(self.h, arr, n, ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[0]
+
+    def add_boost(self, boost, hits):
+        inp = _to_hitlist(hits)
+        _check(self.L.vgpu_add_boost(self.h, json.dumps(boost).encode("utf-8"), ctypes.byref(inp)))
+        return [(inp.hits[i].id, np.float32(inp.hits[i].score)) for i in range(inp.n_hits)]
+
+    def top_n(self, hits, top, skip=0):
+        inp, out = _to_hitlist(hits), _HitList()
+        _check(self.L.vgpu_top_n(self.h, ctypes.byref(inp), top, skip, ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[0]
+
+    def close(self):
+        if self.h:
+            self.L.vgpu_index_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC,-pthread,-Wall,-march=x86-64-v3",
-    "--expt-relaxed-constexpr",
+    "--expt-relaxed-constexpr", "-fmad=false",
 ]
 
 

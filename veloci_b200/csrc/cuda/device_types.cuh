@@ -1,0 +1,108 @@
+// Plain structs shared by the host runtime and the kernels (device pointers inside).
+#pragma once
+#include <cstdint>
+
+namespace vdev {
+
+static const uint32_t kDictTile = 32;       // terms per dictionary tile: one warp, one term per lane
+static const uint32_t kTilePrefixMax = 8;   // symbols of the tile's common prefix that are kept
+static const uint32_t kNoValue = 0xFFFFFFFFu;
+static const uint32_t kMaxLeaves = 12;      // search parts per request tree on the tile path
+static const uint32_t kMaxK = 256;          // top + skip on the tile path
+
+struct TilePrefix {  // 20 bytes
+    uint16_t sym[kTilePrefixMax];
+    uint16_t len;
+    uint16_t pad;
+};
+
+struct DictView {
+    uint32_t n, n_tiles;
+    const uint32_t* ids;
+    const uint16_t* lower_bytes;
+    const uint16_t* sym[2];  // [0] lower-cased, [1] raw
+    const uint32_t* off[2];
+    const TilePrefix* tiles[2];
+};
+
+struct PostingsView {
+    const uint32_t* anchors;
+    const uint16_t* scores;
+    const uint64_t* off;
+    uint32_t n_terms;
+};
+
+struct CsrView {
+    const uint32_t* off;
+    const uint32_t* val;
+    uint32_t n_ids;
+};
+
+// ---- fuzzy match (get_term_ids_in_field, search_field.rs:277-398) ----
+enum PartFlags : uint32_t {
+    kPartPrefix = 1u,         // starts_with
+    kPartTransposition = 2u,  // matching automaton built with transposition_cost_one (search_field.rs:87)
+    kPartRawCase = 4u,        // ignore_case == false: match on raw scalars
+    kPartCheckPrefix = 8u,    // starts_with || levenshtein != 0  (:302)
+    kPartHasBoost = 16u,
+};
+
+struct PartQuery {  // one distinct RequestSearchPart of the batch (272 B)
+    uint16_t match_sym[64];  // query scalars as alphabet codes, in the matching case variant
+    uint16_t score_sym[64];  // lower-cased query (scoring always runs on lower-cased text, :298-317)
+    uint32_t m;              // scalars in the query
+    uint32_t d_match;        // min(d, 4)  (:87)
+    uint32_t d_score;        // d clamped to chars-1 (:286)
+    uint32_t flags;
+    float boost;             // per-part scalar boost (:359-364)
+    uint32_t lower_bytes;    // byte length of the lower-cased query (distance() 255 rule, :706)
+    uint32_t postings;       // index into the batch's PostingsView table, kNoValue if absent
+    uint32_t pad;
+};
+
+struct MatchRecord {  // fuzzy_match output, unordered
+    uint32_t part;
+    uint32_t slot;  // dictionary slot
+};
+
+// ---- per-part posting slices ----
+struct PartSlices {
+    uint32_t m_begin;     // first grouped match of the part
+    uint32_t n_match;     // matches (= matched dictionary terms)
+    uint32_t n_dense;     // the first n_dense grouped matches have a tile-offset row
+    uint32_t sparse_row;  // row of the part in the sparse bucket table
+    uint64_t sparse_base; // first sparse entry of the part
+};
+
+// ---- request programs (plan_creator, execution_plan.rs:132-534) ----
+enum ProgOp : uint32_t {
+    kOpLeaf = 1,       // [op, leaf index]
+    kOpUnion = 2,      // [op, n children, n slots, slot of child 0 .. n-1]      set_op.rs:87-220
+    kOpIntersect = 3,  // [op, n children, sum order: child index 0 .. n-1]      set_op.rs:368-446
+};
+
+enum BoostFunDev : uint32_t { kBoostNone = 0, kBoostLog2 = 1, kBoostLog10 = 2, kBoostMultiply = 3, kBoostAdd = 4, kBoostReplace = 5 };
+enum ExprOp : uint32_t { kExprNone = 0, kExprDiv = 1, kExprMul = 2, kExprAdd = 3, kExprSub = 4 };
+
+struct BoostStep {  // add_boost on anchor ids (boost.rs:470-504, apply_boost :283-377)
+    const uint32_t* column;
+    uint32_t n;
+    uint32_t fun;
+    float param;
+    uint32_t n_skip;
+    float skip[4];
+    uint32_t expr_op;       // `x op y` expression, operands: $SCORE (= boost value) or a float
+    uint32_t expr_left_is_score, expr_right_is_score;
+    float expr_left, expr_right;
+};
+
+struct QueryProgram {
+    uint32_t leaf_begin, n_leaves;  // into the leaf -> part table
+    uint32_t prog_begin, prog_len;  // into the program words
+    uint32_t boost_begin, n_boosts; // into the BoostStep table
+    uint32_t k;                     // top + skip (0: only count)
+    uint32_t active;                // 0 = request failed on the host, skip
+    uint32_t emit_all;              // step seam: also write every hit to the emit buffer
+};
+
+}  // namespace vdev

@@ -1,0 +1,448 @@
+// K1 fuzzy_match + match grouping/scoring + posting slicing.
+//
+//   fuzzy_match_kernel      get_term_ids_in_field (src/search/search_field.rs:277-398): which
+//                           dictionary terms the Levenshtein automaton of each search part accepts.
+//   group_* / score_scatter the (term id, score) hit list per part; score =
+//                           get_default_score_for_distance(distance_dfa(..)) (:27-33, :691-732) * boost.
+//   dense_tile_offsets /    prepare resolve_token_to_anchor (:400-504) for the tile kernel: where the
+//   sparse_*                postings of every matched term cross the anchor-tile boundaries.
+#include <cuda_fp16.h>
+
+#include "bitvec.cuh"
+#include "kernels.cuh"
+
+namespace vdev {
+
+// ---------------------------------------------------------------- fuzzy_match
+// Grid: x = groups of 256 dictionary tiles (8 warps x 32 lanes, one tile per lane),
+//       y = chunks of kPartChunk search parts.  Each lane keeps its tile's common
+// prefix in registers for the whole part loop, so every dictionary byte is read
+// once per part chunk.  Per (part, tile): run the bit-parallel automaton over the
+// prefix; if no extension can stay within d the 32 terms are skipped (exact: the
+// column minimum is a lower bound for every extension), otherwise the warp
+// verifies the tile with one term per lane.
+static const int kPartChunk = 64;
+static const int kFuzzyThreads = 256;
+
+struct PartLite {
+    uint16_t sym[64];
+    uint32_t m, d, flags, pad;
+};
+
+__global__ void __launch_bounds__(kFuzzyThreads) fuzzy_match_kernel(DictView dict, const PartQuery* __restrict__ parts, const uint32_t* __restrict__ part_ids, uint32_t n_parts,
+                                                                    MatchRecord* __restrict__ out, uint32_t capacity, unsigned long long* __restrict__ counter) {
+    __shared__ PartLite sp[kPartChunk];
+    __shared__ uint32_t sp_id[kPartChunk];
+    const uint32_t chunk_begin = blockIdx.y * kPartChunk;
+    const uint32_t chunk_n = min((uint32_t)kPartChunk, n_parts - chunk_begin);
+    for (uint32_t i = threadIdx.x; i < chunk_n * 64; i += blockDim.x) {
+        uint32_t p = i / 64, j = i % 64;
+        sp[p].sym[j] = parts[part_ids[chunk_begin + p]].match_sym[j];
+    }
+    for (uint32_t p = threadIdx.x; p < chunk_n; p += blockDim.x) {
+        const PartQuery& q = parts[part_ids[chunk_begin + p]];
+        sp[p].m = q.m;
+        sp[p].d = q.d_match;
+        sp[p].flags = q.flags;
+        sp_id[p] = part_ids[chunk_begin + p];
+    }
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp_tile0 = (blockIdx.x * (kFuzzyThreads / 32) + (threadIdx.x >> 5)) * 32u;
+    if (warp_tile0 >= dict.n_tiles) return;
+    const uint32_t my_tile = warp_tile0 + lane;
+    const bool have_tile = my_tile < dict.n_tiles;
+    TilePrefix pfx[2];
+    pfx[0].len = 0, pfx[1].len = 0;
+    if (have_tile) {
+        pfx[0] = dict.tiles[0][my_tile];
+        pfx[1] = dict.tiles[1][my_tile];
+    }
+
+    for (uint32_t p = 0; p < chunk_n; ++p) {
+        const PartLite& q = sp[p];
+        const uint32_t m = q.m, d = q.d;
+        const bool prefix_mode = q.flags & kPartPrefix, transposition = q.flags & kPartTransposition;
+        const int variant = (q.flags & kPartRawCase) ? 1 : 0;
+        bool viable = false;
+        if (have_tile) {
+            const TilePrefix& t = pfx[variant];
+            vbit::State s;
+            vbit::init(s, m);
+            for (uint32_t i = 0; i < t.len; ++i) vbit::step(s, vbit::eq_mask(q.sym, m, t.sym[i]), m, transposition);
+            viable = (prefix_mode && s.best <= d) || vbit::column_min(s, m) <= d;
+        }
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, viable);
+        while (todo) {
+            const uint32_t b = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t slot = (warp_tile0 + b) * kDictTile + lane;
+            bool match = false;
+            if (slot < dict.n) {
+                const uint16_t* ts = dict.sym[variant] + dict.off[variant][slot];
+                const uint32_t n = dict.off[variant][slot + 1] - dict.off[variant][slot];
+                vbit::State s;
+                vbit::init(s, m);
+                for (uint32_t i = 0; i < n; ++i) vbit::step(s, vbit::eq_mask(q.sym, m, ts[i]), m, transposition);
+                match = prefix_mode ? (s.best <= d) : (s.score <= d);
+            }
+            const uint32_t mm = __ballot_sync(0xFFFFFFFFu, match);
+            if (mm) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(mm));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (match) {
+                    unsigned long long at = base + __popc(mm & ((1u << lane) - 1u));
+                    if (at < capacity) out[at] = MatchRecord{sp_id[p], slot};
+                }
+            }
+        }
+    }
+}
+
+void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* parts, const uint32_t* part_ids, uint32_t n_parts, MatchRecord* out, uint32_t capacity,
+                        unsigned long long* counter) {
+    if (n_parts == 0 || dict.n == 0) return;
+    dim3 grid((dict.n_tiles + kFuzzyThreads - 1) / kFuzzyThreads, (n_parts + kPartChunk - 1) / kPartChunk);
+    fuzzy_match_kernel<<<grid, kFuzzyThreads, 0, st>>>(dict, parts, part_ids, n_parts, out, capacity, counter);
+    count_launch();
+}
+
+// ---------------------------------------------------------------- grouping
+__global__ void group_count_kernel(const MatchRecord* __restrict__ rec, uint32_t n, uint32_t* __restrict__ part_count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&part_count[rec[i].part], 1u);
+}
+
+// Exclusive scan of `in[0..n)` into `out[0..n]` (out[n] = total) by one block.
+__global__ void __launch_bounds__(1024) scan_u32_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < n ? in[i] : 0u, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_sums[threadIdx.x], z = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xFFFFFFFFu, z, o);
+                if (threadIdx.x >= o) z += y;
+            }
+            warp_sums[threadIdx.x] = z - w;  // exclusive
+        }
+        __syncthreads();
+        uint32_t excl = carry + warp_sums[threadIdx.x >> 5] + x - v;
+        if (i < n) out[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
+
+__global__ void __launch_bounds__(1024) scan_u64_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, uint32_t n) {
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint64_t v = i < n ? in[i] : 0ull, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint64_t w = warp_sums[threadIdx.x], z = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint64_t y = __shfl_up_sync(0xFFFFFFFFu, z, o);
+                if (threadIdx.x >= o) z += y;
+            }
+            warp_sums[threadIdx.x] = z - w;
+        }
+        __syncthreads();
+        uint64_t excl = carry + warp_sums[threadIdx.x >> 5] + x - v;
+        if (i < n) out[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
+
+// One thread per match record: score it (search_field.rs:304-354), look up its
+// posting list, classify it dense/sparse and place it in its part's segment
+// (dense matches from the front, sparse ones from the back).
+__global__ void score_scatter_kernel(ScoreScatterArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_records) return;
+    const MatchRecord r = a.records[i];
+    const PartQuery& q = a.parts[r.part];
+    float score;
+    uint32_t term_id;
+    if (a.inj_terms) {
+        term_id = a.inj_terms[r.slot];
+        score = a.inj_scores[r.slot];
+    } else {
+        const DictView& dict = a.dicts[a.part_dict[r.part]];
+        const uint16_t* ts = dict.sym[0] + dict.off[0][r.slot];
+        const uint32_t n = dict.off[0][r.slot + 1] - dict.off[0][r.slot];
+        const uint32_t m = q.m;
+        bool prefix_matches = false;
+        if ((q.flags & kPartCheckPrefix) && n >= m) {
+            prefix_matches = true;
+            for (uint32_t j = 0; j < m; ++j) prefix_matches = prefix_matches && (ts[j] == q.score_sym[j]);
+        }
+        uint32_t dist = vbit::distance(q.score_sym, m, ts, n, true);  // scoring DFA: transposition on (:298-300)
+        if (dist > (q.d_score & 0xFFu)) {                             // Distance::AtLeast -> distance() (:705-732)
+            if (q.lower_bytes >= 255u || dict.lower_bytes[r.slot] >= 255u) dist = 255u;
+            else dist = vbit::distance(q.score_sym, m, ts, n, false) & 0xFFu;
+        }
+        score = vbit::default_score(dist, prefix_matches);
+        if (q.flags & kPartHasBoost) score = score * q.boost;
+        term_id = dict.ids[r.slot];
+    }
+
+    uint64_t begin = 0;
+    uint32_t df = 0;
+    if (q.postings != kNoValue) {
+        const PostingsView& pv = a.postings[q.postings];
+        if (term_id < pv.n_terms) {
+            begin = pv.off[term_id];
+            df = (uint32_t)(pv.off[term_id + 1] - begin);
+        }
+    }
+    const bool dense = df >= a.dense_min;
+    const uint32_t seg = a.part_begin[r.part], cnt = a.part_begin[r.part + 1] - seg;
+    uint32_t pos, row = kNoValue;
+    if (dense) {
+        pos = seg + atomicAdd(&a.dense_cursor[r.part], 1u);
+        row = atomicAdd(a.n_dense_rows, 1u);
+        if (row < a.dense_row_capacity) a.row_match[row] = pos;
+    } else {
+        pos = seg + cnt - 1u - atomicAdd(&a.sparse_cursor[r.part], 1u);
+    }
+    a.g_term[pos] = term_id;
+    a.g_score[pos] = score;
+    a.g_begin[pos] = begin;
+    a.g_df[pos] = df;
+    a.g_row[pos] = row;
+    a.g_part[pos] = r.part;
+    if (df) atomicAdd(&a.part_est[r.part], (unsigned long long)df);
+}
+
+// One block per dense match: offset of the first posting >= tile start, for every tile boundary.
+__global__ void __launch_bounds__(256) dense_tile_offsets_kernel(DenseOffsetsArgs a) {
+    const uint32_t row = blockIdx.x;
+    const uint32_t mi = a.row_match[row];
+    const PostingsView& pv = a.postings[a.parts[a.g_part[mi]].postings];
+    const uint32_t* anchors = pv.anchors + a.g_begin[mi];
+    const uint32_t df = a.g_df[mi];
+    uint32_t* out = a.toff + (size_t)row * (a.n_tiles + 1);
+    for (uint32_t t = threadIdx.x; t <= a.n_tiles; t += blockDim.x) {
+        const uint64_t bound64 = (uint64_t)a.anchor_lo + ((uint64_t)t << a.tile_log2);
+        uint32_t lo = 0, hi = df;
+        if (bound64 > 0xFFFFFFFFull) lo = df;
+        else {
+            const uint32_t bound = (uint32_t)bound64;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (anchors[mid] < bound) lo = mid + 1;
+                else hi = mid;
+            }
+        }
+        out[t] = lo;
+    }
+}
+
+// One warp per grouped match; sparse ones count their postings per tile.
+__global__ void sparse_count_kernel(SparseArgs a) {
+    const uint32_t mi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (mi >= a.n_matches || a.g_row[mi] != kNoValue) return;
+    const uint32_t df = a.g_df[mi];
+    if (df == 0) return;
+    const uint32_t part = a.g_part[mi];
+    const PostingsView& pv = a.postings[a.parts[part].postings];
+    const uint32_t* anchors = pv.anchors + a.g_begin[mi];
+    uint32_t* row = a.bucket + (size_t)part * (a.n_tiles + 1);
+    for (uint32_t j = lane; j < df; j += 32) {
+        uint32_t t = (anchors[j] - a.anchor_lo) >> a.tile_log2;
+        atomicAdd(&row[t + 1], 1u);
+    }
+}
+
+// One block per part: row[t+1] = first entry of tile t (exclusive scan of the counts), total -> sparse_total.
+__global__ void __launch_bounds__(256) sparse_scan_kernel(uint32_t* __restrict__ bucket, uint32_t n_tiles, uint64_t* __restrict__ sparse_total) {
+    __shared__ uint32_t warp_sums[8];
+    __shared__ uint32_t carry;
+    uint32_t* row = bucket + (size_t)blockIdx.x * (n_tiles + 1);
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_tiles; base += 256) {
+        uint32_t t = base + threadIdx.x;
+        uint32_t v = t < n_tiles ? row[t + 1] : 0u, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = threadIdx.x < 8 ? warp_sums[threadIdx.x] : 0u, z = w;
+            for (int o = 1; o < 8; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xFFFFFFFFu, z, o);
+                if (threadIdx.x >= o) z += y;
+            }
+            if (threadIdx.x < 8) warp_sums[threadIdx.x] = z - w;
+        }
+        __syncthreads();
+        uint32_t excl = carry + warp_sums[threadIdx.x >> 5] + x - v;
+        if (t < n_tiles) row[t + 1] = excl;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        row[0] = 0;
+        sparse_total[blockIdx.x] = carry;
+    }
+}
+
+// Same walk as sparse_count: writes (anchor, score key) into the tile buckets.  row[t+1]
+// is the cursor of tile t; afterwards it is the end of tile t, so bucket t = [row[t], row[t+1]).
+__global__ void sparse_fill_kernel(SparseArgs a) {
+    const uint32_t mi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (mi >= a.n_matches || a.g_row[mi] != kNoValue) return;
+    const uint32_t df = a.g_df[mi];
+    if (df == 0) return;
+    const uint32_t part = a.g_part[mi];
+    const PostingsView& pv = a.postings[a.parts[part].postings];
+    const uint32_t* anchors = pv.anchors + a.g_begin[mi];
+    const uint16_t* scores = pv.scores + a.g_begin[mi];
+    uint32_t* row = a.bucket + (size_t)part * (a.n_tiles + 1);
+    const uint64_t base = a.sparse_base[part];
+    const float term_score = a.g_score[mi];
+    for (uint32_t j = lane; j < df; j += 32) {
+        const uint32_t anchor = anchors[j];
+        const uint32_t t = (anchor - a.anchor_lo) >> a.tile_log2;
+        const uint64_t at = base + atomicAdd(&row[t + 1], 1u);
+        const float w = __half2float(__ushort_as_half(scores[j])) / 100.0f;  // el.score.to_f32() / 100.0 (:426)
+        a.s_anchor[at] = anchor;
+        a.s_key[at] = vbit::score_key(term_score * w);
+    }
+}
+
+__global__ void part_slices_kernel(PartSlices* __restrict__ out, const uint32_t* __restrict__ part_begin, const uint32_t* __restrict__ dense_cursor,
+                                   const uint64_t* __restrict__ sparse_base, uint32_t n_parts) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_parts) return;
+    PartSlices s;
+    s.m_begin = part_begin[p];
+    s.n_match = part_begin[p + 1] - part_begin[p];
+    s.n_dense = dense_cursor[p];
+    s.sparse_row = p;
+    s.sparse_base = sparse_base[p];
+    out[p] = s;
+}
+
+// One thread per request: for every `and` node whose inputs are all search parts, the
+// input with the fewest (estimated) hits is summed last and the former last input takes
+// its place (swap_remove), as in intersect_hits_score (set_op.rs:388-417).
+__global__ void finalize_programs_kernel(const QueryProgram* __restrict__ queries, uint32_t n, uint32_t* __restrict__ prog, const uint32_t* __restrict__ leaf_part,
+                                         const unsigned long long* __restrict__ part_est) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const QueryProgram qp = queries[q];
+    if (!qp.active) return;
+    uint32_t* code = prog + qp.prog_begin;
+    uint32_t pc = 0;
+    while (pc < qp.prog_len) {
+        const uint32_t op = code[pc];
+        if (op == kOpLeaf) pc += 2;
+        else if (op == kOpUnion) pc += 3 + code[pc + 1];
+        else {
+            const uint32_t cnt = code[pc + 1];
+            uint32_t* order = code + pc + 2;
+            const uint32_t* child_leaf = code + pc + 2 + cnt;
+            uint32_t shortest = 0;
+            unsigned long long best = ~0ull;
+            bool known = true;
+            for (uint32_t i = 0; i < cnt; ++i) {
+                if (child_leaf[i] == kNoValue) {
+                    known = false;
+                    continue;
+                }
+                const unsigned long long est = part_est[leaf_part[qp.leaf_begin + child_leaf[i]]];
+                if (est < best) best = est, shortest = i;
+            }
+            if (!known) shortest = cnt - 1;  // nested inputs: lengths unknown, keep request order
+            uint32_t w = 0;
+            for (uint32_t i = 0; i + 1 < cnt; ++i) order[w++] = (i == shortest) ? cnt - 1 : i;
+            order[cnt - 1] = shortest;
+            pc += 2 + 2 * cnt;
+        }
+    }
+}
+void launch_finalize_programs(cudaStream_t st, const QueryProgram* queries, uint32_t n, uint32_t* prog, const uint32_t* leaf_part, const unsigned long long* part_est) {
+    if (!n) return;
+    finalize_programs_kernel<<<(n + 127) / 128, 128, 0, st>>>(queries, n, prog, leaf_part, part_est);
+    count_launch();
+}
+
+void launch_group_count(cudaStream_t st, const MatchRecord* rec, uint32_t n, uint32_t* part_count) {
+    if (!n) return;
+    group_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(rec, n, part_count);
+    count_launch();
+}
+void launch_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, uint32_t n) {
+    scan_u32_kernel<<<1, 1024, 0, st>>>(in, out, n);
+    count_launch();
+}
+void launch_scan_u64(cudaStream_t st, const uint64_t* in, uint64_t* out, uint32_t n) {
+    scan_u64_kernel<<<1, 1024, 0, st>>>(in, out, n);
+    count_launch();
+}
+void launch_score_scatter(cudaStream_t st, const ScoreScatterArgs& a) {
+    if (!a.n_records) return;
+    score_scatter_kernel<<<(a.n_records + 127) / 128, 128, 0, st>>>(a);
+    count_launch();
+}
+void launch_dense_tile_offsets(cudaStream_t st, const DenseOffsetsArgs& a, uint32_t n_rows) {
+    if (!n_rows) return;
+    dense_tile_offsets_kernel<<<n_rows, 256, 0, st>>>(a);
+    count_launch();
+}
+void launch_sparse_count(cudaStream_t st, const SparseArgs& a) {
+    if (!a.n_matches) return;
+    const uint64_t threads = (uint64_t)a.n_matches * 32;
+    sparse_count_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
+    count_launch();
+}
+void launch_sparse_scan(cudaStream_t st, uint32_t* bucket, uint32_t n_tiles, uint64_t* sparse_total, uint32_t n_parts) {
+    if (!n_parts) return;
+    sparse_scan_kernel<<<n_parts, 256, 0, st>>>(bucket, n_tiles, sparse_total);
+    count_launch();
+}
+void launch_sparse_fill(cudaStream_t st, const SparseArgs& a) {
+    if (!a.n_matches) return;
+    const uint64_t threads = (uint64_t)a.n_matches * 32;
+    sparse_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
+    count_launch();
+}
+void launch_part_slices(cudaStream_t st, PartSlices* out, const uint32_t* part_begin, const uint32_t* dense_cursor, const uint64_t* sparse_base, uint32_t n_parts) {
+    if (!n_parts) return;
+    part_slices_kernel<<<(n_parts + 255) / 256, 256, 0, st>>>(out, part_begin, dense_cursor, sparse_base, n_parts);
+    count_launch();
+}
+
+}  // namespace vdev

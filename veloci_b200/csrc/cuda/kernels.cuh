@@ -1,0 +1,134 @@
+// Launch wrappers of every kernel (implemented in fuzzy.cu / tiles.cu) and their argument blocks.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_types.cuh"
+
+namespace vdev {
+
+void count_launch();          // bumps the library-wide kernel launch counter
+uint64_t launches_so_far();
+
+// ---- fuzzy.cu ----
+void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* parts, const uint32_t* part_ids, uint32_t n_parts, MatchRecord* out, uint32_t capacity,
+                        unsigned long long* counter);
+void launch_group_count(cudaStream_t st, const MatchRecord* rec, uint32_t n, uint32_t* part_count);
+void launch_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, uint32_t n);
+void launch_scan_u64(cudaStream_t st, const uint64_t* in, uint64_t* out, uint32_t n);
+
+struct ScoreScatterArgs {
+    const MatchRecord* records;
+    uint32_t n_records;
+    const PartQuery* parts;
+    const uint32_t* part_dict;   // part -> index into dicts
+    const DictView* dicts;
+    const PostingsView* postings;
+    const uint32_t* part_begin;  // n_parts + 1
+    uint32_t* dense_cursor;      // per part, zeroed
+    uint32_t* sparse_cursor;     // per part, zeroed
+    uint32_t* n_dense_rows;      // zeroed
+    uint32_t dense_row_capacity;
+    uint32_t dense_min;          // df >= dense_min -> tile-offset row
+    uint32_t* row_match;         // dense row -> grouped match
+    unsigned long long* part_est; // per part: sum of df over its matches (upper bound of its hit count), zeroed
+    // grouped match arrays
+    uint32_t* g_term;
+    float* g_score;
+    uint64_t* g_begin;
+    uint32_t* g_df;
+    uint32_t* g_row;
+    uint32_t* g_part;
+    // step seam (vgpu_resolve_to_anchor): hits are given, record.slot indexes these arrays
+    const uint32_t* inj_terms;
+    const float* inj_scores;
+};
+void launch_score_scatter(cudaStream_t st, const ScoreScatterArgs& a);
+
+struct DenseOffsetsArgs {
+    const uint32_t* row_match;
+    const uint32_t* g_part;
+    const uint64_t* g_begin;
+    const uint32_t* g_df;
+    const PartQuery* parts;
+    const PostingsView* postings;
+    uint32_t* toff;  // [rows][n_tiles + 1]
+    uint32_t n_tiles, tile_log2, anchor_lo;
+};
+void launch_dense_tile_offsets(cudaStream_t st, const DenseOffsetsArgs& a, uint32_t n_rows);
+
+struct SparseArgs {
+    uint32_t n_matches;
+    const uint32_t* g_row;
+    const uint32_t* g_df;
+    const uint32_t* g_part;
+    const uint64_t* g_begin;
+    const float* g_score;
+    const PartQuery* parts;
+    const PostingsView* postings;
+    uint32_t* bucket;  // [n_parts][n_tiles + 1]
+    const uint64_t* sparse_base;
+    uint32_t* s_anchor;
+    uint32_t* s_key;
+    uint32_t n_tiles, tile_log2, anchor_lo;
+};
+void launch_sparse_count(cudaStream_t st, const SparseArgs& a);
+void launch_sparse_scan(cudaStream_t st, uint32_t* bucket, uint32_t n_tiles, uint64_t* sparse_total, uint32_t n_parts);
+void launch_sparse_fill(cudaStream_t st, const SparseArgs& a);
+void launch_part_slices(cudaStream_t st, PartSlices* out, const uint32_t* part_begin, const uint32_t* dense_cursor, const uint64_t* sparse_base, uint32_t n_parts);
+
+// Patches the sum order of every `and` node (set_op.rs:388-417: the shortest input is
+// swap_remove'd and added last); input lengths are estimated by part_est.
+void launch_finalize_programs(cudaStream_t st, const QueryProgram* queries, uint32_t n, uint32_t* prog, const uint32_t* leaf_part, const unsigned long long* part_est);
+
+// ---- tiles.cu ----
+struct TileArgs {
+    // batch programs
+    const QueryProgram* queries;
+    uint32_t n_queries;
+    const uint32_t* leaf_part;
+    const uint32_t* prog;
+    const BoostStep* boosts;
+    // parts and their slices
+    const PartQuery* parts;
+    const PartSlices* slices;
+    const PostingsView* postings;
+    const float* g_score;
+    const uint64_t* g_begin;
+    const uint32_t* g_row;
+    const uint32_t* g_df;
+    const uint32_t* toff;
+    const uint32_t* bucket;
+    const uint32_t* s_anchor;
+    const uint32_t* s_key;
+    // geometry
+    uint32_t n_tiles, tile_log2, anchor_lo, anchor_hi;
+    uint32_t max_leaves;  // shared-memory arrays per CTA
+    // per-query state
+    unsigned long long* heap;  // [n_queries][heap_stride] keys, sorted descending, 0 = empty
+    uint32_t heap_stride;
+    unsigned long long* tau;   // current k-th best key (0 until k hits were seen)
+    uint32_t* lock;
+    unsigned long long* num_hits;
+    // work queue
+    unsigned long long* work_counter;
+    unsigned long long n_items;
+    // traffic model
+    unsigned long long* stat_postings;
+    // step seam: every hit of requests with emit_all
+    unsigned long long* emit;
+    unsigned long long* emit_count;
+    unsigned long long emit_capacity;
+};
+// Returns the dynamic shared memory the launch needs (0 = cannot run with these parameters).
+size_t tile_kernel_smem(uint32_t tile_log2, uint32_t max_leaves);
+void launch_tile_eval(cudaStream_t st, const TileArgs& a, int n_sms);
+
+// Final ordering of each request's heap: merges `n_src` gathered heaps per query
+// (n_src = 1: the local one) into `out_keys` [n_queries][stride] sorted by key desc,
+// and sums the per-source num_hits.
+void launch_merge_heaps(cudaStream_t st, const uint64_t* src_keys, const uint64_t* src_hits, uint32_t n_src, uint32_t n_queries, uint32_t stride, const QueryProgram* queries,
+                        uint64_t* out_keys, uint64_t* out_hits);
+
+}  // namespace vdev

@@ -1,0 +1,284 @@
+// extern "C" boundary of libveloci_b200.so (include/veloci_b200.h).  No exception
+// crosses it: every entry point maps failures to a VGPU_ERR_* status and leaves the
+// message in a thread-local buffer (vgpu_last_error).
+#include "../../../include/veloci_b200.h"
+
+#include <atomic>
+#include <cstring>
+#include <string>
+
+#include "engine.hpp"
+#include "steps.hpp"
+
+namespace vdev {
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+uint64_t launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
+}  // namespace vdev
+
+struct vgpu_index {
+    std::unique_ptr<vdev::DeviceIndex> ix;
+};
+struct vgpu_batch {
+    vdev::Batch b;
+    std::vector<std::vector<vsteps::FacetGroups>> facets;  // per request, filled on demand
+};
+
+static thread_local std::string t_error;
+
+template <class F>
+static int32_t guarded(F&& f) {
+    try {
+        f();
+        return VGPU_OK;
+    } catch (const vplan::InvalidRequest& e) {
+        t_error = e.what();
+        return VGPU_ERR_INVALID_REQUEST;
+    } catch (const vhost::FstNotFound& e) {
+        t_error = e.what();
+        return VGPU_ERR_FIELD_NOT_FOUND;
+    } catch (const vhost::PathNotFound& e) {
+        t_error = e.what();
+        return VGPU_ERR_PATH_NOT_FOUND;
+    } catch (const vhost::IoError& e) {
+        t_error = e.what();
+        return VGPU_ERR_IO;
+    } catch (const vhost::RequestError& e) {
+        t_error = e.what();
+        return VGPU_ERR_JSON;
+    } catch (const vjson::ParseError& e) {
+        t_error = e.what();
+        return VGPU_ERR_JSON;
+    } catch (const vdev::CudaError& e) {
+        t_error = e.what();
+        return VGPU_ERR_CUDA;
+    } catch (const vplan::Unsupported& e) {
+        t_error = e.what();
+        return VGPU_ERR_UNSUPPORTED;
+    } catch (const std::exception& e) {
+        t_error = e.what();
+        return VGPU_ERR_INTERNAL;
+    } catch (...) {
+        t_error = "unknown error";
+        return VGPU_ERR_INTERNAL;
+    }
+}
+
+extern "C" {
+
+const char* vgpu_last_error(void) { return t_error.c_str(); }
+
+int32_t vgpu_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
+int32_t vgpu_index_open(const char* dir, int32_t device, uint32_t shard_rank, uint32_t n_shards, vgpu_index** out) {
+    if (!dir || !out) {
+        t_error = "null argument";
+        return VGPU_ERR_INVALID_REQUEST;
+    }
+    *out = nullptr;
+    return guarded([&]() {
+        std::unique_ptr<vgpu_index> h(new vgpu_index());
+        h->ix = vdev::DeviceIndex::open(dir, device, shard_rank, n_shards);
+        *out = h.release();
+    });
+}
+
+void vgpu_index_close(vgpu_index* idx) {
+    if (!idx) return;
+    if (idx->ix) cudaSetDevice(idx->ix->device);
+    delete idx;
+}
+
+int32_t vgpu_index_info(const vgpu_index* idx, uint64_t* num_docs, uint64_t* anchor_lo, uint64_t* anchor_hi, uint64_t* device_bytes) {
+    if (!idx) return VGPU_ERR_INVALID_REQUEST;
+    if (num_docs) *num_docs = idx->ix->num_docs;
+    if (anchor_lo) *anchor_lo = idx->ix->anchor_lo;
+    if (anchor_hi) *anchor_hi = idx->ix->anchor_hi;
+    if (device_bytes) *device_bytes = idx->ix->device_bytes;
+    return VGPU_OK;
+}
+
+int32_t vgpu_batch_prepare(vgpu_index* idx, const char* const* request_json, uint32_t n, vgpu_batch** out) {
+    if (!idx || !out || (n && !request_json)) {
+        t_error = "null argument";
+        return VGPU_ERR_INVALID_REQUEST;
+    }
+    *out = nullptr;
+    return guarded([&]() {
+        std::unique_ptr<vgpu_batch> b(new vgpu_batch());
+        b->b.prepare(idx->ix.get(), request_json, n);
+        *out = b.release();
+    });
+}
+
+int32_t vgpu_batch_execute(vgpu_batch* batch) {
+    if (!batch) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() {
+        batch->facets.clear();
+        batch->b.execute();
+    });
+}
+
+void vgpu_batch_free(vgpu_batch* batch) {
+    if (!batch) return;
+    if (batch->b.ix) cudaSetDevice(batch->b.ix->device);
+    delete batch;
+}
+
+int32_t vgpu_batch_status(const vgpu_batch* batch, uint32_t q) {
+    if (!batch || q >= batch->b.n) return VGPU_ERR_INVALID_REQUEST;
+    return batch->b.plan.requests[q].status;
+}
+
+const char* vgpu_batch_message(const vgpu_batch* batch, uint32_t q) {
+    if (!batch || q >= batch->b.n) return "";
+    return batch->b.plan.requests[q].message.c_str();
+}
+
+int32_t vgpu_batch_result(const vgpu_batch* batch_c, uint32_t q, uint64_t* num_hits, vgpu_hit* hits, uint32_t cap, uint32_t* n_hits) {
+    vgpu_batch* batch = const_cast<vgpu_batch*>(batch_c);
+    if (!batch || q >= batch->b.n) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() {
+        uint32_t w = batch->b.result(q, num_hits, reinterpret_cast<vdev::vgpu_hit_pod*>(hits), cap);
+        if (n_hits) *n_hits = w;
+    });
+}
+
+int32_t vgpu_batch_results_flat(const vgpu_batch* batch_c, uint32_t k, uint32_t* ids, float* scores, uint64_t* num_hits, int32_t* status) {
+    vgpu_batch* batch = const_cast<vgpu_batch*>(batch_c);
+    if (!batch) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() {
+        std::vector<vdev::vgpu_hit_pod> row(k ? k : 1);
+        for (uint32_t q = 0; q < batch->b.n; ++q) {
+            uint64_t nh = 0;
+            uint32_t w = batch->b.result(q, &nh, row.data(), k);
+            if (num_hits) num_hits[q] = nh;
+            if (status) status[q] = batch->b.plan.requests[q].status;
+            for (uint32_t i = 0; i < k; ++i) {
+                if (ids) ids[(size_t)q * k + i] = i < w ? row[i].id : 0xFFFFFFFFu;
+                if (scores) scores[(size_t)q * k + i] = i < w ? row[i].score : 0.0f;
+            }
+        }
+    });
+}
+
+int32_t vgpu_search_batch(vgpu_index* idx, const char* const* request_json, uint32_t n, uint32_t k, uint32_t* ids, float* scores, uint64_t* num_hits, int32_t* status) {
+    vgpu_batch* b = nullptr;
+    int32_t rc = vgpu_batch_prepare(idx, request_json, n, &b);
+    if (rc != VGPU_OK) return rc;
+    rc = vgpu_batch_execute(b);
+    if (rc == VGPU_OK) rc = vgpu_batch_results_flat(b, k, ids, scores, num_hits, status);
+    vgpu_batch_free(b);
+    return rc;
+}
+
+int32_t vgpu_batch_facet_count(const vgpu_batch* batch, uint32_t q, uint32_t* n_fields) {
+    if (!batch || q >= batch->b.n || !n_fields) return VGPU_ERR_INVALID_REQUEST;
+    *n_fields = (uint32_t)batch->b.plan.requests[q].facets.size();
+    return VGPU_OK;
+}
+
+int32_t vgpu_batch_facet(const vgpu_batch* batch_c, uint32_t q, uint32_t field, const char** field_name, uint32_t* n_groups) {
+    vgpu_batch* batch = const_cast<vgpu_batch*>(batch_c);
+    if (!batch || q >= batch->b.n) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() {
+        vsteps::materialize_facets(batch->b, batch->facets);
+        const auto& f = batch->facets.at(q).at(field);
+        if (field_name) *field_name = f.field.c_str();
+        if (n_groups) *n_groups = (uint32_t)f.groups.size();
+    });
+}
+
+int32_t vgpu_batch_facet_group(const vgpu_batch* batch_c, uint32_t q, uint32_t field, uint32_t group, uint32_t* value_id, uint32_t* count, const char** text) {
+    vgpu_batch* batch = const_cast<vgpu_batch*>(batch_c);
+    if (!batch || q >= batch->b.n) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() {
+        vsteps::materialize_facets(batch->b, batch->facets);
+        const auto& g = batch->facets.at(q).at(field).groups.at(group);
+        if (value_id) *value_id = g.id;
+        if (count) *count = g.count;
+        if (text) *text = g.text.c_str();
+    });
+}
+
+int32_t vgpu_batch_local_topk(const vgpu_batch* batch, uint64_t** keys_dev, uint64_t** num_hits_dev, uint32_t* stride) {
+    if (!batch || !batch->b.executed) {
+        t_error = "batch was not executed";
+        return VGPU_ERR_INVALID_REQUEST;
+    }
+    if (keys_dev) *keys_dev = batch->b.d_out_keys.p;
+    if (num_hits_dev) *num_hits_dev = batch->b.d_out_hits.p;
+    if (stride) *stride = batch->b.stride;
+    return VGPU_OK;
+}
+
+int32_t vgpu_batch_merge_gathered(vgpu_batch* batch, const uint64_t* gathered_keys_dev, const uint64_t* gathered_num_hits_dev, uint32_t n_shards) {
+    if (!batch || !gathered_keys_dev || !gathered_num_hits_dev || n_shards == 0) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() { batch->b.merge_gathered(gathered_keys_dev, gathered_num_hits_dev, n_shards); });
+}
+
+void vgpu_free(void* p) { free(p); }
+void vgpu_hitlist_free(vgpu_hitlist* l) {
+    if (!l) return;
+    free(l->hits);
+    free(l->ids);
+    l->hits = nullptr, l->ids = nullptr, l->n_hits = 0, l->n_ids = 0;
+}
+
+int32_t vgpu_field_search(vgpu_index* idx, const char* part_json, int32_t get_scores, int32_t get_ids, vgpu_hitlist* out) {
+    if (!idx || !part_json || !out) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() { vsteps::field_search(*idx->ix, part_json, get_scores != 0, get_ids != 0, *out); });
+}
+int32_t vgpu_resolve_to_anchor(vgpu_index* idx, const char* part_json, const vgpu_hitlist* in, vgpu_hitlist* out) {
+    if (!idx || !part_json || !in || !out) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() { vsteps::resolve_to_anchor(*idx->ix, part_json, *in, *out); });
+}
+int32_t vgpu_union_hits_score(vgpu_index* idx, const vgpu_hitlist* inputs, const char* const* terms, uint32_t n, vgpu_hitlist* out) {
+    if (!idx || (n && (!inputs || !terms)) || !out) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() { vsteps::set_op(*idx->ix, inputs, terms, n, true, *out); });
+}
+int32_t vgpu_intersect_hits_score(vgpu_index* idx, const vgpu_hitlist* inputs, uint32_t n, vgpu_hitlist* out) {
+    if (!idx || (n && !inputs) || !out) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() { vsteps::set_op(*idx->ix, inputs, nullptr, n, false, *out); });
+}
+int32_t vgpu_add_boost(vgpu_index* idx, const char* boost_json, vgpu_hitlist* inout) {
+    if (!idx || !boost_json || !inout) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() { vsteps::add_boost(*idx->ix, boost_json, *inout); });
+}
+int32_t vgpu_top_n(vgpu_index* idx, const vgpu_hitlist* in, uint32_t top, uint32_t skip, vgpu_hitlist* out) {
+    if (!idx || !in || !out) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() { vsteps::top_n(*idx->ix, *in, top, skip, *out); });
+}
+
+uint64_t vgpu_launch_count(void) { return vdev::launches_so_far(); }
+
+int32_t vgpu_batch_phase_ms(const vgpu_batch* batch, float* ms, uint32_t n_phases) {
+    if (!batch || !ms) return VGPU_ERR_INVALID_REQUEST;
+    for (uint32_t i = 0; i < n_phases; ++i) ms[i] = i < (uint32_t)vdev::kPhases ? batch->b.phase_ms[i] : 0.0f;
+    return VGPU_OK;
+}
+
+int32_t vgpu_batch_traffic_model(const vgpu_batch* batch_c, uint64_t* posting_bytes, uint64_t* boost_bytes, uint64_t* postings, uint64_t* union_hits) {
+    vgpu_batch* batch = const_cast<vgpu_batch*>(batch_c);
+    if (!batch) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() {
+        batch->b.fetch();
+        // 6 B per posting expanded (+ 8 B of offsets per matched term),
+        // 4 B of boost column per unioned hit and boost step, 8 B per returned hit
+        uint64_t boost_steps = 0;
+        for (uint32_t q = 0; q < batch->b.n; ++q) boost_steps += (uint64_t)batch->b.plan.programs[q].n_boosts * batch->b.h_hits[q];
+        if (posting_bytes) *posting_bytes = batch->b.stat_postings * 6ull + batch->b.stat_matches * 8ull;
+        if (boost_bytes) *boost_bytes = boost_steps * 4ull;
+        if (postings) *postings = batch->b.stat_postings;
+        if (union_hits) *union_hits = batch->b.stat_union;
+    });
+}
+
+}  // extern "C"

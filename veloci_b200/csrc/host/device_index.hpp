@@ -1,0 +1,415 @@
+// Device (HBM) layout of a veloci index directory, built once at open.
+//
+// Replaces the mmap'd views behind the reference's index-access traits
+// (src/persistence.rs:80-87,142-181) with flat arrays the kernels can stream:
+//
+//   term dictionary  (`*.textindex.fst`, search_field.rs:54-65)
+//       terms in byte order; per term its Unicode scalars as u16 alphabet codes
+//       (lower-cased and, if any term has upper case, raw), u32 symbol offsets,
+//       term ids, and one 20-byte common-prefix record per tile of 32 terms.
+//   token -> anchor postings (`*.to_anchor_id_score`, token_to_anchor_score_vint.rs:128-204)
+//       CSR: u64 offsets per term id, u32 anchors (ascending), u16 scores (the f16
+//       bit pattern of AnchorScore, persistence_score/mod.rs:7-17)  = 6 B/posting.
+//       With anchor-range shards only the postings of [anchor_lo, anchor_hi) are kept.
+//   id -> ids stores (`Indirect`, `SingleArrayPacked`; indirect.rs:10-89, single_array.rs:93-147)
+//       CSR u32 offsets + u32 values (vint decoded at load).
+//   boost columns (`*.boost_valid_to_value`, boost.rs:490-494)
+//       dense u32 per id: f32 bits of get_value(), 0xFFFFFFFF = no value.
+//   phrase pairs (`*.phrase_pair_to_anchor`, persistence_data_binary_search.rs:126-203)
+//       sorted u64 keys (t1<<32|t2) + CSR of anchors.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../cuda/device_types.cuh"
+#include "persistence.hpp"
+
+namespace vdev {
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define VDEV_CUDA(expr)                                                                                          \
+    do {                                                                                                         \
+        cudaError_t e__ = (expr);                                                                                \
+        if (e__ != cudaSuccess)                                                                                  \
+            throw vdev::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr, o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p, n = o.n;
+            o.p = nullptr, o.n = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr, n = 0;
+    }
+    void alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        VDEV_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+        n = count;
+    }
+    // keeps the allocation when it is already large enough
+    void reserve(size_t count) {
+        if (count > n) alloc(count + count / 4);
+    }
+    void upload(const std::vector<T>& v) {
+        alloc(v.size());
+        if (!v.empty()) VDEV_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// f32 -> f16 bit pattern, round to nearest even (half::f16::from_f32)
+inline uint16_t f32_to_f16_bits(float f) {
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    uint32_t sign = (x >> 16) & 0x8000u;
+    int32_t exp = (int32_t)((x >> 23) & 0xFF);
+    uint32_t man = x & 0x7FFFFFu;
+    if (exp == 255) return (uint16_t)(sign | 0x7C00u | (man ? (0x200u | (man >> 13)) : 0u));
+    int32_t e = exp - 127 + 15;
+    if (e >= 31) return (uint16_t)(sign | 0x7C00u);
+    if (e <= 0) {
+        if (e < -10) return (uint16_t)sign;
+        man |= 0x800000u;
+        uint32_t shift = (uint32_t)(14 - e);
+        uint32_t hm = man >> shift;
+        uint32_t rem = man & ((1u << shift) - 1u), half = 1u << (shift - 1);
+        if (rem > half || (rem == half && (hm & 1u))) hm++;
+        return (uint16_t)(sign | hm);
+    }
+    uint32_t v = ((uint32_t)e << 10) | (man >> 13);
+    uint32_t rem = man & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (v & 1u))) v++;
+    return (uint16_t)(sign | v);
+}
+
+struct SymbolSet {  // one case variant of a dictionary
+    DevBuf<uint16_t> sym;
+    DevBuf<uint32_t> off;  // n + 1
+    DevBuf<TilePrefix> tiles;
+};
+
+struct DictDev {
+    size_t n = 0;
+    std::vector<uint32_t> alphabet;  // sorted scalars; code = index
+    DevBuf<uint32_t> ids;            // term id per slot
+    DevBuf<uint16_t> lower_bytes;    // byte length of the lower-cased term (clamped)
+    SymbolSet lower;
+    SymbolSet raw;  // empty when identical to `lower`
+    bool has_raw = false;
+    uint32_t n_tiles = 0;
+
+    uint16_t code_of(uint32_t scalar) const {
+        auto it = std::lower_bound(alphabet.begin(), alphabet.end(), scalar);
+        if (it == alphabet.end() || *it != scalar) return 0xFFFFu;
+        return (uint16_t)(it - alphabet.begin());
+    }
+    DictView view() const {
+        DictView v;
+        v.n = (uint32_t)n;
+        v.n_tiles = n_tiles;
+        v.ids = ids.p;
+        v.lower_bytes = lower_bytes.p;
+        v.sym[0] = lower.sym.p, v.off[0] = lower.off.p, v.tiles[0] = lower.tiles.p;
+        const SymbolSet& r = has_raw ? raw : lower;
+        v.sym[1] = r.sym.p, v.off[1] = r.off.p, v.tiles[1] = r.tiles.p;
+        return v;
+    }
+};
+
+struct PostingsDev {
+    size_t n_terms = 0;
+    uint64_t n_postings = 0;
+    DevBuf<uint64_t> off;
+    DevBuf<uint32_t> anchors;
+    DevBuf<uint16_t> scores;
+    PostingsView view() const { return PostingsView{anchors.p, scores.p, off.p, (uint32_t)n_terms}; }
+};
+
+struct CsrDev {  // id -> list<u32>
+    size_t n_ids = 0;
+    DevBuf<uint32_t> off;  // n_ids + 1
+    DevBuf<uint32_t> val;
+    std::vector<uint32_t> h_off, h_val;  // host copy (small stores are also walked on the host)
+    CsrView view() const { return CsrView{off.p, val.p, (uint32_t)n_ids}; }
+};
+
+struct ColumnDev {  // boost column
+    size_t n = 0;
+    DevBuf<uint32_t> bits;
+};
+
+struct PhraseDev {
+    size_t n = 0;
+    DevBuf<uint64_t> keys;
+    DevBuf<uint32_t> off;
+    DevBuf<uint32_t> anchors;
+};
+
+struct DeviceIndex {
+    int device = 0;
+    uint32_t shard_rank = 0, n_shards = 1;
+    uint64_t num_docs = 0, anchor_lo = 0, anchor_hi = 0;
+    std::unique_ptr<vhost::Persistence> host;
+    std::map<std::string, DictDev> dicts;          // "<field>.textindex"
+    std::map<std::string, PostingsDev> postings;   // "<field>.textindex.to_anchor_id_score"
+    std::map<std::string, CsrDev> stores;          // key/value stores
+    std::map<std::string, ColumnDev> boosts;       // "<field>.boost_valid_to_value"
+    std::map<std::string, PhraseDev> phrases;
+    size_t device_bytes = 0;
+
+    static void build_symbol_set(const vhost::TermDict& d, const std::vector<uint32_t>& alphabet, bool lower, SymbolSet& out, std::vector<uint16_t>* lower_bytes) {
+        const size_t n = d.size();
+        std::vector<uint16_t> sym;
+        std::vector<uint32_t> off(n + 1, 0);
+        sym.reserve(d.bytes.size());
+        if (lower_bytes) lower_bytes->assign(n, 0);
+        for (size_t i = 0; i < n; ++i) {
+            const uint8_t* key = &d.bytes[d.offsets[i]];
+            const size_t klen = d.offsets[i + 1] - d.offsets[i];
+            size_t pos = 0, lb = 0;
+            while (pos < klen) {
+                uint32_t cp = vfmt::utf8_next(key, klen, pos);
+                if (lower) cp = vfmt::lower_scalar(cp);
+                lb += cp < 0x80 ? 1 : cp < 0x800 ? 2 : cp < 0x10000 ? 3 : 4;
+                auto it = std::lower_bound(alphabet.begin(), alphabet.end(), cp);
+                sym.push_back((uint16_t)(it - alphabet.begin()));
+            }
+            off[i + 1] = (uint32_t)sym.size();
+            if (lower_bytes) (*lower_bytes)[i] = (uint16_t)std::min<size_t>(lb, 65535);
+        }
+        // common prefix of each tile of kDictTile consecutive terms (first vs last term of the tile)
+        const size_t n_tiles = (n + kDictTile - 1) / kDictTile;
+        std::vector<TilePrefix> tiles(n_tiles);
+        for (size_t t = 0; t < n_tiles; ++t) {
+            size_t a = t * kDictTile, b = std::min(n, a + kDictTile) - 1;
+            uint32_t la = off[a + 1] - off[a], lb2 = off[b + 1] - off[b];
+            uint32_t l = 0, lim = std::min<uint32_t>(std::min(la, lb2), kTilePrefixMax);
+            while (l < lim && sym[off[a] + l] == sym[off[b] + l]) ++l;
+            // byte order == scalar order in UTF-8, but lower-casing can reorder terms:
+            // only the raw variant is sorted.  For the lowered variant verify every term.
+            if (lower)
+                for (size_t i = a + 1; i < b && l > 0; ++i) {
+                    uint32_t li = off[i + 1] - off[i];
+                    uint32_t k = 0;
+                    while (k < l && k < li && sym[off[i] + k] == sym[off[a] + k]) ++k;
+                    l = k;
+                }
+            tiles[t].len = (uint16_t)l;
+            tiles[t].pad = 0;
+            for (uint32_t k = 0; k < kTilePrefixMax; ++k) tiles[t].sym[k] = k < l ? sym[off[a] + k] : 0;
+        }
+        out.sym.upload(sym);
+        out.off.upload(off);
+        out.tiles.upload(tiles);
+    }
+
+    void build_dict(const std::string& path, const vhost::TermDict& d) {
+        DictDev dd;
+        dd.n = d.size();
+        dd.n_tiles = (uint32_t)((dd.n + kDictTile - 1) / kDictTile);
+        bool any_upper = false;
+        std::vector<uint32_t> scalars;
+        {
+            std::vector<uint8_t> seen_small(0x10000 / 8, 0);
+            std::vector<uint32_t> big;
+            auto mark = [&](uint32_t cp) {
+                if (cp < 0x10000) seen_small[cp >> 3] |= (uint8_t)(1u << (cp & 7));
+                else big.push_back(cp);
+            };
+            size_t pos = 0;
+            const size_t total = d.bytes.size();
+            // term boundaries never split a scalar, so the byte stream can be decoded in one go
+            while (pos < total) {
+                uint32_t cp = vfmt::utf8_next(d.bytes.data(), total, pos);
+                uint32_t lc = vfmt::lower_scalar(cp);
+                if (lc != cp) any_upper = true;
+                mark(cp);
+                mark(lc);
+            }
+            for (uint32_t cp = 0; cp < 0x10000; ++cp)
+                if (seen_small[cp >> 3] & (1u << (cp & 7))) scalars.push_back(cp);
+            std::sort(big.begin(), big.end());
+            big.erase(std::unique(big.begin(), big.end()), big.end());
+            scalars.insert(scalars.end(), big.begin(), big.end());
+        }
+        if (scalars.size() >= 0xFFFF) throw std::runtime_error("dictionary " + path + " uses more than 65534 distinct scalars");
+        dd.alphabet = std::move(scalars);
+        dd.ids.upload(d.ids);
+        std::vector<uint16_t> lower_bytes;
+        build_symbol_set(d, dd.alphabet, true, dd.lower, &lower_bytes);
+        dd.lower_bytes.upload(lower_bytes);
+        dd.has_raw = any_upper;
+        if (any_upper) build_symbol_set(d, dd.alphabet, false, dd.raw, nullptr);
+        device_bytes += dd.ids.bytes() + dd.lower_bytes.bytes() + dd.lower.sym.bytes() + dd.lower.off.bytes() + dd.lower.tiles.bytes() + dd.raw.sym.bytes() + dd.raw.off.bytes() + dd.raw.tiles.bytes();
+        dicts.emplace(path, std::move(dd));
+    }
+
+    void build_postings(const std::string& path, const vfmt::AnchorScoreView& v) {
+        const size_t n = v.num_ids();
+        std::vector<uint64_t> off(n + 1, 0);
+        const uint32_t lo = (uint32_t)anchor_lo, hi = (uint32_t)std::min<uint64_t>(anchor_hi, 0xFFFFFFFFull);
+        const bool all = (n_shards == 1);
+        unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        auto parallel_terms = [&](auto&& fn) {
+            std::vector<std::thread> pool;
+            const size_t chunk = (n + hw - 1) / hw;
+            for (unsigned t = 0; t < hw; ++t) {
+                size_t a = (size_t)t * chunk, b = std::min(n, a + chunk);
+                if (a >= b) break;
+                pool.emplace_back([=, &fn]() { fn(a, b); });
+            }
+            for (auto& th : pool) th.join();
+        };
+        parallel_terms([&](size_t a, size_t b) {
+            for (size_t id = a; id < b; ++id) {
+                uint64_t c = 0;
+                v.for_each((uint32_t)id, [&](uint32_t anchor, uint32_t) { c += (all || (anchor >= lo && anchor < hi)) ? 1 : 0; });
+                off[id + 1] = c;
+            }
+        });
+        for (size_t i = 0; i < n; ++i) off[i + 1] += off[i];
+        const uint64_t total = off[n];
+        std::vector<uint32_t> anchors(total);
+        std::vector<uint16_t> scores(total);
+        parallel_terms([&](size_t a, size_t b) {
+            for (size_t id = a; id < b; ++id) {
+                uint64_t at = off[id];
+                v.for_each((uint32_t)id, [&](uint32_t anchor, uint32_t raw) {
+                    if (all || (anchor >= lo && anchor < hi)) {
+                        anchors[at] = anchor;
+                        scores[at] = f32_to_f16_bits((float)raw);
+                        ++at;
+                    }
+                });
+            }
+        });
+        PostingsDev pd;
+        pd.n_terms = n;
+        pd.n_postings = total;
+        pd.off.upload(off);
+        pd.anchors.upload(anchors);
+        pd.scores.upload(scores);
+        device_bytes += pd.off.bytes() + pd.anchors.bytes() + pd.scores.bytes();
+        postings.emplace(path, std::move(pd));
+    }
+
+    void build_store(const std::string& path, const vhost::KeyValueStore& s) {
+        CsrDev c;
+        std::vector<uint32_t> tmp;
+        if (s.kind == vhost::KeyValueStore::Indirect) {
+            c.n_ids = s.ind.n_ids;
+            c.h_off.assign(c.n_ids + 1, 0);
+            for (size_t id = 0; id < c.n_ids; ++id) {
+                s.ind.append_values(id, c.h_val);
+                c.h_off[id + 1] = (uint32_t)c.h_val.size();
+            }
+        } else if (s.kind == vhost::KeyValueStore::Packed) {
+            c.n_ids = s.packed.width ? s.packed.len / (size_t)s.packed.width : 0;
+            if (s.packed.width && s.packed.len % (size_t)s.packed.width) c.n_ids += 1;
+            c.h_off.assign(c.n_ids + 1, 0);
+            for (size_t id = 0; id < c.n_ids; ++id) {
+                uint32_t v;
+                if (s.packed.get_value(id, v)) c.h_val.push_back(v);
+                c.h_off[id + 1] = (uint32_t)c.h_val.size();
+            }
+        } else {
+            c.n_ids = 0;
+            c.h_off.assign(1, 0);
+        }
+        c.off.upload(c.h_off);
+        c.val.upload(c.h_val);
+        device_bytes += c.off.bytes() + c.val.bytes();
+        stores.emplace(path, std::move(c));
+    }
+
+    void build_boost(const std::string& path, const vhost::KeyValueStore& s) {
+        ColumnDev c;
+        size_t n = 0;
+        if (s.kind == vhost::KeyValueStore::Indirect) n = s.ind.n_ids;
+        else if (s.kind == vhost::KeyValueStore::Packed) n = s.packed.width ? (s.packed.len + (size_t)s.packed.width - 1) / (size_t)s.packed.width : 0;
+        std::vector<uint32_t> bits(n, kNoValue);
+        for (size_t id = 0; id < n; ++id) {
+            uint32_t v;
+            if (s.get_value(id, v)) bits[id] = v;
+        }
+        c.n = n;
+        c.bits.upload(bits);
+        device_bytes += c.bits.bytes();
+        boosts.emplace(path, std::move(c));
+    }
+
+    void build_phrase(const std::string& path, const vfmt::PhrasePairView& v) {
+        PhraseDev p;
+        p.n = v.n;
+        std::vector<uint64_t> keys(v.n);
+        std::vector<uint32_t> off(v.n + 1, 0), anchors;
+        for (size_t i = 0; i < v.n; ++i) {
+            uint32_t t1 = vfmt::load_u32(v.recs + i * 12), t2 = vfmt::load_u32(v.recs + i * 12 + 4), o = vfmt::load_u32(v.recs + i * 12 + 8);
+            keys[i] = ((uint64_t)t1 << 32) | t2;
+            if (o < v.data_len) {
+                vfmt::VintArrayIter it(v.data + o, v.data + v.data_len);
+                uint32_t a;
+                while (it.next(a)) anchors.push_back(a);
+            }
+            off[i + 1] = (uint32_t)anchors.size();
+        }
+        p.keys.upload(keys);
+        p.off.upload(off);
+        p.anchors.upload(anchors);
+        device_bytes += p.keys.bytes() + p.off.bytes() + p.anchors.bytes();
+        phrases.emplace(path, std::move(p));
+    }
+
+    static std::unique_ptr<DeviceIndex> open(const std::string& dir, int device, uint32_t rank, uint32_t n_shards) {
+        if (n_shards == 0 || rank >= n_shards) throw std::runtime_error("invalid shard rank");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) throw CudaError(std::string("no usable CUDA device: ") + cudaGetErrorString(e));
+        if (device < 0 || device >= count) throw CudaError("device ordinal out of range");
+        VDEV_CUDA(cudaSetDevice(device));
+        std::unique_ptr<DeviceIndex> ix(new DeviceIndex());
+        ix->device = device;
+        ix->shard_rank = rank;
+        ix->n_shards = n_shards;
+        ix->host = vhost::Persistence::load(dir);
+        ix->num_docs = ix->host->metadata.num_docs;
+        ix->anchor_lo = ix->num_docs * rank / n_shards;
+        ix->anchor_hi = ix->num_docs * (rank + 1) / n_shards;
+        for (auto& kv : ix->host->dict) ix->build_dict(kv.first, kv.second);
+        for (auto& kv : ix->host->token_to_anchor_score) ix->build_postings(kv.first, kv.second);
+        for (auto& kv : ix->host->key_value_stores) ix->build_store(kv.first, kv.second);
+        for (auto& kv : ix->host->boost_valueid_to_value) ix->build_boost(kv.first, kv.second);
+        for (auto& kv : ix->host->phrase_pair_to_anchor) ix->build_phrase(kv.first, kv.second);
+        VDEV_CUDA(cudaDeviceSynchronize());
+        return ix;
+    }
+};
+
+}  // namespace vdev

@@ -1,0 +1,445 @@
+// Batched executor: runs every plan step of every request of a batch as a fixed
+// sequence of kernels (the reference runs one rayon task per step per request,
+// src/plan_creator/execution_plan.rs:538-546).
+//
+//   phase 0  fuzzy_match per dictionary              (PlanStepFieldSearchToTokenIds)
+//   phase 1  group matches by part, score them        (  "  , hits_scores of each part)
+//   phase 2  dense tile offsets + sparse tile buckets (ResolveTokenIdToAnchor, slicing only)
+//   phase 3  tile evaluation                          (ResolveTokenIdToAnchor, Union, Intersect,
+//                                                      BoostPlanStepFromBoostRequest, top_n_sort)
+//   phase 4  heap finalisation                        (apply_top_skip happens on the host view)
+#pragma once
+#include <cstdlib>
+
+#include "../cuda/bitvec.cuh"
+#include "../cuda/kernels.cuh"
+#include "planner.hpp"
+
+namespace vdev {
+
+struct vgpu_hit_pod {  // same layout as vgpu_hit
+    uint32_t id;
+    float score;
+};
+
+struct ExplicitList {  // a caller-provided hit list used as a leaf (step seam)
+    std::vector<uint32_t> anchors;
+    std::vector<float> scores;
+};
+
+static const int kPhases = 5;
+
+struct Batch {
+    DeviceIndex* ix = nullptr;
+    vplan::BatchPlan plan;
+    uint32_t n = 0, n_parts = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[kPhases + 1] = {};
+    int n_sms = 148;
+    enum Mode { kRequests, kTermHits, kLists } mode = kRequests;
+
+    // device: plan
+    DevBuf<PartQuery> d_parts;
+    DevBuf<uint32_t> d_part_dict, d_leaf_part, d_prog;
+    DevBuf<QueryProgram> d_programs;
+    DevBuf<BoostStep> d_boosts;
+    DevBuf<DictView> d_dicts;
+    DevBuf<PostingsView> d_postings;
+    std::vector<std::vector<uint32_t>> parts_of_dict;
+    std::vector<DevBuf<uint32_t>> d_parts_of_dict;
+    // device: match phase
+    DevBuf<MatchRecord> d_records;
+    DevBuf<unsigned long long> d_counters;  // [0] matches, [1] work counter, [2] stat postings, [3] dense rows, [4] emitted hits
+    DevBuf<uint32_t> d_part_count, d_part_begin, d_dense_cursor, d_sparse_cursor, d_row_match;
+    DevBuf<unsigned long long> d_part_est;
+    DevBuf<uint32_t> d_g_term, d_g_df, d_g_row, d_g_part;
+    DevBuf<float> d_g_score;
+    DevBuf<uint64_t> d_g_begin;
+    DevBuf<uint32_t> d_inj_terms;
+    DevBuf<float> d_inj_scores;
+    uint32_t n_injected = 0;
+    // device: slicing
+    DevBuf<uint32_t> d_toff, d_bucket, d_s_anchor, d_s_key;
+    DevBuf<uint64_t> d_sparse_total, d_sparse_base;
+    DevBuf<PartSlices> d_slices;
+    // device: per-request state and results
+    DevBuf<unsigned long long> d_heap, d_tau, d_num_hits;
+    DevBuf<uint32_t> d_lock;
+    DevBuf<uint64_t> d_out_keys, d_out_hits;
+    DevBuf<unsigned long long> d_emit;  // all hits of request 0 (step seam): (score key << 32) | anchor
+    uint64_t emit_capacity = 0;
+    uint32_t stride = 1;
+    // geometry
+    uint32_t tile_log2 = 13, n_tiles = 0;
+    // host results
+    bool matched = false, executed = false, fetched = false;
+    std::vector<uint64_t> h_keys, h_hits;
+    float phase_ms[kPhases] = {};
+    uint64_t stat_postings = 0, stat_matches = 0, stat_union = 0;
+
+    Batch() = default;
+    Batch(const Batch&) = delete;
+    Batch& operator=(const Batch&) = delete;
+    ~Batch() {
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    // ------------------------------------------------------------ preparation
+    void prepare(DeviceIndex* index, const char* const* request_json, uint32_t count) {
+        ix = index;
+        n = count;
+        plan.ix = ix;
+        plan.requests.reserve(n);
+        for (uint32_t i = 0; i < n; ++i) plan.add_request(request_json[i] ? request_json[i] : "");
+        upload_plan();
+    }
+
+    // field search only (vgpu_field_search)
+    void prepare_parts(DeviceIndex* index, const std::vector<vhost::SearchPart>& search_parts) {
+        ix = index;
+        plan.ix = ix;
+        for (auto& p : search_parts) plan.add_part(p);
+        n = 0;
+        upload_plan();
+    }
+
+    // one request whose single leaf is `part` with the given (term id, score) hits (vgpu_resolve_to_anchor)
+    void prepare_term_hits(DeviceIndex* index, const vhost::SearchPart& part, const std::vector<uint32_t>& terms, const std::vector<float>& scores) {
+        ix = index;
+        plan.ix = ix;
+        mode = kTermHits;
+        vhost::SearchPart p = part;
+        p.top.reset(), p.skip.reset(), p.token_value.reset(), p.is_regex = false;
+        if (p.terms.empty()) p.terms.push_back("");
+        const uint32_t pid = plan.add_part(p);
+        QueryProgram qp;
+        memset(&qp, 0, sizeof qp);
+        qp.leaf_begin = 0, qp.n_leaves = 1, qp.k = 0, qp.active = 1, qp.emit_all = 1;
+        plan.leaf_part.push_back(pid);
+        plan.programs.push_back(qp);
+        plan.requests.emplace_back();
+        n = 1;
+        n_injected = (uint32_t)terms.size();
+        d_inj_terms.upload(terms);
+        d_inj_scores.upload(scores);
+        // every posting may become a hit
+        uint64_t cap = 0;
+        std::string path = p.path;
+        if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+        const vfmt::AnchorScoreView& store = ix->host->get_token_to_anchor(path);
+        for (uint32_t t : terms) store.for_each(t, [&](uint32_t, uint32_t) { ++cap; });
+        emit_capacity = cap;
+        upload_plan();
+    }
+
+    // one request over explicit hit lists (union / intersect / add_boost / top_n step entry points)
+    void prepare_lists(DeviceIndex* index, const std::vector<ExplicitList>& lists, const std::vector<uint32_t>& code, const std::vector<BoostStep>& boost_steps, uint32_t k, bool all_hits) {
+        ix = index;
+        plan.ix = ix;
+        mode = kLists;
+        QueryProgram qp;
+        memset(&qp, 0, sizeof qp);
+        qp.leaf_begin = 0, qp.n_leaves = (uint32_t)lists.size(), qp.k = k, qp.active = 1, qp.emit_all = all_hits ? 1 : 0;
+        const bool trivial = lists.size() == 1 && code.size() == 2;
+        qp.prog_begin = 0, qp.prog_len = trivial ? 0u : (uint32_t)code.size();
+        if (!trivial) plan.prog = code;
+        qp.boost_begin = 0, qp.n_boosts = (uint32_t)boost_steps.size();
+        plan.boosts = boost_steps;
+        uint64_t total = 0;
+        for (size_t i = 0; i < lists.size(); ++i) {
+            PartQuery pq;
+            memset(&pq, 0, sizeof pq);
+            pq.postings = kNoValue;
+            plan.parts.push_back(pq);
+            plan.part_dict.push_back(0);
+            plan.leaf_part.push_back((uint32_t)i);
+            total += lists[i].anchors.size();
+        }
+        plan.programs.push_back(qp);
+        plan.requests.emplace_back();
+        plan.max_leaves = std::max<uint32_t>(1, (uint32_t)lists.size());
+        plan.max_k = std::max<uint32_t>(1, k);
+        n = 1;
+        emit_capacity = total;
+        upload_plan();
+        // tile buckets of the lists, built on the host (step seam inputs are small)
+        std::vector<uint32_t> bucket((size_t)lists.size() * (n_tiles + 1), 0), s_anchor, s_key;
+        std::vector<PartSlices> slices(lists.size());
+        for (size_t i = 0; i < lists.size(); ++i) {
+            const ExplicitList& l = lists[i];
+            std::vector<std::pair<uint32_t, uint32_t>> entries;  // dedup keeps the max like resolve_token_to_anchor; inputs are normally unique
+            for (size_t j = 0; j < l.anchors.size(); ++j)
+                if (l.anchors[j] >= ix->anchor_lo && l.anchors[j] < ix->anchor_hi) entries.emplace_back(l.anchors[j], vbit::score_key(l.scores[j]));
+            std::stable_sort(entries.begin(), entries.end(), [](auto& a, auto& b) { return a.first < b.first; });
+            uint32_t* row = &bucket[i * (n_tiles + 1)];
+            for (auto& e : entries) row[((e.first - (uint32_t)ix->anchor_lo) >> tile_log2) + 1]++;
+            for (uint32_t t = 0; t < n_tiles; ++t) row[t + 1] += row[t];
+            slices[i].m_begin = 0, slices[i].n_match = 1, slices[i].n_dense = 0, slices[i].sparse_row = (uint32_t)i, slices[i].sparse_base = s_anchor.size();
+            for (auto& e : entries) s_anchor.push_back(e.first), s_key.push_back(e.second ? e.second : 1u);
+        }
+        d_bucket.upload(bucket);
+        d_s_anchor.upload(s_anchor);
+        d_s_key.upload(s_key);
+        d_slices.upload(slices);
+    }
+
+    void upload_plan() {
+        VDEV_CUDA(cudaSetDevice(ix->device));
+        n_parts = (uint32_t)plan.parts.size();
+        VDEV_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (auto& e : ev) VDEV_CUDA(cudaEventCreate(&e));
+        cudaDeviceProp prop;
+        VDEV_CUDA(cudaGetDeviceProperties(&prop, ix->device));
+        n_sms = prop.multiProcessorCount;
+
+        // geometry: the largest tile whose part arrays leave room for two CTAs per SM
+        const uint32_t L = std::max<uint32_t>(1, plan.max_leaves);
+        tile_log2 = 13;
+        while (tile_log2 > 10 && ((size_t)L << tile_log2) * 4 > 96 * 1024) --tile_log2;
+        if (const char* env = getenv("VELOCI_TILE_LOG2")) {
+            int v = atoi(env);
+            if (v >= 8 && v <= 15 && tile_kernel_smem((uint32_t)v, L)) tile_log2 = (uint32_t)v;
+        }
+        const uint64_t span = ix->anchor_hi - ix->anchor_lo;
+        n_tiles = (uint32_t)((span + (1ull << tile_log2) - 1) >> tile_log2);
+        stride = std::max<uint32_t>(1, plan.max_k);
+
+        d_parts.upload(plan.parts);
+        d_part_dict.upload(plan.part_dict);
+        d_leaf_part.upload(plan.leaf_part);
+        d_prog.upload(plan.prog);
+        d_programs.upload(plan.programs);
+        d_boosts.upload(plan.boosts);
+        std::vector<DictView> dv;
+        for (auto& name : plan.dict_names) dv.push_back(ix->dicts.at(name).view());
+        d_dicts.upload(dv);
+        std::vector<PostingsView> pv;
+        for (auto& name : plan.postings_names) pv.push_back(ix->postings.at(name).view());
+        d_postings.upload(pv);
+        parts_of_dict.assign(plan.dict_names.size(), {});
+        if (mode == kRequests)
+            for (uint32_t p = 0; p < n_parts; ++p) parts_of_dict[plan.part_dict[p]].push_back(p);
+        d_parts_of_dict.resize(parts_of_dict.size());
+        for (size_t d = 0; d < parts_of_dict.size(); ++d) d_parts_of_dict[d].upload(parts_of_dict[d]);
+
+        d_counters.alloc(8);
+        d_part_count.alloc(n_parts + 1);
+        d_part_begin.alloc(n_parts + 2);
+        d_dense_cursor.alloc(n_parts + 1);
+        d_sparse_cursor.alloc(n_parts + 1);
+        d_part_est.alloc(n_parts + 1);
+        d_sparse_total.alloc(n_parts + 1);
+        d_sparse_base.alloc(n_parts + 2);
+        d_slices.alloc(n_parts + 1);
+        d_bucket.alloc((size_t)std::max<uint32_t>(n_parts, 1) * (n_tiles + 1));
+        d_heap.alloc((size_t)std::max<uint32_t>(n, 1) * stride);
+        d_tau.alloc(n + 1);
+        d_num_hits.alloc(n + 1);
+        d_lock.alloc(n + 1);
+        d_out_keys.alloc((size_t)std::max<uint32_t>(n, 1) * stride);
+        d_out_hits.alloc(n + 1);
+        d_emit.alloc((size_t)emit_capacity + 1);
+        if (mode == kRequests) d_records.reserve(std::max<size_t>(1u << 20, (size_t)n_parts * 64));
+        VDEV_CUDA(cudaMemset(d_counters.p, 0, d_counters.bytes()));
+    }
+
+    template <class T>
+    T read_back(const T* dev) {
+        T v;
+        VDEV_CUDA(cudaMemcpyAsync(&v, dev, sizeof(T), cudaMemcpyDeviceToHost, stream));
+        VDEV_CUDA(cudaStreamSynchronize(stream));
+        return v;
+    }
+
+    // ------------------------------------------------------------ phases 0-1
+    void run_match() {
+        VDEV_CUDA(cudaSetDevice(ix->device));
+        VDEV_CUDA(cudaEventRecord(ev[0], stream));
+        uint64_t n_match = 0;
+        if (mode == kRequests) {
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                VDEV_CUDA(cudaMemsetAsync(d_counters.p, 0, d_counters.bytes(), stream));
+                for (size_t d = 0; d < parts_of_dict.size(); ++d) {
+                    const DictDev& dict = ix->dicts.at(plan.dict_names[d]);
+                    launch_fuzzy_match(stream, dict.view(), d_parts.p, d_parts_of_dict[d].p, (uint32_t)parts_of_dict[d].size(), d_records.p,
+                                       (uint32_t)std::min<size_t>(d_records.n, 0xFFFFFFFFu), d_counters.p);
+                }
+                n_match = read_back(d_counters.p);
+                if (n_match <= d_records.n) break;
+                if (n_match > 0xFFFFFFF0ull) throw std::runtime_error("more than 2^32 term matches in one batch");
+                d_records.reserve((size_t)n_match);
+            }
+        } else {  // kTermHits: the hits are given, one record per hit
+            VDEV_CUDA(cudaMemsetAsync(d_counters.p, 0, d_counters.bytes(), stream));
+            std::vector<MatchRecord> rec(n_injected);
+            for (uint32_t i = 0; i < n_injected; ++i) rec[i] = MatchRecord{0u, i};
+            d_records.upload(rec);
+            n_match = n_injected;
+        }
+        stat_matches = n_match;
+        const uint32_t M = (uint32_t)n_match;
+        VDEV_CUDA(cudaEventRecord(ev[1], stream));
+        d_g_term.reserve(M), d_g_df.reserve(M), d_g_row.reserve(M), d_g_part.reserve(M), d_g_score.reserve(M), d_g_begin.reserve(M), d_row_match.reserve(M);
+        VDEV_CUDA(cudaMemsetAsync(d_part_count.p, 0, d_part_count.bytes(), stream));
+        VDEV_CUDA(cudaMemsetAsync(d_dense_cursor.p, 0, d_dense_cursor.bytes(), stream));
+        VDEV_CUDA(cudaMemsetAsync(d_sparse_cursor.p, 0, d_sparse_cursor.bytes(), stream));
+        VDEV_CUDA(cudaMemsetAsync(d_part_est.p, 0, d_part_est.bytes(), stream));
+        launch_group_count(stream, d_records.p, M, d_part_count.p);
+        launch_scan_u32(stream, d_part_count.p, d_part_begin.p, n_parts);
+        ScoreScatterArgs a;
+        a.records = d_records.p, a.n_records = M, a.parts = d_parts.p, a.part_dict = d_part_dict.p, a.dicts = d_dicts.p, a.postings = d_postings.p;
+        a.part_begin = d_part_begin.p, a.dense_cursor = d_dense_cursor.p, a.sparse_cursor = d_sparse_cursor.p, a.n_dense_rows = reinterpret_cast<uint32_t*>(d_counters.p + 3);
+        a.dense_row_capacity = M, a.dense_min = std::max<uint32_t>(1, n_tiles / 2), a.row_match = d_row_match.p, a.part_est = d_part_est.p;
+        a.g_term = d_g_term.p, a.g_score = d_g_score.p, a.g_begin = d_g_begin.p, a.g_df = d_g_df.p, a.g_row = d_g_row.p, a.g_part = d_g_part.p;
+        a.inj_terms = mode == kTermHits ? d_inj_terms.p : nullptr, a.inj_scores = mode == kTermHits ? d_inj_scores.p : nullptr;
+        launch_score_scatter(stream, a);
+        VDEV_CUDA(cudaEventRecord(ev[2], stream));
+        VDEV_CUDA(cudaStreamSynchronize(stream));
+        VDEV_CUDA(cudaGetLastError());
+        matched = true;
+    }
+
+    // (term id, score) hits of one part after run_match, unordered
+    void download_matches(uint32_t part, std::vector<uint32_t>& terms, std::vector<float>& scores) {
+        std::vector<uint32_t> begin(n_parts + 1);
+        VDEV_CUDA(cudaMemcpy(begin.data(), d_part_begin.p, begin.size() * 4, cudaMemcpyDeviceToHost));
+        const uint32_t a = begin[part], cnt = begin[part + 1] - begin[part];
+        terms.resize(cnt), scores.resize(cnt);
+        if (cnt) {
+            VDEV_CUDA(cudaMemcpy(terms.data(), d_g_term.p + a, cnt * 4, cudaMemcpyDeviceToHost));
+            VDEV_CUDA(cudaMemcpy(scores.data(), d_g_score.p + a, cnt * 4, cudaMemcpyDeviceToHost));
+        }
+    }
+
+    // ------------------------------------------------------------ all phases
+    void execute() {
+        VDEV_CUDA(cudaSetDevice(ix->device));
+        executed = false, fetched = false;
+        uint32_t M = 0;
+        if (mode != kLists) {
+            run_match();
+            M = (uint32_t)stat_matches;
+            // ---- phase 2: slicing
+            const uint32_t n_rows = read_back(reinterpret_cast<uint32_t*>(d_counters.p + 3));
+            d_toff.reserve((size_t)std::max<uint32_t>(n_rows, 1) * (n_tiles + 1));
+            DenseOffsetsArgs da;
+            da.row_match = d_row_match.p, da.g_part = d_g_part.p, da.g_begin = d_g_begin.p, da.g_df = d_g_df.p, da.parts = d_parts.p, da.postings = d_postings.p;
+            da.toff = d_toff.p, da.n_tiles = n_tiles, da.tile_log2 = tile_log2, da.anchor_lo = (uint32_t)ix->anchor_lo;
+            launch_dense_tile_offsets(stream, da, n_rows);
+            VDEV_CUDA(cudaMemsetAsync(d_bucket.p, 0, d_bucket.bytes(), stream));
+            SparseArgs sa;
+            sa.n_matches = M, sa.g_row = d_g_row.p, sa.g_df = d_g_df.p, sa.g_part = d_g_part.p, sa.g_begin = d_g_begin.p, sa.g_score = d_g_score.p;
+            sa.parts = d_parts.p, sa.postings = d_postings.p, sa.bucket = d_bucket.p, sa.sparse_base = d_sparse_base.p, sa.s_anchor = nullptr, sa.s_key = nullptr;
+            sa.n_tiles = n_tiles, sa.tile_log2 = tile_log2, sa.anchor_lo = (uint32_t)ix->anchor_lo;
+            launch_sparse_count(stream, sa);
+            launch_sparse_scan(stream, d_bucket.p, n_tiles, d_sparse_total.p, n_parts);
+            launch_scan_u64(stream, d_sparse_total.p, d_sparse_base.p, n_parts);
+            const uint64_t n_sparse = read_back(d_sparse_base.p + n_parts);
+            d_s_anchor.reserve((size_t)std::max<uint64_t>(n_sparse, 1));
+            d_s_key.reserve((size_t)std::max<uint64_t>(n_sparse, 1));
+            sa.s_anchor = d_s_anchor.p, sa.s_key = d_s_key.p;
+            launch_sparse_fill(stream, sa);
+            launch_part_slices(stream, d_slices.p, d_part_begin.p, d_dense_cursor.p, d_sparse_base.p, n_parts);
+            launch_finalize_programs(stream, d_programs.p, n, d_prog.p, d_leaf_part.p, d_part_est.p);
+        } else {
+            VDEV_CUDA(cudaMemsetAsync(d_counters.p, 0, d_counters.bytes(), stream));
+            VDEV_CUDA(cudaEventRecord(ev[0], stream));
+            VDEV_CUDA(cudaEventRecord(ev[1], stream));
+            VDEV_CUDA(cudaEventRecord(ev[2], stream));
+        }
+        VDEV_CUDA(cudaEventRecord(ev[3], stream));
+        // ---- phase 3: tile evaluation
+        VDEV_CUDA(cudaMemsetAsync(d_heap.p, 0, d_heap.bytes(), stream));
+        VDEV_CUDA(cudaMemsetAsync(d_tau.p, 0, d_tau.bytes(), stream));
+        VDEV_CUDA(cudaMemsetAsync(d_num_hits.p, 0, d_num_hits.bytes(), stream));
+        VDEV_CUDA(cudaMemsetAsync(d_lock.p, 0, d_lock.bytes(), stream));
+        {
+            TileArgs a;
+            a.queries = d_programs.p, a.n_queries = n, a.leaf_part = d_leaf_part.p, a.prog = d_prog.p, a.boosts = d_boosts.p;
+            a.parts = d_parts.p, a.slices = d_slices.p, a.postings = d_postings.p, a.g_score = d_g_score.p, a.g_begin = d_g_begin.p, a.g_row = d_g_row.p, a.g_df = d_g_df.p;
+            a.toff = d_toff.p, a.bucket = d_bucket.p, a.s_anchor = d_s_anchor.p, a.s_key = d_s_key.p;
+            a.n_tiles = n_tiles, a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
+            a.max_leaves = std::max<uint32_t>(1, plan.max_leaves);
+            a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
+            a.work_counter = d_counters.p + 1, a.n_items = (unsigned long long)n_tiles * n, a.stat_postings = d_counters.p + 2;
+            a.emit = d_emit.p, a.emit_count = d_counters.p + 4, a.emit_capacity = emit_capacity;
+            launch_tile_eval(stream, a, n_sms);
+        }
+        VDEV_CUDA(cudaEventRecord(ev[4], stream));
+        // ---- phase 4: final order of the local heaps
+        launch_merge_heaps(stream, reinterpret_cast<const uint64_t*>(d_heap.p), reinterpret_cast<const uint64_t*>(d_num_hits.p), 1, n, stride, d_programs.p, d_out_keys.p, d_out_hits.p);
+        VDEV_CUDA(cudaEventRecord(ev[5], stream));
+        VDEV_CUDA(cudaStreamSynchronize(stream));
+        VDEV_CUDA(cudaGetLastError());
+        for (int p = 0; p < kPhases; ++p) VDEV_CUDA(cudaEventElapsedTime(&phase_ms[p], ev[p], ev[p + 1]));
+        executed = true;
+    }
+
+    void merge_gathered(const uint64_t* keys_dev, const uint64_t* hits_dev, uint32_t n_shards) {
+        VDEV_CUDA(cudaSetDevice(ix->device));
+        launch_merge_heaps(stream, keys_dev, hits_dev, n_shards, n, stride, d_programs.p, d_out_keys.p, d_out_hits.p);
+        VDEV_CUDA(cudaStreamSynchronize(stream));
+        fetched = false;
+    }
+
+    void fetch() {
+        if (fetched) return;
+        if (!executed) throw std::runtime_error("batch was not executed");
+        VDEV_CUDA(cudaSetDevice(ix->device));
+        h_keys.resize((size_t)n * stride);
+        h_hits.resize(n);
+        if (n) {
+            VDEV_CUDA(cudaMemcpyAsync(h_keys.data(), d_out_keys.p, h_keys.size() * 8, cudaMemcpyDeviceToHost, stream));
+            VDEV_CUDA(cudaMemcpyAsync(h_hits.data(), d_out_hits.p, h_hits.size() * 8, cudaMemcpyDeviceToHost, stream));
+            uint64_t stats[3];
+            VDEV_CUDA(cudaMemcpyAsync(stats, d_counters.p, sizeof stats, cudaMemcpyDeviceToHost, stream));
+            VDEV_CUDA(cudaStreamSynchronize(stream));
+            stat_postings = stats[2];
+            stat_union = 0;
+            for (uint64_t h : h_hits) stat_union += h;
+        }
+        fetched = true;
+    }
+
+    // SearchResult.data of request q after apply_top_skip (search.rs:230-239)
+    uint32_t result(uint32_t q, uint64_t* num_hits, vgpu_hit_pod* hits, uint32_t cap) {
+        fetch();
+        const vplan::RequestPlan& rp = plan.requests[q];
+        if (num_hits) *num_hits = rp.status == 0 ? h_hits[q] : 0;
+        if (rp.status != 0) return 0;
+        const uint64_t* row = &h_keys[(size_t)q * stride];
+        uint32_t avail = 0;
+        while (avail < stride && avail < rp.top + rp.skip && row[avail] != 0) ++avail;
+        uint32_t w = 0;
+        for (uint64_t i = rp.skip; i < avail && w < rp.top; ++i, ++w) {
+            if (hits && w < cap) {
+                hits[w].id = (uint32_t)(row[i] & 0xFFFFFFFFull);
+                hits[w].score = vbit::key_score((uint32_t)(row[i] >> 32));
+            }
+        }
+        return hits ? std::min(w, cap) : w;
+    }
+
+    // Step seam: every hit of request 0 by ascending anchor id (`all`), or its top-k in rank order.
+    template <class Hit>
+    void download_hits(uint32_t q, bool all, std::vector<Hit>& hits) {
+        hits.clear();
+        if (!all) {
+            fetch();
+            const uint64_t* row = &h_keys[(size_t)q * stride];
+            for (uint32_t i = 0; i < stride && i < plan.programs[q].k && row[i]; ++i) hits.push_back(Hit{(uint32_t)(row[i] & 0xFFFFFFFFull), vbit::key_score((uint32_t)(row[i] >> 32))});
+            return;
+        }
+        unsigned long long cnt = 0;
+        VDEV_CUDA(cudaMemcpy(&cnt, d_counters.p + 4, 8, cudaMemcpyDeviceToHost));
+        if (cnt > emit_capacity) throw std::runtime_error("emit buffer overflow");
+        std::vector<unsigned long long> buf(cnt);
+        if (cnt) VDEV_CUDA(cudaMemcpy(buf.data(), d_emit.p, cnt * 8, cudaMemcpyDeviceToHost));
+        std::sort(buf.begin(), buf.end(), [](unsigned long long a, unsigned long long b) { return (uint32_t)a < (uint32_t)b; });
+        for (auto v : buf) hits.push_back(Hit{(uint32_t)(v & 0xFFFFFFFFull), vbit::key_score((uint32_t)(v >> 32))});
+    }
+};
+
+}  // namespace vdev

@@ -1,0 +1,311 @@
+// Request -> batch programs.  The host half of plan_creator
+// (src/plan_creator/execution_plan.rs:132-534): the request tree becomes a postfix
+// program over "leaves" (one per `search` node), identical RequestSearchParts are
+// searched once per *batch* (FieldRequestCache, :13,91-130, widened from one request
+// to the whole batch), anchor-level boosts are chained after the root (:175-189).
+#pragma once
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../cuda/device_types.cuh"
+#include "device_index.hpp"
+#include "request.hpp"
+
+namespace vplan {
+
+using vdev::BoostStep;
+using vdev::PartQuery;
+using vdev::QueryProgram;
+
+struct Unsupported : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct InvalidRequest : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+struct RequestPlan {
+    int32_t status = 0;
+    std::string message;
+    uint64_t top = 10, skip = 0;
+    std::vector<vhost::FacetRequest> facets;
+    bool has_facets = false;
+};
+
+// `x op y` boost expression (src/expression.rs:25-100)
+inline void parse_expression(const std::string& expression, BoostStep& b) {
+    enum Kind { Division, Mul, Add, Sub, Score, Float };
+    std::vector<std::pair<Kind, float>> ops;
+    std::string current;
+    auto try_float = [&](const std::string& s) {
+        if (s.empty()) return;
+        char* end = nullptr;
+        float v = strtof(s.c_str(), &end);
+        if (end && *end == 0 && end != s.c_str()) ops.emplace_back(Float, v);
+    };
+    for (char c : expression) {
+        if (c == ' ') {
+            try_float(current);
+            current.clear();
+        } else {
+            current.push_back(c);
+        }
+        if (current == "+") ops.emplace_back(Add, 0.f), current.clear();
+        else if (current == "-") ops.emplace_back(Sub, 0.f), current.clear();
+        else if (current == "/") ops.emplace_back(Division, 0.f), current.clear();
+        else if (current == "*") ops.emplace_back(Mul, 0.f), current.clear();
+        else if (current == "$SCORE") ops.emplace_back(Score, 0.f), current.clear();
+    }
+    try_float(current);
+    if (ops.size() < 3) throw InvalidRequest("boost expression must be `x op y`");
+    auto operand = [&](const std::pair<Kind, float>& o, uint32_t& is_score, float& val) {
+        if (o.first == Score) is_score = 1, val = 0.f;
+        else if (o.first == Float) is_score = 0, val = o.second;
+        else throw InvalidRequest("boost expression operand must be a float or $SCORE");
+    };
+    operand(ops[0], b.expr_left_is_score, b.expr_left);
+    operand(ops[2], b.expr_right_is_score, b.expr_right);
+    switch (ops[1].first) {
+        case Division: b.expr_op = vdev::kExprDiv; break;
+        case Mul: b.expr_op = vdev::kExprMul; break;
+        case Add: b.expr_op = vdev::kExprAdd; break;
+        case Sub: b.expr_op = vdev::kExprSub; break;
+        default: throw InvalidRequest("boost expression operator must be one of * + - /");
+    }
+}
+
+struct BatchPlan {
+    const vdev::DeviceIndex* ix = nullptr;
+    std::vector<RequestPlan> requests;
+    // distinct search parts of the batch
+    std::vector<PartQuery> parts;
+    std::vector<uint32_t> part_dict;  // part -> dictionary table index
+    std::unordered_map<std::string, uint32_t> part_index;
+    // tables of device views referenced by index
+    std::vector<std::string> dict_names, postings_names;
+    std::unordered_map<std::string, uint32_t> dict_index, postings_index;
+    // programs
+    std::vector<QueryProgram> programs;
+    std::vector<uint32_t> leaf_part;
+    std::vector<uint32_t> prog;
+    std::vector<BoostStep> boosts;
+    uint32_t max_leaves = 1, max_k = 1;
+
+    uint32_t dict_id(const std::string& path) {
+        auto it = dict_index.find(path);
+        if (it != dict_index.end()) return it->second;
+        if (!ix->dicts.count(path)) throw vhost::FstNotFound(path);
+        uint32_t id = (uint32_t)dict_names.size();
+        dict_names.push_back(path);
+        dict_index.emplace(path, id);
+        return id;
+    }
+    uint32_t postings_id(const std::string& path) {
+        auto it = postings_index.find(path);
+        if (it != postings_index.end()) return it->second;
+        if (!ix->postings.count(path)) ix->host->path_not_found(path);
+        uint32_t id = (uint32_t)postings_names.size();
+        postings_names.push_back(path);
+        postings_index.emplace(path, id);
+        return id;
+    }
+
+    // get_term_ids_in_field's request normalisation (search_field.rs:277-300)
+    uint32_t add_part(const vhost::SearchPart& part_in) {
+        const std::string key = part_in.key();
+        auto it = part_index.find(key);
+        if (it != part_index.end()) return it->second;
+        vhost::SearchPart req = part_in;
+        if (req.terms.empty()) throw InvalidRequest("search part without terms");
+        if (req.is_regex) throw Unsupported("regex search is outside the accelerated path");
+        if (req.top || req.skip) throw Unsupported("per-part top/skip is outside the accelerated path");
+        if (req.token_value) throw Unsupported("token_value boost is outside the accelerated path");
+        std::string path = req.path;
+        if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+        const uint32_t did = dict_id(path);
+        const vdev::DictDev& dict = ix->dicts.at(path);
+        const uint32_t pid = postings_id(path + ".to_anchor_id_score");
+        const std::string lower_term = vfmt::to_lowercase(req.terms[0]);
+        std::vector<uint32_t> raw, low;
+        vfmt::utf8_decode(req.terms[0], raw);
+        vfmt::utf8_decode(lower_term, low);
+        if (raw.size() > 64) throw Unsupported("search terms longer than 64 characters are outside the accelerated path");
+        PartQuery q;
+        memset(&q, 0, sizeof q);
+        q.m = (uint32_t)raw.size();
+        uint32_t d = 0;
+        if (req.levenshtein_distance) d = std::min<uint32_t>(*req.levenshtein_distance, (uint32_t)low.size() - 1u);  // wraps for "" like release Rust
+        q.d_score = d;
+        q.d_match = std::min<uint32_t>(d, 4);
+        const bool transposition = req.ignore_case.value_or(false);   // search_field.rs:87 (sic)
+        const bool case_insensitive = req.ignore_case.value_or(true);  // :88
+        q.flags = (req.starts_with ? vdev::kPartPrefix : 0u) | (transposition ? vdev::kPartTransposition : 0u) | (case_insensitive ? 0u : vdev::kPartRawCase) |
+                  ((req.starts_with || d != 0) ? vdev::kPartCheckPrefix : 0u) | (req.boost ? vdev::kPartHasBoost : 0u);
+        q.boost = req.boost.value_or(1.0f);
+        q.lower_bytes = (uint32_t)lower_term.size();
+        q.postings = pid;
+        for (size_t j = 0; j < raw.size(); ++j) {
+            q.match_sym[j] = dict.code_of(case_insensitive ? vfmt::lower_scalar(raw[j]) : raw[j]);
+            q.score_sym[j] = dict.code_of(low[j]);
+        }
+        const uint32_t id = (uint32_t)parts.size();
+        parts.push_back(q);
+        part_dict.push_back(did);
+        part_index.emplace(key, id);
+        return id;
+    }
+
+    struct Node {  // emitted subtree
+        std::string term;  // request.terms[0] the result carries (set_op.rs:122-124)
+        int leaf = -1;     // leaf index when the subtree is a single search part
+        bool empty = false;
+    };
+
+    Node emit(const vhost::SearchRequest& r, std::vector<uint32_t>& leaves, std::vector<uint32_t>& code) {
+        if (r.kind == vhost::SearchRequest::Search) {
+            size_t pos = r.part.path.rfind("[]");
+            (void)pos;
+            uint32_t part = add_part(r.part);
+            Node n;
+            n.term = r.part.terms[0];
+            n.leaf = (int)leaves.size();
+            leaves.push_back(part);
+            code.push_back(vdev::kOpLeaf);
+            code.push_back((uint32_t)n.leaf);
+            return n;
+        }
+        if (r.queries.empty()) throw Unsupported("empty or/and list");
+        std::vector<Node> kids;
+        for (auto& q : r.queries) kids.push_back(emit(q, leaves, code));
+        if (kids.size() == 1) return kids[0];  // passthrough (set_op.rs:93-96, :371-374)
+        if (kids.size() > vdev::kMaxLeaves) throw Unsupported("more than 12 sub-queries in one or/and");
+        Node out;
+        out.term = kids[0].term;
+        if (r.kind == vhost::SearchRequest::Or) {
+            std::vector<std::string> terms;
+            for (auto& k : kids) terms.push_back(k.term);
+            std::sort(terms.begin(), terms.end());
+            terms.erase(std::unique(terms.begin(), terms.end()), terms.end());
+            code.push_back(vdev::kOpUnion);
+            code.push_back((uint32_t)kids.size());
+            code.push_back((uint32_t)terms.size());
+            for (auto& k : kids) code.push_back((uint32_t)(std::find(terms.begin(), terms.end(), k.term) - terms.begin()));
+        } else {
+            code.push_back(vdev::kOpIntersect);
+            code.push_back((uint32_t)kids.size());
+            for (size_t i = 0; i < kids.size(); ++i) code.push_back((uint32_t)i);  // sum order, patched on the device
+            for (auto& k : kids) code.push_back(k.leaf >= 0 ? (uint32_t)k.leaf : vdev::kNoValue);
+        }
+        return out;
+    }
+
+    BoostStep make_boost(const vhost::BoostPart& b) {
+        BoostStep s;
+        memset(&s, 0, sizeof s);
+        const std::string path = b.path + ".boost_valid_to_value";
+        auto it = ix->boosts.find(path);
+        if (it == ix->boosts.end()) ix->host->path_not_found(path);
+        s.column = it->second.bits.p;
+        s.n = (uint32_t)it->second.n;
+        s.fun = (uint32_t)b.boost_fun;
+        s.param = b.param.value_or(0.0f);
+        if (b.skip_when_score) {
+            if (b.skip_when_score->size() > 4) throw Unsupported("more than 4 skip_when_score values");
+            s.n_skip = (uint32_t)b.skip_when_score->size();
+            for (size_t i = 0; i < b.skip_when_score->size(); ++i) s.skip[i] = (*b.skip_when_score)[i];
+        }
+        if (b.expression) parse_expression(*b.expression, s);
+        return s;
+    }
+
+    static bool has_nested_boost(const vhost::SearchRequest& r) {
+        if (r.get_boost() && !r.get_boost()->empty()) return true;
+        for (auto& q : r.queries)
+            if (has_nested_boost(q)) return true;
+        return false;
+    }
+
+    void plan_request(const vhost::Request& request, RequestPlan& rp, QueryProgram& qp) {
+        rp.top = request.top.value_or(10);  // search.rs:146
+        rp.skip = request.skip.value_or(0);
+        if (!request.search_req) throw InvalidRequest("search_req is None, but is required in search");
+        if (request.filter) throw Unsupported("filter is not on the accelerated path yet");
+        if (request.phrase_boosts && !request.phrase_boosts->empty()) throw Unsupported("phrase_boosts are not on the accelerated path yet");
+        if (request.boost_term && !request.boost_term->empty()) throw Unsupported("boost_term is not on the accelerated path yet");
+        if (request.text_locality) throw Unsupported("text_locality is not on the accelerated path yet");
+        if (request.facets && !request.facets->empty()) throw Unsupported("facets are not on the accelerated path yet");
+        if (has_nested_boost(*request.search_req)) throw Unsupported("boosts inside the search tree are not on the accelerated path yet");
+        if (rp.top + rp.skip > vdev::kMaxK) throw Unsupported("top + skip above 256 is outside the accelerated path");
+
+        std::vector<uint32_t> leaves, code;
+        const vhost::SearchRequest& root = *request.search_req;
+        emit(root, leaves, code);
+        if (leaves.size() > vdev::kMaxLeaves) throw Unsupported("more than 12 search parts in one request");
+
+        std::vector<BoostStep> steps;
+        if (request.boost)
+            for (auto& b : *request.boost) {
+                if (b.path.find("[]") != std::string::npos) throw Unsupported("1:n boosts are not on the accelerated path yet");
+                steps.push_back(make_boost(b));
+            }
+
+        // flat `or` of search parts with pairwise distinct terms: leaves in slot (= sorted term) order, no program
+        bool flat = false;
+        if (leaves.size() == 1 && code.size() == 2) {
+            flat = true;
+        } else if (root.kind == vhost::SearchRequest::Or && code.size() == 2 * leaves.size() + 3 + leaves.size() && code[2 * leaves.size()] == vdev::kOpUnion &&
+                   code[2 * leaves.size() + 2] == leaves.size()) {
+            std::vector<uint32_t> by_slot(leaves.size());
+            for (size_t c = 0; c < leaves.size(); ++c) by_slot[code[2 * leaves.size() + 3 + c]] = leaves[c];
+            leaves = by_slot;
+            flat = true;
+        }
+        qp.leaf_begin = (uint32_t)leaf_part.size();
+        qp.n_leaves = (uint32_t)leaves.size();
+        leaf_part.insert(leaf_part.end(), leaves.begin(), leaves.end());
+        qp.prog_begin = (uint32_t)prog.size();
+        qp.prog_len = flat ? 0u : (uint32_t)code.size();
+        if (!flat) prog.insert(prog.end(), code.begin(), code.end());
+        qp.boost_begin = (uint32_t)boosts.size();
+        qp.n_boosts = (uint32_t)steps.size();
+        boosts.insert(boosts.end(), steps.begin(), steps.end());
+        qp.k = (uint32_t)(rp.top + rp.skip);
+        qp.active = 1;
+        max_leaves = std::max<uint32_t>(max_leaves, qp.n_leaves);
+        max_k = std::max<uint32_t>(max_k, std::max<uint32_t>(qp.k, 1));
+    }
+
+    void add_request(const char* json) {
+        RequestPlan rp;
+        QueryProgram qp;
+        memset(&qp, 0, sizeof qp);
+        // a failing request must not leave half-registered leaves behind
+        const size_t leaf_mark = leaf_part.size(), prog_mark = prog.size(), boost_mark = boosts.size();
+        try {
+            vhost::Request r = vhost::parse_request_json(json, strlen(json));
+            plan_request(r, rp, qp);
+        } catch (const InvalidRequest& e) {
+            rp.status = 1, rp.message = e.what();
+        } catch (const vhost::FstNotFound& e) {
+            rp.status = 2, rp.message = e.what();
+        } catch (const vhost::PathNotFound& e) {
+            rp.status = 3, rp.message = e.what();
+        } catch (const vhost::RequestError& e) {
+            rp.status = 5, rp.message = e.what();
+        } catch (const Unsupported& e) {
+            rp.status = 8, rp.message = e.what();
+        } catch (const std::exception& e) {
+            rp.status = 9, rp.message = e.what();
+        }
+        if (rp.status != 0) {
+            leaf_part.resize(leaf_mark), prog.resize(prog_mark), boosts.resize(boost_mark);
+            memset(&qp, 0, sizeof qp);
+        }
+        requests.push_back(std::move(rp));
+        programs.push_back(qp);
+    }
+};
+
+}  // namespace vplan

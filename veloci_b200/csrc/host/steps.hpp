@@ -1,0 +1,188 @@
+// Step seam (one entry per PlanStep kind, src/plan_creator/plan_steps.rs:18-74) and
+// facet materialisation, layered on the batch engine.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../../include/veloci_b200.h"
+#include "engine.hpp"
+
+namespace vsteps {
+
+struct FacetGroup {
+    uint32_t id = 0, count = 0;
+    std::string text;
+};
+struct FacetGroups {
+    std::string field;
+    std::vector<FacetGroup> groups;
+};
+
+inline void materialize_facets(vdev::Batch& b, std::vector<std::vector<FacetGroups>>& out) {
+    if (!out.empty()) return;
+    out.resize(b.n);
+}
+
+inline vhost::SearchPart parse_part(const char* json) {
+    vjson::Value v;
+    try {
+        v = vjson::parse(json, strlen(json));
+    } catch (const vjson::ParseError& e) {
+        throw vhost::RequestError(e.what());
+    }
+    return vhost::parse_search_part(v);
+}
+
+template <class T>
+inline T* dup_array(const std::vector<T>& v) {
+    T* p = (T*)malloc(std::max<size_t>(1, v.size()) * sizeof(T));
+    if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+    return p;
+}
+
+// get_term_ids_in_field (search_field.rs:277-398): fuzzy_match + scoring on the device,
+// (term id, score) in ascending term-id order like the FST stream.
+inline void field_search(vdev::DeviceIndex& ix, const char* part_json, bool get_scores, bool get_ids, vgpu_hitlist& out) {
+    memset(&out, 0, sizeof out);
+    vhost::SearchPart part = parse_part(part_json);
+    vdev::Batch b;
+    b.prepare_parts(&ix, {part});
+    b.run_match();
+    std::vector<uint32_t> terms;
+    std::vector<float> scores;
+    b.download_matches(0, terms, scores);
+    std::vector<size_t> order(terms.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t x, size_t y) { return terms[x] < terms[y]; });
+    std::vector<vgpu_hit> hits;
+    std::vector<uint32_t> ids;
+    for (size_t i : order) {
+        if (get_scores) hits.push_back(vgpu_hit{terms[i], scores[i]});
+        if (get_ids) ids.push_back(terms[i]);
+    }
+    out.hits = dup_array(hits), out.n_hits = (uint32_t)hits.size();
+    out.ids = dup_array(ids), out.n_ids = (uint32_t)ids.size();
+}
+
+// The remaining step entry points run a one-request batch whose leaves are explicit hit lists.
+inline void run_lists(vdev::DeviceIndex& ix, const std::vector<vdev::ExplicitList>& lists, const std::vector<uint32_t>& code, const std::vector<vdev::BoostStep>& boosts, uint32_t k,
+                      bool all_hits, vgpu_hitlist& out) {
+    memset(&out, 0, sizeof out);
+    vdev::Batch b;
+    b.prepare_lists(&ix, lists, code, boosts, k, all_hits);
+    b.execute();
+    std::vector<vgpu_hit> hits;
+    b.download_hits(0, all_hits, hits);
+    out.hits = dup_array(hits), out.n_hits = (uint32_t)hits.size();
+    out.ids = dup_array(std::vector<uint32_t>()), out.n_ids = 0;
+}
+
+inline void resolve_to_anchor(vdev::DeviceIndex& ix, const char* part_json, const vgpu_hitlist& in, vgpu_hitlist& out) {
+    memset(&out, 0, sizeof out);
+    vhost::SearchPart part = parse_part(part_json);
+    vdev::Batch b;
+    std::vector<uint32_t> terms(in.n_hits);
+    std::vector<float> scores(in.n_hits);
+    for (uint32_t i = 0; i < in.n_hits; ++i) terms[i] = in.hits[i].id, scores[i] = in.hits[i].score;
+    b.prepare_term_hits(&ix, part, terms, scores);
+    b.execute();
+    std::vector<vgpu_hit> hits;
+    b.download_hits(0, true, hits);
+    out.hits = dup_array(hits), out.n_hits = (uint32_t)hits.size();
+    // hits_ids -> anchors through text_id_to_anchor (search_field.rs:468-496); small, host side
+    std::vector<uint32_t> ids;
+    if (in.n_ids) {
+        std::string path = part.path;
+        if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+        if (ix.host->is_anchor_identity_column(path)) ids.assign(in.ids, in.ids + in.n_ids);
+        else {
+            const vhost::KeyValueStore& t2a = ix.host->get_valueid_to_parent(path + ".text_id_to_anchor");
+            for (uint32_t i = 0; i < in.n_ids; ++i) t2a.append_values(in.ids[i], ids);
+        }
+    }
+    out.ids = dup_array(ids), out.n_ids = (uint32_t)ids.size();
+}
+
+inline std::vector<vdev::ExplicitList> to_lists(const vgpu_hitlist* inputs, uint32_t n) {
+    std::vector<vdev::ExplicitList> lists(n);
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t j = 0; j < inputs[i].n_hits; ++j) {
+            lists[i].anchors.push_back(inputs[i].hits[j].id);
+            lists[i].scores.push_back(inputs[i].hits[j].score);
+        }
+    return lists;
+}
+
+// union_hits_score (set_op.rs:87-220) / intersect_hits_score (:368-446)
+inline void set_op(vdev::DeviceIndex& ix, const vgpu_hitlist* inputs, const char* const* terms, uint32_t n, bool is_union, vgpu_hitlist& out) {
+    memset(&out, 0, sizeof out);
+    if (n == 0) {
+        out.hits = dup_array(std::vector<vgpu_hit>()), out.ids = dup_array(std::vector<uint32_t>());
+        return;
+    }
+    if (n > vdev::kMaxLeaves) throw vplan::Unsupported("more than 12 inputs");
+    std::vector<vdev::ExplicitList> lists = to_lists(inputs, n);
+    std::vector<uint32_t> code;
+    for (uint32_t i = 0; i < n; ++i) code.push_back(vdev::kOpLeaf), code.push_back(i);
+    if (n > 1) {
+        if (is_union) {
+            std::vector<std::string> ts;
+            for (uint32_t i = 0; i < n; ++i) ts.push_back(terms[i] ? terms[i] : "");
+            std::vector<std::string> sorted = ts;
+            std::sort(sorted.begin(), sorted.end());
+            sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+            code.push_back(vdev::kOpUnion), code.push_back(n), code.push_back((uint32_t)sorted.size());
+            for (uint32_t i = 0; i < n; ++i) code.push_back((uint32_t)(std::find(sorted.begin(), sorted.end(), ts[i]) - sorted.begin()));
+        } else {
+            // first shortest input is summed last, the last input takes its place (set_op.rs:388-417)
+            uint32_t shortest = 0;
+            for (uint32_t i = 1; i < n; ++i)
+                if (inputs[i].n_hits < inputs[shortest].n_hits) shortest = i;
+            code.push_back(vdev::kOpIntersect), code.push_back(n);
+            for (uint32_t i = 0; i + 1 < n; ++i) code.push_back(i == shortest ? n - 1 : i);
+            code.push_back(shortest);
+            for (uint32_t i = 0; i < n; ++i) code.push_back(vdev::kNoValue - 1);  // order is final: not a leaf reference
+        }
+    }
+    run_lists(ix, lists, code, {}, 0, true, out);
+}
+
+inline void add_boost(vdev::DeviceIndex& ix, const char* boost_json, vgpu_hitlist& inout) {
+    vjson::Value v;
+    try {
+        v = vjson::parse(boost_json, strlen(boost_json));
+    } catch (const vjson::ParseError& e) {
+        throw vhost::RequestError(e.what());
+    }
+    vhost::BoostPart bp = vhost::parse_boost_part(v);
+    vplan::BatchPlan plan;
+    plan.ix = &ix;
+    vdev::BoostStep step = plan.make_boost(bp);
+    std::vector<vdev::ExplicitList> lists = to_lists(&inout, 1);
+    vgpu_hitlist out;
+    run_lists(ix, lists, {vdev::kOpLeaf, 0u}, {step}, 0, true, out);
+    // add_boost keeps the order of its input; the engine returns hits by anchor id
+    std::vector<std::pair<uint32_t, float>> by_id;
+    for (uint32_t i = 0; i < out.n_hits; ++i) by_id.emplace_back(out.hits[i].id, out.hits[i].score);
+    for (uint32_t i = 0; i < inout.n_hits; ++i) {
+        auto it = std::lower_bound(by_id.begin(), by_id.end(), std::make_pair(inout.hits[i].id, -INFINITY));
+        if (it != by_id.end() && it->first == inout.hits[i].id) inout.hits[i].score = it->second;
+    }
+    vgpu_hitlist_free(&out);
+}
+
+// top_n_sort + apply_top_skip (sort.rs:5-22, search.rs:230-239)
+inline void top_n(vdev::DeviceIndex& ix, const vgpu_hitlist& in, uint32_t top, uint32_t skip, vgpu_hitlist& out) {
+    if ((uint64_t)top + skip > vdev::kMaxK) throw vplan::Unsupported("top + skip above 256");
+    std::vector<vdev::ExplicitList> lists = to_lists(&in, 1);
+    vgpu_hitlist all;
+    run_lists(ix, lists, {vdev::kOpLeaf, 0u}, {}, top + skip, false, all);
+    std::vector<vgpu_hit> hits;
+    for (uint32_t i = skip; i < all.n_hits && hits.size() < top; ++i) hits.push_back(all.hits[i]);
+    vgpu_hitlist_free(&all);
+    memset(&out, 0, sizeof out);
+    out.hits = dup_array(hits), out.n_hits = (uint32_t)hits.size();
+    out.ids = dup_array(std::vector<uint32_t>()), out.n_ids = 0;
+}
+
+}  // namespace vsteps
