@@ -148,6 +148,8 @@ int32_t vgpu_top_n(vgpu_index* idx, const vgpu_hitlist* in, uint32_t top, uint32
 uint64_t vgpu_launch_count(void);
 int32_t vgpu_batch_phase_ms(const vgpu_batch* batch, float* ms, uint32_t n_phases);
 int32_t vgpu_batch_traffic_model(const vgpu_batch* batch, uint64_t* posting_bytes, uint64_t* boost_bytes, uint64_t* postings, uint64_t* union_hits);
+/* Bytes copied host->device by prepare (plan tables) and device->host by execute + fetch. */
+int32_t vgpu_batch_io_bytes(const vgpu_batch* batch, uint64_t* h2d, uint64_t* d2h);
 
 #ifdef __cplusplus
 }

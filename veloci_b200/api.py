@@ -78,6 +78,7 @@ def load_library():
     L.vgpu_launch_count.restype = u64
     L.vgpu_batch_phase_ms.argtypes = [vp, P(ctypes.c_float), u32]
     L.vgpu_batch_traffic_model.argtypes = [vp, P(u64), P(u64), P(u64), P(u64)]
+    L.vgpu_batch_io_bytes.argtypes = [vp, P(u64), P(u64)]
     _LIB = L
     return L
 
@@ -193,6 +194,11 @@ class Batch:
         a, b, c, d = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
         _check(self.L.vgpu_batch_traffic_model(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
         return {"posting_bytes": a.value, "boost_bytes": b.value, "postings": c.value, "union_hits": d.value}
+
+    def io_bytes(self):
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        _check(self.L.vgpu_batch_io_bytes(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return {"h2d": a.value, "d2h": b.value}
 
     def close(self):
         if self.h:

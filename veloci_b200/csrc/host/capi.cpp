@@ -281,4 +281,11 @@ int32_t vgpu_batch_traffic_model(const vgpu_batch* batch_c, uint64_t* posting_by
     });
 }
 
+int32_t vgpu_batch_io_bytes(const vgpu_batch* batch, uint64_t* h2d, uint64_t* d2h) {
+    if (!batch) return VGPU_ERR_INVALID_REQUEST;
+    if (h2d) *h2d = batch->b.h2d_bytes;
+    if (d2h) *d2h = batch->b.d2h_bytes;
+    return VGPU_OK;
+}
+
 }  // extern "C"

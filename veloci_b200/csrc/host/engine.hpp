@@ -76,6 +76,7 @@ struct Batch {
     std::vector<uint64_t> h_keys, h_hits;
     float phase_ms[kPhases] = {};
     uint64_t stat_postings = 0, stat_matches = 0, stat_union = 0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
 
     Batch() = default;
     Batch(const Batch&) = delete;
@@ -222,7 +223,9 @@ struct Batch {
         if (mode == kRequests)
             for (uint32_t p = 0; p < n_parts; ++p) parts_of_dict[plan.part_dict[p]].push_back(p);
         d_parts_of_dict.resize(parts_of_dict.size());
-        for (size_t d = 0; d < parts_of_dict.size(); ++d) d_parts_of_dict[d].upload(parts_of_dict[d]);
+        for (size_t d = 0; d < parts_of_dict.size(); ++d) d_parts_of_dict[d].upload(parts_of_dict[d]), h2d_bytes += parts_of_dict[d].size() * 4;
+        h2d_bytes += plan.parts.size() * sizeof(PartQuery) + (plan.part_dict.size() + plan.leaf_part.size() + plan.prog.size()) * 4 + plan.programs.size() * sizeof(QueryProgram) +
+                     plan.boosts.size() * sizeof(BoostStep) + dv.size() * sizeof(DictView) + pv.size() * sizeof(PostingsView);
 
         d_counters.alloc(8);
         d_part_count.alloc(n_parts + 1);
@@ -250,6 +253,7 @@ struct Batch {
         T v;
         VDEV_CUDA(cudaMemcpyAsync(&v, dev, sizeof(T), cudaMemcpyDeviceToHost, stream));
         VDEV_CUDA(cudaStreamSynchronize(stream));
+        d2h_bytes += sizeof(T);
         return v;
     }
 
@@ -317,6 +321,7 @@ struct Batch {
     void execute() {
         VDEV_CUDA(cudaSetDevice(ix->device));
         executed = false, fetched = false;
+        d2h_bytes = 0;
         uint32_t M = 0;
         if (mode != kLists) {
             run_match();
@@ -397,6 +402,7 @@ struct Batch {
             VDEV_CUDA(cudaMemcpyAsync(stats, d_counters.p, sizeof stats, cudaMemcpyDeviceToHost, stream));
             VDEV_CUDA(cudaStreamSynchronize(stream));
             stat_postings = stats[2];
+            d2h_bytes += h_keys.size() * 8 + h_hits.size() * 8 + sizeof stats;
             stat_union = 0;
             for (uint64_t h : h_hits) stat_union += h;
         }
