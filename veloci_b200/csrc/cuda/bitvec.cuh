@@ -36,18 +36,25 @@ VB_HD uint64_t eq_mask(const uint16_t* qsym, uint32_t m, uint16_t c) {
     return eq;
 }
 
-struct State {
-    uint64_t vp, vn;     // vertical +1 / -1 deltas of the current column
-    uint64_t d0, eq;     // previous column's diagonal-zero vector and Eq (transposition)
-    uint32_t score;      // D[m][columns consumed]
-    uint32_t cols;       // columns consumed
-    uint32_t best;       // min over consumed columns (incl. column 0) of D[m][.]  (prefix mode)
+template <class W>
+struct StateT {
+    W vp, vn;        // vertical +1 / -1 deltas of the current column
+    W d0, eq;        // previous column's diagonal-zero vector and Eq (transposition)
+    uint32_t score;  // D[m][columns consumed]
+    uint32_t cols;   // columns consumed
+    uint32_t best;   // min over consumed columns (incl. column 0) of D[m][.]  (prefix mode)
 };
+typedef StateT<uint64_t> State;
 
-VB_HD uint64_t low_mask(uint32_t m) { return m >= 64 ? ~0ull : ((1ull << m) - 1ull); }
+template <class W>
+VB_HD W low_mask_t(uint32_t m) {
+    return m >= sizeof(W) * 8 ? ~(W)0 : (((W)1 << m) - (W)1);
+}
+VB_HD uint64_t low_mask(uint32_t m) { return low_mask_t<uint64_t>(m); }
 
-VB_HD void init(State& s, uint32_t m) {
-    s.vp = low_mask(m);
+template <class W>
+VB_HD void init(StateT<W>& s, uint32_t m) {
+    s.vp = low_mask_t<W>(m);
     s.vn = 0;
     s.d0 = 0;
     s.eq = 0;
@@ -57,23 +64,24 @@ VB_HD void init(State& s, uint32_t m) {
 }
 
 // Consumes one dictionary symbol whose Eq mask is `eq`.
-VB_HD void step(State& s, uint64_t eq, uint32_t m, bool transposition) {
+template <class W>
+VB_HD void step(StateT<W>& s, W eq, uint32_t m, bool transposition) {
     s.cols += 1;
     if (m == 0) {
         s.score = s.cols;
         return;
     }
-    const uint64_t mask = low_mask(m);
-    uint64_t x = eq | s.vn;
-    uint64_t d0 = ((((x & s.vp) + s.vp) ^ s.vp) | x) & mask;
+    const W mask = low_mask_t<W>(m);
+    W x = eq | s.vn;
+    W d0 = ((((x & s.vp) + s.vp) ^ s.vp) | x) & mask;
     if (transposition) d0 |= (((~s.d0) & eq) << 1) & s.eq;
     d0 &= mask;
-    uint64_t hn = s.vp & d0;
-    uint64_t hp = (s.vn | ~(s.vp | d0)) & mask;
-    const uint64_t top = 1ull << (m - 1);
+    W hn = s.vp & d0;
+    W hp = (s.vn | ~(s.vp | d0)) & mask;
+    const W top = (W)1 << (m - 1);
     s.score += (hp & top) ? 1u : 0u;
     s.score -= (hn & top) ? 1u : 0u;
-    uint64_t xh = (hp << 1) | 1ull;  // row 0 grows by one per column (global distance)
+    W xh = (hp << 1) | (W)1;  // row 0 grows by one per column (global distance)
     s.vn = xh & d0 & mask;
     s.vp = ((hn << 1) | ~(xh | d0)) & mask;
     s.d0 = d0;
@@ -83,10 +91,11 @@ VB_HD void step(State& s, uint64_t eq, uint32_t m, bool transposition) {
 
 // min over the cells of the current column: D[0] = cols, D[j] = D[j-1] + vp_j - vn_j.
 // No extension of the consumed prefix can end below this value.
-VB_HD uint32_t column_min(const State& s, uint32_t m) {
+template <class W>
+VB_HD uint32_t column_min(const StateT<W>& s, uint32_t m) {
     int32_t v = (int32_t)s.cols, best = (int32_t)s.cols;
     for (uint32_t j = 0; j < m; ++j) {
-        v += (int32_t)((s.vp >> j) & 1ull) - (int32_t)((s.vn >> j) & 1ull);
+        v += (int32_t)((s.vp >> j) & 1) - (int32_t)((s.vn >> j) & 1);
         best = v < best ? v : best;
     }
     return (uint32_t)best;

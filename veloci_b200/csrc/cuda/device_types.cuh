@@ -94,6 +94,10 @@ struct BoostStep {  // add_boost on anchor ids (boost.rs:470-504, apply_boost :2
     uint32_t expr_op;       // `x op y` expression, operands: $SCORE (= boost value) or a float
     uint32_t expr_left_is_score, expr_right_is_score;
     float expr_left, expr_right;
+    // upper bound of the multiplier this step can apply (Log10/Log2/Multiply over a non-negative column):
+    // lets the tile kernel skip the gather for anchors that cannot reach the running k-th best
+    uint32_t can_prune;
+    float max_mult;
 };
 
 struct QueryProgram {

@@ -23,18 +23,43 @@ namespace vdev {
 // verifies the tile with one term per lane.
 static const int kPartChunk = 64;
 static const int kFuzzyThreads = 256;
+static const int kPeqCodes = 128;  // Eq masks of the first 128 alphabet codes come from a shared-memory table
 
+template <class W>
 struct PartLite {
+    W peq[kPeqCodes];
     uint16_t sym[64];
-    uint32_t m, d, flags, pad;
+    uint32_t m, d, flags, id;
 };
 
+template <class W>
+__device__ __forceinline__ W eq_of(const PartLite<W>& q, uint16_t c) {
+    if (c < kPeqCodes) return q.peq[c];
+    W eq = 0;
+    for (uint32_t j = 0; j < q.m; ++j) eq |= (W)(q.sym[j] == c) << j;
+    return eq;
+}
+
+template <class W>
+__device__ __forceinline__ W shfl_word(W v, int src);
+template <>
+__device__ __forceinline__ uint32_t shfl_word<uint32_t>(uint32_t v, int src) {
+    return __shfl_sync(0xFFFFFFFFu, v, src);
+}
+template <>
+__device__ __forceinline__ uint64_t shfl_word<uint64_t>(uint64_t v, int src) {
+    return __shfl_sync(0xFFFFFFFFu, (unsigned long long)v, src);
+}
+
+// W = uint32_t when every query of the launch has at most 32 scalars (the usual case), else uint64_t.
+template <class W, int CHUNK>
 __global__ void __launch_bounds__(kFuzzyThreads) fuzzy_match_kernel(DictView dict, const PartQuery* __restrict__ parts, const uint32_t* __restrict__ part_ids, uint32_t n_parts,
                                                                     MatchRecord* __restrict__ out, uint32_t capacity, unsigned long long* __restrict__ counter) {
-    __shared__ PartLite sp[kPartChunk];
-    __shared__ uint32_t sp_id[kPartChunk];
-    const uint32_t chunk_begin = blockIdx.y * kPartChunk;
-    const uint32_t chunk_n = min((uint32_t)kPartChunk, n_parts - chunk_begin);
+    extern __shared__ __align__(16) unsigned char fuzzy_smem[];
+    PartLite<W>* sp = reinterpret_cast<PartLite<W>*>(fuzzy_smem);
+    const uint32_t chunk_begin = blockIdx.y * CHUNK;
+    const uint32_t chunk_n = min((uint32_t)CHUNK, n_parts - chunk_begin);
+    for (uint32_t i = threadIdx.x; i < chunk_n * kPeqCodes; i += blockDim.x) sp[i / kPeqCodes].peq[i % kPeqCodes] = 0;
     for (uint32_t i = threadIdx.x; i < chunk_n * 64; i += blockDim.x) {
         uint32_t p = i / 64, j = i % 64;
         sp[p].sym[j] = parts[part_ids[chunk_begin + p]].match_sym[j];
@@ -44,8 +69,12 @@ __global__ void __launch_bounds__(kFuzzyThreads) fuzzy_match_kernel(DictView dic
         sp[p].m = q.m;
         sp[p].d = q.d_match;
         sp[p].flags = q.flags;
-        sp_id[p] = part_ids[chunk_begin + p];
+        sp[p].id = part_ids[chunk_begin + p];
     }
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < chunk_n; p += blockDim.x)  // one thread per part: no atomics needed
+        for (uint32_t j = 0; j < sp[p].m; ++j)
+            if (sp[p].sym[j] < kPeqCodes) sp[p].peq[sp[p].sym[j]] |= (W)1 << j;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31u;
@@ -53,39 +82,46 @@ __global__ void __launch_bounds__(kFuzzyThreads) fuzzy_match_kernel(DictView dic
     if (warp_tile0 >= dict.n_tiles) return;
     const uint32_t my_tile = warp_tile0 + lane;
     const bool have_tile = my_tile < dict.n_tiles;
-    TilePrefix pfx[2];
-    pfx[0].len = 0, pfx[1].len = 0;
+    TilePrefix pfx0, pfx1;
+    pfx0.len = 0, pfx1.len = 0;
     if (have_tile) {
-        pfx[0] = dict.tiles[0][my_tile];
-        pfx[1] = dict.tiles[1][my_tile];
+        pfx0 = dict.tiles[0][my_tile];
+        pfx1 = dict.tiles[1][my_tile];
     }
 
     for (uint32_t p = 0; p < chunk_n; ++p) {
-        const PartLite& q = sp[p];
+        const PartLite<W>& q = sp[p];
         const uint32_t m = q.m, d = q.d;
         const bool prefix_mode = q.flags & kPartPrefix, transposition = q.flags & kPartTransposition;
         const int variant = (q.flags & kPartRawCase) ? 1 : 0;
         bool viable = false;
+        vbit::StateT<W> s;
+        vbit::init(s, m);
+        uint32_t plen = 0;
         if (have_tile) {
-            const TilePrefix& t = pfx[variant];
-            vbit::State s;
-            vbit::init(s, m);
-            for (uint32_t i = 0; i < t.len; ++i) vbit::step(s, vbit::eq_mask(q.sym, m, t.sym[i]), m, transposition);
+            plen = variant ? pfx1.len : pfx0.len;
+#pragma unroll
+            for (uint32_t i = 0; i < kTilePrefixMax; ++i)
+                if (i < plen) vbit::step(s, eq_of(q, variant ? pfx1.sym[i] : pfx0.sym[i]), m, transposition);
             viable = (prefix_mode && s.best <= d) || vbit::column_min(s, m) <= d;
         }
         uint32_t todo = __ballot_sync(0xFFFFFFFFu, viable);
         while (todo) {
-            const uint32_t b = __ffs(todo) - 1;
+            const int b = __ffs(todo) - 1;
             todo &= todo - 1;
+            // every term of tile b starts with the tile prefix: continue from lane b's state
+            vbit::StateT<W> t;
+            t.vp = shfl_word<W>(s.vp, b), t.vn = shfl_word<W>(s.vn, b), t.d0 = shfl_word<W>(s.d0, b), t.eq = shfl_word<W>(s.eq, b);
+            t.score = __shfl_sync(0xFFFFFFFFu, s.score, b), t.cols = __shfl_sync(0xFFFFFFFFu, s.cols, b), t.best = __shfl_sync(0xFFFFFFFFu, s.best, b);
+            const uint32_t skip = __shfl_sync(0xFFFFFFFFu, plen, b);
             const uint32_t slot = (warp_tile0 + b) * kDictTile + lane;
             bool match = false;
             if (slot < dict.n) {
-                const uint16_t* ts = dict.sym[variant] + dict.off[variant][slot];
-                const uint32_t n = dict.off[variant][slot + 1] - dict.off[variant][slot];
-                vbit::State s;
-                vbit::init(s, m);
-                for (uint32_t i = 0; i < n; ++i) vbit::step(s, vbit::eq_mask(q.sym, m, ts[i]), m, transposition);
-                match = prefix_mode ? (s.best <= d) : (s.score <= d);
+                const uint32_t o = dict.off[variant][slot];
+                const uint16_t* ts = dict.sym[variant] + o;
+                const uint32_t n = dict.off[variant][slot + 1] - o;
+                for (uint32_t i = skip; i < n; ++i) vbit::step(t, eq_of(q, ts[i]), m, transposition);
+                match = prefix_mode ? (t.best <= d) : (t.score <= d);
             }
             const uint32_t mm = __ballot_sync(0xFFFFFFFFu, match);
             if (mm) {
@@ -94,18 +130,30 @@ __global__ void __launch_bounds__(kFuzzyThreads) fuzzy_match_kernel(DictView dic
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
                 if (match) {
                     unsigned long long at = base + __popc(mm & ((1u << lane) - 1u));
-                    if (at < capacity) out[at] = MatchRecord{sp_id[p], slot};
+                    if (at < capacity) out[at] = MatchRecord{q.id, slot};
                 }
             }
         }
     }
 }
 
-void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* parts, const uint32_t* part_ids, uint32_t n_parts, MatchRecord* out, uint32_t capacity,
-                        unsigned long long* counter) {
+void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* parts, const uint32_t* part_ids, uint32_t n_parts, uint32_t max_m, MatchRecord* out,
+                        uint32_t capacity, unsigned long long* counter) {
     if (n_parts == 0 || dict.n == 0) return;
-    dim3 grid((dict.n_tiles + kFuzzyThreads - 1) / kFuzzyThreads, (n_parts + kPartChunk - 1) / kPartChunk);
-    fuzzy_match_kernel<<<grid, kFuzzyThreads, 0, st>>>(dict, parts, part_ids, n_parts, out, capacity, counter);
+    const unsigned gx = (dict.n_tiles + kFuzzyThreads - 1) / kFuzzyThreads;
+    if (max_m <= 32) {
+        const size_t smem = sizeof(PartLite<uint32_t>) * kPartChunk;
+        static bool once = false;
+        if (!once) cudaFuncSetAttribute(fuzzy_match_kernel<uint32_t, kPartChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), once = true;
+        dim3 grid(gx, (n_parts + kPartChunk - 1) / kPartChunk);
+        fuzzy_match_kernel<uint32_t, kPartChunk><<<grid, kFuzzyThreads, smem, st>>>(dict, parts, part_ids, n_parts, out, capacity, counter);
+    } else {
+        const size_t smem = sizeof(PartLite<uint64_t>) * (kPartChunk / 2);
+        static bool once = false;
+        if (!once) cudaFuncSetAttribute(fuzzy_match_kernel<uint64_t, kPartChunk / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), once = true;
+        dim3 grid(gx, (n_parts + kPartChunk / 2 - 1) / (kPartChunk / 2));
+        fuzzy_match_kernel<uint64_t, kPartChunk / 2><<<grid, kFuzzyThreads, smem, st>>>(dict, parts, part_ids, n_parts, out, capacity, counter);
+    }
     count_launch();
 }
 

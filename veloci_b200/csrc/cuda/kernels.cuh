@@ -12,8 +12,8 @@ void count_launch();          // bumps the library-wide kernel launch counter
 uint64_t launches_so_far();
 
 // ---- fuzzy.cu ----
-void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* parts, const uint32_t* part_ids, uint32_t n_parts, MatchRecord* out, uint32_t capacity,
-                        unsigned long long* counter);
+void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* parts, const uint32_t* part_ids, uint32_t n_parts, uint32_t max_m, MatchRecord* out,
+                        uint32_t capacity, unsigned long long* counter);
 void launch_group_count(cudaStream_t st, const MatchRecord* rec, uint32_t n, uint32_t* part_count);
 void launch_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, uint32_t n);
 void launch_scan_u64(cudaStream_t st, const uint64_t* in, uint64_t* out, uint32_t n);

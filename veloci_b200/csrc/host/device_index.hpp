@@ -163,6 +163,8 @@ struct CsrDev {  // id -> list<u32>
 struct ColumnDev {  // boost column
     size_t n = 0;
     DevBuf<uint32_t> bits;
+    bool non_negative = true;  // every stored value is a non-negative, non-NaN float
+    float vmax = 0.0f;
 };
 
 struct PhraseDev {
@@ -357,7 +359,13 @@ struct DeviceIndex {
         std::vector<uint32_t> bits(n, kNoValue);
         for (size_t id = 0; id < n; ++id) {
             uint32_t v;
-            if (s.get_value(id, v)) bits[id] = v;
+            if (s.get_value(id, v)) {
+                bits[id] = v;
+                float f;
+                memcpy(&f, &v, 4);
+                if (!(f >= 0.0f)) c.non_negative = false;
+                else if (f > c.vmax) c.vmax = f;
+            }
         }
         c.n = n;
         c.bits.upload(bits);

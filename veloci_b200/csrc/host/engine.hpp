@@ -47,6 +47,7 @@ struct Batch {
     DevBuf<PostingsView> d_postings;
     std::vector<std::vector<uint32_t>> parts_of_dict;
     std::vector<DevBuf<uint32_t>> d_parts_of_dict;
+    std::vector<uint32_t> max_m_of_dict;
     // device: match phase
     DevBuf<MatchRecord> d_records;
     DevBuf<unsigned long long> d_counters;  // [0] matches, [1] work counter, [2] stat postings, [3] dense rows, [4] emitted hits
@@ -222,6 +223,9 @@ struct Batch {
         parts_of_dict.assign(plan.dict_names.size(), {});
         if (mode == kRequests)
             for (uint32_t p = 0; p < n_parts; ++p) parts_of_dict[plan.part_dict[p]].push_back(p);
+        max_m_of_dict.assign(plan.dict_names.size(), 0);
+        for (size_t d = 0; d < parts_of_dict.size(); ++d)
+            for (uint32_t p : parts_of_dict[d]) max_m_of_dict[d] = std::max(max_m_of_dict[d], plan.parts[p].m);
         d_parts_of_dict.resize(parts_of_dict.size());
         for (size_t d = 0; d < parts_of_dict.size(); ++d) d_parts_of_dict[d].upload(parts_of_dict[d]), h2d_bytes += parts_of_dict[d].size() * 4;
         h2d_bytes += plan.parts.size() * sizeof(PartQuery) + (plan.part_dict.size() + plan.leaf_part.size() + plan.prog.size()) * 4 + plan.programs.size() * sizeof(QueryProgram) +
@@ -267,7 +271,7 @@ struct Batch {
                 VDEV_CUDA(cudaMemsetAsync(d_counters.p, 0, d_counters.bytes(), stream));
                 for (size_t d = 0; d < parts_of_dict.size(); ++d) {
                     const DictDev& dict = ix->dicts.at(plan.dict_names[d]);
-                    launch_fuzzy_match(stream, dict.view(), d_parts.p, d_parts_of_dict[d].p, (uint32_t)parts_of_dict[d].size(), d_records.p,
+                    launch_fuzzy_match(stream, dict.view(), d_parts.p, d_parts_of_dict[d].p, (uint32_t)parts_of_dict[d].size(), max_m_of_dict[d], d_records.p,
                                        (uint32_t)std::min<size_t>(d_records.n, 0xFFFFFFFFu), d_counters.p);
                 }
                 n_match = read_back(d_counters.p);

@@ -4,6 +4,7 @@
 // searched once per *batch* (FieldRequestCache, :13,91-130, widened from one request
 // to the whole batch), anchor-level boosts are chained after the root (:175-189).
 #pragma once
+#include <cmath>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -217,6 +218,24 @@ struct BatchPlan {
             for (size_t i = 0; i < b.skip_when_score->size(); ++i) s.skip[i] = (*b.skip_when_score)[i];
         }
         if (b.expression) parse_expression(*b.expression, s);
+        // upper bound of the multiplier (used by the tile kernel to skip hopeless anchors)
+        s.can_prune = 0, s.max_mult = 0.0f;
+        const vdev::ColumnDev& col = it->second;
+        if (!b.expression && s.n_skip == 0 && col.non_negative && s.param >= 0.0f && std::isfinite(s.param) && std::isfinite(col.vmax)) {
+            float m = 0.0f;
+            bool ok = true;
+            switch (b.boost_fun) {
+                case vhost::BoostFun::Log10: m = log10f(col.vmax + s.param); break;
+                case vhost::BoostFun::Log2: m = log2f(col.vmax + s.param); break;
+                case vhost::BoostFun::Multiply: m = col.vmax + s.param; break;
+                default: ok = false; break;
+            }
+            if (ok && std::isfinite(m)) {
+                m = m + fabsf(m) * 1e-6f + 1e-30f;  // device log10f/log2f may differ from the host's by a few ulp
+                s.can_prune = 1;
+                s.max_mult = std::max(m, 1.0f);  // anchors without a boost value keep their score
+            }
+        }
         return s;
     }
 
