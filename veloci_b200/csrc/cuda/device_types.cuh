@@ -74,6 +74,22 @@ struct PartSlices {
     uint64_t sparse_base; // first sparse entry of the part
 };
 
+// ---- non-empty (tile, request) work items and their posting slices (item_scan_kernel -> tile_eval_kernel) ----
+struct ItemRec {  // 24 B
+    uint32_t q, t;
+    unsigned long long slice_begin;
+    uint32_t n_slices, npost;
+};
+struct SliceRec {  // 24 B
+    unsigned long long begin;  // dense: first posting (index into the PostingsView arrays); sparse: first bucket entry
+    uint32_t n;
+    float term_score;          // dense: score of the matched term
+    uint16_t leaf;
+    uint8_t kind;              // 0 dense posting slice, 1 sparse bucket slice
+    uint8_t single;            // the part has exactly one matched term: plain stores suffice
+    uint32_t postings;         // PostingsView index (dense)
+};
+
 // ---- request programs (plan_creator, execution_plan.rs:132-534) ----
 enum ProgOp : uint32_t {
     kOpLeaf = 1,       // [op, leaf index]

@@ -83,7 +83,28 @@ void launch_part_slices(cudaStream_t st, PartSlices* out, const uint32_t* part_b
 void launch_finalize_programs(cudaStream_t st, const QueryProgram* queries, uint32_t n, uint32_t* prog, const uint32_t* leaf_part, const unsigned long long* part_est);
 
 // ---- tiles.cu ----
+struct ItemScanArgs {
+    const QueryProgram* queries;
+    uint32_t n_queries;
+    const uint32_t* leaf_part;
+    const PartSlices* slices;
+    const PartQuery* parts;
+    const uint32_t* g_row;
+    const uint64_t* g_begin;
+    const float* g_score;
+    const uint32_t* toff;
+    const uint32_t* bucket;
+    uint32_t n_tiles;
+    unsigned long long n_items_total;  // n_tiles * n_queries
+    unsigned long long* counters;      // [0] items, [1] slices (zeroed before each pass)
+    ItemRec* items;
+    SliceRec* slice_recs;
+};
+void launch_item_scan(cudaStream_t st, const ItemScanArgs& a, bool fill);
+
 struct TileArgs {
+    const ItemRec* items;
+    const SliceRec* slice_recs;
     // batch programs
     const QueryProgram* queries;
     uint32_t n_queries;

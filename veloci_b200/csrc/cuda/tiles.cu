@@ -9,19 +9,21 @@
 //   top_n_sort                src/search/sort.rs:5-22, order src/search.rs:123-130 (score desc, id desc)
 //
 // Posting lists are anchor-sorted, so the part of a list that falls into an anchor
-// tile is one contiguous slice: the CTA streams those slices with coalesced loads
-// and scatters score keys into one shared-memory array per search part (direct
-// mapped: index = anchor - tile start, so no sorting and no hashing collisions).
-// A dense list touches every anchor at most once, so its scatter needs no atomics;
-// only the pre-bucketed sparse lists use shared-memory atomicMax.  The epilogue
-// walks the tile once: tree evaluation, boost column gather (coalesced, the tile
-// is a contiguous range of the column), hit count, and a threshold test against
-// the request's running k-th best; the few survivors are merged into the
-// request's top-k heap in global memory under a per-request lock.
+// tile is one contiguous slice.  item_scan_kernel finds, for every (tile, request),
+// the non-empty slices and writes them as flat records (tile-major); tile_eval_kernel
+// takes one record per CTA: it streams the slices with coalesced loads and scatters
+// score keys into one shared-memory array per search part (direct mapped: index =
+// anchor - tile start, so no sorting and no hash collisions).  The epilogue walks the
+// tile once -- four anchors per 128-bit shared load when the tile is densely hit,
+// posting-driven when it is sparsely hit -- and does the tree evaluation, the boost
+// column gather (coalesced: the tile is a contiguous range of the column), the hit
+// count and a threshold test against the request's running k-th best; the few
+// survivors are merged into the request's top-k heap in global memory under a
+// per-request lock.  The epilogue leaves the arrays zeroed for the next item.
 //
-// Work items are ordered tile-major (all requests of tile 0, then tile 1, ...), so
-// the posting slices of a tile are re-read from L2, not HBM, by the many requests
-// that share frequent terms.
+// Items are ordered tile-major (all requests of tile 0, then tile 1, ...), so the
+// posting slices of a tile are re-read from L2, not HBM, by the many requests that
+// share frequent terms.
 #include <cuda_fp16.h>
 
 #include "bitvec.cuh"
@@ -30,8 +32,102 @@
 namespace vdev {
 
 static const int kTileThreads = 512;
-static const uint32_t kSurvivorCap = 1024;
+static const uint32_t kSurvivorCap = 512;
+static const uint32_t kSliceChunk = 64;     // slice records staged in shared memory at a time
+static const uint32_t kTaskPostings = 128;  // postings one warp takes from a slice at a time
 
+// ---------------------------------------------------------------- item scan
+// One thread per (tile, request), tile-major.  Pass 0 counts the non-empty items and
+// their slices; pass 1 writes them.  Blocks reserve output ranges in index order, so
+// the item list stays (nearly) tile-major.
+template <bool FILL>
+__global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
+    __shared__ uint32_t s_warp_items[8], s_warp_slices[8];
+    __shared__ unsigned long long s_base_items, s_base_slices;
+    const unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t n_slices = 0, npost = 0, t = 0, q = 0;
+    QueryProgram qp;
+    qp.active = 0;
+    if (i < a.n_items_total) {
+        t = (uint32_t)(i / a.n_queries), q = (uint32_t)(i % a.n_queries);
+        qp = a.queries[q];
+    }
+    if (qp.active && qp.n_leaves) {
+        for (uint32_t l = 0; l < qp.n_leaves; ++l) {
+            const PartSlices ps = a.slices[a.leaf_part[qp.leaf_begin + l]];
+            for (uint32_t r = 0; r < ps.n_dense; ++r) {
+                const uint32_t* trow = a.toff + (size_t)a.g_row[ps.m_begin + r] * (a.n_tiles + 1);
+                const uint32_t n = trow[t + 1] - trow[t];
+                npost += n, n_slices += n ? 1u : 0u;
+            }
+            if (ps.n_match != ps.n_dense) {
+                const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
+                const uint32_t n = brow[t + 1] - brow[t];
+                npost += n, n_slices += n ? 1u : 0u;
+            }
+        }
+    }
+    // block-ordered reservation: exclusive prefix of (items, slices) over the block
+    const uint32_t has = npost ? 1u : 0u;
+    uint32_t xi = has, xs = n_slices;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t yi = __shfl_up_sync(0xFFFFFFFFu, xi, o), ys = __shfl_up_sync(0xFFFFFFFFu, xs, o);
+        if ((int)lane >= o) xi += yi, xs += ys;
+    }
+    if (lane == 31) s_warp_items[warp] = xi, s_warp_slices[warp] = xs;
+    __syncthreads();
+    uint32_t wi = 0, ws = 0, ti = 0, ts = 0;
+    for (uint32_t w = 0; w < 8; ++w) {
+        if (w < warp) wi += s_warp_items[w], ws += s_warp_slices[w];
+        ti += s_warp_items[w], ts += s_warp_slices[w];
+    }
+    if (threadIdx.x == 0) {
+        s_base_items = ti ? atomicAdd(a.counters + 0, (unsigned long long)ti) : 0ull;
+        s_base_slices = ts ? atomicAdd(a.counters + 1, (unsigned long long)ts) : 0ull;
+    }
+    if (!FILL) return;
+    __syncthreads();
+    if (!has) return;
+    const unsigned long long item_at = s_base_items + wi + xi - has;
+    unsigned long long slice_at = s_base_slices + ws + xs - n_slices;
+    ItemRec rec;
+    rec.q = q, rec.t = t, rec.slice_begin = slice_at, rec.n_slices = n_slices, rec.npost = npost;
+    a.items[item_at] = rec;
+    for (uint32_t l = 0; l < qp.n_leaves; ++l) {
+        const uint32_t part = a.leaf_part[qp.leaf_begin + l];
+        const PartSlices ps = a.slices[part];
+        for (uint32_t r = 0; r < ps.n_dense; ++r) {
+            const uint32_t mi = ps.m_begin + r;
+            const uint32_t* trow = a.toff + (size_t)a.g_row[mi] * (a.n_tiles + 1);
+            const uint32_t s = trow[t], e = trow[t + 1];
+            if (e == s) continue;
+            SliceRec sr;
+            sr.begin = a.g_begin[mi] + s, sr.n = e - s, sr.term_score = a.g_score[mi];
+            sr.leaf = (uint16_t)l, sr.kind = 0, sr.single = ps.n_match == 1 ? 1 : 0, sr.postings = a.parts[part].postings;
+            a.slice_recs[slice_at++] = sr;
+        }
+        if (ps.n_match != ps.n_dense) {
+            const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
+            const uint32_t s = brow[t], e = brow[t + 1];
+            if (e == s) continue;
+            SliceRec sr;
+            sr.begin = ps.sparse_base + s, sr.n = e - s, sr.term_score = 0.0f;
+            sr.leaf = (uint16_t)l, sr.kind = 1, sr.single = 0, sr.postings = 0;
+            a.slice_recs[slice_at++] = sr;
+        }
+    }
+}
+
+void launch_item_scan(cudaStream_t st, const ItemScanArgs& a, bool fill) {
+    if (!a.n_items_total) return;
+    const unsigned blocks = (unsigned)((a.n_items_total + 255) / 256);
+    if (fill) item_scan_kernel<true><<<blocks, 256, 0, st>>>(a);
+    else item_scan_kernel<false><<<blocks, 256, 0, st>>>(a);
+    count_launch();
+}
+
+// ---------------------------------------------------------------- per-anchor evaluation
 __device__ __forceinline__ float apply_boost_step(const BoostStep& b, float score, float v) {
     const float x = v + b.param;
     switch (b.fun) {
@@ -198,16 +294,21 @@ __device__ __forceinline__ uint32_t eval_idx(const TileArgs& a, const ItemCtx& c
     return 1;
 }
 
+// ---------------------------------------------------------------- tile evaluation
 __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
     extern __shared__ __align__(16) uint32_t arr[];  // [max_leaves][tile], all zero between items
-    __shared__ unsigned long long s_item;
+    __shared__ ItemRec s_item[2];
+    __shared__ unsigned long long s_item_idx[2];
+    __shared__ SliceRec s_slice[kSliceChunk];
+    __shared__ uint32_t s_task_begin[kSliceChunk + 1];  // warp tasks: exclusive prefix of ceil(n / kTaskPostings)
     __shared__ uint32_t s_npresent, s_nsurv;
     __shared__ unsigned long long s_list[kSurvivorCap];
     __shared__ unsigned long long s_heap[kMaxK];
     __shared__ unsigned long long s_out[kMaxK];
     __shared__ uint32_t s_claim[1024];  // one bit per anchor of the tile (tiles up to 2^15)
 
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n_warps = kTileThreads / 32;
     const uint32_t tile = 1u << a.tile_log2;
     unsigned long long cta_postings = 0;  // thread 0 only
     {
@@ -215,82 +316,39 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
         const uint32_t n4 = (a.max_leaves * tile) >> 2;
         for (uint32_t i = tid; i < n4; i += kTileThreads) p4[i] = make_uint4(0u, 0u, 0u, 0u);
     }
+    if (tid == 0) {
+        const unsigned long long first = atomicAdd(a.work_counter, 1ull);
+        s_item_idx[0] = first;
+        if (first < a.n_items) s_item[0] = a.items[first];
+    }
+    uint32_t parity = 0;
 
     while (true) {
-        __syncthreads();  // everyone is done with the previous item's shared state
-        if (tid == 0) s_item = atomicAdd(a.work_counter, 1ull), s_npresent = 0, s_nsurv = 0;
-        __syncthreads();
-        const unsigned long long item = s_item;
-        if (item >= a.n_items) break;
-        const uint32_t t = (uint32_t)(item / a.n_queries), q = (uint32_t)(item % a.n_queries);
+        __syncthreads();  // previous item fully retired; s_item[parity] is ready
+        const unsigned long long item_idx = s_item_idx[parity];
+        if (item_idx >= a.n_items) break;
+        const ItemRec it = s_item[parity];
+        if (tid == 32) {  // prefetch the next item while this one is processed
+            const unsigned long long nxt = atomicAdd(a.work_counter, 1ull);
+            s_item_idx[parity ^ 1] = nxt;
+            if (nxt < a.n_items) s_item[parity ^ 1] = a.items[nxt];
+        }
+        if (tid == 0) s_npresent = 0, s_nsurv = 0, cta_postings += it.npost;
+        parity ^= 1;
+
+        const uint32_t t = it.t, q = it.q;
         ItemCtx c;
         c.qp = a.queries[q];
-        if (!c.qp.active || c.qp.n_leaves == 0) continue;
         const QueryProgram& qp = c.qp;
         const uint32_t L = qp.n_leaves;
         const uint64_t tile_base64 = (uint64_t)a.anchor_lo + ((uint64_t)t << a.tile_log2);
         const uint32_t tile_base = (uint32_t)tile_base64;
         const uint32_t tile_n = (uint32_t)min((uint64_t)tile, (uint64_t)a.anchor_hi - tile_base64);
         c.tile = tile, c.tile_base = tile_base;
-
-        // (0) how many postings of this request fall into the tile (uniform across the CTA)
-        uint32_t max_dense = 0, npost = 0;
-        for (uint32_t l = 0; l < L; ++l) {
-            const PartSlices ps = a.slices[a.leaf_part[qp.leaf_begin + l]];
-            max_dense = max(max_dense, ps.n_dense);
-            for (uint32_t r = 0; r < ps.n_dense; ++r) {
-                const uint32_t* trow = a.toff + (size_t)a.g_row[ps.m_begin + r] * (a.n_tiles + 1);
-                npost += trow[t + 1] - trow[t];
-            }
-            if (ps.n_match != ps.n_dense) {
-                const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
-                npost += brow[t + 1] - brow[t];
-            }
-        }
-        if (npost == 0) continue;  // nothing of this request lives in the tile
-        if (tid == 0) cta_postings += npost;
-        const bool sparse_mode = npost * 4u < tile_n;
+        const bool sparse_mode = it.npost * 4u < tile_n;
         if (sparse_mode)
             for (uint32_t i = tid; i < (tile >> 5); i += kTileThreads) s_claim[i] = 0;
-
-        // (1) dense slices, one round per rank so that a part array sees one list at a time
-        for (uint32_t r = 0; r < max_dense; ++r) {
-            for (uint32_t l = 0; l < L; ++l) {
-                const uint32_t part = a.leaf_part[qp.leaf_begin + l];
-                const PartSlices ps = a.slices[part];
-                if (r >= ps.n_dense) continue;
-                const uint32_t mi = ps.m_begin + r;
-                const uint32_t* trow = a.toff + (size_t)a.g_row[mi] * (a.n_tiles + 1);
-                const uint32_t s = trow[t], e = trow[t + 1];
-                const PostingsView& pv = a.postings[a.parts[part].postings];
-                const uint32_t* anchors = pv.anchors + a.g_begin[mi];
-                const uint16_t* scores = pv.scores + a.g_begin[mi];
-                const float term_score = a.g_score[mi];
-                uint32_t* dst = arr + l * tile;
-                const bool single = ps.n_match == 1;
-                for (uint32_t j = s + tid; j < e; j += kTileThreads) {
-                    const uint32_t idx = anchors[j] - tile_base;
-                    const float w = __half2float(__ushort_as_half(scores[j])) / 100.0f;  // el.score.to_f32() / 100.0 (:426)
-                    const uint32_t key = vbit::score_key(term_score * w);
-                    if (single) dst[idx] = key;
-                    else dst[idx] = max(dst[idx], key);
-                }
-            }
-            __syncthreads();
-        }
-        // (2) sparse buckets (several terms of a part may hit the same anchor: atomicMax)
-        for (uint32_t l = 0; l < L; ++l) {
-            const uint32_t part = a.leaf_part[qp.leaf_begin + l];
-            const PartSlices ps = a.slices[part];
-            if (ps.n_match == ps.n_dense) continue;
-            const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
-            const uint32_t s = brow[t], e = brow[t + 1];
-            uint32_t* dst = arr + l * tile;
-            for (uint32_t j = s + tid; j < e; j += kTileThreads) atomicMax(&dst[a.s_anchor[ps.sparse_base + j] - tile_base], a.s_key[ps.sparse_base + j]);
-        }
-        __syncthreads();
-
-        // (3) epilogue: tree, boosts, count, threshold; leaves the part arrays zeroed
+        // boost step and threshold: issued now, consumed after the scatter
         c.tau = __ldcg(a.tau + q);
         c.fast_boost = false, c.can_prune = false;
         c.col = nullptr, c.col_n = 0, c.fun = 0, c.param = 0.0f, c.max_mult = 0.0f;
@@ -302,80 +360,113 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
                 c.can_prune = bs.can_prune != 0 && !qp.emit_all && qp.k != 0 && c.tau != 0;
             }
         }
+
+        // (1) scatter: slices are staged in chunks; each warp takes runs of kTaskPostings postings of one slice
         uint32_t my_present = 0;
-        if (sparse_mode) {
-            // posting-driven: visit only the anchors that were touched; the claim bit makes each one count once
-            for (uint32_t l = 0; l < L; ++l) {
-                const uint32_t part = a.leaf_part[qp.leaf_begin + l];
-                const PartSlices ps = a.slices[part];
-                for (uint32_t r = 0; r < ps.n_dense; ++r) {
-                    const uint32_t mi = ps.m_begin + r;
-                    const uint32_t* trow = a.toff + (size_t)a.g_row[mi] * (a.n_tiles + 1);
-                    const uint32_t s = trow[t], e = trow[t + 1];
-                    const uint32_t* anchors = a.postings[a.parts[part].postings].anchors + a.g_begin[mi];
-                    for (uint32_t j = s + tid; j < e; j += kTileThreads) {
-                        const uint32_t idx = anchors[j] - tile_base;
-                        const uint32_t bit = 1u << (idx & 31u);
-                        if (!(atomicOr(&s_claim[idx >> 5], bit) & bit)) my_present += eval_idx(a, c, arr, idx, &s_nsurv, s_list);
+        for (int pass = 0; pass < (sparse_mode ? 2 : 1); ++pass) {
+            // pass 0 scatters; pass 1 (sparsely hit tiles only) is the posting-driven epilogue over the same slices
+            for (uint32_t sb = 0; sb < it.n_slices; sb += kSliceChunk) {
+                const uint32_t ns = min(kSliceChunk, it.n_slices - sb);
+                if (it.n_slices > kSliceChunk || pass == 0) {
+                    __syncthreads();
+                    if (tid < ns) s_slice[tid] = a.slice_recs[it.slice_begin + sb + tid];
+                    __syncthreads();
+                    if (tid == 0) {
+                        uint32_t acc = 0;
+                        for (uint32_t i = 0; i < ns; ++i) s_task_begin[i] = acc, acc += (s_slice[i].n + kTaskPostings - 1) / kTaskPostings;
+                        s_task_begin[ns] = acc;
                     }
                 }
-                if (ps.n_match != ps.n_dense) {
-                    const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
-                    const uint32_t s = brow[t], e = brow[t + 1];
-                    for (uint32_t j = s + tid; j < e; j += kTileThreads) {
-                        const uint32_t idx = a.s_anchor[ps.sparse_base + j] - tile_base;
-                        const uint32_t bit = 1u << (idx & 31u);
-                        if (!(atomicOr(&s_claim[idx >> 5], bit) & bit)) my_present += eval_idx(a, c, arr, idx, &s_nsurv, s_list);
-                    }
-                }
-            }
-        } else if (qp.prog_len == 0 && L <= 4) {
-            // vector sweep: four anchors per step, untouched groups cost one 128-bit load per part
-            const uint32_t n_groups = tile >> 2;
-            for (uint32_t g = tid; g < n_groups; g += kTileThreads) {
-                uint4 v[4];
-                uint32_t any = 0;
-#pragma unroll
-                for (int l = 0; l < 4; ++l) {
-                    v[l] = (uint32_t)l < L ? reinterpret_cast<const uint4*>(arr + l * tile)[g] : make_uint4(0u, 0u, 0u, 0u);
-                    any |= v[l].x | v[l].y | v[l].z | v[l].w;
-                }
-                if (!any) continue;
-                uint32_t keep[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const uint32_t k0 = comp4(v[0], cc), k1 = comp4(v[1], cc), k2 = comp4(v[2], cc), k3 = comp4(v[3], cc);
-                    if (!(k0 | k1 | k2 | k3)) continue;
-                    float score;
-                    if (L == 1) score = vbit::key_score(k0);
-                    else {
-                        float nd = 0.0f, sum = 0.0f;
-                        const uint32_t ks[4] = {k0, k1, k2, k3};
-#pragma unroll
-                        for (int l = 0; l < 4; ++l) {
-                            const float x = ks[l] ? fmaxf(0.0f, vbit::key_score(ks[l])) : 0.0f;
-                            if (x >= 0.00001f) nd += 1.0f;
-                            sum += x;  // absent parts add +0.0: the sum over the request's own parts is unchanged
+                __syncthreads();
+                const uint32_t n_tasks = s_task_begin[ns];
+                uint32_t si = 0;
+                for (uint32_t task = warp; task < n_tasks; task += n_warps) {
+                    while (s_task_begin[si + 1] <= task) ++si;
+                    const SliceRec sr = s_slice[si];
+                    const uint32_t j0 = (task - s_task_begin[si]) * kTaskPostings, j1 = min(sr.n, j0 + kTaskPostings);
+                    uint32_t* dst = arr + (uint32_t)sr.leaf * tile;
+                    if (pass == 0) {
+                        if (sr.kind == 0) {
+                            const PostingsView& pv = a.postings[sr.postings];
+                            const uint32_t* anchors = pv.anchors + sr.begin;
+                            const uint16_t* scores = pv.scores + sr.begin;
+#pragma unroll 4
+                            for (uint32_t j = j0 + lane; j < j1; j += 32) {
+                                const uint32_t idx = anchors[j] - tile_base;
+                                const float w = __half2float(__ushort_as_half(scores[j])) / 100.0f;  // el.score.to_f32() / 100.0 (:426)
+                                const uint32_t key = vbit::score_key(sr.term_score * w);
+                                if (sr.single) dst[idx] = key;  // the only list of this part: anchors are unique
+                                else atomicMax(&dst[idx], key);
+                            }
+                        } else {
+                            const uint32_t* sa = a.s_anchor + sr.begin;
+                            const uint32_t* sk = a.s_key + sr.begin;
+#pragma unroll 4
+                            for (uint32_t j = j0 + lane; j < j1; j += 32) atomicMax(&dst[sa[j] - tile_base], sk[j]);
                         }
-                        score = sum * nd * nd;
+                    } else {
+                        const uint32_t* anchors = sr.kind == 0 ? a.postings[sr.postings].anchors + sr.begin : a.s_anchor + sr.begin;
+                        for (uint32_t j = j0 + lane; j < j1; j += 32) {
+                            const uint32_t idx = anchors[j] - tile_base;
+                            const uint32_t bit = 1u << (idx & 31u);
+                            if (!(atomicOr(&s_claim[idx >> 5], bit) & bit)) my_present += eval_idx(a, c, arr, idx, &s_nsurv, s_list);
+                        }
                     }
-                    ++my_present;
-                    keep[cc] = finish_anchor(a, c, tile_base + (g << 2) + cc, score, &s_nsurv, s_list);
                 }
-#pragma unroll
-                for (int l = 1; l < 4; ++l)
-                    if ((uint32_t)l < L && (v[l].x | v[l].y | v[l].z | v[l].w)) reinterpret_cast<uint4*>(arr + l * tile)[g] = make_uint4(0u, 0u, 0u, 0u);
-                reinterpret_cast<uint4*>(arr)[g] = make_uint4(keep[0], keep[1], keep[2], keep[3]);
             }
-        } else {
-            for (uint32_t idx = tid; idx < tile; idx += kTileThreads) my_present += eval_idx(a, c, arr, idx, &s_nsurv, s_list);
+            __syncthreads();
+        }
+
+        // (2) epilogue of densely hit tiles: tree, boosts, count, threshold; leaves the part arrays zeroed
+        if (!sparse_mode) {
+            if (qp.prog_len == 0 && L <= 4) {
+                // vector sweep: four anchors per step, untouched groups cost one 128-bit load per part
+                const uint32_t n_groups = tile >> 2;
+                for (uint32_t g = tid; g < n_groups; g += kTileThreads) {
+                    uint4 v[4];
+                    uint32_t any = 0;
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) {
+                        v[l] = (uint32_t)l < L ? reinterpret_cast<const uint4*>(arr + l * tile)[g] : make_uint4(0u, 0u, 0u, 0u);
+                        any |= v[l].x | v[l].y | v[l].z | v[l].w;
+                    }
+                    if (!any) continue;
+                    uint32_t keep[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const uint32_t k0 = comp4(v[0], cc), k1 = comp4(v[1], cc), k2 = comp4(v[2], cc), k3 = comp4(v[3], cc);
+                        if (!(k0 | k1 | k2 | k3)) continue;
+                        float score;
+                        if (L == 1) score = vbit::key_score(k0);
+                        else {
+                            float nd = 0.0f, sum = 0.0f;
+                            const uint32_t ks[4] = {k0, k1, k2, k3};
+#pragma unroll
+                            for (int l = 0; l < 4; ++l) {
+                                const float x = ks[l] ? fmaxf(0.0f, vbit::key_score(ks[l])) : 0.0f;
+                                if (x >= 0.00001f) nd += 1.0f;
+                                sum += x;  // absent parts add +0.0: the sum over the request's own parts is unchanged
+                            }
+                            score = sum * nd * nd;
+                        }
+                        ++my_present;
+                        keep[cc] = finish_anchor(a, c, tile_base + (g << 2) + cc, score, &s_nsurv, s_list);
+                    }
+#pragma unroll
+                    for (int l = 1; l < 4; ++l)
+                        if ((uint32_t)l < L && (v[l].x | v[l].y | v[l].z | v[l].w)) reinterpret_cast<uint4*>(arr + l * tile)[g] = make_uint4(0u, 0u, 0u, 0u);
+                    reinterpret_cast<uint4*>(arr)[g] = make_uint4(keep[0], keep[1], keep[2], keep[3]);
+                }
+            } else {
+                for (uint32_t idx = tid; idx < tile; idx += kTileThreads) my_present += eval_idx(a, c, arr, idx, &s_nsurv, s_list);
+            }
         }
         for (int o = 16; o > 0; o >>= 1) my_present += __shfl_xor_sync(0xFFFFFFFFu, my_present, o);
-        if ((tid & 31) == 0 && my_present) atomicAdd(&s_npresent, my_present);
+        if (lane == 0 && my_present) atomicAdd(&s_npresent, my_present);
         __syncthreads();
         if (tid == 0 && s_npresent) atomicAdd(a.num_hits + q, (unsigned long long)s_npresent);
 
-        // (4) merge survivors into the request's heap (sorted, k slots) under its lock
+        // (3) merge survivors into the request's heap (sorted, k slots) under its lock
         uint32_t nsurv = s_nsurv;
         const uint32_t k = qp.k;
         unsigned long long* heap = a.heap + (size_t)q * a.heap_stride;
@@ -434,9 +525,12 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
     if (tid == 0 && cta_postings) atomicAdd(a.stat_postings, cta_postings);
 }
 
+static const size_t kTileStaticSmem = 14 * 1024;  // static __shared__ of tile_eval_kernel, rounded up
+
 size_t tile_kernel_smem(uint32_t tile_log2, uint32_t max_leaves) {
+    if (tile_log2 > 15) return 0;
     size_t need = ((size_t)max_leaves << tile_log2) * sizeof(uint32_t);
-    return need <= 200 * 1024 ? need : 0;
+    return need + kTileStaticSmem <= 227 * 1024 ? need : 0;
 }
 
 void launch_tile_eval(cudaStream_t st, const TileArgs& a, int n_sms) {
@@ -444,7 +538,7 @@ void launch_tile_eval(cudaStream_t st, const TileArgs& a, int n_sms) {
     const size_t smem = tile_kernel_smem(a.tile_log2, a.max_leaves);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(tile_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(tile_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - kTileStaticSmem));
         configured = true;
     }
     int per_sm = 1;

@@ -63,6 +63,8 @@ struct Batch {
     DevBuf<uint32_t> d_toff, d_bucket, d_s_anchor, d_s_key;
     DevBuf<uint64_t> d_sparse_total, d_sparse_base;
     DevBuf<PartSlices> d_slices;
+    DevBuf<ItemRec> d_items;
+    DevBuf<SliceRec> d_slice_recs;
     // device: per-request state and results
     DevBuf<unsigned long long> d_heap, d_tau, d_num_hits;
     DevBuf<uint32_t> d_lock;
@@ -358,6 +360,26 @@ struct Batch {
             VDEV_CUDA(cudaEventRecord(ev[1], stream));
             VDEV_CUDA(cudaEventRecord(ev[2], stream));
         }
+        // non-empty (tile, request) items and their slices, tile-major
+        unsigned long long n_items = 0;
+        {
+            ItemScanArgs sc;
+            sc.queries = d_programs.p, sc.n_queries = n, sc.leaf_part = d_leaf_part.p, sc.slices = d_slices.p, sc.parts = d_parts.p;
+            sc.g_row = d_g_row.p, sc.g_begin = d_g_begin.p, sc.g_score = d_g_score.p, sc.toff = d_toff.p, sc.bucket = d_bucket.p;
+            sc.n_tiles = n_tiles, sc.n_items_total = (unsigned long long)n_tiles * n, sc.counters = d_counters.p + 5, sc.items = nullptr, sc.slice_recs = nullptr;
+            VDEV_CUDA(cudaMemsetAsync(d_counters.p + 5, 0, 16, stream));
+            launch_item_scan(stream, sc, false);
+            unsigned long long counts[2];
+            VDEV_CUDA(cudaMemcpyAsync(counts, d_counters.p + 5, 16, cudaMemcpyDeviceToHost, stream));
+            VDEV_CUDA(cudaStreamSynchronize(stream));
+            d2h_bytes += 16;
+            n_items = counts[0];
+            d_items.reserve((size_t)std::max<unsigned long long>(n_items, 1));
+            d_slice_recs.reserve((size_t)std::max<unsigned long long>(counts[1], 1));
+            sc.items = d_items.p, sc.slice_recs = d_slice_recs.p;
+            VDEV_CUDA(cudaMemsetAsync(d_counters.p + 5, 0, 16, stream));
+            launch_item_scan(stream, sc, true);
+        }
         VDEV_CUDA(cudaEventRecord(ev[3], stream));
         // ---- phase 3: tile evaluation
         VDEV_CUDA(cudaMemsetAsync(d_heap.p, 0, d_heap.bytes(), stream));
@@ -366,13 +388,14 @@ struct Batch {
         VDEV_CUDA(cudaMemsetAsync(d_lock.p, 0, d_lock.bytes(), stream));
         {
             TileArgs a;
+            a.items = d_items.p, a.slice_recs = d_slice_recs.p;
             a.queries = d_programs.p, a.n_queries = n, a.leaf_part = d_leaf_part.p, a.prog = d_prog.p, a.boosts = d_boosts.p;
             a.parts = d_parts.p, a.slices = d_slices.p, a.postings = d_postings.p, a.g_score = d_g_score.p, a.g_begin = d_g_begin.p, a.g_row = d_g_row.p, a.g_df = d_g_df.p;
             a.toff = d_toff.p, a.bucket = d_bucket.p, a.s_anchor = d_s_anchor.p, a.s_key = d_s_key.p;
             a.n_tiles = n_tiles, a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
             a.max_leaves = std::max<uint32_t>(1, plan.max_leaves);
             a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
-            a.work_counter = d_counters.p + 1, a.n_items = (unsigned long long)n_tiles * n, a.stat_postings = d_counters.p + 2;
+            a.work_counter = d_counters.p + 1, a.n_items = n_items, a.stat_postings = d_counters.p + 2;
             a.emit = d_emit.p, a.emit_count = d_counters.p + 4, a.emit_capacity = emit_capacity;
             launch_tile_eval(stream, a, n_sms);
         }
