@@ -25,11 +25,20 @@ struct DictView {
     const TilePrefix* tiles[2];
 };
 
+struct Posting {  // 8 B, one 64-bit load
+    uint32_t anchor;
+    float weight;  // AnchorScore.score.to_f32() / 100.0 (search_field.rs:426), exact: divided once at load
+};
+
 struct PostingsView {
-    const uint32_t* anchors;
-    const uint16_t* scores;
+    const Posting* post;
     const uint64_t* off;
     uint32_t n_terms;
+};
+
+struct SparseEntry {  // 8 B: one posting of a sparse (rarely matched) term, already scored
+    uint32_t anchor;
+    uint32_t key;  // score_key(term_score * weight)
 };
 
 struct CsrView {
@@ -80,15 +89,18 @@ struct ItemRec {  // 24 B
     unsigned long long slice_begin;
     uint32_t n_slices, npost;
 };
-struct SliceRec {  // 24 B
-    unsigned long long begin;  // dense: first posting (index into the PostingsView arrays); sparse: first bucket entry
+struct SliceRec {  // 32 B
+    unsigned long long begin;  // dense: first posting (index into the PostingsView array); sparse: first bucket entry
     uint32_t n;
     float term_score;          // dense: score of the matched term
+    uint32_t task_begin;       // warp tasks (runs of kTaskPostings postings) of the item before this slice
     uint16_t leaf;
     uint8_t kind;              // 0 dense posting slice, 1 sparse bucket slice
     uint8_t single;            // the part has exactly one matched term: plain stores suffice
     uint32_t postings;         // PostingsView index (dense)
+    uint32_t pad;
 };
+static const uint32_t kTaskPostings = 128;  // postings one warp takes from a slice at a time
 
 // ---- request programs (plan_creator, execution_plan.rs:132-534) ----
 enum ProgOp : uint32_t {
@@ -123,6 +135,7 @@ struct QueryProgram {
     uint32_t k;                     // top + skip (0: only count)
     uint32_t active;                // 0 = request failed on the host, skip
     uint32_t emit_all;              // step seam: also write every hit to the emit buffer
+    uint32_t nonneg;                // every part score of the request is >= 0 (no negative part boost): cheap key decode
 };
 
 }  // namespace vdev

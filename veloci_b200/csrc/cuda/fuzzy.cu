@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) dense_tile_offsets_kernel(DenseOffsetsArg
     const uint32_t row = blockIdx.x;
     const uint32_t mi = a.row_match[row];
     const PostingsView& pv = a.postings[a.parts[a.g_part[mi]].postings];
-    const uint32_t* anchors = pv.anchors + a.g_begin[mi];
+    const Posting* post = pv.post + a.g_begin[mi];
     const uint32_t df = a.g_df[mi];
     uint32_t* out = a.toff + (size_t)row * (a.n_tiles + 1);
     for (uint32_t t = threadIdx.x; t <= a.n_tiles; t += blockDim.x) {
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256) dense_tile_offsets_kernel(DenseOffsetsArg
             const uint32_t bound = (uint32_t)bound64;
             while (lo < hi) {
                 uint32_t mid = (lo + hi) >> 1;
-                if (anchors[mid] < bound) lo = mid + 1;
+                if (post[mid].anchor < bound) lo = mid + 1;
                 else hi = mid;
             }
         }
@@ -321,10 +321,10 @@ __global__ void sparse_count_kernel(SparseArgs a) {
     if (df == 0) return;
     const uint32_t part = a.g_part[mi];
     const PostingsView& pv = a.postings[a.parts[part].postings];
-    const uint32_t* anchors = pv.anchors + a.g_begin[mi];
+    const Posting* post = pv.post + a.g_begin[mi];
     uint32_t* row = a.bucket + (size_t)part * (a.n_tiles + 1);
     for (uint32_t j = lane; j < df; j += 32) {
-        uint32_t t = (anchors[j] - a.anchor_lo) >> a.tile_log2;
+        uint32_t t = (post[j].anchor - a.anchor_lo) >> a.tile_log2;
         atomicAdd(&row[t + 1], 1u);
     }
 }
@@ -375,18 +375,15 @@ __global__ void sparse_fill_kernel(SparseArgs a) {
     if (df == 0) return;
     const uint32_t part = a.g_part[mi];
     const PostingsView& pv = a.postings[a.parts[part].postings];
-    const uint32_t* anchors = pv.anchors + a.g_begin[mi];
-    const uint16_t* scores = pv.scores + a.g_begin[mi];
+    const Posting* post = pv.post + a.g_begin[mi];
     uint32_t* row = a.bucket + (size_t)part * (a.n_tiles + 1);
     const uint64_t base = a.sparse_base[part];
     const float term_score = a.g_score[mi];
     for (uint32_t j = lane; j < df; j += 32) {
-        const uint32_t anchor = anchors[j];
-        const uint32_t t = (anchor - a.anchor_lo) >> a.tile_log2;
+        const Posting p = post[j];
+        const uint32_t t = (p.anchor - a.anchor_lo) >> a.tile_log2;
         const uint64_t at = base + atomicAdd(&row[t + 1], 1u);
-        const float w = __half2float(__ushort_as_half(scores[j])) / 100.0f;  // el.score.to_f32() / 100.0 (:426)
-        a.s_anchor[at] = anchor;
-        a.s_key[at] = vbit::score_key(term_score * w);
+        a.sparse[at] = SparseEntry{p.anchor, vbit::score_key(term_score * p.weight)};  // hit.score * (el.score / 100.0) (:426)
     }
 }
 

@@ -69,8 +69,7 @@ struct SparseArgs {
     const PostingsView* postings;
     uint32_t* bucket;  // [n_parts][n_tiles + 1]
     const uint64_t* sparse_base;
-    uint32_t* s_anchor;
-    uint32_t* s_key;
+    SparseEntry* sparse;
     uint32_t n_tiles, tile_log2, anchor_lo;
 };
 void launch_sparse_count(cudaStream_t st, const SparseArgs& a);
@@ -121,8 +120,7 @@ struct TileArgs {
     const uint32_t* g_df;
     const uint32_t* toff;
     const uint32_t* bucket;
-    const uint32_t* s_anchor;
-    const uint32_t* s_key;
+    const SparseEntry* sparse;
     // geometry
     uint32_t n_tiles, tile_log2, anchor_lo, anchor_hi;
     uint32_t max_leaves;  // shared-memory arrays per CTA

@@ -34,7 +34,6 @@ namespace vdev {
 static const int kTileThreads = 512;
 static const uint32_t kSurvivorCap = 512;
 static const uint32_t kSliceChunk = 64;     // slice records staged in shared memory at a time
-static const uint32_t kTaskPostings = 128;  // postings one warp takes from a slice at a time
 
 // ---------------------------------------------------------------- item scan
 // One thread per (tile, request), tile-major.  Pass 0 counts the non-empty items and
@@ -94,6 +93,7 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
     ItemRec rec;
     rec.q = q, rec.t = t, rec.slice_begin = slice_at, rec.n_slices = n_slices, rec.npost = npost;
     a.items[item_at] = rec;
+    uint32_t task_at = 0;
     for (uint32_t l = 0; l < qp.n_leaves; ++l) {
         const uint32_t part = a.leaf_part[qp.leaf_begin + l];
         const PartSlices ps = a.slices[part];
@@ -103,8 +103,9 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
             const uint32_t s = trow[t], e = trow[t + 1];
             if (e == s) continue;
             SliceRec sr;
-            sr.begin = a.g_begin[mi] + s, sr.n = e - s, sr.term_score = a.g_score[mi];
-            sr.leaf = (uint16_t)l, sr.kind = 0, sr.single = ps.n_match == 1 ? 1 : 0, sr.postings = a.parts[part].postings;
+            sr.begin = a.g_begin[mi] + s, sr.n = e - s, sr.term_score = a.g_score[mi], sr.task_begin = task_at;
+            sr.leaf = (uint16_t)l, sr.kind = 0, sr.single = ps.n_match == 1 ? 1 : 0, sr.postings = a.parts[part].postings, sr.pad = 0;
+            task_at += (sr.n + kTaskPostings - 1) / kTaskPostings;
             a.slice_recs[slice_at++] = sr;
         }
         if (ps.n_match != ps.n_dense) {
@@ -112,8 +113,9 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
             const uint32_t s = brow[t], e = brow[t + 1];
             if (e == s) continue;
             SliceRec sr;
-            sr.begin = ps.sparse_base + s, sr.n = e - s, sr.term_score = 0.0f;
-            sr.leaf = (uint16_t)l, sr.kind = 1, sr.single = 0, sr.postings = 0;
+            sr.begin = ps.sparse_base + s, sr.n = e - s, sr.term_score = 0.0f, sr.task_begin = task_at;
+            sr.leaf = (uint16_t)l, sr.kind = 1, sr.single = 0, sr.postings = 0, sr.pad = 0;
+            task_at += (sr.n + kTaskPostings - 1) / kTaskPostings;
             a.slice_recs[slice_at++] = sr;
         }
     }
@@ -215,7 +217,8 @@ struct ItemCtx {
     bool fast_boost, can_prune;
     const uint32_t* col;
     uint32_t col_n, fun;
-    float param, max_mult;
+    float param;
+    float prune_below;  // scores below this cannot reach the k-th best even with the largest boost multiplier
 };
 
 // Everything after the request tree for one present anchor: boosts, threshold, survivor list.
@@ -224,10 +227,7 @@ __device__ __forceinline__ uint32_t finish_anchor(const TileArgs& a, const ItemC
     if (c.qp.n_boosts) {
         if (c.fast_boost) {
             // the boost can only shrink `score * max_mult`: skip the gather when even that cannot beat the k-th best so far
-            if (c.can_prune && score >= 0.0f) {
-                const float bound = score * c.max_mult;
-                if ((((unsigned long long)vbit::score_key(bound) << 32) | 0xFFFFFFFFull) <= c.tau) return 0;
-            }
+            if (c.can_prune && score < c.prune_below) return 0;
             if (anchor < c.col_n) {
                 const uint32_t bits = __ldg(c.col + anchor);
                 if (bits != kNoValue) {
@@ -295,12 +295,104 @@ __device__ __forceinline__ uint32_t eval_idx(const TileArgs& a, const ItemCtx& c
 }
 
 // ---------------------------------------------------------------- tile evaluation
+// Vector sweep of a densely hit tile for programs without a tree (one part, or a flat `or`
+// of L parts with distinct terms): four anchors per step, untouched groups cost one 128-bit
+// shared load per part.  NONNEG: every part score is >= 0, so a key decodes with one AND.
+template <int L, bool NONNEG>
+__device__ __forceinline__ uint32_t sweep_flat(const TileArgs& a, const ItemCtx& c, uint32_t* arr, uint32_t tid, uint32_t* s_nsurv, unsigned long long* s_list) {
+    const uint32_t tile = c.tile, n_groups = tile >> 2;
+    uint32_t present = 0;
+    for (uint32_t g = tid; g < n_groups; g += kTileThreads) {
+        uint4 v[L];
+        uint32_t any = 0;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            v[l] = reinterpret_cast<const uint4*>(arr + l * tile)[g];
+            any |= v[l].x | v[l].y | v[l].z | v[l].w;
+        }
+        if (!any) continue;
+        uint32_t keep[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            uint32_t ks[L], kor = 0;
+#pragma unroll
+            for (int l = 0; l < L; ++l) ks[l] = comp4(v[l], cc), kor |= ks[l];
+            if (!kor) continue;
+            float score;
+            if (L == 1) {
+                score = NONNEG ? __uint_as_float(ks[0] & 0x7FFFFFFFu) : vbit::key_score(ks[0]);
+            } else {
+                float nd = 0.0f, sum = 0.0f;
+#pragma unroll
+                for (int l = 0; l < L; ++l) {
+                    const float x = NONNEG ? __uint_as_float(ks[l] & 0x7FFFFFFFu) : (ks[l] ? fmaxf(0.0f, vbit::key_score(ks[l])) : 0.0f);
+                    if (x >= 0.00001f) nd += 1.0f;
+                    sum += x;
+                }
+                score = sum * nd * nd;
+            }
+            ++present;
+            keep[cc] = finish_anchor(a, c, c.tile_base + (g << 2) + cc, score, s_nsurv, s_list);
+        }
+#pragma unroll
+        for (int l = 1; l < L; ++l)
+            if (v[l].x | v[l].y | v[l].z | v[l].w) reinterpret_cast<uint4*>(arr + l * tile)[g] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(arr)[g] = make_uint4(keep[0], keep[1], keep[2], keep[3]);
+    }
+    return present;
+}
+
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
+
+// One warp task: postings [j0, j1) of slice `sr`.  pass 0 scatters score keys into the part array;
+// pass 1 (sparsely hit tiles) evaluates each touched anchor once (claim bit) straight from the arrays.
+__device__ __forceinline__ uint32_t run_task(const TileArgs& a, const ItemCtx& c, const SliceRec& sr, uint32_t local_task, int pass, uint32_t lane, uint32_t* arr,
+                                             uint32_t* s_claim, uint32_t* s_nsurv, unsigned long long* s_list) {
+    const uint32_t j0 = local_task * kTaskPostings, j1 = min(sr.n, j0 + kTaskPostings);
+    const uint32_t tile_base = c.tile_base;
+    uint32_t present = 0;
+    if (pass == 0) {
+        uint32_t* dst = arr + (uint32_t)sr.leaf * c.tile;
+        if (sr.kind == 0) {
+            const Posting* post = a.postings[sr.postings].post + sr.begin;
+            const float ts = sr.term_score;
+            if (sr.single) {  // the only list of this part: anchors are unique, plain stores
+#pragma unroll 4
+                for (uint32_t j = j0 + lane; j < j1; j += 32) {
+                    const Posting p = post[j];
+                    dst[p.anchor - tile_base] = vbit::score_key(ts * p.weight);  // hit.score * (el.score / 100.0) (:426)
+                }
+            } else {
+#pragma unroll 4
+                for (uint32_t j = j0 + lane; j < j1; j += 32) {
+                    const Posting p = post[j];
+                    atomicMax(&dst[p.anchor - tile_base], vbit::score_key(ts * p.weight));
+                }
+            }
+        } else {
+            const SparseEntry* se = a.sparse + sr.begin;
+#pragma unroll 4
+            for (uint32_t j = j0 + lane; j < j1; j += 32) {
+                const SparseEntry e = se[j];
+                atomicMax(&dst[e.anchor - tile_base], e.key);
+            }
+        }
+    } else {
+        for (uint32_t j = j0 + lane; j < j1; j += 32) {
+            const uint32_t anchor = sr.kind == 0 ? a.postings[sr.postings].post[sr.begin + j].anchor : a.sparse[sr.begin + j].anchor;
+            const uint32_t idx = anchor - tile_base;
+            const uint32_t bit = 1u << (idx & 31u);
+            if (!(atomicOr(&s_claim[idx >> 5], bit) & bit)) present += eval_idx(a, c, arr, idx, s_nsurv, s_list);
+        }
+    }
+    return present;
+}
+
 __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
     extern __shared__ __align__(16) uint32_t arr[];  // [max_leaves][tile], all zero between items
     __shared__ ItemRec s_item[2];
     __shared__ unsigned long long s_item_idx[2];
-    __shared__ SliceRec s_slice[kSliceChunk];
-    __shared__ uint32_t s_task_begin[kSliceChunk + 1];  // warp tasks: exclusive prefix of ceil(n / kTaskPostings)
+    __shared__ __align__(16) SliceRec s_slice[kSliceChunk];
     __shared__ uint32_t s_npresent, s_nsurv;
     __shared__ unsigned long long s_list[kSurvivorCap];
     __shared__ unsigned long long s_heap[kMaxK];
@@ -348,114 +440,89 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
         const bool sparse_mode = it.npost * 4u < tile_n;
         if (sparse_mode)
             for (uint32_t i = tid; i < (tile >> 5); i += kTileThreads) s_claim[i] = 0;
+        // slice records: up to 32 live in registers (one per lane, every warp has its own copy)
+        const bool reg_slices = it.n_slices <= 32;
+        SliceRec mine;
+        mine.task_begin = 0xFFFFFFFFu, mine.n = 0;
+        if (reg_slices && lane < it.n_slices) mine = a.slice_recs[it.slice_begin + lane];
         // boost step and threshold: issued now, consumed after the scatter
         c.tau = __ldcg(a.tau + q);
         c.fast_boost = false, c.can_prune = false;
-        c.col = nullptr, c.col_n = 0, c.fun = 0, c.param = 0.0f, c.max_mult = 0.0f;
+        c.col = nullptr, c.col_n = 0, c.fun = 0, c.param = 0.0f, c.prune_below = 0.0f;
         if (qp.n_boosts == 1) {
             const BoostStep& bs = a.boosts[qp.boost_begin];
             if (bs.n_skip == 0 && bs.expr_op == kExprNone) {
                 c.fast_boost = true;
-                c.col = bs.column, c.col_n = bs.n, c.fun = bs.fun, c.param = bs.param, c.max_mult = bs.max_mult;
-                c.can_prune = bs.can_prune != 0 && !qp.emit_all && qp.k != 0 && c.tau != 0;
+                c.col = bs.column, c.col_n = bs.n, c.fun = bs.fun, c.param = bs.param;
+                if (bs.can_prune != 0 && !qp.emit_all && qp.k != 0 && c.tau != 0 && bs.max_mult > 0.0f) {
+                    const float tau_score = vbit::key_score((uint32_t)(c.tau >> 32));
+                    if (tau_score > 1e-30f) {
+                        // score < prune_below  =>  fl(score * max_mult) < tau_score  (one part in 2^20 of slack for the roundings)
+                        c.prune_below = (tau_score / bs.max_mult) * 0.99999905f;
+                        c.can_prune = true;
+                    }
+                }
             }
         }
 
-        // (1) scatter: slices are staged in chunks; each warp takes runs of kTaskPostings postings of one slice
+        // (1) pass 0: scatter; pass 1 (sparsely hit tiles only): posting-driven epilogue over the same slices
         uint32_t my_present = 0;
-        for (int pass = 0; pass < (sparse_mode ? 2 : 1); ++pass) {
-            // pass 0 scatters; pass 1 (sparsely hit tiles only) is the posting-driven epilogue over the same slices
-            for (uint32_t sb = 0; sb < it.n_slices; sb += kSliceChunk) {
-                const uint32_t ns = min(kSliceChunk, it.n_slices - sb);
-                if (it.n_slices > kSliceChunk || pass == 0) {
+        const int n_pass = sparse_mode ? 2 : 1;
+        if (reg_slices) {
+            const int last = (int)it.n_slices - 1;
+            const uint32_t n_tasks = __shfl_sync(0xFFFFFFFFu, mine.task_begin, last) + (__shfl_sync(0xFFFFFFFFu, mine.n, last) + kTaskPostings - 1) / kTaskPostings;
+            for (int pass = 0; pass < n_pass; ++pass) {
+                for (uint32_t task = warp; task < n_tasks; task += n_warps) {
+                    const int si = __popc(__ballot_sync(0xFFFFFFFFu, mine.task_begin <= task)) - 1;
+                    SliceRec sr;
+                    sr.begin = shfl64(mine.begin, si);
+                    sr.n = __shfl_sync(0xFFFFFFFFu, mine.n, si);
+                    sr.term_score = __shfl_sync(0xFFFFFFFFu, mine.term_score, si);
+                    sr.task_begin = __shfl_sync(0xFFFFFFFFu, mine.task_begin, si);
+                    const uint32_t packed = __shfl_sync(0xFFFFFFFFu, (uint32_t)mine.leaf | ((uint32_t)mine.kind << 16) | ((uint32_t)mine.single << 24), si);
+                    sr.leaf = (uint16_t)(packed & 0xFFFFu), sr.kind = (uint8_t)((packed >> 16) & 0xFFu), sr.single = (uint8_t)(packed >> 24);
+                    sr.postings = __shfl_sync(0xFFFFFFFFu, mine.postings, si);
+                    my_present += run_task(a, c, sr, task - sr.task_begin, pass, lane, arr, s_claim, &s_nsurv, s_list);
+                }
+                __syncthreads();
+            }
+        } else {
+            for (int pass = 0; pass < n_pass; ++pass) {
+                for (uint32_t sb = 0; sb < it.n_slices; sb += kSliceChunk) {
+                    const uint32_t ns = min(kSliceChunk, it.n_slices - sb);
                     __syncthreads();
                     if (tid < ns) s_slice[tid] = a.slice_recs[it.slice_begin + sb + tid];
                     __syncthreads();
-                    if (tid == 0) {
-                        uint32_t acc = 0;
-                        for (uint32_t i = 0; i < ns; ++i) s_task_begin[i] = acc, acc += (s_slice[i].n + kTaskPostings - 1) / kTaskPostings;
-                        s_task_begin[ns] = acc;
+                    const uint32_t first_task = s_slice[0].task_begin;
+                    const uint32_t end_task = s_slice[ns - 1].task_begin + (s_slice[ns - 1].n + kTaskPostings - 1) / kTaskPostings;
+                    uint32_t si = 0;
+                    for (uint32_t task = first_task + warp; task < end_task; task += n_warps) {
+                        while (si + 1 < ns && s_slice[si + 1].task_begin <= task) ++si;
+                        const SliceRec sr = s_slice[si];
+                        my_present += run_task(a, c, sr, task - sr.task_begin, pass, lane, arr, s_claim, &s_nsurv, s_list);
                     }
                 }
                 __syncthreads();
-                const uint32_t n_tasks = s_task_begin[ns];
-                uint32_t si = 0;
-                for (uint32_t task = warp; task < n_tasks; task += n_warps) {
-                    while (s_task_begin[si + 1] <= task) ++si;
-                    const SliceRec sr = s_slice[si];
-                    const uint32_t j0 = (task - s_task_begin[si]) * kTaskPostings, j1 = min(sr.n, j0 + kTaskPostings);
-                    uint32_t* dst = arr + (uint32_t)sr.leaf * tile;
-                    if (pass == 0) {
-                        if (sr.kind == 0) {
-                            const PostingsView& pv = a.postings[sr.postings];
-                            const uint32_t* anchors = pv.anchors + sr.begin;
-                            const uint16_t* scores = pv.scores + sr.begin;
-#pragma unroll 4
-                            for (uint32_t j = j0 + lane; j < j1; j += 32) {
-                                const uint32_t idx = anchors[j] - tile_base;
-                                const float w = __half2float(__ushort_as_half(scores[j])) / 100.0f;  // el.score.to_f32() / 100.0 (:426)
-                                const uint32_t key = vbit::score_key(sr.term_score * w);
-                                if (sr.single) dst[idx] = key;  // the only list of this part: anchors are unique
-                                else atomicMax(&dst[idx], key);
-                            }
-                        } else {
-                            const uint32_t* sa = a.s_anchor + sr.begin;
-                            const uint32_t* sk = a.s_key + sr.begin;
-#pragma unroll 4
-                            for (uint32_t j = j0 + lane; j < j1; j += 32) atomicMax(&dst[sa[j] - tile_base], sk[j]);
-                        }
-                    } else {
-                        const uint32_t* anchors = sr.kind == 0 ? a.postings[sr.postings].anchors + sr.begin : a.s_anchor + sr.begin;
-                        for (uint32_t j = j0 + lane; j < j1; j += 32) {
-                            const uint32_t idx = anchors[j] - tile_base;
-                            const uint32_t bit = 1u << (idx & 31u);
-                            if (!(atomicOr(&s_claim[idx >> 5], bit) & bit)) my_present += eval_idx(a, c, arr, idx, &s_nsurv, s_list);
-                        }
-                    }
-                }
             }
-            __syncthreads();
         }
 
         // (2) epilogue of densely hit tiles: tree, boosts, count, threshold; leaves the part arrays zeroed
         if (!sparse_mode) {
             if (qp.prog_len == 0 && L <= 4) {
-                // vector sweep: four anchors per step, untouched groups cost one 128-bit load per part
-                const uint32_t n_groups = tile >> 2;
-                for (uint32_t g = tid; g < n_groups; g += kTileThreads) {
-                    uint4 v[4];
-                    uint32_t any = 0;
-#pragma unroll
-                    for (int l = 0; l < 4; ++l) {
-                        v[l] = (uint32_t)l < L ? reinterpret_cast<const uint4*>(arr + l * tile)[g] : make_uint4(0u, 0u, 0u, 0u);
-                        any |= v[l].x | v[l].y | v[l].z | v[l].w;
+                if (qp.nonneg) {
+                    switch (L) {
+                        case 1: my_present += sweep_flat<1, true>(a, c, arr, tid, &s_nsurv, s_list); break;
+                        case 2: my_present += sweep_flat<2, true>(a, c, arr, tid, &s_nsurv, s_list); break;
+                        case 3: my_present += sweep_flat<3, true>(a, c, arr, tid, &s_nsurv, s_list); break;
+                        default: my_present += sweep_flat<4, true>(a, c, arr, tid, &s_nsurv, s_list); break;
                     }
-                    if (!any) continue;
-                    uint32_t keep[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        const uint32_t k0 = comp4(v[0], cc), k1 = comp4(v[1], cc), k2 = comp4(v[2], cc), k3 = comp4(v[3], cc);
-                        if (!(k0 | k1 | k2 | k3)) continue;
-                        float score;
-                        if (L == 1) score = vbit::key_score(k0);
-                        else {
-                            float nd = 0.0f, sum = 0.0f;
-                            const uint32_t ks[4] = {k0, k1, k2, k3};
-#pragma unroll
-                            for (int l = 0; l < 4; ++l) {
-                                const float x = ks[l] ? fmaxf(0.0f, vbit::key_score(ks[l])) : 0.0f;
-                                if (x >= 0.00001f) nd += 1.0f;
-                                sum += x;  // absent parts add +0.0: the sum over the request's own parts is unchanged
-                            }
-                            score = sum * nd * nd;
-                        }
-                        ++my_present;
-                        keep[cc] = finish_anchor(a, c, tile_base + (g << 2) + cc, score, &s_nsurv, s_list);
+                } else {
+                    switch (L) {
+                        case 1: my_present += sweep_flat<1, false>(a, c, arr, tid, &s_nsurv, s_list); break;
+                        case 2: my_present += sweep_flat<2, false>(a, c, arr, tid, &s_nsurv, s_list); break;
+                        case 3: my_present += sweep_flat<3, false>(a, c, arr, tid, &s_nsurv, s_list); break;
+                        default: my_present += sweep_flat<4, false>(a, c, arr, tid, &s_nsurv, s_list); break;
                     }
-#pragma unroll
-                    for (int l = 1; l < 4; ++l)
-                        if ((uint32_t)l < L && (v[l].x | v[l].y | v[l].z | v[l].w)) reinterpret_cast<uint4*>(arr + l * tile)[g] = make_uint4(0u, 0u, 0u, 0u);
-                    reinterpret_cast<uint4*>(arr)[g] = make_uint4(keep[0], keep[1], keep[2], keep[3]);
                 }
             } else {
                 for (uint32_t idx = tid; idx < tile; idx += kTileThreads) my_present += eval_idx(a, c, arr, idx, &s_nsurv, s_list);

@@ -8,8 +8,9 @@
 //       (lower-cased and, if any term has upper case, raw), u32 symbol offsets,
 //       term ids, and one 20-byte common-prefix record per tile of 32 terms.
 //   token -> anchor postings (`*.to_anchor_id_score`, token_to_anchor_score_vint.rs:128-204)
-//       CSR: u64 offsets per term id, u32 anchors (ascending), u16 scores (the f16
-//       bit pattern of AnchorScore, persistence_score/mod.rs:7-17)  = 6 B/posting.
+//       CSR: u64 offsets per term id, then 8-byte postings (u32 anchor ascending, f32
+//       weight = f16 score / 100, the f16 round trip of AnchorScore applied at load,
+//       persistence_score/mod.rs:7-17): one 64-bit load per posting, no divide in the kernel.
 //       With anchor-range shards only the postings of [anchor_lo, anchor_hi) are kept.
 //   id -> ids stores (`Indirect`, `SingleArrayPacked`; indirect.rs:10-89, single_array.rs:93-147)
 //       CSR u32 offsets + u32 values (vint decoded at load).
@@ -109,6 +110,26 @@ inline uint16_t f32_to_f16_bits(float f) {
     return (uint16_t)(sign | v);
 }
 
+// f16 bit pattern -> f32 (half::f16::to_f32, exact)
+inline float f16_bits_to_f32(uint16_t h) {
+    uint32_t hs = (uint32_t)(h & 0x8000u) << 16, he = (h >> 10) & 0x1Fu, hm = h & 0x3FFu, out;
+    if (he == 0) {
+        if (hm == 0) out = hs;
+        else {
+            int e = -1;
+            do {
+                hm <<= 1;
+                e++;
+            } while (!(hm & 0x400u));
+            out = hs | ((uint32_t)(127 - 15 - e) << 23) | ((hm & 0x3FFu) << 13);
+        }
+    } else if (he == 31) out = hs | 0x7F800000u | (hm << 13);
+    else out = hs | ((he + 112) << 23) | (hm << 13);
+    float r;
+    memcpy(&r, &out, 4);
+    return r;
+}
+
 struct SymbolSet {  // one case variant of a dictionary
     DevBuf<uint16_t> sym;
     DevBuf<uint32_t> off;  // n + 1
@@ -147,9 +168,8 @@ struct PostingsDev {
     size_t n_terms = 0;
     uint64_t n_postings = 0;
     DevBuf<uint64_t> off;
-    DevBuf<uint32_t> anchors;
-    DevBuf<uint16_t> scores;
-    PostingsView view() const { return PostingsView{anchors.p, scores.p, off.p, (uint32_t)n_terms}; }
+    DevBuf<Posting> post;
+    PostingsView view() const { return PostingsView{post.p, off.p, (uint32_t)n_terms}; }
 };
 
 struct CsrDev {  // id -> list<u32>
@@ -298,15 +318,16 @@ struct DeviceIndex {
         });
         for (size_t i = 0; i < n; ++i) off[i + 1] += off[i];
         const uint64_t total = off[n];
-        std::vector<uint32_t> anchors(total);
-        std::vector<uint16_t> scores(total);
+        std::vector<Posting> post(total);
         parallel_terms([&](size_t a, size_t b) {
             for (size_t id = a; id < b; ++id) {
                 uint64_t at = off[id];
                 v.for_each((uint32_t)id, [&](uint32_t anchor, uint32_t raw) {
                     if (all || (anchor >= lo && anchor < hi)) {
-                        anchors[at] = anchor;
-                        scores[at] = f32_to_f16_bits((float)raw);
+                        post[at].anchor = anchor;
+                        // AnchorScore keeps the score as f16 (persistence_score/mod.rs:9-12); resolve_token_to_anchor
+                        // uses `score.to_f32() / 100.0` (search_field.rs:426): divided here, once, in IEEE f32
+                        post[at].weight = f16_bits_to_f32(f32_to_f16_bits((float)raw)) / 100.0f;
                         ++at;
                     }
                 });
@@ -316,9 +337,8 @@ struct DeviceIndex {
         pd.n_terms = n;
         pd.n_postings = total;
         pd.off.upload(off);
-        pd.anchors.upload(anchors);
-        pd.scores.upload(scores);
-        device_bytes += pd.off.bytes() + pd.anchors.bytes() + pd.scores.bytes();
+        pd.post.upload(post);
+        device_bytes += pd.off.bytes() + pd.post.bytes();
         postings.emplace(path, std::move(pd));
     }
 

@@ -60,7 +60,8 @@ struct Batch {
     DevBuf<float> d_inj_scores;
     uint32_t n_injected = 0;
     // device: slicing
-    DevBuf<uint32_t> d_toff, d_bucket, d_s_anchor, d_s_key;
+    DevBuf<uint32_t> d_toff, d_bucket;
+    DevBuf<SparseEntry> d_sparse;
     DevBuf<uint64_t> d_sparse_total, d_sparse_base;
     DevBuf<PartSlices> d_slices;
     DevBuf<ItemRec> d_items;
@@ -121,6 +122,9 @@ struct Batch {
         QueryProgram qp;
         memset(&qp, 0, sizeof qp);
         qp.leaf_begin = 0, qp.n_leaves = 1, qp.k = 0, qp.active = 1, qp.emit_all = 1;
+        qp.nonneg = 1;
+        for (float sc : scores)
+            if (!(sc >= 0.0f)) qp.nonneg = 0;
         plan.leaf_part.push_back(pid);
         plan.programs.push_back(qp);
         plan.requests.emplace_back();
@@ -146,6 +150,10 @@ struct Batch {
         QueryProgram qp;
         memset(&qp, 0, sizeof qp);
         qp.leaf_begin = 0, qp.n_leaves = (uint32_t)lists.size(), qp.k = k, qp.active = 1, qp.emit_all = all_hits ? 1 : 0;
+        qp.nonneg = 1;
+        for (auto& l : lists)
+            for (float sc : l.scores)
+                if (!(sc >= 0.0f)) qp.nonneg = 0;
         const bool trivial = lists.size() == 1 && code.size() == 2;
         qp.prog_begin = 0, qp.prog_len = trivial ? 0u : (uint32_t)code.size();
         if (!trivial) plan.prog = code;
@@ -169,7 +177,8 @@ struct Batch {
         emit_capacity = total;
         upload_plan();
         // tile buckets of the lists, built on the host (step seam inputs are small)
-        std::vector<uint32_t> bucket((size_t)lists.size() * (n_tiles + 1), 0), s_anchor, s_key;
+        std::vector<uint32_t> bucket((size_t)lists.size() * (n_tiles + 1), 0);
+        std::vector<SparseEntry> sparse;
         std::vector<PartSlices> slices(lists.size());
         for (size_t i = 0; i < lists.size(); ++i) {
             const ExplicitList& l = lists[i];
@@ -180,12 +189,11 @@ struct Batch {
             uint32_t* row = &bucket[i * (n_tiles + 1)];
             for (auto& e : entries) row[((e.first - (uint32_t)ix->anchor_lo) >> tile_log2) + 1]++;
             for (uint32_t t = 0; t < n_tiles; ++t) row[t + 1] += row[t];
-            slices[i].m_begin = 0, slices[i].n_match = 1, slices[i].n_dense = 0, slices[i].sparse_row = (uint32_t)i, slices[i].sparse_base = s_anchor.size();
-            for (auto& e : entries) s_anchor.push_back(e.first), s_key.push_back(e.second ? e.second : 1u);
+            slices[i].m_begin = 0, slices[i].n_match = 1, slices[i].n_dense = 0, slices[i].sparse_row = (uint32_t)i, slices[i].sparse_base = sparse.size();
+            for (auto& e : entries) sparse.push_back(SparseEntry{e.first, e.second ? e.second : 1u});
         }
         d_bucket.upload(bucket);
-        d_s_anchor.upload(s_anchor);
-        d_s_key.upload(s_key);
+        d_sparse.upload(sparse);
         d_slices.upload(slices);
     }
 
@@ -342,15 +350,14 @@ struct Batch {
             VDEV_CUDA(cudaMemsetAsync(d_bucket.p, 0, d_bucket.bytes(), stream));
             SparseArgs sa;
             sa.n_matches = M, sa.g_row = d_g_row.p, sa.g_df = d_g_df.p, sa.g_part = d_g_part.p, sa.g_begin = d_g_begin.p, sa.g_score = d_g_score.p;
-            sa.parts = d_parts.p, sa.postings = d_postings.p, sa.bucket = d_bucket.p, sa.sparse_base = d_sparse_base.p, sa.s_anchor = nullptr, sa.s_key = nullptr;
+            sa.parts = d_parts.p, sa.postings = d_postings.p, sa.bucket = d_bucket.p, sa.sparse_base = d_sparse_base.p, sa.sparse = nullptr;
             sa.n_tiles = n_tiles, sa.tile_log2 = tile_log2, sa.anchor_lo = (uint32_t)ix->anchor_lo;
             launch_sparse_count(stream, sa);
             launch_sparse_scan(stream, d_bucket.p, n_tiles, d_sparse_total.p, n_parts);
             launch_scan_u64(stream, d_sparse_total.p, d_sparse_base.p, n_parts);
             const uint64_t n_sparse = read_back(d_sparse_base.p + n_parts);
-            d_s_anchor.reserve((size_t)std::max<uint64_t>(n_sparse, 1));
-            d_s_key.reserve((size_t)std::max<uint64_t>(n_sparse, 1));
-            sa.s_anchor = d_s_anchor.p, sa.s_key = d_s_key.p;
+            d_sparse.reserve((size_t)std::max<uint64_t>(n_sparse, 1));
+            sa.sparse = d_sparse.p;
             launch_sparse_fill(stream, sa);
             launch_part_slices(stream, d_slices.p, d_part_begin.p, d_dense_cursor.p, d_sparse_base.p, n_parts);
             launch_finalize_programs(stream, d_programs.p, n, d_prog.p, d_leaf_part.p, d_part_est.p);
@@ -391,7 +398,7 @@ struct Batch {
             a.items = d_items.p, a.slice_recs = d_slice_recs.p;
             a.queries = d_programs.p, a.n_queries = n, a.leaf_part = d_leaf_part.p, a.prog = d_prog.p, a.boosts = d_boosts.p;
             a.parts = d_parts.p, a.slices = d_slices.p, a.postings = d_postings.p, a.g_score = d_g_score.p, a.g_begin = d_g_begin.p, a.g_row = d_g_row.p, a.g_df = d_g_df.p;
-            a.toff = d_toff.p, a.bucket = d_bucket.p, a.s_anchor = d_s_anchor.p, a.s_key = d_s_key.p;
+            a.toff = d_toff.p, a.bucket = d_bucket.p, a.sparse = d_sparse.p;
             a.n_tiles = n_tiles, a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
             a.max_leaves = std::max<uint32_t>(1, plan.max_leaves);
             a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;

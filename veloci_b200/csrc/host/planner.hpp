@@ -292,6 +292,9 @@ struct BatchPlan {
         boosts.insert(boosts.end(), steps.begin(), steps.end());
         qp.k = (uint32_t)(rp.top + rp.skip);
         qp.active = 1;
+        qp.nonneg = 1;
+        for (uint32_t part : leaves)
+            if (!(parts[part].boost >= 0.0f)) qp.nonneg = 0;
         max_leaves = std::max<uint32_t>(max_leaves, qp.n_leaves);
         max_k = std::max<uint32_t>(max_k, std::max<uint32_t>(qp.k, 1));
     }
