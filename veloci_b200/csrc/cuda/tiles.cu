@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
     if (tid == 0 && cta_postings) atomicAdd(a.stat_postings, cta_postings);
 }
 
-static const size_t kTileStaticSmem = 14 * 1024;  // static __shared__ of tile_eval_kernel, rounded up
+static const size_t kTileStaticSmem = 15 * 1024;  // static __shared__ of tile_eval_kernel, rounded up
 
 size_t tile_kernel_smem(uint32_t tile_log2, uint32_t max_leaves) {
     if (tile_log2 > 15) return 0;
