@@ -128,7 +128,7 @@ struct BoostStep {  // add_boost on anchor ids (boost.rs:470-504, apply_boost :2
     float max_mult;
 };
 
-struct QueryProgram {
+struct alignas(16) QueryProgram {  // 80 B: copied to shared memory with five 16-byte async copies
     uint32_t leaf_begin, n_leaves;  // into the leaf -> part table
     uint32_t prog_begin, prog_len;  // into the program words
     uint32_t boost_begin, n_boosts; // into the BoostStep table
@@ -136,6 +136,13 @@ struct QueryProgram {
     uint32_t active;                // 0 = request failed on the host, skip
     uint32_t emit_all;              // step seam: also write every hit to the emit buffer
     uint32_t nonneg;                // every part score of the request is >= 0 (no negative part boost): cheap key decode
+    // the request's only boost step when it has neither skip list nor expression ("fast boost"), inlined
+    uint32_t fb_flags;              // bit 0: fast boost present, bit 1: max_mult bounds the multiplier (can prune)
+    uint32_t fb_n, fb_fun;
+    float fb_param, fb_max_mult;
+    uint32_t pad0;
+    const uint32_t* fb_col;
+    uint32_t pad1[2];
 };
 
 }  // namespace vdev

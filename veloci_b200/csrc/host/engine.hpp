@@ -159,6 +159,7 @@ struct Batch {
         if (!trivial) plan.prog = code;
         qp.boost_begin = 0, qp.n_boosts = (uint32_t)boost_steps.size();
         plan.boosts = boost_steps;
+        vplan::BatchPlan::set_fast_boost(qp, boost_steps);
         uint64_t total = 0;
         for (size_t i = 0; i < lists.size(); ++i) {
             PartQuery pq;
@@ -206,13 +207,13 @@ struct Batch {
         VDEV_CUDA(cudaGetDeviceProperties(&prop, ix->device));
         n_sms = prop.multiProcessorCount;
 
-        // geometry: the largest tile whose part arrays leave room for two CTAs per SM
+        // geometry: the largest tile (<= 8192 anchors) whose part arrays leave room for four CTAs per SM
         const uint32_t L = std::max<uint32_t>(1, plan.max_leaves);
         tile_log2 = 13;
-        while (tile_log2 > 10 && ((size_t)L << tile_log2) * 4 > 96 * 1024) --tile_log2;
+        while (tile_log2 > 10 && ((size_t)L << tile_log2) * 4 > 48 * 1024) --tile_log2;
         if (const char* env = getenv("VELOCI_TILE_LOG2")) {
             int v = atoi(env);
-            if (v >= 8 && v <= 15 && tile_kernel_smem((uint32_t)v, L)) tile_log2 = (uint32_t)v;
+            if (v >= 8 && v <= 13 && tile_kernel_smem((uint32_t)v, L)) tile_log2 = (uint32_t)v;
         }
         const uint64_t span = ix->anchor_hi - ix->anchor_lo;
         n_tiles = (uint32_t)((span + (1ull << tile_log2) - 1) >> tile_log2);

@@ -239,6 +239,15 @@ struct BatchPlan {
         return s;
     }
 
+    // a single boost step without skip list or expression travels inside the QueryProgram
+    static void set_fast_boost(QueryProgram& qp, const std::vector<BoostStep>& steps) {
+        qp.fb_flags = 0;
+        if (steps.size() != 1 || steps[0].n_skip != 0 || steps[0].expr_op != vdev::kExprNone) return;
+        const BoostStep& s = steps[0];
+        qp.fb_flags = 1u | ((s.can_prune && s.max_mult > 0.0f) ? 2u : 0u);
+        qp.fb_col = s.column, qp.fb_n = s.n, qp.fb_fun = s.fun, qp.fb_param = s.param, qp.fb_max_mult = s.max_mult;
+    }
+
     static bool has_nested_boost(const vhost::SearchRequest& r) {
         if (r.get_boost() && !r.get_boost()->empty()) return true;
         for (auto& q : r.queries)
@@ -290,6 +299,7 @@ struct BatchPlan {
         qp.boost_begin = (uint32_t)boosts.size();
         qp.n_boosts = (uint32_t)steps.size();
         boosts.insert(boosts.end(), steps.begin(), steps.end());
+        set_fast_boost(qp, steps);
         qp.k = (uint32_t)(rp.top + rp.skip);
         qp.active = 1;
         qp.nonneg = 1;
