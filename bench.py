@@ -273,7 +273,8 @@ def run_ours(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    tile_ms = statistics.mean(p[3] for p in phase)
+    tile_ms = statistics.mean(p[3] + p[4] for p in phase)
+    paths = batch.path_stats()
     alg_bytes = traffic["posting_bytes"] + traffic["boost_bytes"] + 8 * 10 * len(reqs)
     achieved = alg_bytes / (tile_ms / 1000.0) / 1e9 if tile_ms > 0 else 0.0
     value = len(reqs) * args.steps / elapsed
@@ -282,11 +283,12 @@ def run_ours(args):
         "ms_per_step": 1000.0 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "p50_batch_latency_ms": statistics.median(step_ms),
-        "phase_ms": {k: statistics.mean(p[i] for p in phase) for i, k in enumerate(["fuzzy_match", "group_score", "slice", "tile_eval", "final_topk"])},
+        "phase_ms": {k: statistics.mean(p[i] for p in phase) for i, k in enumerate(["fuzzy_match", "group_score", "slice", "plane_eval", "tile_eval", "final_topk"])},
+        "paths": paths,
         "requests_ok": n_ok,
         "index": {"open_s": open_s, "device_bytes": info["device_bytes"], "anchor_range": [info["anchor_lo"], info["anchor_hi"]]},
         "roofline": {
-            "kernel": "tile_eval_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "kernel": "plane_eval_kernel + tile_eval_kernel (tile evaluation: posting expansion, merge, boost, top-k)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "postings_per_launch": traffic["postings"], "union_hits_per_launch": traffic["union_hits"],
             "launch_ms": tile_ms,
         },

@@ -142,12 +142,15 @@ int32_t vgpu_top_n(vgpu_index* idx, const vgpu_hitlist* in, uint32_t top, uint32
 /* ---- instrumentation ---------------------------------------------------------
  * Kernel launches issued by this library since process start, and per-phase device
  * time (CUDA events on the library's stream) of the last vgpu_batch_execute:
- * phase 0 fuzzy match, 1 match grouping + scoring, 2 posting slicing, 3 tile
- * evaluation (expand + merge + boost + tile top-k), 4 final top-k.  Also the
- * algorithmic byte counts of the last execute. */
+ * phase 0 fuzzy match, 1 match grouping + scoring, 2 posting slicing, 3 plane
+ * evaluation and 4 tile evaluation (expand + merge + boost + tile top-k of the
+ * (tile, request) items on the head-term plane path / the general posting path),
+ * 5 final top-k.  Also the algorithmic byte counts of the last execute
+ *  and how many items took which path. */
 uint64_t vgpu_launch_count(void);
 int32_t vgpu_batch_phase_ms(const vgpu_batch* batch, float* ms, uint32_t n_phases);
 int32_t vgpu_batch_traffic_model(const vgpu_batch* batch, uint64_t* posting_bytes, uint64_t* boost_bytes, uint64_t* postings, uint64_t* union_hits);
+int32_t vgpu_batch_path_stats(const vgpu_batch* batch, uint64_t* plane_items, uint64_t* general_items, uint64_t* plane_evaluated);
 /* Bytes copied host->device by prepare (plan tables) and device->host by execute + fetch. */
 int32_t vgpu_batch_io_bytes(const vgpu_batch* batch, uint64_t* h2d, uint64_t* d2h);
 

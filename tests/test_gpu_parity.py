@@ -219,3 +219,29 @@ def test_resolve_and_boost_and_topn_step_seam(small):
     top = index.top_n(got, 7, 2)
     ref_top = oracle.call("top_n_sort", hits=[[i, float(s)] for i, s in got], top=9)[2:9]
     assert_same_topk(top, [(r[0], np.float32(r[1])) for r in ref_top])
+
+
+def test_plane_path_equals_posting_path(gpu, native_libs, monkeypatch):
+    """The head-term plane path and the general posting path are two evaluations of the same
+    arithmetic: hit counts, ids and score bits must be identical."""
+    d = tempfile.mkdtemp(prefix="vb200_gpu_planes_")
+    params = dict(num_docs=150000, vocab=8000, seed=21)
+    helpers.create_synthetic_index(d, **params)
+    reqs = helpers.synthetic_requests(num_queries=500, query_kind="or3", levenshtein=1, query_seed=3, **params)
+    reqs += helpers.synthetic_requests(num_queries=200, query_kind="single", levenshtein=1, query_seed=4, **params)
+    with_planes = gpu.Index(d)
+    b = with_planes.prepare(reqs)
+    b.execute()
+    got = b.results_flat(10)
+    stats = b.path_stats()
+    assert stats["plane_items"] > 0, "the plane path did not run"
+    monkeypatch.setenv("VELOCI_NO_PLANES", "1")
+    without = gpu.Index(d)
+    b2 = without.prepare(reqs)
+    b2.execute()
+    ref = b2.results_flat(10)
+    assert b2.path_stats()["plane_items"] == 0
+    assert (got["status"] == 0).all() and (ref["status"] == 0).all()
+    assert (got["num_hits"] == ref["num_hits"]).all()
+    assert (got["ids"] == ref["ids"]).all()
+    assert (got["scores"].view(np.uint32) == ref["scores"].view(np.uint32)).all()

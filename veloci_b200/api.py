@@ -78,6 +78,7 @@ def load_library():
     L.vgpu_launch_count.restype = u64
     L.vgpu_batch_phase_ms.argtypes = [vp, P(ctypes.c_float), u32]
     L.vgpu_batch_traffic_model.argtypes = [vp, P(u64), P(u64), P(u64), P(u64)]
+    L.vgpu_batch_path_stats.argtypes = [vp, P(u64), P(u64), P(u64)]
     L.vgpu_batch_io_bytes.argtypes = [vp, P(u64), P(u64)]
     _LIB = L
     return L
@@ -186,9 +187,14 @@ class Batch:
         _check(self.L.vgpu_batch_merge_gathered(self.h, ctypes.c_void_p(keys_ptr), ctypes.c_void_p(hits_ptr), n_shards))
 
     def phase_ms(self):
-        ms = (ctypes.c_float * 5)()
-        _check(self.L.vgpu_batch_phase_ms(self.h, ms, 5))
+        ms = (ctypes.c_float * 6)()
+        _check(self.L.vgpu_batch_phase_ms(self.h, ms, 6))
         return [float(x) for x in ms]
+
+    def path_stats(self):
+        a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        _check(self.L.vgpu_batch_path_stats(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"plane_items": a.value, "general_items": b.value, "plane_evaluated": c.value}
 
     def traffic_model(self):
         a, b, c, d = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()

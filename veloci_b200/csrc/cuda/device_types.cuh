@@ -34,7 +34,60 @@ struct PostingsView {
     const Posting* post;
     const uint64_t* off;
     uint32_t n_terms;
+    const uint32_t* term_plane;  // per term id: head-term plane of the index, kNoValue if the term has none
 };
+
+// ---- head-term planes ----
+// The most frequent terms of the index (df >= anchors / 128, at most kMaxPlanes over all
+// fields) also exist anchor-indexed: one presence bit and the f16 score per anchor of the
+// shard.  The plane path (planes.cu) evaluates them with word-wide bit operations instead
+// of scattering their postings.
+static const uint32_t kMaxPlanes = 96;
+static const uint32_t kPlaneTileLog2 = 13;   // planes are padded to whole tiles of 2^13 anchors
+struct PlaneSetView {
+    const uint32_t* bits;    // [n_planes][words]
+    const uint16_t* score;   // [n_planes][words * 32] f16 bits of AnchorScore.score; weight = f16 / 100 (search_field.rs:426)
+    const float* wmax;       // [n_planes] largest weight of the plane
+    uint32_t n_planes;
+    uint32_t words;          // 32-anchor words per plane (multiple of 2^kPlaneTileLog2 / 32)
+};
+
+// Nested "value >= threshold" bitmaps of a boost column (anchors without a value are set in
+// every level): lets the plane path restrict the exact evaluation to anchors whose boost
+// multiplier can still reach the request's running k-th best.
+static const uint32_t kBoostLevels = 16;
+struct ColumnLevels {
+    const uint32_t* bits;  // [kBoostLevels][words], word 0 = anchors [anchor_lo, anchor_lo + 32)
+    uint32_t words;
+    uint32_t pad;
+    float thr[kBoostLevels];  // ascending
+};
+
+static const uint32_t kPartPlaneSlots = 4;
+struct PartPlanes {  // head-term matches of one search part (48 B)
+    uint32_t n;      // matches registered (more than kPartPlaneSlots: the part cannot take the plane path)
+    uint32_t plane[kPartPlaneSlots];
+    float ts[kPartPlaneSlots];  // term score of the match
+    uint32_t pad[3];
+};
+
+// Everything the plane path needs to know about one request (144 B).
+static const uint32_t kFastMaxLeaves = 4;
+static const uint32_t kFastMaxK = 64;
+static const uint32_t kFastMaxEntries = 128;  // postings of non-plane terms in one (tile, request) item
+enum FastFlags : uint32_t { kFastOk = 1u, kFastBoost = 2u };
+struct alignas(16) FastDesc {
+    uint32_t flags, n_leaves, k, fb_fun;
+    float fb_param, fb_max_mult;
+    uint32_t fb_n;
+    uint8_t n_planes[kFastMaxLeaves];
+    float bound[kFastMaxLeaves];  // bound[n-1]: no anchor with n parts present, all through planes, scores above it (before the boost)
+    float ts[kFastMaxLeaves][kPartPlaneSlots];
+    uint8_t plane[kFastMaxLeaves][kPartPlaneSlots];
+    const uint32_t* fb_col;
+    const ColumnLevels* fb_lev;
+};
+static_assert(sizeof(FastDesc) == 144, "FastDesc is copied as nine 16-byte words");
 
 struct SparseEntry {  // 8 B: one posting of a sparse (rarely matched) term, already scored
     uint32_t anchor;
@@ -126,6 +179,7 @@ struct BoostStep {  // add_boost on anchor ids (boost.rs:470-504, apply_boost :2
     // lets the tile kernel skip the gather for anchors that cannot reach the running k-th best
     uint32_t can_prune;
     float max_mult;
+    const ColumnLevels* levels;  // level bitmaps of the column (nullptr: none)
 };
 
 struct alignas(16) QueryProgram {  // 80 B: copied to shared memory with five 16-byte async copies
@@ -142,7 +196,8 @@ struct alignas(16) QueryProgram {  // 80 B: copied to shared memory with five 16
     float fb_param, fb_max_mult;
     uint32_t pad0;
     const uint32_t* fb_col;
-    uint32_t pad1[2];
+    const ColumnLevels* fb_lev;     // level bitmaps of the fast-boost column (nullptr: none)
 };
+static_assert(sizeof(QueryProgram) == 80, "QueryProgram layout");
 
 }  // namespace vdev

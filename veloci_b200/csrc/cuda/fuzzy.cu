@@ -262,15 +262,21 @@ __global__ void score_scatter_kernel(ScoreScatterArgs a) {
     }
 
     uint64_t begin = 0;
-    uint32_t df = 0;
+    uint32_t df = 0, plane = kNoValue;
     if (q.postings != kNoValue) {
         const PostingsView& pv = a.postings[q.postings];
         if (term_id < pv.n_terms) {
             begin = pv.off[term_id];
             df = (uint32_t)(pv.off[term_id + 1] - begin);
+            if (pv.term_plane != nullptr && a.part_planes != nullptr) plane = pv.term_plane[term_id];
         }
     }
-    const bool dense = df >= a.dense_min;
+    if (plane != kNoValue) {  // head term: register it with its part for the plane path
+        PartPlanes& pp = a.part_planes[r.part];
+        const uint32_t slot = atomicAdd(&pp.n, 1u);
+        if (slot < kPartPlaneSlots) pp.plane[slot] = plane, pp.ts[slot] = score;
+    }
+    const bool dense = df >= a.dense_min || plane != kNoValue;
     const uint32_t seg = a.part_begin[r.part], cnt = a.part_begin[r.part + 1] - seg;
     uint32_t pos, row = kNoValue;
     if (dense) {
@@ -286,6 +292,7 @@ __global__ void score_scatter_kernel(ScoreScatterArgs a) {
     a.g_df[pos] = df;
     a.g_row[pos] = row;
     a.g_part[pos] = r.part;
+    if (a.g_plane) a.g_plane[pos] = plane;
     if (df) atomicAdd(&a.part_est[r.part], (unsigned long long)df);
 }
 
@@ -404,11 +411,16 @@ __global__ void part_slices_kernel(PartSlices* __restrict__ out, const uint32_t*
 // input with the fewest (estimated) hits is summed last and the former last input takes
 // its place (swap_remove), as in intersect_hits_score (set_op.rs:388-417).
 __global__ void finalize_programs_kernel(const QueryProgram* __restrict__ queries, uint32_t n, uint32_t* __restrict__ prog, const uint32_t* __restrict__ leaf_part,
-                                         const unsigned long long* __restrict__ part_est) {
+                                         const unsigned long long* __restrict__ part_est, unsigned long long* __restrict__ stat_postings) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const QueryProgram qp = queries[q];
     if (!qp.active) return;
+    if (stat_postings) {
+        unsigned long long sum = 0;
+        for (uint32_t l = 0; l < qp.n_leaves; ++l) sum += part_est[leaf_part[qp.leaf_begin + l]];
+        if (sum) atomicAdd(stat_postings, sum);
+    }
     uint32_t* code = prog + qp.prog_begin;
     uint32_t pc = 0;
     while (pc < qp.prog_len) {
@@ -438,9 +450,10 @@ __global__ void finalize_programs_kernel(const QueryProgram* __restrict__ querie
         }
     }
 }
-void launch_finalize_programs(cudaStream_t st, const QueryProgram* queries, uint32_t n, uint32_t* prog, const uint32_t* leaf_part, const unsigned long long* part_est) {
+void launch_finalize_programs(cudaStream_t st, const QueryProgram* queries, uint32_t n, uint32_t* prog, const uint32_t* leaf_part, const unsigned long long* part_est,
+                              unsigned long long* stat_postings) {
     if (!n) return;
-    finalize_programs_kernel<<<(n + 127) / 128, 128, 0, st>>>(queries, n, prog, leaf_part, part_est);
+    finalize_programs_kernel<<<(n + 127) / 128, 128, 0, st>>>(queries, n, prog, leaf_part, part_est, stat_postings);
     count_launch();
 }
 

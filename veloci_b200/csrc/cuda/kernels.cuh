@@ -43,6 +43,9 @@ struct ScoreScatterArgs {
     // step seam (vgpu_resolve_to_anchor): hits are given, record.slot indexes these arrays
     const uint32_t* inj_terms;
     const float* inj_scores;
+    // head-term planes: matches of plane terms are also registered per part (zeroed before the launch)
+    PartPlanes* part_planes;
+    uint32_t* g_plane;  // per grouped match: plane id or kNoValue
 };
 void launch_score_scatter(cudaStream_t st, const ScoreScatterArgs& a);
 
@@ -79,25 +82,40 @@ void launch_part_slices(cudaStream_t st, PartSlices* out, const uint32_t* part_b
 
 // Patches the sum order of every `and` node (set_op.rs:388-417: the shortest input is
 // swap_remove'd and added last); input lengths are estimated by part_est.
-void launch_finalize_programs(cudaStream_t st, const QueryProgram* queries, uint32_t n, uint32_t* prog, const uint32_t* leaf_part, const unsigned long long* part_est);
+// Also sums, over all requests, the postings of their matched terms into *stat_postings (traffic model).
+void launch_finalize_programs(cudaStream_t st, const QueryProgram* queries, uint32_t n, uint32_t* prog, const uint32_t* leaf_part, const unsigned long long* part_est,
+                              unsigned long long* stat_postings);
 
 // ---- tiles.cu ----
+// Classifies every (tile, request) pair: nothing to do / fast item (planes + at most
+// kFastMaxEntries posting entries, evaluated by plane_eval_kernel) / general item
+// (tile_eval_kernel).  Pass 0 counts, pass 1 writes the item and slice records; fast items
+// are grouped per tile, general items form one flat list.
 struct ItemScanArgs {
     const QueryProgram* queries;
     uint32_t n_queries;
+    const FastDesc* fast;  // nullptr: no fast path in this batch
     const uint32_t* leaf_part;
     const PartSlices* slices;
     const PartQuery* parts;
     const uint32_t* g_row;
+    const uint32_t* g_plane;
     const uint64_t* g_begin;
     const float* g_score;
     const uint32_t* toff;
     const uint32_t* bucket;
     uint32_t n_tiles;
     unsigned long long n_items_total;  // n_tiles * n_queries
-    unsigned long long* counters;      // [0] items, [1] slices (zeroed before each pass)
-    ItemRec* items;
-    SliceRec* slice_recs;
+    unsigned long long* counters;      // [0] general items, [1] general slices (zeroed before each pass)
+    ItemRec* items;                    // general items
+    SliceRec* slice_recs;              // general slices
+    // fast items, per tile: pass 0 accumulates counts in *_cursor, pass 1 uses them as cursors (zeroed before each pass)
+    uint32_t* fast_item_cursor;              // [n_tiles]
+    unsigned long long* fast_slice_cursor;   // [n_tiles]
+    const uint32_t* fast_item_begin;         // [n_tiles + 1] (pass 1)
+    const unsigned long long* fast_slice_begin;  // [n_tiles + 1] (pass 1)
+    ItemRec* fast_items;
+    SliceRec* fast_slices;
 };
 void launch_item_scan(cudaStream_t st, const ItemScanArgs& a, bool fill);
 
@@ -133,8 +151,6 @@ struct TileArgs {
     // work queue
     unsigned long long* work_counter;
     unsigned long long n_items;
-    // traffic model
-    unsigned long long* stat_postings;
     // step seam: every hit of requests with emit_all
     unsigned long long* emit;
     unsigned long long* emit_count;
@@ -143,6 +159,41 @@ struct TileArgs {
 // Returns the dynamic shared memory the launch needs (0 = cannot run with these parameters).
 size_t tile_kernel_smem(uint32_t tile_log2, uint32_t max_leaves);
 void launch_tile_eval(cudaStream_t st, const TileArgs& a, int n_sms);
+
+// ---- planes.cu ----
+// Index build: presence bits, f16 scores and the largest weight of one head-term plane from its posting list
+// (*bad is set when the list cannot be represented: unsorted anchors or a weight that is not f16 / 100).
+void launch_plane_fill(cudaStream_t st, const Posting* post, uint64_t n, uint32_t* bits_row, uint16_t* score_row, float* wmax_slot, uint32_t* bad, uint32_t anchor_lo);
+// Index build: the kBoostLevels nested bitmaps of a boost column for the shard's anchors.
+void launch_level_fill(cudaStream_t st, const uint32_t* col, uint32_t col_n, uint32_t anchor_lo, uint32_t span, const float* thr, uint32_t* bits, uint32_t words);
+
+// One thread per request: the request's FastDesc (flags == 0 when it has to take the general path).
+void launch_build_fast_desc(cudaStream_t st, const QueryProgram* queries, uint32_t n, const uint32_t* leaf_part, const PartPlanes* part_planes, const float* wmax, FastDesc* out);
+
+struct PlaneArgs {
+    const ItemRec* items;                 // fast items, grouped per tile
+    const uint32_t* tile_item_begin;      // [n_tiles + 1]
+    const SliceRec* slice_recs;
+    const FastDesc* fast;
+    const PostingsView* postings;
+    const SparseEntry* sparse;
+    PlaneSetView planes;
+    const ColumnLevels* lev_dev;          // the column whose level bits are staged in shared memory (nullptr: none)
+    ColumnLevels lev_hdr;                 // host copy of *lev_dev
+    uint32_t n_tiles, tile_log2, anchor_lo, anchor_hi;
+    uint32_t chunks_per_tile, n_units;    // work unit u = (tile u / chunks_per_tile, chunk u % chunks_per_tile of plane_unit_items() items)
+    // per-query state (shared with tile_eval_kernel)
+    unsigned long long* heap;
+    uint32_t heap_stride;
+    unsigned long long* tau;
+    uint32_t* lock;
+    unsigned long long* num_hits;
+    unsigned long long* work_counter;
+    unsigned long long* stats;  // [0] items, [1] anchors evaluated exactly
+};
+size_t plane_kernel_smem(uint32_t tile_log2, uint32_t n_planes);
+uint32_t plane_unit_items();
+void launch_plane_eval(cudaStream_t st, const PlaneArgs& a, int n_sms);
 
 // Final ordering of each request's heap: merges `n_src` gathered heaps per query
 // (n_src = 1: the local one) into `out_keys` [n_queries][stride] sorted by key desc,

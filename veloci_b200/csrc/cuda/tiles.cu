@@ -37,20 +37,25 @@ static const uint32_t kSliceChunk = 64;     // slice records staged in shared me
 
 // ---------------------------------------------------------------- item scan
 // One thread per (tile, request), tile-major.  Pass 0 counts the non-empty items and
-// their slices; pass 1 writes them.  Blocks reserve output ranges in index order, so
-// the item list stays (nearly) tile-major.
+// their slices; pass 1 writes them.  A request with a FastDesc takes the plane path in
+// every tile where its non-plane terms have at most kFastMaxEntries postings: those
+// items carry only the slices of the non-plane terms and are grouped per tile (per-tile
+// cursors).  Everything else becomes a general item with all its slices; blocks reserve
+// general output ranges in index order, so that list stays (nearly) tile-major.
 template <bool FILL>
 __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
     __shared__ uint32_t s_warp_items[8], s_warp_slices[8];
     __shared__ unsigned long long s_base_items, s_base_slices;
     const unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t n_slices = 0, npost = 0, t = 0, q = 0;
+    uint32_t all_slices = 0, all_post = 0, ent_slices = 0, ent_post = 0, t = 0, q = 0;
+    bool plane_hit = false, fastq = false;
     QueryProgram qp;
     qp.active = 0;
     if (i < a.n_items_total) {
         t = (uint32_t)(i / a.n_queries), q = (uint32_t)(i % a.n_queries);
         qp = a.queries[q];
+        fastq = a.fast != nullptr && (a.fast[q].flags & kFastOk) != 0;
     }
     if (qp.active && qp.n_leaves) {
         for (uint32_t l = 0; l < qp.n_leaves; ++l) {
@@ -58,17 +63,52 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
             for (uint32_t r = 0; r < ps.n_dense; ++r) {
                 const uint32_t* trow = a.toff + (size_t)a.g_row[ps.m_begin + r] * (a.n_tiles + 1);
                 const uint32_t n = trow[t + 1] - trow[t];
-                npost += n, n_slices += n ? 1u : 0u;
+                all_post += n, all_slices += n ? 1u : 0u;
+                if (fastq && a.g_plane[ps.m_begin + r] != kNoValue) plane_hit = plane_hit || n != 0;
+                else ent_post += n, ent_slices += n ? 1u : 0u;
             }
             if (ps.n_match != ps.n_dense) {
                 const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
                 const uint32_t n = brow[t + 1] - brow[t];
-                npost += n, n_slices += n ? 1u : 0u;
+                all_post += n, all_slices += n ? 1u : 0u;
+                ent_post += n, ent_slices += n ? 1u : 0u;
             }
         }
     }
-    // block-ordered reservation: exclusive prefix of (items, slices) over the block
-    const uint32_t has = npost ? 1u : 0u;
+    const bool fast_item = fastq && ent_post <= kFastMaxEntries && (plane_hit || ent_post != 0);
+    const bool general_item = !(fastq && ent_post <= kFastMaxEntries) && all_post != 0;
+    const uint32_t n_slices = general_item ? all_slices : 0u;
+
+    // ---- plane-path items: per-tile cursors, one atomic per (warp, tile)
+    uint32_t fast_item_at = 0;
+    unsigned long long fast_slice_at = 0;
+    {
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, fast_item ? t : 0xFFFFFFFFu);
+        uint32_t slices_before = 0, slices_total = 0;
+        for (int src = 0; src < 32; ++src) {
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, ent_slices, src);
+            if ((peers >> src) & 1u) {
+                slices_total += v;
+                if (src < (int)lane) slices_before += v;
+            }
+        }
+        const int leader = __ffs((int)peers) - 1;
+        uint32_t base_i = 0;
+        unsigned long long base_s = 0;
+        if (fast_item && (int)lane == leader) {
+            base_i = atomicAdd(a.fast_item_cursor + t, (uint32_t)__popc(peers));
+            if (slices_total) base_s = atomicAdd(a.fast_slice_cursor + t, (unsigned long long)slices_total);
+        }
+        base_i = __shfl_sync(0xFFFFFFFFu, base_i, leader);
+        base_s = __shfl_sync(0xFFFFFFFFu, base_s, leader);
+        if (FILL && fast_item) {
+            fast_item_at = a.fast_item_begin[t] + base_i + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            fast_slice_at = a.fast_slice_begin[t] + base_s + slices_before;
+        }
+    }
+
+    // ---- general items: block-ordered reservation, exclusive prefix of (items, slices) over the block
+    const uint32_t has = general_item ? 1u : 0u;
     uint32_t xi = has, xs = n_slices;
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t yi = __shfl_up_sync(0xFFFFFFFFu, xi, o), ys = __shfl_up_sync(0xFFFFFFFFu, xs, o);
@@ -87,18 +127,28 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
     }
     if (!FILL) return;
     __syncthreads();
-    if (!has) return;
-    const unsigned long long item_at = s_base_items + wi + xi - has;
-    unsigned long long slice_at = s_base_slices + ws + xs - n_slices;
+    if (!has && !fast_item) return;
     ItemRec rec;
-    rec.q = q, rec.t = t, rec.slice_begin = slice_at, rec.n_slices = n_slices, rec.npost = npost;
-    a.items[item_at] = rec;
+    rec.q = q, rec.t = t;
+    unsigned long long slice_at;
+    SliceRec* slice_out;
+    if (fast_item) {
+        slice_at = fast_slice_at, slice_out = a.fast_slices;
+        rec.slice_begin = slice_at, rec.n_slices = ent_slices, rec.npost = ent_post;
+        a.fast_items[fast_item_at] = rec;
+        if (ent_post == 0) return;
+    } else {
+        slice_at = s_base_slices + ws + xs - n_slices, slice_out = a.slice_recs;
+        rec.slice_begin = slice_at, rec.n_slices = n_slices, rec.npost = all_post;
+        a.items[s_base_items + wi + xi - has] = rec;
+    }
     uint32_t task_at = 0;
     for (uint32_t l = 0; l < qp.n_leaves; ++l) {
         const uint32_t part = a.leaf_part[qp.leaf_begin + l];
         const PartSlices ps = a.slices[part];
         for (uint32_t r = 0; r < ps.n_dense; ++r) {
             const uint32_t mi = ps.m_begin + r;
+            if (fast_item && a.g_plane[mi] != kNoValue) continue;
             const uint32_t* trow = a.toff + (size_t)a.g_row[mi] * (a.n_tiles + 1);
             const uint32_t s = trow[t], e = trow[t + 1];
             if (e == s) continue;
@@ -106,7 +156,7 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
             sr.begin = a.g_begin[mi] + s, sr.n = e - s, sr.term_score = a.g_score[mi], sr.task_begin = task_at;
             sr.leaf = (uint16_t)l, sr.kind = 0, sr.single = ps.n_match == 1 ? 1 : 0, sr.postings = a.parts[part].postings, sr.pad = 0;
             task_at += (sr.n + kTaskPostings - 1) / kTaskPostings;
-            a.slice_recs[slice_at++] = sr;
+            slice_out[slice_at++] = sr;
         }
         if (ps.n_match != ps.n_dense) {
             const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
@@ -116,7 +166,7 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
             sr.begin = ps.sparse_base + s, sr.n = e - s, sr.term_score = 0.0f, sr.task_begin = task_at;
             sr.leaf = (uint16_t)l, sr.kind = 1, sr.single = 0, sr.postings = 0, sr.pad = 0;
             task_at += (sr.n + kTaskPostings - 1) / kTaskPostings;
-            a.slice_recs[slice_at++] = sr;
+            slice_out[slice_at++] = sr;
         }
     }
 }
@@ -402,7 +452,6 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t n_warps = kTileThreads / 32;
     const uint32_t tile = 1u << a.tile_log2;
-    unsigned long long cta_postings = 0;  // thread 0 only
     {
         uint4* p4 = reinterpret_cast<uint4*>(arr);
         const uint32_t n4 = (a.max_leaves * tile) >> 2;
@@ -425,7 +474,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
             s_item_idx[parity ^ 1] = nxt;
             if (nxt < a.n_items) s_item[parity ^ 1] = a.items[nxt];
         }
-        if (tid == 0) s_npresent = 0, s_nsurv = 0, cta_postings += it.npost;
+        if (tid == 0) s_npresent = 0, s_nsurv = 0;
         parity ^= 1;
 
         const uint32_t t = it.t, q = it.q;
@@ -589,7 +638,6 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
             nsurv = s_nsurv;
         }
     }
-    if (tid == 0 && cta_postings) atomicAdd(a.stat_postings, cta_postings);
 }
 
 static const size_t kTileStaticSmem = 15 * 1024;  // static __shared__ of tile_eval_kernel, rounded up

@@ -281,6 +281,17 @@ int32_t vgpu_batch_traffic_model(const vgpu_batch* batch_c, uint64_t* posting_by
     });
 }
 
+int32_t vgpu_batch_path_stats(const vgpu_batch* batch_c, uint64_t* plane_items, uint64_t* general_items, uint64_t* plane_evaluated) {
+    vgpu_batch* batch = const_cast<vgpu_batch*>(batch_c);
+    if (!batch) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() {
+        batch->b.fetch();
+        if (plane_items) *plane_items = batch->b.stat_fast_items;
+        if (general_items) *general_items = batch->b.stat_general_items;
+        if (plane_evaluated) *plane_evaluated = batch->b.stat_plane_evaluated;
+    });
+}
+
 int32_t vgpu_batch_io_bytes(const vgpu_batch* batch, uint64_t* h2d, uint64_t* d2h) {
     if (!batch) return VGPU_ERR_INVALID_REQUEST;
     if (h2d) *h2d = batch->b.h2d_bytes;

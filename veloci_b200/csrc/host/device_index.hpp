@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -32,6 +34,7 @@
 #include <vector>
 
 #include "../cuda/device_types.cuh"
+#include "../cuda/kernels.cuh"
 #include "persistence.hpp"
 
 namespace vdev {
@@ -169,7 +172,17 @@ struct PostingsDev {
     uint64_t n_postings = 0;
     DevBuf<uint64_t> off;
     DevBuf<Posting> post;
-    PostingsView view() const { return PostingsView{post.p, off.p, (uint32_t)n_terms}; }
+    std::vector<uint64_t> h_off;    // host copy of the offsets (head-term selection)
+    DevBuf<uint32_t> term_plane;    // per term id: head-term plane or kNoValue (empty: the store has no planes)
+    PostingsView view() const { return PostingsView{post.p, off.p, (uint32_t)n_terms, term_plane.p}; }
+};
+
+struct PlaneSetDev {  // head-term planes of every postings store of the shard
+    uint32_t n_planes = 0, words = 0;
+    DevBuf<uint32_t> bits;
+    DevBuf<uint16_t> score;
+    DevBuf<float> wmax;
+    PlaneSetView view() const { return PlaneSetView{bits.p, score.p, wmax.p, n_planes, words}; }
 };
 
 struct CsrDev {  // id -> list<u32>
@@ -185,6 +198,10 @@ struct ColumnDev {  // boost column
     DevBuf<uint32_t> bits;
     bool non_negative = true;  // every stored value is a non-negative, non-NaN float
     float vmax = 0.0f;
+    // nested "value >= threshold" bitmaps over the shard's anchors (plane path)
+    DevBuf<uint32_t> level_bits;
+    DevBuf<ColumnLevels> level_hdr;
+    ColumnLevels h_levels{};
 };
 
 struct PhraseDev {
@@ -204,7 +221,14 @@ struct DeviceIndex {
     std::map<std::string, CsrDev> stores;          // key/value stores
     std::map<std::string, ColumnDev> boosts;       // "<field>.boost_valid_to_value"
     std::map<std::string, PhraseDev> phrases;
+    PlaneSetDev planes;
     size_t device_bytes = 0;
+
+    uint32_t shard_words() const {  // 32-anchor words of the shard, padded to whole plane tiles
+        const uint64_t span = anchor_hi - anchor_lo;
+        const uint64_t tiles = (span + (1ull << kPlaneTileLog2) - 1) >> kPlaneTileLog2;
+        return (uint32_t)(tiles << (kPlaneTileLog2 - 5));
+    }
 
     static void build_symbol_set(const vhost::TermDict& d, const std::vector<uint32_t>& alphabet, bool lower, SymbolSet& out, std::vector<uint16_t>* lower_bytes) {
         const size_t n = d.size();
@@ -338,6 +362,7 @@ struct DeviceIndex {
         pd.n_postings = total;
         pd.off.upload(off);
         pd.post.upload(post);
+        pd.h_off = std::move(off);
         device_bytes += pd.off.bytes() + pd.post.bytes();
         postings.emplace(path, std::move(pd));
     }
@@ -390,7 +415,90 @@ struct DeviceIndex {
         c.n = n;
         c.bits.upload(bits);
         device_bytes += c.bits.bytes();
+        // level thresholds: the (1 - 2^-(j+1)) quantiles of a sample of the shard's values
+        const uint64_t span = anchor_hi - anchor_lo;
+        if (c.non_negative && span > 0 && span < 0xFFFFFFFFull && !getenv("VELOCI_NO_PLANES")) {
+            std::vector<float> sample;
+            const size_t lo = (size_t)std::min<uint64_t>(anchor_lo, n), hi = (size_t)std::min<uint64_t>(anchor_hi, n);
+            const size_t stride = std::max<size_t>(1, (hi - lo) >> 20);
+            for (size_t id = lo; id < hi; id += stride)
+                if (bits[id] != kNoValue) {
+                    float f;
+                    memcpy(&f, &bits[id], 4);
+                    sample.push_back(f);
+                }
+            std::sort(sample.begin(), sample.end());
+            const uint32_t words = shard_words();
+            c.h_levels.words = words, c.h_levels.pad = 0;
+            for (uint32_t j = 0; j < kBoostLevels; ++j) {
+                if (sample.empty()) {
+                    c.h_levels.thr[j] = 3.0e38f;
+                    continue;
+                }
+                const double frac = 1.0 - std::ldexp(1.0, -(int)(j + 1));
+                const size_t at = std::min(sample.size() - 1, (size_t)(frac * (double)sample.size()));
+                c.h_levels.thr[j] = sample[at];
+            }
+            c.level_bits.alloc((size_t)kBoostLevels * words);
+            launch_level_fill(nullptr, c.bits.p, (uint32_t)n, (uint32_t)anchor_lo, (uint32_t)span, c.h_levels.thr, c.level_bits.p, words);
+            c.h_levels.bits = c.level_bits.p;
+            c.level_hdr.upload(std::vector<ColumnLevels>{c.h_levels});
+            device_bytes += c.level_bits.bytes();
+        }
         boosts.emplace(path, std::move(c));
+    }
+
+    // Head-term planes: the terms with df >= span / 128 over all postings stores, at most kMaxPlanes by df.
+    void build_planes() {
+        const uint64_t span = anchor_hi - anchor_lo;
+        if (getenv("VELOCI_NO_PLANES") || span == 0 || span >= 0xFFFFFFFFull) return;
+        const uint64_t min_df = std::max<uint64_t>(1, span / 128);
+        struct Cand {
+            uint64_t df;
+            PostingsDev* store;
+            uint32_t term;
+        };
+        std::vector<Cand> cands;
+        for (auto& kv : postings) {
+            PostingsDev& pd = kv.second;
+            for (size_t t = 0; t < pd.n_terms; ++t) {
+                const uint64_t df = pd.h_off[t + 1] - pd.h_off[t];
+                if (df >= min_df) cands.push_back(Cand{df, &pd, (uint32_t)t});
+            }
+        }
+        if (cands.empty()) return;
+        std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.df > b.df; });
+        if (cands.size() > kMaxPlanes) cands.resize(kMaxPlanes);
+        const uint32_t n = (uint32_t)cands.size(), words = shard_words();
+        planes.n_planes = n, planes.words = words;
+        planes.bits.alloc((size_t)n * words);
+        planes.score.alloc((size_t)n * words * 32);
+        planes.wmax.alloc(n);
+        DevBuf<uint32_t> bad;
+        bad.alloc(n);
+        VDEV_CUDA(cudaMemset(planes.bits.p, 0, planes.bits.bytes()));
+        VDEV_CUDA(cudaMemset(planes.score.p, 0, planes.score.bytes()));
+        VDEV_CUDA(cudaMemset(planes.wmax.p, 0, planes.wmax.bytes()));
+        VDEV_CUDA(cudaMemset(bad.p, 0, bad.bytes()));
+        for (uint32_t p = 0; p < n; ++p) {
+            const Cand& c = cands[p];
+            launch_plane_fill(nullptr, c.store->post.p + c.store->h_off[c.term], c.df, planes.bits.p + (size_t)p * words, planes.score.p + (size_t)p * words * 32, planes.wmax.p + p,
+                              bad.p + p, (uint32_t)anchor_lo);
+        }
+        std::vector<uint32_t> h_bad(n);
+        VDEV_CUDA(cudaMemcpy(h_bad.data(), bad.p, n * 4, cudaMemcpyDeviceToHost));
+        std::map<PostingsDev*, std::vector<uint32_t>> maps;
+        for (uint32_t p = 0; p < n; ++p) {
+            if (h_bad[p]) continue;  // the list cannot be represented as a plane: the term stays on the posting path
+            auto& m = maps[cands[p].store];
+            if (m.empty()) m.assign(cands[p].store->n_terms, kNoValue);
+            m[cands[p].term] = p;
+        }
+        for (auto& kv : maps) {
+            kv.first->term_plane.upload(kv.second);
+            device_bytes += kv.first->term_plane.bytes();
+        }
+        device_bytes += planes.bits.bytes() + planes.score.bytes() + planes.wmax.bytes();
     }
 
     void build_phrase(const std::string& path, const vfmt::PhrasePairView& v) {
@@ -432,6 +540,7 @@ struct DeviceIndex {
         ix->anchor_hi = ix->num_docs * (rank + 1) / n_shards;
         for (auto& kv : ix->host->dict) ix->build_dict(kv.first, kv.second);
         for (auto& kv : ix->host->token_to_anchor_score) ix->build_postings(kv.first, kv.second);
+        ix->build_planes();
         for (auto& kv : ix->host->key_value_stores) ix->build_store(kv.first, kv.second);
         for (auto& kv : ix->host->boost_valueid_to_value) ix->build_boost(kv.first, kv.second);
         for (auto& kv : ix->host->phrase_pair_to_anchor) ix->build_phrase(kv.first, kv.second);

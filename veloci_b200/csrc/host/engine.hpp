@@ -5,9 +5,9 @@
 //   phase 0  fuzzy_match per dictionary              (PlanStepFieldSearchToTokenIds)
 //   phase 1  group matches by part, score them        (  "  , hits_scores of each part)
 //   phase 2  dense tile offsets + sparse tile buckets (ResolveTokenIdToAnchor, slicing only)
-//   phase 3  tile evaluation                          (ResolveTokenIdToAnchor, Union, Intersect,
-//                                                      BoostPlanStepFromBoostRequest, top_n_sort)
-//   phase 4  heap finalisation                        (apply_top_skip happens on the host view)
+//   phase 3  plane evaluation  } ResolveTokenIdToAnchor, Union, Intersect, BoostPlanStepFromBoostRequest,
+//   phase 4  tile evaluation   } top_n_sort: (tile, request) items on the plane path / the general path
+//   phase 5  heap finalisation                        (apply_top_skip happens on the host view)
 #pragma once
 #include <cstdlib>
 
@@ -27,7 +27,7 @@ struct ExplicitList {  // a caller-provided hit list used as a leaf (step seam)
     std::vector<float> scores;
 };
 
-static const int kPhases = 5;
+static const int kPhases = 6;
 
 struct Batch {
     DeviceIndex* ix = nullptr;
@@ -66,6 +66,18 @@ struct Batch {
     DevBuf<PartSlices> d_slices;
     DevBuf<ItemRec> d_items;
     DevBuf<SliceRec> d_slice_recs;
+    // device: plane path
+    bool use_planes = false;
+    DevBuf<PartPlanes> d_part_planes;
+    DevBuf<uint32_t> d_g_plane;
+    DevBuf<FastDesc> d_fast;
+    DevBuf<uint32_t> d_fast_item_cursor, d_fast_item_begin;
+    DevBuf<unsigned long long> d_fast_slice_cursor, d_fast_slice_begin;
+    DevBuf<ItemRec> d_fast_items;
+    DevBuf<SliceRec> d_fast_slices;
+    const ColumnLevels* lev_dev = nullptr;  // boost column whose level bits the plane kernel stages in shared memory
+    ColumnLevels lev_hdr{};
+    uint64_t stat_fast_items = 0, stat_general_items = 0, stat_plane_evaluated = 0;
     // device: per-request state and results
     DevBuf<unsigned long long> d_heap, d_tau, d_num_hits;
     DevBuf<uint32_t> d_lock;
@@ -211,6 +223,21 @@ struct Batch {
         const uint32_t L = std::max<uint32_t>(1, plan.max_leaves);
         tile_log2 = 13;
         while (tile_log2 > 10 && ((size_t)L << tile_log2) * 4 > 48 * 1024) --tile_log2;
+        // plane path: requests that are flat `or`s of few parts run on head-term planes, with plane-sized tiles
+        use_planes = mode == kRequests && ix->planes.n_planes > 0 && plane_kernel_smem(kPlaneTileLog2, ix->planes.n_planes) != 0;
+        if (use_planes) {
+            uint32_t eligible = 0;
+            for (auto& qp : plan.programs)
+                if (qp.active && qp.prog_len == 0 && qp.n_leaves <= kFastMaxLeaves && qp.nonneg && qp.k >= 1 && qp.k <= kFastMaxK) ++eligible;
+            if (eligible == 0) use_planes = false;
+            else if (eligible * 2 >= n && tile_kernel_smem(kPlaneTileLog2, L) != 0) tile_log2 = kPlaneTileLog2;
+        }
+        lev_dev = nullptr;
+        if (use_planes)
+            for (auto& bs : plan.boosts)
+                if (bs.levels && !lev_dev)
+                    for (auto& kv : ix->boosts)
+                        if (kv.second.level_hdr.p == bs.levels) lev_dev = bs.levels, lev_hdr = kv.second.h_levels;
         if (const char* env = getenv("VELOCI_TILE_LOG2")) {
             int v = atoi(env);
             if (v >= 8 && v <= 13 && tile_kernel_smem((uint32_t)v, L)) tile_log2 = (uint32_t)v;
@@ -242,7 +269,11 @@ struct Batch {
         h2d_bytes += plan.parts.size() * sizeof(PartQuery) + (plan.part_dict.size() + plan.leaf_part.size() + plan.prog.size()) * 4 + plan.programs.size() * sizeof(QueryProgram) +
                      plan.boosts.size() * sizeof(BoostStep) + dv.size() * sizeof(DictView) + pv.size() * sizeof(PostingsView);
 
-        d_counters.alloc(8);
+        d_counters.alloc(16);  // [0] matches [1] tile work [2] postings [3] dense rows [4] emitted [5,6] item scan [7] plane work [8,9] plane stats
+        if (use_planes) {
+            d_part_planes.alloc(n_parts + 1);
+            d_fast.alloc(n + 1);
+        }
         d_part_count.alloc(n_parts + 1);
         d_part_begin.alloc(n_parts + 2);
         d_dense_cursor.alloc(n_parts + 1);
@@ -301,6 +332,10 @@ struct Batch {
         const uint32_t M = (uint32_t)n_match;
         VDEV_CUDA(cudaEventRecord(ev[1], stream));
         d_g_term.reserve(M), d_g_df.reserve(M), d_g_row.reserve(M), d_g_part.reserve(M), d_g_score.reserve(M), d_g_begin.reserve(M), d_row_match.reserve(M);
+        if (use_planes) {
+            d_g_plane.reserve(M);
+            VDEV_CUDA(cudaMemsetAsync(d_part_planes.p, 0, d_part_planes.bytes(), stream));
+        }
         VDEV_CUDA(cudaMemsetAsync(d_part_count.p, 0, d_part_count.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_dense_cursor.p, 0, d_dense_cursor.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_sparse_cursor.p, 0, d_sparse_cursor.bytes(), stream));
@@ -313,6 +348,7 @@ struct Batch {
         a.dense_row_capacity = M, a.dense_min = std::max<uint32_t>(1, n_tiles / 2), a.row_match = d_row_match.p, a.part_est = d_part_est.p;
         a.g_term = d_g_term.p, a.g_score = d_g_score.p, a.g_begin = d_g_begin.p, a.g_df = d_g_df.p, a.g_row = d_g_row.p, a.g_part = d_g_part.p;
         a.inj_terms = mode == kTermHits ? d_inj_terms.p : nullptr, a.inj_scores = mode == kTermHits ? d_inj_scores.p : nullptr;
+        a.part_planes = use_planes ? d_part_planes.p : nullptr, a.g_plane = use_planes ? d_g_plane.p : nullptr;
         launch_score_scatter(stream, a);
         VDEV_CUDA(cudaEventRecord(ev[2], stream));
         VDEV_CUDA(cudaStreamSynchronize(stream));
@@ -361,39 +397,82 @@ struct Batch {
             sa.sparse = d_sparse.p;
             launch_sparse_fill(stream, sa);
             launch_part_slices(stream, d_slices.p, d_part_begin.p, d_dense_cursor.p, d_sparse_base.p, n_parts);
-            launch_finalize_programs(stream, d_programs.p, n, d_prog.p, d_leaf_part.p, d_part_est.p);
+            launch_finalize_programs(stream, d_programs.p, n, d_prog.p, d_leaf_part.p, d_part_est.p, d_counters.p + 2);
+            if (use_planes) launch_build_fast_desc(stream, d_programs.p, n, d_leaf_part.p, d_part_planes.p, ix->planes.wmax.p, d_fast.p);
         } else {
             VDEV_CUDA(cudaMemsetAsync(d_counters.p, 0, d_counters.bytes(), stream));
             VDEV_CUDA(cudaEventRecord(ev[0], stream));
             VDEV_CUDA(cudaEventRecord(ev[1], stream));
             VDEV_CUDA(cudaEventRecord(ev[2], stream));
         }
-        // non-empty (tile, request) items and their slices, tile-major
+        // non-empty (tile, request) items and their slices: plane-path items grouped per tile, general items tile-major
         unsigned long long n_items = 0;
+        uint32_t n_fast_items = 0;
+        const bool planes_on = use_planes && mode == kRequests;
         {
             ItemScanArgs sc;
+            memset(&sc, 0, sizeof sc);
             sc.queries = d_programs.p, sc.n_queries = n, sc.leaf_part = d_leaf_part.p, sc.slices = d_slices.p, sc.parts = d_parts.p;
             sc.g_row = d_g_row.p, sc.g_begin = d_g_begin.p, sc.g_score = d_g_score.p, sc.toff = d_toff.p, sc.bucket = d_bucket.p;
             sc.n_tiles = n_tiles, sc.n_items_total = (unsigned long long)n_tiles * n, sc.counters = d_counters.p + 5, sc.items = nullptr, sc.slice_recs = nullptr;
+            if (planes_on) {
+                d_fast_item_cursor.reserve(n_tiles + 1), d_fast_item_begin.reserve(n_tiles + 2);
+                d_fast_slice_cursor.reserve(n_tiles + 1), d_fast_slice_begin.reserve(n_tiles + 2);
+                sc.fast = d_fast.p, sc.g_plane = d_g_plane.p;
+                sc.fast_item_cursor = d_fast_item_cursor.p, sc.fast_slice_cursor = d_fast_slice_cursor.p;
+                sc.fast_item_begin = d_fast_item_begin.p, sc.fast_slice_begin = d_fast_slice_begin.p;
+                VDEV_CUDA(cudaMemsetAsync(d_fast_item_cursor.p, 0, d_fast_item_cursor.bytes(), stream));
+                VDEV_CUDA(cudaMemsetAsync(d_fast_slice_cursor.p, 0, d_fast_slice_cursor.bytes(), stream));
+            }
             VDEV_CUDA(cudaMemsetAsync(d_counters.p + 5, 0, 16, stream));
             launch_item_scan(stream, sc, false);
-            unsigned long long counts[2];
+            unsigned long long counts[2], fast_slices = 0;
             VDEV_CUDA(cudaMemcpyAsync(counts, d_counters.p + 5, 16, cudaMemcpyDeviceToHost, stream));
+            if (planes_on) {
+                launch_scan_u32(stream, d_fast_item_cursor.p, d_fast_item_begin.p, n_tiles);
+                launch_scan_u64(stream, reinterpret_cast<const uint64_t*>(d_fast_slice_cursor.p), reinterpret_cast<uint64_t*>(d_fast_slice_begin.p), n_tiles);
+                VDEV_CUDA(cudaMemcpyAsync(&n_fast_items, d_fast_item_begin.p + n_tiles, 4, cudaMemcpyDeviceToHost, stream));
+                VDEV_CUDA(cudaMemcpyAsync(&fast_slices, d_fast_slice_begin.p + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
+                d2h_bytes += 12;
+            }
             VDEV_CUDA(cudaStreamSynchronize(stream));
             d2h_bytes += 16;
             n_items = counts[0];
             d_items.reserve((size_t)std::max<unsigned long long>(n_items, 1));
             d_slice_recs.reserve((size_t)std::max<unsigned long long>(counts[1], 1));
             sc.items = d_items.p, sc.slice_recs = d_slice_recs.p;
+            if (planes_on) {
+                d_fast_items.reserve(std::max<size_t>(n_fast_items, 1));
+                d_fast_slices.reserve((size_t)std::max<unsigned long long>(fast_slices, 1));
+                sc.fast_items = d_fast_items.p, sc.fast_slices = d_fast_slices.p;
+                VDEV_CUDA(cudaMemsetAsync(d_fast_item_cursor.p, 0, d_fast_item_cursor.bytes(), stream));
+                VDEV_CUDA(cudaMemsetAsync(d_fast_slice_cursor.p, 0, d_fast_slice_cursor.bytes(), stream));
+            }
             VDEV_CUDA(cudaMemsetAsync(d_counters.p + 5, 0, 16, stream));
             launch_item_scan(stream, sc, true);
         }
+        stat_fast_items = n_fast_items, stat_general_items = n_items;
         VDEV_CUDA(cudaEventRecord(ev[3], stream));
-        // ---- phase 3: tile evaluation
         VDEV_CUDA(cudaMemsetAsync(d_heap.p, 0, d_heap.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_tau.p, 0, d_tau.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_num_hits.p, 0, d_num_hits.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_lock.p, 0, d_lock.bytes(), stream));
+        // ---- phase 3: plane evaluation
+        if (planes_on && n_fast_items) {
+            PlaneArgs a;
+            memset(&a, 0, sizeof a);
+            a.items = d_fast_items.p, a.tile_item_begin = d_fast_item_begin.p, a.slice_recs = d_fast_slices.p, a.fast = d_fast.p;
+            a.postings = d_postings.p, a.sparse = d_sparse.p, a.planes = ix->planes.view();
+            a.lev_dev = lev_dev, a.lev_hdr = lev_hdr;
+            a.n_tiles = n_tiles, a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
+            a.chunks_per_tile = (n + plane_unit_items() - 1) / plane_unit_items();
+            a.n_units = n_tiles * a.chunks_per_tile;
+            a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
+            a.work_counter = d_counters.p + 7, a.stats = d_counters.p + 8;
+            launch_plane_eval(stream, a, n_sms);
+        }
+        VDEV_CUDA(cudaEventRecord(ev[4], stream));
+        // ---- phase 4: tile evaluation of the general items
         {
             TileArgs a;
             a.items = d_items.p, a.slice_recs = d_slice_recs.p;
@@ -403,14 +482,14 @@ struct Batch {
             a.n_tiles = n_tiles, a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
             a.max_leaves = std::max<uint32_t>(1, plan.max_leaves);
             a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
-            a.work_counter = d_counters.p + 1, a.n_items = n_items, a.stat_postings = d_counters.p + 2;
+            a.work_counter = d_counters.p + 1, a.n_items = n_items;
             a.emit = d_emit.p, a.emit_count = d_counters.p + 4, a.emit_capacity = emit_capacity;
             launch_tile_eval(stream, a, n_sms);
         }
-        VDEV_CUDA(cudaEventRecord(ev[4], stream));
-        // ---- phase 4: final order of the local heaps
-        launch_merge_heaps(stream, reinterpret_cast<const uint64_t*>(d_heap.p), reinterpret_cast<const uint64_t*>(d_num_hits.p), 1, n, stride, d_programs.p, d_out_keys.p, d_out_hits.p);
         VDEV_CUDA(cudaEventRecord(ev[5], stream));
+        // ---- phase 5: final order of the local heaps
+        launch_merge_heaps(stream, reinterpret_cast<const uint64_t*>(d_heap.p), reinterpret_cast<const uint64_t*>(d_num_hits.p), 1, n, stride, d_programs.p, d_out_keys.p, d_out_hits.p);
+        VDEV_CUDA(cudaEventRecord(ev[6], stream));
         VDEV_CUDA(cudaStreamSynchronize(stream));
         VDEV_CUDA(cudaGetLastError());
         for (int p = 0; p < kPhases; ++p) VDEV_CUDA(cudaEventElapsedTime(&phase_ms[p], ev[p], ev[p + 1]));
@@ -433,10 +512,11 @@ struct Batch {
         if (n) {
             VDEV_CUDA(cudaMemcpyAsync(h_keys.data(), d_out_keys.p, h_keys.size() * 8, cudaMemcpyDeviceToHost, stream));
             VDEV_CUDA(cudaMemcpyAsync(h_hits.data(), d_out_hits.p, h_hits.size() * 8, cudaMemcpyDeviceToHost, stream));
-            uint64_t stats[3];
+            uint64_t stats[10];
             VDEV_CUDA(cudaMemcpyAsync(stats, d_counters.p, sizeof stats, cudaMemcpyDeviceToHost, stream));
             VDEV_CUDA(cudaStreamSynchronize(stream));
             stat_postings = stats[2];
+            stat_plane_evaluated = stats[9];
             d2h_bytes += h_keys.size() * 8 + h_hits.size() * 8 + sizeof stats;
             stat_union = 0;
             for (uint64_t h : h_hits) stat_union += h;

@@ -209,6 +209,7 @@ struct BatchPlan {
         auto it = ix->boosts.find(path);
         if (it == ix->boosts.end()) ix->host->path_not_found(path);
         s.column = it->second.bits.p;
+        s.levels = it->second.level_hdr.p;
         s.n = (uint32_t)it->second.n;
         s.fun = (uint32_t)b.boost_fun;
         s.param = b.param.value_or(0.0f);
@@ -245,7 +246,7 @@ struct BatchPlan {
         if (steps.size() != 1 || steps[0].n_skip != 0 || steps[0].expr_op != vdev::kExprNone) return;
         const BoostStep& s = steps[0];
         qp.fb_flags = 1u | ((s.can_prune && s.max_mult > 0.0f) ? 2u : 0u);
-        qp.fb_col = s.column, qp.fb_n = s.n, qp.fb_fun = s.fun, qp.fb_param = s.param, qp.fb_max_mult = s.max_mult;
+        qp.fb_col = s.column, qp.fb_lev = s.levels, qp.fb_n = s.n, qp.fb_fun = s.fun, qp.fb_param = s.param, qp.fb_max_mult = s.max_mult;
     }
 
     static bool has_nested_boost(const vhost::SearchRequest& r) {
