@@ -71,7 +71,7 @@ struct PartPlanes {  // head-term matches of one search part (48 B)
     uint32_t pad[3];
 };
 
-// Everything the plane path needs to know about one request (144 B).
+// Everything the plane path needs to know about one request (160 B).
 static const uint32_t kFastMaxLeaves = 4;
 static const uint32_t kFastMaxK = 64;
 static const uint32_t kFastMaxEntries = 128;  // postings of non-plane terms in one (tile, request) item
@@ -82,12 +82,22 @@ struct alignas(16) FastDesc {
     uint32_t fb_n;
     uint8_t n_planes[kFastMaxLeaves];
     float bound[kFastMaxLeaves];  // bound[n-1]: no anchor with n parts present, all through planes, scores above it (before the boost)
+    float ub[kFastMaxLeaves];     // per part: largest score a plane match can contribute
     float ts[kFastMaxLeaves][kPartPlaneSlots];
     uint8_t plane[kFastMaxLeaves][kPartPlaneSlots];
     const uint32_t* fb_col;
     const ColumnLevels* fb_lev;
 };
-static_assert(sizeof(FastDesc) == 144, "FastDesc is copied as nine 16-byte words");
+static_assert(sizeof(FastDesc) == 160, "FastDesc is copied as ten 16-byte words");
+
+// One (tile, request) item of the plane path: per part, the request's entries (postings of
+// non-plane terms inside the tile) are one contiguous range of the part's sparse tile bucket.
+struct alignas(16) FastItem {  // 32 B
+    uint32_t q;
+    uint16_t n[kFastMaxLeaves];
+    uint32_t begin[kFastMaxLeaves];  // index into the batch's SparseEntry array
+    uint32_t pad;
+};
 
 struct SparseEntry {  // 8 B: one posting of a sparse (rarely matched) term, already scored
     uint32_t anchor;

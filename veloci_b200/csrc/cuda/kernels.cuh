@@ -87,14 +87,15 @@ void launch_finalize_programs(cudaStream_t st, const QueryProgram* queries, uint
                               unsigned long long* stat_postings);
 
 // ---- tiles.cu ----
-// Classifies every (tile, request) pair: nothing to do / fast item (planes + at most
-// kFastMaxEntries posting entries, evaluated by plane_eval_kernel) / general item
-// (tile_eval_kernel).  Pass 0 counts, pass 1 writes the item and slice records; fast items
-// are grouped per tile, general items form one flat list.
+// Classifies every (tile, request) pair: nothing to do / plane-path item (the request has a
+// FastDesc and at most kFastMaxEntries postings of non-plane terms in the tile, all of them in
+// sparse buckets; evaluated by plane_eval_kernel) / general item (tile_eval_kernel).  Pass 0
+// counts, pass 1 writes the records; plane-path items are grouped per tile, general items
+// form one flat tile-major list with their slice records.
 struct ItemScanArgs {
     const QueryProgram* queries;
     uint32_t n_queries;
-    const FastDesc* fast;  // nullptr: no fast path in this batch
+    const FastDesc* fast;  // nullptr: no plane path in this batch
     const uint32_t* leaf_part;
     const PartSlices* slices;
     const PartQuery* parts;
@@ -109,13 +110,10 @@ struct ItemScanArgs {
     unsigned long long* counters;      // [0] general items, [1] general slices (zeroed before each pass)
     ItemRec* items;                    // general items
     SliceRec* slice_recs;              // general slices
-    // fast items, per tile: pass 0 accumulates counts in *_cursor, pass 1 uses them as cursors (zeroed before each pass)
-    uint32_t* fast_item_cursor;              // [n_tiles]
-    unsigned long long* fast_slice_cursor;   // [n_tiles]
-    const uint32_t* fast_item_begin;         // [n_tiles + 1] (pass 1)
-    const unsigned long long* fast_slice_begin;  // [n_tiles + 1] (pass 1)
-    ItemRec* fast_items;
-    SliceRec* fast_slices;
+    // plane-path items, per tile: pass 0 accumulates counts in the cursor, pass 1 uses it as cursor (zeroed before each pass)
+    uint32_t* fast_item_cursor;        // [n_tiles]
+    const uint32_t* fast_item_begin;   // [n_tiles + 1] (pass 1)
+    FastItem* fast_items;
 };
 void launch_item_scan(cudaStream_t st, const ItemScanArgs& a, bool fill);
 
@@ -171,17 +169,16 @@ void launch_level_fill(cudaStream_t st, const uint32_t* col, uint32_t col_n, uin
 void launch_build_fast_desc(cudaStream_t st, const QueryProgram* queries, uint32_t n, const uint32_t* leaf_part, const PartPlanes* part_planes, const float* wmax, FastDesc* out);
 
 struct PlaneArgs {
-    const ItemRec* items;                 // fast items, grouped per tile
+    const FastItem* items;                // plane-path items, grouped per tile
     const uint32_t* tile_item_begin;      // [n_tiles + 1]
-    const SliceRec* slice_recs;
     const FastDesc* fast;
-    const PostingsView* postings;
     const SparseEntry* sparse;
     PlaneSetView planes;
     const ColumnLevels* lev_dev;          // the column whose level bits are staged in shared memory (nullptr: none)
     ColumnLevels lev_hdr;                 // host copy of *lev_dev
-    uint32_t n_tiles, tile_log2, anchor_lo, anchor_hi;
-    uint32_t chunks_per_tile, n_units;    // work unit u = (tile u / chunks_per_tile, chunk u % chunks_per_tile of plane_unit_items() items)
+    uint32_t tile_log2, anchor_lo, anchor_hi;
+    // work unit u = (tile tile_begin + u / chunks_per_tile, chunk u % chunks_per_tile of unit_items items)
+    uint32_t tile_begin, unit_items, chunks_per_tile, n_units;
     // per-query state (shared with tile_eval_kernel)
     unsigned long long* heap;
     uint32_t heap_stride;
@@ -192,7 +189,6 @@ struct PlaneArgs {
     unsigned long long* stats;  // [0] items, [1] anchors evaluated exactly
 };
 size_t plane_kernel_smem(uint32_t tile_log2, uint32_t n_planes);
-uint32_t plane_unit_items();
 void launch_plane_eval(cudaStream_t st, const PlaneArgs& a, int n_sms);
 
 // Final ordering of each request's heap: merges `n_src` gathered heaps per query

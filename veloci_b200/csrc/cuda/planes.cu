@@ -27,19 +27,45 @@ namespace vdev {
 
 static const int kPlaneThreads = 512;
 static const int kPlaneWarps = kPlaneThreads / 32;
-static const uint32_t kUnitItems = 1024;   // items of one tile a CTA takes at a time
-static const uint32_t kQueueCap = 128;     // pending candidates of a warp (sparse mode)
-static const uint32_t kDenseGroup = 96;    // candidates in one 32-word group from which every lane walks its own word
-static const uint32_t kSurvCap = 64;
+static const uint32_t kQueueCap = 64;      // pending candidates of a warp (sparse mode)
+static const uint32_t kSurvCap = 32;
+static const uint32_t kHashSlots = 256;    // >= 2 * kFastMaxEntries
+static const uint32_t kHashEmpty = 0xFFFFFFFFu;
+static const uint32_t kEntRegs = kFastMaxEntries / 32;  // entries a lane holds
 
 struct WarpScratch {
-    FastDesc desc;                         // 144
+    FastDesc desc;                         // 160
+    float mult[kBoostLevels];              // largest boost multiplier of an anchor below the level's threshold
     uint32_t ebits[256];                   // anchors of the tile that have entries
-    uint32_t ent_key[kFastMaxEntries];
-    uint16_t ent_code[kFastMaxEntries];    // index in tile | leaf << 13
+    uint32_t hkey[kHashSlots];             // entries: index in tile | leaf << 13 -> largest score key
+    uint32_t hval[kHashSlots];
     uint16_t queue[kQueueCap];
+    uint16_t ent_idx[kFastMaxEntries];     // index in tile of entry r * 32 + lane
     unsigned long long surv[kSurvCap];
     unsigned long long merge[kFastMaxK + kSurvCap];
+    // state of the item being processed (warp-uniform)
+    unsigned long long tau;                // the request's k-th best so far (0: fewer than k hits)
+    float tau_score;                       // score of tau when pruning is possible, else 0
+    int lev[kFastMaxLeaves];               // per count of present parts: -2 no candidates, -1 every anchor, else boost level
+    uint32_t ns;                           // survivors pending in surv[]
+    uint32_t q, n_ent, tile_base_rel;
+    uint32_t lev_in_smem;
+    uint32_t pl_off[kFastMaxLeaves * kPartPlaneSlots];  // word offset of the request's planes in the staged tile
+    // which (boost function, param, column) mult[] was computed for
+    uint32_t mult_fun;
+    float mult_param;
+    const ColumnLevels* mult_lev;
+};
+
+struct CtaContext {  // kernel-constant values the out-of-line helpers need
+    const uint16_t* score;
+    size_t plane_stride;
+    unsigned long long* heap;
+    unsigned long long* tau;
+    uint32_t* lock;
+    uint32_t heap_stride, anchor_lo, W, pad;
+    const uint32_t* s_bits;
+    const uint32_t* s_lev;
 };
 
 // ---------------------------------------------------------------- index build
@@ -128,6 +154,7 @@ __global__ void build_fast_desc_kernel(const QueryProgram* __restrict__ queries,
                 d.ts[l][j] = pp.ts[j];
                 u[l] = fmaxf(u[l], pp.ts[j] * wmax[pp.plane[j]]);
             }
+            d.ub[l] = u[l] * 1.00001f;
         }
     }
     if (ok) {
@@ -161,16 +188,6 @@ void launch_build_fast_desc(cudaStream_t st, const QueryProgram* queries, uint32
 }
 
 // ---------------------------------------------------------------- plane evaluation
-struct ItemState {  // per-warp registers of the item being processed (warp-uniform unless noted)
-    uint32_t q, t, n_ent;
-    uint32_t L, k;
-    uint32_t tile_base_rel;  // first anchor of the tile, relative to anchor_lo
-    unsigned long long tau;
-    int lev[kFastMaxLeaves];  // per count of present parts: -2 no candidates, -1 every anchor, else boost level
-    uint32_t ns;              // survivors pending in scratch
-    bool lev_in_smem;
-};
-
 __device__ __forceinline__ float boost_mult(uint32_t fun, float x) {
     switch (fun) {
         case kBoostLog10: return log10f(x);
@@ -180,43 +197,45 @@ __device__ __forceinline__ float boost_mult(uint32_t fun, float x) {
 }
 
 // Which anchors still have to be evaluated, per number of parts present (see the file comment).
-__device__ __forceinline__ void compute_levels(const FastDesc& D, ItemState& s, uint32_t lane) {
+__device__ __forceinline__ void compute_levels(WarpScratch& S, uint32_t lane) {
+    const FastDesc& D = S.desc;
+    int lev[kFastMaxLeaves] = {-1, -1, -1, -1};
+    float tau_score = 0.0f;
+    if (S.tau != 0) {
+        const float ts = vbit::key_score((uint32_t)(S.tau >> 32));
+        if (ts > 1e-30f) tau_score = ts;
+    }
+    if (tau_score > 0.0f) {
+        if (D.flags & kFastBoost) {
+            const float m = S.mult[lane & (kBoostLevels - 1)];
 #pragma unroll
-    for (int i = 0; i < (int)kFastMaxLeaves; ++i) s.lev[i] = -1;
-    if (s.tau == 0) return;
-    const float tau_score = vbit::key_score((uint32_t)(s.tau >> 32));
-    if (!(tau_score > 1e-30f)) return;
-    if (D.flags & kFastBoost) {
-        float m = 0.0f;
-        if (lane < kBoostLevels) {
-            m = boost_mult(D.fb_fun, __ldg(&D.fb_lev->thr[lane]) + D.fb_param);
-            m = fmaxf(m, 0.0f) * 1.00001f + 1e-6f;  // anchors below the level's threshold multiply by at most this
-        }
-#pragma unroll
-        for (int i = 0; i < (int)kFastMaxLeaves; ++i) {
-            if ((uint32_t)i >= s.L) break;
-            const float B = D.bound[i];
-            if (B * D.fb_max_mult * 1.00001f < tau_score) {
-                s.lev[i] = -2;
-                continue;
+            for (int i = 0; i < (int)kFastMaxLeaves; ++i) {
+                const float B = D.bound[i];
+                const uint32_t mask = __ballot_sync(0xFFFFFFFFu, lane < kBoostLevels && B * m < tau_score);
+                lev[i] = B * D.fb_max_mult * 1.00001f < tau_score ? -2 : mask ? 31 - __clz((int)mask) : -1;
             }
-            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, lane < kBoostLevels && B * m < tau_score);
-            s.lev[i] = mask ? 31 - __clz((int)mask) : -1;
-        }
-    } else {
+        } else {
 #pragma unroll
-        for (int i = 0; i < (int)kFastMaxLeaves; ++i) {
-            if ((uint32_t)i >= s.L) break;
-            if (D.bound[i] * 1.00001f < tau_score) s.lev[i] = -2;
+            for (int i = 0; i < (int)kFastMaxLeaves; ++i)
+                if (D.bound[i] * 1.00001f < tau_score) lev[i] = -2;
         }
     }
+    __syncwarp();
+    if (lane == 0) {
+        S.tau_score = tau_score;
+#pragma unroll
+        for (int i = 0; i < (int)kFastMaxLeaves; ++i) S.lev[i] = (uint32_t)i < D.n_leaves ? lev[i] : -2;
+    }
+    __syncwarp();
 }
 
-// Merges the warp's pending survivors into the request's heap (sorted, k slots) under its lock; returns the new threshold.
-__device__ __noinline__ unsigned long long flush_survivors(unsigned long long* heap, unsigned long long* tau_slot, uint32_t* lock_slot, WarpScratch* Sp, uint32_t k, uint32_t ns, uint32_t lane) {
+// Merges the warp's pending survivors into the request's heap (sorted, k slots) under its lock and refreshes the threshold.
+__device__ __noinline__ void flush_survivors(const CtaContext* C, WarpScratch* Sp, uint32_t lane) {
     WarpScratch& S = *Sp;
+    const uint32_t q = S.q, k = S.desc.k, ns = S.ns;
+    unsigned long long* heap = C->heap + (size_t)q * C->heap_stride;
     if (lane == 0) {
-        while (atomicCAS(lock_slot, 0u, 1u) != 0u) __nanosleep(32);
+        while (atomicCAS(C->lock + q, 0u, 1u) != 0u) __nanosleep(32);
         __threadfence();
     }
     __syncwarp();
@@ -230,50 +249,70 @@ __device__ __noinline__ unsigned long long flush_survivors(unsigned long long* h
         uint32_t rank = 0;
         for (uint32_t j = 0; j < n; ++j) rank += S.merge[j] > key;
         if (rank < k) __stcg(heap + rank, key);
-        if (rank == k - 1) __stcg(tau_slot, key);
+        if (rank == k - 1) __stcg(C->tau + q, key);
     }
     __threadfence();
     __syncwarp();
-    const unsigned long long tau = __ldcg(tau_slot);
+    const unsigned long long tau = __ldcg(C->tau + q);
     __syncwarp();
-    if (lane == 0) atomicExch(lock_slot, 0u);
-    return tau;
+    if (lane == 0) {
+        atomicExch(C->lock + q, 0u);
+        S.tau = tau, S.ns = 0;
+    }
+    __syncwarp();
+    compute_levels(S, lane);
 }
 
-// Exact score of one anchor of the tile (index `idx`); returns its order key when it beats the threshold, else 0.
-__device__ __forceinline__ unsigned long long eval_candidate(const PlaneArgs& a, const WarpScratch& S, const ItemState& s, const uint32_t* __restrict__ s_bits, uint32_t W, uint32_t idx) {
+__device__ __forceinline__ uint32_t hash_slot(uint32_t code) { return (code * 0x9E3779B1u) >> 24; }
+
+__device__ __forceinline__ void hash_insert(WarpScratch& S, uint32_t code, uint32_t key) {
+    uint32_t h = hash_slot(code);
+    while (true) {
+        const uint32_t old = atomicCAS(&S.hkey[h], kHashEmpty, code);
+        if (old == kHashEmpty || old == code) break;
+        h = (h + 1u) & (kHashSlots - 1u);
+    }
+    atomicMax(&S.hval[h], key);
+}
+
+// Largest score key of the entries with this code, 0 when there is none.
+__device__ __forceinline__ uint32_t hash_lookup(const WarpScratch& S, uint32_t code) {
+    uint32_t h = hash_slot(code);
+    while (true) {
+        const uint32_t k = S.hkey[h];
+        if (k == code) return S.hval[h];
+        if (k == kHashEmpty) return 0u;
+        h = (h + 1u) & (kHashSlots - 1u);
+    }
+}
+
+// Exact score of one anchor of the tile (index `idx`): its order key.
+__device__ __forceinline__ unsigned long long eval_candidate(const CtaContext& C, const WarpScratch& S, uint32_t idx) {
     const FastDesc& D = S.desc;
     const uint32_t w = idx >> 5, bit = 1u << (idx & 31u);
-    const uint32_t rel = s.tile_base_rel + idx;
-    const bool in_e = s.n_ent != 0 && (S.ebits[w] & bit) != 0;
-    const size_t plane_stride = (size_t)a.planes.words * 32u;
+    const uint32_t rel = S.tile_base_rel + idx;
+    const bool in_e = S.n_ent != 0 && (S.ebits[w] & bit) != 0;
+    const uint32_t L = D.n_leaves;
     float sum = 0.0f, nd = 0.0f, v0 = 0.0f;
-#pragma unroll
-    for (uint32_t l = 0; l < kFastMaxLeaves; ++l) {
-        if (l >= s.L) break;
+#pragma unroll 1
+    for (uint32_t l = 0; l < L; ++l) {
         float v = 0.0f;
         const uint32_t np = D.n_planes[l];
-#pragma unroll
-        for (uint32_t j = 0; j < kPartPlaneSlots; ++j) {
-            if (j >= np) break;
-            const uint32_t p = D.plane[l][j];
-            if (s_bits[p * W + w] & bit) {
-                const unsigned short h = __ldg(a.planes.score + p * plane_stride + rel);
+#pragma unroll 1
+        for (uint32_t j = 0; j < np; ++j) {
+            if (C.s_bits[S.pl_off[l * kPartPlaneSlots + j] + w] & bit) {
+                const unsigned short h = __ldg(C.score + D.plane[l][j] * C.plane_stride + rel);
                 const float wgt = __fdiv_rn(__half2float(__ushort_as_half(h)), 100.0f);  // el.score.to_f32() / 100.0 (search_field.rs:426)
                 v = fmaxf(v, D.ts[l][j] * wgt);
             }
         }
-        if (in_e) {
-            const uint32_t code = idx | (l << 13);
-            for (uint32_t e = 0; e < s.n_ent; ++e)
-                if (S.ent_code[e] == code) v = fmaxf(v, __uint_as_float(S.ent_key[e] & 0x7FFFFFFFu));
-        }
+        if (in_e) v = fmaxf(v, __uint_as_float(hash_lookup(S, idx | (l << 13)) & 0x7FFFFFFFu));
         if (v >= 0.00001f) nd += 1.0f;
         sum += v;
         if (l == 0) v0 = v;
     }
-    float score = s.L == 1 ? v0 : sum * nd * nd;
-    const uint32_t anchor = a.anchor_lo + rel;
+    float score = L == 1 ? v0 : sum * nd * nd;
+    const uint32_t anchor = C.anchor_lo + rel;
     if (D.flags & kFastBoost) {
         if (anchor < D.fb_n) {
             const uint32_t bits = __ldg(D.fb_col + anchor);
@@ -289,32 +328,115 @@ __device__ __forceinline__ unsigned long long eval_candidate(const PlaneArgs& a,
     }
     uint32_t key = vbit::score_key(score);
     if (key == 0) key = 1;
-    const unsigned long long comp = ((unsigned long long)key << 32) | anchor;
-    return comp > s.tau ? comp : 0ull;
+    return ((unsigned long long)key << 32) | anchor;
 }
 
-__device__ __forceinline__ void push_survivors(const PlaneArgs& a, WarpScratch& S, ItemState& s, uint32_t lane, unsigned long long comp) {
+// Evaluates queue[from, from + count) (count <= 32), one anchor per lane; survivors go to the pending list.
+__device__ __noinline__ void drain(const CtaContext* C, WarpScratch* Sp, uint32_t lane, uint32_t from, uint32_t count) {
+    WarpScratch& S = *Sp;
+    unsigned long long comp = 0;
+    if (lane < count) comp = eval_candidate(*C, S, S.queue[from + lane]);
+    if (comp <= S.tau) comp = 0;
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, comp != 0);
     if (!m) return;
-    if (comp) S.surv[s.ns + __popc(m & ((1u << lane) - 1u))] = comp;
-    s.ns += __popc(m);
+    if (S.ns + __popc(m) > kSurvCap) {
+        flush_survivors(C, Sp, lane);
+        if (comp <= S.tau) comp = 0;
+    }
+    const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, comp != 0);
+    const uint32_t ns = S.ns;
     __syncwarp();
-    if (s.ns > kSurvCap - 32) {
-        s.tau = flush_survivors(a.heap + (size_t)s.q * a.heap_stride, a.tau + s.q, a.lock + s.q, &S, s.k, s.ns, lane);
-        s.ns = 0;
-        compute_levels(S.desc, s, lane);
+    if (comp) S.surv[ns + __popc(m2 & ((1u << lane) - 1u))] = comp;
+    if (lane == 0) S.ns = ns + __popc(m2);
+    __syncwarp();
+}
+
+// Appends the flagged lanes' anchors to the warp's candidate queue and evaluates full groups of 32.
+__device__ __forceinline__ void enqueue(const CtaContext* C, WarpScratch& S, uint32_t lane, bool flag, uint32_t idx, uint32_t& qn, uint32_t& ncand) {
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, flag);
+    if (!m) return;
+    if (flag) S.queue[qn + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
+    qn += __popc(m);
+    ncand += __popc(m);
+    __syncwarp();
+    if (qn >= 32) {
+        qn -= 32;
+        drain(C, &S, lane, qn, 32);
     }
 }
 
+struct ItemLoad {  // what the pipeline fetches one item ahead (per lane)
+    uint4 d;                      // lane < 10: 16-byte word of the request's FastDesc
+    unsigned long long tau;
+    uint2 ent[kEntRegs];          // entries lane, lane + 32, ... of the item (anchor, key)
+    uint32_t ent_leaf;            // 2 bits per held entry
+};
+
+__device__ __forceinline__ void load_item(const PlaneArgs& a, const FastItem& it, uint32_t lane, ItemLoad& o) {
+    o.d = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < 10) o.d = __ldg(reinterpret_cast<const uint4*>(a.fast + it.q) + lane);
+    o.tau = __ldcg(a.tau + it.q);
+    o.ent_leaf = 0;
+    const uint32_t n0 = it.n[0], n1 = n0 + it.n[1], n2 = n1 + it.n[2], n3 = n2 + it.n[3];
+#pragma unroll
+    for (uint32_t r = 0; r < kEntRegs; ++r) {
+        const uint32_t j = r * 32u + lane;
+        o.ent[r] = make_uint2(0u, 0u);
+        if (j < n3) {
+            const uint32_t l = (j >= n0) + (j >= n1) + (j >= n2);
+            const uint32_t at = l == 0 ? it.begin[0] + j : l == 1 ? it.begin[1] + (j - n0) : l == 2 ? it.begin[2] + (j - n1) : it.begin[3] + (j - n2);
+            o.ent[r] = __ldg(reinterpret_cast<const uint2*>(a.sparse + at));
+            o.ent_leaf |= l << (2u * r);
+        }
+    }
+}
+
+__device__ __forceinline__ FastItem load_record(const PlaneArgs& a, uint32_t at, uint32_t iend) {
+    FastItem it;
+    it.q = 0, it.pad = 0;
+#pragma unroll
+    for (int l = 0; l < (int)kFastMaxLeaves; ++l) it.n[l] = 0, it.begin[l] = 0;
+    if (at < iend) {
+        const uint4* p = reinterpret_cast<const uint4*>(a.items + at);
+        const uint4 lo = __ldg(p), hi = __ldg(p + 1);
+        it.q = lo.x, it.n[0] = (uint16_t)lo.y, it.n[1] = (uint16_t)(lo.y >> 16), it.n[2] = (uint16_t)lo.z, it.n[3] = (uint16_t)(lo.z >> 16);
+        it.begin[0] = lo.w, it.begin[1] = hi.x, it.begin[2] = hi.y, it.begin[3] = hi.z;
+    }
+    return it;
+}
+
+__device__ __forceinline__ FastItem shfl_item(const FastItem& mine, int src) {
+    FastItem it;
+    it.q = __shfl_sync(0xFFFFFFFFu, mine.q, src);
+    const uint32_t n01 = __shfl_sync(0xFFFFFFFFu, (uint32_t)mine.n[0] | ((uint32_t)mine.n[1] << 16), src);
+    const uint32_t n23 = __shfl_sync(0xFFFFFFFFu, (uint32_t)mine.n[2] | ((uint32_t)mine.n[3] << 16), src);
+    it.n[0] = (uint16_t)n01, it.n[1] = (uint16_t)(n01 >> 16), it.n[2] = (uint16_t)n23, it.n[3] = (uint16_t)(n23 >> 16);
+#pragma unroll
+    for (int l = 0; l < (int)kFastMaxLeaves; ++l) it.begin[l] = __shfl_sync(0xFFFFFFFFu, mine.begin[l], src);
+    it.pad = 0;
+    return it;
+}
+
+__device__ __forceinline__ uint32_t comp4(const uint4& v, int c) { return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w; }
+
 __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs a) {
     extern __shared__ __align__(16) uint32_t plane_smem[];
-    __shared__ uint32_t s_unit, s_next;
+    __shared__ uint32_t s_unit;
+    __shared__ CtaContext s_ctx;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t W = 1u << (a.tile_log2 - 5);
     uint32_t* s_bits = plane_smem;
     uint32_t* s_lev = s_bits + a.planes.n_planes * W;
     WarpScratch& S = reinterpret_cast<WarpScratch*>(s_lev + kBoostLevels * W)[warp];
+    const CtaContext* C = &s_ctx;
+    if (tid == 0) {
+        s_ctx.score = a.planes.score, s_ctx.plane_stride = (size_t)a.planes.words * 32u;
+        s_ctx.heap = a.heap, s_ctx.tau = a.tau, s_ctx.lock = a.lock, s_ctx.heap_stride = a.heap_stride;
+        s_ctx.anchor_lo = a.anchor_lo, s_ctx.W = W, s_ctx.pad = 0, s_ctx.s_bits = s_bits, s_ctx.s_lev = s_lev;
+    }
     for (uint32_t i = lane; i < 256; i += 32) S.ebits[i] = 0;
+    for (uint32_t i = lane; i < kHashSlots; i += 32) S.hkey[i] = kHashEmpty, S.hval[i] = 0;
+    if (lane == 0) S.mult_lev = nullptr, S.mult_fun = 0xFFFFFFFFu, S.mult_param = 0.0f;
     unsigned long long st_cand = 0, st_items = 0;  // lane 0
 
     while (true) {
@@ -323,10 +445,10 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
         __syncthreads();
         const uint32_t unit = s_unit;
         if (unit >= a.n_units) break;
-        const uint32_t t = unit / a.chunks_per_tile, c = unit % a.chunks_per_tile;
+        const uint32_t t = a.tile_begin + unit / a.chunks_per_tile, c = unit % a.chunks_per_tile;
         const uint32_t tb = a.tile_item_begin[t], te = a.tile_item_begin[t + 1];
-        if (te - tb <= c * kUnitItems) continue;
-        const uint32_t ibeg = tb + c * kUnitItems, iend = min(te, ibeg + kUnitItems);
+        if (te - tb <= c * a.unit_items) continue;
+        const uint32_t ibeg = tb + c * a.unit_items, iend = min(te, ibeg + a.unit_items);
         {   // stage the tile's plane bits and boost level bits
             const uint32_t w4 = W >> 2;
             const uint32_t n4 = a.planes.n_planes * w4;
@@ -341,161 +463,194 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                     reinterpret_cast<uint4*>(s_lev)[i] = __ldg(reinterpret_cast<const uint4*>(a.lev_hdr.bits + (size_t)p * a.lev_hdr.words + (size_t)t * W) + j);
                 }
             }
-            if (tid == 0) s_next = ibeg + 2 * kPlaneWarps;
         }
         __syncthreads();
+        const uint32_t tile_base_rel = t << a.tile_log2;
+        const uint32_t tile_base = a.anchor_lo + tile_base_rel;
 
-        // two-deep software pipeline over the warp's items: item record two ahead, descriptor + threshold one ahead
-        uint32_t idx0 = ibeg + warp, idx1 = ibeg + kPlaneWarps + warp;
-        ItemRec it0, it1;
-        it0.q = 0, it1.q = 0;
-        if (idx0 < iend) it0 = a.items[idx0];
-        if (idx1 < iend) it1 = a.items[idx1];
-        uint4 d0 = make_uint4(0u, 0u, 0u, 0u);
-        unsigned long long tau0 = 0;
-        if (idx0 < iend) {
-            if (lane < 9) d0 = __ldg(reinterpret_cast<const uint4*>(a.fast + it0.q) + lane);
-            tau0 = __ldcg(a.tau + it0.q);
-        }
-        while (idx0 < iend) {
-            uint32_t idx2 = 0;
-            if (lane == 0) idx2 = atomicAdd(&s_next, 1u);
-            idx2 = __shfl_sync(0xFFFFFFFFu, idx2, 0);
-            ItemRec it2;
-            it2.q = 0;
-            if (idx2 < iend) it2 = a.items[idx2];
-            uint4 d1 = make_uint4(0u, 0u, 0u, 0u);
-            unsigned long long tau1 = 0;
-            if (idx1 < iend) {
-                if (lane < 9) d1 = __ldg(reinterpret_cast<const uint4*>(a.fast + it1.q) + lane);
-                tau1 = __ldcg(a.tau + it1.q);
+        // The warp takes items ibeg + warp, + kPlaneWarps, ...: records are fetched 32 items at a time (one per lane),
+        // descriptor + threshold + entries one item ahead of the evaluation.
+        const uint32_t first = ibeg + warp;
+        if (first >= iend) continue;
+        const uint32_t n_mine = (iend - first + kPlaneWarps - 1) / kPlaneWarps;
+        FastItem mine = load_record(a, first + lane * kPlaneWarps, iend);
+        FastItem it_cur = shfl_item(mine, 0), it_nxt = it_cur;
+        ItemLoad cur, nxt;
+        load_item(a, it_cur, lane, cur);
+        nxt = cur;
+#pragma unroll 1
+        for (uint32_t i = 0; i < n_mine; ++i) {
+            const bool has_next = i + 1 < n_mine;
+            if (has_next) {
+                if (((i + 1) & 31u) == 0) mine = load_record(a, first + (i + 1 + lane) * kPlaneWarps, iend);
+                it_nxt = shfl_item(mine, (int)((i + 1) & 31u));
+                load_item(a, it_nxt, lane, nxt);
             }
 
-            // ---- item (t, it0.q)
+            // ---- item (t, it_cur.q)
             __syncwarp();
-            if (lane < 9) reinterpret_cast<uint4*>(&S.desc)[lane] = d0;
+            if (lane < 10) reinterpret_cast<uint4*>(&S.desc)[lane] = cur.d;
+            const uint32_t n_ent = (uint32_t)it_cur.n[0] + it_cur.n[1] + it_cur.n[2] + it_cur.n[3];
             __syncwarp();
             const FastDesc& D = S.desc;
-            ItemState s;
-            s.q = it0.q, s.t = t, s.n_ent = it0.npost, s.L = D.n_leaves, s.k = D.k, s.tau = tau0, s.ns = 0;
-            s.tile_base_rel = t << a.tile_log2;
-            s.lev_in_smem = D.fb_lev == a.lev_dev;
-            const uint32_t tile_base = a.anchor_lo + s.tile_base_rel;
-            if (s.n_ent) {  // entries: postings of the request's non-plane terms inside the tile
-                uint32_t ne = 0;
-                for (uint32_t si = 0; si < it0.n_slices; ++si) {
-                    const SliceRec sr = a.slice_recs[it0.slice_begin + si];
-                    for (uint32_t j = lane; j < sr.n; j += 32) {
-                        uint32_t anchor, key;
-                        if (sr.kind == 0) {
-                            const Posting p = a.postings[sr.postings].post[sr.begin + j];
-                            anchor = p.anchor, key = vbit::score_key(sr.term_score * p.weight);  // hit.score * (el.score / 100.0) (:426)
-                        } else {
-                            const SparseEntry e = a.sparse[sr.begin + j];
-                            anchor = e.anchor, key = e.key;
-                        }
-                        const uint32_t idx = anchor - tile_base;
-                        S.ent_code[ne + j] = (uint16_t)(idx | ((uint32_t)sr.leaf << 13));
-                        S.ent_key[ne + j] = key;
-                        atomicOr(&S.ebits[idx >> 5], 1u << (idx & 31u));
-                    }
-                    ne += sr.n;
-                }
-                __syncwarp();
+            const uint32_t L = D.n_leaves;
+            if (lane == 0) {
+                S.q = it_cur.q, S.tau = cur.tau, S.ns = 0, S.n_ent = n_ent, S.tile_base_rel = tile_base_rel;
+                S.lev_in_smem = D.fb_lev == a.lev_dev ? 1u : 0u;
             }
-            compute_levels(D, s, lane);
-            // word offsets of the request's planes in the staged tile
-            uint32_t pb[kFastMaxLeaves][kPartPlaneSlots];
+            if (lane < kFastMaxLeaves * kPartPlaneSlots) S.pl_off[lane] = (uint32_t)D.plane[lane / kPartPlaneSlots][lane % kPartPlaneSlots] * W;
+            const bool need_mult = (D.flags & kFastBoost) && (S.mult_lev != D.fb_lev || S.mult_fun != D.fb_fun || S.mult_param != D.fb_param);
+            __syncwarp();
+            if (need_mult) {
+                if (lane < kBoostLevels) {
+                    const float m = boost_mult(D.fb_fun, __ldg(&D.fb_lev->thr[lane]) + D.fb_param);
+                    S.mult[lane] = fmaxf(m, 0.0f) * 1.00001f + 1e-6f;
+                }
+                if (lane == 0) S.mult_lev = D.fb_lev, S.mult_fun = D.fb_fun, S.mult_param = D.fb_param;
+            }
+            uint32_t own = 0;  // bit r: this lane's entry r is the first of its anchor
+            if (n_ent) {
 #pragma unroll
-            for (uint32_t l = 0; l < kFastMaxLeaves; ++l)
-#pragma unroll
-                for (uint32_t j = 0; j < kPartPlaneSlots; ++j) pb[l][j] = (uint32_t)D.plane[l][j] * W;
+                for (uint32_t r = 0; r < kEntRegs; ++r) {
+                    if (r * 32u + lane < n_ent) {
+                        const uint32_t idx = cur.ent[r].x - tile_base, l = (cur.ent_leaf >> (2u * r)) & 3u;
+                        const uint32_t bit = 1u << (idx & 31u);
+                        if (!(atomicOr(&S.ebits[idx >> 5], bit) & bit)) own |= 1u << r;
+                        S.ent_idx[r * 32u + lane] = (uint16_t)idx;
+                        hash_insert(S, idx | (l << 13), cur.ent[r].y);
+                    }
+                }
+            }
+            __syncwarp();
+            compute_levels(S, lane);
             const uint32_t np0 = D.n_planes[0], np1 = D.n_planes[1], np2 = D.n_planes[2], np3 = D.n_planes[3];
+            const bool lev_in_smem = S.lev_in_smem != 0;
             const uint32_t* lev_glob = (D.flags & kFastBoost) ? D.fb_lev->bits + (size_t)t * W : nullptr;
             const uint32_t lev_words = (D.flags & kFastBoost) ? D.fb_lev->words : 0u;
-
             uint32_t cnt = 0, qn = 0, ncand = 0;
-            for (uint32_t w = lane; w < W; w += 32) {
-                uint32_t x[kFastMaxLeaves] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                for (uint32_t j = 0; j < kPartPlaneSlots; ++j) {
-                    if (j < np0) x[0] |= s_bits[pb[0][j] + w];
-                    if (j < np1) x[1] |= s_bits[pb[1][j] + w];
-                    if (j < np2) x[2] |= s_bits[pb[2][j] + w];
-                    if (j < np3) x[3] |= s_bits[pb[3][j] + w];
-                }
-                const uint32_t e = s.n_ent ? S.ebits[w] : 0u;
-                cnt += __popc(x[0] | x[1] | x[2] | x[3] | e);
-                // bit-sliced count of the parts present per anchor
-                uint32_t ones = x[0], twos = 0, fours = 0, cy, cy2;
-                cy = ones & x[1], ones ^= x[1], twos ^= cy;
-                cy = ones & x[2], ones ^= x[2], cy2 = twos & cy, twos ^= cy, fours |= cy2;
-                cy = ones & x[3], ones ^= x[3], cy2 = twos & cy, twos ^= cy, fours |= cy2;
-                const uint32_t ex[kFastMaxLeaves] = {ones & ~twos & ~fours, twos & ~ones & ~fours, ones & twos, fours};
-                uint32_t cm = e;
-#pragma unroll
-                for (int i = 0; i < (int)kFastMaxLeaves; ++i) {
-                    if ((uint32_t)i >= s.L) break;
-                    const int lv = s.lev[i];
-                    if (lv == -2 || ex[i] == 0) continue;
-                    uint32_t lw = 0xFFFFFFFFu;
-                    if (lv >= 0) lw = s.lev_in_smem ? s_lev[(uint32_t)lv * W + w] : __ldg(lev_glob + (size_t)lv * lev_words + w);
-                    cm |= ex[i] & lw;
-                }
-                if (__ballot_sync(0xFFFFFFFFu, cm != 0) == 0) continue;
-                const uint32_t pc = __popc(cm);
-                uint32_t incl = pc;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                    if ((int)lane >= o) incl += y;
-                }
-                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                ncand += total;
-                if (total >= kDenseGroup) {  // densely hit group (threshold not converged yet): every lane walks its own word
-                    while (__ballot_sync(0xFFFFFFFFu, cm != 0)) {
-                        unsigned long long comp = 0;
-                        if (cm) {
-                            const uint32_t idx = w * 32u + (uint32_t)__ffs((int)cm) - 1u;
-                            cm &= cm - 1u;
-                            comp = eval_candidate(a, S, s, s_bits, W, idx);
+
+            // anchors with entries: bounded one by one (entry scores are known exactly, plane parts by their bound)
+            if (n_ent) {
+#pragma unroll 1
+                for (uint32_t r = 0; r < kEntRegs; ++r) {
+                    if (r * 32u >= n_ent) break;
+                    const bool mine_r = (own >> r) & 1u;
+                    const uint32_t idx = mine_r ? S.ent_idx[r * 32u + lane] : 0u;
+                    bool cand = mine_r;
+                    const float tau_score = S.tau_score;
+                    if (mine_r && tau_score > 0.0f) {
+                        const uint32_t w = idx >> 5, bit = 1u << (idx & 31u);
+                        float sum_ub = 0.0f;
+                        uint32_t n = 0;
+#pragma unroll 1
+                        for (uint32_t l = 0; l < L; ++l) {
+                            const uint32_t ev = hash_lookup(S, idx | (l << 13));
+                            uint32_t pbits = 0;
+                            const uint32_t np = D.n_planes[l];
+#pragma unroll 1
+                            for (uint32_t j = 0; j < np; ++j) pbits |= s_bits[S.pl_off[l * kPartPlaneSlots + j] + w];
+                            const bool by_plane = (pbits & bit) != 0;
+                            if (ev || by_plane) {
+                                n += 1;
+                                sum_ub += fmaxf(ev ? __uint_as_float(ev & 0x7FFFFFFFu) : 0.0f, by_plane ? D.ub[l] : 0.0f);
+                            }
                         }
-                        push_survivors(a, S, s, lane, comp);
+                        const float B = (L == 1 ? sum_ub : sum_ub * (float)(n * n)) * 1.00001f;
+                        if (D.flags & kFastBoost) {
+                            if (B * D.fb_max_mult * 1.00001f < tau_score) cand = false;
+                            else {
+                                // deepest level whose outside cannot reach the threshold (mult[] ascends): the anchor must be inside it
+                                int lo = -1;
+#pragma unroll
+                                for (int step = (int)kBoostLevels / 2; step > 0; step >>= 1)
+                                    if (B * S.mult[lo + step] < tau_score) lo += step;
+                                if (lo + 1 < (int)kBoostLevels && B * S.mult[lo + 1] < tau_score) lo += 1;
+                                if (lo >= 0) {
+                                    const uint32_t lw = lev_in_smem ? s_lev[(uint32_t)lo * W + w] : __ldg(lev_glob + (size_t)lo * lev_words + w);
+                                    cand = (lw & bit) != 0;
+                                }
+                            }
+                        } else if (B * 1.00001f < tau_score) {
+                            cand = false;
+                        }
                     }
-                } else {
-                    uint32_t at = qn + incl - pc;
-                    while (cm) {
-                        S.queue[at++] = (uint16_t)(w * 32u + (uint32_t)__ffs((int)cm) - 1u);
-                        cm &= cm - 1u;
-                    }
-                    qn += total;
-                    __syncwarp();
-                    while (qn >= 32) {
-                        qn -= 32;
-                        const unsigned long long comp = eval_candidate(a, S, s, s_bits, W, S.queue[qn + lane]);
-                        push_survivors(a, S, s, lane, comp);
-                    }
-                    __syncwarp();
+                    enqueue(C, S, lane, cand, idx, qn, ncand);
                 }
             }
-            if (qn) {
-                unsigned long long comp = 0;
-                if (lane < qn) comp = eval_candidate(a, S, s, s_bits, W, S.queue[lane]);
-                push_survivors(a, S, s, lane, comp);
+
+            // plane sweep: four 32-anchor words per lane and step
+#pragma unroll 1
+            for (uint32_t w4 = lane; w4 < (W >> 2); w4 += 32) {
+                uint4 ones = make_uint4(0u, 0u, 0u, 0u), twos = ones, fours = ones;
+                auto add_part = [&](uint32_t l, uint32_t np) {
+                    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+                    for (uint32_t j = 0; j < np; ++j) {
+                        const uint4 v = reinterpret_cast<const uint4*>(s_bits + S.pl_off[l * kPartPlaneSlots + j])[w4];
+                        x.x |= v.x, x.y |= v.y, x.z |= v.z, x.w |= v.w;
+                    }
+                    uint32_t cy, cy2;
+                    cy = ones.x & x.x, ones.x ^= x.x, cy2 = twos.x & cy, twos.x ^= cy, fours.x |= cy2;
+                    cy = ones.y & x.y, ones.y ^= x.y, cy2 = twos.y & cy, twos.y ^= cy, fours.y |= cy2;
+                    cy = ones.z & x.z, ones.z ^= x.z, cy2 = twos.z & cy, twos.z ^= cy, fours.z |= cy2;
+                    cy = ones.w & x.w, ones.w ^= x.w, cy2 = twos.w & cy, twos.w ^= cy, fours.w |= cy2;
+                };
+                add_part(0, np0);
+                if (L > 1) add_part(1, np1);
+                if (L > 2) add_part(2, np2);
+                if (L > 3) add_part(3, np3);
+                uint4 e = make_uint4(0u, 0u, 0u, 0u);
+                if (n_ent) e = reinterpret_cast<const uint4*>(S.ebits)[w4];
+                cnt += __popc(ones.x | twos.x | fours.x | e.x) + __popc(ones.y | twos.y | fours.y | e.y) + __popc(ones.z | twos.z | fours.z | e.z) + __popc(ones.w | twos.w | fours.w | e.w);
+                uint32_t cm[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int i2 = 0; i2 < (int)kFastMaxLeaves; ++i2) {
+                    const int lv = S.lev[i2];
+                    if (lv == -2) continue;
+                    uint4 ex;  // anchors with exactly i2 + 1 parts present
+                    if (i2 == 0) ex = make_uint4(ones.x & ~twos.x & ~fours.x, ones.y & ~twos.y & ~fours.y, ones.z & ~twos.z & ~fours.z, ones.w & ~twos.w & ~fours.w);
+                    else if (i2 == 1) ex = make_uint4(twos.x & ~ones.x & ~fours.x, twos.y & ~ones.y & ~fours.y, twos.z & ~ones.z & ~fours.z, twos.w & ~ones.w & ~fours.w);
+                    else if (i2 == 2) ex = make_uint4(ones.x & twos.x, ones.y & twos.y, ones.z & twos.z, ones.w & twos.w);
+                    else ex = fours;
+                    if (lv >= 0) {
+                        uint4 lw;
+                        if (lev_in_smem) lw = reinterpret_cast<const uint4*>(s_lev + (uint32_t)lv * W)[w4];
+                        else lw = __ldg(reinterpret_cast<const uint4*>(lev_glob + (size_t)lv * lev_words) + w4);
+                        ex.x &= lw.x, ex.y &= lw.y, ex.z &= lw.z, ex.w &= lw.w;
+                    }
+                    cm[0] |= ex.x, cm[1] |= ex.y, cm[2] |= ex.z, cm[3] |= ex.w;
+                }
+                cm[0] &= ~e.x, cm[1] &= ~e.y, cm[2] &= ~e.z, cm[3] &= ~e.w;  // anchors with entries were handled above
+                if (__ballot_sync(0xFFFFFFFFu, (cm[0] | cm[1] | cm[2] | cm[3]) != 0) == 0) continue;
+#pragma unroll 1
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    uint32_t m = c4 == 0 ? cm[0] : c4 == 1 ? cm[1] : c4 == 2 ? cm[2] : cm[3];
+                    while (__ballot_sync(0xFFFFFFFFu, m != 0)) {
+                        const bool flag = m != 0;
+                        const uint32_t idx = (w4 * 4u + (uint32_t)c4) * 32u + (uint32_t)__ffs((int)m) - 1u;
+                        m &= m - 1u;
+                        enqueue(C, S, lane, flag, idx, qn, ncand);
+                    }
+                }
             }
-            if (s.ns) flush_survivors(a.heap + (size_t)s.q * a.heap_stride, a.tau + s.q, a.lock + s.q, &S, s.k, s.ns, lane);
+            if (qn) drain(C, &S, lane, 0, qn);
+            if (S.ns) flush_survivors(C, &S, lane);
             for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
             if (lane == 0) {
-                if (cnt) atomicAdd(a.num_hits + s.q, (unsigned long long)cnt);
+                if (cnt) atomicAdd(a.num_hits + it_cur.q, (unsigned long long)cnt);
                 st_cand += ncand, st_items += 1;
             }
-            if (s.n_ent) {  // leave the entry bitmap zeroed
+            if (n_ent) {  // leave the entry bitmap and the hash table empty
                 __syncwarp();
-                for (uint32_t e = lane; e < s.n_ent; e += 32) S.ebits[(S.ent_code[e] & 0x1FFFu) >> 5] = 0;
+#pragma unroll
+                for (uint32_t r = 0; r < kEntRegs; ++r)
+                    if (r * 32u + lane < n_ent) S.ebits[(cur.ent[r].x - tile_base) >> 5] = 0;
+                for (uint32_t j = lane; j < kHashSlots / 4; j += 32) {
+                    reinterpret_cast<uint4*>(S.hkey)[j] = make_uint4(kHashEmpty, kHashEmpty, kHashEmpty, kHashEmpty);
+                    reinterpret_cast<uint4*>(S.hval)[j] = make_uint4(0u, 0u, 0u, 0u);
+                }
             }
-
-            idx0 = idx1, it0 = it1, d0 = d1, tau0 = tau1;
-            idx1 = idx2, it1 = it2;
+            cur = nxt, it_cur = it_nxt;
         }
     }
     if (lane == 0 && st_items) {
@@ -510,12 +665,10 @@ static size_t plane_smem_bytes(uint32_t tile_log2, uint32_t n_planes) {
 }
 
 size_t plane_kernel_smem(uint32_t tile_log2, uint32_t n_planes) {
-    if (tile_log2 < 10 || tile_log2 > kPlaneTileLog2 || n_planes > kMaxPlanes) return 0;
+    if (tile_log2 < 12 || tile_log2 > kPlaneTileLog2 || n_planes > kMaxPlanes) return 0;
     const size_t need = plane_smem_bytes(tile_log2, n_planes);
     return need + 1024 <= 227 * 1024 ? need : 0;
 }
-
-uint32_t plane_unit_items() { return kUnitItems; }
 
 void launch_plane_eval(cudaStream_t st, const PlaneArgs& a, int n_sms) {
     if (a.n_units == 0) return;

@@ -38,18 +38,22 @@ static const uint32_t kSliceChunk = 64;     // slice records staged in shared me
 // ---------------------------------------------------------------- item scan
 // One thread per (tile, request), tile-major.  Pass 0 counts the non-empty items and
 // their slices; pass 1 writes them.  A request with a FastDesc takes the plane path in
-// every tile where its non-plane terms have at most kFastMaxEntries postings: those
-// items carry only the slices of the non-plane terms and are grouped per tile (per-tile
-// cursors).  Everything else becomes a general item with all its slices; blocks reserve
-// general output ranges in index order, so that list stays (nearly) tile-major.
+// every tile where its non-plane terms have at most kFastMaxEntries postings, all in the
+// parts' sparse tile buckets: those items only record the bucket ranges and are grouped
+// per tile (per-tile cursors).  Everything else becomes a general item with all its
+// slices; blocks reserve general output ranges in index order, so that list stays
+// (nearly) tile-major.
 template <bool FILL>
 __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
     __shared__ uint32_t s_warp_items[8], s_warp_slices[8];
     __shared__ unsigned long long s_base_items, s_base_slices;
     const unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t all_slices = 0, all_post = 0, ent_slices = 0, ent_post = 0, t = 0, q = 0;
-    bool plane_hit = false, fastq = false;
+    uint32_t all_slices = 0, all_post = 0, ent_post = 0, t = 0, q = 0;
+    bool plane_hit = false, fastq = false, fast_fits = true;
+    FastItem fi;
+    fi.q = 0, fi.pad = 0;
+    for (uint32_t l = 0; l < kFastMaxLeaves; ++l) fi.n[l] = 0, fi.begin[l] = 0;
     QueryProgram qp;
     qp.active = 0;
     if (i < a.n_items_total) {
@@ -64,46 +68,39 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
                 const uint32_t* trow = a.toff + (size_t)a.g_row[ps.m_begin + r] * (a.n_tiles + 1);
                 const uint32_t n = trow[t + 1] - trow[t];
                 all_post += n, all_slices += n ? 1u : 0u;
-                if (fastq && a.g_plane[ps.m_begin + r] != kNoValue) plane_hit = plane_hit || n != 0;
-                else ent_post += n, ent_slices += n ? 1u : 0u;
+                if (fastq) {
+                    if (a.g_plane[ps.m_begin + r] != kNoValue) plane_hit = plane_hit || n != 0;
+                    else if (n) fast_fits = false;  // a frequent term without a plane: general path
+                }
             }
             if (ps.n_match != ps.n_dense) {
                 const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
-                const uint32_t n = brow[t + 1] - brow[t];
+                const uint32_t s = brow[t], n = brow[t + 1] - s;
                 all_post += n, all_slices += n ? 1u : 0u;
-                ent_post += n, ent_slices += n ? 1u : 0u;
+                ent_post += n;
+                if (fastq && l < kFastMaxLeaves) {
+                    const unsigned long long at = ps.sparse_base + s;
+                    if (at + n > 0xFFFFFFFFull) fast_fits = false;
+                    fi.n[l] = (uint16_t)min(n, 0xFFFFu), fi.begin[l] = (uint32_t)at;
+                }
             }
         }
     }
-    const bool fast_item = fastq && ent_post <= kFastMaxEntries && (plane_hit || ent_post != 0);
-    const bool general_item = !(fastq && ent_post <= kFastMaxEntries) && all_post != 0;
+    fast_fits = fastq && fast_fits && ent_post <= kFastMaxEntries;
+    const bool fast_item = fast_fits && (plane_hit || ent_post != 0);
+    const bool general_item = !fast_fits && all_post != 0;
     const uint32_t n_slices = general_item ? all_slices : 0u;
 
     // ---- plane-path items: per-tile cursors, one atomic per (warp, tile)
-    uint32_t fast_item_at = 0;
-    unsigned long long fast_slice_at = 0;
     {
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, fast_item ? t : 0xFFFFFFFFu);
-        uint32_t slices_before = 0, slices_total = 0;
-        for (int src = 0; src < 32; ++src) {
-            const uint32_t v = __shfl_sync(0xFFFFFFFFu, ent_slices, src);
-            if ((peers >> src) & 1u) {
-                slices_total += v;
-                if (src < (int)lane) slices_before += v;
-            }
-        }
         const int leader = __ffs((int)peers) - 1;
         uint32_t base_i = 0;
-        unsigned long long base_s = 0;
-        if (fast_item && (int)lane == leader) {
-            base_i = atomicAdd(a.fast_item_cursor + t, (uint32_t)__popc(peers));
-            if (slices_total) base_s = atomicAdd(a.fast_slice_cursor + t, (unsigned long long)slices_total);
-        }
+        if (fast_item && (int)lane == leader) base_i = atomicAdd(a.fast_item_cursor + t, (uint32_t)__popc(peers));
         base_i = __shfl_sync(0xFFFFFFFFu, base_i, leader);
-        base_s = __shfl_sync(0xFFFFFFFFu, base_s, leader);
         if (FILL && fast_item) {
-            fast_item_at = a.fast_item_begin[t] + base_i + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-            fast_slice_at = a.fast_slice_begin[t] + base_s + slices_before;
+            fi.q = q;
+            a.fast_items[a.fast_item_begin[t] + base_i + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = fi;
         }
     }
 
@@ -127,28 +124,18 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
     }
     if (!FILL) return;
     __syncthreads();
-    if (!has && !fast_item) return;
+    if (!has) return;
+    const unsigned long long item_at = s_base_items + wi + xi - has;
+    unsigned long long slice_at = s_base_slices + ws + xs - n_slices;
     ItemRec rec;
-    rec.q = q, rec.t = t;
-    unsigned long long slice_at;
-    SliceRec* slice_out;
-    if (fast_item) {
-        slice_at = fast_slice_at, slice_out = a.fast_slices;
-        rec.slice_begin = slice_at, rec.n_slices = ent_slices, rec.npost = ent_post;
-        a.fast_items[fast_item_at] = rec;
-        if (ent_post == 0) return;
-    } else {
-        slice_at = s_base_slices + ws + xs - n_slices, slice_out = a.slice_recs;
-        rec.slice_begin = slice_at, rec.n_slices = n_slices, rec.npost = all_post;
-        a.items[s_base_items + wi + xi - has] = rec;
-    }
+    rec.q = q, rec.t = t, rec.slice_begin = slice_at, rec.n_slices = n_slices, rec.npost = all_post;
+    a.items[item_at] = rec;
     uint32_t task_at = 0;
     for (uint32_t l = 0; l < qp.n_leaves; ++l) {
         const uint32_t part = a.leaf_part[qp.leaf_begin + l];
         const PartSlices ps = a.slices[part];
         for (uint32_t r = 0; r < ps.n_dense; ++r) {
             const uint32_t mi = ps.m_begin + r;
-            if (fast_item && a.g_plane[mi] != kNoValue) continue;
             const uint32_t* trow = a.toff + (size_t)a.g_row[mi] * (a.n_tiles + 1);
             const uint32_t s = trow[t], e = trow[t + 1];
             if (e == s) continue;
@@ -156,7 +143,7 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
             sr.begin = a.g_begin[mi] + s, sr.n = e - s, sr.term_score = a.g_score[mi], sr.task_begin = task_at;
             sr.leaf = (uint16_t)l, sr.kind = 0, sr.single = ps.n_match == 1 ? 1 : 0, sr.postings = a.parts[part].postings, sr.pad = 0;
             task_at += (sr.n + kTaskPostings - 1) / kTaskPostings;
-            slice_out[slice_at++] = sr;
+            a.slice_recs[slice_at++] = sr;
         }
         if (ps.n_match != ps.n_dense) {
             const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
@@ -166,7 +153,7 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
             sr.begin = ps.sparse_base + s, sr.n = e - s, sr.term_score = 0.0f, sr.task_begin = task_at;
             sr.leaf = (uint16_t)l, sr.kind = 1, sr.single = 0, sr.postings = 0, sr.pad = 0;
             task_at += (sr.n + kTaskPostings - 1) / kTaskPostings;
-            slice_out[slice_at++] = sr;
+            a.slice_recs[slice_at++] = sr;
         }
     }
 }

@@ -94,6 +94,7 @@ void vgpu_index_close(vgpu_index* idx) {
     if (!idx) return;
     if (idx->ix) cudaSetDevice(idx->ix->device);
     delete idx;
+    vdev::ScratchPool::instance().trim();
 }
 
 int32_t vgpu_index_info(const vgpu_index* idx, uint64_t* num_docs, uint64_t* anchor_lo, uint64_t* anchor_hi, uint64_t* device_bytes) {

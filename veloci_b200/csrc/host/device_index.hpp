@@ -28,6 +28,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -50,31 +51,103 @@ struct CudaError : std::runtime_error {
             throw vdev::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
     } while (0)
 
+// Device allocations are recycled through a process-wide pool (per device, size classes of a
+// quarter octave): a batch's scratch buffers come back from the previous batch instead of
+// cudaMalloc / cudaFree, which cost milliseconds and synchronise the device.
+class ScratchPool {
+   public:
+    static ScratchPool& instance() {
+        static ScratchPool pool;
+        return pool;
+    }
+    static size_t size_class(size_t bytes) {
+        if (bytes <= 512) return 512;
+        int top = 63 - __builtin_clzll((unsigned long long)bytes);
+        const size_t step = (size_t)1 << (top - 2);
+        return (bytes + step - 1) / step * step;
+    }
+    void* take(size_t cls) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            auto it = free_.find(std::make_pair(dev, cls));
+            if (it != free_.end() && !it->second.empty()) {
+                void* p = it->second.back();
+                it->second.pop_back();
+                cached_ -= cls;
+                return p;
+            }
+        }
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, cls);
+        if (e != cudaSuccess) {
+            trim();
+            e = cudaMalloc(&p, cls);
+        }
+        if (e != cudaSuccess) throw std::runtime_error(std::string("cudaMalloc of ") + std::to_string(cls) + " bytes failed: " + cudaGetErrorString(e));
+        return p;
+    }
+    void give(void* p, size_t cls) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            if (cached_ + cls <= kMaxCached) {
+                free_[std::make_pair(dev, cls)].push_back(p);
+                cached_ += cls;
+                return;
+            }
+        }
+        cudaFree(p);
+    }
+    void trim() {  // releases everything cached (all devices)
+        std::lock_guard<std::mutex> g(mu_);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto& kv : free_) {
+            cudaSetDevice(kv.first.first);
+            for (void* p : kv.second) cudaFree(p);
+        }
+        cudaSetDevice(cur);
+        free_.clear();
+        cached_ = 0;
+    }
+
+   private:
+    static constexpr size_t kMaxCached = (size_t)24 << 30;
+    std::mutex mu_;
+    std::map<std::pair<int, size_t>, std::vector<void*>> free_;
+    size_t cached_ = 0;
+};
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    size_t cls = 0;  // pool size class of the allocation
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr, o.n = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), cls(o.cls) { o.p = nullptr, o.n = 0, o.cls = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept {
         if (this != &o) {
             release();
-            p = o.p, n = o.n;
-            o.p = nullptr, o.n = 0;
+            p = o.p, n = o.n, cls = o.cls;
+            o.p = nullptr, o.n = 0, o.cls = 0;
         }
         return *this;
     }
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
-        p = nullptr, n = 0;
+        if (p) ScratchPool::instance().give(p, cls);
+        p = nullptr, n = 0, cls = 0;
     }
     void alloc(size_t count) {
         release();
         if (count == 0) count = 1;
-        VDEV_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+        cls = ScratchPool::size_class(count * sizeof(T));
+        p = static_cast<T*>(ScratchPool::instance().take(cls));
         n = count;
     }
     // keeps the allocation when it is already large enough

@@ -72,9 +72,7 @@ struct Batch {
     DevBuf<uint32_t> d_g_plane;
     DevBuf<FastDesc> d_fast;
     DevBuf<uint32_t> d_fast_item_cursor, d_fast_item_begin;
-    DevBuf<unsigned long long> d_fast_slice_cursor, d_fast_slice_begin;
-    DevBuf<ItemRec> d_fast_items;
-    DevBuf<SliceRec> d_fast_slices;
+    DevBuf<FastItem> d_fast_items;
     const ColumnLevels* lev_dev = nullptr;  // boost column whose level bits the plane kernel stages in shared memory
     ColumnLevels lev_hdr{};
     uint64_t stat_fast_items = 0, stat_general_items = 0, stat_plane_evaluated = 0;
@@ -229,8 +227,8 @@ struct Batch {
             uint32_t eligible = 0;
             for (auto& qp : plan.programs)
                 if (qp.active && qp.prog_len == 0 && qp.n_leaves <= kFastMaxLeaves && qp.nonneg && qp.k >= 1 && qp.k <= kFastMaxK) ++eligible;
-            if (eligible == 0) use_planes = false;
-            else if (eligible * 2 >= n && tile_kernel_smem(kPlaneTileLog2, L) != 0) tile_log2 = kPlaneTileLog2;
+            if (eligible * 2 >= n && eligible > 0 && tile_kernel_smem(kPlaneTileLog2, L) != 0) tile_log2 = kPlaneTileLog2;
+            else use_planes = false;
         }
         lev_dev = nullptr;
         if (use_planes)
@@ -269,7 +267,7 @@ struct Batch {
         h2d_bytes += plan.parts.size() * sizeof(PartQuery) + (plan.part_dict.size() + plan.leaf_part.size() + plan.prog.size()) * 4 + plan.programs.size() * sizeof(QueryProgram) +
                      plan.boosts.size() * sizeof(BoostStep) + dv.size() * sizeof(DictView) + pv.size() * sizeof(PostingsView);
 
-        d_counters.alloc(16);  // [0] matches [1] tile work [2] postings [3] dense rows [4] emitted [5,6] item scan [7] plane work [8,9] plane stats
+        d_counters.alloc(16);  // [0] matches [1] tile work [2] postings [3] dense rows [4] emitted [5,6] item scan [8,9] plane stats [10..12] plane work
         if (use_planes) {
             d_part_planes.alloc(n_parts + 1);
             d_fast.alloc(n + 1);
@@ -292,6 +290,15 @@ struct Batch {
         d_emit.alloc((size_t)emit_capacity + 1);
         if (mode == kRequests) d_records.reserve(std::max<size_t>(1u << 20, (size_t)n_parts * 64));
         VDEV_CUDA(cudaMemset(d_counters.p, 0, d_counters.bytes()));
+    }
+
+    // Matched terms with at least this many postings get a tile-offset row, the others are copied into their part's
+    // sparse tile buckets.  With the plane path every term without a plane goes to the buckets (its postings are the
+    // "entries" of the plane-path items); only head terms keep offset rows (for the items that take the general path).
+    uint32_t dense_min() const {
+        const uint32_t base = std::max<uint32_t>(1, n_tiles / 2);
+        if (!use_planes) return base;
+        return 0xFFFFFFFFu;
     }
 
     template <class T>
@@ -345,7 +352,7 @@ struct Batch {
         ScoreScatterArgs a;
         a.records = d_records.p, a.n_records = M, a.parts = d_parts.p, a.part_dict = d_part_dict.p, a.dicts = d_dicts.p, a.postings = d_postings.p;
         a.part_begin = d_part_begin.p, a.dense_cursor = d_dense_cursor.p, a.sparse_cursor = d_sparse_cursor.p, a.n_dense_rows = reinterpret_cast<uint32_t*>(d_counters.p + 3);
-        a.dense_row_capacity = M, a.dense_min = std::max<uint32_t>(1, n_tiles / 2), a.row_match = d_row_match.p, a.part_est = d_part_est.p;
+        a.dense_row_capacity = M, a.dense_min = dense_min(), a.row_match = d_row_match.p, a.part_est = d_part_est.p;
         a.g_term = d_g_term.p, a.g_score = d_g_score.p, a.g_begin = d_g_begin.p, a.g_df = d_g_df.p, a.g_row = d_g_row.p, a.g_part = d_g_part.p;
         a.inj_terms = mode == kTermHits ? d_inj_terms.p : nullptr, a.inj_scores = mode == kTermHits ? d_inj_scores.p : nullptr;
         a.part_planes = use_planes ? d_part_planes.p : nullptr, a.g_plane = use_planes ? d_g_plane.p : nullptr;
@@ -399,6 +406,19 @@ struct Batch {
             launch_part_slices(stream, d_slices.p, d_part_begin.p, d_dense_cursor.p, d_sparse_base.p, n_parts);
             launch_finalize_programs(stream, d_programs.p, n, d_prog.p, d_leaf_part.p, d_part_est.p, d_counters.p + 2);
             if (use_planes) launch_build_fast_desc(stream, d_programs.p, n, d_leaf_part.p, d_part_planes.p, ix->planes.wmax.p, d_fast.p);
+            if (use_planes && getenv("VELOCI_DEBUG")) {
+                std::vector<FastDesc> fd(n);
+                std::vector<PartPlanes> pp(n_parts);
+                VDEV_CUDA(cudaStreamSynchronize(stream));
+                VDEV_CUDA(cudaMemcpy(fd.data(), d_fast.p, n * sizeof(FastDesc), cudaMemcpyDeviceToHost));
+                VDEV_CUDA(cudaMemcpy(pp.data(), d_part_planes.p, n_parts * sizeof(PartPlanes), cudaMemcpyDeviceToHost));
+                uint32_t not_fast = 0, hist[8] = {};
+                for (auto& d : fd) not_fast += d.flags == 0;
+                for (auto& p : pp) hist[std::min<uint32_t>(p.n, 7)]++;
+                fprintf(stderr, "[veloci] requests %u not on the plane path %u; parts by plane matches:", n, not_fast);
+                for (int i = 0; i < 8; ++i) fprintf(stderr, " %u", hist[i]);
+                fprintf(stderr, "\n");
+            }
         } else {
             VDEV_CUDA(cudaMemsetAsync(d_counters.p, 0, d_counters.bytes(), stream));
             VDEV_CUDA(cudaEventRecord(ev[0], stream));
@@ -417,23 +437,18 @@ struct Batch {
             sc.n_tiles = n_tiles, sc.n_items_total = (unsigned long long)n_tiles * n, sc.counters = d_counters.p + 5, sc.items = nullptr, sc.slice_recs = nullptr;
             if (planes_on) {
                 d_fast_item_cursor.reserve(n_tiles + 1), d_fast_item_begin.reserve(n_tiles + 2);
-                d_fast_slice_cursor.reserve(n_tiles + 1), d_fast_slice_begin.reserve(n_tiles + 2);
                 sc.fast = d_fast.p, sc.g_plane = d_g_plane.p;
-                sc.fast_item_cursor = d_fast_item_cursor.p, sc.fast_slice_cursor = d_fast_slice_cursor.p;
-                sc.fast_item_begin = d_fast_item_begin.p, sc.fast_slice_begin = d_fast_slice_begin.p;
+                sc.fast_item_cursor = d_fast_item_cursor.p, sc.fast_item_begin = d_fast_item_begin.p;
                 VDEV_CUDA(cudaMemsetAsync(d_fast_item_cursor.p, 0, d_fast_item_cursor.bytes(), stream));
-                VDEV_CUDA(cudaMemsetAsync(d_fast_slice_cursor.p, 0, d_fast_slice_cursor.bytes(), stream));
             }
             VDEV_CUDA(cudaMemsetAsync(d_counters.p + 5, 0, 16, stream));
             launch_item_scan(stream, sc, false);
-            unsigned long long counts[2], fast_slices = 0;
+            unsigned long long counts[2];
             VDEV_CUDA(cudaMemcpyAsync(counts, d_counters.p + 5, 16, cudaMemcpyDeviceToHost, stream));
             if (planes_on) {
                 launch_scan_u32(stream, d_fast_item_cursor.p, d_fast_item_begin.p, n_tiles);
-                launch_scan_u64(stream, reinterpret_cast<const uint64_t*>(d_fast_slice_cursor.p), reinterpret_cast<uint64_t*>(d_fast_slice_begin.p), n_tiles);
                 VDEV_CUDA(cudaMemcpyAsync(&n_fast_items, d_fast_item_begin.p + n_tiles, 4, cudaMemcpyDeviceToHost, stream));
-                VDEV_CUDA(cudaMemcpyAsync(&fast_slices, d_fast_slice_begin.p + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
-                d2h_bytes += 12;
+                d2h_bytes += 4;
             }
             VDEV_CUDA(cudaStreamSynchronize(stream));
             d2h_bytes += 16;
@@ -443,10 +458,8 @@ struct Batch {
             sc.items = d_items.p, sc.slice_recs = d_slice_recs.p;
             if (planes_on) {
                 d_fast_items.reserve(std::max<size_t>(n_fast_items, 1));
-                d_fast_slices.reserve((size_t)std::max<unsigned long long>(fast_slices, 1));
-                sc.fast_items = d_fast_items.p, sc.fast_slices = d_fast_slices.p;
+                sc.fast_items = d_fast_items.p;
                 VDEV_CUDA(cudaMemsetAsync(d_fast_item_cursor.p, 0, d_fast_item_cursor.bytes(), stream));
-                VDEV_CUDA(cudaMemsetAsync(d_fast_slice_cursor.p, 0, d_fast_slice_cursor.bytes(), stream));
             }
             VDEV_CUDA(cudaMemsetAsync(d_counters.p + 5, 0, 16, stream));
             launch_item_scan(stream, sc, true);
@@ -457,19 +470,32 @@ struct Batch {
         VDEV_CUDA(cudaMemsetAsync(d_tau.p, 0, d_tau.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_num_hits.p, 0, d_num_hits.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_lock.p, 0, d_lock.bytes(), stream));
-        // ---- phase 3: plane evaluation
+        // ---- phase 3: plane evaluation.  Tile 0 first, its requests spread over all SMs, then a few more tiles: the
+        // requests' thresholds are then close to final when the bulk of the tiles runs and prunes against them.
         if (planes_on && n_fast_items) {
             PlaneArgs a;
             memset(&a, 0, sizeof a);
-            a.items = d_fast_items.p, a.tile_item_begin = d_fast_item_begin.p, a.slice_recs = d_fast_slices.p, a.fast = d_fast.p;
-            a.postings = d_postings.p, a.sparse = d_sparse.p, a.planes = ix->planes.view();
+            a.items = d_fast_items.p, a.tile_item_begin = d_fast_item_begin.p, a.fast = d_fast.p;
+            a.sparse = d_sparse.p, a.planes = ix->planes.view();
             a.lev_dev = lev_dev, a.lev_hdr = lev_hdr;
-            a.n_tiles = n_tiles, a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
-            a.chunks_per_tile = (n + plane_unit_items() - 1) / plane_unit_items();
-            a.n_units = n_tiles * a.chunks_per_tile;
+            a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
             a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
-            a.work_counter = d_counters.p + 7, a.stats = d_counters.p + 8;
-            launch_plane_eval(stream, a, n_sms);
+            a.stats = d_counters.p + 8;
+            const uint32_t stage_end[3] = {std::min<uint32_t>(1, n_tiles), std::min<uint32_t>(4, n_tiles), n_tiles};
+            uint32_t t0 = 0;
+            for (int stage = 0; stage < 3; ++stage) {
+                const uint32_t t1 = stage_end[stage];
+                if (t1 <= t0) continue;
+                const uint32_t want_units = (uint32_t)n_sms * 2;
+                uint32_t unit = stage == 2 ? 1024u : std::max<uint32_t>(16, ((uint64_t)n * (t1 - t0) + want_units - 1) / want_units);
+                unit = (std::min<uint32_t>(unit, 1024u) + 15u) & ~15u;
+                a.tile_begin = t0, a.unit_items = unit;
+                a.chunks_per_tile = (n + unit - 1) / unit;
+                a.n_units = (t1 - t0) * a.chunks_per_tile;
+                a.work_counter = d_counters.p + 10 + stage;
+                launch_plane_eval(stream, a, n_sms);
+                t0 = t1;
+            }
         }
         VDEV_CUDA(cudaEventRecord(ev[4], stream));
         // ---- phase 4: tile evaluation of the general items

@@ -284,12 +284,21 @@ struct BatchPlan {
         bool flat = false;
         if (leaves.size() == 1 && code.size() == 2) {
             flat = true;
-        } else if (root.kind == vhost::SearchRequest::Or && code.size() == 2 * leaves.size() + 3 + leaves.size() && code[2 * leaves.size()] == vdev::kOpUnion &&
-                   code[2 * leaves.size() + 2] == leaves.size()) {
-            std::vector<uint32_t> by_slot(leaves.size());
-            for (size_t c = 0; c < leaves.size(); ++c) by_slot[code[2 * leaves.size() + 3 + c]] = leaves[c];
-            leaves = by_slot;
-            flat = true;
+        } else if (root.kind == vhost::SearchRequest::Or && code.size() == 2 * leaves.size() + 3 + leaves.size() && code[2 * leaves.size()] == vdev::kOpUnion) {
+            // Parts that share a term slot must be the very same search part (then their hit lists are identical and
+            // max(x, x) = x, so one leaf stands for the slot); at least two slots, so that the n * n rule still applies.
+            const uint32_t n_slots = code[2 * leaves.size() + 2];
+            std::vector<uint32_t> by_slot(n_slots, vdev::kNoValue);
+            bool same = n_slots == leaves.size() || n_slots >= 2;
+            for (size_t c = 0; c < leaves.size() && same; ++c) {
+                uint32_t& slot = by_slot[code[2 * leaves.size() + 3 + c]];
+                if (slot == vdev::kNoValue) slot = leaves[c];
+                else if (slot != leaves[c]) same = false;
+            }
+            if (same) {
+                leaves = by_slot;
+                flat = true;
+            }
         }
         qp.leaf_begin = (uint32_t)leaf_part.size();
         qp.n_leaves = (uint32_t)leaves.size();
