@@ -245,3 +245,21 @@ def test_plane_path_equals_posting_path(gpu, native_libs, monkeypatch):
     assert (got["num_hits"] == ref["num_hits"]).all()
     assert (got["ids"] == ref["ids"]).all()
     assert (got["scores"].view(np.uint32) == ref["scores"].view(np.uint32)).all()
+
+
+def test_deletion_index_equals_dictionary_scan(gpu, native_libs, monkeypatch):
+    """Fuzzy matching through the deletion-neighbourhood index finds exactly the terms the dictionary scan finds."""
+    d = tempfile.mkdtemp(prefix="vb200_gpu_delidx_")
+    params = dict(num_docs=40000, vocab=30000, seed=5)
+    helpers.create_synthetic_index(d, **params)
+    reqs = []
+    for lev, seed in ((0, 1), (1, 2), (2, 3)):
+        reqs += helpers.synthetic_requests(num_queries=150, query_kind="single", levenshtein=lev, query_seed=seed, **params)
+    probe = gpu.Index(d).search_batch(reqs, k=10)
+    monkeypatch.setenv("VELOCI_NO_DELINDEX", "1")
+    scan = gpu.Index(d).search_batch(reqs, k=10)
+    assert (probe["status"] == 0).all() and (scan["status"] == 0).all()
+    assert probe["num_hits"].sum() > 0
+    assert (probe["num_hits"] == scan["num_hits"]).all()
+    assert (probe["ids"] == scan["ids"]).all()
+    assert (probe["scores"].view(np.uint32) == scan["scores"].view(np.uint32)).all()

@@ -16,8 +16,24 @@ struct TilePrefix {  // 20 bytes
     uint16_t pad;
 };
 
+// Deletion-neighbourhood index of a dictionary (lower-cased symbols): every term filed under the hash of each
+// of its variants with at most max_del symbols deleted.  Two strings within edit distance d (transpositions
+// included) share a variant with at most d deletions each, so probing the query's variants yields a superset of
+// the matching terms; candidates are verified with the bit-parallel automaton.
+struct DelEntry {
+    uint32_t slot;  // dictionary slot of the term
+    uint32_t tag;   // upper half of the variant hash
+};
+struct DelIndexView {
+    const uint32_t* off;   // [mask + 2] bucket offsets (nullptr: not built)
+    const DelEntry* ent;
+    uint32_t mask;         // buckets - 1
+    uint32_t max_del;
+};
+
 struct DictView {
     uint32_t n, n_tiles;
+    DelIndexView del[2];   // [0] one deletion, [1] two deletions
     const uint32_t* ids;
     const uint16_t* lower_bytes;
     const uint16_t* sym[2];  // [0] lower-cased, [1] raw

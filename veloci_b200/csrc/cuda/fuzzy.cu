@@ -157,6 +157,173 @@ void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* 
     count_launch();
 }
 
+// ---------------------------------------------------------------- deletion-neighbourhood index
+__device__ __forceinline__ uint64_t variant_hash(const uint16_t* __restrict__ sym, uint32_t n, uint32_t skip_a, uint32_t skip_b) {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (i == skip_a || i == skip_b) continue;
+        h = (h ^ sym[i]) * 0xFF51AFD7ED558CCDull;
+        h ^= h >> 29;
+    }
+    h *= 0xC4CEB9FE1A85EC53ull;
+    return h ^ (h >> 32);
+}
+
+// Variant v of a string of n symbols: 0 = the string, 1..n = one deletion, then the pairs (i < j).
+__device__ __forceinline__ void variant_skips(uint32_t v, uint32_t n, uint32_t& a, uint32_t& b) {
+    a = b = 0xFFFFFFFFu;
+    if (v == 0) return;
+    if (v <= n) {
+        a = v - 1;
+        return;
+    }
+    uint32_t p = v - 1 - n, i = 0;
+    while (p >= n - 1 - i) p -= n - 1 - i, ++i;
+    a = i, b = i + 1 + p;
+}
+__device__ __forceinline__ uint32_t variant_count(uint32_t n, uint32_t max_del) {
+    uint32_t c = 1;
+    if (max_del >= 1) c += n;
+    if (max_del >= 2 && n >= 2) c += n * (n - 1) / 2;
+    return c;
+}
+
+template <bool FILL>
+__global__ void del_index_kernel(DictView dict, uint32_t max_del, uint32_t mask, uint32_t* __restrict__ count_or_cursor, const uint32_t* __restrict__ off, DelEntry* __restrict__ ent) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= dict.n) return;
+    const uint32_t o = dict.off[0][slot], n = dict.off[0][slot + 1] - o;
+    const uint16_t* sym = dict.sym[0] + o;
+    const uint32_t nv = variant_count(n, max_del);
+    for (uint32_t v = 0; v < nv; ++v) {
+        uint32_t a, b;
+        variant_skips(v, n, a, b);
+        const uint64_t h = variant_hash(sym, n, a, b);
+        const uint32_t bucket = (uint32_t)h & mask;
+        const uint32_t at = atomicAdd(&count_or_cursor[bucket], 1u);
+        if (FILL) ent[off[bucket] + at] = DelEntry{slot, (uint32_t)(h >> 32)};
+    }
+}
+
+void launch_del_index_pass(cudaStream_t st, const DictView& dict, uint32_t max_del, uint32_t mask, uint32_t* count_or_cursor, const uint32_t* off, DelEntry* ent) {
+    if (!dict.n) return;
+    const unsigned blocks = (dict.n + 127) / 128;
+    if (ent) del_index_kernel<true><<<blocks, 128, 0, st>>>(dict, max_del, mask, count_or_cursor, off, ent);
+    else del_index_kernel<false><<<blocks, 128, 0, st>>>(dict, max_del, mask, count_or_cursor, off, ent);
+    count_launch();
+}
+
+static const int kProbeWarps = 4;
+static const uint32_t kProbeSet = 2048;      // candidate set slots per warp
+static const uint32_t kProbeSetMax = 1024;   // candidates above which the part is handed to the scan
+static const uint32_t kSetEmpty = 0xFFFFFFFFu;
+
+__global__ void __launch_bounds__(kProbeWarps * 32) fuzzy_probe_kernel(DictView dict, const PartQuery* __restrict__ parts, const uint32_t* __restrict__ part_ids, uint32_t n_parts,
+                                                                      MatchRecord* __restrict__ out, uint32_t capacity, unsigned long long* __restrict__ counter,
+                                                                      uint32_t* __restrict__ overflow_parts, unsigned long long* __restrict__ overflow_count) {
+    __shared__ uint32_t s_set[kProbeWarps][kProbeSet];
+    __shared__ uint64_t s_peq[kProbeWarps][kPeqCodes];
+    __shared__ uint16_t s_sym[kProbeWarps][64];
+    __shared__ uint32_t s_count[kProbeWarps];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t pi = blockIdx.x * kProbeWarps + warp;
+    if (pi >= n_parts) return;
+    const uint32_t pid = part_ids[pi];
+    const PartQuery& q = parts[pid];
+    const uint32_t m = q.m, d = q.d_match;
+    const bool transposition = q.flags & kPartTransposition;
+    uint32_t* set = s_set[warp];
+    uint64_t* peq = s_peq[warp];
+    uint16_t* qs = s_sym[warp];
+    for (uint32_t i = lane; i < kProbeSet; i += 32) set[i] = kSetEmpty;
+    for (uint32_t i = lane; i < kPeqCodes; i += 32) peq[i] = 0;
+    for (uint32_t i = lane; i < 64; i += 32) qs[i] = q.match_sym[i];
+    if (lane == 0) s_count[warp] = 0;
+    __syncwarp();
+    if (lane == 0)
+        for (uint32_t j = 0; j < m; ++j)
+            if (qs[j] < kPeqCodes) peq[qs[j]] |= 1ull << j;
+    __syncwarp();
+    const DelIndexView ix = dict.del[d >= 2 ? 1 : 0];
+    const uint32_t nv = variant_count(m, d);
+    for (uint32_t v = lane; v < nv; v += 32) {
+        if (s_count[warp] > kProbeSetMax) break;
+        uint32_t a, b;
+        variant_skips(v, m, a, b);
+        const uint64_t h = variant_hash(qs, m, a, b);
+        const uint32_t bucket = (uint32_t)h & ix.mask, tag = (uint32_t)(h >> 32);
+        const uint32_t beg = ix.off[bucket], end = ix.off[bucket + 1];
+        for (uint32_t e = beg; e < end; ++e) {
+            const DelEntry en = ix.ent[e];
+            if (en.tag != tag) continue;
+            // new candidate?
+            uint32_t hs = (en.slot * 0x9E3779B1u) >> 21;
+            bool fresh = false;
+            while (true) {
+                const uint32_t old = atomicCAS(&set[hs], kSetEmpty, en.slot);
+                if (old == kSetEmpty) {
+                    fresh = true;
+                    break;
+                }
+                if ((old & 0x7FFFFFFFu) == en.slot) break;
+                hs = (hs + 1u) & (kProbeSet - 1u);
+            }
+            if (!fresh) continue;
+            if (atomicAdd(&s_count[warp], 1u) >= kProbeSetMax) break;
+            // verify with the automaton (same acceptance as fuzzy_match_kernel)
+            const uint32_t o = dict.off[0][en.slot], n = dict.off[0][en.slot + 1] - o;
+            const uint16_t* ts = dict.sym[0] + o;
+            vbit::State st;
+            vbit::init(st, m);
+            for (uint32_t i = 0; i < n; ++i) {
+                const uint16_t c = ts[i];
+                uint64_t eq;
+                if (c < kPeqCodes) eq = peq[c];
+                else {
+                    eq = 0;
+                    for (uint32_t j = 0; j < m; ++j) eq |= (uint64_t)(qs[j] == c) << j;
+                }
+                vbit::step(st, eq, m, transposition);
+            }
+            if (st.score <= d) atomicOr(&set[hs], 0x80000000u);
+        }
+    }
+    __syncwarp();
+    if (s_count[warp] > kProbeSetMax) {  // too many candidates for the table: the scan kernel takes this part
+        if (lane == 0) overflow_parts[atomicAdd(overflow_count, 1ull)] = pid;
+        return;
+    }
+    uint32_t mine = 0;
+    for (uint32_t i = lane; i < kProbeSet; i += 32) {
+        const uint32_t v = set[i];
+        mine += (v != kSetEmpty && (v & 0x80000000u)) ? 1u : 0u;
+    }
+    uint32_t incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((int)lane >= o) incl += y;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (!total) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0) + incl - mine;
+    for (uint32_t i = lane; i < kProbeSet; i += 32) {
+        const uint32_t v = set[i];
+        if (v != kSetEmpty && (v & 0x80000000u)) {
+            if (base < capacity) out[base] = MatchRecord{pid, v & 0x7FFFFFFFu};
+            ++base;
+        }
+    }
+}
+
+void launch_fuzzy_probe(cudaStream_t st, const DictView& dict, const PartQuery* parts, const uint32_t* part_ids, uint32_t n_parts, MatchRecord* out, uint32_t capacity,
+                        unsigned long long* counter, uint32_t* overflow_parts, unsigned long long* overflow_count) {
+    if (n_parts == 0 || dict.n == 0) return;
+    fuzzy_probe_kernel<<<(n_parts + kProbeWarps - 1) / kProbeWarps, kProbeWarps * 32, 0, st>>>(dict, parts, part_ids, n_parts, out, capacity, counter, overflow_parts, overflow_count);
+    count_launch();
+}
+
 // ---------------------------------------------------------------- grouping
 __global__ void group_count_kernel(const MatchRecord* __restrict__ rec, uint32_t n, uint32_t* __restrict__ part_count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -14,6 +14,14 @@ uint64_t launches_so_far();
 // ---- fuzzy.cu ----
 void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* parts, const uint32_t* part_ids, uint32_t n_parts, uint32_t max_m, MatchRecord* out,
                         uint32_t capacity, unsigned long long* counter);
+// Deletion-neighbourhood index build: pass 0 counts the variants per hash bucket, pass 1 (after an exclusive scan of
+// the counts into `off`, cursor zeroed) files the terms.
+void launch_del_index_pass(cudaStream_t st, const DictView& dict, uint32_t max_del, uint32_t mask, uint32_t* count_or_cursor, const uint32_t* off, DelEntry* ent);
+// Fuzzy match by probing the deletion-neighbourhood index: one warp per search part (not starts_with, lower-cased
+// matching, distance <= 2).  Parts whose candidate set overflows the warp's table are appended to `overflow_parts`
+// (count in *overflow_count) and have to be scanned.
+void launch_fuzzy_probe(cudaStream_t st, const DictView& dict, const PartQuery* parts, const uint32_t* part_ids, uint32_t n_parts, MatchRecord* out, uint32_t capacity,
+                        unsigned long long* counter, uint32_t* overflow_parts, unsigned long long* overflow_count);
 void launch_group_count(cudaStream_t st, const MatchRecord* rec, uint32_t n, uint32_t* part_count);
 void launch_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, uint32_t n);
 void launch_scan_u64(cudaStream_t st, const uint64_t* in, uint64_t* out, uint32_t n);

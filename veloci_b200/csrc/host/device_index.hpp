@@ -212,8 +212,18 @@ struct SymbolSet {  // one case variant of a dictionary
     DevBuf<TilePrefix> tiles;
 };
 
+struct DelIndexDev {  // deletion-neighbourhood index (see DelIndexView)
+    DevBuf<uint32_t> off;
+    DevBuf<DelEntry> ent;
+    uint32_t mask = 0, max_del = 0;
+    bool built = false;
+    DelIndexView view() const { return built ? DelIndexView{off.p, ent.p, mask, max_del} : DelIndexView{nullptr, nullptr, 0u, 0u}; }
+};
+
 struct DictDev {
     size_t n = 0;
+    DelIndexDev del[2];       // [0] one deletion (built at open), [1] two deletions (built on first use)
+    uint64_t variants[2] = {0, 0};  // entries each of them holds
     std::vector<uint32_t> alphabet;  // sorted scalars; code = index
     DevBuf<uint32_t> ids;            // term id per slot
     DevBuf<uint16_t> lower_bytes;    // byte length of the lower-cased term (clamped)
@@ -231,6 +241,7 @@ struct DictDev {
         DictView v;
         v.n = (uint32_t)n;
         v.n_tiles = n_tiles;
+        v.del[0] = del[0].view(), v.del[1] = del[1].view();
         v.ids = ids.p;
         v.lower_bytes = lower_bytes.p;
         v.sym[0] = lower.sym.p, v.off[0] = lower.off.p, v.tiles[0] = lower.tiles.p;
@@ -349,6 +360,40 @@ struct DeviceIndex {
         out.tiles.upload(tiles);
     }
 
+    // Files every term of the dictionary under the hashes of its variants with at most level + 1 deletions.
+    void build_del_index(DictDev& dd, int level) {
+        DelIndexDev& di = dd.del[level];
+        if (di.built || dd.n == 0) return;
+        const uint64_t entries = dd.variants[level];
+        if (entries >= (1ull << 31)) return;  // the scan kernel stays responsible
+        uint32_t buckets = 1024;
+        while (buckets < entries * (level == 0 ? 2 : 1) && buckets < (1u << 28)) buckets <<= 1;
+        DevBuf<uint32_t> count;
+        count.alloc((size_t)buckets + 1);
+        di.off.alloc((size_t)buckets + 2);
+        di.ent.alloc((size_t)entries + 1);
+        di.mask = buckets - 1, di.max_del = (uint32_t)level + 1;
+        DictView v = dd.view();
+        VDEV_CUDA(cudaMemset(count.p, 0, count.bytes()));
+        launch_del_index_pass(nullptr, v, di.max_del, di.mask, count.p, nullptr, nullptr);
+        launch_scan_u32(nullptr, count.p, di.off.p, buckets);
+        VDEV_CUDA(cudaMemset(count.p, 0, count.bytes()));
+        launch_del_index_pass(nullptr, v, di.max_del, di.mask, count.p, di.off.p, di.ent.p);
+        VDEV_CUDA(cudaDeviceSynchronize());
+        di.built = true;
+        device_bytes += di.off.bytes() + di.ent.bytes();
+    }
+
+    std::mutex build_mu;
+    // two-deletion index of a dictionary, built when the first request needs it
+    void ensure_del_index(const std::string& path, int level) {
+        std::lock_guard<std::mutex> g(build_mu);
+        auto it = dicts.find(path);
+        if (it == dicts.end() || it->second.del[level].built || getenv("VELOCI_NO_DELINDEX")) return;
+        VDEV_CUDA(cudaSetDevice(device));
+        build_del_index(it->second, level);
+    }
+
     void build_dict(const std::string& path, const vhost::TermDict& d) {
         DictDev dd;
         dd.n = d.size();
@@ -386,6 +431,16 @@ struct DeviceIndex {
         dd.lower_bytes.upload(lower_bytes);
         dd.has_raw = any_upper;
         if (any_upper) build_symbol_set(d, dd.alphabet, false, dd.raw, nullptr);
+        {
+            std::vector<uint32_t> off(dd.n + 1);
+            if (dd.n) VDEV_CUDA(cudaMemcpy(off.data(), dd.lower.off.p, (dd.n + 1) * 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < dd.n; ++i) {
+                const uint64_t len = off[i + 1] - off[i];
+                dd.variants[0] += 1 + len;
+                dd.variants[1] += 1 + len + (len >= 2 ? len * (len - 1) / 2 : 0);
+            }
+        }
+        if (!getenv("VELOCI_NO_DELINDEX")) build_del_index(dd, 0);
         device_bytes += dd.ids.bytes() + dd.lower_bytes.bytes() + dd.lower.sym.bytes() + dd.lower.off.bytes() + dd.lower.tiles.bytes() + dd.raw.sym.bytes() + dd.raw.off.bytes() + dd.raw.tiles.bytes();
         dicts.emplace(path, std::move(dd));
     }

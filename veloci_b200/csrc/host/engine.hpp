@@ -45,8 +45,11 @@ struct Batch {
     DevBuf<BoostStep> d_boosts;
     DevBuf<DictView> d_dicts;
     DevBuf<PostingsView> d_postings;
-    std::vector<std::vector<uint32_t>> parts_of_dict;
+    std::vector<std::vector<uint32_t>> parts_of_dict;   // parts the dictionary scan matches (starts_with, raw case, distance > 2)
     std::vector<DevBuf<uint32_t>> d_parts_of_dict;
+    std::vector<std::vector<uint32_t>> probe_of_dict;   // parts matched through the deletion-neighbourhood index
+    std::vector<DevBuf<uint32_t>> d_probe_of_dict, d_overflow_of_dict;
+    DevBuf<unsigned long long> d_overflow_count;
     std::vector<uint32_t> max_m_of_dict;
     // device: match phase
     DevBuf<MatchRecord> d_records;
@@ -250,20 +253,35 @@ struct Batch {
         d_prog.upload(plan.prog);
         d_programs.upload(plan.programs);
         d_boosts.upload(plan.boosts);
+        parts_of_dict.assign(plan.dict_names.size(), {});
+        probe_of_dict.assign(plan.dict_names.size(), {});
+        max_m_of_dict.assign(plan.dict_names.size(), 0);
+        if (mode == kRequests) {
+            for (uint32_t p = 0; p < n_parts; ++p) {
+                const PartQuery& pq = plan.parts[p];
+                const uint32_t d = plan.part_dict[p];
+                const DictDev& dict = ix->dicts.at(plan.dict_names[d]);
+                bool probe = pq.m >= 1 && pq.d_match <= 2 && !(pq.flags & (kPartPrefix | kPartRawCase));
+                if (probe && pq.d_match == 2 && !dict.del[1].built) ix->ensure_del_index(plan.dict_names[d], 1);
+                probe = probe && dict.del[pq.d_match == 2 ? 1 : 0].built;
+                (probe ? probe_of_dict : parts_of_dict)[d].push_back(p);
+                max_m_of_dict[d] = std::max(max_m_of_dict[d], pq.m);
+            }
+        }
         std::vector<DictView> dv;
         for (auto& name : plan.dict_names) dv.push_back(ix->dicts.at(name).view());
         d_dicts.upload(dv);
         std::vector<PostingsView> pv;
         for (auto& name : plan.postings_names) pv.push_back(ix->postings.at(name).view());
         d_postings.upload(pv);
-        parts_of_dict.assign(plan.dict_names.size(), {});
-        if (mode == kRequests)
-            for (uint32_t p = 0; p < n_parts; ++p) parts_of_dict[plan.part_dict[p]].push_back(p);
-        max_m_of_dict.assign(plan.dict_names.size(), 0);
-        for (size_t d = 0; d < parts_of_dict.size(); ++d)
-            for (uint32_t p : parts_of_dict[d]) max_m_of_dict[d] = std::max(max_m_of_dict[d], plan.parts[p].m);
-        d_parts_of_dict.resize(parts_of_dict.size());
-        for (size_t d = 0; d < parts_of_dict.size(); ++d) d_parts_of_dict[d].upload(parts_of_dict[d]), h2d_bytes += parts_of_dict[d].size() * 4;
+        const size_t n_dicts = parts_of_dict.size();
+        d_parts_of_dict.resize(n_dicts), d_probe_of_dict.resize(n_dicts), d_overflow_of_dict.resize(n_dicts);
+        for (size_t d = 0; d < n_dicts; ++d) {
+            d_parts_of_dict[d].upload(parts_of_dict[d]), d_probe_of_dict[d].upload(probe_of_dict[d]);
+            d_overflow_of_dict[d].alloc(probe_of_dict[d].size() + 1);
+            h2d_bytes += (parts_of_dict[d].size() + probe_of_dict[d].size()) * 4;
+        }
+        d_overflow_count.alloc(n_dicts + 1);
         h2d_bytes += plan.parts.size() * sizeof(PartQuery) + (plan.part_dict.size() + plan.leaf_part.size() + plan.prog.size()) * 4 + plan.programs.size() * sizeof(QueryProgram) +
                      plan.boosts.size() * sizeof(BoostStep) + dv.size() * sizeof(DictView) + pv.size() * sizeof(PostingsView);
 
@@ -316,14 +334,29 @@ struct Batch {
         VDEV_CUDA(cudaEventRecord(ev[0], stream));
         uint64_t n_match = 0;
         if (mode == kRequests) {
+            const size_t n_dicts = parts_of_dict.size();
+            std::vector<unsigned long long> overflow(n_dicts + 1);
             for (int attempt = 0; attempt < 2; ++attempt) {
                 VDEV_CUDA(cudaMemsetAsync(d_counters.p, 0, d_counters.bytes(), stream));
-                for (size_t d = 0; d < parts_of_dict.size(); ++d) {
-                    const DictDev& dict = ix->dicts.at(plan.dict_names[d]);
-                    launch_fuzzy_match(stream, dict.view(), d_parts.p, d_parts_of_dict[d].p, (uint32_t)parts_of_dict[d].size(), max_m_of_dict[d], d_records.p,
-                                       (uint32_t)std::min<size_t>(d_records.n, 0xFFFFFFFFu), d_counters.p);
+                VDEV_CUDA(cudaMemsetAsync(d_overflow_count.p, 0, d_overflow_count.bytes(), stream));
+                const uint32_t capacity = (uint32_t)std::min<size_t>(d_records.n, 0xFFFFFFFFu);
+                for (size_t d = 0; d < n_dicts; ++d) {
+                    const DictView dict = ix->dicts.at(plan.dict_names[d]).view();
+                    launch_fuzzy_probe(stream, dict, d_parts.p, d_probe_of_dict[d].p, (uint32_t)probe_of_dict[d].size(), d_records.p, capacity, d_counters.p, d_overflow_of_dict[d].p,
+                                       d_overflow_count.p + d);
+                    launch_fuzzy_match(stream, dict, d_parts.p, d_parts_of_dict[d].p, (uint32_t)parts_of_dict[d].size(), max_m_of_dict[d], d_records.p, capacity, d_counters.p);
                 }
+                VDEV_CUDA(cudaMemcpyAsync(overflow.data(), d_overflow_count.p, n_dicts * 8, cudaMemcpyDeviceToHost, stream));
                 n_match = read_back(d_counters.p);
+                d2h_bytes += n_dicts * 8;
+                bool rescanned = false;
+                for (size_t d = 0; d < n_dicts; ++d)
+                    if (overflow[d]) {  // candidate sets too large for the probe: scan the dictionary for those parts
+                        const DictView dict = ix->dicts.at(plan.dict_names[d]).view();
+                        launch_fuzzy_match(stream, dict, d_parts.p, d_overflow_of_dict[d].p, (uint32_t)overflow[d], max_m_of_dict[d], d_records.p, capacity, d_counters.p);
+                        rescanned = true;
+                    }
+                if (rescanned) n_match = read_back(d_counters.p);
                 if (n_match <= d_records.n) break;
                 if (n_match > 0xFFFFFFF0ull) throw std::runtime_error("more than 2^32 term matches in one batch");
                 d_records.reserve((size_t)n_match);
