@@ -234,12 +234,15 @@ def run_ours(args):
 
     # end to end: host JSON in, host rows out, every step
     e2e_ms = []
+    e2e_parts = {"prepare": 0.0, "execute": 0.0, "results": 0.0}
     io = {"h2d": 0, "d2h": 0}
     for i in range(args.warmup + args.steps):
         sync_all()
         t1 = time.perf_counter()
         b = index.prepare(reqs)
+        t2 = time.perf_counter()
         b.execute()
+        t3 = time.perf_counter()
         if dist:
             keys_ptr, hits_ptr, stride = b.local_topk()
             n = len(reqs)
@@ -250,11 +253,15 @@ def run_ours(args):
             torch.cuda.synchronize()
             b.merge_gathered(g_keys.data_ptr(), g_hits.data_ptr(), world)
         out = b.results_flat(10)
-        dt = 1000.0 * (time.perf_counter() - t1)
+        t4 = time.perf_counter()
+        dt = 1000.0 * (t4 - t1)
         io = b.io_bytes()
         b.close()
         if i >= args.warmup:
             e2e_ms.append(dt)
+            e2e_parts["prepare"] += 1000.0 * (t2 - t1) / args.steps
+            e2e_parts["execute"] += 1000.0 * (t3 - t2) / args.steps
+            e2e_parts["results"] += 1000.0 * (t4 - t3) / args.steps
     sync_all()
 
     # max over ranks
@@ -293,7 +300,7 @@ def run_ours(args):
             "launch_ms": tile_ms,
         },
         "e2e": {"value": len(reqs) * len(e2e_ms) / e2e_s if e2e_s > 0 else 0.0, "unit": UNIT, "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
-                "ms_per_step": 1000.0 * e2e_s / max(1, len(e2e_ms))},
+                "ms_per_step": 1000.0 * e2e_s / max(1, len(e2e_ms)), "host_ms": e2e_parts},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }

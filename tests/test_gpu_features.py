@@ -1,0 +1,104 @@
+"""GPU parity of the plan steps around the core path: filters,
+boost_term, phrase boosts, text locality, facets.  Every request runs through the C ABI on the
+device and through the CPU oracle on the same index directory; hit counts, hit ids, facet
+groups are compared exactly, scores within 1e-5 relative."""
+import json
+import tempfile
+
+import numpy as np
+import pytest
+
+import helpers
+import ref_fixtures as fx
+from test_gpu_parity import assert_same_topk, close  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import veloci_b200
+
+    assert veloci_b200.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return veloci_b200
+
+
+def _pair(gpu, docs=None, config=None, synth=None):
+    d = tempfile.mkdtemp(prefix="vb200_gpu_feat_")
+    if synth is not None:
+        helpers.create_synthetic_index(d, **synth)
+    else:
+        helpers.create_index(d, docs, config)
+    return gpu.Index(d), helpers.Oracle(d)
+
+
+def compare(index, oracle, requests):
+    reqs = [r if isinstance(r, str) else json.dumps(r, ensure_ascii=False) for r in requests]
+    b = index.prepare(reqs).execute()
+    for q, r in enumerate(reqs):
+        assert b.status(q) == 0, (r, b.message(q))
+        g = b.result(q)
+        c = oracle.search(r)
+        assert g["num_hits"] == c["num_hits"], (r, g["num_hits"], c["num_hits"])
+        assert_same_topk(g["data"], [(h[0], np.float32(h[1])) for h in c["data"]], ctx=r)
+        if "facets" in c:
+            assert "facets" in g, r
+            assert set(g["facets"]) == set(c["facets"]), r
+            for field, groups in c["facets"].items():
+                assert [(t, n, i) for t, n, i in g["facets"][field]] == [(t, n, i) for t, n, i in groups], (r, field)
+    return b
+
+
+S = lambda term, path, **kw: {"search": {"terms": [term], "path": path, **kw}}
+OR_MAJ_URGE = {"or": {"queries": [S("majestät", "meanings.ger[]"), S("urge", "meanings.eng[]")]}}
+
+
+@pytest.fixture(scope="module")
+def test_all(gpu, native_libs):
+    return _pair(gpu, fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG)
+
+
+def test_filters(test_all):  # tests/all/tests.rs:753-824
+    index, oracle = test_all
+    compare(index, oracle, [
+        {"search_req": S("urge", "meanings.eng[]"), "filter": S("1587690", "ent_seq")},
+        {"search_req": OR_MAJ_URGE, "filter": S("1587690", "ent_seq")},
+        {"search_req": OR_MAJ_URGE, "filter": S("urge", "meanings.eng[]")},
+        {"search_req": OR_MAJ_URGE, "filter": {"or": {"queries": [S("1587690", "ent_seq"), S("urge", "meanings.eng[]")]}}},
+        {"search_req": OR_MAJ_URGE, "filter": {"and": {"queries": [S("majestät", "meanings.ger[]"), S("urge", "meanings.eng[]")]}}},
+        {"search_req": S("will", "meanings.eng[]"), "filter": S("nothing-matches", "ent_seq"), "boost": [{"path": "commonness", "boost_fun": "Log10", "param": 1}]},
+    ])
+
+
+def test_boost_term(test_all):  # tests/all/tests.rs:1232-1256
+    index, oracle = test_all
+    compare(index, oracle, [
+        {"search_req": S("will", "meanings.eng[]"), "boost_term": [{"terms": ["9555"], "path": "ent_seq", "boost": 5.0}]},
+        {"search_req": OR_MAJ_URGE, "boost_term": [{"terms": ["urge"], "path": "meanings.eng[]"}, {"terms": ["1587690"], "path": "ent_seq", "boost": 3.5}]},
+        {"search_req": OR_MAJ_URGE, "boost_term": [{"terms": ["will"], "path": "meanings.eng[]", "levenshtein_distance": 1}],
+         "boost": [{"path": "commonness", "boost_fun": "Log2", "param": 2}], "filter": S("urge", "meanings.eng[]")},
+    ])
+
+
+def test_facets_reference_fixture(gpu, native_libs):  # tests/all/tests_facet.rs:60-117
+    index, oracle = _pair(gpu, fx.TEST_FACET_DOCS, fx.TEST_FACET_CONFIG)
+    b = compare(index, oracle, [
+        {"search_req": S("will", "meanings.eng[]"), "facets": [{"field": "tags[]"}, {"field": "commonness"}]},
+        {"search_req": S("test", "meanings.ger[]"), "facets": [{"field": "meanings.eng[]"}]},
+        {"search_req": S("will", "meanings.eng[]"), "facets": [{"field": "tags[]", "top": 1}]},
+    ])
+    assert [f[:2] for f in b.result(0)["facets"]["tags[]"]] == [("nice", 2), ("cool", 1)]
+    assert [f[:2] for f in b.result(0)["facets"]["commonness"]] == [("20", 2)]
+    assert [f[:2] for f in b.result(1)["facets"]["meanings.eng[]"]] == [("test1", 1)]
+
+
+def test_facets_large(gpu, native_libs):  # tests/all/tests_large.rs:40-112
+    docs = [{"category": "superb", "tags": ["nice", "cool"]}] * 300 + [{"category": "awesome", "tags": ["is", "cool"]}] * 300
+    index, oracle = _pair(gpu, docs, {"*GLOBAL*": {"features": ["All"]}, "tags[]": {"facet": True}})
+    b = compare(index, oracle, [
+        {"search_req": S("superb", "category"), "facets": [{"field": "tags[]"}]},
+        {"search_req": {"or": {"queries": [S("superb", "category"), S("awesome", "category")]}}, "facets": [{"field": "tags[]"}]},
+        {"search_req": S("superb", "category"), "filter": S("awesome", "category"), "facets": [{"field": "tags[]"}]},
+    ])
+    assert sorted(f[:2] for f in b.result(0)["facets"]["tags[]"]) == sorted([("nice", 300), ("cool", 300)])
+    assert b.result(1)["num_hits"] == 600

@@ -186,6 +186,23 @@ enum ProgOp : uint32_t {
     kOpLeaf = 1,       // [op, leaf index]
     kOpUnion = 2,      // [op, n children, n slots, slot of child 0 .. n-1]      set_op.rs:87-220
     kOpIntersect = 3,  // [op, n children, sum order: child index 0 .. n-1]      set_op.rs:368-446
+    kOpFilter = 4,     // [op]: (search result, filter result) -> search result where the filter is present   set_op.rs:311-326
+};
+
+// Steps that run on every hit after the request tree and the column boosts, in the reference's order
+// (execution_plan.rs:202-262 phrase boosts, search.rs:176 boost_term, search.rs:180-184 text locality).
+enum PostOp : uint32_t {
+    kPostMulIfPresent = 1,  // [op, leaf, f32 bits]: score *= value when the leaf has the anchor   boost.rs:380-402
+    kPostMulValue = 2,      // [op, leaf]: score *= the leaf's value for the anchor               boost.rs:197-237
+};
+
+// One facet of one request (facet.rs:31-73): hit anchor -> value ids through up to three id -> ids joins, counted.
+static const uint32_t kMaxFacetSteps = 3;
+struct FacetStep {
+    CsrView step[kMaxFacetSteps];
+    uint32_t n_steps;
+    uint32_t hist_size;
+    uint32_t* hist;  // [hist_size] counts of this (request, facet)
 };
 
 enum BoostFunDev : uint32_t { kBoostNone = 0, kBoostLog2 = 1, kBoostLog10 = 2, kBoostMultiply = 3, kBoostAdd = 4, kBoostReplace = 5 };
@@ -208,7 +225,7 @@ struct BoostStep {  // add_boost on anchor ids (boost.rs:470-504, apply_boost :2
     const ColumnLevels* levels;  // level bitmaps of the column (nullptr: none)
 };
 
-struct alignas(16) QueryProgram {  // 80 B: copied to shared memory with five 16-byte async copies
+struct alignas(16) QueryProgram {  // 96 B
     uint32_t leaf_begin, n_leaves;  // into the leaf -> part table
     uint32_t prog_begin, prog_len;  // into the program words
     uint32_t boost_begin, n_boosts; // into the BoostStep table
@@ -223,7 +240,9 @@ struct alignas(16) QueryProgram {  // 80 B: copied to shared memory with five 16
     uint32_t pad0;
     const uint32_t* fb_col;
     const ColumnLevels* fb_lev;     // level bitmaps of the fast-boost column (nullptr: none)
+    uint32_t post_begin, post_len;  // post ops, into the program words
+    uint32_t facet_begin, n_facets; // into the FacetStep table
 };
-static_assert(sizeof(QueryProgram) == 80, "QueryProgram layout");
+static_assert(sizeof(QueryProgram) == 96, "QueryProgram layout");
 
 }  // namespace vdev

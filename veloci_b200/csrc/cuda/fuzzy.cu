@@ -594,6 +594,7 @@ __global__ void finalize_programs_kernel(const QueryProgram* __restrict__ querie
         const uint32_t op = code[pc];
         if (op == kOpLeaf) pc += 2;
         else if (op == kOpUnion) pc += 3 + code[pc + 1];
+        else if (op == kOpFilter) pc += 1;
         else {
             const uint32_t cnt = code[pc + 1];
             uint32_t* order = code + pc + 2;

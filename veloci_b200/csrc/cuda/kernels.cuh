@@ -134,6 +134,7 @@ struct TileArgs {
     const uint32_t* leaf_part;
     const uint32_t* prog;
     const BoostStep* boosts;
+    const FacetStep* facets;
     // parts and their slices
     const PartQuery* parts;
     const PartSlices* slices;
@@ -198,6 +199,10 @@ struct PlaneArgs {
 };
 size_t plane_kernel_smem(uint32_t tile_log2, uint32_t n_planes);
 void launch_plane_eval(cudaStream_t st, const PlaneArgs& a, int n_sms);
+
+// Top groups of every facet histogram: block f writes the `top[f]` largest counts of facets[f] (count desc, value id
+// asc; zero counts never) to out_ids / out_counts [f * stride ...] and the number written to out_n[f].
+void launch_facet_topk(cudaStream_t st, const FacetStep* facets, const uint32_t* top, uint32_t n_facets, uint32_t stride, uint32_t* out_ids, uint32_t* out_counts, uint32_t* out_n);
 
 // Final ordering of each request's heap: merges `n_src` gathered heaps per query
 // (n_src = 1: the local one) into `out_keys` [n_queries][stride] sorted by key desc,

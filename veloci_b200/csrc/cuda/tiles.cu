@@ -226,6 +226,10 @@ __device__ bool eval_program(const uint32_t* __restrict__ prog, uint32_t len, co
             sc[sp] = sum * nd * nd;
             ++sp;
             pc += 3 + n;
+        } else if (op == kOpFilter) {
+            sp -= 1;
+            pr[sp - 1] = pr[sp - 1] && pr[sp];
+            pc += 1;
         } else {  // kOpIntersect
             const int n = (int)prog[pc + 1];
             bool all = true;
@@ -260,7 +264,9 @@ struct ItemCtx {
 
 // Everything after the request tree for one present anchor: boosts, threshold, survivor list.
 // Returns the key to leave in arr[0][idx] (non-zero only for a survivor deferred to the next merge round).
-__device__ __forceinline__ uint32_t finish_anchor(const TileArgs& a, const ItemCtx& c, uint32_t anchor, float score, uint32_t* s_nsurv, unsigned long long* s_list) {
+// `leaf_keys` (with `leaf_stride` between leaves) are the anchor's keys in the part arrays, for the post ops.
+__device__ __forceinline__ uint32_t finish_anchor(const TileArgs& a, const ItemCtx& c, uint32_t anchor, float score, uint32_t* s_nsurv, unsigned long long* s_list,
+                                                  const uint32_t* leaf_keys = nullptr, uint32_t leaf_stride = 0) {
     if (c.qp.n_boosts) {
         if (c.fast_boost) {
             // the boost can only shrink `score * max_mult`: skip the gather when even that cannot beat the k-th best so far
@@ -287,6 +293,45 @@ __device__ __forceinline__ uint32_t finish_anchor(const TileArgs& a, const ItemC
                 if (skip || anchor >= bs.n) continue;
                 const uint32_t bits = __ldg(bs.column + anchor);
                 if (bits != kNoValue) score = apply_boost_step(bs, score, __uint_as_float(bits));
+            }
+        }
+    }
+    if (c.qp.post_len) {
+        const uint32_t* post = a.prog + c.qp.post_begin;
+        uint32_t pc = 0;
+        while (pc < c.qp.post_len) {
+            const uint32_t op = post[pc];
+            const uint32_t key = leaf_keys[post[pc + 1] * leaf_stride];
+            if (op == kPostMulIfPresent) {
+                if (key) score = score * __uint_as_float(post[pc + 2]);
+                pc += 3;
+            } else {  // kPostMulValue
+                if (key) score = score * vbit::key_score(~key);  // the leaf keeps the smallest value: keys are complemented
+                pc += 2;
+            }
+        }
+    }
+    for (uint32_t f = 0; f < c.qp.n_facets; ++f) {  // count_values_for_ids / join_anchor_to_leaf (facet.rs:31-83)
+        const FacetStep& fs = a.facets[c.qp.facet_begin + f];
+        if (anchor >= fs.step[0].n_ids) continue;
+        for (uint32_t i0 = fs.step[0].off[anchor]; i0 < fs.step[0].off[anchor + 1]; ++i0) {
+            const uint32_t v0 = fs.step[0].val[i0];
+            if (fs.n_steps == 1) {
+                if (v0 < fs.hist_size) atomicAdd(fs.hist + v0, 1u);
+                continue;
+            }
+            if (v0 >= fs.step[1].n_ids) continue;
+            for (uint32_t i1 = fs.step[1].off[v0]; i1 < fs.step[1].off[v0 + 1]; ++i1) {
+                const uint32_t v1 = fs.step[1].val[i1];
+                if (fs.n_steps == 2) {
+                    if (v1 < fs.hist_size) atomicAdd(fs.hist + v1, 1u);
+                    continue;
+                }
+                if (v1 >= fs.step[2].n_ids) continue;
+                for (uint32_t i2 = fs.step[2].off[v1]; i2 < fs.step[2].off[v1 + 1]; ++i2) {
+                    const uint32_t v2 = fs.step[2].val[i2];
+                    if (v2 < fs.hist_size) atomicAdd(fs.hist + v2, 1u);
+                }
             }
         }
     }
@@ -324,11 +369,11 @@ __device__ __forceinline__ uint32_t eval_idx(const TileArgs& a, const ItemCtx& c
     } else {
         present = eval_program(a.prog + c.qp.prog_begin, c.qp.prog_len, arr, c.tile, idx, score);
     }
-    for (uint32_t l = 0; l < L; ++l) arr[l * c.tile + idx] = 0;
-    if (!present) return 0;
-    const uint32_t keep = finish_anchor(a, c, c.tile_base + idx, score, s_nsurv, s_list);
-    if (keep) arr[idx] = keep;
-    return 1;
+    uint32_t keep = 0;
+    if (present) keep = finish_anchor(a, c, c.tile_base + idx, score, s_nsurv, s_list, arr + idx, c.tile);
+    for (uint32_t l = 1; l < L; ++l) arr[l * c.tile + idx] = 0;
+    arr[idx] = keep;
+    return present ? 1u : 0u;
 }
 
 // ---------------------------------------------------------------- tile evaluation
@@ -490,7 +535,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
             if (bs.n_skip == 0 && bs.expr_op == kExprNone) {
                 c.fast_boost = true;
                 c.col = bs.column, c.col_n = bs.n, c.fun = bs.fun, c.param = bs.param;
-                if (bs.can_prune != 0 && !qp.emit_all && qp.k != 0 && c.tau != 0 && bs.max_mult > 0.0f) {
+                if (bs.can_prune != 0 && !qp.emit_all && qp.k != 0 && c.tau != 0 && bs.max_mult > 0.0f && qp.post_len == 0 && qp.n_facets == 0) {
                     const float tau_score = vbit::key_score((uint32_t)(c.tau >> 32));
                     if (tau_score > 1e-30f) {
                         // score < prune_below  =>  fl(score * max_mult) < tau_score  (one part in 2^20 of slack for the roundings)
@@ -544,7 +589,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
 
         // (2) epilogue of densely hit tiles: tree, boosts, count, threshold; leaves the part arrays zeroed
         if (!sparse_mode) {
-            if (qp.prog_len == 0 && L <= 4) {
+            if (qp.prog_len == 0 && L <= 4 && qp.post_len == 0 && qp.n_facets == 0) {
                 if (qp.nonneg) {
                     switch (L) {
                         case 1: my_present += sweep_flat<1, true>(a, c, arr, tid, &s_nsurv, s_list); break;
@@ -649,6 +694,56 @@ void launch_tile_eval(cudaStream_t st, const TileArgs& a, int n_sms) {
     unsigned long long blocks = (unsigned long long)n_sms * (unsigned)per_sm;
     if (blocks > a.n_items) blocks = a.n_items;
     tile_eval_kernel<<<(unsigned)blocks, kTileThreads, smem, st>>>(a);
+    count_launch();
+}
+
+// ---------------------------------------------------------------- facet groups
+// One block per facet histogram: repeated arg-max in (count desc, value id asc) order below the previous pick.
+__global__ void __launch_bounds__(256) facet_topk_kernel(const FacetStep* __restrict__ facets, const uint32_t* __restrict__ top, uint32_t stride, uint32_t* __restrict__ out_ids,
+                                                         uint32_t* __restrict__ out_counts, uint32_t* __restrict__ out_n) {
+    __shared__ unsigned long long s_best[8];
+    __shared__ unsigned long long s_pick;
+    const FacetStep fs = facets[blockIdx.x];
+    const uint32_t want = min(top[blockIdx.x], stride);
+    // order key: count in the upper half, complemented value id below (larger key = earlier group)
+    unsigned long long prev = ~0ull;
+    uint32_t n_out = 0;
+    for (uint32_t r = 0; r < want; ++r) {
+        unsigned long long best = 0;
+        for (uint32_t v = threadIdx.x; v < fs.hist_size; v += blockDim.x) {
+            const uint32_t cnt = fs.hist[v];
+            if (!cnt) continue;
+            const unsigned long long key = ((unsigned long long)cnt << 32) | (0xFFFFFFFFu - v);
+            if (key < prev && key > best) best = key;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long y = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+            best = y > best ? y : best;
+        }
+        if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long b = 0;
+            for (int w = 0; w < 8; ++w) b = s_best[w] > b ? s_best[w] : b;
+            s_pick = b;
+        }
+        __syncthreads();
+        const unsigned long long pick = s_pick;
+        if (pick == 0) break;
+        if (threadIdx.x == 0) {
+            out_ids[(size_t)blockIdx.x * stride + r] = 0xFFFFFFFFu - (uint32_t)pick;
+            out_counts[(size_t)blockIdx.x * stride + r] = (uint32_t)(pick >> 32);
+        }
+        prev = pick;
+        n_out = r + 1;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_n[blockIdx.x] = n_out;
+}
+
+void launch_facet_topk(cudaStream_t st, const FacetStep* facets, const uint32_t* top, uint32_t n_facets, uint32_t stride, uint32_t* out_ids, uint32_t* out_counts, uint32_t* out_n) {
+    if (!n_facets) return;
+    facet_topk_kernel<<<n_facets, 256, 0, st>>>(facets, top, stride, out_ids, out_counts, out_n);
     count_launch();
 }
 

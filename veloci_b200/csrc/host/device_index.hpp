@@ -274,6 +274,7 @@ struct CsrDev {  // id -> list<u32>
     DevBuf<uint32_t> off;  // n_ids + 1
     DevBuf<uint32_t> val;
     std::vector<uint32_t> h_off, h_val;  // host copy (small stores are also walked on the host)
+    uint32_t n_values = 0;               // largest value + 1
     CsrView view() const { return CsrView{off.p, val.p, (uint32_t)n_ids}; }
 };
 
@@ -518,6 +519,7 @@ struct DeviceIndex {
             c.n_ids = 0;
             c.h_off.assign(1, 0);
         }
+        for (uint32_t v : c.h_val) c.n_values = std::max(c.n_values, v + 1);
         c.off.upload(c.h_off);
         c.val.upload(c.h_val);
         device_bytes += c.off.bytes() + c.val.bytes();

@@ -9,7 +9,9 @@
 //   phase 4  tile evaluation   } top_n_sort: (tile, request) items on the plane path / the general path
 //   phase 5  heap finalisation                        (apply_top_skip happens on the host view)
 #pragma once
+#include <chrono>
 #include <cstdlib>
+#include <thread>
 
 #include "../cuda/bitvec.cuh"
 #include "../cuda/kernels.cuh"
@@ -76,6 +78,11 @@ struct Batch {
     DevBuf<FastDesc> d_fast;
     DevBuf<uint32_t> d_fast_item_cursor, d_fast_item_begin;
     DevBuf<FastItem> d_fast_items;
+    // device: facets
+    DevBuf<FacetStep> d_facets;
+    DevBuf<uint32_t> d_facet_top, d_facet_hist, d_facet_ids, d_facet_counts, d_facet_n;
+    uint32_t n_facets = 0, facet_stride = 1;
+    std::vector<uint32_t> h_facet_ids, h_facet_counts, h_facet_n;
     const ColumnLevels* lev_dev = nullptr;  // boost column whose level bits the plane kernel stages in shared memory
     ColumnLevels lev_hdr{};
     uint64_t stat_fast_items = 0, stat_general_items = 0, stat_plane_evaluated = 0;
@@ -110,8 +117,36 @@ struct Batch {
         n = count;
         plan.ix = ix;
         plan.requests.reserve(n);
-        for (uint32_t i = 0; i < n; ++i) plan.add_request(request_json[i] ? request_json[i] : "");
+        const auto t0 = std::chrono::steady_clock::now();
+        // every thread parses and plans a contiguous chunk of the requests; the chunk plans are merged in request order
+        const unsigned hw = n >= 256 ? std::max(1u, std::min(16u, std::thread::hardware_concurrency())) : 1u;
+        if (hw > 1) {
+            std::vector<vplan::BatchPlan> chunks(hw);
+            std::vector<std::thread> pool;
+            const uint32_t chunk = (n + hw - 1) / hw;
+            for (unsigned t = 0; t < hw; ++t) {
+                const uint32_t a = t * chunk, b = std::min(n, a + chunk);
+                if (a >= b) break;
+                chunks[t].ix = ix;
+                pool.emplace_back([&, t, a, b]() {
+                    for (uint32_t i = a; i < b; ++i) chunks[t].add_request(request_json[i] ? request_json[i] : "");
+                });
+            }
+            for (auto& th : pool) th.join();
+            const auto t1m = std::chrono::steady_clock::now();
+            (void)t1m;
+            for (unsigned t = 0; t < hw; ++t) plan.merge(chunks[t]);
+        } else {
+            for (uint32_t i = 0; i < n; ++i) plan.add_request(request_json[i] ? request_json[i] : "");
+        }
+        const auto t1 = std::chrono::steady_clock::now();
+        const auto t2 = std::chrono::steady_clock::now();
         upload_plan();
+        if (getenv("VELOCI_DEBUG")) {
+            const auto t3 = std::chrono::steady_clock::now();
+            auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "[veloci] prepare: parse + plan %.2f ms (%u threads), upload %.2f ms\n", ms(t0, t1), hw, ms(t2, t3));
+        }
     }
 
     // field search only (vgpu_field_search)
@@ -253,6 +288,24 @@ struct Batch {
         d_prog.upload(plan.prog);
         d_programs.upload(plan.programs);
         d_boosts.upload(plan.boosts);
+        n_facets = (uint32_t)plan.facets.size();
+        if (n_facets) {
+            uint64_t total = 0;
+            for (auto& f : plan.facets) total += f.hist_size;
+            if (total > (1ull << 30)) throw std::runtime_error("facet histograms of this batch exceed 4 GB");
+            d_facet_hist.alloc((size_t)total + 1);
+            uint64_t at = 0;
+            facet_stride = 1;
+            for (size_t i = 0; i < plan.facets.size(); ++i) {
+                plan.facets[i].hist = d_facet_hist.p + at;
+                at += plan.facets[i].hist_size;
+                facet_stride = std::max(facet_stride, plan.facet_top[i]);
+            }
+            d_facets.upload(plan.facets);
+            d_facet_top.upload(plan.facet_top);
+            d_facet_ids.alloc((size_t)n_facets * facet_stride), d_facet_counts.alloc((size_t)n_facets * facet_stride), d_facet_n.alloc(n_facets);
+            h2d_bytes += plan.facets.size() * sizeof(FacetStep) + plan.facet_top.size() * 4;
+        }
         parts_of_dict.assign(plan.dict_names.size(), {});
         probe_of_dict.assign(plan.dict_names.size(), {});
         max_m_of_dict.assign(plan.dict_names.size(), 0);
@@ -503,6 +556,7 @@ struct Batch {
         VDEV_CUDA(cudaMemsetAsync(d_tau.p, 0, d_tau.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_num_hits.p, 0, d_num_hits.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_lock.p, 0, d_lock.bytes(), stream));
+        if (n_facets) VDEV_CUDA(cudaMemsetAsync(d_facet_hist.p, 0, d_facet_hist.bytes(), stream));
         // ---- phase 3: plane evaluation.  Tile 0 first, its requests spread over all SMs, then a few more tiles: the
         // requests' thresholds are then close to final when the bulk of the tiles runs and prunes against them.
         if (planes_on && n_fast_items) {
@@ -535,7 +589,7 @@ struct Batch {
         {
             TileArgs a;
             a.items = d_items.p, a.slice_recs = d_slice_recs.p;
-            a.queries = d_programs.p, a.n_queries = n, a.leaf_part = d_leaf_part.p, a.prog = d_prog.p, a.boosts = d_boosts.p;
+            a.queries = d_programs.p, a.n_queries = n, a.leaf_part = d_leaf_part.p, a.prog = d_prog.p, a.boosts = d_boosts.p, a.facets = d_facets.p;
             a.parts = d_parts.p, a.slices = d_slices.p, a.postings = d_postings.p, a.g_score = d_g_score.p, a.g_begin = d_g_begin.p, a.g_row = d_g_row.p, a.g_df = d_g_df.p;
             a.toff = d_toff.p, a.bucket = d_bucket.p, a.sparse = d_sparse.p;
             a.n_tiles = n_tiles, a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
@@ -546,7 +600,8 @@ struct Batch {
             launch_tile_eval(stream, a, n_sms);
         }
         VDEV_CUDA(cudaEventRecord(ev[5], stream));
-        // ---- phase 5: final order of the local heaps
+        // ---- phase 5: final order of the local heaps, top groups of the facet histograms
+        if (n_facets) launch_facet_topk(stream, d_facets.p, d_facet_top.p, n_facets, facet_stride, d_facet_ids.p, d_facet_counts.p, d_facet_n.p);
         launch_merge_heaps(stream, reinterpret_cast<const uint64_t*>(d_heap.p), reinterpret_cast<const uint64_t*>(d_num_hits.p), 1, n, stride, d_programs.p, d_out_keys.p, d_out_hits.p);
         VDEV_CUDA(cudaEventRecord(ev[6], stream));
         VDEV_CUDA(cudaStreamSynchronize(stream));
@@ -579,6 +634,14 @@ struct Batch {
             d2h_bytes += h_keys.size() * 8 + h_hits.size() * 8 + sizeof stats;
             stat_union = 0;
             for (uint64_t h : h_hits) stat_union += h;
+        }
+        if (n_facets) {
+            h_facet_ids.resize((size_t)n_facets * facet_stride), h_facet_counts.resize((size_t)n_facets * facet_stride), h_facet_n.resize(n_facets);
+            VDEV_CUDA(cudaMemcpyAsync(h_facet_ids.data(), d_facet_ids.p, h_facet_ids.size() * 4, cudaMemcpyDeviceToHost, stream));
+            VDEV_CUDA(cudaMemcpyAsync(h_facet_counts.data(), d_facet_counts.p, h_facet_counts.size() * 4, cudaMemcpyDeviceToHost, stream));
+            VDEV_CUDA(cudaMemcpyAsync(h_facet_n.data(), d_facet_n.p, h_facet_n.size() * 4, cudaMemcpyDeviceToHost, stream));
+            VDEV_CUDA(cudaStreamSynchronize(stream));
+            d2h_bytes += (h_facet_ids.size() * 2 + h_facet_n.size()) * 4;
         }
         fetched = true;
     }

@@ -33,6 +33,7 @@ struct RequestPlan {
     uint64_t top = 10, skip = 0;
     std::vector<vhost::FacetRequest> facets;
     bool has_facets = false;
+    uint32_t facet_begin = 0;  // first of the request's entries in BatchPlan::facets
 };
 
 // `x op y` boost expression (src/expression.rs:25-100)
@@ -84,6 +85,7 @@ struct BatchPlan {
     std::vector<PartQuery> parts;
     std::vector<uint32_t> part_dict;  // part -> dictionary table index
     std::unordered_map<std::string, uint32_t> part_index;
+    std::vector<std::string> part_keys;  // part -> its key in part_index
     // tables of device views referenced by index
     std::vector<std::string> dict_names, postings_names;
     std::unordered_map<std::string, uint32_t> dict_index, postings_index;
@@ -92,6 +94,9 @@ struct BatchPlan {
     std::vector<uint32_t> leaf_part;
     std::vector<uint32_t> prog;
     std::vector<BoostStep> boosts;
+    std::vector<vdev::FacetStep> facets;   // hist pointers are set by the engine
+    std::vector<uint32_t> facet_top;       // groups wanted per facet
+    std::vector<std::string> facet_text_path;  // dictionary the value ids of the facet belong to
     uint32_t max_leaves = 1, max_k = 1;
 
     uint32_t dict_id(const std::string& path) {
@@ -155,7 +160,47 @@ struct BatchPlan {
         parts.push_back(q);
         part_dict.push_back(did);
         part_index.emplace(key, id);
+        part_keys.push_back(key);
         return id;
+    }
+
+    // Appends the plan of another chunk of the same batch (built on another thread): its parts are unified with the
+    // parts already known, its tables are appended with their indexes shifted.
+    void merge(const BatchPlan& o) {
+        std::vector<uint32_t> dict_map(o.dict_names.size()), post_map(o.postings_names.size()), part_map(o.parts.size());
+        for (size_t i = 0; i < o.dict_names.size(); ++i) dict_map[i] = dict_id(o.dict_names[i]);
+        for (size_t i = 0; i < o.postings_names.size(); ++i) post_map[i] = postings_id(o.postings_names[i]);
+        for (size_t i = 0; i < o.parts.size(); ++i) {
+            auto it = part_index.find(o.part_keys[i]);
+            if (it != part_index.end()) {
+                part_map[i] = it->second;
+                continue;
+            }
+            PartQuery q = o.parts[i];
+            if (q.postings != vdev::kNoValue) q.postings = post_map[q.postings];
+            const uint32_t id = (uint32_t)parts.size();
+            parts.push_back(q);
+            part_dict.push_back(dict_map[o.part_dict[i]]);
+            part_index.emplace(o.part_keys[i], id);
+            part_keys.push_back(o.part_keys[i]);
+            part_map[i] = id;
+        }
+        const uint32_t leaf_base = (uint32_t)leaf_part.size(), prog_base = (uint32_t)prog.size(), boost_base = (uint32_t)boosts.size(), facet_base = (uint32_t)facets.size();
+        facets.insert(facets.end(), o.facets.begin(), o.facets.end());
+        facet_top.insert(facet_top.end(), o.facet_top.begin(), o.facet_top.end());
+        facet_text_path.insert(facet_text_path.end(), o.facet_text_path.begin(), o.facet_text_path.end());
+        for (uint32_t p : o.leaf_part) leaf_part.push_back(part_map[p]);
+        prog.insert(prog.end(), o.prog.begin(), o.prog.end());
+        boosts.insert(boosts.end(), o.boosts.begin(), o.boosts.end());
+        for (size_t i = 0; i < o.programs.size(); ++i) {
+            QueryProgram qp = o.programs[i];
+            if (qp.active) qp.leaf_begin += leaf_base, qp.prog_begin += prog_base, qp.boost_begin += boost_base, qp.post_begin += prog_base, qp.facet_begin += facet_base;
+            programs.push_back(qp);
+            requests.push_back(o.requests[i]);
+            requests.back().facet_begin += facet_base;
+        }
+        max_leaves = std::max(max_leaves, o.max_leaves);
+        max_k = std::max(max_k, o.max_k);
     }
 
     struct Node {  // emitted subtree
@@ -240,6 +285,31 @@ struct BatchPlan {
         return s;
     }
 
+    // get_facet's index walk (facet.rs:31-83): one id -> ids join, or the chain of parent_to_value_id joins
+    void add_facet(const vhost::FacetRequest& fr) {
+        const std::vector<std::string> steps = vfmt::get_steps_to_anchor(fr.field);
+        std::vector<std::string> paths;
+        if (steps.size() == 1 || ix->host->has_index(steps.back() + ".anchor_to_text_id"))
+            paths.push_back(steps.size() == 1 ? steps.front() + ".parent_to_value_id" : steps.back() + ".anchor_to_text_id");
+        else
+            for (auto& st : steps) paths.push_back(st + ".parent_to_value_id");
+        if (paths.size() > vdev::kMaxFacetSteps) throw Unsupported("facet fields nested deeper than three levels are outside the accelerated path");
+        vdev::FacetStep fs;
+        memset(&fs, 0, sizeof fs);
+        fs.n_steps = (uint32_t)paths.size();
+        for (size_t i = 0; i < paths.size(); ++i) {
+            auto it = ix->stores.find(paths[i]);
+            if (it == ix->stores.end()) ix->host->path_not_found(paths[i]);
+            fs.step[i] = it->second.view();
+            fs.hist_size = it->second.n_values;
+        }
+        const uint64_t top = fr.top ? *fr.top : (uint64_t)fs.hist_size;
+        if (std::min<uint64_t>(top, fs.hist_size) > 1024) throw Unsupported("facets with more than 1024 groups are outside the accelerated path");
+        facets.push_back(fs);
+        facet_top.push_back((uint32_t)std::min<uint64_t>(top, fs.hist_size));
+        facet_text_path.push_back(steps.back());
+    }
+
     // a single boost step without skip list or expression travels inside the QueryProgram
     static void set_fast_boost(QueryProgram& qp, const std::vector<BoostStep>& steps) {
         qp.fb_flags = 0;
@@ -260,18 +330,39 @@ struct BatchPlan {
         rp.top = request.top.value_or(10);  // search.rs:146
         rp.skip = request.skip.value_or(0);
         if (!request.search_req) throw InvalidRequest("search_req is None, but is required in search");
-        if (request.filter) throw Unsupported("filter is not on the accelerated path yet");
         if (request.phrase_boosts && !request.phrase_boosts->empty()) throw Unsupported("phrase_boosts are not on the accelerated path yet");
-        if (request.boost_term && !request.boost_term->empty()) throw Unsupported("boost_term is not on the accelerated path yet");
         if (request.text_locality) throw Unsupported("text_locality is not on the accelerated path yet");
-        if (request.facets && !request.facets->empty()) throw Unsupported("facets are not on the accelerated path yet");
         if (has_nested_boost(*request.search_req)) throw Unsupported("boosts inside the search tree are not on the accelerated path yet");
         if (rp.top + rp.skip > vdev::kMaxK) throw Unsupported("top + skip above 256 is outside the accelerated path");
 
-        std::vector<uint32_t> leaves, code;
+        std::vector<uint32_t> leaves, code, post;
         const vhost::SearchRequest& root = *request.search_req;
         emit(root, leaves, code);
+        bool extras = false;
+        if (request.filter) {  // the filter tree is evaluated for presence only; hits outside it are dropped (set_op.rs:311-326)
+            emit(*request.filter, leaves, code);
+            code.push_back(vdev::kOpFilter);
+            extras = true;
+        }
+        if (request.boost_term)  // search.rs:176, boost.rs:89-195: hits that the part also finds are multiplied by its boost (default 2.0)
+            for (auto& part : *request.boost_term) {
+                const uint32_t leaf = (uint32_t)leaves.size();
+                leaves.push_back(add_part(part));
+                const float v = part.boost.value_or(2.0f);
+                uint32_t bits;
+                memcpy(&bits, &v, 4);
+                post.push_back(vdev::kPostMulIfPresent), post.push_back(leaf), post.push_back(bits);
+                extras = true;
+            }
         if (leaves.size() > vdev::kMaxLeaves) throw Unsupported("more than 12 search parts in one request");
+        if (request.facets && !request.facets->empty()) {
+            if (ix->n_shards > 1) throw Unsupported("facets on a sharded index are not on the accelerated path yet");
+            rp.facets = *request.facets;
+            rp.has_facets = true;
+            rp.facet_begin = (uint32_t)facets.size();
+            for (auto& fr : rp.facets) add_facet(fr);
+            extras = true;
+        }
 
         std::vector<BoostStep> steps;
         if (request.boost)
@@ -282,7 +373,9 @@ struct BatchPlan {
 
         // flat `or` of search parts with pairwise distinct terms: leaves in slot (= sorted term) order, no program
         bool flat = false;
-        if (leaves.size() == 1 && code.size() == 2) {
+        if (extras) {
+            // filters, post ops and facets run on the program path
+        } else if (leaves.size() == 1 && code.size() == 2) {
             flat = true;
         } else if (root.kind == vhost::SearchRequest::Or && code.size() == 2 * leaves.size() + 3 + leaves.size() && code[2 * leaves.size()] == vdev::kOpUnion) {
             // Parts that share a term slot must be the very same search part (then their hit lists are identical and
@@ -306,6 +399,11 @@ struct BatchPlan {
         qp.prog_begin = (uint32_t)prog.size();
         qp.prog_len = flat ? 0u : (uint32_t)code.size();
         if (!flat) prog.insert(prog.end(), code.begin(), code.end());
+        qp.post_begin = (uint32_t)prog.size();
+        qp.post_len = (uint32_t)post.size();
+        prog.insert(prog.end(), post.begin(), post.end());
+        qp.facet_begin = rp.facet_begin;
+        qp.n_facets = (uint32_t)rp.facets.size();
         qp.boost_begin = (uint32_t)boosts.size();
         qp.n_boosts = (uint32_t)steps.size();
         boosts.insert(boosts.end(), steps.begin(), steps.end());
@@ -319,15 +417,40 @@ struct BatchPlan {
         max_k = std::max<uint32_t>(max_k, std::max<uint32_t>(qp.k, 1));
     }
 
+    // Request JSON -> Request: independent of the batch, so a batch parses its requests on several threads.
+    struct Parsed {
+        vhost::Request request;
+        int32_t status = 0;
+        std::string message;
+    };
+    static void parse_into(const char* json, Parsed& out) {
+        try {
+            out.request = vhost::parse_request_json(json, strlen(json));
+        } catch (const vhost::RequestError& e) {
+            out.status = 5, out.message = e.what();
+        } catch (const std::exception& e) {
+            out.status = 9, out.message = e.what();
+        }
+    }
+
     void add_request(const char* json) {
+        Parsed p;
+        parse_into(json, p);
+        add_parsed(p);
+    }
+
+    void add_parsed(const Parsed& parsed) {
         RequestPlan rp;
         QueryProgram qp;
         memset(&qp, 0, sizeof qp);
         // a failing request must not leave half-registered leaves behind
-        const size_t leaf_mark = leaf_part.size(), prog_mark = prog.size(), boost_mark = boosts.size();
+        const size_t leaf_mark = leaf_part.size(), prog_mark = prog.size(), boost_mark = boosts.size(), facet_mark = facets.size();
         try {
-            vhost::Request r = vhost::parse_request_json(json, strlen(json));
-            plan_request(r, rp, qp);
+            if (parsed.status != 0) {
+                rp.status = parsed.status, rp.message = parsed.message;
+            } else {
+                plan_request(parsed.request, rp, qp);
+            }
         } catch (const InvalidRequest& e) {
             rp.status = 1, rp.message = e.what();
         } catch (const vhost::FstNotFound& e) {
@@ -343,6 +466,8 @@ struct BatchPlan {
         }
         if (rp.status != 0) {
             leaf_part.resize(leaf_mark), prog.resize(prog_mark), boosts.resize(boost_mark);
+            facets.resize(facet_mark), facet_top.resize(facet_mark), facet_text_path.resize(facet_mark);
+            rp.facets.clear(), rp.has_facets = false;
             memset(&qp, 0, sizeof qp);
         }
         requests.push_back(std::move(rp));

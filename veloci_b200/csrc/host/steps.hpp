@@ -18,9 +18,28 @@ struct FacetGroups {
     std::vector<FacetGroup> groups;
 };
 
+// SearchResult.facets: the device's (value id, count) groups plus their text (facet.rs:60-72)
 inline void materialize_facets(vdev::Batch& b, std::vector<std::vector<FacetGroups>>& out) {
     if (!out.empty()) return;
+    b.fetch();
     out.resize(b.n);
+    for (uint32_t q = 0; q < b.n; ++q) {
+        const vplan::RequestPlan& rp = b.plan.requests[q];
+        if (rp.status != 0) continue;
+        for (size_t f = 0; f < rp.facets.size(); ++f) {
+            const uint32_t fi = rp.facet_begin + (uint32_t)f;
+            FacetGroups fg;
+            fg.field = rp.facets[f].field;
+            for (uint32_t g = 0; g < b.h_facet_n[fi]; ++g) {
+                FacetGroup grp;
+                grp.id = b.h_facet_ids[(size_t)fi * b.facet_stride + g];
+                grp.count = b.h_facet_counts[(size_t)fi * b.facet_stride + g];
+                grp.text = b.ix->host->get_text_for_id(b.plan.facet_text_path[fi], grp.id);
+                fg.groups.push_back(std::move(grp));
+            }
+            out[q].push_back(std::move(fg));
+        }
+    }
 }
 
 inline vhost::SearchPart parse_part(const char* json) {
