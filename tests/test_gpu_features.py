@@ -67,6 +67,10 @@ def test_filters(test_all):  # tests/all/tests.rs:753-824
         {"search_req": OR_MAJ_URGE, "filter": {"or": {"queries": [S("1587690", "ent_seq"), S("urge", "meanings.eng[]")]}}},
         {"search_req": OR_MAJ_URGE, "filter": {"and": {"queries": [S("majestät", "meanings.ger[]"), S("urge", "meanings.eng[]")]}}},
         {"search_req": S("will", "meanings.eng[]"), "filter": S("nothing-matches", "ent_seq"), "boost": [{"path": "commonness", "boost_fun": "Log10", "param": 1}]},
+        # filter parts are searched for ids: a term that only occurs as a token of longer texts selects nothing (search_field.rs:468-498)
+        {"search_req": OR_MAJ_URGE, "filter": S("majestätischer", "meanings.ger[]")},
+        {"search_req": OR_MAJ_URGE, "filter": S("majestät", "meanings.ger[]", levenshtein_distance=1)},
+        {"search_req": S("will", "meanings.eng[]"), "filter": S("will", "meanings.eng[]")},
     ])
 
 
@@ -102,3 +106,27 @@ def test_facets_large(gpu, native_libs):  # tests/all/tests_large.rs:40-112
     ])
     assert sorted(f[:2] for f in b.result(0)["facets"]["tags[]"]) == sorted([("nice", 300), ("cool", 300)])
     assert b.result(1)["num_hits"] == 600
+
+
+def _pb(path, t1="die", t2="erbin"):
+    return {"path": path, "search1": {"terms": [t1], "path": path}, "search2": {"terms": [t2], "path": path}}
+
+
+def test_phrase_boosts(gpu, native_libs):  # tests/all/test_phrase.rs:39-99, test_scores.rs:106-126
+    index, oracle = _pair(gpu, fx.TEST_PHRASE_DOCS, fx.TEST_PHRASE_CONFIG)
+    b = compare(index, oracle, [
+        {"search_req": S("erbin", "title"), "phrase_boosts": [_pb("title")]},
+        {"search_req": {"or": {"queries": [S(t, p) for p in ("title", "tags[]") for t in ("die", "erbin")]}}, "phrase_boosts": [_pb("title"), _pb("tags[]")]},
+        {"search_req": {"and": {"queries": [S("die", "title"), S("erbin", "title")]}}, "phrase_boosts": [_pb("title")]},
+        {"search_req": {"or": {"queries": [S(t, "tags[]") for t in ("greg", "tagebuch", "05")]}},
+         "phrase_boosts": [_pb("tags[]", "greg", "tagebuch"), _pb("tags[]", "tagebuch", "05")]},
+        {"search_req": {"or": {"queries": [S("greg", "tags[]", levenshtein_distance=1), S("tagebuch", "tags[]")]}},
+         "phrase_boosts": [{"path": "tags[]", "search1": {"terms": ["greg"], "path": "tags[]", "levenshtein_distance": 1}, "search2": {"terms": ["tagebuch"], "path": "tags[]"}}],
+         "boost_term": [{"terms": ["05"], "path": "tags[]"}]},
+    ])
+    first = b.result(0)["data"][0][0]
+    assert fx.TEST_PHRASE_DOCS[first]["title"] == "die erbin"
+    index2, oracle2 = _pair(gpu, fx.TEST_SCORE_DOCS, fx.TEST_SCORE_CONFIG)
+    compare(index2, oracle2, [
+        {"search_req": {"or": {"queries": [S(t, "title") for t in ("greg", "tagebuch", "05")]}}, "phrase_boosts": [_pb("title", "greg", "tagebuch")]},
+    ])

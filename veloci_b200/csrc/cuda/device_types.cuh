@@ -133,6 +133,7 @@ enum PartFlags : uint32_t {
     kPartRawCase = 4u,        // ignore_case == false: match on raw scalars
     kPartCheckPrefix = 8u,    // starts_with || levenshtein != 0  (:302)
     kPartHasBoost = 16u,
+    kPartList = 32u,          // not a search part: its tile bucket is filled by a list producer (phrase pairs, text locality, 1:n boosts)
 };
 
 struct PartQuery {  // one distinct RequestSearchPart of the batch (272 B)
@@ -180,6 +181,23 @@ struct SliceRec {  // 32 B
     uint32_t pad;
 };
 static const uint32_t kTaskPostings = 128;  // postings one warp takes from a slice at a time
+
+// ---- list producers: anchors (with a value) computed from the matched terms of search parts ----
+struct PhraseView {  // persistence_data_binary_search.rs:126-203, flattened
+    const uint64_t* keys;     // sorted (term1 << 32 | term2)
+    const uint32_t* off;      // [n + 1]
+    const uint32_t* anchors;
+    uint32_t n;
+};
+struct PhraseMember {  // one phrase_boosts entry: every (term of part1, term of part2) pair's anchors go to `list_part`
+    uint32_t part1, part2, list_part, pad;
+    PhraseView store;
+};
+
+struct IdsMember {  // hits_ids of a part resolved to anchors: text_id_to_anchor, or the id itself on an anchor-identity column (search_field.rs:468-498)
+    uint32_t part, list_part, identity, pad;
+    CsrView text_id_to_anchor;
+};
 
 // ---- request programs (plan_creator, execution_plan.rs:132-534) ----
 enum ProgOp : uint32_t {

@@ -562,16 +562,73 @@ __global__ void sparse_fill_kernel(SparseArgs a) {
 }
 
 __global__ void part_slices_kernel(PartSlices* __restrict__ out, const uint32_t* __restrict__ part_begin, const uint32_t* __restrict__ dense_cursor,
-                                   const uint64_t* __restrict__ sparse_base, uint32_t n_parts) {
+                                   const uint64_t* __restrict__ sparse_base, const PartQuery* __restrict__ parts, uint32_t n_parts) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_parts) return;
     PartSlices s;
     s.m_begin = part_begin[p];
     s.n_match = part_begin[p + 1] - part_begin[p];
     s.n_dense = dense_cursor[p];
+    if (parts[p].flags & kPartList) s.n_match = 1, s.n_dense = 0;  // a list part: everything it has is in its tile bucket
     s.sparse_row = p;
     s.sparse_base = sparse_base[p];
     out[p] = s;
+}
+
+// ---------------------------------------------------------------- list producers
+// Adds one entry to the tile bucket of a list part (count pass: only counts it).
+__device__ __forceinline__ void list_emit(const ListArgs& a, uint32_t list_part, uint32_t anchor, uint32_t key) {
+    if (anchor < a.anchor_lo || anchor >= a.anchor_hi) return;
+    uint32_t* row = a.bucket + (size_t)list_part * (a.n_tiles + 1);
+    const uint32_t t = (anchor - a.anchor_lo) >> a.tile_log2;
+    const uint32_t at = atomicAdd(&row[t + 1], 1u);
+    if (a.sparse) a.sparse[a.sparse_base[list_part] + at] = SparseEntry{anchor, key};
+}
+
+// One block per phrase_boosts entry: for every (t1, t2) of the two parts' matched terms, the anchors of the pair.
+__global__ void __launch_bounds__(128) phrase_pairs_kernel(const PhraseMember* __restrict__ members, ListArgs a) {
+    const PhraseMember m = members[blockIdx.x];
+    const uint32_t b1 = a.part_begin[m.part1], n1 = a.part_begin[m.part1 + 1] - b1;
+    const uint32_t b2 = a.part_begin[m.part2], n2 = a.part_begin[m.part2 + 1] - b2;
+    const unsigned long long pairs = (unsigned long long)n1 * n2;
+    for (unsigned long long x = threadIdx.x; x < pairs; x += blockDim.x) {
+        const uint64_t key = ((uint64_t)a.g_term[b1 + (uint32_t)(x / n2)] << 32) | a.g_term[b2 + (uint32_t)(x % n2)];
+        uint32_t lo = 0, hi = m.store.n;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (m.store.keys[mid] < key) lo = mid + 1;
+            else hi = mid;
+        }
+        if (lo >= m.store.n || m.store.keys[lo] != key) continue;
+        for (uint32_t i = m.store.off[lo]; i < m.store.off[lo + 1]; ++i) list_emit(a, m.list_part, m.store.anchors[i], 0x80000000u);
+    }
+}
+
+// One block per member: the matched term ids of the part, as text ids, to their anchors.
+__global__ void __launch_bounds__(128) ids_to_anchor_kernel(const IdsMember* __restrict__ members, ListArgs a) {
+    const IdsMember m = members[blockIdx.x];
+    const uint32_t b = a.part_begin[m.part], n = a.part_begin[m.part + 1] - b;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t id = a.g_term[b + i];
+        if (m.identity) {
+            list_emit(a, m.list_part, id, 0x80000000u);
+            continue;
+        }
+        if (id >= m.text_id_to_anchor.n_ids) continue;
+        for (uint32_t j = m.text_id_to_anchor.off[id]; j < m.text_id_to_anchor.off[id + 1]; ++j) list_emit(a, m.list_part, m.text_id_to_anchor.val[j], 0x80000000u);
+    }
+}
+
+void launch_ids_to_anchor(cudaStream_t st, const IdsMember* members, uint32_t n_members, const ListArgs& a) {
+    if (!n_members) return;
+    ids_to_anchor_kernel<<<n_members, 128, 0, st>>>(members, a);
+    count_launch();
+}
+
+void launch_phrase_pairs(cudaStream_t st, const PhraseMember* members, uint32_t n_members, const ListArgs& a) {
+    if (!n_members) return;
+    phrase_pairs_kernel<<<n_members, 128, 0, st>>>(members, a);
+    count_launch();
 }
 
 // One thread per request: for every `and` node whose inputs are all search parts, the
@@ -665,9 +722,9 @@ void launch_sparse_fill(cudaStream_t st, const SparseArgs& a) {
     sparse_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
     count_launch();
 }
-void launch_part_slices(cudaStream_t st, PartSlices* out, const uint32_t* part_begin, const uint32_t* dense_cursor, const uint64_t* sparse_base, uint32_t n_parts) {
+void launch_part_slices(cudaStream_t st, PartSlices* out, const uint32_t* part_begin, const uint32_t* dense_cursor, const uint64_t* sparse_base, const PartQuery* parts, uint32_t n_parts) {
     if (!n_parts) return;
-    part_slices_kernel<<<(n_parts + 255) / 256, 256, 0, st>>>(out, part_begin, dense_cursor, sparse_base, n_parts);
+    part_slices_kernel<<<(n_parts + 255) / 256, 256, 0, st>>>(out, part_begin, dense_cursor, sparse_base, parts, n_parts);
     count_launch();
 }
 

@@ -86,7 +86,22 @@ struct SparseArgs {
 void launch_sparse_count(cudaStream_t st, const SparseArgs& a);
 void launch_sparse_scan(cudaStream_t st, uint32_t* bucket, uint32_t n_tiles, uint64_t* sparse_total, uint32_t n_parts);
 void launch_sparse_fill(cudaStream_t st, const SparseArgs& a);
-void launch_part_slices(cudaStream_t st, PartSlices* out, const uint32_t* part_begin, const uint32_t* dense_cursor, const uint64_t* sparse_base, uint32_t n_parts);
+void launch_part_slices(cudaStream_t st, PartSlices* out, const uint32_t* part_begin, const uint32_t* dense_cursor, const uint64_t* sparse_base, const PartQuery* parts, uint32_t n_parts);
+
+// List producers write into the sparse tile buckets of their list parts, in the same two passes as the sparse postings:
+// count (sparse == nullptr) between launch_sparse_count and launch_sparse_scan, fill after launch_sparse_fill.
+struct ListArgs {
+    const uint32_t* part_begin;  // grouped matches of every part
+    const uint32_t* g_term;      // matched term ids
+    uint32_t* bucket;
+    const uint64_t* sparse_base;
+    SparseEntry* sparse;         // nullptr: count pass
+    uint32_t n_tiles, tile_log2, anchor_lo, anchor_hi;
+};
+// get_anchor_for_phrases_in_field (search_field.rs:263-275): one block per member
+void launch_phrase_pairs(cudaStream_t st, const PhraseMember* members, uint32_t n_members, const ListArgs& a);
+// the ids half of resolve_token_to_anchor (search_field.rs:468-498): one block per member
+void launch_ids_to_anchor(cudaStream_t st, const IdsMember* members, uint32_t n_members, const ListArgs& a);
 
 // Patches the sum order of every `and` node (set_op.rs:388-417: the shortest input is
 // swap_remove'd and added last); input lengths are estimated by part_est.

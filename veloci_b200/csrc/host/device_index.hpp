@@ -294,6 +294,7 @@ struct PhraseDev {
     DevBuf<uint64_t> keys;
     DevBuf<uint32_t> off;
     DevBuf<uint32_t> anchors;
+    PhraseView view() const { return PhraseView{keys.p, off.p, anchors.p, (uint32_t)n}; }
 };
 
 struct DeviceIndex {

@@ -78,6 +78,9 @@ struct Batch {
     DevBuf<FastDesc> d_fast;
     DevBuf<uint32_t> d_fast_item_cursor, d_fast_item_begin;
     DevBuf<FastItem> d_fast_items;
+    // device: list producers
+    DevBuf<PhraseMember> d_phrase_members;
+    DevBuf<IdsMember> d_ids_members;
     // device: facets
     DevBuf<FacetStep> d_facets;
     DevBuf<uint32_t> d_facet_top, d_facet_hist, d_facet_ids, d_facet_counts, d_facet_n;
@@ -288,6 +291,10 @@ struct Batch {
         d_prog.upload(plan.prog);
         d_programs.upload(plan.programs);
         d_boosts.upload(plan.boosts);
+        d_ids_members.upload(plan.ids_members);
+        h2d_bytes += plan.ids_members.size() * sizeof(IdsMember);
+        d_phrase_members.upload(plan.phrase_members);
+        h2d_bytes += plan.phrase_members.size() * sizeof(PhraseMember);
         n_facets = (uint32_t)plan.facets.size();
         if (n_facets) {
             uint64_t total = 0;
@@ -312,6 +319,7 @@ struct Batch {
         if (mode == kRequests) {
             for (uint32_t p = 0; p < n_parts; ++p) {
                 const PartQuery& pq = plan.parts[p];
+                if (pq.flags & kPartList) continue;
                 const uint32_t d = plan.part_dict[p];
                 const DictDev& dict = ix->dicts.at(plan.dict_names[d]);
                 bool probe = pq.m >= 1 && pq.d_match <= 2 && !(pq.flags & (kPartPrefix | kPartRawCase));
@@ -370,6 +378,12 @@ struct Batch {
         const uint32_t base = std::max<uint32_t>(1, n_tiles / 2);
         if (!use_planes) return base;
         return 0xFFFFFFFFu;
+    }
+
+    // count pass (la.sparse == nullptr) or fill pass of every list producer of the batch
+    void run_list_producers(const ListArgs& la) {
+        launch_phrase_pairs(stream, d_phrase_members.p, (uint32_t)plan.phrase_members.size(), la);
+        launch_ids_to_anchor(stream, d_ids_members.p, (uint32_t)plan.ids_members.size(), la);
     }
 
     template <class T>
@@ -483,13 +497,19 @@ struct Batch {
             sa.parts = d_parts.p, sa.postings = d_postings.p, sa.bucket = d_bucket.p, sa.sparse_base = d_sparse_base.p, sa.sparse = nullptr;
             sa.n_tiles = n_tiles, sa.tile_log2 = tile_log2, sa.anchor_lo = (uint32_t)ix->anchor_lo;
             launch_sparse_count(stream, sa);
+            ListArgs la;
+            la.part_begin = d_part_begin.p, la.g_term = d_g_term.p, la.bucket = d_bucket.p, la.sparse_base = d_sparse_base.p, la.sparse = nullptr;
+            la.n_tiles = n_tiles, la.tile_log2 = tile_log2, la.anchor_lo = (uint32_t)ix->anchor_lo, la.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
+            run_list_producers(la);
             launch_sparse_scan(stream, d_bucket.p, n_tiles, d_sparse_total.p, n_parts);
             launch_scan_u64(stream, d_sparse_total.p, d_sparse_base.p, n_parts);
             const uint64_t n_sparse = read_back(d_sparse_base.p + n_parts);
             d_sparse.reserve((size_t)std::max<uint64_t>(n_sparse, 1));
             sa.sparse = d_sparse.p;
             launch_sparse_fill(stream, sa);
-            launch_part_slices(stream, d_slices.p, d_part_begin.p, d_dense_cursor.p, d_sparse_base.p, n_parts);
+            la.sparse = d_sparse.p;
+            run_list_producers(la);
+            launch_part_slices(stream, d_slices.p, d_part_begin.p, d_dense_cursor.p, d_sparse_base.p, d_parts.p, n_parts);
             launch_finalize_programs(stream, d_programs.p, n, d_prog.p, d_leaf_part.p, d_part_est.p, d_counters.p + 2);
             if (use_planes) launch_build_fast_desc(stream, d_programs.p, n, d_leaf_part.p, d_part_planes.p, ix->planes.wmax.p, d_fast.p);
             if (use_planes && getenv("VELOCI_DEBUG")) {

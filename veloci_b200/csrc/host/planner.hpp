@@ -7,6 +7,7 @@
 #include <cmath>
 #include <map>
 #include <string>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -94,6 +95,8 @@ struct BatchPlan {
     std::vector<uint32_t> leaf_part;
     std::vector<uint32_t> prog;
     std::vector<BoostStep> boosts;
+    std::vector<vdev::PhraseMember> phrase_members;
+    std::vector<vdev::IdsMember> ids_members;
     std::vector<vdev::FacetStep> facets;   // hist pointers are set by the engine
     std::vector<uint32_t> facet_top;       // groups wanted per facet
     std::vector<std::string> facet_text_path;  // dictionary the value ids of the facet belong to
@@ -164,6 +167,21 @@ struct BatchPlan {
         return id;
     }
 
+    // A part whose hits are produced by a list kernel (phrase pairs, text locality, 1:n boosts) instead of a field search.
+    uint32_t add_list_part() {
+        PartQuery q;
+        memset(&q, 0, sizeof q);
+        q.flags = vdev::kPartList;
+        q.postings = vdev::kNoValue;
+        const uint32_t id = (uint32_t)parts.size();
+        const std::string key = std::string("\x01list#") + std::to_string(id);
+        parts.push_back(q);
+        part_dict.push_back(0);
+        part_index.emplace(key, id);
+        part_keys.push_back(key);
+        return id;
+    }
+
     // Appends the plan of another chunk of the same batch (built on another thread): its parts are unified with the
     // parts already known, its tables are appended with their indexes shifted.
     void merge(const BatchPlan& o) {
@@ -171,6 +189,10 @@ struct BatchPlan {
         for (size_t i = 0; i < o.dict_names.size(); ++i) dict_map[i] = dict_id(o.dict_names[i]);
         for (size_t i = 0; i < o.postings_names.size(); ++i) post_map[i] = postings_id(o.postings_names[i]);
         for (size_t i = 0; i < o.parts.size(); ++i) {
+            if (o.parts[i].flags & vdev::kPartList) {  // list parts are never shared
+                part_map[i] = add_list_part();
+                continue;
+            }
             auto it = part_index.find(o.part_keys[i]);
             if (it != part_index.end()) {
                 part_map[i] = it->second;
@@ -186,6 +208,14 @@ struct BatchPlan {
             part_map[i] = id;
         }
         const uint32_t leaf_base = (uint32_t)leaf_part.size(), prog_base = (uint32_t)prog.size(), boost_base = (uint32_t)boosts.size(), facet_base = (uint32_t)facets.size();
+        for (vdev::PhraseMember m : o.phrase_members) {
+            m.part1 = part_map[m.part1], m.part2 = part_map[m.part2], m.list_part = part_map[m.list_part];
+            phrase_members.push_back(m);
+        }
+        for (vdev::IdsMember m : o.ids_members) {
+            m.part = part_map[m.part], m.list_part = part_map[m.list_part];
+            ids_members.push_back(m);
+        }
         facets.insert(facets.end(), o.facets.begin(), o.facets.end());
         facet_top.insert(facet_top.end(), o.facet_top.begin(), o.facet_top.end());
         facet_text_path.insert(facet_text_path.end(), o.facet_text_path.begin(), o.facet_text_path.end());
@@ -203,17 +233,34 @@ struct BatchPlan {
         max_k = std::max(max_k, o.max_k);
     }
 
+    // A part searched for ids only (filter trees, boost_term): its matched term ids, taken as text ids, resolve to
+    // anchors through text_id_to_anchor (search_field.rs:468-498).  Returns the list part that receives them.
+    uint32_t add_ids_part(const vhost::SearchPart& part) {
+        std::string path = part.path;
+        if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+        vdev::IdsMember m;
+        memset(&m, 0, sizeof m);
+        m.part = add_part(part);
+        m.identity = ix->host->is_anchor_identity_column(path) ? 1u : 0u;
+        if (!m.identity) {
+            auto it = ix->stores.find(path + ".text_id_to_anchor");
+            if (it == ix->stores.end()) ix->host->path_not_found(path + ".text_id_to_anchor");
+            m.text_id_to_anchor = it->second.view();
+        }
+        m.list_part = add_list_part();
+        ids_members.push_back(m);
+        return m.list_part;
+    }
+
     struct Node {  // emitted subtree
         std::string term;  // request.terms[0] the result carries (set_op.rs:122-124)
         int leaf = -1;     // leaf index when the subtree is a single search part
         bool empty = false;
     };
 
-    Node emit(const vhost::SearchRequest& r, std::vector<uint32_t>& leaves, std::vector<uint32_t>& code) {
+    Node emit(const vhost::SearchRequest& r, std::vector<uint32_t>& leaves, std::vector<uint32_t>& code, bool ids_only = false) {
         if (r.kind == vhost::SearchRequest::Search) {
-            size_t pos = r.part.path.rfind("[]");
-            (void)pos;
-            uint32_t part = add_part(r.part);
+            uint32_t part = ids_only ? add_ids_part(r.part) : add_part(r.part);
             Node n;
             n.term = r.part.terms[0];
             n.leaf = (int)leaves.size();
@@ -224,7 +271,7 @@ struct BatchPlan {
         }
         if (r.queries.empty()) throw Unsupported("empty or/and list");
         std::vector<Node> kids;
-        for (auto& q : r.queries) kids.push_back(emit(q, leaves, code));
+        for (auto& q : r.queries) kids.push_back(emit(q, leaves, code, ids_only));
         if (kids.size() == 1) return kids[0];  // passthrough (set_op.rs:93-96, :371-374)
         if (kids.size() > vdev::kMaxLeaves) throw Unsupported("more than 12 sub-queries in one or/and");
         Node out;
@@ -330,7 +377,6 @@ struct BatchPlan {
         rp.top = request.top.value_or(10);  // search.rs:146
         rp.skip = request.skip.value_or(0);
         if (!request.search_req) throw InvalidRequest("search_req is None, but is required in search");
-        if (request.phrase_boosts && !request.phrase_boosts->empty()) throw Unsupported("phrase_boosts are not on the accelerated path yet");
         if (request.text_locality) throw Unsupported("text_locality is not on the accelerated path yet");
         if (has_nested_boost(*request.search_req)) throw Unsupported("boosts inside the search tree are not on the accelerated path yet");
         if (rp.top + rp.skip > vdev::kMaxK) throw Unsupported("top + skip above 256 is outside the accelerated path");
@@ -340,14 +386,50 @@ struct BatchPlan {
         emit(root, leaves, code);
         bool extras = false;
         if (request.filter) {  // the filter tree is evaluated for presence only; hits outside it are dropped (set_op.rs:311-326)
-            emit(*request.filter, leaves, code);
+            emit(*request.filter, leaves, code, true);
             code.push_back(vdev::kOpFilter);
+            extras = true;
+        }
+        if (request.phrase_boosts && !request.phrase_boosts->empty()) {
+            // add_phrase_boost_plan_steps (execution_plan.rs:202-262) + sort_and_group_boosts_by_phrase_terms (plan_steps.rs:235-258):
+            // the entries with the same (term1, term2) texts form one group; a hit in the group's anchors is multiplied by 5.0
+            struct Entry {
+                std::string t1, t2;
+                uint32_t p1, p2;
+                vdev::PhraseView store;
+            };
+            std::vector<Entry> entries;
+            for (auto& pb : *request.phrase_boosts) {
+                if (pb.search1.path != pb.search2.path) throw InvalidRequest("phrase boost parts must be on the same path");
+                if (pb.search1.terms.empty() || pb.search2.terms.empty()) throw InvalidRequest("search part without terms");
+                std::string path = pb.search1.path;
+                if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+                if (!vfmt::ends_with(path, ".phrase_pair_to_anchor")) path += ".phrase_pair_to_anchor";
+                auto it = ix->phrases.find(path);
+                if (it == ix->phrases.end()) ix->host->path_not_found(path);
+                entries.push_back(Entry{pb.search1.terms[0], pb.search2.terms[0], add_part(pb.search1), add_part(pb.search2), it->second.view()});
+            }
+            std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return std::tie(a.t1, a.t2) < std::tie(b.t1, b.t2); });
+            for (size_t i = 0; i < entries.size();) {
+                const uint32_t list_part = add_list_part();
+                const uint32_t leaf = (uint32_t)leaves.size();
+                leaves.push_back(list_part);
+                size_t j = i;
+                for (; j < entries.size() && entries[j].t1 == entries[i].t1 && entries[j].t2 == entries[i].t2; ++j)
+                    phrase_members.push_back(vdev::PhraseMember{entries[j].p1, entries[j].p2, list_part, 0u, entries[j].store});
+                const float five = 5.0f;
+                uint32_t bits;
+                memcpy(&bits, &five, 4);
+                post.push_back(vdev::kPostMulIfPresent), post.push_back(leaf), post.push_back(bits);
+                i = j;
+            }
             extras = true;
         }
         if (request.boost_term)  // search.rs:176, boost.rs:89-195: hits that the part also finds are multiplied by its boost (default 2.0)
             for (auto& part : *request.boost_term) {
+                const uint32_t list_part = add_ids_part(part);
                 const uint32_t leaf = (uint32_t)leaves.size();
-                leaves.push_back(add_part(part));
+                leaves.push_back(list_part);
                 const float v = part.boost.value_or(2.0f);
                 uint32_t bits;
                 memcpy(&bits, &v, 4);
@@ -444,7 +526,7 @@ struct BatchPlan {
         QueryProgram qp;
         memset(&qp, 0, sizeof qp);
         // a failing request must not leave half-registered leaves behind
-        const size_t leaf_mark = leaf_part.size(), prog_mark = prog.size(), boost_mark = boosts.size(), facet_mark = facets.size();
+        const size_t leaf_mark = leaf_part.size(), prog_mark = prog.size(), boost_mark = boosts.size(), facet_mark = facets.size(), phrase_mark = phrase_members.size(), ids_mark = ids_members.size();
         try {
             if (parsed.status != 0) {
                 rp.status = parsed.status, rp.message = parsed.message;
@@ -467,6 +549,7 @@ struct BatchPlan {
         if (rp.status != 0) {
             leaf_part.resize(leaf_mark), prog.resize(prog_mark), boosts.resize(boost_mark);
             facets.resize(facet_mark), facet_top.resize(facet_mark), facet_text_path.resize(facet_mark);
+            phrase_members.resize(phrase_mark), ids_members.resize(ids_mark);
             rp.facets.clear(), rp.has_facets = false;
             memset(&qp, 0, sizeof qp);
         }
