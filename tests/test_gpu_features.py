@@ -130,3 +130,30 @@ def test_phrase_boosts(gpu, native_libs):  # tests/all/test_phrase.rs:39-99, tes
     compare(index2, oracle2, [
         {"search_req": {"or": {"queries": [S(t, "title") for t in ("greg", "tagebuch", "05")]}}, "phrase_boosts": [_pb("title", "greg", "tagebuch")]},
     ])
+
+
+def test_text_locality(test_all, gpu, native_libs):  # tests/all/tests.rs:1296-1313
+    index, oracle = test_all
+    b = compare(index, oracle, [
+        {"search_req": {"or": {"queries": [S("text", "meanings.ger[]"), S("localität", "meanings.ger[]")]}}, "text_locality": True},
+        {"search_req": {"or": {"queries": [S("text", "meanings.ger[]"), S("localität", "meanings.ger[]"), S("urge", "meanings.eng[]")]}}, "text_locality": True,
+         "boost": [{"path": "commonness", "boost_fun": "Log10", "param": 1}]},
+        {"search_req": {"and": {"queries": [S("alle", "meanings.ger[]"), S("meine", "meanings.ger[]"), S("words", "meanings.ger[]")]}}, "text_locality": True},
+        {"search_req": S("text", "meanings.ger[]"), "text_locality": True},
+    ])
+    first = b.result(0)["data"][0][0]
+    assert fx.TEST_ALL_DOCS[first]["meanings"]["ger"][0] == "text localität"
+    index2, oracle2 = _pair(gpu, fx.TEST_PHRASE_DOCS, fx.TEST_PHRASE_CONFIG)
+    compare(index2, oracle2, [
+        {"search_req": {"or": {"queries": [S(t, p) for p in ("title", "tags[]") for t in ("greg", "tagebuch", "05")]}}, "text_locality": True,
+         "phrase_boosts": [_pb("tags[]", "greg", "tagebuch")]},
+    ])
+
+
+def test_config3_shape(gpu, native_libs):  # BASELINE config 3: AND + phrase + text locality + facets on a synthetic corpus
+    params = dict(num_docs=30000, vocab=2500, seed=13, tags=40, text_locality=True, phrase=True)
+    index, oracle = _pair(gpu, synth=params)
+    reqs = helpers.synthetic_requests(num_queries=150, query_kind="and", levenshtein=1, query_seed=17, **params)
+    assert "phrase_boosts" in reqs[0] and "text_locality" in reqs[0] and "facets" in reqs[0]
+    b = compare(index, oracle, reqs)
+    assert sum(b.result(q)["num_hits"] for q in range(len(reqs))) > 0

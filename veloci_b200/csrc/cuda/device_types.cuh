@@ -199,6 +199,18 @@ struct IdsMember {  // hits_ids of a part resolved to anchors: text_id_to_anchor
     CsrView text_id_to_anchor;
 };
 
+// boost_text_locality (boost.rs:34-87) of one (request, field): the matched tokens of every query term -> text ids;
+// a text id reached c > 1 times boosts its anchors by 2 * c * c.
+static const uint32_t kTlMaxLists = 256;
+struct TlInstance {
+    uint32_t list_part;
+    uint32_t term_begin, n_terms;   // into the table of parts (one per distinct query term of the field)
+    uint32_t identity;              // anchor-identity column: text id == anchor
+    uint32_t request;
+    uint32_t pad[3];
+    CsrView tokens_to_text_id, text_id_to_anchor;
+};
+
 // ---- request programs (plan_creator, execution_plan.rs:132-534) ----
 enum ProgOp : uint32_t {
     kOpLeaf = 1,       // [op, leaf index]

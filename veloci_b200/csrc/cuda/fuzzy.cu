@@ -625,6 +625,95 @@ void launch_ids_to_anchor(cudaStream_t st, const IdsMember* members, uint32_t n_
     count_launch();
 }
 
+// Text locality.  The lists are the tokens_to_text_id rows of the matched tokens (sorted, unique).  A text id that is in
+// two lists is in a list other than the longest one, so the candidates are the elements of all lists but the longest;
+// each candidate is emitted from the first list that has it, with c = the number of lists that have it.
+__global__ void __launch_bounds__(256) text_locality_kernel(const TlInstance* __restrict__ insts, const uint32_t* __restrict__ term_parts, uint32_t* __restrict__ req_error, ListArgs a) {
+    __shared__ uint32_t s_begin[kTlMaxLists], s_len[kTlMaxLists], s_prefix[kTlMaxLists + 1];
+    __shared__ uint32_t s_n, s_terms, s_longest;
+    const TlInstance in = insts[blockIdx.x];
+    if (threadIdx.x == 0) {
+        uint32_t n = 0, terms = 0, longest = 0;
+        bool overflow = false;
+        for (uint32_t t = 0; t < in.n_terms && !overflow; ++t) {
+            const uint32_t part = term_parts[in.term_begin + t];
+            const uint32_t b = a.part_begin[part], cnt = a.part_begin[part + 1] - b;
+            if (cnt) ++terms;  // a term without matches is not in term_id_hits_in_field (search_field.rs:379-383)
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const uint32_t id = a.g_term[b + k];
+                if (id >= in.tokens_to_text_id.n_ids) continue;
+                const uint32_t o = in.tokens_to_text_id.off[id], len = in.tokens_to_text_id.off[id + 1] - o;
+                if (!len) continue;
+                if (n == kTlMaxLists) {
+                    overflow = true;
+                    break;
+                }
+                s_begin[n] = o, s_len[n] = len;
+                if (n == 0 || len > s_len[longest]) longest = n;
+                ++n;
+            }
+        }
+        if (overflow) {
+            if (blockIdx.y == 0) req_error[in.request] = 1;
+            n = 0;
+        }
+        // prefix of the candidate counts (the longest list contributes none)
+        uint32_t acc = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            s_prefix[i] = acc;
+            if (i != longest) acc += s_len[i];
+        }
+        s_prefix[n] = acc;
+        s_n = n, s_terms = terms, s_longest = longest;
+    }
+    __syncthreads();
+    const uint32_t n = s_n, longest = s_longest;
+    if (s_terms <= 1 || n <= 1) return;  // boost.rs:36-38
+    const uint32_t* val = in.tokens_to_text_id.val;
+    const uint32_t total = s_prefix[n];
+    for (uint32_t x = blockIdx.y * blockDim.x + threadIdx.x; x < total; x += gridDim.y * blockDim.x) {
+        uint32_t lo = 0, hi = n;  // list of candidate x: last i with prefix[i] <= x (skipping the longest, whose range is empty)
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_prefix[mid] <= x) lo = mid;
+            else hi = mid;
+        }
+        uint32_t i = lo;
+        if (i == longest) continue;  // cannot happen: its range is empty and a later list starts at the same prefix
+        const uint32_t e = val[s_begin[i] + (x - s_prefix[i])];
+        uint32_t c = 1;
+        bool first = true;
+        for (uint32_t j = 0; j < n && first; ++j) {
+            if (j == i) continue;
+            const uint32_t* l = val + s_begin[j];
+            uint32_t a0 = 0, a1 = s_len[j];
+            while (a0 < a1) {
+                const uint32_t mid = (a0 + a1) >> 1;
+                if (l[mid] < e) a0 = mid + 1;
+                else a1 = mid;
+            }
+            if (a0 < s_len[j] && l[a0] == e) {
+                if (j < i && j != longest) first = false;  // an earlier candidate list emits it
+                ++c;
+            }
+        }
+        if (!first || c <= 1) continue;
+        const float boost = 2.0f * (float)c * (float)c;
+        const uint32_t key = ~vbit::score_key(boost);  // the leaf keeps the maximum key = the minimum boost (boost.rs:23-28)
+        if (in.identity) {
+            list_emit(a, in.list_part, e, key);
+        } else if (e < in.text_id_to_anchor.n_ids) {
+            for (uint32_t k = in.text_id_to_anchor.off[e]; k < in.text_id_to_anchor.off[e + 1]; ++k) list_emit(a, in.list_part, in.text_id_to_anchor.val[k], key);
+        }
+    }
+}
+
+void launch_text_locality(cudaStream_t st, const TlInstance* inst, uint32_t n_inst, const uint32_t* term_parts, uint32_t* req_error, const ListArgs& a) {
+    if (!n_inst) return;
+    text_locality_kernel<<<dim3(n_inst, 16), 256, 0, st>>>(inst, term_parts, req_error, a);
+    count_launch();
+}
+
 void launch_phrase_pairs(cudaStream_t st, const PhraseMember* members, uint32_t n_members, const ListArgs& a) {
     if (!n_members) return;
     phrase_pairs_kernel<<<n_members, 128, 0, st>>>(members, a);

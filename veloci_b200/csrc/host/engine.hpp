@@ -81,6 +81,9 @@ struct Batch {
     // device: list producers
     DevBuf<PhraseMember> d_phrase_members;
     DevBuf<IdsMember> d_ids_members;
+    DevBuf<TlInstance> d_tl_instances;
+    DevBuf<uint32_t> d_tl_term_parts, d_req_error;
+    std::vector<uint32_t> h_req_error;
     // device: facets
     DevBuf<FacetStep> d_facets;
     DevBuf<uint32_t> d_facet_top, d_facet_hist, d_facet_ids, d_facet_counts, d_facet_n;
@@ -291,6 +294,11 @@ struct Batch {
         d_prog.upload(plan.prog);
         d_programs.upload(plan.programs);
         d_boosts.upload(plan.boosts);
+        d_tl_instances.upload(plan.tl_instances);
+        d_tl_term_parts.upload(plan.tl_term_parts);
+        d_req_error.alloc(n + 1);
+        VDEV_CUDA(cudaMemset(d_req_error.p, 0, d_req_error.bytes()));
+        h2d_bytes += plan.tl_instances.size() * sizeof(TlInstance) + plan.tl_term_parts.size() * 4;
         d_ids_members.upload(plan.ids_members);
         h2d_bytes += plan.ids_members.size() * sizeof(IdsMember);
         d_phrase_members.upload(plan.phrase_members);
@@ -384,6 +392,7 @@ struct Batch {
     void run_list_producers(const ListArgs& la) {
         launch_phrase_pairs(stream, d_phrase_members.p, (uint32_t)plan.phrase_members.size(), la);
         launch_ids_to_anchor(stream, d_ids_members.p, (uint32_t)plan.ids_members.size(), la);
+        launch_text_locality(stream, d_tl_instances.p, (uint32_t)plan.tl_instances.size(), d_tl_term_parts.p, d_req_error.p, la);
     }
 
     template <class T>
@@ -654,6 +663,16 @@ struct Batch {
             d2h_bytes += h_keys.size() * 8 + h_hits.size() * 8 + sizeof stats;
             stat_union = 0;
             for (uint64_t h : h_hits) stat_union += h;
+        }
+        if (!plan.tl_instances.empty()) {  // requests the device could not finish (text locality over too many matched tokens)
+            h_req_error.resize(n);
+            VDEV_CUDA(cudaMemcpy(h_req_error.data(), d_req_error.p, n * 4, cudaMemcpyDeviceToHost));
+            d2h_bytes += n * 4;
+            for (uint32_t q = 0; q < n; ++q)
+                if (h_req_error[q] && plan.requests[q].status == 0) {
+                    plan.requests[q].status = 8;
+                    plan.requests[q].message = "text_locality over more than 256 matched tokens in one field is outside the accelerated path";
+                }
         }
         if (n_facets) {
             h_facet_ids.resize((size_t)n_facets * facet_stride), h_facet_counts.resize((size_t)n_facets * facet_stride), h_facet_n.resize(n_facets);

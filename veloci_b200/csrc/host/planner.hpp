@@ -97,6 +97,13 @@ struct BatchPlan {
     std::vector<BoostStep> boosts;
     std::vector<vdev::PhraseMember> phrase_members;
     std::vector<vdev::IdsMember> ids_members;
+    std::vector<vdev::TlInstance> tl_instances;
+    std::vector<uint32_t> tl_term_parts;
+    struct TlTerm {  // a search part of the request tree, for term_id_hits_in_field (search_field.rs:379-383)
+        std::string path, term;
+        uint32_t part;
+    };
+    std::vector<TlTerm> tl_seen;  // of the request being planned
     std::vector<vdev::FacetStep> facets;   // hist pointers are set by the engine
     std::vector<uint32_t> facet_top;       // groups wanted per facet
     std::vector<std::string> facet_text_path;  // dictionary the value ids of the facet belong to
@@ -212,6 +219,12 @@ struct BatchPlan {
             m.part1 = part_map[m.part1], m.part2 = part_map[m.part2], m.list_part = part_map[m.list_part];
             phrase_members.push_back(m);
         }
+        const uint32_t tl_term_base = (uint32_t)tl_term_parts.size(), request_base = (uint32_t)requests.size();
+        for (uint32_t p : o.tl_term_parts) tl_term_parts.push_back(part_map[p]);
+        for (vdev::TlInstance t : o.tl_instances) {
+            t.list_part = part_map[t.list_part], t.term_begin += tl_term_base, t.request += request_base;
+            tl_instances.push_back(t);
+        }
         for (vdev::IdsMember m : o.ids_members) {
             m.part = part_map[m.part], m.list_part = part_map[m.list_part];
             ids_members.push_back(m);
@@ -261,6 +274,11 @@ struct BatchPlan {
     Node emit(const vhost::SearchRequest& r, std::vector<uint32_t>& leaves, std::vector<uint32_t>& code, bool ids_only = false) {
         if (r.kind == vhost::SearchRequest::Search) {
             uint32_t part = ids_only ? add_ids_part(r.part) : add_part(r.part);
+            if (!ids_only) {
+                std::string path = r.part.path;
+                if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+                tl_seen.push_back(TlTerm{path, r.part.terms[0], part});
+            }
             Node n;
             n.term = r.part.terms[0];
             n.leaf = (int)leaves.size();
@@ -377,13 +395,14 @@ struct BatchPlan {
         rp.top = request.top.value_or(10);  // search.rs:146
         rp.skip = request.skip.value_or(0);
         if (!request.search_req) throw InvalidRequest("search_req is None, but is required in search");
-        if (request.text_locality) throw Unsupported("text_locality is not on the accelerated path yet");
         if (has_nested_boost(*request.search_req)) throw Unsupported("boosts inside the search tree are not on the accelerated path yet");
         if (rp.top + rp.skip > vdev::kMaxK) throw Unsupported("top + skip above 256 is outside the accelerated path");
 
         std::vector<uint32_t> leaves, code, post;
         const vhost::SearchRequest& root = *request.search_req;
+        tl_seen.clear();
         emit(root, leaves, code);
+        const std::vector<TlTerm> tree_terms = tl_seen;
         bool extras = false;
         if (request.filter) {  // the filter tree is evaluated for presence only; hits outside it are dropped (set_op.rs:311-326)
             emit(*request.filter, leaves, code, true);
@@ -436,6 +455,38 @@ struct BatchPlan {
                 post.push_back(vdev::kPostMulIfPresent), post.push_back(leaf), post.push_back(bits);
                 extras = true;
             }
+        if (request.text_locality) {
+            // boost_text_locality_all (boost.rs:11-32): per field with at least two query terms, one list; the smallest boost wins
+            std::map<std::string, std::map<std::string, uint32_t>> by_path;  // later parts replace earlier ones (set_op.rs:29-47)
+            for (auto& t : tree_terms) by_path[t.path][t.term] = t.part;
+            uint32_t list_part = vdev::kNoValue;
+            for (auto& kv : by_path) {
+                if (kv.second.size() <= 1) continue;
+                vdev::TlInstance t;
+                memset(&t, 0, sizeof t);
+                auto t2t = ix->stores.find(kv.first + ".tokens_to_text_id");
+                if (t2t == ix->stores.end()) ix->host->path_not_found(kv.first + ".tokens_to_text_id");
+                t.tokens_to_text_id = t2t->second.view();
+                t.identity = ix->host->is_anchor_identity_column(kv.first) ? 1u : 0u;
+                if (!t.identity) {
+                    auto t2a = ix->stores.find(kv.first + ".text_id_to_anchor");
+                    if (t2a == ix->stores.end()) ix->host->path_not_found(kv.first + ".text_id_to_anchor");
+                    t.text_id_to_anchor = t2a->second.view();
+                }
+                if (list_part == vdev::kNoValue) list_part = add_list_part();
+                t.list_part = list_part;
+                t.term_begin = (uint32_t)tl_term_parts.size(), t.n_terms = (uint32_t)kv.second.size();
+                t.request = (uint32_t)requests.size();
+                for (auto& tp : kv.second) tl_term_parts.push_back(tp.second);
+                tl_instances.push_back(t);
+            }
+            if (list_part != vdev::kNoValue) {
+                const uint32_t leaf = (uint32_t)leaves.size();
+                leaves.push_back(list_part);
+                post.push_back(vdev::kPostMulValue), post.push_back(leaf);
+                extras = true;
+            }
+        }
         if (leaves.size() > vdev::kMaxLeaves) throw Unsupported("more than 12 search parts in one request");
         if (request.facets && !request.facets->empty()) {
             if (ix->n_shards > 1) throw Unsupported("facets on a sharded index are not on the accelerated path yet");
@@ -526,7 +577,8 @@ struct BatchPlan {
         QueryProgram qp;
         memset(&qp, 0, sizeof qp);
         // a failing request must not leave half-registered leaves behind
-        const size_t leaf_mark = leaf_part.size(), prog_mark = prog.size(), boost_mark = boosts.size(), facet_mark = facets.size(), phrase_mark = phrase_members.size(), ids_mark = ids_members.size();
+        const size_t leaf_mark = leaf_part.size(), prog_mark = prog.size(), boost_mark = boosts.size(), facet_mark = facets.size(), phrase_mark = phrase_members.size(), ids_mark = ids_members.size(), tl_mark = tl_instances.size(),
+                     tl_term_mark = tl_term_parts.size();
         try {
             if (parsed.status != 0) {
                 rp.status = parsed.status, rp.message = parsed.message;
@@ -549,7 +601,7 @@ struct BatchPlan {
         if (rp.status != 0) {
             leaf_part.resize(leaf_mark), prog.resize(prog_mark), boosts.resize(boost_mark);
             facets.resize(facet_mark), facet_top.resize(facet_mark), facet_text_path.resize(facet_mark);
-            phrase_members.resize(phrase_mark), ids_members.resize(ids_mark);
+            phrase_members.resize(phrase_mark), ids_members.resize(ids_mark), tl_instances.resize(tl_mark), tl_term_parts.resize(tl_term_mark);
             rp.facets.clear(), rp.has_facets = false;
             memset(&qp, 0, sizeof qp);
         }
