@@ -157,3 +157,18 @@ def test_config3_shape(gpu, native_libs):  # BASELINE config 3: AND + phrase + t
     assert "phrase_boosts" in reqs[0] and "text_locality" in reqs[0] and "facets" in reqs[0]
     b = compare(index, oracle, reqs)
     assert sum(b.result(q)["num_hits"] for q in range(len(reqs))) > 0
+
+
+def test_one_to_n_boosts(test_all):  # tests/all/tests.rs:839-931 (BoostToAnchor + ApplyAnchorBoost)
+    index, oracle = test_all
+    compare(index, oracle, [
+        {"search_req": S("意慾", "kanji[].text"), "boost": [{"path": "kanji[].commonness", "boost_fun": "Log10", "param": 1}]},
+        {"search_req": S("awesome", "field1[].text"),
+         "boost": [{"path": "commonness", "boost_fun": "Log10", "param": 1}, {"path": "field1[].rank", "expression": "10 / $SCORE", "skip_when_score": [0]}]},
+        {"search_req": {"or": {"queries": [
+            {"search": {"terms": ["awesome"], "path": "field1[].text", "options": {"boost": [{"path": "field1[].rank", "boost_fun": "Log10", "param": 1}]}}},
+            {"search": {"terms": ["urge"], "path": "meanings.eng[]", "options": {"boost": [{"path": "commonness", "boost_fun": "Log10", "param": 1}]}}},
+        ]}}},
+        {"search_req": {"or": {"queries": [S("awesome", "field1[].text"), S("意慾", "kanji[].text", levenshtein_distance=1)]}},
+         "boost": [{"path": "field1[].rank", "boost_fun": "Multiply"}, {"path": "kanji[].commonness", "boost_fun": "Add", "param": 2}, {"path": "commonness", "boost_fun": "Log2", "param": 2}]},
+    ])

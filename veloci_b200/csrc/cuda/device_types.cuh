@@ -199,6 +199,16 @@ struct IdsMember {  // hits_ids of a part resolved to anchors: text_id_to_anchor
     CsrView text_id_to_anchor;
 };
 
+// BoostToAnchor (plan_steps.rs:173-196): matched tokens -> text ids -> parent value ids -> (boost value, anchor)
+struct BoostListMember {
+    uint32_t part, list_part;
+    uint32_t tokenized;        // tokens resolve through tokens_to_text_id (a token without entry is its own text id)
+    uint32_t use_ids;          // untokenized field: the matched term ids are the text ids only when the part is also searched for ids
+    CsrView tokens_to_text_id, value_id_to_parent, value_id_to_anchor;
+    const uint32_t* column;    // boost values by value id
+    uint32_t column_n, pad;
+};
+
 // boost_text_locality (boost.rs:34-87) of one (request, field): the matched tokens of every query term -> text ids;
 // a text id reached c > 1 times boosts its anchors by 2 * c * c.
 static const uint32_t kTlMaxLists = 256;
@@ -217,6 +227,7 @@ enum ProgOp : uint32_t {
     kOpUnion = 2,      // [op, n children, n slots, slot of child 0 .. n-1]      set_op.rs:87-220
     kOpIntersect = 3,  // [op, n children, sum order: child index 0 .. n-1]      set_op.rs:368-446
     kOpFilter = 4,     // [op]: (search result, filter result) -> search result where the filter is present   set_op.rs:311-326
+    kOpLeafBoost = 5,  // [op, leaf, list leaf, boost step]: the leaf, boosted by the list's value for the anchor   plan_steps.rs:173-233 (BoostToAnchor + ApplyAnchorBoost)
 };
 
 // Steps that run on every hit after the request tree and the column boosts, in the reference's order

@@ -714,6 +714,41 @@ void launch_text_locality(cudaStream_t st, const TlInstance* inst, uint32_t n_in
     count_launch();
 }
 
+// One block per member: every matched token -> its text ids -> their parent value ids -> boost value and anchor.
+__global__ void __launch_bounds__(128) boost_to_anchor_kernel(const BoostListMember* __restrict__ members, ListArgs a) {
+    const BoostListMember m = members[blockIdx.x];
+    if (!m.tokenized && !m.use_ids) return;
+    const uint32_t b = a.part_begin[m.part], n = a.part_begin[m.part + 1] - b;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t token = a.g_term[b + i];
+        uint32_t t0 = 0, t1 = 1;  // text ids: the token's row, or the token itself
+        bool self = true;
+        if (m.tokenized && token < m.tokens_to_text_id.n_ids) {
+            const uint32_t o0 = m.tokens_to_text_id.off[token], o1 = m.tokens_to_text_id.off[token + 1];
+            if (o1 > o0) t0 = o0, t1 = o1, self = false;
+        }
+        for (uint32_t t = t0; t < t1; ++t) {
+            const uint32_t text = self ? token : m.tokens_to_text_id.val[t];
+            if (text >= m.value_id_to_parent.n_ids) continue;
+            for (uint32_t j = m.value_id_to_parent.off[text]; j < m.value_id_to_parent.off[text + 1]; ++j) {
+                const uint32_t value_id = m.value_id_to_parent.val[j];
+                if (value_id >= m.column_n || value_id >= m.value_id_to_anchor.n_ids) continue;
+                const uint32_t bits = m.column[value_id];
+                if (bits == kNoValue) continue;
+                const uint32_t o = m.value_id_to_anchor.off[value_id];
+                if (m.value_id_to_anchor.off[value_id + 1] == o) continue;
+                list_emit(a, m.list_part, m.value_id_to_anchor.val[o], vbit::score_key(__uint_as_float(bits)));
+            }
+        }
+    }
+}
+
+void launch_boost_to_anchor(cudaStream_t st, const BoostListMember* members, uint32_t n_members, const ListArgs& a) {
+    if (!n_members) return;
+    boost_to_anchor_kernel<<<n_members, 128, 0, st>>>(members, a);
+    count_launch();
+}
+
 void launch_phrase_pairs(cudaStream_t st, const PhraseMember* members, uint32_t n_members, const ListArgs& a) {
     if (!n_members) return;
     phrase_pairs_kernel<<<n_members, 128, 0, st>>>(members, a);
@@ -741,6 +776,7 @@ __global__ void finalize_programs_kernel(const QueryProgram* __restrict__ querie
         if (op == kOpLeaf) pc += 2;
         else if (op == kOpUnion) pc += 3 + code[pc + 1];
         else if (op == kOpFilter) pc += 1;
+        else if (op == kOpLeafBoost) pc += 4;
         else {
             const uint32_t cnt = code[pc + 1];
             uint32_t* order = code + pc + 2;

@@ -103,6 +103,8 @@ void launch_phrase_pairs(cudaStream_t st, const PhraseMember* members, uint32_t 
 // boost_text_locality (boost.rs:34-87): gridDim = (instances, chunks).  Requests with more than kTlMaxLists matched
 // tokens in one field get req_error[request] = 1 (reported as VGPU_ERR_UNSUPPORTED).
 void launch_text_locality(cudaStream_t st, const TlInstance* inst, uint32_t n_inst, const uint32_t* term_parts, uint32_t* req_error, const ListArgs& a);
+// BoostToAnchor (plan_steps.rs:173-196): one block per member
+void launch_boost_to_anchor(cudaStream_t st, const BoostListMember* members, uint32_t n_members, const ListArgs& a);
 // the ids half of resolve_token_to_anchor (search_field.rs:468-498): one block per member
 void launch_ids_to_anchor(cudaStream_t st, const IdsMember* members, uint32_t n_members, const ListArgs& a);
 

@@ -192,7 +192,7 @@ __device__ __forceinline__ float apply_boost_step(const BoostStep& b, float scor
 }
 
 // Generic request tree, postfix.  Returns presence; score in `out`.
-__device__ bool eval_program(const uint32_t* __restrict__ prog, uint32_t len, const uint32_t* arr, uint32_t tile, uint32_t idx, float& out) {
+__device__ bool eval_program(const uint32_t* __restrict__ prog, uint32_t len, const uint32_t* arr, uint32_t tile, uint32_t idx, const BoostStep* __restrict__ boosts, float& out) {
     float sc[kMaxLeaves];
     bool pr[kMaxLeaves];
     int sp = 0;
@@ -226,6 +226,14 @@ __device__ bool eval_program(const uint32_t* __restrict__ prog, uint32_t len, co
             sc[sp] = sum * nd * nd;
             ++sp;
             pc += 3 + n;
+        } else if (op == kOpLeafBoost) {
+            const uint32_t key = arr[prog[pc + 1] * tile + idx];
+            pr[sp] = key != 0;
+            sc[sp] = key ? vbit::key_score(key) : 0.0f;
+            const uint32_t bkey = arr[prog[pc + 2] * tile + idx];
+            if (key && bkey) sc[sp] = apply_boost_step(boosts[prog[pc + 3]], sc[sp], vbit::key_score(bkey));
+            ++sp;
+            pc += 4;
         } else if (op == kOpFilter) {
             sp -= 1;
             pr[sp - 1] = pr[sp - 1] && pr[sp];
@@ -367,7 +375,7 @@ __device__ __forceinline__ uint32_t eval_idx(const TileArgs& a, const ItemCtx& c
         }
         score = L == 1 ? vbit::key_score(arr[idx]) : sum * nd * nd;
     } else {
-        present = eval_program(a.prog + c.qp.prog_begin, c.qp.prog_len, arr, c.tile, idx, score);
+        present = eval_program(a.prog + c.qp.prog_begin, c.qp.prog_len, arr, c.tile, idx, a.boosts + c.qp.boost_begin, score);
     }
     uint32_t keep = 0;
     if (present) keep = finish_anchor(a, c, c.tile_base + idx, score, s_nsurv, s_list, arr + idx, c.tile);

@@ -81,6 +81,7 @@ struct Batch {
     // device: list producers
     DevBuf<PhraseMember> d_phrase_members;
     DevBuf<IdsMember> d_ids_members;
+    DevBuf<BoostListMember> d_boost_members;
     DevBuf<TlInstance> d_tl_instances;
     DevBuf<uint32_t> d_tl_term_parts, d_req_error;
     std::vector<uint32_t> h_req_error;
@@ -294,6 +295,8 @@ struct Batch {
         d_prog.upload(plan.prog);
         d_programs.upload(plan.programs);
         d_boosts.upload(plan.boosts);
+        d_boost_members.upload(plan.boost_members);
+        h2d_bytes += plan.boost_members.size() * sizeof(BoostListMember);
         d_tl_instances.upload(plan.tl_instances);
         d_tl_term_parts.upload(plan.tl_term_parts);
         d_req_error.alloc(n + 1);
@@ -392,6 +395,7 @@ struct Batch {
     void run_list_producers(const ListArgs& la) {
         launch_phrase_pairs(stream, d_phrase_members.p, (uint32_t)plan.phrase_members.size(), la);
         launch_ids_to_anchor(stream, d_ids_members.p, (uint32_t)plan.ids_members.size(), la);
+        launch_boost_to_anchor(stream, d_boost_members.p, (uint32_t)plan.boost_members.size(), la);
         launch_text_locality(stream, d_tl_instances.p, (uint32_t)plan.tl_instances.size(), d_tl_term_parts.p, d_req_error.p, la);
     }
 

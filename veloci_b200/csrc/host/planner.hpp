@@ -97,6 +97,7 @@ struct BatchPlan {
     std::vector<BoostStep> boosts;
     std::vector<vdev::PhraseMember> phrase_members;
     std::vector<vdev::IdsMember> ids_members;
+    std::vector<vdev::BoostListMember> boost_members;
     std::vector<vdev::TlInstance> tl_instances;
     std::vector<uint32_t> tl_term_parts;
     struct TlTerm {  // a search part of the request tree, for term_id_hits_in_field (search_field.rs:379-383)
@@ -229,6 +230,10 @@ struct BatchPlan {
             m.part = part_map[m.part], m.list_part = part_map[m.list_part];
             ids_members.push_back(m);
         }
+        for (vdev::BoostListMember m : o.boost_members) {
+            m.part = part_map[m.part], m.list_part = part_map[m.list_part];
+            boost_members.push_back(m);
+        }
         facets.insert(facets.end(), o.facets.begin(), o.facets.end());
         facet_top.insert(facet_top.end(), o.facet_top.begin(), o.facet_top.end());
         facet_text_path.insert(facet_text_path.end(), o.facet_text_path.begin(), o.facet_text_path.end());
@@ -271,25 +276,79 @@ struct BatchPlan {
         bool empty = false;
     };
 
-    Node emit(const vhost::SearchRequest& r, std::vector<uint32_t>& leaves, std::vector<uint32_t>& code, bool ids_only = false) {
+    // state of the request being planned
+    std::vector<BoostStep>* cur_steps = nullptr;       // its boost steps (1:n boosts are appended here)
+    std::vector<std::string> cur_ids_keys;             // parts that are also searched for ids (filter, phrase boosts)
+    bool cur_leaf_boost = false;
+
+    Node emit(const vhost::SearchRequest& r, std::vector<uint32_t>& leaves, std::vector<uint32_t>& code, bool ids_only = false,
+              const std::vector<vhost::BoostPart>& boosts = std::vector<vhost::BoostPart>()) {
         if (r.kind == vhost::SearchRequest::Search) {
             uint32_t part = ids_only ? add_ids_part(r.part) : add_part(r.part);
-            if (!ids_only) {
-                std::string path = r.part.path;
-                if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
-                tl_seen.push_back(TlTerm{path, r.part.terms[0], part});
-            }
             Node n;
             n.term = r.part.terms[0];
             n.leaf = (int)leaves.size();
             leaves.push_back(part);
+            if (!ids_only) {
+                std::string path = r.part.path;
+                if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+                tl_seen.push_back(TlTerm{path, r.part.terms[0], part});
+                // a boost on the same 1:n level as the part (execution_plan.rs:422-436): BoostToAnchor + ApplyAnchorBoost
+                const size_t pos = r.part.path.rfind("[]");
+                if (pos != std::string::npos) {
+                    const std::string end_obj = r.part.path.substr(0, pos);
+                    const vhost::BoostPart* found = nullptr;
+                    for (auto& b : boosts) {
+                        const size_t bp = b.path.rfind("[]");
+                        if (bp == std::string::npos || b.path.substr(0, bp) != end_obj) continue;
+                        if (found) throw InvalidRequest("more than one boost on the same 1:n level");
+                        found = &b;
+                    }
+                    if (found) {
+                        vdev::BoostListMember m;
+                        memset(&m, 0, sizeof m);
+                        m.part = part;
+                        m.tokenized = ix->host->is_tokenized(path) ? 1u : 0u;
+                        m.use_ids = std::find(cur_ids_keys.begin(), cur_ids_keys.end(), r.part.key()) != cur_ids_keys.end() ? 1u : 0u;
+                        auto need = [&](const std::string& p) -> const vdev::CsrDev& {
+                            auto it = ix->stores.find(p);
+                            if (it == ix->stores.end()) ix->host->path_not_found(p);
+                            return it->second;
+                        };
+                        if (m.tokenized) m.tokens_to_text_id = need(path + ".tokens_to_text_id").view();
+                        m.value_id_to_parent = need(r.part.path + ".textindex.value_id_to_parent").view();
+                        auto col = ix->boosts.find(found->path + ".boost_valid_to_value");
+                        if (col == ix->boosts.end()) ix->host->path_not_found(found->path + ".boost_valid_to_value");
+                        m.column = col->second.bits.p, m.column_n = (uint32_t)col->second.n;
+                        m.value_id_to_anchor = need(found->path + ".value_id_to_anchor").view();
+                        m.list_part = add_list_part();
+                        boost_members.push_back(m);
+                        BoostStep step;
+                        memset(&step, 0, sizeof step);
+                        step.fun = (uint32_t)found->boost_fun;
+                        step.param = found->param.value_or(0.0f);
+                        if (found->expression) parse_expression(*found->expression, step);
+                        const uint32_t step_index = (uint32_t)cur_steps->size();
+                        cur_steps->push_back(step);
+                        const uint32_t list_leaf = (uint32_t)leaves.size();
+                        leaves.push_back(m.list_part);
+                        code.push_back(vdev::kOpLeafBoost), code.push_back((uint32_t)n.leaf), code.push_back(list_leaf), code.push_back(step_index);
+                        cur_leaf_boost = true;
+                        return n;
+                    }
+                }
+            }
             code.push_back(vdev::kOpLeaf);
             code.push_back((uint32_t)n.leaf);
             return n;
         }
         if (r.queries.empty()) throw Unsupported("empty or/and list");
         std::vector<Node> kids;
-        for (auto& q : r.queries) kids.push_back(emit(q, leaves, code, ids_only));
+        for (auto& q : r.queries) {
+            std::vector<vhost::BoostPart> b = boosts;  // merge_vec (execution_plan.rs:263-270)
+            if (q.get_boost()) b.insert(b.end(), q.get_boost()->begin(), q.get_boost()->end());
+            kids.push_back(emit(q, leaves, code, ids_only, b));
+        }
         if (kids.size() == 1) return kids[0];  // passthrough (set_op.rs:93-96, :371-374)
         if (kids.size() > vdev::kMaxLeaves) throw Unsupported("more than 12 sub-queries in one or/and");
         Node out;
@@ -384,6 +443,11 @@ struct BatchPlan {
         qp.fb_col = s.column, qp.fb_lev = s.levels, qp.fb_n = s.n, qp.fb_fun = s.fun, qp.fb_param = s.param, qp.fb_max_mult = s.max_mult;
     }
 
+    static void collect_keys(const vhost::SearchRequest& r, std::vector<std::string>& out) {
+        if (r.kind == vhost::SearchRequest::Search) out.push_back(r.part.key());
+        for (auto& q : r.queries) collect_keys(q, out);
+    }
+
     static bool has_nested_boost(const vhost::SearchRequest& r) {
         if (r.get_boost() && !r.get_boost()->empty()) return true;
         for (auto& q : r.queries)
@@ -395,15 +459,24 @@ struct BatchPlan {
         rp.top = request.top.value_or(10);  // search.rs:146
         rp.skip = request.skip.value_or(0);
         if (!request.search_req) throw InvalidRequest("search_req is None, but is required in search");
-        if (has_nested_boost(*request.search_req)) throw Unsupported("boosts inside the search tree are not on the accelerated path yet");
         if (rp.top + rp.skip > vdev::kMaxK) throw Unsupported("top + skip above 256 is outside the accelerated path");
 
         std::vector<uint32_t> leaves, code, post;
         const vhost::SearchRequest& root = *request.search_req;
         tl_seen.clear();
-        emit(root, leaves, code);
+        std::vector<BoostStep> steps;
+        cur_steps = &steps, cur_leaf_boost = false;
+        cur_ids_keys.clear();
+        if (request.phrase_boosts)
+            for (auto& pb : *request.phrase_boosts) cur_ids_keys.push_back(pb.search1.key()), cur_ids_keys.push_back(pb.search2.key());
+        if (request.filter) collect_keys(*request.filter, cur_ids_keys);
+        {
+            std::vector<vhost::BoostPart> top = request.boost.value_or(std::vector<vhost::BoostPart>());
+            if (root.get_boost()) top.insert(top.end(), root.get_boost()->begin(), root.get_boost()->end());
+            emit(root, leaves, code, false, top);
+        }
         const std::vector<TlTerm> tree_terms = tl_seen;
-        bool extras = false;
+        bool extras = cur_leaf_boost;
         if (request.filter) {  // the filter tree is evaluated for presence only; hits outside it are dropped (set_op.rs:311-326)
             emit(*request.filter, leaves, code, true);
             code.push_back(vdev::kOpFilter);
@@ -497,12 +570,9 @@ struct BatchPlan {
             extras = true;
         }
 
-        std::vector<BoostStep> steps;
         if (request.boost)
-            for (auto& b : *request.boost) {
-                if (b.path.find("[]") != std::string::npos) throw Unsupported("1:n boosts are not on the accelerated path yet");
-                steps.push_back(make_boost(b));
-            }
+            for (auto& b : *request.boost)  // anchor-level boosts run after the root (execution_plan.rs:175-189); 1:n boosts were matched to their parts above
+                if (b.path.find("[]") == std::string::npos) steps.push_back(make_boost(b));
 
         // flat `or` of search parts with pairwise distinct terms: leaves in slot (= sorted term) order, no program
         bool flat = false;
@@ -578,7 +648,7 @@ struct BatchPlan {
         memset(&qp, 0, sizeof qp);
         // a failing request must not leave half-registered leaves behind
         const size_t leaf_mark = leaf_part.size(), prog_mark = prog.size(), boost_mark = boosts.size(), facet_mark = facets.size(), phrase_mark = phrase_members.size(), ids_mark = ids_members.size(), tl_mark = tl_instances.size(),
-                     tl_term_mark = tl_term_parts.size();
+                     tl_term_mark = tl_term_parts.size(), bm_mark = boost_members.size();
         try {
             if (parsed.status != 0) {
                 rp.status = parsed.status, rp.message = parsed.message;
@@ -601,7 +671,7 @@ struct BatchPlan {
         if (rp.status != 0) {
             leaf_part.resize(leaf_mark), prog.resize(prog_mark), boosts.resize(boost_mark);
             facets.resize(facet_mark), facet_top.resize(facet_mark), facet_text_path.resize(facet_mark);
-            phrase_members.resize(phrase_mark), ids_members.resize(ids_mark), tl_instances.resize(tl_mark), tl_term_parts.resize(tl_term_mark);
+            phrase_members.resize(phrase_mark), ids_members.resize(ids_mark), tl_instances.resize(tl_mark), tl_term_parts.resize(tl_term_mark), boost_members.resize(bm_mark);
             rp.facets.clear(), rp.has_facets = false;
             memset(&qp, 0, sizeof qp);
         }
