@@ -263,3 +263,37 @@ def test_deletion_index_equals_dictionary_scan(gpu, native_libs, monkeypatch):
     assert (probe["num_hits"] == scan["num_hits"]).all()
     assert (probe["ids"] == scan["ids"]).all()
     assert (probe["scores"].view(np.uint32) == scan["scores"].view(np.uint32)).all()
+
+
+class _DevArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def test_sharded_index_equals_unsharded(gpu, native_libs):
+    """Two anchor-range shards (both on this device), local top-k rows gathered and merged by
+    merge_heaps_kernel: identical to the unsharded index."""
+    import torch
+
+    d = tempfile.mkdtemp(prefix="vb200_gpu_shards_")
+    params = dict(num_docs=90000, vocab=6000, seed=31)
+    helpers.create_synthetic_index(d, **params)
+    reqs = helpers.synthetic_requests(num_queries=300, query_kind="or3", levenshtein=1, query_seed=8, **params)
+    reqs += helpers.synthetic_requests(num_queries=100, query_kind="and", levenshtein=1, query_seed=9, **params)
+    whole = gpu.Index(d).search_batch(reqs, k=10)
+    shards = [gpu.Index(d, shard_rank=r, n_shards=2) for r in range(2)]
+    batches = [s.prepare(reqs) for s in shards]
+    keys, hits = [], []
+    for b in batches:
+        b.execute()
+        kp, hp, stride = b.local_topk()
+        keys.append(torch.as_tensor(_DevArray(kp, len(reqs) * stride), device="cuda").clone())
+        hits.append(torch.as_tensor(_DevArray(hp, len(reqs)), device="cuda").clone())
+    g_keys, g_hits = torch.cat(keys), torch.cat(hits)
+    torch.cuda.synchronize()
+    for b in batches:  # every rank merges the same gathered buffers
+        b.merge_gathered(g_keys.data_ptr(), g_hits.data_ptr(), 2)
+        got = b.results_flat(10)
+        assert (got["num_hits"] == whole["num_hits"]).all()
+        assert (got["ids"] == whole["ids"]).all()
+        assert (got["scores"].view(np.uint32) == whole["scores"].view(np.uint32)).all()
