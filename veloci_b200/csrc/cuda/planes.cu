@@ -37,6 +37,7 @@ struct WarpScratch {
     FastDesc desc;                         // 160
     float mult[kBoostLevels];              // largest boost multiplier of an anchor below the level's threshold
     uint32_t ebits[256];                   // anchors of the tile that have entries
+    uint32_t mbits[256];                   // ... that have more than one entry
     uint32_t hkey[kHashSlots];             // entries: index in tile | leaf << 13 -> largest score key
     uint32_t hval[kHashSlots];
     uint16_t queue[kQueueCap];
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
         s_ctx.heap = a.heap, s_ctx.tau = a.tau, s_ctx.lock = a.lock, s_ctx.heap_stride = a.heap_stride;
         s_ctx.anchor_lo = a.anchor_lo, s_ctx.W = W, s_ctx.pad = 0, s_ctx.s_bits = s_bits, s_ctx.s_lev = s_lev;
     }
-    for (uint32_t i = lane; i < 256; i += 32) S.ebits[i] = 0;
+    for (uint32_t i = lane; i < 256; i += 32) S.ebits[i] = 0, S.mbits[i] = 0;
     for (uint32_t i = lane; i < kHashSlots; i += 32) S.hkey[i] = kHashEmpty, S.hval[i] = 0;
     if (lane == 0) S.mult_lev = nullptr, S.mult_fun = 0xFFFFFFFFu, S.mult_param = 0.0f;
     unsigned long long st_cand = 0, st_items = 0;  // lane 0
@@ -516,7 +517,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                         const uint32_t idx = cur.ent[r].x - tile_base, l = (cur.ent_leaf >> (2u * r)) & 3u;
                         const uint32_t bit = 1u << (idx & 31u);
                         if (!(atomicOr(&S.ebits[idx >> 5], bit) & bit)) own |= 1u << r;
-                        S.ent_idx[r * 32u + lane] = (uint16_t)idx;
+                        else atomicOr(&S.mbits[idx >> 5], bit);
+                        S.ent_idx[r * 32u + lane] = (uint16_t)(idx | (l << 13));
                         hash_insert(S, idx | (l << 13), cur.ent[r].y);
                     }
                 }
@@ -535,16 +537,20 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                 for (uint32_t r = 0; r < kEntRegs; ++r) {
                     if (r * 32u >= n_ent) break;
                     const bool mine_r = (own >> r) & 1u;
-                    const uint32_t idx = mine_r ? S.ent_idx[r * 32u + lane] : 0u;
+                    const uint32_t code = mine_r ? S.ent_idx[r * 32u + lane] : 0u;
+                    const uint32_t idx = code & 0x1FFFu, el = code >> 13;
                     bool cand = mine_r;
                     const float tau_score = S.tau_score;
                     if (mine_r && tau_score > 0.0f) {
                         const uint32_t w = idx >> 5, bit = 1u << (idx & 31u);
+                        const bool multi = (S.mbits[w] & bit) != 0;
                         float sum_ub = 0.0f;
                         uint32_t n = 0;
 #pragma unroll 1
                         for (uint32_t l = 0; l < L; ++l) {
-                            const uint32_t ev = hash_lookup(S, idx | (l << 13));
+                            // the anchor's only entry is this lane's; anchors with several entries look them up
+                            uint32_t ev = 0;
+                            if (multi || l == el) ev = hash_lookup(S, idx | (l << 13));
                             uint32_t pbits = 0;
                             const uint32_t np = D.n_planes[l];
 #pragma unroll 1
@@ -579,48 +585,81 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
             }
 
             // plane sweep: four 32-anchor words per lane and step
+            const int lev_top = S.lev[L - 1];
+            bool lower_dead = true;
+#pragma unroll
+            for (int i2 = 0; i2 < (int)kFastMaxLeaves - 1; ++i2)
+                if ((uint32_t)i2 + 1 < L && S.lev[i2] != -2) lower_dead = false;
 #pragma unroll 1
             for (uint32_t w4 = lane; w4 < (W >> 2); w4 += 32) {
-                uint4 ones = make_uint4(0u, 0u, 0u, 0u), twos = ones, fours = ones;
-                auto add_part = [&](uint32_t l, uint32_t np) {
-                    uint4 x = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll 1
-                    for (uint32_t j = 0; j < np; ++j) {
-                        const uint4 v = reinterpret_cast<const uint4*>(s_bits + S.pl_off[l * kPartPlaneSlots + j])[w4];
-                        x.x |= v.x, x.y |= v.y, x.z |= v.z, x.w |= v.w;
-                    }
-                    uint32_t cy, cy2;
-                    cy = ones.x & x.x, ones.x ^= x.x, cy2 = twos.x & cy, twos.x ^= cy, fours.x |= cy2;
-                    cy = ones.y & x.y, ones.y ^= x.y, cy2 = twos.y & cy, twos.y ^= cy, fours.y |= cy2;
-                    cy = ones.z & x.z, ones.z ^= x.z, cy2 = twos.z & cy, twos.z ^= cy, fours.z |= cy2;
-                    cy = ones.w & x.w, ones.w ^= x.w, cy2 = twos.w & cy, twos.w ^= cy, fours.w |= cy2;
-                };
-                add_part(0, np0);
-                if (L > 1) add_part(1, np1);
-                if (L > 2) add_part(2, np2);
-                if (L > 3) add_part(3, np3);
                 uint4 e = make_uint4(0u, 0u, 0u, 0u);
                 if (n_ent) e = reinterpret_cast<const uint4*>(S.ebits)[w4];
-                cnt += __popc(ones.x | twos.x | fours.x | e.x) + __popc(ones.y | twos.y | fours.y | e.y) + __popc(ones.z | twos.z | fours.z | e.z) + __popc(ones.w | twos.w | fours.w | e.w);
                 uint32_t cm[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                for (int i2 = 0; i2 < (int)kFastMaxLeaves; ++i2) {
-                    const int lv = S.lev[i2];
-                    if (lv == -2) continue;
-                    uint4 ex;  // anchors with exactly i2 + 1 parts present
-                    if (i2 == 0) ex = make_uint4(ones.x & ~twos.x & ~fours.x, ones.y & ~twos.y & ~fours.y, ones.z & ~twos.z & ~fours.z, ones.w & ~twos.w & ~fours.w);
-                    else if (i2 == 1) ex = make_uint4(twos.x & ~ones.x & ~fours.x, twos.y & ~ones.y & ~fours.y, twos.z & ~ones.z & ~fours.z, twos.w & ~ones.w & ~fours.w);
-                    else if (i2 == 2) ex = make_uint4(ones.x & twos.x, ones.y & twos.y, ones.z & twos.z, ones.w & twos.w);
-                    else ex = fours;
-                    if (lv >= 0) {
+                if (lower_dead && S.lev[L - 1] == lev_top) {
+                    // converged threshold: only anchors with every part present can still matter -> OR for the count, AND for the candidates
+                    uint4 any = make_uint4(0u, 0u, 0u, 0u), all = make_uint4(~0u, ~0u, ~0u, ~0u);
+                    auto add_part = [&](uint32_t l, uint32_t np) {
+                        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+                        for (uint32_t j = 0; j < np; ++j) {
+                            const uint4 v = reinterpret_cast<const uint4*>(s_bits + S.pl_off[l * kPartPlaneSlots + j])[w4];
+                            x.x |= v.x, x.y |= v.y, x.z |= v.z, x.w |= v.w;
+                        }
+                        any.x |= x.x, any.y |= x.y, any.z |= x.z, any.w |= x.w;
+                        all.x &= x.x, all.y &= x.y, all.z &= x.z, all.w &= x.w;
+                    };
+                    add_part(0, np0);
+                    if (L > 1) add_part(1, np1);
+                    if (L > 2) add_part(2, np2);
+                    if (L > 3) add_part(3, np3);
+                    cnt += __popc(any.x | e.x) + __popc(any.y | e.y) + __popc(any.z | e.z) + __popc(any.w | e.w);
+                    if (lev_top == -2) continue;
+                    if (lev_top >= 0) {
                         uint4 lw;
-                        if (lev_in_smem) lw = reinterpret_cast<const uint4*>(s_lev + (uint32_t)lv * W)[w4];
-                        else lw = __ldg(reinterpret_cast<const uint4*>(lev_glob + (size_t)lv * lev_words) + w4);
-                        ex.x &= lw.x, ex.y &= lw.y, ex.z &= lw.z, ex.w &= lw.w;
+                        if (lev_in_smem) lw = reinterpret_cast<const uint4*>(s_lev + (uint32_t)lev_top * W)[w4];
+                        else lw = __ldg(reinterpret_cast<const uint4*>(lev_glob + (size_t)lev_top * lev_words) + w4);
+                        all.x &= lw.x, all.y &= lw.y, all.z &= lw.z, all.w &= lw.w;
                     }
-                    cm[0] |= ex.x, cm[1] |= ex.y, cm[2] |= ex.z, cm[3] |= ex.w;
+                    cm[0] = all.x & ~e.x, cm[1] = all.y & ~e.y, cm[2] = all.z & ~e.z, cm[3] = all.w & ~e.w;
+                } else {
+                    uint4 ones = make_uint4(0u, 0u, 0u, 0u), twos = ones, fours = ones;
+                    auto add_part = [&](uint32_t l, uint32_t np) {
+                        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+                        for (uint32_t j = 0; j < np; ++j) {
+                            const uint4 v = reinterpret_cast<const uint4*>(s_bits + S.pl_off[l * kPartPlaneSlots + j])[w4];
+                            x.x |= v.x, x.y |= v.y, x.z |= v.z, x.w |= v.w;
+                        }
+                        uint32_t cy, cy2;
+                        cy = ones.x & x.x, ones.x ^= x.x, cy2 = twos.x & cy, twos.x ^= cy, fours.x |= cy2;
+                        cy = ones.y & x.y, ones.y ^= x.y, cy2 = twos.y & cy, twos.y ^= cy, fours.y |= cy2;
+                        cy = ones.z & x.z, ones.z ^= x.z, cy2 = twos.z & cy, twos.z ^= cy, fours.z |= cy2;
+                        cy = ones.w & x.w, ones.w ^= x.w, cy2 = twos.w & cy, twos.w ^= cy, fours.w |= cy2;
+                    };
+                    add_part(0, np0);
+                    if (L > 1) add_part(1, np1);
+                    if (L > 2) add_part(2, np2);
+                    if (L > 3) add_part(3, np3);
+                    cnt += __popc(ones.x | twos.x | fours.x | e.x) + __popc(ones.y | twos.y | fours.y | e.y) + __popc(ones.z | twos.z | fours.z | e.z) + __popc(ones.w | twos.w | fours.w | e.w);
+#pragma unroll
+                    for (int i2 = 0; i2 < (int)kFastMaxLeaves; ++i2) {
+                        const int lv = S.lev[i2];
+                        if (lv == -2) continue;
+                        uint4 ex;  // anchors with exactly i2 + 1 parts present
+                        if (i2 == 0) ex = make_uint4(ones.x & ~twos.x & ~fours.x, ones.y & ~twos.y & ~fours.y, ones.z & ~twos.z & ~fours.z, ones.w & ~twos.w & ~fours.w);
+                        else if (i2 == 1) ex = make_uint4(twos.x & ~ones.x & ~fours.x, twos.y & ~ones.y & ~fours.y, twos.z & ~ones.z & ~fours.z, twos.w & ~ones.w & ~fours.w);
+                        else if (i2 == 2) ex = make_uint4(ones.x & twos.x, ones.y & twos.y, ones.z & twos.z, ones.w & twos.w);
+                        else ex = fours;
+                        if (lv >= 0) {
+                            uint4 lw;
+                            if (lev_in_smem) lw = reinterpret_cast<const uint4*>(s_lev + (uint32_t)lv * W)[w4];
+                            else lw = __ldg(reinterpret_cast<const uint4*>(lev_glob + (size_t)lv * lev_words) + w4);
+                            ex.x &= lw.x, ex.y &= lw.y, ex.z &= lw.z, ex.w &= lw.w;
+                        }
+                        cm[0] |= ex.x, cm[1] |= ex.y, cm[2] |= ex.z, cm[3] |= ex.w;
+                    }
+                    cm[0] &= ~e.x, cm[1] &= ~e.y, cm[2] &= ~e.z, cm[3] &= ~e.w;  // anchors with entries were handled above
                 }
-                cm[0] &= ~e.x, cm[1] &= ~e.y, cm[2] &= ~e.z, cm[3] &= ~e.w;  // anchors with entries were handled above
                 if (__ballot_sync(0xFFFFFFFFu, (cm[0] | cm[1] | cm[2] | cm[3]) != 0) == 0) continue;
 #pragma unroll 1
                 for (int c4 = 0; c4 < 4; ++c4) {
@@ -644,7 +683,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                 __syncwarp();
 #pragma unroll
                 for (uint32_t r = 0; r < kEntRegs; ++r)
-                    if (r * 32u + lane < n_ent) S.ebits[(cur.ent[r].x - tile_base) >> 5] = 0;
+                    if (r * 32u + lane < n_ent) S.ebits[(cur.ent[r].x - tile_base) >> 5] = 0, S.mbits[(cur.ent[r].x - tile_base) >> 5] = 0;
                 for (uint32_t j = lane; j < kHashSlots / 4; j += 32) {
                     reinterpret_cast<uint4*>(S.hkey)[j] = make_uint4(kHashEmpty, kHashEmpty, kHashEmpty, kHashEmpty);
                     reinterpret_cast<uint4*>(S.hval)[j] = make_uint4(0u, 0u, 0u, 0u);
