@@ -27,8 +27,7 @@ namespace vdev {
 
 static const int kPlaneThreads = 512;
 static const int kPlaneWarps = kPlaneThreads / 32;
-static const uint32_t kQueueCap = 64;      // pending candidates of a warp (sparse mode)
-static const uint32_t kSurvCap = 32;
+static const uint32_t kQueueCap = 64;      // pending candidates of a warp: evaluated 32 at a time, one anchor per lane
 static const uint32_t kHashSlots = 256;    // >= 2 * kFastMaxEntries
 static const uint32_t kHashEmpty = 0xFFFFFFFFu;
 static const uint32_t kEntRegs = kFastMaxEntries / 32;  // entries a lane holds
@@ -40,15 +39,16 @@ struct WarpScratch {
     uint32_t mbits[256];                   // ... that have more than one entry
     uint32_t hkey[kHashSlots];             // entries: index in tile | leaf << 13 -> largest score key
     uint32_t hval[kHashSlots];
-    uint16_t queue[kQueueCap];
+    // candidates waiting for their exact evaluation; self-contained, so they outlive the item that produced them
+    uint32_t cand_q[kQueueCap];            // request
+    uint32_t cand_idx[kQueueCap];          // anchor index in the tile
+    float cand_e[kFastMaxLeaves][kQueueCap];  // per part: largest entry score of the anchor (0: none)
     uint16_t ent_idx[kFastMaxEntries];     // index in tile of entry r * 32 + lane
-    unsigned long long surv[kSurvCap];
-    unsigned long long merge[kFastMaxK + kSurvCap];
+    unsigned long long merge[kFastMaxK + 1];
     // state of the item being processed (warp-uniform)
     unsigned long long tau;                // the request's k-th best so far (0: fewer than k hits)
     float tau_score;                       // score of tau when pruning is possible, else 0
     int lev[kFastMaxLeaves];               // per count of present parts: -2 no candidates, -1 every anchor, else boost level
-    uint32_t ns;                           // survivors pending in surv[]
     uint32_t q, n_ent, tile_base_rel;
     uint32_t lev_in_smem;
     uint32_t pl_off[kFastMaxLeaves * kPartPlaneSlots];  // word offset of the request's planes in the staged tile
@@ -59,6 +59,7 @@ struct WarpScratch {
 };
 
 struct CtaContext {  // kernel-constant values the out-of-line helpers need
+    const FastDesc* fast;
     const uint16_t* score;
     size_t plane_stride;
     unsigned long long* heap;
@@ -230,10 +231,10 @@ __device__ __forceinline__ void compute_levels(WarpScratch& S, uint32_t lane) {
     __syncwarp();
 }
 
-// Merges the warp's pending survivors into the request's heap (sorted, k slots) under its lock and refreshes the threshold.
-__device__ __noinline__ void flush_survivors(const CtaContext* C, WarpScratch* Sp, uint32_t lane) {
+// Inserts one hit into the request's heap (sorted, k slots) under its lock, if it still beats the k-th best.
+__device__ __noinline__ void merge_one(const CtaContext* C, WarpScratch* Sp, uint32_t lane, uint32_t q, unsigned long long comp) {
     WarpScratch& S = *Sp;
-    const uint32_t q = S.q, k = S.desc.k, ns = S.ns;
+    const uint32_t k = C->fast[q].k;
     unsigned long long* heap = C->heap + (size_t)q * C->heap_stride;
     if (lane == 0) {
         while (atomicCAS(C->lock + q, 0u, 1u) != 0u) __nanosleep(32);
@@ -241,27 +242,23 @@ __device__ __noinline__ void flush_survivors(const CtaContext* C, WarpScratch* S
     }
     __syncwarp();
     for (uint32_t i = lane; i < k; i += 32) S.merge[i] = __ldcg(heap + i);
-    for (uint32_t i = lane; i < ns; i += 32) S.merge[k + i] = S.surv[i];
+    if (lane == 0) S.merge[k] = comp;
     __syncwarp();
-    const uint32_t n = k + ns;
-    for (uint32_t e = lane; e < n; e += 32) {
-        const unsigned long long key = S.merge[e];
-        if (key == 0) continue;
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < n; ++j) rank += S.merge[j] > key;
-        if (rank < k) __stcg(heap + rank, key);
-        if (rank == k - 1) __stcg(C->tau + q, key);
-    }
-    __threadfence();
-    __syncwarp();
-    const unsigned long long tau = __ldcg(C->tau + q);
-    __syncwarp();
-    if (lane == 0) {
-        atomicExch(C->lock + q, 0u);
-        S.tau = tau, S.ns = 0;
+    const uint32_t n = k + 1;
+    if (comp > S.merge[k - 1]) {
+        for (uint32_t e = lane; e < n; e += 32) {
+            const unsigned long long key = S.merge[e];
+            if (key == 0) continue;
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n; ++j) rank += S.merge[j] > key;
+            if (rank < k) __stcg(heap + rank, key);
+            if (rank == k - 1) __stcg(C->tau + q, key);
+        }
+        __threadfence();
     }
     __syncwarp();
-    compute_levels(S, lane);
+    if (lane == 0) atomicExch(C->lock + q, 0u);
+    __syncwarp();
 }
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t code) { return (code * 0x9E3779B1u) >> 24; }
@@ -287,27 +284,27 @@ __device__ __forceinline__ uint32_t hash_lookup(const WarpScratch& S, uint32_t c
     }
 }
 
-// Exact score of one anchor of the tile (index `idx`): its order key.
-__device__ __forceinline__ unsigned long long eval_candidate(const CtaContext& C, const WarpScratch& S, uint32_t idx) {
-    const FastDesc& D = S.desc;
+// Exact score of candidate `c` of the warp's list: its order key.  The plane bits of the tile are still staged.
+__device__ __forceinline__ unsigned long long eval_candidate(const CtaContext& C, const WarpScratch& S, uint32_t c, uint32_t q) {
+    const FastDesc& D = C.fast[q];
+    const uint32_t idx = S.cand_idx[c];
     const uint32_t w = idx >> 5, bit = 1u << (idx & 31u);
     const uint32_t rel = S.tile_base_rel + idx;
-    const bool in_e = S.n_ent != 0 && (S.ebits[w] & bit) != 0;
-    const uint32_t L = D.n_leaves;
+    const uint32_t L = D.n_leaves, W = C.W;
     float sum = 0.0f, nd = 0.0f, v0 = 0.0f;
 #pragma unroll 1
     for (uint32_t l = 0; l < L; ++l) {
-        float v = 0.0f;
+        float v = S.cand_e[l][c];
         const uint32_t np = D.n_planes[l];
 #pragma unroll 1
         for (uint32_t j = 0; j < np; ++j) {
-            if (C.s_bits[S.pl_off[l * kPartPlaneSlots + j] + w] & bit) {
-                const unsigned short h = __ldg(C.score + D.plane[l][j] * C.plane_stride + rel);
+            const uint32_t p = D.plane[l][j];
+            if (C.s_bits[p * W + w] & bit) {
+                const unsigned short h = __ldg(C.score + p * C.plane_stride + rel);
                 const float wgt = __fdiv_rn(__half2float(__ushort_as_half(h)), 100.0f);  // el.score.to_f32() / 100.0 (search_field.rs:426)
                 v = fmaxf(v, D.ts[l][j] * wgt);
             }
         }
-        if (in_e) v = fmaxf(v, __uint_as_float(hash_lookup(S, idx | (l << 13)) & 0x7FFFFFFFu));
         if (v >= 0.00001f) nd += 1.0f;
         sum += v;
         if (l == 0) v0 = v;
@@ -332,31 +329,37 @@ __device__ __forceinline__ unsigned long long eval_candidate(const CtaContext& C
     return ((unsigned long long)key << 32) | anchor;
 }
 
-// Evaluates queue[from, from + count) (count <= 32), one anchor per lane; survivors go to the pending list.
+// Evaluates candidates [from, from + count) (count <= 32) of the warp's list, one per lane, and merges the survivors.
 __device__ __noinline__ void drain(const CtaContext* C, WarpScratch* Sp, uint32_t lane, uint32_t from, uint32_t count) {
     WarpScratch& S = *Sp;
     unsigned long long comp = 0;
-    if (lane < count) comp = eval_candidate(*C, S, S.queue[from + lane]);
-    if (comp <= S.tau) comp = 0;
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, comp != 0);
-    if (!m) return;
-    if (S.ns + __popc(m) > kSurvCap) {
-        flush_survivors(C, Sp, lane);
-        if (comp <= S.tau) comp = 0;
+    uint32_t q = 0;
+    if (lane < count) {
+        q = S.cand_q[from + lane];
+        comp = eval_candidate(*C, S, from + lane, q);
+        if (comp <= __ldcg(C->tau + q)) comp = 0;
     }
-    const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, comp != 0);
-    const uint32_t ns = S.ns;
-    __syncwarp();
-    if (comp) S.surv[ns + __popc(m2 & ((1u << lane) - 1u))] = comp;
-    if (lane == 0) S.ns = ns + __popc(m2);
-    __syncwarp();
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, comp != 0);
+    while (m) {
+        const int src = __ffs((int)m) - 1;
+        m &= m - 1u;
+        const uint32_t sq = __shfl_sync(0xFFFFFFFFu, q, src);
+        const unsigned long long sc = __shfl_sync(0xFFFFFFFFu, comp, src);
+        merge_one(C, Sp, lane, sq, sc);
+    }
 }
 
-// Appends the flagged lanes' anchors to the warp's candidate queue and evaluates full groups of 32.
-__device__ __forceinline__ void enqueue(const CtaContext* C, WarpScratch& S, uint32_t lane, bool flag, uint32_t idx, uint32_t& qn, uint32_t& ncand) {
+// Appends the flagged lanes' anchors (with the entry scores of their parts) to the warp's candidate list and evaluates
+// a full group of 32 when there is one.
+__device__ __forceinline__ void enqueue(const CtaContext* C, WarpScratch& S, uint32_t lane, bool flag, uint32_t idx, float e0, float e1, float e2, float e3, uint32_t& qn,
+                                        uint32_t& ncand) {
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, flag);
     if (!m) return;
-    if (flag) S.queue[qn + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
+    if (flag) {
+        const uint32_t at = qn + __popc(m & ((1u << lane) - 1u));
+        S.cand_q[at] = S.q, S.cand_idx[at] = idx;
+        S.cand_e[0][at] = e0, S.cand_e[1][at] = e1, S.cand_e[2][at] = e2, S.cand_e[3][at] = e3;
+    }
     qn += __popc(m);
     ncand += __popc(m);
     __syncwarp();
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
     WarpScratch& S = reinterpret_cast<WarpScratch*>(s_lev + kBoostLevels * W)[warp];
     const CtaContext* C = &s_ctx;
     if (tid == 0) {
-        s_ctx.score = a.planes.score, s_ctx.plane_stride = (size_t)a.planes.words * 32u;
+        s_ctx.fast = a.fast, s_ctx.score = a.planes.score, s_ctx.plane_stride = (size_t)a.planes.words * 32u;
         s_ctx.heap = a.heap, s_ctx.tau = a.tau, s_ctx.lock = a.lock, s_ctx.heap_stride = a.heap_stride;
         s_ctx.anchor_lo = a.anchor_lo, s_ctx.W = W, s_ctx.pad = 0, s_ctx.s_bits = s_bits, s_ctx.s_lev = s_lev;
     }
@@ -479,6 +482,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
         ItemLoad cur, nxt;
         load_item(a, it_cur, lane, cur);
         nxt = cur;
+        uint32_t qn = 0;  // candidates of this warp waiting for their exact evaluation
 #pragma unroll 1
         for (uint32_t i = 0; i < n_mine; ++i) {
             const bool has_next = i + 1 < n_mine;
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
             const FastDesc& D = S.desc;
             const uint32_t L = D.n_leaves;
             if (lane == 0) {
-                S.q = it_cur.q, S.tau = cur.tau, S.ns = 0, S.n_ent = n_ent, S.tile_base_rel = tile_base_rel;
+                S.q = it_cur.q, S.tau = cur.tau, S.n_ent = n_ent, S.tile_base_rel = tile_base_rel;
                 S.lev_in_smem = D.fb_lev == a.lev_dev ? 1u : 0u;
             }
             if (lane < kFastMaxLeaves * kPartPlaneSlots) S.pl_off[lane] = (uint32_t)D.plane[lane / kPartPlaneSlots][lane % kPartPlaneSlots] * W;
@@ -528,8 +532,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
             const uint32_t np0 = D.n_planes[0], np1 = D.n_planes[1], np2 = D.n_planes[2], np3 = D.n_planes[3];
             const bool lev_in_smem = S.lev_in_smem != 0;
             const uint32_t* lev_glob = (D.flags & kFastBoost) ? D.fb_lev->bits + (size_t)t * W : nullptr;
-            const uint32_t lev_words = (D.flags & kFastBoost) ? D.fb_lev->words : 0u;
-            uint32_t cnt = 0, qn = 0, ncand = 0;
+            const uint32_t lev_words = lev_in_smem ? a.lev_hdr.words : (D.flags & kFastBoost) ? D.fb_lev->words : 0u;
+            uint32_t cnt = 0, ncand = 0;
 
             // anchors with entries: bounded one by one (entry scores are known exactly, plane parts by their bound)
             if (n_ent) {
@@ -541,7 +545,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                     const uint32_t idx = code & 0x1FFFu, el = code >> 13;
                     bool cand = mine_r;
                     const float tau_score = S.tau_score;
-                    if (mine_r && tau_score > 0.0f) {
+                    float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f, e3 = 0.0f;
+                    if (mine_r) {
                         const uint32_t w = idx >> 5, bit = 1u << (idx & 31u);
                         const bool multi = (S.mbits[w] & bit) != 0;
                         float sum_ub = 0.0f;
@@ -551,6 +556,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                             // the anchor's only entry is this lane's; anchors with several entries look them up
                             uint32_t ev = 0;
                             if (multi || l == el) ev = hash_lookup(S, idx | (l << 13));
+                            const float evf = ev ? __uint_as_float(ev & 0x7FFFFFFFu) : 0.0f;
+                            e0 = l == 0 ? evf : e0, e1 = l == 1 ? evf : e1, e2 = l == 2 ? evf : e2, e3 = l == 3 ? evf : e3;
                             uint32_t pbits = 0;
                             const uint32_t np = D.n_planes[l];
 #pragma unroll 1
@@ -558,29 +565,31 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                             const bool by_plane = (pbits & bit) != 0;
                             if (ev || by_plane) {
                                 n += 1;
-                                sum_ub += fmaxf(ev ? __uint_as_float(ev & 0x7FFFFFFFu) : 0.0f, by_plane ? D.ub[l] : 0.0f);
+                                sum_ub += fmaxf(evf, by_plane ? D.ub[l] : 0.0f);
                             }
                         }
                         const float B = (L == 1 ? sum_ub : sum_ub * (float)(n * n)) * 1.00001f;
-                        if (D.flags & kFastBoost) {
-                            if (B * D.fb_max_mult * 1.00001f < tau_score) cand = false;
-                            else {
-                                // deepest level whose outside cannot reach the threshold (mult[] ascends): the anchor must be inside it
-                                int lo = -1;
+                        if (tau_score > 0.0f) {
+                            if (D.flags & kFastBoost) {
+                                if (B * D.fb_max_mult * 1.00001f < tau_score) cand = false;
+                                else {
+                                    // deepest level whose outside cannot reach the threshold (mult[] ascends): the anchor must be inside it
+                                    int lo = -1;
 #pragma unroll
-                                for (int step = (int)kBoostLevels / 2; step > 0; step >>= 1)
-                                    if (B * S.mult[lo + step] < tau_score) lo += step;
-                                if (lo + 1 < (int)kBoostLevels && B * S.mult[lo + 1] < tau_score) lo += 1;
-                                if (lo >= 0) {
-                                    const uint32_t lw = lev_in_smem ? s_lev[(uint32_t)lo * W + w] : __ldg(lev_glob + (size_t)lo * lev_words + w);
-                                    cand = (lw & bit) != 0;
+                                    for (int step = (int)kBoostLevels / 2; step > 0; step >>= 1)
+                                        if (B * S.mult[lo + step] < tau_score) lo += step;
+                                    if (lo + 1 < (int)kBoostLevels && B * S.mult[lo + 1] < tau_score) lo += 1;
+                                    if (lo >= 0) {
+                                        const uint32_t lw = lev_in_smem ? s_lev[(uint32_t)lo * W + w] : __ldg(lev_glob + (size_t)lo * lev_words + w);
+                                        cand = (lw & bit) != 0;
+                                    }
                                 }
+                            } else if (B * 1.00001f < tau_score) {
+                                cand = false;
                             }
-                        } else if (B * 1.00001f < tau_score) {
-                            cand = false;
                         }
                     }
-                    enqueue(C, S, lane, cand, idx, qn, ncand);
+                    enqueue(C, S, lane, cand, idx, e0, e1, e2, e3, qn, ncand);
                 }
             }
 
@@ -668,12 +677,10 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                         const bool flag = m != 0;
                         const uint32_t idx = (w4 * 4u + (uint32_t)c4) * 32u + (uint32_t)__ffs((int)m) - 1u;
                         m &= m - 1u;
-                        enqueue(C, S, lane, flag, idx, qn, ncand);
+                        enqueue(C, S, lane, flag, idx, 0.0f, 0.0f, 0.0f, 0.0f, qn, ncand);
                     }
                 }
             }
-            if (qn) drain(C, &S, lane, 0, qn);
-            if (S.ns) flush_survivors(C, &S, lane);
             for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
             if (lane == 0) {
                 if (cnt) atomicAdd(a.num_hits + it_cur.q, (unsigned long long)cnt);
@@ -691,6 +698,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
             }
             cur = nxt, it_cur = it_nxt;
         }
+        if (qn) drain(C, &S, lane, 0, qn);  // the tile's bits are still staged
     }
     if (lane == 0 && st_items) {
         atomicAdd(a.stats + 0, st_items);
