@@ -198,36 +198,37 @@ __device__ __forceinline__ float boost_mult(uint32_t fun, float x) {
     }
 }
 
-// Which anchors still have to be evaluated, per number of parts present (see the file comment).
+// Which anchors still have to be evaluated, per number of parts present (see the file comment): lane n - 1 decides
+// for n parts present.
 __device__ __forceinline__ void compute_levels(WarpScratch& S, uint32_t lane) {
     const FastDesc& D = S.desc;
-    int lev[kFastMaxLeaves] = {-1, -1, -1, -1};
     float tau_score = 0.0f;
     if (S.tau != 0) {
         const float ts = vbit::key_score((uint32_t)(S.tau >> 32));
         if (ts > 1e-30f) tau_score = ts;
     }
-    if (tau_score > 0.0f) {
-        if (D.flags & kFastBoost) {
-            const float m = S.mult[lane & (kBoostLevels - 1)];
+    if (lane < kFastMaxLeaves) {
+        int lev = -1;
+        if (lane >= D.n_leaves) lev = -2;
+        else if (tau_score > 0.0f) {
+            const float B = D.bound[lane];
+            if (D.flags & kFastBoost) {
+                if (B * D.fb_max_mult * 1.00001f < tau_score) lev = -2;
+                else {  // deepest level whose outside cannot reach the threshold (mult[] ascends)
+                    int lo = -1;
 #pragma unroll
-            for (int i = 0; i < (int)kFastMaxLeaves; ++i) {
-                const float B = D.bound[i];
-                const uint32_t mask = __ballot_sync(0xFFFFFFFFu, lane < kBoostLevels && B * m < tau_score);
-                lev[i] = B * D.fb_max_mult * 1.00001f < tau_score ? -2 : mask ? 31 - __clz((int)mask) : -1;
+                    for (int step = (int)kBoostLevels / 2; step > 0; step >>= 1)
+                        if (B * S.mult[lo + step] < tau_score) lo += step;
+                    if (lo + 1 < (int)kBoostLevels && B * S.mult[lo + 1] < tau_score) lo += 1;
+                    lev = lo;
+                }
+            } else if (B * 1.00001f < tau_score) {
+                lev = -2;
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < (int)kFastMaxLeaves; ++i)
-                if (D.bound[i] * 1.00001f < tau_score) lev[i] = -2;
         }
+        S.lev[lane] = lev;
     }
-    __syncwarp();
-    if (lane == 0) {
-        S.tau_score = tau_score;
-#pragma unroll
-        for (int i = 0; i < (int)kFastMaxLeaves; ++i) S.lev[i] = (uint32_t)i < D.n_leaves ? lev[i] : -2;
-    }
+    if (lane == 0) S.tau_score = tau_score;
     __syncwarp();
 }
 
@@ -426,6 +427,7 @@ __device__ __forceinline__ uint32_t comp4(const uint4& v, int c) { return c == 0
 __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs a) {
     extern __shared__ __align__(16) uint32_t plane_smem[];
     __shared__ uint32_t s_unit;
+    __shared__ uint32_t s_pcount[kMaxPlanes];  // anchors of the staged tile per plane
     __shared__ CtaContext s_ctx;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t W = 1u << (a.tile_log2 - 5);
@@ -467,6 +469,13 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                     reinterpret_cast<uint4*>(s_lev)[i] = __ldg(reinterpret_cast<const uint4*>(a.lev_hdr.bits + (size_t)p * a.lev_hdr.words + (size_t)t * W) + j);
                 }
             }
+        }
+        __syncthreads();
+        for (uint32_t p = warp; p < a.planes.n_planes; p += kPlaneWarps) {  // per-plane hit count of the tile
+            uint32_t c = 0;
+            for (uint32_t w = lane; w < W; w += 32) c += __popc(s_bits[p * W + w]);
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+            if (lane == 0) s_pcount[p] = c;
         }
         __syncthreads();
         const uint32_t tile_base_rel = t << a.tile_log2;
@@ -530,10 +539,36 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
             __syncwarp();
             compute_levels(S, lane);
             const uint32_t np0 = D.n_planes[0], np1 = D.n_planes[1], np2 = D.n_planes[2], np3 = D.n_planes[3];
+            // word offset of each part's first plane (most parts match at most one head term)
+            const uint32_t po0 = (uint32_t)D.plane[0][0] * W, po1 = (uint32_t)D.plane[1][0] * W, po2 = (uint32_t)D.plane[2][0] * W, po3 = (uint32_t)D.plane[3][0] * W;
+            // presence word `w` of part l
+            auto part_word = [&](uint32_t l, uint32_t np, uint32_t po, uint32_t w) -> uint32_t {
+                if (np == 0) return 0u;
+                uint32_t x = s_bits[po + w];
+#pragma unroll 1
+                for (uint32_t j = 1; j < np; ++j) x |= s_bits[S.pl_off[l * kPartPlaneSlots + j] + w];
+                return x;
+            };
+            auto part_words4 = [&](uint32_t l, uint32_t np, uint32_t po, uint32_t w4) -> uint4 {
+                if (np == 0) return make_uint4(0u, 0u, 0u, 0u);
+                uint4 x = reinterpret_cast<const uint4*>(s_bits + po)[w4];
+#pragma unroll 1
+                for (uint32_t j = 1; j < np; ++j) {
+                    const uint4 v = reinterpret_cast<const uint4*>(s_bits + S.pl_off[l * kPartPlaneSlots + j])[w4];
+                    x.x |= v.x, x.y |= v.y, x.z |= v.z, x.w |= v.w;
+                }
+                return x;
+            };
             const bool lev_in_smem = S.lev_in_smem != 0;
             const uint32_t* lev_glob = (D.flags & kFastBoost) ? D.fb_lev->bits + (size_t)t * W : nullptr;
             const uint32_t lev_words = lev_in_smem ? a.lev_hdr.words : (D.flags & kFastBoost) ? D.fb_lev->words : 0u;
             uint32_t cnt = 0, ncand = 0;
+            // A request with at most one head term in total needs no sweep once anchors with a single part present cannot
+            // reach the threshold any more: its hit count is the plane's count of the tile plus the entry anchors outside it.
+            const uint32_t np_total = np0 + np1 + np2 + np3;
+            const bool sweepless = np_total == 0 || (np_total == 1 && S.lev[0] == -2);
+            const uint32_t only_po = np0 ? po0 : np1 ? po1 : np2 ? po2 : po3;  // the single plane (np_total == 1)
+            if (sweepless && np_total == 1 && lane == 0) cnt = s_pcount[only_po / W];
 
             // anchors with entries: bounded one by one (entry scores are known exactly, plane parts by their bound)
             if (n_ent) {
@@ -548,26 +583,26 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                     float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f, e3 = 0.0f;
                     if (mine_r) {
                         const uint32_t w = idx >> 5, bit = 1u << (idx & 31u);
+                        if (sweepless && !(np_total == 1 && (s_bits[only_po + w] & bit))) cnt += 1;  // a hit the plane count does not include
                         const bool multi = (S.mbits[w] & bit) != 0;
                         float sum_ub = 0.0f;
                         uint32_t n = 0;
-#pragma unroll 1
-                        for (uint32_t l = 0; l < L; ++l) {
-                            // the anchor's only entry is this lane's; anchors with several entries look them up
-                            uint32_t ev = 0;
-                            if (multi || l == el) ev = hash_lookup(S, idx | (l << 13));
-                            const float evf = ev ? __uint_as_float(ev & 0x7FFFFFFFu) : 0.0f;
-                            e0 = l == 0 ? evf : e0, e1 = l == 1 ? evf : e1, e2 = l == 2 ? evf : e2, e3 = l == 3 ? evf : e3;
-                            uint32_t pbits = 0;
-                            const uint32_t np = D.n_planes[l];
-#pragma unroll 1
-                            for (uint32_t j = 0; j < np; ++j) pbits |= s_bits[S.pl_off[l * kPartPlaneSlots + j] + w];
-                            const bool by_plane = (pbits & bit) != 0;
+                        // the anchor's only entry is this lane's own; anchors with several entries look them up per part
+                        const uint32_t own_ev = hash_lookup(S, code);
+                        auto part = [&](uint32_t l, uint32_t np, uint32_t po, float& e) {
+                            uint32_t ev = l == el ? own_ev : 0u;
+                            if (multi && l != el) ev = hash_lookup(S, idx | (l << 13));
+                            e = ev ? __uint_as_float(ev & 0x7FFFFFFFu) : 0.0f;
+                            const bool by_plane = (part_word(l, np, po, w) & bit) != 0;
                             if (ev || by_plane) {
                                 n += 1;
-                                sum_ub += fmaxf(evf, by_plane ? D.ub[l] : 0.0f);
+                                sum_ub += fmaxf(e, by_plane ? D.ub[l] : 0.0f);
                             }
-                        }
+                        };
+                        part(0, np0, po0, e0);
+                        if (L > 1) part(1, np1, po1, e1);
+                        if (L > 2) part(2, np2, po2, e2);
+                        if (L > 3) part(3, np3, po3, e3);
                         const float B = (L == 1 ? sum_ub : sum_ub * (float)(n * n)) * 1.00001f;
                         if (tau_score > 0.0f) {
                             if (D.flags & kFastBoost) {
@@ -600,27 +635,28 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
             for (int i2 = 0; i2 < (int)kFastMaxLeaves - 1; ++i2)
                 if ((uint32_t)i2 + 1 < L && S.lev[i2] != -2) lower_dead = false;
 #pragma unroll 1
-            for (uint32_t w4 = lane; w4 < (W >> 2); w4 += 32) {
+            for (uint32_t w4 = lane; w4 < (sweepless ? 0u : (W >> 2)); w4 += 32) {
                 uint4 e = make_uint4(0u, 0u, 0u, 0u);
                 if (n_ent) e = reinterpret_cast<const uint4*>(S.ebits)[w4];
                 uint32_t cm[4] = {0u, 0u, 0u, 0u};
                 if (lower_dead && S.lev[L - 1] == lev_top) {
                     // converged threshold: only anchors with every part present can still matter -> OR for the count, AND for the candidates
-                    uint4 any = make_uint4(0u, 0u, 0u, 0u), all = make_uint4(~0u, ~0u, ~0u, ~0u);
-                    auto add_part = [&](uint32_t l, uint32_t np) {
-                        uint4 x = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll 1
-                        for (uint32_t j = 0; j < np; ++j) {
-                            const uint4 v = reinterpret_cast<const uint4*>(s_bits + S.pl_off[l * kPartPlaneSlots + j])[w4];
-                            x.x |= v.x, x.y |= v.y, x.z |= v.z, x.w |= v.w;
-                        }
+                    uint4 any = part_words4(0, np0, po0, w4), all = any;
+                    if (L > 1) {
+                        const uint4 x = part_words4(1, np1, po1, w4);
                         any.x |= x.x, any.y |= x.y, any.z |= x.z, any.w |= x.w;
                         all.x &= x.x, all.y &= x.y, all.z &= x.z, all.w &= x.w;
-                    };
-                    add_part(0, np0);
-                    if (L > 1) add_part(1, np1);
-                    if (L > 2) add_part(2, np2);
-                    if (L > 3) add_part(3, np3);
+                    }
+                    if (L > 2) {
+                        const uint4 x = part_words4(2, np2, po2, w4);
+                        any.x |= x.x, any.y |= x.y, any.z |= x.z, any.w |= x.w;
+                        all.x &= x.x, all.y &= x.y, all.z &= x.z, all.w &= x.w;
+                    }
+                    if (L > 3) {
+                        const uint4 x = part_words4(3, np3, po3, w4);
+                        any.x |= x.x, any.y |= x.y, any.z |= x.z, any.w |= x.w;
+                        all.x &= x.x, all.y &= x.y, all.z &= x.z, all.w &= x.w;
+                    }
                     cnt += __popc(any.x | e.x) + __popc(any.y | e.y) + __popc(any.z | e.z) + __popc(any.w | e.w);
                     if (lev_top == -2) continue;
                     if (lev_top >= 0) {
@@ -632,23 +668,18 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                     cm[0] = all.x & ~e.x, cm[1] = all.y & ~e.y, cm[2] = all.z & ~e.z, cm[3] = all.w & ~e.w;
                 } else {
                     uint4 ones = make_uint4(0u, 0u, 0u, 0u), twos = ones, fours = ones;
-                    auto add_part = [&](uint32_t l, uint32_t np) {
-                        uint4 x = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll 1
-                        for (uint32_t j = 0; j < np; ++j) {
-                            const uint4 v = reinterpret_cast<const uint4*>(s_bits + S.pl_off[l * kPartPlaneSlots + j])[w4];
-                            x.x |= v.x, x.y |= v.y, x.z |= v.z, x.w |= v.w;
-                        }
+                    auto add_part = [&](uint32_t l, uint32_t np, uint32_t po) {
+                        const uint4 x = part_words4(l, np, po, w4);
                         uint32_t cy, cy2;
                         cy = ones.x & x.x, ones.x ^= x.x, cy2 = twos.x & cy, twos.x ^= cy, fours.x |= cy2;
                         cy = ones.y & x.y, ones.y ^= x.y, cy2 = twos.y & cy, twos.y ^= cy, fours.y |= cy2;
                         cy = ones.z & x.z, ones.z ^= x.z, cy2 = twos.z & cy, twos.z ^= cy, fours.z |= cy2;
                         cy = ones.w & x.w, ones.w ^= x.w, cy2 = twos.w & cy, twos.w ^= cy, fours.w |= cy2;
                     };
-                    add_part(0, np0);
-                    if (L > 1) add_part(1, np1);
-                    if (L > 2) add_part(2, np2);
-                    if (L > 3) add_part(3, np3);
+                    add_part(0, np0, po0);
+                    if (L > 1) add_part(1, np1, po1);
+                    if (L > 2) add_part(2, np2, po2);
+                    if (L > 3) add_part(3, np3, po3);
                     cnt += __popc(ones.x | twos.x | fours.x | e.x) + __popc(ones.y | twos.y | fours.y | e.y) + __popc(ones.z | twos.z | fours.z | e.z) + __popc(ones.w | twos.w | fours.w | e.w);
 #pragma unroll
                     for (int i2 = 0; i2 < (int)kFastMaxLeaves; ++i2) {
