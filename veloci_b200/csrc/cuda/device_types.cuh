@@ -91,7 +91,7 @@ struct PartPlanes {  // head-term matches of one search part (48 B)
 static const uint32_t kFastMaxLeaves = 4;
 static const uint32_t kFastMaxK = 64;
 static const uint32_t kFastMaxEntries = 128;  // postings of non-plane terms in one (tile, request) item
-enum FastFlags : uint32_t { kFastOk = 1u, kFastBoost = 2u };
+enum FastFlags : uint32_t { kFastOk = 1u, kFastBoost = 2u, kFastUnion1 = 4u };
 struct alignas(16) FastDesc {
     uint32_t flags, n_leaves, k, fb_fun;
     float fb_param, fb_max_mult;
@@ -278,7 +278,7 @@ struct alignas(16) QueryProgram {  // 96 B
     uint32_t fb_flags;              // bit 0: fast boost present, bit 1: max_mult bounds the multiplier (can prune)
     uint32_t fb_n, fb_fun;
     float fb_param, fb_max_mult;
-    uint32_t pad0;
+    uint32_t union1;                // one leaf standing for an `or` of identical parts: the union rule applies (score * n * n with n in {0, 1}), not the passthrough
     const uint32_t* fb_col;
     const ColumnLevels* fb_lev;     // level bitmaps of the fast-boost column (nullptr: none)
     uint32_t post_begin, post_len;  // post ops, into the program words

@@ -173,7 +173,7 @@ __global__ void build_fast_desc_kernel(const QueryProgram* __restrict__ queries,
             const float f = qp.n_leaves == 1 ? 1.0f : (float)(nn * nn);
             d.bound[nn - 1] = sum * f * 1.00001f;
         }
-        d.flags = kFastOk | (qp.n_boosts ? kFastBoost : 0u);
+        d.flags = kFastOk | (qp.n_boosts ? kFastBoost : 0u) | (qp.union1 ? kFastUnion1 : 0u);
         d.n_leaves = qp.n_leaves, d.k = qp.k;
         d.fb_fun = qp.fb_fun, d.fb_param = qp.fb_param, d.fb_max_mult = qp.fb_max_mult, d.fb_n = qp.fb_n;
         d.fb_col = qp.fb_col, d.fb_lev = qp.fb_lev;
@@ -310,7 +310,7 @@ __device__ __forceinline__ unsigned long long eval_candidate(const CtaContext& C
         sum += v;
         if (l == 0) v0 = v;
     }
-    float score = L == 1 ? v0 : sum * nd * nd;
+    float score = (L == 1 && !(D.flags & kFastUnion1)) ? v0 : sum * nd * nd;
     const uint32_t anchor = C.anchor_lo + rel;
     if (D.flags & kFastBoost) {
         if (anchor < D.fb_n) {

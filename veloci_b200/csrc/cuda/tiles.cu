@@ -373,7 +373,7 @@ __device__ __forceinline__ uint32_t eval_idx(const TileArgs& a, const ItemCtx& c
             if (v >= 0.00001f) nd += 1.0f;
             sum += v;
         }
-        score = L == 1 ? vbit::key_score(arr[idx]) : sum * nd * nd;
+        score = (L == 1 && !c.qp.union1) ? vbit::key_score(arr[idx]) : sum * nd * nd;
     } else {
         present = eval_program(a.prog + c.qp.prog_begin, c.qp.prog_len, arr, c.tile, idx, a.boosts + c.qp.boost_begin, score);
     }
@@ -409,7 +409,7 @@ __device__ __forceinline__ uint32_t sweep_flat(const TileArgs& a, const ItemCtx&
             for (int l = 0; l < L; ++l) ks[l] = comp4(v[l], cc), kor |= ks[l];
             if (!kor) continue;
             float score;
-            if (L == 1) {
+            if (L == 1 && !c.qp.union1) {
                 score = NONNEG ? __uint_as_float(ks[0] & 0x7FFFFFFFu) : vbit::key_score(ks[0]);
             } else {
                 float nd = 0.0f, sum = 0.0f;

@@ -534,6 +534,14 @@ struct Batch {
                 uint32_t not_fast = 0, hist[8] = {};
                 for (auto& d : fd) not_fast += d.flags == 0;
                 for (auto& p : pp) hist[std::min<uint32_t>(p.n, 7)]++;
+                for (uint32_t q = 0; q < n; ++q)
+                    if (fd[q].flags == 0) {
+                        const QueryProgram& qp = plan.programs[q];
+                        fprintf(stderr, "[veloci] request %u off the plane path: active %u prog_len %u leaves %u nonneg %u k %u boosts %u fb_flags %u post %u facets %u planes", q, qp.active,
+                                qp.prog_len, qp.n_leaves, qp.nonneg, qp.k, qp.n_boosts, qp.fb_flags, qp.post_len, qp.n_facets);
+                        for (uint32_t l = 0; l < qp.n_leaves; ++l) fprintf(stderr, " %u", pp[plan.leaf_part[qp.leaf_begin + l]].n);
+                        fprintf(stderr, "\n");
+                    }
                 fprintf(stderr, "[veloci] requests %u not on the plane path %u; parts by plane matches:", n, not_fast);
                 for (int i = 0; i < 8; ++i) fprintf(stderr, " %u", hist[i]);
                 fprintf(stderr, "\n");

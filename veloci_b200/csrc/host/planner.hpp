@@ -582,16 +582,17 @@ struct BatchPlan {
             flat = true;
         } else if (root.kind == vhost::SearchRequest::Or && code.size() == 2 * leaves.size() + 3 + leaves.size() && code[2 * leaves.size()] == vdev::kOpUnion) {
             // Parts that share a term slot must be the very same search part (then their hit lists are identical and
-            // max(x, x) = x, so one leaf stands for the slot); at least two slots, so that the n * n rule still applies.
+            // max(x, x) = x, so one leaf stands for the slot).
             const uint32_t n_slots = code[2 * leaves.size() + 2];
             std::vector<uint32_t> by_slot(n_slots, vdev::kNoValue);
-            bool same = n_slots == leaves.size() || n_slots >= 2;
+            bool same = true;
             for (size_t c = 0; c < leaves.size() && same; ++c) {
                 uint32_t& slot = by_slot[code[2 * leaves.size() + 3 + c]];
                 if (slot == vdev::kNoValue) slot = leaves[c];
                 else if (slot != leaves[c]) same = false;
             }
             if (same) {
+                if (by_slot.size() == 1 && leaves.size() > 1) qp.union1 = 1;  // [A, A, ..]: still a union (n * n with n in {0, 1}), not the one-input passthrough
                 leaves = by_slot;
                 flat = true;
             }
