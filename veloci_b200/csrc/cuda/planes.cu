@@ -43,7 +43,8 @@ struct WarpScratch {
     uint32_t cand_q[kQueueCap];            // request
     uint32_t cand_idx[kQueueCap];          // anchor index in the tile
     float cand_e[kFastMaxLeaves][kQueueCap];  // per part: largest entry score of the anchor (0: none)
-    uint16_t ent_idx[kFastMaxEntries];     // index in tile of entry r * 32 + lane
+    uint16_t ent_idx[kFastMaxEntries];     // index in tile | leaf << 13 of entry r * 32 + lane
+    uint32_t ent_key[kFastMaxEntries];     // its score key
     unsigned long long merge[kFastMaxK + 1];
     // state of the item being processed (warp-uniform)
     unsigned long long tau;                // the request's k-th best so far (0: fewer than k hits)
@@ -523,6 +524,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                 if (lane == 0) S.mult_lev = D.fb_lev, S.mult_fun = D.fb_fun, S.mult_param = D.fb_param;
             }
             uint32_t own = 0;  // bit r: this lane's entry r is the first of its anchor
+            bool any_multi = false;
             if (n_ent) {
 #pragma unroll
                 for (uint32_t r = 0; r < kEntRegs; ++r) {
@@ -532,9 +534,22 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                         if (!(atomicOr(&S.ebits[idx >> 5], bit) & bit)) own |= 1u << r;
                         else atomicOr(&S.mbits[idx >> 5], bit);
                         S.ent_idx[r * 32u + lane] = (uint16_t)(idx | (l << 13));
-                        hash_insert(S, idx | (l << 13), cur.ent[r].y);
+                        S.ent_key[r * 32u + lane] = cur.ent[r].y;
                     }
                 }
+                __syncwarp();
+                // only anchors with several entries need the hash (per-part maximum over their entries)
+#pragma unroll
+                for (uint32_t r = 0; r < kEntRegs; ++r) {
+                    if (r * 32u + lane < n_ent) {
+                        const uint32_t idx = cur.ent[r].x - tile_base, l = (cur.ent_leaf >> (2u * r)) & 3u;
+                        if (S.mbits[idx >> 5] & (1u << (idx & 31u))) {
+                            hash_insert(S, idx | (l << 13), cur.ent[r].y);
+                            any_multi = true;
+                        }
+                    }
+                }
+                any_multi = __ballot_sync(0xFFFFFFFFu, any_multi) != 0;
             }
             __syncwarp();
             compute_levels(S, lane);
@@ -588,7 +603,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                         float sum_ub = 0.0f;
                         uint32_t n = 0;
                         // the anchor's only entry is this lane's own; anchors with several entries look them up per part
-                        const uint32_t own_ev = hash_lookup(S, code);
+                        const uint32_t own_ev = multi ? hash_lookup(S, code) : S.ent_key[r * 32u + lane];
                         auto part = [&](uint32_t l, uint32_t np, uint32_t po, float& e) {
                             uint32_t ev = l == el ? own_ev : 0u;
                             if (multi && l != el) ev = hash_lookup(S, idx | (l << 13));
@@ -722,10 +737,11 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
 #pragma unroll
                 for (uint32_t r = 0; r < kEntRegs; ++r)
                     if (r * 32u + lane < n_ent) S.ebits[(cur.ent[r].x - tile_base) >> 5] = 0, S.mbits[(cur.ent[r].x - tile_base) >> 5] = 0;
-                for (uint32_t j = lane; j < kHashSlots / 4; j += 32) {
-                    reinterpret_cast<uint4*>(S.hkey)[j] = make_uint4(kHashEmpty, kHashEmpty, kHashEmpty, kHashEmpty);
-                    reinterpret_cast<uint4*>(S.hval)[j] = make_uint4(0u, 0u, 0u, 0u);
-                }
+                if (any_multi)
+                    for (uint32_t j = lane; j < kHashSlots / 4; j += 32) {
+                        reinterpret_cast<uint4*>(S.hkey)[j] = make_uint4(kHashEmpty, kHashEmpty, kHashEmpty, kHashEmpty);
+                        reinterpret_cast<uint4*>(S.hval)[j] = make_uint4(0u, 0u, 0u, 0u);
+                    }
             }
             cur = nxt, it_cur = it_nxt;
         }

@@ -1,6 +1,7 @@
 // extern "C" boundary of libveloci_b200.so (include/veloci_b200.h).  No exception
 // crosses it: every entry point maps failures to a VGPU_ERR_* status and leaves the
 // message in a thread-local buffer (vgpu_last_error).
+#include <malloc.h>
 #include "../../../include/veloci_b200.h"
 
 #include <atomic>
@@ -77,7 +78,19 @@ int32_t vgpu_device_count(void) {
     return count;
 }
 
+// The planner allocates and frees tens of megabytes per batch: keep that memory in the process instead of returning it
+// to the kernel (and page-faulting it back in) every time.
+static void tune_allocator_once() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_ARENA_MAX, 32);
+}
+
 int32_t vgpu_index_open(const char* dir, int32_t device, uint32_t shard_rank, uint32_t n_shards, vgpu_index** out) {
+    tune_allocator_once();
     if (!dir || !out) {
         t_error = "null argument";
         return VGPU_ERR_INVALID_REQUEST;

@@ -121,6 +121,55 @@ class ScratchPool {
     size_t cached_ = 0;
 };
 
+// While an UploadScope is alive on a thread, DevBuf::upload stages its source through pinned host memory and copies
+// asynchronously on the scope's stream (a batch uploads a dozen small plan tables: one pageable cudaMemcpy each costs more
+// than the whole transfer).  The scope's destructor waits for the copies, so the staging buffer can be reused.
+class UploadScope {
+   public:
+    explicit UploadScope(cudaStream_t st) : stream_(st) {
+        Buf& b = buf();
+        if (!b.p) {
+            if (cudaHostAlloc((void**)&b.p, kCap, cudaHostAllocDefault) != cudaSuccess) b.p = nullptr;
+        }
+        used_ = 0;
+        current() = b.p ? this : nullptr;
+    }
+    ~UploadScope() {
+        if (current() == this) {
+            cudaStreamSynchronize(stream_);
+            current() = nullptr;
+        }
+    }
+    static UploadScope*& current() {
+        static thread_local UploadScope* cur = nullptr;
+        return cur;
+    }
+    // copies `bytes` from pageable `src` to device `dst`; false = too large for the staging buffer
+    bool copy(void* dst, const void* src, size_t bytes) {
+        if (bytes > kCap) return false;
+        if (used_ + bytes > kCap) {
+            cudaStreamSynchronize(stream_);
+            used_ = 0;
+        }
+        char* at = buf().p + used_;
+        memcpy(at, src, bytes);
+        used_ += (bytes + 255) & ~(size_t)255;
+        return cudaMemcpyAsync(dst, at, bytes, cudaMemcpyHostToDevice, stream_) == cudaSuccess;
+    }
+
+   private:
+    static constexpr size_t kCap = (size_t)32 << 20;
+    struct Buf {
+        char* p = nullptr;
+    };
+    static Buf& buf() {
+        static thread_local Buf b;
+        return b;
+    }
+    cudaStream_t stream_;
+    size_t used_ = 0;
+};
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -156,7 +205,10 @@ struct DevBuf {
     }
     void upload(const std::vector<T>& v) {
         alloc(v.size());
-        if (!v.empty()) VDEV_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        if (v.empty()) return;
+        UploadScope* scope = UploadScope::current();
+        if (scope && scope->copy(p, v.data(), v.size() * sizeof(T))) return;
+        VDEV_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     }
     size_t bytes() const { return n * sizeof(T); }
 };
@@ -299,6 +351,7 @@ struct PhraseDev {
 
 struct DeviceIndex {
     int device = 0;
+    int n_sms = 148;
     uint32_t shard_rank = 0, n_shards = 1;
     uint64_t num_docs = 0, anchor_lo = 0, anchor_hi = 0;
     std::unique_ptr<vhost::Persistence> host;
@@ -663,6 +716,7 @@ struct DeviceIndex {
         VDEV_CUDA(cudaSetDevice(device));
         std::unique_ptr<DeviceIndex> ix(new DeviceIndex());
         ix->device = device;
+        VDEV_CUDA(cudaDeviceGetAttribute(&ix->n_sms, cudaDevAttrMultiProcessorCount, device));
         ix->shard_rank = rank;
         ix->n_shards = n_shards;
         ix->host = vhost::Persistence::load(dir);

@@ -125,6 +125,7 @@ struct Batch {
         plan.ix = ix;
         plan.requests.reserve(n);
         const auto t0 = std::chrono::steady_clock::now();
+        auto t_joined = t0;
         // every thread parses and plans a contiguous chunk of the requests; the chunk plans are merged in request order
         const unsigned hw = n >= 256 ? std::max(1u, std::min(16u, std::thread::hardware_concurrency())) : 1u;
         if (hw > 1) {
@@ -140,8 +141,7 @@ struct Batch {
                 });
             }
             for (auto& th : pool) th.join();
-            const auto t1m = std::chrono::steady_clock::now();
-            (void)t1m;
+            t_joined = std::chrono::steady_clock::now();
             for (unsigned t = 0; t < hw; ++t) plan.merge(chunks[t]);
         } else {
             for (uint32_t i = 0; i < n; ++i) plan.add_request(request_json[i] ? request_json[i] : "");
@@ -152,7 +152,7 @@ struct Batch {
         if (getenv("VELOCI_DEBUG")) {
             const auto t3 = std::chrono::steady_clock::now();
             auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-            fprintf(stderr, "[veloci] prepare: parse + plan %.2f ms (%u threads), upload %.2f ms\n", ms(t0, t1), hw, ms(t2, t3));
+            fprintf(stderr, "[veloci] prepare: parse + plan %.2f ms on %u threads + merge %.2f ms, upload %.2f ms\n", ms(t0, t_joined), hw, ms(t_joined, t1), ms(t2, t3));
         }
     }
 
@@ -258,9 +258,8 @@ struct Batch {
         n_parts = (uint32_t)plan.parts.size();
         VDEV_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (auto& e : ev) VDEV_CUDA(cudaEventCreate(&e));
-        cudaDeviceProp prop;
-        VDEV_CUDA(cudaGetDeviceProperties(&prop, ix->device));
-        n_sms = prop.multiProcessorCount;
+        UploadScope staged_uploads(stream);  // every table below goes through pinned memory, asynchronously
+        n_sms = ix->n_sms;  // (cudaGetDeviceProperties costs milliseconds: asked once, at index open)
 
         // geometry: the largest tile (<= 8192 anchors) whose part arrays leave room for four CTAs per SM
         const uint32_t L = std::max<uint32_t>(1, plan.max_leaves);
@@ -300,7 +299,7 @@ struct Batch {
         d_tl_instances.upload(plan.tl_instances);
         d_tl_term_parts.upload(plan.tl_term_parts);
         d_req_error.alloc(n + 1);
-        VDEV_CUDA(cudaMemset(d_req_error.p, 0, d_req_error.bytes()));
+        VDEV_CUDA(cudaMemsetAsync(d_req_error.p, 0, d_req_error.bytes(), stream));
         h2d_bytes += plan.tl_instances.size() * sizeof(TlInstance) + plan.tl_term_parts.size() * 4;
         d_ids_members.upload(plan.ids_members);
         h2d_bytes += plan.ids_members.size() * sizeof(IdsMember);
@@ -379,7 +378,7 @@ struct Batch {
         d_out_hits.alloc(n + 1);
         d_emit.alloc((size_t)emit_capacity + 1);
         if (mode == kRequests) d_records.reserve(std::max<size_t>(1u << 20, (size_t)n_parts * 64));
-        VDEV_CUDA(cudaMemset(d_counters.p, 0, d_counters.bytes()));
+        VDEV_CUDA(cudaMemsetAsync(d_counters.p, 0, d_counters.bytes(), stream));
     }
 
     // Matched terms with at least this many postings get a tile-offset row, the others are copied into their part's
