@@ -198,9 +198,25 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     batch = index.prepare(reqs)
+    SIGN = -(1 << 63)
+
+    def run_batch(b):
+        """One step on this rank's shard.  With several shards the per-request thresholds are shared after the first
+        tiles: all-reduce MAX in unsigned order (the sign bit is flipped around the signed reduction)."""
+        if not dist:
+            b.execute()
+            return
+        b.execute_begin()
+        ptr, cnt = b.thresholds()
+        tau = torch.as_tensor(DevArray(ptr, cnt), device="cuda")
+        tau.bitwise_xor_(SIGN)
+        dist.all_reduce(tau, op=dist.ReduceOp.MAX)
+        tau.bitwise_xor_(SIGN)
+        torch.cuda.synchronize()
+        b.execute_finish()
 
     def step_resident():
-        batch.execute()
+        run_batch(batch)
         if dist:
             keys_ptr, hits_ptr, stride = batch.local_topk()
             n = len(reqs)
@@ -241,7 +257,7 @@ def run_ours(args):
         t1 = time.perf_counter()
         b = index.prepare(reqs)
         t2 = time.perf_counter()
-        b.execute()
+        run_batch(b)
         t3 = time.perf_counter()
         if dist:
             keys_ptr, hits_ptr, stride = b.local_topk()

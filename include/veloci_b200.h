@@ -110,6 +110,14 @@ int32_t vgpu_search_batch(vgpu_index* idx, const char* const* request_json, uint
  * vgpu_batch_merge_gathered on every rank: final top-k of n_shards * stride
  * candidates, num_hits summed.  Pointers are device pointers. */
 int32_t vgpu_batch_local_topk(const vgpu_batch* batch, uint64_t** keys_dev, uint64_t** num_hits_dev, uint32_t* stride);
+/* Optional threshold exchange.  vgpu_batch_execute == execute_begin + execute_finish.  After execute_begin every shard
+ * has evaluated its first anchor tiles and holds, per request, the order key of its k-th best hit so far (0: fewer than k
+ * hits) in the device array returned by vgpu_batch_thresholds.  The global k-th best is at least the largest of the
+ * shards' values, so the host may all-reduce the arrays with MAX (unsigned 64-bit order) before execute_finish: every
+ * shard then prunes against the shared threshold.  The merged result is unchanged (hits below it cannot reach the top k). */
+int32_t vgpu_batch_execute_begin(vgpu_batch* batch);
+int32_t vgpu_batch_thresholds(const vgpu_batch* batch, uint64_t** tau_dev, uint32_t* n);
+int32_t vgpu_batch_execute_finish(vgpu_batch* batch);
 int32_t vgpu_batch_merge_gathered(vgpu_batch* batch, const uint64_t* gathered_keys_dev, const uint64_t* gathered_num_hits_dev, uint32_t n_shards);
 
 /* ---- step seam -------------------------------------------------------------

@@ -284,8 +284,20 @@ def test_sharded_index_equals_unsharded(gpu, native_libs):
     shards = [gpu.Index(d, shard_rank=r, n_shards=2) for r in range(2)]
     batches = [s.prepare(reqs) for s in shards]
     keys, hits = [], []
+    # threshold exchange between the shards after their first tiles (MAX in unsigned order), as bench.py does over NCCL
+    sign = -(1 << 63)
+    taus = []
     for b in batches:
-        b.execute()
+        b.execute_begin()
+        ptr, cnt = b.thresholds()
+        taus.append(torch.as_tensor(_DevArray(ptr, cnt), device="cuda"))
+    shared = torch.maximum(taus[0] ^ sign, taus[1] ^ sign) ^ sign
+    assert (shared != 0).any()
+    for t in taus:
+        t.copy_(shared)
+    torch.cuda.synchronize()
+    for b in batches:
+        b.execute_finish()
         kp, hp, stride = b.local_topk()
         keys.append(torch.as_tensor(_DevArray(kp, len(reqs) * stride), device="cuda").clone())
         hits.append(torch.as_tensor(_DevArray(hp, len(reqs)), device="cuda").clone())

@@ -52,6 +52,9 @@ def load_library():
     L.vgpu_index_info.argtypes = [vp, P(u64), P(u64), P(u64), P(u64)]
     L.vgpu_batch_prepare.argtypes = [vp, P(cp), u32, P(vp)]
     L.vgpu_batch_execute.argtypes = [vp]
+    L.vgpu_batch_execute_begin.argtypes = [vp]
+    L.vgpu_batch_execute_finish.argtypes = [vp]
+    L.vgpu_batch_thresholds.argtypes = [vp, P(vp), P(u32)]
     L.vgpu_batch_free.argtypes = [vp]
     L.vgpu_batch_free.restype = None
     L.vgpu_batch_status.argtypes = [vp, u32]
@@ -176,6 +179,20 @@ class Batch:
         status = np.zeros(self.n, dtype=np.int32)
         _check(self.L.vgpu_batch_results_flat(self.h, k, ids.ctypes.data, scores.ctypes.data, num_hits.ctypes.data, status.ctypes.data))
         return {"ids": ids, "scores": scores, "num_hits": num_hits, "status": status}
+
+    def execute_begin(self):
+        _check(self.L.vgpu_batch_execute_begin(self.h))
+        return self
+
+    def execute_finish(self):
+        _check(self.L.vgpu_batch_execute_finish(self.h))
+        return self
+
+    def thresholds(self):
+        """Device pointer and length of the per-request thresholds (64-bit order keys) after execute_begin."""
+        ptr, n = ctypes.c_void_p(), ctypes.c_uint32()
+        _check(self.L.vgpu_batch_thresholds(self.h, ctypes.byref(ptr), ctypes.byref(n)))
+        return ptr.value, int(n.value)
 
     def local_topk(self):
         """Device pointers of the shard-local result rows: (keys_ptr, num_hits_ptr, stride)."""

@@ -254,7 +254,7 @@ __device__ __noinline__ void merge_one(const CtaContext* C, WarpScratch* Sp, uin
             uint32_t rank = 0;
             for (uint32_t j = 0; j < n; ++j) rank += S.merge[j] > key;
             if (rank < k) __stcg(heap + rank, key);
-            if (rank == k - 1) __stcg(C->tau + q, key);
+            if (rank == k - 1) atomicMax(C->tau + q, key);  // never below a threshold shared by the other shards
         }
         __threadfence();
     }

@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
             const unsigned long long new_tau = s_out[k - 1];
             __syncthreads();
             if (tid == 0) {
-                __stcg(a.tau + q, new_tau);
+                atomicMax(a.tau + q, new_tau);  // never below a threshold shared by the other shards
                 __threadfence();
                 atomicExch(a.lock + q, 0u);
                 s_nsurv = 0;

@@ -140,6 +140,26 @@ int32_t vgpu_batch_execute(vgpu_batch* batch) {
     });
 }
 
+int32_t vgpu_batch_execute_begin(vgpu_batch* batch) {
+    if (!batch) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() {
+        batch->facets.clear();
+        batch->b.execute_begin();
+    });
+}
+
+int32_t vgpu_batch_thresholds(const vgpu_batch* batch, uint64_t** tau_dev, uint32_t* n) {
+    if (!batch || !tau_dev || !n) return VGPU_ERR_INVALID_REQUEST;
+    *tau_dev = reinterpret_cast<uint64_t*>(batch->b.d_tau.p);
+    *n = batch->b.n;
+    return VGPU_OK;
+}
+
+int32_t vgpu_batch_execute_finish(vgpu_batch* batch) {
+    if (!batch) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() { batch->b.execute_finish(); });
+}
+
 void vgpu_batch_free(vgpu_batch* batch) {
     if (!batch) return;
     if (batch->b.ix) cudaSetDevice(batch->b.ix->device);

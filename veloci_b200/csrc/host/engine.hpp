@@ -93,6 +93,10 @@ struct Batch {
     const ColumnLevels* lev_dev = nullptr;  // boost column whose level bits the plane kernel stages in shared memory
     ColumnLevels lev_hdr{};
     uint64_t stat_fast_items = 0, stat_general_items = 0, stat_plane_evaluated = 0;
+    // between execute_begin and execute_finish
+    unsigned long long pending_items = 0;
+    uint32_t pending_fast_items = 0;
+    bool begun = false;
     // device: per-request state and results
     DevBuf<unsigned long long> d_heap, d_tau, d_num_hits;
     DevBuf<uint32_t> d_lock;
@@ -489,8 +493,35 @@ struct Batch {
 
     // ------------------------------------------------------------ all phases
     void execute() {
+        execute_begin();
+        execute_finish();
+    }
+
+    // PlaneArgs of one stage of the plane evaluation: tiles [t0, t1)
+    PlaneArgs plane_stage_args(int stage, uint32_t t0, uint32_t t1) {
+        PlaneArgs a;
+        memset(&a, 0, sizeof a);
+        a.items = d_fast_items.p, a.tile_item_begin = d_fast_item_begin.p, a.fast = d_fast.p;
+        a.sparse = d_sparse.p, a.planes = ix->planes.view();
+        a.lev_dev = lev_dev, a.lev_hdr = lev_hdr;
+        a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
+        a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
+        a.stats = d_counters.p + 8;
+        const uint32_t want_units = (uint32_t)n_sms * 2;
+        uint32_t unit = stage == 2 ? 1024u : std::max<uint32_t>(16, ((uint64_t)n * (t1 - t0) + want_units - 1) / want_units);
+        unit = (std::min<uint32_t>(unit, 1024u) + 15u) & ~15u;
+        a.tile_begin = t0, a.unit_items = unit;
+        a.chunks_per_tile = (n + unit - 1) / unit;
+        a.n_units = (t1 - t0) * a.chunks_per_tile;
+        a.work_counter = d_counters.p + 10 + stage;
+        return a;
+    }
+
+    // Everything up to the point where the requests' thresholds (k-th best so far) are worth sharing between anchor-range
+    // shards: match, slicing, item scan and the plane evaluation of the first four tiles.  Returns with the stream idle.
+    void execute_begin() {
         VDEV_CUDA(cudaSetDevice(ix->device));
-        executed = false, fetched = false;
+        executed = false, fetched = false, begun = false;
         d2h_bytes = 0;
         uint32_t M = 0;
         if (mode != kLists) {
@@ -599,30 +630,27 @@ struct Batch {
         if (n_facets) VDEV_CUDA(cudaMemsetAsync(d_facet_hist.p, 0, d_facet_hist.bytes(), stream));
         // ---- phase 3: plane evaluation.  Tile 0 first, its requests spread over all SMs, then a few more tiles: the
         // requests' thresholds are then close to final when the bulk of the tiles runs and prunes against them.
+        pending_items = n_items, pending_fast_items = n_fast_items;
         if (planes_on && n_fast_items) {
-            PlaneArgs a;
-            memset(&a, 0, sizeof a);
-            a.items = d_fast_items.p, a.tile_item_begin = d_fast_item_begin.p, a.fast = d_fast.p;
-            a.sparse = d_sparse.p, a.planes = ix->planes.view();
-            a.lev_dev = lev_dev, a.lev_hdr = lev_hdr;
-            a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
-            a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
-            a.stats = d_counters.p + 8;
-            const uint32_t stage_end[3] = {std::min<uint32_t>(1, n_tiles), std::min<uint32_t>(4, n_tiles), n_tiles};
-            uint32_t t0 = 0;
-            for (int stage = 0; stage < 3; ++stage) {
-                const uint32_t t1 = stage_end[stage];
-                if (t1 <= t0) continue;
-                const uint32_t want_units = (uint32_t)n_sms * 2;
-                uint32_t unit = stage == 2 ? 1024u : std::max<uint32_t>(16, ((uint64_t)n * (t1 - t0) + want_units - 1) / want_units);
-                unit = (std::min<uint32_t>(unit, 1024u) + 15u) & ~15u;
-                a.tile_begin = t0, a.unit_items = unit;
-                a.chunks_per_tile = (n + unit - 1) / unit;
-                a.n_units = (t1 - t0) * a.chunks_per_tile;
-                a.work_counter = d_counters.p + 10 + stage;
-                launch_plane_eval(stream, a, n_sms);
-                t0 = t1;
-            }
+            const uint32_t e0 = std::min<uint32_t>(1, n_tiles), e1 = std::min<uint32_t>(4, n_tiles);
+            if (e0 > 0) launch_plane_eval(stream, plane_stage_args(0, 0, e0), n_sms);
+            if (e1 > e0) launch_plane_eval(stream, plane_stage_args(1, e0, e1), n_sms);
+        }
+        VDEV_CUDA(cudaStreamSynchronize(stream));
+        VDEV_CUDA(cudaGetLastError());
+        begun = true;
+    }
+
+    // The rest of the step: the bulk of the plane evaluation, the general items, the final order.
+    void execute_finish() {
+        if (!begun) throw std::runtime_error("execute_finish without execute_begin");
+        VDEV_CUDA(cudaSetDevice(ix->device));
+        begun = false;
+        const unsigned long long n_items = pending_items;
+        const bool planes_on = use_planes && mode == kRequests;
+        if (planes_on && pending_fast_items) {
+            const uint32_t e1 = std::min<uint32_t>(4, n_tiles);
+            if (n_tiles > e1) launch_plane_eval(stream, plane_stage_args(2, e1, n_tiles), n_sms);
         }
         VDEV_CUDA(cudaEventRecord(ev[4], stream));
         // ---- phase 4: tile evaluation of the general items
