@@ -208,6 +208,10 @@ struct PlaneArgs {
     uint32_t tile_log2, anchor_lo, anchor_hi;
     // work unit u = (tile tile_begin + u / chunks_per_tile, chunk u % chunks_per_tile of unit_items items)
     uint32_t tile_begin, unit_items, chunks_per_tile, n_units;
+    // 0: normal.  1: seed pass -- only anchors without entries inside boost level `seed_level` are evaluated, nothing is
+    // counted: it gives every request a useful threshold for a fraction of a tile's evaluations.  2: the normal pass over
+    // tiles that were seeded: the anchors the seed pass evaluated are skipped.
+    uint32_t pass_mode, seed_level;
     // per-query state (shared with tile_eval_kernel)
     unsigned long long* heap;
     uint32_t heap_stride;

@@ -201,7 +201,7 @@ __device__ __forceinline__ float boost_mult(uint32_t fun, float x) {
 
 // Which anchors still have to be evaluated, per number of parts present (see the file comment): lane n - 1 decides
 // for n parts present.
-__device__ __forceinline__ void compute_levels(WarpScratch& S, uint32_t lane) {
+__device__ __forceinline__ void compute_levels(WarpScratch& S, uint32_t lane, uint32_t pass_mode, int seed_level) {
     const FastDesc& D = S.desc;
     float tau_score = 0.0f;
     if (S.tau != 0) {
@@ -227,6 +227,7 @@ __device__ __forceinline__ void compute_levels(WarpScratch& S, uint32_t lane) {
                 lev = -2;
             }
         }
+        if (pass_mode == 1 && lev != -2) lev = (D.flags & kFastBoost) ? max(lev, seed_level) : -2;  // seed pass: inside the seed level only
         S.lev[lane] = lev;
     }
     if (lane == 0) S.tau_score = tau_score;
@@ -541,7 +542,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                 // only anchors with several entries need the hash (per-part maximum over their entries)
 #pragma unroll
                 for (uint32_t r = 0; r < kEntRegs; ++r) {
-                    if (r * 32u + lane < n_ent) {
+                    if (r * 32u + lane < n_ent && a.pass_mode != 1) {
                         const uint32_t idx = cur.ent[r].x - tile_base, l = (cur.ent_leaf >> (2u * r)) & 3u;
                         if (S.mbits[idx >> 5] & (1u << (idx & 31u))) {
                             hash_insert(S, idx | (l << 13), cur.ent[r].y);
@@ -552,7 +553,9 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                 any_multi = __ballot_sync(0xFFFFFFFFu, any_multi) != 0;
             }
             __syncwarp();
-            compute_levels(S, lane);
+            compute_levels(S, lane, a.pass_mode, (int)a.seed_level);
+            const bool seed_pass = a.pass_mode == 1;
+            const bool skip_seeded = a.pass_mode == 2 && (D.flags & kFastBoost) != 0;
             const uint32_t np0 = D.n_planes[0], np1 = D.n_planes[1], np2 = D.n_planes[2], np3 = D.n_planes[3];
             // word offset of each part's first plane (most parts match at most one head term)
             const uint32_t po0 = (uint32_t)D.plane[0][0] * W, po1 = (uint32_t)D.plane[1][0] * W, po2 = (uint32_t)D.plane[2][0] * W, po3 = (uint32_t)D.plane[3][0] * W;
@@ -581,12 +584,14 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
             // A request with at most one head term in total needs no sweep once anchors with a single part present cannot
             // reach the threshold any more: its hit count is the plane's count of the tile plus the entry anchors outside it.
             const uint32_t np_total = np0 + np1 + np2 + np3;
-            const bool sweepless = np_total == 0 || (np_total == 1 && S.lev[0] == -2);
+            const bool sweepless = np_total == 0 || (np_total == 1 && S.lev[0] == -2 && !seed_pass);
             const uint32_t only_po = np0 ? po0 : np1 ? po1 : np2 ? po2 : po3;  // the single plane (np_total == 1)
             if (sweepless && np_total == 1 && lane == 0) cnt = s_pcount[only_po / W];
+            // boost level of the seed pass, for the candidates of pass 2 to skip
+            const uint32_t* seed_bits = lev_in_smem ? s_lev + a.seed_level * W : (skip_seeded ? lev_glob + (size_t)a.seed_level * lev_words : nullptr);
 
             // anchors with entries: bounded one by one (entry scores are known exactly, plane parts by their bound)
-            if (n_ent) {
+            if (n_ent && !seed_pass) {
 #pragma unroll 1
                 for (uint32_t r = 0; r < kEntRegs; ++r) {
                     if (r * 32u >= n_ent) break;
@@ -681,6 +686,10 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                         all.x &= lw.x, all.y &= lw.y, all.z &= lw.z, all.w &= lw.w;
                     }
                     cm[0] = all.x & ~e.x, cm[1] = all.y & ~e.y, cm[2] = all.z & ~e.z, cm[3] = all.w & ~e.w;
+                    if (skip_seeded) {
+                        const uint4 sw = reinterpret_cast<const uint4*>(seed_bits)[w4];
+                        cm[0] &= ~sw.x, cm[1] &= ~sw.y, cm[2] &= ~sw.z, cm[3] &= ~sw.w;
+                    }
                 } else {
                     uint4 ones = make_uint4(0u, 0u, 0u, 0u), twos = ones, fours = ones;
                     auto add_part = [&](uint32_t l, uint32_t np, uint32_t po) {
@@ -714,6 +723,10 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
                         cm[0] |= ex.x, cm[1] |= ex.y, cm[2] |= ex.z, cm[3] |= ex.w;
                     }
                     cm[0] &= ~e.x, cm[1] &= ~e.y, cm[2] &= ~e.z, cm[3] &= ~e.w;  // anchors with entries were handled above
+                    if (skip_seeded) {
+                        const uint4 sw = reinterpret_cast<const uint4*>(seed_bits)[w4];
+                        cm[0] &= ~sw.x, cm[1] &= ~sw.y, cm[2] &= ~sw.z, cm[3] &= ~sw.w;
+                    }
                 }
                 if (__ballot_sync(0xFFFFFFFFu, (cm[0] | cm[1] | cm[2] | cm[3]) != 0) == 0) continue;
 #pragma unroll 1
@@ -729,7 +742,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
             }
             for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
             if (lane == 0) {
-                if (cnt) atomicAdd(a.num_hits + it_cur.q, (unsigned long long)cnt);
+                if (cnt && !seed_pass) atomicAdd(a.num_hits + it_cur.q, (unsigned long long)cnt);
                 st_cand += ncand, st_items += 1;
             }
             if (n_ent) {  // leave the entry bitmap and the hash table empty

@@ -633,7 +633,16 @@ struct Batch {
         pending_items = n_items, pending_fast_items = n_fast_items;
         if (planes_on && n_fast_items) {
             const uint32_t e0 = std::min<uint32_t>(1, n_tiles), e1 = std::min<uint32_t>(4, n_tiles);
-            if (e0 > 0) launch_plane_eval(stream, plane_stage_args(0, 0, e0), n_sms);
+            if (e0 > 0) {
+                // tile 0 twice: a seed pass over the anchors in the top 1/64 of the boost column gives every request a
+                // threshold, then the normal pass (which skips what the seed pass evaluated) prunes against it
+                PlaneArgs seed = plane_stage_args(0, 0, e0);
+                seed.pass_mode = 1, seed.seed_level = 5, seed.work_counter = d_counters.p + 13;
+                PlaneArgs rest = plane_stage_args(0, 0, e0);
+                rest.pass_mode = lev_dev ? 2 : 0, rest.seed_level = 5;
+                if (lev_dev) launch_plane_eval(stream, seed, n_sms);
+                launch_plane_eval(stream, rest, n_sms);
+            }
             if (e1 > e0) launch_plane_eval(stream, plane_stage_args(1, e0, e1), n_sms);
         }
         VDEV_CUDA(cudaStreamSynchronize(stream));
