@@ -146,7 +146,8 @@ struct Batch {
             }
             for (auto& th : pool) th.join();
             t_joined = std::chrono::steady_clock::now();
-            for (unsigned t = 0; t < hw; ++t) plan.merge(chunks[t]);
+            plan.reserve_for(chunks);
+            for (unsigned t = 0; t < hw; ++t) plan.merge(std::move(chunks[t]));
         } else {
             for (uint32_t i = 0; i < n; ++i) plan.add_request(request_json[i] ? request_json[i] : "");
         }

@@ -190,9 +190,17 @@ struct BatchPlan {
         return id;
     }
 
+    // Room for the merged tables of `chunks`, so that merging does not reallocate.
+    void reserve_for(const std::vector<BatchPlan>& chunks) {
+        size_t n_parts = 0, n_leaf = 0, n_prog = 0, n_boost = 0, n_req = 0;
+        for (auto& c : chunks) n_parts += c.parts.size(), n_leaf += c.leaf_part.size(), n_prog += c.prog.size(), n_boost += c.boosts.size(), n_req += c.requests.size();
+        parts.reserve(n_parts), part_dict.reserve(n_parts), part_index.reserve(n_parts);
+        leaf_part.reserve(n_leaf), prog.reserve(n_prog), boosts.reserve(n_boost), programs.reserve(n_req), requests.reserve(n_req);
+    }
+
     // Appends the plan of another chunk of the same batch (built on another thread): its parts are unified with the
     // parts already known, its tables are appended with their indexes shifted.
-    void merge(const BatchPlan& o) {
+    void merge(BatchPlan&& o) {
         std::vector<uint32_t> dict_map(o.dict_names.size()), post_map(o.postings_names.size()), part_map(o.parts.size());
         for (size_t i = 0; i < o.dict_names.size(); ++i) dict_map[i] = dict_id(o.dict_names[i]);
         for (size_t i = 0; i < o.postings_names.size(); ++i) post_map[i] = postings_id(o.postings_names[i]);
@@ -211,8 +219,7 @@ struct BatchPlan {
             const uint32_t id = (uint32_t)parts.size();
             parts.push_back(q);
             part_dict.push_back(dict_map[o.part_dict[i]]);
-            part_index.emplace(o.part_keys[i], id);
-            part_keys.push_back(o.part_keys[i]);
+            part_index.emplace(std::move(o.part_keys[i]), id);  // (the merged plan does not keep part_keys: it is never merged again)
             part_map[i] = id;
         }
         const uint32_t leaf_base = (uint32_t)leaf_part.size(), prog_base = (uint32_t)prog.size(), boost_base = (uint32_t)boosts.size(), facet_base = (uint32_t)facets.size();
@@ -244,7 +251,7 @@ struct BatchPlan {
             QueryProgram qp = o.programs[i];
             if (qp.active) qp.leaf_begin += leaf_base, qp.prog_begin += prog_base, qp.boost_begin += boost_base, qp.post_begin += prog_base, qp.facet_begin += facet_base;
             programs.push_back(qp);
-            requests.push_back(o.requests[i]);
+            requests.push_back(std::move(o.requests[i]));
             requests.back().facet_begin += facet_base;
         }
         max_leaves = std::max(max_leaves, o.max_leaves);
