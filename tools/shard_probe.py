@@ -1,5 +1,7 @@
+"""Times execute_begin / execute_finish of the bench workload on one GPU for an unsharded index and for shard 0 of 8."""
 import os, sys, time, json
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench, helpers, veloci_b200
 class A: pass
 args = A(); args.docs=10_000_000; args.vocab=1_000_000; args.queries=10_000; args.cache="/tmp/veloci_b200_bench"

@@ -455,13 +455,6 @@ struct BatchPlan {
         for (auto& q : r.queries) collect_keys(q, out);
     }
 
-    static bool has_nested_boost(const vhost::SearchRequest& r) {
-        if (r.get_boost() && !r.get_boost()->empty()) return true;
-        for (auto& q : r.queries)
-            if (has_nested_boost(q)) return true;
-        return false;
-    }
-
     void plan_request(const vhost::Request& request, RequestPlan& rp, QueryProgram& qp) {
         rp.top = request.top.value_or(10);  // search.rs:146
         rp.skip = request.skip.value_or(0);
