@@ -172,3 +172,54 @@ def test_one_to_n_boosts(test_all):  # tests/all/tests.rs:839-931 (BoostToAnchor
         {"search_req": {"or": {"queries": [S("awesome", "field1[].text"), S("意慾", "kanji[].text", levenshtein_distance=1)]}},
          "boost": [{"path": "field1[].rank", "boost_fun": "Multiply"}, {"path": "kanji[].commonness", "boost_fun": "Add", "param": 2}, {"path": "commonness", "boost_fun": "Log2", "param": 2}]},
     ])
+
+
+def _jmdict_request(term, lev):  # benches/bench_jmdict.rs:115-235, verbatim shape
+    def part(path, boosts, starts_with):
+        p = {"terms": [term], "path": path, "levenshtein_distance": lev, "options": {"boost": boosts}}
+        if starts_with:
+            p["starts_with"] = True
+        return {"search": p}
+    c1 = {"path": "commonness", "boost_fun": "Log10", "param": 1}
+    return {"search_req": {"or": {"queries": [
+        part("kanji[].text", [c1, {"path": "kanji[].commonness", "boost_fun": "Log10", "param": 1}], True),
+        part("kana[].text", [c1, {"path": "kana[].commonness", "boost_fun": "Log10", "param": 1}], True),
+        part("kana[].text", [c1, {"path": "kana[].commonness", "boost_fun": "Log10", "param": 1}], True),
+        part("meanings.ger[].text", [{"path": "commonness", "boost_fun": "Log10", "param": 0}, {"path": "meanings.ger[].rank", "expression": "10 / $SCORE"}], False),
+        part("meanings.eng[]", [c1], False),
+    ], "options": {"top": 10, "skip": 0}}}}
+
+
+def test_config1_jmdict_shape(gpu, native_libs):  # BASELINE config 1: jmdict-shaped corpus, the 5-way OR of bench_jmdict
+    rng = np.random.default_rng(7)
+    syll = ["ka", "ki", "ku", "ke", "ko", "sa", "shi", "su", "ta", "chi", "to", "na", "ni", "no", "ma", "mi", "mo", "ra", "ri", "ru"]
+    words = ["".join(rng.choice(syll, size=int(rng.integers(2, 5)))) for _ in range(600)]
+    eng = ["will", "urge", "house", "water", "test", "light", "dark", "river", "stone", "tree", "majesty", "appearance", "long", "torso"]
+    docs = []
+    for i in range(2500):
+        d = {"ent_seq": str(100000 + i)}
+        if rng.random() < 0.7:
+            d["commonness"] = int(rng.integers(1, 3000))
+        # at most one boosted value per 1:n field and document: with several, the reference's merge join
+        # (boost.rs:255-281) applies the first or all of them depending on the position in the hit list, see DESIGN.md section 8
+        def values(texts, key, lo, hi):
+            boosted = int(rng.integers(0, len(texts) + 1))
+            return [{"text": t, **({key: int(rng.integers(lo, hi))} if i == boosted else {})} for i, t in enumerate(texts)]
+        if rng.random() < 0.8:
+            d["kanji"] = values([str(rng.choice(words)) for _ in range(int(rng.integers(1, 3)))], "commonness", 1, 500)
+        d["kana"] = values([str(rng.choice(words)) for _ in range(int(rng.integers(1, 3)))], "commonness", 1, 500)
+        d["meanings"] = {
+            "ger": values([" ".join(rng.choice(words, size=int(rng.integers(1, 4)))) for _ in range(int(rng.integers(0, 3)))], "rank", 1, 10),
+            "eng": [" ".join(rng.choice(eng, size=int(rng.integers(1, 4)))) for _ in range(int(rng.integers(1, 3)))],
+        }
+        docs.append(d)
+    config = {
+        "kanji[].text": {"fulltext": {"tokenize": True}}, "kana[].text": {"fulltext": {"tokenize": True}},
+        "meanings.ger[].text": {"fulltext": {"tokenize": True}}, "meanings.eng[]": {"fulltext": {"tokenize": True}},
+        "commonness": dict(fx.BOOST), "kanji[].commonness": dict(fx.BOOST), "kana[].commonness": dict(fx.BOOST), "meanings.ger[].rank": dict(fx.BOOST),
+    }
+    index, oracle = _pair(gpu, docs, config)
+    terms = [str(w) for w in rng.choice(words, size=25)] + [str(w)[:3] for w in rng.choice(words, size=10)] + ["will", "urge", "wate", "majesty"]
+    reqs = [_jmdict_request(t, lev) for t in terms for lev in (0, 1)]
+    b = compare(index, oracle, reqs)
+    assert sum(b.result(q)["num_hits"] for q in range(len(reqs))) > 0

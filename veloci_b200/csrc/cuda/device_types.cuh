@@ -182,6 +182,29 @@ struct SliceRec {  // 32 B
 };
 static const uint32_t kTaskPostings = 128;  // postings one warp takes from a slice at a time
 
+// ---- boosts (boost.rs:283-377, 470-504) ----
+enum BoostFunDev : uint32_t { kBoostNone = 0, kBoostLog2 = 1, kBoostLog10 = 2, kBoostMultiply = 3, kBoostAdd = 4, kBoostReplace = 5 };
+enum ExprOp : uint32_t { kExprNone = 0, kExprDiv = 1, kExprMul = 2, kExprAdd = 3, kExprSub = 4 };
+
+struct BoostStep {  // add_boost on anchor ids (boost.rs:470-504, apply_boost :283-377)
+    const uint32_t* column;
+    uint32_t n;
+    uint32_t fun;
+    float param;
+    uint32_t n_skip;
+    float skip[4];
+    uint32_t expr_op;       // `x op y` expression, operands: $SCORE (= boost value) or a float
+    uint32_t expr_left_is_score, expr_right_is_score;
+    float expr_left, expr_right;
+    // upper bound of the multiplier this step can apply (Log10/Log2/Multiply over a non-negative column):
+    // lets the tile kernel skip the gather for anchors that cannot reach the running k-th best
+    uint32_t can_prune;
+    float max_mult;
+    const ColumnLevels* levels;  // level bitmaps of the column (nullptr: none)
+    uint32_t list_only;          // a 1:n boost: applied by kOpLeafBoost with the value id a list part supplies, never per anchor
+    uint32_t pad;
+};
+
 // ---- list producers: anchors (with a value) computed from the matched terms of search parts ----
 struct PhraseView {  // persistence_data_binary_search.rs:126-203, flattened
     const uint64_t* keys;     // sorted (term1 << 32 | term2)
@@ -227,7 +250,8 @@ enum ProgOp : uint32_t {
     kOpUnion = 2,      // [op, n children, n slots, slot of child 0 .. n-1]      set_op.rs:87-220
     kOpIntersect = 3,  // [op, n children, sum order: child index 0 .. n-1]      set_op.rs:368-446
     kOpFilter = 4,     // [op]: (search result, filter result) -> search result where the filter is present   set_op.rs:311-326
-    kOpLeafBoost = 5,  // [op, leaf, list leaf, boost step]: the leaf, boosted by the list's value for the anchor   plan_steps.rs:173-233 (BoostToAnchor + ApplyAnchorBoost)
+    kOpLeafBoost = 5,  // [op, leaf, list leaf, boost step]: the leaf, boosted with the boost value of the list's value id for the anchor
+                       // (BoostToAnchor + ApplyAnchorBoost, plan_steps.rs:173-233)
 };
 
 // Steps that run on every hit after the request tree and the column boosts, in the reference's order
@@ -246,25 +270,6 @@ struct FacetStep {
     uint32_t* hist;  // [hist_size] counts of this (request, facet)
 };
 
-enum BoostFunDev : uint32_t { kBoostNone = 0, kBoostLog2 = 1, kBoostLog10 = 2, kBoostMultiply = 3, kBoostAdd = 4, kBoostReplace = 5 };
-enum ExprOp : uint32_t { kExprNone = 0, kExprDiv = 1, kExprMul = 2, kExprAdd = 3, kExprSub = 4 };
-
-struct BoostStep {  // add_boost on anchor ids (boost.rs:470-504, apply_boost :283-377)
-    const uint32_t* column;
-    uint32_t n;
-    uint32_t fun;
-    float param;
-    uint32_t n_skip;
-    float skip[4];
-    uint32_t expr_op;       // `x op y` expression, operands: $SCORE (= boost value) or a float
-    uint32_t expr_left_is_score, expr_right_is_score;
-    float expr_left, expr_right;
-    // upper bound of the multiplier this step can apply (Log10/Log2/Multiply over a non-negative column):
-    // lets the tile kernel skip the gather for anchors that cannot reach the running k-th best
-    uint32_t can_prune;
-    float max_mult;
-    const ColumnLevels* levels;  // level bitmaps of the column (nullptr: none)
-};
 
 struct alignas(16) QueryProgram {  // 96 B
     uint32_t leaf_begin, n_leaves;  // into the leaf -> part table

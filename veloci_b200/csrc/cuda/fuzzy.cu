@@ -714,7 +714,10 @@ void launch_text_locality(cudaStream_t st, const TlInstance* inst, uint32_t n_in
     count_launch();
 }
 
-// One block per member: every matched token -> its text ids -> their parent value ids -> boost value and anchor.
+// One block per member: every matched token -> its text ids -> their parent value ids -> those with a boost value, filed
+// under their anchor.  apply_boost_values_anchor (boost.rs:255-281) walks the (anchor, value) list, which is in value-id
+// order, next to the hits: of several values of one anchor only the first is applied, so the entry carries the value id
+// (complemented: the tile scatter keeps the maximum key = the smallest value id).
 __global__ void __launch_bounds__(128) boost_to_anchor_kernel(const BoostListMember* __restrict__ members, ListArgs a) {
     const BoostListMember m = members[blockIdx.x];
     if (!m.tokenized && !m.use_ids) return;
@@ -733,11 +736,10 @@ __global__ void __launch_bounds__(128) boost_to_anchor_kernel(const BoostListMem
             for (uint32_t j = m.value_id_to_parent.off[text]; j < m.value_id_to_parent.off[text + 1]; ++j) {
                 const uint32_t value_id = m.value_id_to_parent.val[j];
                 if (value_id >= m.column_n || value_id >= m.value_id_to_anchor.n_ids) continue;
-                const uint32_t bits = m.column[value_id];
-                if (bits == kNoValue) continue;
+                if (m.column[value_id] == kNoValue) continue;
                 const uint32_t o = m.value_id_to_anchor.off[value_id];
                 if (m.value_id_to_anchor.off[value_id + 1] == o) continue;
-                list_emit(a, m.list_part, m.value_id_to_anchor.val[o], vbit::score_key(__uint_as_float(bits)));
+                list_emit(a, m.list_part, m.value_id_to_anchor.val[o], ~value_id);
             }
         }
     }

@@ -231,7 +231,11 @@ __device__ bool eval_program(const uint32_t* __restrict__ prog, uint32_t len, co
             pr[sp] = key != 0;
             sc[sp] = key ? vbit::key_score(key) : 0.0f;
             const uint32_t bkey = arr[prog[pc + 2] * tile + idx];
-            if (key && bkey) sc[sp] = apply_boost_step(boosts[prog[pc + 3]], sc[sp], vbit::key_score(bkey));
+            if (key && bkey) {  // the list leaf holds the complement of the anchor's first boosted value id
+                const BoostStep& bs = boosts[prog[pc + 3]];
+                const uint32_t bits = __ldg(bs.column + (~bkey));
+                if (bits != kNoValue) sc[sp] = apply_boost_step(bs, sc[sp], __uint_as_float(bits));
+            }
             ++sp;
             pc += 4;
         } else if (op == kOpFilter) {
@@ -298,7 +302,7 @@ __device__ __forceinline__ uint32_t finish_anchor(const TileArgs& a, const ItemC
                 const BoostStep& bs = a.boosts[c.qp.boost_begin + b];
                 bool skip = false;
                 for (uint32_t i = 0; i < bs.n_skip; ++i) skip = skip || fabsf(bs.skip[i] - score) < 0.00001f;
-                if (skip || anchor >= bs.n) continue;
+                if (skip || bs.list_only || anchor >= bs.n) continue;
                 const uint32_t bits = __ldg(bs.column + anchor);
                 if (bits != kNoValue) score = apply_boost_step(bs, score, __uint_as_float(bits));
             }
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
         c.col = nullptr, c.col_n = 0, c.fun = 0, c.param = 0.0f, c.prune_below = 0.0f;
         if (qp.n_boosts == 1) {
             const BoostStep& bs = a.boosts[qp.boost_begin];
-            if (bs.n_skip == 0 && bs.expr_op == kExprNone) {
+            if (bs.n_skip == 0 && bs.expr_op == kExprNone && !bs.list_only) {
                 c.fast_boost = true;
                 c.col = bs.column, c.col_n = bs.n, c.fun = bs.fun, c.param = bs.param;
                 if (bs.can_prune != 0 && !qp.emit_all && qp.k != 0 && c.tau != 0 && bs.max_mult > 0.0f && qp.post_len == 0 && qp.n_facets == 0) {

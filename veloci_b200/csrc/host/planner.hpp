@@ -332,8 +332,10 @@ struct BatchPlan {
                         boost_members.push_back(m);
                         BoostStep step;
                         memset(&step, 0, sizeof step);
+                        step.column = col->second.bits.p, step.n = (uint32_t)col->second.n;
                         step.fun = (uint32_t)found->boost_fun;
                         step.param = found->param.value_or(0.0f);
+                        step.list_only = 1;
                         if (found->expression) parse_expression(*found->expression, step);
                         const uint32_t step_index = (uint32_t)cur_steps->size();
                         cur_steps->push_back(step);
@@ -444,7 +446,7 @@ struct BatchPlan {
     // a single boost step without skip list or expression travels inside the QueryProgram
     static void set_fast_boost(QueryProgram& qp, const std::vector<BoostStep>& steps) {
         qp.fb_flags = 0;
-        if (steps.size() != 1 || steps[0].n_skip != 0 || steps[0].expr_op != vdev::kExprNone) return;
+        if (steps.size() != 1 || steps[0].n_skip != 0 || steps[0].expr_op != vdev::kExprNone || steps[0].list_only) return;
         const BoostStep& s = steps[0];
         qp.fb_flags = 1u | ((s.can_prune && s.max_mult > 0.0f) ? 2u : 0u);
         qp.fb_col = s.column, qp.fb_lev = s.levels, qp.fb_n = s.n, qp.fb_fun = s.fun, qp.fb_param = s.param, qp.fb_max_mult = s.max_mult;
@@ -471,8 +473,8 @@ struct BatchPlan {
             for (auto& pb : *request.phrase_boosts) cur_ids_keys.push_back(pb.search1.key()), cur_ids_keys.push_back(pb.search2.key());
         if (request.filter) collect_keys(*request.filter, cur_ids_keys);
         {
-            std::vector<vhost::BoostPart> top = request.boost.value_or(std::vector<vhost::BoostPart>());
-            if (root.get_boost()) top.insert(top.end(), root.get_boost()->begin(), root.get_boost()->end());
+            // the request's boosts go down the tree; sub-queries add their own options (execution_plan.rs:263-270), the root's own do not apply
+            const std::vector<vhost::BoostPart> top = request.boost.value_or(std::vector<vhost::BoostPart>());
             emit(root, leaves, code, false, top);
         }
         const std::vector<TlTerm> tree_terms = tl_seen;
