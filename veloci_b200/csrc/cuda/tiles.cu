@@ -191,8 +191,91 @@ __device__ __forceinline__ float apply_boost_step(const BoostStep& b, float scor
     return score;
 }
 
+// ApplyAnchorBoost for an anchor with a 1:n boost (apply_boost_values_anchor, boost.rs:255-281).  The reference walks the
+// part's hits and the (anchor, value) list, both ascending, with one look-ahead element; the effect is: along a run of
+// consecutive hits that all have boost values, the first hit takes only its first value, the second all of its values,
+// the third only the first again, ...  So an anchor with several values takes all of them exactly when the number of
+// boosted hits directly before it (in the part's hit order) is odd.  Its predecessors are found in the posting lists of
+// the part's matched terms, their boost entries in the list part's tile buckets.
+struct LeafBoostGlobals {  // the batch tables the rule needs; one copy per CTA in shared memory
+    const uint32_t* bucket;
+    const SparseEntry* sparse;
+    const PartSlices* slices;
+    const PostingsView* postings;
+    const PartQuery* parts;
+    const uint64_t* g_begin;
+    const uint32_t* g_df;
+    const uint32_t* leaf_part;
+    uint32_t n_tiles, tile_log2, anchor_lo, pad;
+};
+struct LeafBoostCtx {
+    uint32_t part, list_part;   // the search part and the list part that holds its (anchor, ~value id) entries
+    uint32_t anchor;
+};
+
+__device__ __noinline__ float apply_leaf_boost(const LeafBoostGlobals* gp, LeafBoostCtx x, const BoostStep* bsp, float score, uint32_t first_vid) {
+    const LeafBoostGlobals& a = *gp;
+    const BoostStep& bs = *bsp;
+    const uint32_t* brow = a.bucket + (size_t)x.list_part * (a.n_tiles + 1);
+    const SparseEntry* ent = a.sparse + a.slices[x.list_part].sparse_base;
+    auto boosted = [&](uint32_t anchor, uint32_t* vids, uint32_t cap) -> uint32_t {  // distinct value ids of the anchor, ascending
+        const uint32_t t = (anchor - a.anchor_lo) >> a.tile_log2;
+        uint32_t n = 0;
+        for (uint32_t i = brow[t]; i < brow[t + 1]; ++i) {
+            if (ent[i].anchor != anchor) continue;
+            const uint32_t v = ~ent[i].key;
+            uint32_t at = 0;
+            bool dup = false;
+            while (at < n && vids[at] <= v) dup = dup || vids[at] == v, ++at;
+            if (dup) continue;
+            if (n < cap) {
+                for (uint32_t j = n; j > at; --j) vids[j] = vids[j - 1];
+                vids[at] = v;
+                ++n;
+            }
+        }
+        return n;
+    };
+    uint32_t vids[8];
+    const uint32_t n_vids = boosted(x.anchor, vids, 8);
+    bool all = false;
+    if (n_vids > 1) {
+        // how many hits of the part directly before this anchor have boost values?
+        const PartSlices ps = a.slices[x.part];
+        const PostingsView pv = a.postings[a.parts[x.part].postings];
+        uint32_t cur = x.anchor, run = 0;
+        while (true) {
+            uint32_t pred = 0;
+            bool found = false;
+            for (uint32_t r = 0; r < ps.n_match; ++r) {  // largest anchor below `cur` over the matched terms' posting lists
+                const Posting* post = pv.post + a.g_begin[ps.m_begin + r];
+                uint32_t lo = 0, hi = a.g_df[ps.m_begin + r];
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (post[mid].anchor < cur) lo = mid + 1;
+                    else hi = mid;
+                }
+                if (lo > 0 && (!found || post[lo - 1].anchor > pred)) pred = post[lo - 1].anchor, found = true;
+            }
+            if (!found) break;
+            uint32_t tmp[1];
+            if (boosted(pred, tmp, 1) == 0) break;
+            ++run, cur = pred;
+        }
+        all = (run & 1u) != 0;
+    }
+    const uint32_t n_apply = all ? n_vids : 1u;
+    for (uint32_t i = 0; i < n_apply; ++i) {
+        const uint32_t vid = n_vids ? vids[i] : first_vid;
+        const uint32_t bits = __ldg(bs.column + vid);
+        if (bits != kNoValue) score = apply_boost_step(bs, score, __uint_as_float(bits));
+    }
+    return score;
+}
+
 // Generic request tree, postfix.  Returns presence; score in `out`.
-__device__ bool eval_program(const uint32_t* __restrict__ prog, uint32_t len, const uint32_t* arr, uint32_t tile, uint32_t idx, const BoostStep* __restrict__ boosts, float& out) {
+__device__ bool eval_program(const uint32_t* __restrict__ prog, uint32_t len, const uint32_t* arr, uint32_t tile, uint32_t idx, const BoostStep* __restrict__ boosts,
+                             const LeafBoostGlobals* lb, uint32_t leaf_begin, uint32_t anchor, float& out) {
     float sc[kMaxLeaves];
     bool pr[kMaxLeaves];
     int sp = 0;
@@ -232,9 +315,9 @@ __device__ bool eval_program(const uint32_t* __restrict__ prog, uint32_t len, co
             sc[sp] = key ? vbit::key_score(key) : 0.0f;
             const uint32_t bkey = arr[prog[pc + 2] * tile + idx];
             if (key && bkey) {  // the list leaf holds the complement of the anchor's first boosted value id
-                const BoostStep& bs = boosts[prog[pc + 3]];
-                const uint32_t bits = __ldg(bs.column + (~bkey));
-                if (bits != kNoValue) sc[sp] = apply_boost_step(bs, sc[sp], __uint_as_float(bits));
+                LeafBoostCtx x;
+                x.part = lb->leaf_part[leaf_begin + prog[pc + 1]], x.list_part = lb->leaf_part[leaf_begin + prog[pc + 2]], x.anchor = anchor;
+                sc[sp] = apply_leaf_boost(lb, x, boosts + prog[pc + 3], sc[sp], ~bkey);
             }
             ++sp;
             pc += 4;
@@ -272,6 +355,7 @@ struct ItemCtx {
     uint32_t col_n, fun;
     float param;
     float prune_below;  // scores below this cannot reach the k-th best even with the largest boost multiplier
+    const LeafBoostGlobals* lb;
 };
 
 // Everything after the request tree for one present anchor: boosts, threshold, survivor list.
@@ -379,7 +463,7 @@ __device__ __forceinline__ uint32_t eval_idx(const TileArgs& a, const ItemCtx& c
         }
         score = (L == 1 && !c.qp.union1) ? vbit::key_score(arr[idx]) : sum * nd * nd;
     } else {
-        present = eval_program(a.prog + c.qp.prog_begin, c.qp.prog_len, arr, c.tile, idx, a.boosts + c.qp.boost_begin, score);
+        present = eval_program(a.prog + c.qp.prog_begin, c.qp.prog_len, arr, c.tile, idx, a.boosts + c.qp.boost_begin, c.lb, c.qp.leaf_begin, c.tile_base + idx, score);
     }
     uint32_t keep = 0;
     if (present) keep = finish_anchor(a, c, c.tile_base + idx, score, s_nsurv, s_list, arr + idx, c.tile);
@@ -492,6 +576,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
     __shared__ unsigned long long s_heap[kMaxK];
     __shared__ unsigned long long s_out[kMaxK];
     __shared__ uint32_t s_claim[1024];  // one bit per anchor of the tile (tiles up to 2^15)
+    __shared__ LeafBoostGlobals s_lb;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t n_warps = kTileThreads / 32;
@@ -502,6 +587,9 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
         for (uint32_t i = tid; i < n4; i += kTileThreads) p4[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
+        s_lb.bucket = a.bucket, s_lb.sparse = a.sparse, s_lb.slices = a.slices, s_lb.postings = a.postings, s_lb.parts = a.parts;
+        s_lb.g_begin = a.g_begin, s_lb.g_df = a.g_df, s_lb.leaf_part = a.leaf_part;
+        s_lb.n_tiles = a.n_tiles, s_lb.tile_log2 = a.tile_log2, s_lb.anchor_lo = a.anchor_lo, s_lb.pad = 0;
         const unsigned long long first = atomicAdd(a.work_counter, 1ull);
         s_item_idx[0] = first;
         if (first < a.n_items) s_item[0] = a.items[first];
@@ -523,6 +611,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
 
         const uint32_t t = it.t, q = it.q;
         ItemCtx c;
+        c.lb = &s_lb;
         c.qp = a.queries[q];
         const QueryProgram& qp = c.qp;
         const uint32_t L = qp.n_leaves;
