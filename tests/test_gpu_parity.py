@@ -309,3 +309,41 @@ def test_sharded_index_equals_unsharded(gpu, native_libs):
         assert (got["num_hits"] == whole["num_hits"]).all()
         assert (got["ids"] == whole["ids"]).all()
         assert (got["scores"].view(np.uint32) == whole["scores"].view(np.uint32)).all()
+
+
+def test_edge_requests(small):
+    """Boundary shapes of the request surface on the bench-shaped index: no hits, top 0, skip past the end, many parts,
+    long and non-ASCII terms, a part repeated many times, distance larger than the term."""
+    index, oracle, _ = small
+    words = [json.loads(r)["search_req"]["search"]["terms"][0] for r in helpers.synthetic_requests(num_queries=14, query_kind="single", query_seed=21, **SMALL)]
+    P = lambda w, **kw: {"search": {"terms": [w], "path": "body", **kw}}
+    boost = [{"path": "commonness", "boost_fun": "Log10", "param": 1}]
+    reqs = [
+        {"search_req": P("zzzzzzzzzzzzqqqq")},                                             # no term matches
+        {"search_req": P(words[0]), "top": 0},                                              # only the count
+        {"search_req": P("zzzzzzzzzzzzqqqq", levenshtein_distance=1), "top": 5, "skip": 250},   # skip past every hit
+        {"search_req": P(words[2]), "top": 64, "boost": boost},                             # largest k of the plane path
+        {"search_req": P(words[2]), "top": 65, "boost": boost},                             # first k of the general path
+        {"search_req": P(words[3]), "top": 200, "skip": 56},                                # k = 256
+        {"search_req": {"or": {"queries": [P(w) for w in words[:12]]}}, "boost": boost},    # 12 parts
+        {"search_req": {"or": {"queries": [P(words[4])] * 6}}},                             # one part six times
+        {"search_req": {"and": {"queries": [P(words[5]), P(words[5])]}}},                   # intersection with itself
+        {"search_req": P("ab", levenshtein_distance=5)},                                    # distance clamped to len - 1
+        {"search_req": P("a" * 64, levenshtein_distance=2)},                                # longest supported term
+        {"search_req": P("größe", levenshtein_distance=1)},                                 # scalars outside the dictionary alphabet
+        {"search_req": P("日本語", levenshtein_distance=1)},
+        {"search_req": {"or": {"queries": [P(words[6], boost=0.5), P(words[7], boost=3.0), P(words[8])]}}, "boost": boost},
+        {"search_req": {"or": {"queries": [{"and": {"queries": [P(words[9]), P(words[10])]}}, {"or": {"queries": [P(words[11]), P(words[12])]}}]}}},
+    ]
+    texts = [json.dumps(r, ensure_ascii=False) for r in reqs]
+    b = index.prepare(texts).execute()
+    for q, r in enumerate(texts):
+        assert b.status(q) == 0, (r, b.message(q))
+        g = b.result(q, cap=256)
+        c = oracle.search(r)
+        assert g["num_hits"] == c["num_hits"], r
+        assert_same_topk(g["data"], [(h[0], np.float32(h[1])) for h in c["data"]], ctx=r)
+    # an empty batch and a batch whose every request fails are not errors of the call
+    assert index.prepare([]).execute().n == 0
+    bad = index.prepare(["{", json.dumps({"top": 1})]).execute()
+    assert [bad.status(0), bad.status(1)] == [5, 1]
