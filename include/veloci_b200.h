@@ -119,6 +119,10 @@ int32_t vgpu_batch_execute_begin(vgpu_batch* batch);
 int32_t vgpu_batch_thresholds(const vgpu_batch* batch, uint64_t** tau_dev, uint32_t* n);
 int32_t vgpu_batch_execute_finish(vgpu_batch* batch);
 int32_t vgpu_batch_merge_gathered(vgpu_batch* batch, const uint64_t* gathered_keys_dev, const uint64_t* gathered_num_hits_dev, uint32_t n_shards);
+/* Facets on shards: after execute every shard holds the counts of its anchors in one device array of u32 (all facet
+ * histograms of the batch, back to back; NULL / 0 when the batch has no facets).  The host all-reduces the arrays with SUM
+ * before vgpu_batch_merge_gathered, which then picks the top groups of the summed histograms on every rank. */
+int32_t vgpu_batch_facet_histograms(const vgpu_batch* batch, uint32_t** hist_dev, uint64_t* n);
 
 /* ---- step seam -------------------------------------------------------------
  * One symbol per PlanStep kind (src/plan_creator/plan_steps.rs:18-74), each over host

@@ -276,11 +276,13 @@ def test_sharded_index_equals_unsharded(gpu, native_libs):
     import torch
 
     d = tempfile.mkdtemp(prefix="vb200_gpu_shards_")
-    params = dict(num_docs=90000, vocab=6000, seed=31)
+    params = dict(num_docs=90000, vocab=6000, seed=31, tags=30)
     helpers.create_synthetic_index(d, **params)
     reqs = helpers.synthetic_requests(num_queries=300, query_kind="or3", levenshtein=1, query_seed=8, **params)
-    reqs += helpers.synthetic_requests(num_queries=100, query_kind="and", levenshtein=1, query_seed=9, **params)
-    whole = gpu.Index(d).search_batch(reqs, k=10)
+    reqs += helpers.synthetic_requests(num_queries=100, query_kind="and", levenshtein=1, query_seed=9, **params)  # with facets on tags[]
+    assert "facets" in reqs[-1]
+    whole_batch = gpu.Index(d).prepare(reqs).execute()
+    whole = whole_batch.results_flat(10)
     shards = [gpu.Index(d, shard_rank=r, n_shards=2) for r in range(2)]
     batches = [s.prepare(reqs) for s in shards]
     keys, hits = [], []
@@ -302,6 +304,15 @@ def test_sharded_index_equals_unsharded(gpu, native_libs):
         keys.append(torch.as_tensor(_DevArray(kp, len(reqs) * stride), device="cuda").clone())
         hits.append(torch.as_tensor(_DevArray(hp, len(reqs)), device="cuda").clone())
     g_keys, g_hits = torch.cat(keys), torch.cat(hits)
+    # facet histograms: summed over the shards (all-reduce SUM), written back to every shard
+    hists = []
+    for b in batches:
+        ptr, cnt = b.facet_histograms()
+        assert cnt > 0  # (the array has one pad word when the histograms' total is even; it is dropped or harmlessly summed)
+        hists.append(torch.as_tensor(_DevArray(ptr, cnt // 2), device="cuda").view(torch.int32))
+    total = hists[0] + hists[1]
+    for h in hists:
+        h.copy_(total)
     torch.cuda.synchronize()
     for b in batches:  # every rank merges the same gathered buffers
         b.merge_gathered(g_keys.data_ptr(), g_hits.data_ptr(), 2)
@@ -309,6 +320,8 @@ def test_sharded_index_equals_unsharded(gpu, native_libs):
         assert (got["num_hits"] == whole["num_hits"]).all()
         assert (got["ids"] == whole["ids"]).all()
         assert (got["scores"].view(np.uint32) == whole["scores"].view(np.uint32)).all()
+        for q in range(300, 400, 7):
+            assert b.result(q)["facets"] == whole_batch.result(q)["facets"]
 
 
 def test_edge_requests(small):

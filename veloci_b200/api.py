@@ -55,6 +55,7 @@ def load_library():
     L.vgpu_batch_execute_begin.argtypes = [vp]
     L.vgpu_batch_execute_finish.argtypes = [vp]
     L.vgpu_batch_thresholds.argtypes = [vp, P(vp), P(u32)]
+    L.vgpu_batch_facet_histograms.argtypes = [vp, P(vp), P(u64)]
     L.vgpu_batch_free.argtypes = [vp]
     L.vgpu_batch_free.restype = None
     L.vgpu_batch_status.argtypes = [vp, u32]
@@ -192,6 +193,12 @@ class Batch:
         """Device pointer and length of the per-request thresholds (64-bit order keys) after execute_begin."""
         ptr, n = ctypes.c_void_p(), ctypes.c_uint32()
         _check(self.L.vgpu_batch_thresholds(self.h, ctypes.byref(ptr), ctypes.byref(n)))
+        return ptr.value, int(n.value)
+
+    def facet_histograms(self):
+        """Device pointer and length (u32 words) of the batch's facet histograms (None, 0 without facets)."""
+        ptr, n = ctypes.c_void_p(), ctypes.c_uint64()
+        _check(self.L.vgpu_batch_facet_histograms(self.h, ctypes.byref(ptr), ctypes.byref(n)))
         return ptr.value, int(n.value)
 
     def local_topk(self):

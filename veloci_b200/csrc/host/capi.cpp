@@ -155,6 +155,13 @@ int32_t vgpu_batch_thresholds(const vgpu_batch* batch, uint64_t** tau_dev, uint3
     return VGPU_OK;
 }
 
+int32_t vgpu_batch_facet_histograms(const vgpu_batch* batch, uint32_t** hist_dev, uint64_t* n) {
+    if (!batch || !hist_dev || !n) return VGPU_ERR_INVALID_REQUEST;
+    *hist_dev = batch->b.n_facets ? batch->b.d_facet_hist.p : nullptr;
+    *n = batch->b.n_facets ? batch->b.d_facet_hist.n : 0;
+    return VGPU_OK;
+}
+
 int32_t vgpu_batch_execute_finish(vgpu_batch* batch) {
     if (!batch) return VGPU_ERR_INVALID_REQUEST;
     return guarded([&]() { batch->b.execute_finish(); });

@@ -315,7 +315,7 @@ struct Batch {
             uint64_t total = 0;
             for (auto& f : plan.facets) total += f.hist_size;
             if (total > (1ull << 30)) throw std::runtime_error("facet histograms of this batch exceed 4 GB");
-            d_facet_hist.alloc((size_t)total + 1);
+            d_facet_hist.alloc((size_t)total + 1 + (total & 1));  // even word count: the host may reduce it as 64-bit lanes
             uint64_t at = 0;
             facet_stride = 1;
             for (size_t i = 0; i < plan.facets.size(); ++i) {
@@ -691,6 +691,8 @@ struct Batch {
     void merge_gathered(const uint64_t* keys_dev, const uint64_t* hits_dev, uint32_t n_shards) {
         VDEV_CUDA(cudaSetDevice(ix->device));
         launch_merge_heaps(stream, keys_dev, hits_dev, n_shards, n, stride, d_programs.p, d_out_keys.p, d_out_hits.p);
+        // the caller has summed the shards' facet histograms (vgpu_batch_facet_histograms) by now: pick the groups again
+        if (n_facets) launch_facet_topk(stream, d_facets.p, d_facet_top.p, n_facets, facet_stride, d_facet_ids.p, d_facet_counts.p, d_facet_n.p);
         VDEV_CUDA(cudaStreamSynchronize(stream));
         fetched = false;
     }

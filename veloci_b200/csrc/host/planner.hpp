@@ -564,7 +564,6 @@ struct BatchPlan {
         }
         if (leaves.size() > vdev::kMaxLeaves) throw Unsupported("more than 12 search parts in one request");
         if (request.facets && !request.facets->empty()) {
-            if (ix->n_shards > 1) throw Unsupported("facets on a sharded index are not on the accelerated path yet");
             rp.facets = *request.facets;
             rp.has_facets = true;
             rp.facet_begin = (uint32_t)facets.size();
