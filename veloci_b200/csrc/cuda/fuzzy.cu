@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(128) phrase_pairs_kernel(const PhraseMember* _
 __global__ void __launch_bounds__(128) ids_to_anchor_kernel(const IdsMember* __restrict__ members, ListArgs a) {
     const IdsMember m = members[blockIdx.x];
     const uint32_t b = a.part_begin[m.part], n = a.part_begin[m.part + 1] - b;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const uint32_t id = a.g_term[b + i];
         if (m.identity) {
             list_emit(a, m.list_part, id, 0x80000000u);
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(128) ids_to_anchor_kernel(const IdsMember* __r
 
 void launch_ids_to_anchor(cudaStream_t st, const IdsMember* members, uint32_t n_members, const ListArgs& a) {
     if (!n_members) return;
-    ids_to_anchor_kernel<<<n_members, 128, 0, st>>>(members, a);
+    ids_to_anchor_kernel<<<dim3(n_members, 4), 128, 0, st>>>(members, a);
     count_launch();
 }
 
@@ -722,7 +722,11 @@ __global__ void __launch_bounds__(128) boost_to_anchor_kernel(const BoostListMem
     const BoostListMember m = members[blockIdx.x];
     if (!m.tokenized && !m.use_ids) return;
     const uint32_t b = a.part_begin[m.part], n = a.part_begin[m.part + 1] - b;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    // The member's 32 warps share the texts of every matched token (32 texts per warp and step); the value ids of a text
+    // are walked by its lane, or by the whole warp when there are many (a frequent token is in tens of thousands of texts,
+    // a frequent text the value of as many documents).
+    const uint32_t lane = threadIdx.x & 31u, warps = (blockDim.x >> 5) * gridDim.y, warp = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (uint32_t i = 0; i < n; ++i) {  // every warp visits every token and takes its share of the token's texts
         const uint32_t token = a.g_term[b + i];
         uint32_t t0 = 0, t1 = 1;  // text ids: the token's row, or the token itself
         bool self = true;
@@ -730,16 +734,29 @@ __global__ void __launch_bounds__(128) boost_to_anchor_kernel(const BoostListMem
             const uint32_t o0 = m.tokens_to_text_id.off[token], o1 = m.tokens_to_text_id.off[token + 1];
             if (o1 > o0) t0 = o0, t1 = o1, self = false;
         }
-        for (uint32_t t = t0; t < t1; ++t) {
-            const uint32_t text = self ? token : m.tokens_to_text_id.val[t];
-            if (text >= m.value_id_to_parent.n_ids) continue;
-            for (uint32_t j = m.value_id_to_parent.off[text]; j < m.value_id_to_parent.off[text + 1]; ++j) {
+        for (uint32_t tb = t0 + 32u * ((warp + warps - i % warps) % warps); tb < t1; tb += 32u * warps) {
+            uint32_t j0 = 0, j1 = 0;  // this lane's text: its value ids
+            if (tb + lane < t1) {
+                const uint32_t text = self ? token : m.tokens_to_text_id.val[tb + lane];
+                if (text < m.value_id_to_parent.n_ids) j0 = m.value_id_to_parent.off[text], j1 = m.value_id_to_parent.off[text + 1];
+            }
+            auto emit_value = [&](uint32_t j) {
                 const uint32_t value_id = m.value_id_to_parent.val[j];
-                if (value_id >= m.column_n || value_id >= m.value_id_to_anchor.n_ids) continue;
-                if (m.column[value_id] == kNoValue) continue;
+                if (value_id >= m.column_n || value_id >= m.value_id_to_anchor.n_ids) return;
+                if (m.column[value_id] == kNoValue) return;
                 const uint32_t o = m.value_id_to_anchor.off[value_id];
-                if (m.value_id_to_anchor.off[value_id + 1] == o) continue;
+                if (m.value_id_to_anchor.off[value_id + 1] == o) return;
                 list_emit(a, m.list_part, m.value_id_to_anchor.val[o], ~value_id);
+            };
+            const bool long_range = j1 - j0 > 16;
+            if (!long_range)  // few values: the lane walks its own text
+                for (uint32_t j = j0; j < j1; ++j) emit_value(j);
+            uint32_t todo = __ballot_sync(0xFFFFFFFFu, long_range);
+            while (todo) {  // many values: the warp walks the text together
+                const int src = __ffs((int)todo) - 1;
+                todo &= todo - 1;
+                const uint32_t r0 = __shfl_sync(0xFFFFFFFFu, j0, src), r1 = __shfl_sync(0xFFFFFFFFu, j1, src);
+                for (uint32_t j = r0 + lane; j < r1; j += 32) emit_value(j);
             }
         }
     }
@@ -747,7 +764,7 @@ __global__ void __launch_bounds__(128) boost_to_anchor_kernel(const BoostListMem
 
 void launch_boost_to_anchor(cudaStream_t st, const BoostListMember* members, uint32_t n_members, const ListArgs& a) {
     if (!n_members) return;
-    boost_to_anchor_kernel<<<n_members, 128, 0, st>>>(members, a);
+    boost_to_anchor_kernel<<<dim3(n_members, 8), 128, 0, st>>>(members, a);
     count_launch();
 }
 
