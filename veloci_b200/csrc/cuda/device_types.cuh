@@ -134,6 +134,8 @@ enum PartFlags : uint32_t {
     kPartCheckPrefix = 8u,    // starts_with || levenshtein != 0  (:302)
     kPartHasBoost = 16u,
     kPartList = 32u,          // not a search part: its tile bucket is filled by a list producer (phrase pairs, text locality, 1:n boosts)
+    kPartListBoost = 64u,     // list part of a 1:n boost: entries carry 0x7FFFFFFF - value id; the tile keeps the smallest value id of an
+                              // anchor plus (bit 31) whether the anchor has several
 };
 
 struct PartQuery {  // one distinct RequestSearchPart of the batch (272 B)
@@ -271,7 +273,7 @@ struct FacetStep {
 };
 
 
-struct alignas(16) QueryProgram {  // 96 B
+struct alignas(16) QueryProgram {  // 112 B
     uint32_t leaf_begin, n_leaves;  // into the leaf -> part table
     uint32_t prog_begin, prog_len;  // into the program words
     uint32_t boost_begin, n_boosts; // into the BoostStep table
@@ -288,7 +290,10 @@ struct alignas(16) QueryProgram {  // 96 B
     const ColumnLevels* fb_lev;     // level bitmaps of the fast-boost column (nullptr: none)
     uint32_t post_begin, post_len;  // post ops, into the program words
     uint32_t facet_begin, n_facets; // into the FacetStep table
+    uint32_t n_leaf_boosts;         // kOpLeafBoost ops in the program (at most kMaxLeafBoosts)
+    uint32_t pad2[3];
 };
-static_assert(sizeof(QueryProgram) == 96, "QueryProgram layout");
+static_assert(sizeof(QueryProgram) == 112, "QueryProgram layout");
+static const uint32_t kMaxLeafBoosts = 4;
 
 }  // namespace vdev

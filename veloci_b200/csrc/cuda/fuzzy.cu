@@ -716,8 +716,8 @@ void launch_text_locality(cudaStream_t st, const TlInstance* inst, uint32_t n_in
 
 // One block per member: every matched token -> its text ids -> their parent value ids -> those with a boost value, filed
 // under their anchor.  apply_boost_values_anchor (boost.rs:255-281) walks the (anchor, value) list, which is in value-id
-// order, next to the hits: of several values of one anchor only the first is applied, so the entry carries the value id
-// (complemented: the tile scatter keeps the maximum key = the smallest value id).
+// order, next to the hits, so the entry carries the value id (as 0x7FFFFFFF - id: the tile scatter keeps the largest key =
+// the smallest value id of an anchor, and notes in bit 31 whether the anchor has several).
 __global__ void __launch_bounds__(128) boost_to_anchor_kernel(const BoostListMember* __restrict__ members, ListArgs a) {
     const BoostListMember m = members[blockIdx.x];
     if (!m.tokenized && !m.use_ids) return;
@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(128) boost_to_anchor_kernel(const BoostListMem
                 if (m.column[value_id] == kNoValue) return;
                 const uint32_t o = m.value_id_to_anchor.off[value_id];
                 if (m.value_id_to_anchor.off[value_id + 1] == o) return;
-                list_emit(a, m.list_part, m.value_id_to_anchor.val[o], ~value_id);
+                if (value_id < 0x7FFFFFFEu) list_emit(a, m.list_part, m.value_id_to_anchor.val[o], 0x7FFFFFFFu - value_id);
             };
             const bool long_range = j1 - j0 > 16;
             if (!long_range)  // few values: the lane walks its own text

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
             if (e == s) continue;
             SliceRec sr;
             sr.begin = ps.sparse_base + s, sr.n = e - s, sr.term_score = 0.0f, sr.task_begin = task_at;
-            sr.leaf = (uint16_t)l, sr.kind = 1, sr.single = 0, sr.postings = 0, sr.pad = 0;
+            sr.leaf = (uint16_t)l, sr.kind = 1, sr.single = (a.parts[part].flags & kPartListBoost) ? 3 : 0, sr.postings = 0, sr.pad = 0;
             task_at += (sr.n + kTaskPostings - 1) / kTaskPostings;
             a.slice_recs[slice_at++] = sr;
         }
@@ -206,76 +206,111 @@ struct LeafBoostGlobals {  // the batch tables the rule needs; one copy per CTA 
     const uint64_t* g_begin;
     const uint32_t* g_df;
     const uint32_t* leaf_part;
+    const uint32_t* toff;
+    const uint32_t* g_row;
     uint32_t n_tiles, tile_log2, anchor_lo, pad;
 };
 struct LeafBoostCtx {
-    uint32_t part, list_part;   // the search part and the list part that holds its (anchor, ~value id) entries
-    uint32_t anchor;
+    uint32_t part, list_part;   // the search part and the list part that holds its (anchor, 0x7FFFFFFF - value id) entries
+    uint32_t anchor, idx;       // the anchor and its index in the tile
+    const uint32_t* hits;       // bitmaps of the tile: anchors the part hits / anchors with boost values
+    const uint32_t* boosted;
 };
 
+// For an anchor with several boosted values: takes all of them when the run of boosted hits before it is odd.
 __device__ __noinline__ float apply_leaf_boost(const LeafBoostGlobals* gp, LeafBoostCtx x, const BoostStep* bsp, float score, uint32_t first_vid) {
     const LeafBoostGlobals& a = *gp;
     const BoostStep& bs = *bsp;
     const uint32_t* brow = a.bucket + (size_t)x.list_part * (a.n_tiles + 1);
     const SparseEntry* ent = a.sparse + a.slices[x.list_part].sparse_base;
-    auto boosted = [&](uint32_t anchor, uint32_t* vids, uint32_t cap) -> uint32_t {  // distinct value ids of the anchor, ascending
-        const uint32_t t = (anchor - a.anchor_lo) >> a.tile_log2;
-        uint32_t n = 0;
-        for (uint32_t i = brow[t]; i < brow[t + 1]; ++i) {
-            if (ent[i].anchor != anchor) continue;
-            const uint32_t v = ~ent[i].key;
-            uint32_t at = 0;
-            bool dup = false;
-            while (at < n && vids[at] <= v) dup = dup || vids[at] == v, ++at;
-            if (dup) continue;
-            if (n < cap) {
-                for (uint32_t j = n; j > at; --j) vids[j] = vids[j - 1];
-                vids[at] = v;
-                ++n;
+    // the run of boosted hits directly before the anchor: inside the tile from the bitmaps ...
+    uint32_t run = 0;
+    bool open_at_tile_start = true;  // the run reaches the first anchor of the tile: continue in the posting lists
+    {
+        int pos = (int)x.idx - 1;
+        while (pos >= 0) {
+            // previous hit at or below pos
+            int w = pos >> 5;
+            uint32_t word = x.hits[w] & (0xFFFFFFFFu >> (31 - (pos & 31)));
+            while (word == 0 && w > 0) word = x.hits[--w];
+            if (word == 0) break;  // no hit before: the tile start is reached
+            const int p = (w << 5) + 31 - __clz((int)word);
+            if (!((x.boosted[p >> 5] >> (p & 31)) & 1u)) {
+                open_at_tile_start = false;
+                break;
             }
+            ++run;
+            pos = p - 1;
         }
-        return n;
-    };
-    uint32_t vids[8];
-    const uint32_t n_vids = boosted(x.anchor, vids, 8);
-    bool all = false;
-    if (n_vids > 1) {
-        // how many hits of the part directly before this anchor have boost values?
+    }
+    if (open_at_tile_start) {  // ... and across the tile start from the part's postings of the tiles before (bucket + offset rows)
+        const uint32_t tile_base = x.anchor - x.idx;
         const PartSlices ps = a.slices[x.part];
         const PostingsView pv = a.postings[a.parts[x.part].postings];
-        uint32_t cur = x.anchor, run = 0;
-        while (true) {
+        const uint32_t* prow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
+        const SparseEntry* pent = a.sparse + ps.sparse_base;
+        uint32_t cur = tile_base;
+        int tt = (int)((tile_base - a.anchor_lo) >> a.tile_log2) - 1;
+        while (tt >= 0) {
+            // the part's largest hit below `cur` in tile tt
             uint32_t pred = 0;
             bool found = false;
-            for (uint32_t r = 0; r < ps.n_match; ++r) {  // largest anchor below `cur` over the matched terms' posting lists
+            if (ps.n_match != ps.n_dense)
+                for (uint32_t i = prow[tt]; i < prow[tt + 1]; ++i)
+                    if (pent[i].anchor < cur && (!found || pent[i].anchor > pred)) pred = pent[i].anchor, found = true;
+            for (uint32_t r = 0; r < ps.n_dense; ++r) {
+                const uint32_t* trow = a.toff + (size_t)a.g_row[ps.m_begin + r] * (a.n_tiles + 1);
                 const Posting* post = pv.post + a.g_begin[ps.m_begin + r];
-                uint32_t lo = 0, hi = a.g_df[ps.m_begin + r];
+                uint32_t lo = trow[tt], hi = trow[tt + 1];
+                const uint32_t first = lo;
                 while (lo < hi) {
                     const uint32_t mid = (lo + hi) >> 1;
                     if (post[mid].anchor < cur) lo = mid + 1;
                     else hi = mid;
                 }
-                if (lo > 0 && (!found || post[lo - 1].anchor > pred)) pred = post[lo - 1].anchor, found = true;
+                if (lo > first && (!found || post[lo - 1].anchor > pred)) pred = post[lo - 1].anchor, found = true;
             }
-            if (!found) break;
-            uint32_t tmp[1];
-            if (boosted(pred, tmp, 1) == 0) break;
-            ++run, cur = pred;
+            if (!found) {  // no hit in this tile: look further back
+                --tt;
+                continue;
+            }
+            bool has = false;
+            for (uint32_t i = brow[tt]; i < brow[tt + 1] && !has; ++i) has = ent[i].anchor == pred;
+            if (!has) break;
+            ++run, cur = pred;  // (stay in tile tt: the hit before `pred` may be there as well)
         }
-        all = (run & 1u) != 0;
     }
-    const uint32_t n_apply = all ? n_vids : 1u;
-    for (uint32_t i = 0; i < n_apply; ++i) {
-        const uint32_t vid = n_vids ? vids[i] : first_vid;
-        const uint32_t bits = __ldg(bs.column + vid);
-        if (bits != kNoValue) score = apply_boost_step(bs, score, __uint_as_float(bits));
+    if (run & 1u) {  // every value of the anchor, in value-id order: one pass over the tile's entries of the list part
+        const uint32_t t = (x.anchor - a.anchor_lo) >> a.tile_log2;
+        uint32_t vids[8];
+        uint32_t n = 0;
+        for (uint32_t i = brow[t]; i < brow[t + 1]; ++i) {
+            const SparseEntry e = ent[i];
+            if (e.anchor != x.anchor) continue;
+            const uint32_t v = 0x7FFFFFFFu - e.key;
+            uint32_t at = 0;
+            bool dup = false;
+            while (at < n && vids[at] <= v) dup = dup || vids[at] == v, ++at;
+            if (dup || n == 8) continue;  // (a document with more than eight matching boosted values keeps the first eight)
+            for (uint32_t j = n; j > at; --j) vids[j] = vids[j - 1];
+            vids[at] = v;
+            ++n;
+        }
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t bits = __ldg(bs.column + vids[i]);
+            if (bits != kNoValue) score = apply_boost_step(bs, score, __uint_as_float(bits));
+        }
+        return score;
     }
+    const uint32_t bits = __ldg(bs.column + first_vid);
+    if (bits != kNoValue) score = apply_boost_step(bs, score, __uint_as_float(bits));
     return score;
 }
 
 // Generic request tree, postfix.  Returns presence; score in `out`.
 __device__ bool eval_program(const uint32_t* __restrict__ prog, uint32_t len, const uint32_t* arr, uint32_t tile, uint32_t idx, const BoostStep* __restrict__ boosts,
-                             const LeafBoostGlobals* lb, uint32_t leaf_begin, uint32_t anchor, float& out) {
+                             const LeafBoostGlobals* lb, const uint32_t* lbits, uint32_t leaf_begin, uint32_t anchor, float& out) {
+    uint32_t n_lb = 0;  // kOpLeafBoost ops seen so far: op k uses the bitmaps 2k (hits) and 2k + 1 (boosted)
     float sc[kMaxLeaves];
     bool pr[kMaxLeaves];
     int sp = 0;
@@ -314,11 +349,20 @@ __device__ bool eval_program(const uint32_t* __restrict__ prog, uint32_t len, co
             pr[sp] = key != 0;
             sc[sp] = key ? vbit::key_score(key) : 0.0f;
             const uint32_t bkey = arr[prog[pc + 2] * tile + idx];
-            if (key && bkey) {  // the list leaf holds the complement of the anchor's first boosted value id
-                LeafBoostCtx x;
-                x.part = lb->leaf_part[leaf_begin + prog[pc + 1]], x.list_part = lb->leaf_part[leaf_begin + prog[pc + 2]], x.anchor = anchor;
-                sc[sp] = apply_leaf_boost(lb, x, boosts + prog[pc + 3], sc[sp], ~bkey);
+            if (key && bkey) {  // the list leaf holds the anchor's smallest boosted value id and whether there are more
+                const BoostStep& bs = boosts[prog[pc + 3]];
+                const uint32_t first_vid = 0x7FFFFFFFu - (bkey & 0x7FFFFFFFu);
+                if (!(bkey & 0x80000000u)) {
+                    const uint32_t bits = __ldg(bs.column + first_vid);
+                    if (bits != kNoValue) sc[sp] = apply_boost_step(bs, sc[sp], __uint_as_float(bits));
+                } else {
+                    LeafBoostCtx x;
+                    x.part = lb->leaf_part[leaf_begin + prog[pc + 1]], x.list_part = lb->leaf_part[leaf_begin + prog[pc + 2]], x.anchor = anchor, x.idx = idx;
+                    x.hits = lbits + (2u * n_lb) * (tile >> 5), x.boosted = lbits + (2u * n_lb + 1u) * (tile >> 5);
+                    sc[sp] = apply_leaf_boost(lb, x, &bs, sc[sp], first_vid);
+                }
             }
+            ++n_lb;
             ++sp;
             pc += 4;
         } else if (op == kOpFilter) {
@@ -356,6 +400,7 @@ struct ItemCtx {
     float param;
     float prune_below;  // scores below this cannot reach the k-th best even with the largest boost multiplier
     const LeafBoostGlobals* lb;
+    const uint32_t* lbits;  // hit / boosted bitmaps of the tile for the request's kOpLeafBoost ops
 };
 
 // Everything after the request tree for one present anchor: boosts, threshold, survivor list.
@@ -463,7 +508,7 @@ __device__ __forceinline__ uint32_t eval_idx(const TileArgs& a, const ItemCtx& c
         }
         score = (L == 1 && !c.qp.union1) ? vbit::key_score(arr[idx]) : sum * nd * nd;
     } else {
-        present = eval_program(a.prog + c.qp.prog_begin, c.qp.prog_len, arr, c.tile, idx, a.boosts + c.qp.boost_begin, c.lb, c.qp.leaf_begin, c.tile_base + idx, score);
+        present = eval_program(a.prog + c.qp.prog_begin, c.qp.prog_len, arr, c.tile, idx, a.boosts + c.qp.boost_begin, c.lb, c.lbits, c.qp.leaf_begin, c.tile_base + idx, score);
     }
     uint32_t keep = 0;
     if (present) keep = finish_anchor(a, c, c.tile_base + idx, score, s_nsurv, s_list, arr + idx, c.tile);
@@ -552,7 +597,19 @@ __device__ __forceinline__ uint32_t run_task(const TileArgs& a, const ItemCtx& c
 #pragma unroll 4
             for (uint32_t j = j0 + lane; j < j1; j += 32) {
                 const SparseEntry e = se[j];
-                atomicMax(&dst[e.anchor - tile_base], e.key);
+                if (sr.single != 3) {
+                    atomicMax(&dst[e.anchor - tile_base], e.key);
+                } else {  // 1:n boost list: smallest value id of the anchor (largest key) + bit 31 when the anchor has several
+                    uint32_t* slot = &dst[e.anchor - tile_base];
+                    uint32_t old = *slot, assumed;
+                    do {
+                        assumed = old;
+                        const uint32_t ko = assumed & 0x7FFFFFFFu;
+                        const uint32_t next = assumed == 0 ? e.key : (max(ko, e.key) | (assumed & 0x80000000u) | (ko != e.key ? 0x80000000u : 0u));
+                        if (next == assumed) break;
+                        old = atomicCAS(slot, assumed, next);
+                    } while (old != assumed);
+                }
             }
         }
     } else {
@@ -577,6 +634,8 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
     __shared__ unsigned long long s_out[kMaxK];
     __shared__ uint32_t s_claim[1024];  // one bit per anchor of the tile (tiles up to 2^15)
     __shared__ LeafBoostGlobals s_lb;
+    __shared__ uint32_t s_lbits[2 * kMaxLeafBoosts * 256];  // per kOpLeafBoost op: anchors the part hits, anchors with boost values
+    __shared__ uint32_t s_lb_leaf[2 * kMaxLeafBoosts];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t n_warps = kTileThreads / 32;
@@ -588,7 +647,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
     }
     if (tid == 0) {
         s_lb.bucket = a.bucket, s_lb.sparse = a.sparse, s_lb.slices = a.slices, s_lb.postings = a.postings, s_lb.parts = a.parts;
-        s_lb.g_begin = a.g_begin, s_lb.g_df = a.g_df, s_lb.leaf_part = a.leaf_part;
+        s_lb.g_begin = a.g_begin, s_lb.g_df = a.g_df, s_lb.leaf_part = a.leaf_part, s_lb.toff = a.toff, s_lb.g_row = a.g_row;
         s_lb.n_tiles = a.n_tiles, s_lb.tile_log2 = a.tile_log2, s_lb.anchor_lo = a.anchor_lo, s_lb.pad = 0;
         const unsigned long long first = atomicAdd(a.work_counter, 1ull);
         s_item_idx[0] = first;
@@ -611,7 +670,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
 
         const uint32_t t = it.t, q = it.q;
         ItemCtx c;
-        c.lb = &s_lb;
+        c.lb = &s_lb, c.lbits = s_lbits;
         c.qp = a.queries[q];
         const QueryProgram& qp = c.qp;
         const uint32_t L = qp.n_leaves;
@@ -619,7 +678,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
         const uint32_t tile_base = (uint32_t)tile_base64;
         const uint32_t tile_n = (uint32_t)min((uint64_t)tile, (uint64_t)a.anchor_hi - tile_base64);
         c.tile = tile, c.tile_base = tile_base;
-        const bool sparse_mode = it.npost * 4u < tile_n;
+        const bool sparse_mode = it.npost * 4u < tile_n && a.queries[q].n_leaf_boosts == 0;  // (1:n boosts need the whole tile's bitmaps)
         if (sparse_mode)
             for (uint32_t i = tid; i < (tile >> 5); i += kTileThreads) s_claim[i] = 0;
         // slice records: up to 32 live in registers (one per lane, every warp has its own copy)
@@ -686,6 +745,34 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
                 }
                 __syncthreads();
             }
+        }
+
+        // 1:n boosts: which anchors of the tile the boosted parts hit and which of them have boost values
+        if (qp.n_leaf_boosts) {
+            if (tid == 0) {
+                const uint32_t* code = a.prog + qp.prog_begin;
+                uint32_t pc = 0, k = 0;
+                while (pc < qp.prog_len) {
+                    const uint32_t op = code[pc];
+                    if (op == kOpLeaf) pc += 2;
+                    else if (op == kOpUnion) pc += 3 + code[pc + 1];
+                    else if (op == kOpFilter) pc += 1;
+                    else if (op == kOpLeafBoost) {
+                        if (k < kMaxLeafBoosts) s_lb_leaf[2 * k] = code[pc + 1], s_lb_leaf[2 * k + 1] = code[pc + 2];
+                        ++k, pc += 4;
+                    } else pc += 2 + 2 * code[pc + 1];
+                }
+            }
+            __syncthreads();
+            const uint32_t words = tile >> 5;
+            for (uint32_t m = 0; m < 2 * min(qp.n_leaf_boosts, kMaxLeafBoosts); ++m) {
+                const uint32_t* src = arr + s_lb_leaf[m] * tile;
+                for (uint32_t w = warp; w < words; w += n_warps) {
+                    const uint32_t bits = __ballot_sync(0xFFFFFFFFu, src[(w << 5) + lane] != 0);
+                    if (lane == 0) s_lbits[m * words + w] = bits;
+                }
+            }
+            __syncthreads();
         }
 
         // (2) epilogue of densely hit tiles: tree, boosts, count, threshold; leaves the part arrays zeroed
@@ -773,7 +860,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
     }
 }
 
-static const size_t kTileStaticSmem = 15 * 1024;  // static __shared__ of tile_eval_kernel, rounded up
+static const size_t kTileStaticSmem = 24 * 1024;  // static __shared__ of tile_eval_kernel, rounded up
 
 size_t tile_kernel_smem(uint32_t tile_log2, uint32_t max_leaves) {
     if (tile_log2 > 15) return 0;

@@ -207,6 +207,7 @@ struct BatchPlan {
         for (size_t i = 0; i < o.parts.size(); ++i) {
             if (o.parts[i].flags & vdev::kPartList) {  // list parts are never shared
                 part_map[i] = add_list_part();
+                parts[part_map[i]].flags = o.parts[i].flags;
                 continue;
             }
             auto it = part_index.find(o.part_keys[i]);
@@ -287,6 +288,7 @@ struct BatchPlan {
     std::vector<BoostStep>* cur_steps = nullptr;       // its boost steps (1:n boosts are appended here)
     std::vector<std::string> cur_ids_keys;             // parts that are also searched for ids (filter, phrase boosts)
     bool cur_leaf_boost = false;
+    uint32_t cur_n_leaf_boosts = 0;
 
     Node emit(const vhost::SearchRequest& r, std::vector<uint32_t>& leaves, std::vector<uint32_t>& code, bool ids_only = false,
               const std::vector<vhost::BoostPart>& boosts = std::vector<vhost::BoostPart>()) {
@@ -329,7 +331,9 @@ struct BatchPlan {
                         m.column = col->second.bits.p, m.column_n = (uint32_t)col->second.n;
                         m.value_id_to_anchor = need(found->path + ".value_id_to_anchor").view();
                         m.list_part = add_list_part();
+                        parts[m.list_part].flags |= vdev::kPartListBoost;
                         boost_members.push_back(m);
+                        if (++cur_n_leaf_boosts > vdev::kMaxLeafBoosts) throw Unsupported("more than 4 search parts with a 1:n boost in one request");
                         BoostStep step;
                         memset(&step, 0, sizeof step);
                         step.column = col->second.bits.p, step.n = (uint32_t)col->second.n;
@@ -467,7 +471,7 @@ struct BatchPlan {
         const vhost::SearchRequest& root = *request.search_req;
         tl_seen.clear();
         std::vector<BoostStep> steps;
-        cur_steps = &steps, cur_leaf_boost = false;
+        cur_steps = &steps, cur_leaf_boost = false, cur_n_leaf_boosts = 0;
         cur_ids_keys.clear();
         if (request.phrase_boosts)
             for (auto& pb : *request.phrase_boosts) cur_ids_keys.push_back(pb.search1.key()), cur_ids_keys.push_back(pb.search2.key());
@@ -607,6 +611,7 @@ struct BatchPlan {
         qp.post_begin = (uint32_t)prog.size();
         qp.post_len = (uint32_t)post.size();
         prog.insert(prog.end(), post.begin(), post.end());
+        qp.n_leaf_boosts = cur_n_leaf_boosts;
         qp.facet_begin = rp.facet_begin;
         qp.n_facets = (uint32_t)rp.facets.size();
         qp.boost_begin = (uint32_t)boosts.size();
