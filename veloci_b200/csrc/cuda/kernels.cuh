@@ -210,8 +210,8 @@ struct PlaneArgs {
     uint32_t tile_begin, unit_items, chunks_per_tile, n_units;
     // 0: normal.  1: seed pass -- only anchors without entries inside boost level `seed_level` are evaluated, nothing is
     // counted: it gives every request a useful threshold for a fraction of a tile's evaluations.  2: the normal pass over
-    // tiles that were seeded: the anchors the seed pass evaluated are skipped.
-    uint32_t pass_mode, seed_level;
+    // tiles that were seeded (tiles below `seeded_tiles`): the anchors the seed pass evaluated are skipped.
+    uint32_t pass_mode, seed_level, seeded_tiles;
     // per-query state (shared with tile_eval_kernel)
     unsigned long long* heap;
     uint32_t heap_stride;

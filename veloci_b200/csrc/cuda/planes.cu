@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
             __syncwarp();
             compute_levels(S, lane, a.pass_mode, (int)a.seed_level);
             const bool seed_pass = a.pass_mode == 1;
-            const bool skip_seeded = a.pass_mode == 2 && (D.flags & kFastBoost) != 0;
+            const bool skip_seeded = a.pass_mode == 2 && t < a.seeded_tiles && (D.flags & kFastBoost) != 0;
             const uint32_t np0 = D.n_planes[0], np1 = D.n_planes[1], np2 = D.n_planes[2], np3 = D.n_planes[3];
             // word offset of each part's first plane (most parts match at most one head term)
             const uint32_t po0 = (uint32_t)D.plane[0][0] * W, po1 = (uint32_t)D.plane[1][0] * W, po2 = (uint32_t)D.plane[2][0] * W, po3 = (uint32_t)D.plane[3][0] * W;

@@ -95,7 +95,7 @@ struct Batch {
     uint64_t stat_fast_items = 0, stat_general_items = 0, stat_plane_evaluated = 0;
     // between execute_begin and execute_finish
     unsigned long long pending_items = 0;
-    uint32_t pending_fast_items = 0;
+    uint32_t pending_fast_items = 0, seeded_tiles = 0;
     bool begun = false;
     // device: per-request state and results
     DevBuf<unsigned long long> d_heap, d_tau, d_num_hits;
@@ -509,7 +509,9 @@ struct Batch {
         a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
         a.stats = d_counters.p + 8;
         const uint32_t want_units = (uint32_t)n_sms * 2;
-        uint32_t unit = stage == 2 ? 1024u : std::max<uint32_t>(16, ((uint64_t)n * (t1 - t0) + want_units - 1) / want_units);
+        // items of one tile a CTA takes at a time: at most 1024, and small enough for ~24 units per SM (tail balance on small shards)
+        uint32_t unit = stage == 2 ? std::max<uint32_t>(256, (uint32_t)(((uint64_t)n * (t1 - t0)) / ((uint64_t)n_sms * 24) + 1))
+                                   : std::max<uint32_t>(16, ((uint64_t)n * (t1 - t0) + want_units - 1) / want_units);
         unit = (std::min<uint32_t>(unit, 1024u) + 15u) & ~15u;
         a.tile_begin = t0, a.unit_items = unit;
         a.chunks_per_tile = (n + unit - 1) / unit;
@@ -519,7 +521,7 @@ struct Batch {
     }
 
     // Everything up to the point where the requests' thresholds (k-th best so far) are worth sharing between anchor-range
-    // shards: match, slicing, item scan and the plane evaluation of the first four tiles.  Returns with the stream idle.
+    // shards: match, slicing, item scan and the seed pass of the plane evaluation.  Returns with the stream idle.
     void execute_begin() {
         VDEV_CUDA(cudaSetDevice(ix->device));
         executed = false, fetched = false, begun = false;
@@ -633,18 +635,17 @@ struct Batch {
         // requests' thresholds are then close to final when the bulk of the tiles runs and prunes against them.
         pending_items = n_items, pending_fast_items = n_fast_items;
         if (planes_on && n_fast_items) {
-            const uint32_t e0 = std::min<uint32_t>(1, n_tiles), e1 = std::min<uint32_t>(4, n_tiles);
-            if (e0 > 0) {
-                // tile 0 twice: a seed pass over the anchors in the top 1/64 of the boost column gives every request a
-                // threshold, then the normal pass (which skips what the seed pass evaluated) prunes against it
-                PlaneArgs seed = plane_stage_args(0, 0, e0);
-                seed.pass_mode = 1, seed.seed_level = 5, seed.work_counter = d_counters.p + 13;
-                PlaneArgs rest = plane_stage_args(0, 0, e0);
-                rest.pass_mode = lev_dev ? 2 : 0, rest.seed_level = 5;
-                if (lev_dev) launch_plane_eval(stream, seed, n_sms);
-                launch_plane_eval(stream, rest, n_sms);
+            // Seed pass over the first tiles: only the anchors in the top 1/64 of the boost column are evaluated (and nothing
+            // is counted), which gives every request a threshold close to its final one for a fraction of a tile's work.
+            // Without a boost column in the batch the first tile runs in full instead.
+            seeded_tiles = lev_dev ? std::min<uint32_t>(8, n_tiles) : 0;
+            if (seeded_tiles) {
+                PlaneArgs seed = plane_stage_args(0, 0, seeded_tiles);
+                seed.pass_mode = 1, seed.seed_level = 5;
+                launch_plane_eval(stream, seed, n_sms);
+            } else {
+                launch_plane_eval(stream, plane_stage_args(0, 0, std::min<uint32_t>(1, n_tiles)), n_sms);
             }
-            if (e1 > e0) launch_plane_eval(stream, plane_stage_args(1, e0, e1), n_sms);
         }
         VDEV_CUDA(cudaStreamSynchronize(stream));
         VDEV_CUDA(cudaGetLastError());
@@ -659,8 +660,13 @@ struct Batch {
         const unsigned long long n_items = pending_items;
         const bool planes_on = use_planes && mode == kRequests;
         if (planes_on && pending_fast_items) {
-            const uint32_t e1 = std::min<uint32_t>(4, n_tiles);
-            if (n_tiles > e1) launch_plane_eval(stream, plane_stage_args(2, e1, n_tiles), n_sms);
+            // the normal pass: every tile (the seeded ones skip what the seed pass evaluated), or the tiles after the first
+            const uint32_t first = seeded_tiles ? 0u : std::min<uint32_t>(1, n_tiles);
+            if (n_tiles > first) {
+                PlaneArgs rest = plane_stage_args(2, first, n_tiles);
+                rest.pass_mode = seeded_tiles ? 2 : 0, rest.seed_level = 5, rest.seeded_tiles = seeded_tiles;
+                launch_plane_eval(stream, rest, n_sms);
+            }
         }
         VDEV_CUDA(cudaEventRecord(ev[4], stream));
         // ---- phase 4: tile evaluation of the general items
