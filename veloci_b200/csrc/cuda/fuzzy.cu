@@ -8,6 +8,8 @@
 //   sparse_*                postings of every matched term cross the anchor-tile boundaries.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "bitvec.cuh"
 #include "kernels.cuh"
 
@@ -22,6 +24,7 @@ namespace vdev {
 // column minimum is a lower bound for every extension), otherwise the warp
 // verifies the tile with one term per lane.
 static const int kPartChunk = 64;
+static const uint32_t kSparseSegment = 2048;  // postings of one sparse match a warp walks (grid.y = segments of the longest list)
 static const int kFuzzyThreads = 256;
 static const int kPeqCodes = 128;  // Eq masks of the first 128 alphabet codes come from a shared-memory table
 
@@ -492,12 +495,13 @@ __global__ void sparse_count_kernel(SparseArgs a) {
     const uint32_t mi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (mi >= a.n_matches || a.g_row[mi] != kNoValue) return;
     const uint32_t df = a.g_df[mi];
-    if (df == 0) return;
+    if (df <= blockIdx.y * kSparseSegment) return;
     const uint32_t part = a.g_part[mi];
     const PostingsView& pv = a.postings[a.parts[part].postings];
     const Posting* post = pv.post + a.g_begin[mi];
     uint32_t* row = a.bucket + (size_t)part * (a.n_tiles + 1);
-    for (uint32_t j = lane; j < df; j += 32) {
+    const uint32_t j0 = blockIdx.y * kSparseSegment, j1 = min(df, j0 + kSparseSegment);
+    for (uint32_t j = j0 + lane; j < j1; j += 32) {
         uint32_t t = (post[j].anchor - a.anchor_lo) >> a.tile_log2;
         atomicAdd(&row[t + 1], 1u);
     }
@@ -546,14 +550,15 @@ __global__ void sparse_fill_kernel(SparseArgs a) {
     const uint32_t mi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (mi >= a.n_matches || a.g_row[mi] != kNoValue) return;
     const uint32_t df = a.g_df[mi];
-    if (df == 0) return;
+    if (df <= blockIdx.y * kSparseSegment) return;
     const uint32_t part = a.g_part[mi];
     const PostingsView& pv = a.postings[a.parts[part].postings];
     const Posting* post = pv.post + a.g_begin[mi];
     uint32_t* row = a.bucket + (size_t)part * (a.n_tiles + 1);
     const uint64_t base = a.sparse_base[part];
     const float term_score = a.g_score[mi];
-    for (uint32_t j = lane; j < df; j += 32) {
+    const uint32_t j0 = blockIdx.y * kSparseSegment, j1 = min(df, j0 + kSparseSegment);
+    for (uint32_t j = j0 + lane; j < j1; j += 32) {
         const Posting p = post[j];
         const uint32_t t = (p.anchor - a.anchor_lo) >> a.tile_log2;
         const uint64_t at = base + atomicAdd(&row[t + 1], 1u);
@@ -852,7 +857,7 @@ void launch_dense_tile_offsets(cudaStream_t st, const DenseOffsetsArgs& a, uint3
 void launch_sparse_count(cudaStream_t st, const SparseArgs& a) {
     if (!a.n_matches) return;
     const uint64_t threads = (uint64_t)a.n_matches * 32;
-    sparse_count_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
+    sparse_count_kernel<<<dim3((unsigned)((threads + 255) / 256), std::max<uint32_t>(1, (a.max_df + kSparseSegment - 1) / kSparseSegment)), 256, 0, st>>>(a);
     count_launch();
 }
 void launch_sparse_scan(cudaStream_t st, uint32_t* bucket, uint32_t n_tiles, uint64_t* sparse_total, uint32_t n_parts) {
@@ -863,7 +868,7 @@ void launch_sparse_scan(cudaStream_t st, uint32_t* bucket, uint32_t n_tiles, uin
 void launch_sparse_fill(cudaStream_t st, const SparseArgs& a) {
     if (!a.n_matches) return;
     const uint64_t threads = (uint64_t)a.n_matches * 32;
-    sparse_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
+    sparse_fill_kernel<<<dim3((unsigned)((threads + 255) / 256), std::max<uint32_t>(1, (a.max_df + kSparseSegment - 1) / kSparseSegment)), 256, 0, st>>>(a);
     count_launch();
 }
 void launch_part_slices(cudaStream_t st, PartSlices* out, const uint32_t* part_begin, const uint32_t* dense_cursor, const uint64_t* sparse_base, const PartQuery* parts, uint32_t n_parts) {

@@ -82,6 +82,7 @@ struct SparseArgs {
     const uint64_t* sparse_base;
     SparseEntry* sparse;
     uint32_t n_tiles, tile_log2, anchor_lo;
+    uint32_t max_df;  // largest posting list a sparse match can have (the lists are walked in segments by several warps)
 };
 void launch_sparse_count(cudaStream_t st, const SparseArgs& a);
 void launch_sparse_scan(cudaStream_t st, uint32_t* bucket, uint32_t n_tiles, uint64_t* sparse_total, uint32_t n_parts);

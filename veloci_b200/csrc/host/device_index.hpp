@@ -361,6 +361,8 @@ struct DeviceIndex {
     std::map<std::string, ColumnDev> boosts;       // "<field>.boost_valid_to_value"
     std::map<std::string, PhraseDev> phrases;
     PlaneSetDev planes;
+    uint64_t max_posting_list = 0;   // longest posting list of the shard
+    uint64_t max_nonplane_list = 0;  // ... among the terms without a plane
     size_t device_bytes = 0;
 
     uint32_t shard_words() const {  // 32-anchor words of the shard, padded to whole plane tiles
@@ -682,6 +684,13 @@ struct DeviceIndex {
             kv.first->term_plane.upload(kv.second);
             device_bytes += kv.first->term_plane.bytes();
         }
+        max_nonplane_list = 0;
+        for (auto& kv : postings) {
+            PostingsDev& pd = kv.second;
+            auto it = maps.find(&pd);
+            for (size_t t = 0; t < pd.n_terms; ++t)
+                if (it == maps.end() || it->second[t] == kNoValue) max_nonplane_list = std::max<uint64_t>(max_nonplane_list, pd.h_off[t + 1] - pd.h_off[t]);
+        }
         device_bytes += planes.bits.bytes() + planes.score.bytes() + planes.wmax.bytes();
     }
 
@@ -725,6 +734,9 @@ struct DeviceIndex {
         ix->anchor_hi = ix->num_docs * (rank + 1) / n_shards;
         for (auto& kv : ix->host->dict) ix->build_dict(kv.first, kv.second);
         for (auto& kv : ix->host->token_to_anchor_score) ix->build_postings(kv.first, kv.second);
+        for (auto& kv : ix->postings)
+            for (size_t t = 0; t < kv.second.n_terms; ++t) ix->max_posting_list = std::max<uint64_t>(ix->max_posting_list, kv.second.h_off[t + 1] - kv.second.h_off[t]);
+        ix->max_nonplane_list = ix->max_posting_list;
         ix->build_planes();
         for (auto& kv : ix->host->key_value_stores) ix->build_store(kv.first, kv.second);
         for (auto& kv : ix->host->boost_valueid_to_value) ix->build_boost(kv.first, kv.second);

@@ -542,6 +542,7 @@ struct Batch {
             sa.n_matches = M, sa.g_row = d_g_row.p, sa.g_df = d_g_df.p, sa.g_part = d_g_part.p, sa.g_begin = d_g_begin.p, sa.g_score = d_g_score.p;
             sa.parts = d_parts.p, sa.postings = d_postings.p, sa.bucket = d_bucket.p, sa.sparse_base = d_sparse_base.p, sa.sparse = nullptr;
             sa.n_tiles = n_tiles, sa.tile_log2 = tile_log2, sa.anchor_lo = (uint32_t)ix->anchor_lo;
+            sa.max_df = (uint32_t)std::min<uint64_t>(use_planes ? ix->max_nonplane_list : std::min<uint64_t>(dense_min(), ix->max_posting_list), 0xFFFFFFFFull);
             launch_sparse_count(stream, sa);
             ListArgs la;
             la.part_begin = d_part_begin.p, la.g_term = d_g_term.p, la.bucket = d_bucket.p, la.sparse_base = d_sparse_base.p, la.sparse = nullptr;
