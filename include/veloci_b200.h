@@ -77,6 +77,9 @@ int32_t vgpu_index_info(const vgpu_index* idx, uint64_t* num_docs, uint64_t* anc
  * A request that fails (invalid, unknown field, unsupported) gets its status set and
  * an empty result; the other requests of the batch are unaffected. */
 int32_t vgpu_batch_prepare(vgpu_index* idx, const char* const* request_json, uint32_t n, vgpu_batch** out);
+/* The same with the requests as JSON lines in one buffer (one `search::Request` per line; empty lines are skipped):
+ * what a server hands over when it drains its request queue.  *n_requests receives the number of requests found. */
+int32_t vgpu_batch_prepare_jsonl(vgpu_index* idx, const char* text, size_t len, uint32_t* n_requests, vgpu_batch** out);
 int32_t vgpu_batch_execute(vgpu_batch* batch);
 void vgpu_batch_free(vgpu_batch* batch);
 

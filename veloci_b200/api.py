@@ -51,6 +51,7 @@ def load_library():
     L.vgpu_index_close.restype = None
     L.vgpu_index_info.argtypes = [vp, P(u64), P(u64), P(u64), P(u64)]
     L.vgpu_batch_prepare.argtypes = [vp, P(cp), u32, P(vp)]
+    L.vgpu_batch_prepare_jsonl.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, P(u32), P(vp)]
     L.vgpu_batch_execute.argtypes = [vp]
     L.vgpu_batch_execute_begin.argtypes = [vp]
     L.vgpu_batch_execute_finish.argtypes = [vp]
@@ -134,9 +135,16 @@ class Batch:
         self.L = load_library()
         self.index = index
         self.n = len(requests)
-        arr, self._keep = _encode_requests(requests)
         self.h = ctypes.c_void_p()
-        _check(self.L.vgpu_batch_prepare(index.h, arr, self.n, ctypes.byref(self.h)))
+        if self.n >= 64 and all(isinstance(r, str) and r and "\n" not in r for r in requests):
+            # many requests: one JSON-lines buffer instead of one C string per request
+            blob = "\n".join(requests).encode("utf-8")
+            n = ctypes.c_uint32()
+            _check(self.L.vgpu_batch_prepare_jsonl(index.h, blob, len(blob), ctypes.byref(n), ctypes.byref(self.h)))
+            assert n.value == self.n
+        else:
+            arr, self._keep = _encode_requests(requests)
+            _check(self.L.vgpu_batch_prepare(index.h, arr, self.n, ctypes.byref(self.h)))
 
     def execute(self):
         _check(self.L.vgpu_batch_execute(self.h))

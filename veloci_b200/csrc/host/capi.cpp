@@ -23,6 +23,7 @@ struct vgpu_index {
 struct vgpu_batch {
     vdev::Batch b;
     std::vector<std::vector<vsteps::FacetGroups>> facets;  // per request, filled on demand
+    std::vector<char> jsonl;                                // vgpu_batch_prepare_jsonl: the request lines
 };
 
 static thread_local std::string t_error;
@@ -128,6 +129,35 @@ int32_t vgpu_batch_prepare(vgpu_index* idx, const char* const* request_json, uin
     return guarded([&]() {
         std::unique_ptr<vgpu_batch> b(new vgpu_batch());
         b->b.prepare(idx->ix.get(), request_json, n);
+        *out = b.release();
+    });
+}
+
+int32_t vgpu_batch_prepare_jsonl(vgpu_index* idx, const char* text, size_t len, uint32_t* n_out, vgpu_batch** out) {
+    if (!idx || !out || (len && !text)) {
+        t_error = "null argument";
+        return VGPU_ERR_INVALID_REQUEST;
+    }
+    *out = nullptr;
+    return guarded([&]() {
+        // one request per line (JSON escapes line feeds inside strings); empty lines are skipped.  The lines are
+        // terminated in a private copy so that every request is a C string.
+        std::unique_ptr<vgpu_batch> b(new vgpu_batch());
+        b->jsonl.assign(text, text + len);
+        b->jsonl.push_back('\0');
+        std::vector<const char*> lines;
+        char* p = b->jsonl.data();
+        char* end = p + len;
+        while (p < end) {
+            char* nl = static_cast<char*>(memchr(p, '\n', (size_t)(end - p)));
+            if (!nl) nl = end;
+            *nl = '\0';
+            if (nl > p) lines.push_back(p);
+            p = nl + 1;
+        }
+        if (lines.size() > 0xFFFFFFF0ull) throw std::runtime_error("too many requests in one batch");
+        b->b.prepare(idx->ix.get(), lines.data(), (uint32_t)lines.size());
+        if (n_out) *n_out = (uint32_t)lines.size();
         *out = b.release();
     });
 }
