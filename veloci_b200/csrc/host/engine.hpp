@@ -509,10 +509,13 @@ struct Batch {
         a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
         a.stats = d_counters.p + 8;
         const uint32_t want_units = (uint32_t)n_sms * 2;
-        // items of one tile a CTA takes at a time: at most 1024, and small enough for ~24 units per SM (tail balance on small shards)
+        // items of one tile a CTA takes at a time: at most 4096 (the tile's bits are staged once per unit), and small enough for
+        // ~24 units per SM (tail balance on small shards)
         uint32_t unit = stage == 2 ? std::max<uint32_t>(256, (uint32_t)(((uint64_t)n * (t1 - t0)) / ((uint64_t)n_sms * 24) + 1))
                                    : std::max<uint32_t>(16, ((uint64_t)n * (t1 - t0) + want_units - 1) / want_units);
-        unit = (std::min<uint32_t>(unit, 1024u) + 15u) & ~15u;
+        uint32_t unit_cap = 4096u;
+        if (const char* env = getenv("VELOCI_UNIT_ITEMS")) unit_cap = (uint32_t)std::max(16, atoi(env));
+        unit = (std::min<uint32_t>(unit, unit_cap) + 15u) & ~15u;
         a.tile_begin = t0, a.unit_items = unit;
         a.chunks_per_tile = (n + unit - 1) / unit;
         a.n_units = (t1 - t0) * a.chunks_per_tile;
