@@ -1,0 +1,80 @@
+"""The drop-in boundary on a machine without a GPU: the shared library loads, exports every symbol that
+include/veloci_b200.h declares, answers the calls that need no device, and refuses -- loudly, with VGPU_ERR_CUDA --
+every call that would compute.  No compute entry point is exercised here (that is tests/test_gpu_*.py, -m gpu)."""
+import ctypes
+import json
+import os
+import re
+import tempfile
+
+import pytest
+
+import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "veloci_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from veloci_b200 import build
+
+    return ctypes.CDLL(build.build_main_lib())  # nvcc cross-compiles for sm_100a without a device
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vgpu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_seams():
+    names = declared_symbols()
+    for must in ("vgpu_index_open", "vgpu_batch_prepare", "vgpu_batch_execute", "vgpu_batch_result", "vgpu_search_batch", "vgpu_field_search",
+                 "vgpu_resolve_to_anchor", "vgpu_union_hits_score", "vgpu_intersect_hits_score", "vgpu_add_boost", "vgpu_top_n",
+                 "vgpu_batch_local_topk", "vgpu_batch_merge_gathered", "vgpu_batch_facet_group"):
+        assert must in names
+    assert len(names) >= 30
+
+
+def test_library_exports_every_declared_symbol(lib):
+    missing = [n for n in declared_symbols() if not hasattr(lib, n)]
+    assert not missing, f"declared in include/veloci_b200.h but not exported: {missing}"
+
+
+def test_python_binding_binds_only_declared_symbols():
+    src = open(os.path.join(ROOT, "veloci_b200", "api.py")).read()
+    used = set(re.findall(r"\bL\.(vgpu_[a-z0-9_]+)", src))
+    assert used and used <= set(declared_symbols()), used - set(declared_symbols())
+
+
+def test_no_device_no_result(lib, native_libs):
+    """Without a CUDA device the library reports zero devices and index_open fails with VGPU_ERR_CUDA: there is no CPU path."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("this check is for machines without a GPU")
+    lib.vgpu_device_count.restype = ctypes.c_int32
+    lib.vgpu_last_error.restype = ctypes.c_char_p
+    assert lib.vgpu_device_count() == 0
+    d = tempfile.mkdtemp(prefix="vb200_cabi_")
+    helpers.create_synthetic_index(d, num_docs=200, vocab=50, seed=1)
+    handle = ctypes.c_void_p()
+    rc = lib.vgpu_index_open(d.encode(), 0, 0, 1, ctypes.byref(handle))
+    assert rc == 6 and not handle.value, rc  # VGPU_ERR_CUDA
+    assert b"CUDA" in lib.vgpu_last_error() or b"cuda" in lib.vgpu_last_error()
+    # null handles are rejected, not dereferenced
+    assert lib.vgpu_batch_execute(None) == 1
+    n = ctypes.c_uint32()
+    assert lib.vgpu_batch_prepare_jsonl(None, b"{}", 2, ctypes.byref(n), ctypes.byref(handle)) == 1
+
+
+def test_python_loader_has_no_fallback(monkeypatch):
+    import veloci_b200
+    from veloci_b200 import api
+
+    monkeypatch.setattr(api, "_LIB", None)
+    monkeypatch.setattr(api, "lib_path", lambda: os.path.join(ROOT, "veloci_b200", "lib", "missing.so"))
+    with pytest.raises(veloci_b200.api.VelociGpuError) as e:
+        api.load_library()
+    assert e.value.status == 6
