@@ -360,3 +360,45 @@ def test_edge_requests(small):
     assert index.prepare([]).execute().n == 0
     bad = index.prepare(["{", json.dumps({"top": 1})]).execute()
     assert [bad.status(0), bad.status(1)] == [5, 1]
+
+
+def test_search_stream_equals_batches(small):
+    """Index.search_stream (planning of batch i+1 overlapped with the GPU work of batch i) returns, batch by batch, what
+    search_batch returns for the same requests."""
+    index, oracle, _ = small
+    batches = [helpers.synthetic_requests(num_queries=150, query_kind=kind, levenshtein=1, query_seed=seed, **SMALL) for kind, seed in (("or3", 31), ("and", 32), ("single", 33), ("or3", 34))]
+    batches.append([])  # an empty batch in the middle of the stream
+    batches.append(batches[0])
+    streamed = list(index.search_stream(iter(batches), k=10))
+    assert len(streamed) == len(batches)
+    for reqs, got in zip(batches, streamed):
+        want = index.search_batch(reqs, k=10) if reqs else None
+        assert len(got["num_hits"]) == len(reqs)
+        if not reqs:
+            continue
+        assert np.array_equal(got["num_hits"], want["num_hits"])
+        assert np.array_equal(got["ids"][:, :10], want["ids"])
+        assert np.array_equal(got["scores"][:, :10], want["scores"])
+    compare_batch(index, oracle, batches[0])
+
+
+def test_parts_shared_by_what_the_device_sees(small):
+    """The planner unifies search parts by their device form (symbols, distance, flags, boost), not by their JSON: parts
+    that differ only in fields that do not change the hits (ignore_case spelled out, a distance above len - 1) share
+    one part, parts that differ in a field that does change them (boost, starts_with, distance) do not."""
+    index, oracle, _ = small
+    w = [json.loads(r)["search_req"]["search"]["terms"][0] for r in helpers.synthetic_requests(num_queries=3, query_kind="single", query_seed=77, **SMALL)]
+    P = lambda t, **kw: {"search": {"terms": [t], "path": "body", **kw}}
+    reqs = [
+        {"search_req": P(w[0], levenshtein_distance=1)},
+        {"search_req": P(w[0], levenshtein_distance=1, ignore_case=True)},
+        {"search_req": P(w[0], levenshtein_distance=1, boost=2.0)},
+        {"search_req": P(w[0], levenshtein_distance=1, starts_with=True)},
+        {"search_req": P(w[0], levenshtein_distance=2)},
+        {"search_req": P(w[0])},
+        {"search_req": P("ab", levenshtein_distance=1)},
+        {"search_req": P("ab", levenshtein_distance=7)},
+        {"search_req": {"or": {"queries": [P(w[0], levenshtein_distance=1), P(w[0], levenshtein_distance=1, boost=3.0), P(w[1])]}}},
+        {"search_req": {"and": {"queries": [P(w[1], levenshtein_distance=1, ignore_case=True), P(w[1], levenshtein_distance=1), P(w[2], starts_with=True)]}}},
+    ]
+    compare_batch(index, oracle, [json.dumps(r) for r in reqs] * 30, k=10)

@@ -284,6 +284,35 @@ class Index:
         _check(self.L.vgpu_search_batch(self.h, arr, n, k, ids.ctypes.data, scores.ctypes.data, num_hits.ctypes.data, status.ctypes.data))
         return {"ids": ids, "scores": scores, "num_hits": num_hits, "status": status}
 
+    def search_stream(self, batches, k=10, run=None):
+        """Evaluates a sequence of request batches, yielding one `results_flat(k)` dict per batch, in order.
+
+        A planner thread parses, plans and uploads batch i+1 (`vgpu_batch_prepare`, host work + H2D on its own stream)
+        while the calling thread has batch i on the GPU and reads its rows back: the steady-state time per batch is
+        max(prepare, execute + fetch) instead of their sum.  `run(batch)` replaces the plain `batch.execute()` when
+        the caller has more to do per batch (the sharded path: threshold exchange, all-gather, merge)."""
+        from concurrent.futures import ThreadPoolExecutor
+        it = iter(batches)
+        with ThreadPoolExecutor(max_workers=1, thread_name_prefix="veloci-plan") as planner:
+            def plan_next():
+                try:
+                    reqs = next(it)
+                except StopIteration:
+                    return None
+                return planner.submit(self.prepare, reqs)
+            ahead = plan_next()
+            while ahead is not None:
+                batch = ahead.result()
+                ahead = plan_next()
+                try:
+                    if run is None:
+                        batch.execute()
+                    else:
+                        run(batch)
+                    yield batch.results_flat(k)
+                finally:
+                    batch.close()
+
     # ---- step seam
     def field_search(self, part, get_scores=True, get_ids=False):
         out = _HitList()

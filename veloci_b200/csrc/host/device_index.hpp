@@ -127,19 +127,19 @@ class ScratchPool {
 class UploadScope {
    public:
     explicit UploadScope(cudaStream_t st) : stream_(st) {
-        Buf& b = buf();
-        if (!b.p) {
-            if (cudaHostAlloc((void**)&b.p, kCap, cudaHostAllocDefault) != cudaSuccess) b.p = nullptr;
-        }
+        buf_ = take_buffer();
         used_ = 0;
-        current() = b.p ? this : nullptr;
+        current() = buf_ ? this : nullptr;
     }
     ~UploadScope() {
         if (current() == this) {
             cudaStreamSynchronize(stream_);
             current() = nullptr;
         }
+        if (buf_) give_buffer(buf_);
     }
+    UploadScope(const UploadScope&) = delete;
+    UploadScope& operator=(const UploadScope&) = delete;
     static UploadScope*& current() {
         static thread_local UploadScope* cur = nullptr;
         return cur;
@@ -151,7 +151,7 @@ class UploadScope {
             cudaStreamSynchronize(stream_);
             used_ = 0;
         }
-        char* at = buf().p + used_;
+        char* at = buf_ + used_;
         memcpy(at, src, bytes);
         used_ += (bytes + 255) & ~(size_t)255;
         return cudaMemcpyAsync(dst, at, bytes, cudaMemcpyHostToDevice, stream_) == cudaSuccess;
@@ -159,14 +159,35 @@ class UploadScope {
 
    private:
     static constexpr size_t kCap = (size_t)32 << 20;
-    struct Buf {
-        char* p = nullptr;
+    // The pinned staging buffers are shared by all threads (cudaHostAlloc costs tens of milliseconds and stalls the
+    // device: a planner thread that comes and goes must not pay it again); a few are ever alive at once.
+    struct BufferPool {
+        std::mutex mu;
+        std::vector<char*> free;
     };
-    static Buf& buf() {
-        static thread_local Buf b;
-        return b;
+    static BufferPool& pool() {
+        static BufferPool* p = new BufferPool();  // never destroyed: outlives the CUDA context teardown order
+        return *p;
+    }
+    static char* take_buffer() {
+        {
+            std::lock_guard<std::mutex> g(pool().mu);
+            if (!pool().free.empty()) {
+                char* p = pool().free.back();
+                pool().free.pop_back();
+                return p;
+            }
+        }
+        char* p = nullptr;
+        if (cudaHostAlloc((void**)&p, kCap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        return p;
+    }
+    static void give_buffer(char* p) {
+        std::lock_guard<std::mutex> g(pool().mu);
+        pool().free.push_back(p);
     }
     cudaStream_t stream_;
+    char* buf_ = nullptr;
     size_t used_ = 0;
 };
 

@@ -85,8 +85,58 @@ struct BatchPlan {
     // distinct search parts of the batch
     std::vector<PartQuery> parts;
     std::vector<uint32_t> part_dict;  // part -> dictionary table index
-    std::unordered_map<std::string, uint32_t> part_index;
-    std::vector<std::string> part_keys;  // part -> its key in part_index
+    // Parts are unified by what the device sees of them: two RequestSearchParts with the same PartQuery on the same
+    // dictionary produce the same hits (the reference's FieldRequestCache keys on the request text instead,
+    // execution_plan.rs:13,108-130; sharing more is not observable).  Open addressing over the part's hash.
+    std::vector<uint64_t> part_hash;   // part -> hash of its PartQuery (without the table indexes), 0 for list parts
+    std::vector<uint32_t> part_slot;   // hash table: part id + 1, 0 = empty
+    size_t part_slots_used = 0;
+
+    static uint64_t hash_part(const PartQuery& q) {
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        auto mix = [&](uint64_t v) {
+            h ^= v;
+            h *= 0xFF51AFD7ED558CCDull;
+            h ^= h >> 32;
+        };
+        const uint32_t m = std::min<uint32_t>(q.m, 64);
+        for (uint32_t j = 0; j < m; ++j) mix(((uint64_t)q.match_sym[j] << 16) | q.score_sym[j]);
+        uint32_t boost_bits;
+        memcpy(&boost_bits, &q.boost, 4);
+        mix(((uint64_t)q.m << 32) | q.d_score);
+        mix(((uint64_t)q.flags << 32) | boost_bits);
+        mix(q.lower_bytes);
+        return h | 1;  // never 0
+    }
+    void grow_part_slots(size_t want_parts) {
+        size_t cap = 64;
+        while (cap < want_parts * 2 + 2) cap <<= 1;
+        if (cap <= part_slot.size()) return;
+        part_slot.assign(cap, 0);
+        part_slots_used = 0;
+        for (size_t i = 0; i < parts.size(); ++i)
+            if (part_hash[i]) {
+                size_t at = part_hash[i] & (cap - 1);
+                while (part_slot[at]) at = (at + 1) & (cap - 1);
+                part_slot[at] = (uint32_t)i + 1, ++part_slots_used;
+            }
+    }
+    // The part equal to (q, dictionary), added if new.  `q` must have been zero-filled before its fields were set.
+    uint32_t find_or_add_part(const PartQuery& q, uint32_t dict, uint64_t h) {
+        if ((part_slots_used + 1) * 2 > part_slot.size()) grow_part_slots(std::max<size_t>(parts.size() + 1, part_slots_used * 2));
+        const size_t mask = part_slot.size() - 1;
+        size_t at = h & mask;
+        for (; part_slot[at]; at = (at + 1) & mask) {
+            const uint32_t id = part_slot[at] - 1;
+            if (part_hash[id] == h && part_dict[id] == dict && memcmp(&parts[id], &q, sizeof q) == 0) return id;
+        }
+        const uint32_t id = (uint32_t)parts.size();
+        parts.push_back(q);
+        part_dict.push_back(dict);
+        part_hash.push_back(h);
+        part_slot[at] = id + 1, ++part_slots_used;
+        return id;
+    }
     // tables of device views referenced by index
     std::vector<std::string> dict_names, postings_names;
     std::unordered_map<std::string, uint32_t> dict_index, postings_index;
@@ -129,25 +179,52 @@ struct BatchPlan {
         return id;
     }
 
+    // What a field's search parts look up, resolved once per plan and field.
+    struct FieldTables {
+        std::string field;  // as written in the request
+        uint32_t dict_id, postings_id;
+        const vdev::DictDev* dict;
+        uint16_t ascii_code[128];  // alphabet code of the ASCII scalars
+    };
+    std::vector<FieldTables> fields_seen;
+    const FieldTables& field_tables(const std::string& field) {
+        for (auto& f : fields_seen)
+            if (f.field == field) return f;
+        std::string path = field;
+        if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+        FieldTables f;
+        f.field = field;
+        f.dict_id = dict_id(path);  // FstNotFound
+        f.dict = &ix->dicts.at(path);
+        f.postings_id = postings_id(path + ".to_anchor_id_score");
+        for (uint32_t c = 0; c < 128; ++c) f.ascii_code[c] = f.dict->code_of(c);
+        fields_seen.push_back(std::move(f));
+        return fields_seen.back();
+    }
+
     // get_term_ids_in_field's request normalisation (search_field.rs:277-300)
     uint32_t add_part(const vhost::SearchPart& part_in) {
-        const std::string key = part_in.key();
-        auto it = part_index.find(key);
-        if (it != part_index.end()) return it->second;
-        vhost::SearchPart req = part_in;
+        const vhost::SearchPart& req = part_in;
         if (req.terms.empty()) throw InvalidRequest("search part without terms");
         if (req.is_regex) throw Unsupported("regex search is outside the accelerated path");
         if (req.top || req.skip) throw Unsupported("per-part top/skip is outside the accelerated path");
         if (req.token_value) throw Unsupported("token_value boost is outside the accelerated path");
-        std::string path = req.path;
-        if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
-        const uint32_t did = dict_id(path);
-        const vdev::DictDev& dict = ix->dicts.at(path);
-        const uint32_t pid = postings_id(path + ".to_anchor_id_score");
-        const std::string lower_term = vfmt::to_lowercase(req.terms[0]);
-        std::vector<uint32_t> raw, low;
-        vfmt::utf8_decode(req.terms[0], raw);
-        vfmt::utf8_decode(lower_term, low);
+        const FieldTables& ft = field_tables(req.path);
+        const uint32_t did = ft.dict_id, pid = ft.postings_id;
+        const std::string& term = req.terms[0];
+        bool ascii = true;
+        for (unsigned char c : term) ascii &= c < 0x80;
+        std::vector<uint32_t>&raw = scratch_raw, &low = scratch_low;
+        raw.clear(), low.clear();
+        size_t lower_bytes = term.size();
+        if (ascii) {
+            for (unsigned char c : term) raw.push_back(c), low.push_back((c >= 'A' && c <= 'Z') ? c + 32u : c);
+        } else {
+            const std::string lower_term = vfmt::to_lowercase(term);
+            vfmt::utf8_decode(term, raw);
+            vfmt::utf8_decode(lower_term, low);
+            lower_bytes = lower_term.size();
+        }
         if (raw.size() > 64) throw Unsupported("search terms longer than 64 characters are outside the accelerated path");
         PartQuery q;
         memset(&q, 0, sizeof q);
@@ -161,18 +238,14 @@ struct BatchPlan {
         q.flags = (req.starts_with ? vdev::kPartPrefix : 0u) | (transposition ? vdev::kPartTransposition : 0u) | (case_insensitive ? 0u : vdev::kPartRawCase) |
                   ((req.starts_with || d != 0) ? vdev::kPartCheckPrefix : 0u) | (req.boost ? vdev::kPartHasBoost : 0u);
         q.boost = req.boost.value_or(1.0f);
-        q.lower_bytes = (uint32_t)lower_term.size();
+        q.lower_bytes = (uint32_t)lower_bytes;
         q.postings = pid;
+        auto code_of = [&](uint32_t scalar) { return scalar < 128 ? ft.ascii_code[scalar] : ft.dict->code_of(scalar); };
         for (size_t j = 0; j < raw.size(); ++j) {
-            q.match_sym[j] = dict.code_of(case_insensitive ? vfmt::lower_scalar(raw[j]) : raw[j]);
-            q.score_sym[j] = dict.code_of(low[j]);
+            q.match_sym[j] = code_of(case_insensitive ? vfmt::lower_scalar(raw[j]) : raw[j]);
+            q.score_sym[j] = code_of(low[j]);
         }
-        const uint32_t id = (uint32_t)parts.size();
-        parts.push_back(q);
-        part_dict.push_back(did);
-        part_index.emplace(key, id);
-        part_keys.push_back(key);
-        return id;
+        return find_or_add_part(q, did, hash_part(q));
     }
 
     // A part whose hits are produced by a list kernel (phrase pairs, text locality, 1:n boosts) instead of a field search.
@@ -182,11 +255,9 @@ struct BatchPlan {
         q.flags = vdev::kPartList;
         q.postings = vdev::kNoValue;
         const uint32_t id = (uint32_t)parts.size();
-        const std::string key = std::string("\x01list#") + std::to_string(id);
         parts.push_back(q);
         part_dict.push_back(0);
-        part_index.emplace(key, id);
-        part_keys.push_back(key);
+        part_hash.push_back(0);  // never shared
         return id;
     }
 
@@ -194,7 +265,8 @@ struct BatchPlan {
     void reserve_for(const std::vector<BatchPlan>& chunks) {
         size_t n_parts = 0, n_leaf = 0, n_prog = 0, n_boost = 0, n_req = 0;
         for (auto& c : chunks) n_parts += c.parts.size(), n_leaf += c.leaf_part.size(), n_prog += c.prog.size(), n_boost += c.boosts.size(), n_req += c.requests.size();
-        parts.reserve(n_parts), part_dict.reserve(n_parts), part_index.reserve(n_parts);
+        parts.reserve(n_parts), part_dict.reserve(n_parts), part_hash.reserve(n_parts);
+        grow_part_slots(n_parts);
         leaf_part.reserve(n_leaf), prog.reserve(n_prog), boosts.reserve(n_boost), programs.reserve(n_req), requests.reserve(n_req);
     }
 
@@ -210,18 +282,9 @@ struct BatchPlan {
                 parts[part_map[i]].flags = o.parts[i].flags;
                 continue;
             }
-            auto it = part_index.find(o.part_keys[i]);
-            if (it != part_index.end()) {
-                part_map[i] = it->second;
-                continue;
-            }
             PartQuery q = o.parts[i];
             if (q.postings != vdev::kNoValue) q.postings = post_map[q.postings];
-            const uint32_t id = (uint32_t)parts.size();
-            parts.push_back(q);
-            part_dict.push_back(dict_map[o.part_dict[i]]);
-            part_index.emplace(std::move(o.part_keys[i]), id);  // (the merged plan does not keep part_keys: it is never merged again)
-            part_map[i] = id;
+            part_map[i] = find_or_add_part(q, dict_map[o.part_dict[i]], o.part_hash[i]);
         }
         const uint32_t leaf_base = (uint32_t)leaf_part.size(), prog_base = (uint32_t)prog.size(), boost_base = (uint32_t)boosts.size(), facet_base = (uint32_t)facets.size();
         for (vdev::PhraseMember m : o.phrase_members) {
@@ -285,6 +348,10 @@ struct BatchPlan {
     };
 
     // state of the request being planned
+    std::vector<uint32_t> scratch_raw, scratch_low;    // decoded term of the part being added
+    std::vector<uint32_t> scratch_leaves, scratch_code, scratch_post;
+    std::vector<BoostStep> scratch_steps;
+    bool cur_want_terms = false;                       // text locality asked for: remember the tree's (path, term, part)
     std::vector<BoostStep>* cur_steps = nullptr;       // its boost steps (1:n boosts are appended here)
     std::vector<std::string> cur_ids_keys;             // parts that are also searched for ids (filter, phrase boosts)
     bool cur_leaf_boost = false;
@@ -298,12 +365,12 @@ struct BatchPlan {
             n.term = r.part.terms[0];
             n.leaf = (int)leaves.size();
             leaves.push_back(part);
-            if (!ids_only) {
+            if (!ids_only && (cur_want_terms || !boosts.empty())) {
                 std::string path = r.part.path;
                 if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
-                tl_seen.push_back(TlTerm{path, r.part.terms[0], part});
+                if (cur_want_terms) tl_seen.push_back(TlTerm{path, r.part.terms[0], part});
                 // a boost on the same 1:n level as the part (execution_plan.rs:422-436): BoostToAnchor + ApplyAnchorBoost
-                const size_t pos = r.part.path.rfind("[]");
+                const size_t pos = boosts.empty() ? std::string::npos : r.part.path.rfind("[]");
                 if (pos != std::string::npos) {
                     const std::string end_obj = r.part.path.substr(0, pos);
                     const vhost::BoostPart* found = nullptr;
@@ -357,24 +424,33 @@ struct BatchPlan {
         }
         if (r.queries.empty()) throw Unsupported("empty or/and list");
         std::vector<Node> kids;
+        kids.reserve(r.queries.size());
         for (auto& q : r.queries) {
-            std::vector<vhost::BoostPart> b = boosts;  // merge_vec (execution_plan.rs:263-270)
-            if (q.get_boost()) b.insert(b.end(), q.get_boost()->begin(), q.get_boost()->end());
-            kids.push_back(emit(q, leaves, code, ids_only, b));
+            if (q.get_boost() && !q.get_boost()->empty()) {  // merge_vec (execution_plan.rs:263-270)
+                std::vector<vhost::BoostPart> b = boosts;
+                b.insert(b.end(), q.get_boost()->begin(), q.get_boost()->end());
+                kids.push_back(emit(q, leaves, code, ids_only, b));
+            } else {
+                kids.push_back(emit(q, leaves, code, ids_only, boosts));
+            }
         }
         if (kids.size() == 1) return kids[0];  // passthrough (set_op.rs:93-96, :371-374)
         if (kids.size() > vdev::kMaxLeaves) throw Unsupported("more than 12 sub-queries in one or/and");
         Node out;
         out.term = kids[0].term;
         if (r.kind == vhost::SearchRequest::Or) {
-            std::vector<std::string> terms;
-            for (auto& k : kids) terms.push_back(k.term);
-            std::sort(terms.begin(), terms.end());
-            terms.erase(std::unique(terms.begin(), terms.end()), terms.end());
+            // term slots of the union (set_op.rs:122-137): the distinct terms in sorted order
+            const std::string* terms[vdev::kMaxLeaves];
+            size_t n_terms = 0;
+            for (auto& k : kids) terms[n_terms++] = &k.term;
+            auto less = [](const std::string* a, const std::string* b) { return *a < *b; };
+            auto same = [](const std::string* a, const std::string* b) { return *a == *b; };
+            std::sort(terms, terms + n_terms, less);
+            n_terms = (size_t)(std::unique(terms, terms + n_terms, same) - terms);
             code.push_back(vdev::kOpUnion);
             code.push_back((uint32_t)kids.size());
-            code.push_back((uint32_t)terms.size());
-            for (auto& k : kids) code.push_back((uint32_t)(std::find(terms.begin(), terms.end(), k.term) - terms.begin()));
+            code.push_back((uint32_t)n_terms);
+            for (auto& k : kids) code.push_back((uint32_t)(std::lower_bound(terms, terms + n_terms, &k.term, less) - terms));
         } else {
             code.push_back(vdev::kOpIntersect);
             code.push_back((uint32_t)kids.size());
@@ -384,15 +460,24 @@ struct BatchPlan {
         return out;
     }
 
+    std::vector<std::pair<std::string, const vdev::ColumnDev*>> columns_seen;  // boost path -> its column, per plan
     BoostStep make_boost(const vhost::BoostPart& b) {
         BoostStep s;
         memset(&s, 0, sizeof s);
-        const std::string path = b.path + ".boost_valid_to_value";
-        auto it = ix->boosts.find(path);
-        if (it == ix->boosts.end()) ix->host->path_not_found(path);
-        s.column = it->second.bits.p;
-        s.levels = it->second.level_hdr.p;
-        s.n = (uint32_t)it->second.n;
+        const vdev::ColumnDev* found = nullptr;
+        for (auto& seen : columns_seen)
+            if (seen.first == b.path) found = seen.second;
+        if (!found) {
+            const std::string path = b.path + ".boost_valid_to_value";
+            auto it = ix->boosts.find(path);
+            if (it == ix->boosts.end()) ix->host->path_not_found(path);
+            found = &it->second;
+            columns_seen.emplace_back(b.path, found);
+        }
+        const vdev::ColumnDev& col = *found;
+        s.column = col.bits.p;
+        s.levels = col.level_hdr.p;
+        s.n = (uint32_t)col.n;
         s.fun = (uint32_t)b.boost_fun;
         s.param = b.param.value_or(0.0f);
         if (b.skip_when_score) {
@@ -403,7 +488,6 @@ struct BatchPlan {
         if (b.expression) parse_expression(*b.expression, s);
         // upper bound of the multiplier (used by the tile kernel to skip hopeless anchors)
         s.can_prune = 0, s.max_mult = 0.0f;
-        const vdev::ColumnDev& col = it->second;
         if (!b.expression && s.n_skip == 0 && col.non_negative && s.param >= 0.0f && std::isfinite(s.param) && std::isfinite(col.vmax)) {
             float m = 0.0f;
             bool ok = true;
@@ -467,10 +551,13 @@ struct BatchPlan {
         if (!request.search_req) throw InvalidRequest("search_req is None, but is required in search");
         if (rp.top + rp.skip > vdev::kMaxK) throw Unsupported("top + skip above 256 is outside the accelerated path");
 
-        std::vector<uint32_t> leaves, code, post;
+        std::vector<uint32_t>&leaves = scratch_leaves, &code = scratch_code, &post = scratch_post;
+        leaves.clear(), code.clear(), post.clear();
         const vhost::SearchRequest& root = *request.search_req;
         tl_seen.clear();
-        std::vector<BoostStep> steps;
+        cur_want_terms = request.text_locality;
+        std::vector<BoostStep>& steps = scratch_steps;
+        steps.clear();
         cur_steps = &steps, cur_leaf_boost = false, cur_n_leaf_boosts = 0;
         cur_ids_keys.clear();
         if (request.phrase_boosts)
@@ -478,10 +565,12 @@ struct BatchPlan {
         if (request.filter) collect_keys(*request.filter, cur_ids_keys);
         {
             // the request's boosts go down the tree; sub-queries add their own options (execution_plan.rs:263-270), the root's own do not apply
-            const std::vector<vhost::BoostPart> top = request.boost.value_or(std::vector<vhost::BoostPart>());
-            emit(root, leaves, code, false, top);
+            static const std::vector<vhost::BoostPart> none;
+            emit(root, leaves, code, false, request.boost ? *request.boost : none);
         }
-        const std::vector<TlTerm> tree_terms = tl_seen;
+        cur_want_terms = false;  // the filter tree and the extra parts below are not part of term_id_hits_in_field
+        const std::vector<TlTerm> tree_terms = std::move(tl_seen);
+        tl_seen.clear();
         bool extras = cur_leaf_boost;
         if (request.filter) {  // the filter tree is evaluated for presence only; hits outside it are dropped (set_op.rs:311-326)
             emit(*request.filter, leaves, code, true);
@@ -635,7 +724,7 @@ struct BatchPlan {
     };
     static void parse_into(const char* json, Parsed& out) {
         try {
-            out.request = vhost::parse_request_json(json, strlen(json));
+            out.request = vhost::read_request_json(json, strlen(json));
         } catch (const vhost::RequestError& e) {
             out.status = 5, out.message = e.what();
         } catch (const std::exception& e) {

@@ -8,6 +8,7 @@
 // when the key is absent and to None when it is null.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -64,30 +65,32 @@ struct SearchPart {
     // RequestSearchPart derives Hash/Eq over every field: the FieldRequestCache key
     // (execution_plan.rs:13,108-130).
     std::string key() const {
-        std::string k = path;
-        for (auto& t : terms) k += "\x1e" + t;
-        k += "\x1f";
+        std::string k;
+        k.reserve(path.size() + 24 + (terms.empty() ? 0 : terms[0].size()));
+        k += path;
+        for (auto& t : terms) k += '\x1e', k += t;
+        k += '\x1f';
         if (levenshtein_distance) k += std::to_string(*levenshtein_distance);
         k += starts_with ? "\x1fS" : "\x1fs";
-        k += is_regex ? "R" : "r";
-        k += "\x1f";
+        k += is_regex ? 'R' : 'r';
+        k += '\x1f';
         if (token_value) k += token_value->key();
-        k += "\x1f";
+        k += '\x1f';
         if (boost) k += std::to_string(*boost);
-        k += "\x1f";
-        if (ignore_case) k += *ignore_case ? "1" : "0";
-        k += "\x1f";
+        k += '\x1f';
+        if (ignore_case) k += *ignore_case ? '1' : '0';
+        k += '\x1f';
         if (top) k += std::to_string(*top);
-        k += "\x1f";
+        k += '\x1f';
         if (skip) k += std::to_string(*skip);
-        k += "\x1f";
+        k += '\x1f';
         if (options.present) {
-            k += options.explain ? "E" : "e";
+            k += options.explain ? 'E' : 'e';
             if (options.top) k += std::to_string(*options.top);
-            k += ",";
+            k += ',';
             if (options.skip) k += std::to_string(*options.skip);
             if (options.boost)
-                for (auto& b : *options.boost) k += "|" + b.key();
+                for (auto& b : *options.boost) k += '|', k += b.key();
         }
         return k;
     }
@@ -315,6 +318,428 @@ inline Request parse_request(const vjson::Value& v) {
     if (auto* f = field(v, "text_locality")) r.text_locality = as_bool(*f, "text_locality");
     if (auto* f = field(v, "explain")) r.explain = as_bool(*f, "explain");
     return r;
+}
+
+// One pass over the request text straight into the Request structs, without a DOM: the planner's way in (a batch is
+// thousands of requests; the DOM's allocations were the larger part of planning a request).  Same surface and serde
+// semantics as parse_request: unknown keys are skipped, `null` leaves an Option field absent, a repeated key takes its
+// last value, the messages of type errors are the same.  tests/test_request_reader.py holds the two against each other.
+class RequestReader : private vjson::Parser {
+  public:
+    RequestReader(const char* p, size_t n) : Parser(p, n) {}
+
+    Request read() {
+        Request r;
+        try {
+            skip_ws();
+            read_request(r);
+            skip_ws();
+            if (p_ != end_) fail("trailing characters");
+        } catch (const vjson::ParseError& e) {
+            throw RequestError(e.what());
+        }
+        return r;
+    }
+
+  private:
+    std::string key_;
+    vjson::Value num_;
+
+    template <size_t N>
+    static bool is(const std::string& key, const char (&name)[N]) {
+        return key.size() == N - 1 && memcmp(key.data(), name, N - 1) == 0;
+    }
+    char peek() {
+        skip_ws();
+        if (p_ == end_) fail("unexpected end");
+        return *p_;
+    }
+    bool null_next() {
+        if (peek() != 'n') return false;
+        expect("null");
+        return true;
+    }
+    void skip_value() {
+        vjson::Value ignored;
+        parse_value_into(ignored);
+    }
+    // Walks the members of the object at the cursor: on_key(key) consumes the member's value.
+    template <class F>
+    void members(const char* not_object, F&& on_key) {
+        if (peek() != '{') throw RequestError(not_object);
+        ++p_;
+        if (peek() == '}') {
+            ++p_;
+            return;
+        }
+        while (true) {
+            if (peek() != '"') fail("expected object key");
+            parse_string(key_);
+            if (peek() != ':') fail("expected :");
+            ++p_;
+            skip_ws();
+            on_key(key_);
+            const char c = peek();
+            ++p_;
+            if (c == ',') continue;
+            if (c == '}') return;
+            fail("expected , or }");
+        }
+    }
+    // Walks the elements of the array at the cursor: on_element() consumes one element.
+    template <class F>
+    void elements(const char* not_array, F&& on_element) {
+        if (peek() != '[') throw RequestError(not_array);
+        ++p_;
+        if (peek() == ']') {
+            ++p_;
+            return;
+        }
+        while (true) {
+            skip_ws();
+            on_element();
+            const char c = peek();
+            ++p_;
+            if (c == ',') continue;
+            if (c == ']') return;
+            fail("expected , or ]");
+        }
+    }
+    [[noreturn]] static void bad_type(const char* what, const char* expected) { throw RequestError(std::string("invalid type for ") + what + ": expected " + expected); }
+    void number(const char* what, const char* expected) {
+        const char c = peek();
+        if (c != '-' && (c < '0' || c > '9')) {
+            skip_value();  // a syntax error is reported as such
+            bad_type(what, expected);
+        }
+        num_.num_is_u64 = num_.num_is_i64 = false;
+        parse_number(num_);
+    }
+    uint64_t u64(const char* what) {
+        number(what, "unsigned integer");
+        if (!num_.num_is_u64) bad_type(what, "unsigned integer");
+        return num_.u64;
+    }
+    float f32(const char* what) {
+        number(what, "number");
+        return (float)num_.num;
+    }
+    bool boolean(const char* what) {
+        const char c = peek();
+        if (c == 't') {
+            expect("true");
+            return true;
+        }
+        if (c == 'f') {
+            expect("false");
+            return false;
+        }
+        skip_value();
+        bad_type(what, "bool");
+    }
+    void str(const char* what, std::string& out) {
+        if (peek() != '"') {
+            skip_value();
+            bad_type(what, "string");
+        }
+        parse_string(out);
+    }
+    template <class T, class F>
+    void optional_field(std::optional<T>& field, F&& read) {  // null = None
+        if (null_next()) field.reset();
+        else field = read();
+    }
+
+    void read_boost_part(BoostPart& b) {
+        b = BoostPart();
+        bool have_path = false;
+        std::string fun;
+        members("boost part must be an object", [&](const std::string& k) {
+            if (is(k, "path")) {
+                str("path", b.path), have_path = true;
+            } else if (is(k, "boost_fun")) {
+                if (null_next()) {
+                    b.boost_fun = BoostFun::None;
+                    return;
+                }
+                str("boost_fun", fun);
+                if (fun == "Log2") b.boost_fun = BoostFun::Log2;
+                else if (fun == "Log10") b.boost_fun = BoostFun::Log10;
+                else if (fun == "Multiply") b.boost_fun = BoostFun::Multiply;
+                else if (fun == "Add") b.boost_fun = BoostFun::Add;
+                else if (fun == "Replace") b.boost_fun = BoostFun::Replace;
+                else throw RequestError("unknown variant `" + fun + "`, expected one of `Log2`, `Log10`, `Multiply`, `Add`, `Replace`");
+            } else if (is(k, "param")) {
+                optional_field(b.param, [&] { return f32("param"); });
+            } else if (is(k, "skip_when_score")) {
+                optional_field(b.skip_when_score, [&] {
+                    std::vector<float> s;
+                    elements("skip_when_score must be an array", [&] { s.push_back(f32("skip_when_score")); });
+                    return s;
+                });
+            } else if (is(k, "expression")) {
+                optional_field(b.expression, [&] {
+                    std::string e;
+                    str("expression", e);
+                    return e;
+                });
+            } else {
+                skip_value();
+            }
+        });
+        if (!have_path) throw RequestError("missing field `path`");
+    }
+    std::vector<BoostPart> read_boost_list(const char* not_array) {
+        std::vector<BoostPart> bs;
+        elements(not_array, [&] {
+            bs.emplace_back();
+            read_boost_part(bs.back());
+        });
+        return bs;
+    }
+    void read_options(SearchOptions& o) {
+        o = SearchOptions();
+        o.present = true;
+        members("options must be an object", [&](const std::string& k) {
+            if (is(k, "explain")) {
+                o.explain = null_next() ? false : boolean("explain");
+            } else if (is(k, "top")) {
+                optional_field(o.top, [&] { return u64("top"); });
+            } else if (is(k, "skip")) {
+                optional_field(o.skip, [&] { return u64("skip"); });
+            } else if (is(k, "boost")) {
+                optional_field(o.boost, [&] { return read_boost_list("options.boost must be an array"); });
+            } else {
+                skip_value();
+            }
+        });
+    }
+    void read_search_part(SearchPart& s) {
+        s = SearchPart();
+        bool have_path = false, have_terms = false;
+        members("search part must be an object", [&](const std::string& k) {
+            if (is(k, "path")) {
+                str("path", s.path), have_path = true;
+            } else if (is(k, "terms")) {
+                s.terms.clear();
+                elements("terms must be an array", [&] {
+                    s.terms.emplace_back();
+                    str("terms", s.terms.back());
+                });
+                have_terms = true;
+            } else if (is(k, "levenshtein_distance")) {
+                optional_field(s.levenshtein_distance, [&] { return (uint32_t)u64("levenshtein_distance"); });
+            } else if (is(k, "starts_with")) {
+                s.starts_with = null_next() ? false : boolean("starts_with");
+            } else if (is(k, "is_regex")) {
+                s.is_regex = null_next() ? false : boolean("is_regex");
+            } else if (is(k, "token_value")) {
+                optional_field(s.token_value, [&] {
+                    BoostPart b;
+                    read_boost_part(b);
+                    return b;
+                });
+            } else if (is(k, "boost")) {
+                optional_field(s.boost, [&] { return f32("boost"); });
+            } else if (is(k, "ignore_case")) {
+                optional_field(s.ignore_case, [&] { return boolean("ignore_case"); });
+            } else if (is(k, "top")) {
+                optional_field(s.top, [&] { return u64("top"); });
+            } else if (is(k, "skip")) {
+                optional_field(s.skip, [&] { return u64("skip"); });
+            } else if (is(k, "options")) {
+                if (null_next()) s.options = SearchOptions();
+                else read_options(s.options);
+            } else {
+                skip_value();
+            }
+        });
+        if (!have_path) throw RequestError("missing field `path`");
+        if (!have_terms) throw RequestError("missing field `terms`");
+    }
+    void read_search_request(SearchRequest& r) {
+        static const char* const shape = "search request must be an object with exactly one of `or`, `and`, `search`";
+        uint32_t n_keys = 0;
+        members(shape, [&](const std::string& tag) {
+            if (++n_keys > 1) throw RequestError(shape);
+            if (is(tag, "search")) {
+                r.kind = SearchRequest::Search;
+                read_search_part(r.part);
+                return;
+            }
+            if (is(tag, "or")) r.kind = SearchRequest::Or;
+            else if (is(tag, "and")) r.kind = SearchRequest::And;
+            else throw RequestError("unknown variant `" + tag + "`, expected one of `or`, `and`, `search`");
+            bool have_queries = false;
+            members("search tree must be an object", [&](const std::string& k) {
+                if (is(k, "queries")) {
+                    r.queries.clear();
+                    r.queries.reserve(4);
+                    elements("missing field `queries`", [&] {
+                        r.queries.emplace_back();
+                        read_search_request(r.queries.back());
+                    });
+                    have_queries = true;
+                } else if (is(k, "options")) {
+                    if (null_next()) r.options = SearchOptions();
+                    else read_options(r.options);
+                } else {
+                    skip_value();
+                }
+            });
+            if (!have_queries) throw RequestError("missing field `queries`");
+        });
+        if (n_keys != 1) throw RequestError(shape);
+    }
+    void read_request(Request& r) {
+        members("request must be a JSON object", [&](const std::string& k) {
+            if (is(k, "search_req")) {
+                optional_field(r.search_req, [&] {
+                    SearchRequest s;
+                    read_search_request(s);
+                    return s;
+                });
+            } else if (is(k, "boost")) {
+                optional_field(r.boost, [&] { return read_boost_list("boost must be an array"); });
+            } else if (is(k, "boost_term")) {
+                optional_field(r.boost_term, [&] {
+                    std::vector<SearchPart> ps;
+                    elements("boost_term must be an array", [&] {
+                        ps.emplace_back();
+                        read_search_part(ps.back());
+                    });
+                    return ps;
+                });
+            } else if (is(k, "facets")) {
+                optional_field(r.facets, [&] {
+                    std::vector<FacetRequest> fs;
+                    elements("facets must be an array", [&] {
+                        FacetRequest fr;
+                        bool have_field = false;
+                        members("facet must be an object", [&](const std::string& fk) {
+                            if (is(fk, "field")) str("field", fr.field), have_field = true;
+                            else if (is(fk, "top")) optional_field(fr.top, [&] { return u64("top"); });
+                            else skip_value();
+                        });
+                        if (!have_field) throw RequestError("missing field `field`");
+                        fs.push_back(std::move(fr));
+                    });
+                    return fs;
+                });
+            } else if (is(k, "phrase_boosts")) {
+                optional_field(r.phrase_boosts, [&] {
+                    std::vector<PhraseBoost> ps;
+                    elements("phrase_boosts must be an array", [&] {
+                        PhraseBoost pb;
+                        bool have1 = false, have2 = false;
+                        members("phrase boost needs `search1` and `search2`", [&](const std::string& pk) {
+                            if (is(pk, "search1")) read_search_part(pb.search1), have1 = true;
+                            else if (is(pk, "search2")) read_search_part(pb.search2), have2 = true;
+                            else skip_value();
+                        });
+                        if (!have1 || !have2) throw RequestError("phrase boost needs `search1` and `search2`");
+                        ps.push_back(std::move(pb));
+                    });
+                    return ps;
+                });
+            } else if (is(k, "select")) {
+                optional_field(r.select, [&] {
+                    std::vector<std::string> s;
+                    elements("select must be an array", [&] {
+                        s.emplace_back();
+                        str("select", s.back());
+                    });
+                    return s;
+                });
+            } else if (is(k, "filter")) {
+                if (null_next()) {
+                    r.filter.reset();
+                } else {
+                    auto f = std::make_shared<SearchRequest>();
+                    read_search_request(*f);
+                    r.filter = std::move(f);
+                }
+            } else if (is(k, "top")) {
+                optional_field(r.top, [&] { return u64("top"); });  // absent: Some(10); null: None
+            } else if (is(k, "skip")) {
+                optional_field(r.skip, [&] { return u64("skip"); });
+            } else if (is(k, "why_found")) {
+                r.why_found = null_next() ? false : boolean("why_found");
+            } else if (is(k, "text_locality")) {
+                r.text_locality = null_next() ? false : boolean("text_locality");
+            } else if (is(k, "explain")) {
+                r.explain = null_next() ? false : boolean("explain");
+            } else {
+                skip_value();
+            }
+        });
+    }
+};
+
+inline Request read_request_json(const char* json, size_t len) { return RequestReader(json, len).read(); }
+
+// Canonical text of a parsed request: every field, in declaration order (the tests compare the two parsers with it).
+inline void describe(const BoostPart& b, std::string& out) { out += "B(" + b.key() + ")"; }
+inline void describe(const SearchOptions& o, std::string& out) {
+    if (!o.present) return;
+    out += "O(";
+    out += o.explain ? "E" : "e";
+    out += o.top ? std::to_string(*o.top) : "-";
+    out += ",";
+    out += o.skip ? std::to_string(*o.skip) : "-";
+    if (o.boost) {
+        out += "[";
+        for (auto& b : *o.boost) describe(b, out);
+        out += "]";
+    }
+    out += ")";
+}
+inline void describe(const SearchPart& p, std::string& out) { out += "P(" + p.key() + ")"; }
+inline void describe(const SearchRequest& r, std::string& out) {
+    if (r.kind == SearchRequest::Search) {
+        describe(r.part, out);
+        return;
+    }
+    out += r.kind == SearchRequest::Or ? "or{" : "and{";
+    for (auto& q : r.queries) describe(q, out), out += ";";
+    describe(r.options, out);
+    out += "}";
+}
+inline std::string describe(const Request& r) {
+    std::string out;
+    auto u = [&](const char* name, const std::optional<uint64_t>& v) { out += name, out += v ? "=" + std::to_string(*v) : "=None", out += " "; };
+    if (r.search_req) out += "search_req=", describe(*r.search_req, out), out += " ";
+    if (r.boost) {
+        out += "boost=[";
+        for (auto& b : *r.boost) describe(b, out);
+        out += "] ";
+    }
+    if (r.boost_term) {
+        out += "boost_term=[";
+        for (auto& p : *r.boost_term) describe(p, out);
+        out += "] ";
+    }
+    if (r.facets) {
+        out += "facets=[";
+        for (auto& f : *r.facets) out += f.field + ":" + (f.top ? std::to_string(*f.top) : "None") + ",";
+        out += "] ";
+    }
+    if (r.phrase_boosts) {
+        out += "phrase_boosts=[";
+        for (auto& p : *r.phrase_boosts) describe(p.search1, out), out += "+", describe(p.search2, out), out += ",";
+        out += "] ";
+    }
+    if (r.select) {
+        out += "select=[";
+        for (auto& f : *r.select) out += f + ",";
+        out += "] ";
+    }
+    if (r.filter) out += "filter=", describe(*r.filter, out), out += " ";
+    u("top", r.top), u("skip", r.skip);
+    out += r.why_found ? "W" : "w";
+    out += r.text_locality ? "T" : "t";
+    out += r.explain ? "E" : "e";
+    return out;
 }
 
 inline Request parse_request_json(const char* json, size_t len) {

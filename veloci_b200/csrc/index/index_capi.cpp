@@ -4,6 +4,7 @@
 #include <cstring>
 #include <sstream>
 
+#include "../host/request.hpp"
 #include "indexer.hpp"
 #include "synth.hpp"
 
@@ -57,6 +58,23 @@ int vidx_write_synthetic_requests(const char* out_path, const char* params_json,
     } catch (const std::exception& e) {
         set_err(err, errlen, e.what());
         return 1;
+    }
+}
+
+// The request surface, for the tests that hold its two parsers against each other: `reader` = 0 parses through the JSON
+// DOM (parse_request, what the oracle uses), 1 through the one-pass RequestReader (what the planner uses).  Writes the
+// canonical text of the parsed request (or the error message) into `out`; returns 0, or 5 for a RequestError.
+int vidx_describe_request(const char* json, int reader, char* out, size_t outlen) {
+    try {
+        const vhost::Request r = reader ? vhost::read_request_json(json, strlen(json)) : vhost::parse_request_json(json, strlen(json));
+        set_err(out, outlen, vhost::describe(r).c_str());
+        return 0;
+    } catch (const vhost::RequestError& e) {
+        set_err(out, outlen, e.what());
+        return 5;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
+        return 9;
     }
 }
 

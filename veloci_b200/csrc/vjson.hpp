@@ -41,12 +41,14 @@ struct Value {
     bool is_array() const { return kind == Array; }
     bool is_object() const { return kind == Object; }
 
-    const Value* get(const std::string& key) const {
+    const Value* get(const char* key, size_t len) const {
         if (kind != Object) return nullptr;
         for (auto& kv : obj)
-            if (kv.first == key) return &kv.second;
+            if (kv.first.size() == len && memcmp(kv.first.data(), key, len) == 0) return &kv.second;
         return nullptr;
     }
+    const Value* get(const char* key) const { return get(key, strlen(key)); }
+    const Value* get(const std::string& key) const { return get(key.data(), key.size()); }
     bool has(const std::string& key) const { return get(key) != nullptr; }
 
     static Value make_string(std::string s) {
@@ -148,7 +150,7 @@ class Parser {
         return true;
     }
 
-  private:
+  protected:  // (the tokenizer is shared with readers that fill their own structs without a DOM)
     const char* p_;
     const char* end_;
 
@@ -157,27 +159,32 @@ class Parser {
         while (p_ < end_ && (*p_ == ' ' || *p_ == '\t' || *p_ == '\n' || *p_ == '\r')) ++p_;
     }
     Value parse_value() {
+        Value v;
+        parse_value_into(v);
+        return v;
+    }
+    // Values are built where they will live: no moves of half-built subtrees.
+    void parse_value_into(Value& v) {
         if (p_ == end_) fail("unexpected end");
         switch (*p_) {
-            case '{': return parse_object();
-            case '[': return parse_array();
-            case '"': {
-                Value v;
+            case '{': parse_object(v); return;
+            case '[': parse_array(v); return;
+            case '"':
                 v.kind = Value::String;
-                v.str = parse_string();
-                return v;
-            }
+                parse_string(v.str);
+                return;
             case 't':
                 expect("true");
-                return Value::make_bool(true);
+                v.kind = Value::Bool, v.b = true;
+                return;
             case 'f':
                 expect("false");
-                return Value::make_bool(false);
-            case 'n': {
+                v.kind = Value::Bool, v.b = false;
+                return;
+            case 'n':
                 expect("null");
-                return Value();
-            }
-            default: return parse_number();
+                return;
+            default: parse_number(v);
         }
     }
     void expect(const char* lit) {
@@ -185,29 +192,55 @@ class Parser {
         if ((size_t)(end_ - p_) < n || memcmp(p_, lit, n) != 0) fail("bad literal");
         p_ += n;
     }
-    Value parse_number() {
+    void parse_number(Value& v) {
+        // RFC 8259 grammar, as serde_json reads it: -? (0 | [1-9][0-9]*) (. [0-9]+)? ([eE] [+-]? [0-9]+)?
         const char* s = p_;
+        auto digits = [&]() {
+            const char* a = p_;
+            while (p_ < end_ && *p_ >= '0' && *p_ <= '9') ++p_;
+            if (p_ == a) fail("bad number");
+        };
         if (p_ < end_ && *p_ == '-') ++p_;
+        if (p_ < end_ && *p_ == '0') ++p_;
+        else digits();
         bool is_float = false;
-        while (p_ < end_ && ((*p_ >= '0' && *p_ <= '9') || *p_ == '.' || *p_ == 'e' || *p_ == 'E' || *p_ == '+' || *p_ == '-')) {
-            if (*p_ == '.' || *p_ == 'e' || *p_ == 'E') is_float = true;
-            ++p_;
+        if (p_ < end_ && *p_ == '.') {
+            ++p_, is_float = true;
+            digits();
         }
-        if (p_ == s) fail("bad number");
-        std::string txt(s, p_ - s);
-        Value v;
+        if (p_ < end_ && (*p_ == 'e' || *p_ == 'E')) {
+            ++p_, is_float = true;
+            if (p_ < end_ && (*p_ == '+' || *p_ == '-')) ++p_;
+            digits();
+        }
         v.kind = Value::Number;
-        v.num = strtod(txt.c_str(), nullptr);
+        const size_t len = (size_t)(p_ - s);
+        if (!is_float && *s != '-' && len <= 15) {  // short unsigned integers: exact in a double, no strtod
+            uint64_t u = 0;
+            for (const char* c = s; c < p_; ++c) u = u * 10 + (uint64_t)(*c - '0');
+            v.num = (double)u, v.num_is_u64 = true, v.u64 = u;
+            return;
+        }
+        char small[48];
+        std::string big;
+        const char* txt = small;
+        if (len < sizeof small) {
+            memcpy(small, s, len);
+            small[len] = 0;
+        } else {
+            big.assign(s, len);
+            txt = big.c_str();
+        }
+        v.num = strtod(txt, nullptr);
         if (!is_float) {
             if (txt[0] == '-') {
                 v.num_is_i64 = true;
-                v.i64 = strtoll(txt.c_str(), nullptr, 10);
+                v.i64 = strtoll(txt, nullptr, 10);
             } else {
                 v.num_is_u64 = true;
-                v.u64 = strtoull(txt.c_str(), nullptr, 10);
+                v.u64 = strtoull(txt, nullptr, 10);
             }
         }
-        return v;
     }
     static void append_utf8(std::string& out, uint32_t cp) {
         if (cp < 0x80) {
@@ -240,8 +273,21 @@ class Parser {
         return v;
     }
     std::string parse_string() {
-        ++p_;  // opening quote
         std::string out;
+        parse_string(out);
+        return out;
+    }
+    void parse_string(std::string& out) {
+        ++p_;  // opening quote
+        {   // the common case: no escapes before the closing quote
+            const char* q = p_;
+            while (q < end_ && *q != '"' && *q != '\\') ++q;
+            if (q < end_ && *q == '"') {
+                out.assign(p_, (size_t)(q - p_));
+                p_ = q + 1;
+                return;
+            }
+        }
         while (true) {
             if (p_ == end_) fail("unterminated string");
             char c = *p_++;
@@ -274,20 +320,20 @@ class Parser {
                 out.push_back(c);
             }
         }
-        return out;
     }
-    Value parse_array() {
+    void parse_array(Value& v) {
         ++p_;
-        Value v;
         v.kind = Value::Array;
         skip_ws();
         if (p_ < end_ && *p_ == ']') {
             ++p_;
-            return v;
+            return;
         }
+        v.arr.reserve(4);
         while (true) {
             skip_ws();
-            v.arr.push_back(parse_value());
+            v.arr.emplace_back();
+            parse_value_into(v.arr.back());
             skip_ws();
             if (p_ == end_) fail("unterminated array");
             if (*p_ == ',') {
@@ -300,34 +346,34 @@ class Parser {
             }
             fail("expected , or ]");
         }
-        return v;
     }
-    Value parse_object() {
+    void parse_object(Value& v) {
         ++p_;
-        Value v;
         v.kind = Value::Object;
         skip_ws();
         if (p_ < end_ && *p_ == '}') {
             ++p_;
-            return v;
+            return;
         }
+        v.obj.reserve(4);
         while (true) {
             skip_ws();
             if (p_ == end_ || *p_ != '"') fail("expected object key");
-            std::string key = parse_string();
+            v.obj.emplace_back();
+            parse_string(v.obj.back().first);
             skip_ws();
             if (p_ == end_ || *p_ != ':') fail("expected :");
             ++p_;
             skip_ws();
-            Value child = parse_value();
-            bool replaced = false;
-            for (auto& kv : v.obj)
-                if (kv.first == key) {
-                    kv.second = std::move(child);
-                    replaced = true;
+            parse_value_into(v.obj.back().second);
+            // a repeated key keeps its first position and takes the last value
+            const std::string& key = v.obj.back().first;
+            for (size_t i = 0; i + 1 < v.obj.size(); ++i)
+                if (v.obj[i].first == key) {
+                    v.obj[i].second = std::move(v.obj.back().second);
+                    v.obj.pop_back();
                     break;
                 }
-            if (!replaced) v.obj.emplace_back(std::move(key), std::move(child));
             skip_ws();
             if (p_ == end_) fail("unterminated object");
             if (*p_ == ',') {
@@ -340,7 +386,6 @@ class Parser {
             }
             fail("expected , or }");
         }
-        return v;
     }
 };
 
