@@ -127,6 +127,28 @@ int32_t vgpu_batch_merge_gathered(vgpu_batch* batch, const uint64_t* gathered_ke
  * before vgpu_batch_merge_gathered, which then picks the top groups of the summed histograms on every rank. */
 int32_t vgpu_batch_facet_histograms(const vgpu_batch* batch, uint32_t** hist_dev, uint64_t* n);
 
+/* ---- suggest ---------------------------------------------------------------
+ * suggest_multi (src/search/search_field.rs:178-217): `request_json` is a search::Request with `suggest` (a list of
+ * RequestSearchPart), `top` and `skip`.  Every part is matched and scored on the device (get_term_ids_in_field with
+ * return_term), the parts' own top/skip bound their hits (:292-294,:322-331,:366-369), equal lower-cased texts merge
+ * keeping the largest score, the list is ordered by score and cut by skip/top: SuggestFieldResult = Vec<(String, Score,
+ * TermId)>.  Among equal scores the reference's order is whatever its unstable sort leaves; here it is descending text.
+ * vgpu_suggest_part is search_field::suggest (:219-228): one part whose top/skip also cut the list.
+ * `items[i].text` points into `text_block`; release with vgpu_suggestions_free. */
+typedef struct vgpu_suggestion {
+    const char* text;  /* lower-cased term, UTF-8, NUL-terminated */
+    float score;
+    uint32_t id;       /* term id in the part's field */
+} vgpu_suggestion;
+typedef struct vgpu_suggestions {
+    vgpu_suggestion* items;
+    uint32_t n;
+    char* text_block;
+} vgpu_suggestions;
+int32_t vgpu_suggest(vgpu_index* idx, const char* request_json, vgpu_suggestions* out);
+int32_t vgpu_suggest_part(vgpu_index* idx, const char* part_json, vgpu_suggestions* out);
+void vgpu_suggestions_free(vgpu_suggestions* s);
+
 /* ---- step seam -------------------------------------------------------------
  * One symbol per PlanStep kind (src/plan_creator/plan_steps.rs:18-74), each over host
  * hit lists; used by the step-level parity tests.  Outputs are malloc'd by the

@@ -60,6 +60,7 @@ struct SearchFieldResult {  // result/field_result.rs:6-30 (hit-bearing fields o
     SearchPart request;
     std::optional<vhost::PhraseBoost> phrase_boost;
     std::map<std::string, std::map<std::string, std::vector<uint32_t>>> term_id_hits_in_field;
+    std::map<uint32_t, std::string> terms;  // term id -> text, when the plan asks for it (suggest)
     static SearchFieldResult new_from(const SearchFieldResult& o) {  // :42-52
         SearchFieldResult r;
         r.request = o.request;
@@ -90,6 +91,7 @@ struct PlanRequestSearchPart {  // execution_plan.rs:16-44
     bool get_scores = false;
     bool get_ids = false;
     bool store_term_id_hits = false;
+    bool return_term = false, return_term_lowercase = false;
 };
 
 // search.rs:123-130
@@ -282,6 +284,7 @@ static SearchFieldResult get_term_ids_in_field(const Persistence& p, PlanRequest
             }
             result.hits_scores.push_back(Hit{token_text_id, score});
         }
+        if (options.return_term) result.terms[token_text_id] = options.return_term_lowercase ? vfmt::to_lowercase(dict.term(slot)) : dict.term(slot);  // :331-337
     });
     if (req.boost)
         for (auto& h : result.hits_scores) h.score *= *req.boost;
@@ -1140,6 +1143,51 @@ static std::string ids_to_json(const std::vector<uint32_t>& ids) {
     return s + "]";
 }
 
+// search_field.rs:147-176 get_text_score_id_from_result(suggest_text = true) and :178-217 suggest_multi / suggest.
+// The reference sorts with sort_unstable_by (by text, then by score): which of several equal texts keeps its id, and
+// the order among equal scores, are whatever its sort leaves; stable sorts here.
+struct Suggestion {
+    std::string text;
+    float score;
+    uint32_t id;
+};
+static std::vector<Suggestion> suggest_multi(const Persistence& p, const Request& req) {
+    if (!req.suggest) throw InvalidRequest("only suggest allowed in suggest function");
+    std::vector<Suggestion> out;
+    for (const SearchPart& part : *req.suggest) {
+        PlanRequestSearchPart plan;
+        plan.request = part;
+        plan.get_scores = true, plan.return_term = true, plan.return_term_lowercase = true;
+        SearchFieldResult res = get_term_ids_in_field(p, plan);
+        for (const Hit& h : res.hits_scores) out.push_back(Suggestion{res.terms[h.id], h.score, h.id});
+    }
+    std::stable_sort(out.begin(), out.end(), [](const Suggestion& a, const Suggestion& b) { return b.text < a.text; });
+    std::vector<Suggestion> merged;  // dedup_by: the first of a run of equal texts stays and takes the largest score
+    for (const Suggestion& sgg : out) {
+        if (!merged.empty() && merged.back().text == sgg.text) {
+            if (sgg.score > merged.back().score) merged.back().score = sgg.score;
+        } else {
+            merged.push_back(sgg);
+        }
+    }
+    std::stable_sort(merged.begin(), merged.end(), [](const Suggestion& a, const Suggestion& b) { return a.score > b.score; });
+    if (req.skip) merged.erase(merged.begin(), merged.begin() + (long)std::min<uint64_t>(*req.skip, merged.size()));  // search.rs:230-239
+    if (req.top && merged.size() > *req.top) merged.resize(*req.top);
+    return merged;
+}
+static std::string suggestions_to_json(const std::vector<Suggestion>& v) {
+    std::string s = "[";
+    char buf[64];
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (i) s += ",";
+        s += "[";
+        vjson::write_string(s, v[i].text);
+        snprintf(buf, sizeof buf, ",%.9g,%u]", (double)v[i].score, v[i].id);
+        s += buf;
+    }
+    return s + "]";
+}
+
 // Named entry points for the unit-level known-answer tests.
 static std::string call(const Persistence* p, const std::string& fn, const vjson::Value& a) {
     auto results_from = [&](const vjson::Value& arr) {
@@ -1155,6 +1203,17 @@ static std::string call(const Persistence* p, const std::string& fn, const vjson
         }
         return rs;
     };
+    if (fn == "suggest_multi") {  // the whole Request (suggest, top, skip); Request.top is None unless given (`..Default::default()` is not serde's default)
+        Request r = vhost::parse_request(*a.get("request"));
+        return suggestions_to_json(suggest_multi(*p, r));
+    }
+    if (fn == "suggest") {  // search_field.rs:219-228: one part, its own top/skip also bound the merged list
+        Request r;
+        SearchPart part = vhost::parse_search_part(*a.get("part"));
+        r.suggest = std::vector<SearchPart>{part};
+        r.top = part.top, r.skip = part.skip;
+        return suggestions_to_json(suggest_multi(*p, r));
+    }
     if (fn == "union_hits_score") return hits_to_json(union_hits_score(results_from(*a.get("inputs"))).hits_scores);
     if (fn == "union_hits_ids") return ids_to_json(union_hits_ids(results_from(*a.get("inputs"))).hits_ids);
     if (fn == "intersect_hits_score") return hits_to_json(intersect_hits_score(results_from(*a.get("inputs"))).hits_scores);

@@ -267,3 +267,65 @@ def test_one_to_n_boost_with_several_values_per_document(gpu, native_libs):
             reqs.append({"search_req": {"search": {"terms": [t], "path": "kana[].text", "levenshtein_distance": 1, "starts_with": True}},
                          "boost": [{"path": "kana[].commonness", "boost_fun": fun, "param": 1}], "top": 50})
     compare(index, oracle, reqs)
+
+
+# ---- suggest (search_field.rs:147-228)
+def _same_suggestions(got, want, ctx):
+    assert [(t, i) for t, _, i in got] == [(t, i) for t, _, i in want], ctx
+    for (_, gs, _), (_, cs, _) in zip(got, want):
+        assert abs(float(gs) - float(cs)) <= 1e-5 * max(abs(float(cs)), 1e-30), ctx
+
+
+def test_suggest_on_the_reference_corpus(gpu, native_libs):
+    """The reference's suggest tests (tests.rs:1087-1132) on its own corpus: the golden lists as sets (its order among equal
+    scores is its unstable sort's), and the CUDA path against the oracle element by element (both break ties the same way)."""
+    import ref_fixtures as fx
+    d = tempfile.mkdtemp(prefix="vb200_gpu_")
+    helpers.create_index(d, fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG)
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    part = {"terms": ["majes"], "path": "meanings.ger[]", "levenshtein_distance": 0, "starts_with": True, "top": 10, "skip": 0}
+    got = index.suggest(part)
+    assert sorted(t for t, _, _ in got) == sorted(["majestät", "majestät (f)", "majestätisches", "majestätischer", "majestätischer anblick (m)", "majestätisches aussehen (n)"])
+    _same_suggestions(got, oracle.call("suggest", part=part), part)
+    req = {"suggest": [{"terms": ["will"], "path": "meanings.ger[]", "levenshtein_distance": 0, "starts_with": True},
+                       {"terms": ["will"], "path": "meanings.eng[]", "levenshtein_distance": 0, "starts_with": True}], "top": 10, "skip": 0}
+    got = index.suggest_multi(req)
+    assert sorted(t for t, _, _ in got) == sorted(["will", "wille", "wille (m)", "will testo"])
+    _same_suggestions(got, oracle.call("suggest_multi", request=req), req)
+    for req in ({"suggest": [{"terms": ["majes"], "path": "meanings.ger[]", "starts_with": True}], "top": 2, "skip": 1},
+                {"suggest": [{"terms": ["Majestat"], "path": "meanings.ger[]", "levenshtein_distance": 2}], "top": None},
+                {"suggest": [], "top": 10},
+                {"suggest": [{"terms": ["zzzzzz"], "path": "meanings.ger[]"}]}):
+        _same_suggestions(index.suggest_multi(req), oracle.call("suggest_multi", request=req), req)
+    with pytest.raises(Exception):
+        index.suggest_multi({"search_req": {"search": {"terms": ["a"], "path": "meanings.ger[]"}}})  # "only suggest allowed in suggest function"
+    with pytest.raises(Exception):
+        index.suggest({"terms": ["a"], "path": "nope"})
+
+
+def test_suggest_bounds_and_boosts_on_a_large_dictionary(gpu, native_libs):
+    """Prefix and fuzzy suggestions over a 20k-term dictionary: hundreds of matches per part, so the per-part top bound
+    (keep top + skip + 200, cut, drop what scores below the worst kept) is exercised, with part boosts (also negative),
+    several parts on one field merging equal texts, and skip."""
+    synth = dict(num_docs=30000, vocab=20000, seed=11)
+    d = tempfile.mkdtemp(prefix="vb200_gpu_")
+    helpers.create_synthetic_index(d, **synth)
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    words = [json.loads(r)["search_req"]["search"]["terms"][0] for r in helpers.synthetic_requests(num_queries=40, query_kind="single", query_seed=13, **synth)]
+    n_long = 0
+    for i, w in enumerate(words):
+        parts = [{"terms": [w[:1 + i % 3]], "path": "body", "starts_with": True, "levenshtein_distance": i % 2}]
+        if i % 2 == 0:
+            parts[0]["top"], parts[0]["skip"] = 1 + i % 7, i % 3
+        if i % 3 == 0:
+            parts.append({"terms": [w], "path": "body", "levenshtein_distance": 2, "boost": -1.5 if i % 6 == 0 else 3.0})
+        if i % 5 == 0:
+            parts.append({"terms": [w[:2]], "path": "body", "starts_with": True, "top": 300})
+        req = {"suggest": parts, "top": 25 if i % 4 else None, "skip": i % 4}
+        got = index.suggest_multi(req)
+        want = oracle.call("suggest_multi", request=req)
+        n_long += len(index.field_search({k: v for k, v in parts[0].items() if k not in ("top", "skip")})[0]) > 210
+        _same_suggestions(got, want, req)
+        one = dict(parts[0])
+        _same_suggestions(index.suggest(one), oracle.call("suggest", part=one), one)
+    assert n_long >= 5, "no part matched enough terms to reach the bound"

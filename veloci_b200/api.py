@@ -29,6 +29,14 @@ class _HitList(ctypes.Structure):
     _fields_ = [("hits", ctypes.POINTER(_Hit)), ("n_hits", ctypes.c_uint32), ("ids", ctypes.POINTER(ctypes.c_uint32)), ("n_ids", ctypes.c_uint32)]
 
 
+class _Suggestion(ctypes.Structure):
+    _fields_ = [("text", ctypes.c_char_p), ("score", ctypes.c_float), ("id", ctypes.c_uint32)]
+
+
+class _Suggestions(ctypes.Structure):
+    _fields_ = [("items", ctypes.POINTER(_Suggestion)), ("n", ctypes.c_uint32), ("text_block", ctypes.c_void_p)]
+
+
 def lib_path():
     return os.path.join(_HERE, "lib", "libveloci_b200.so")
 
@@ -80,6 +88,10 @@ def load_library():
     L.vgpu_intersect_hits_score.argtypes = [vp, P(_HitList), u32, P(_HitList)]
     L.vgpu_add_boost.argtypes = [vp, cp, P(_HitList)]
     L.vgpu_top_n.argtypes = [vp, P(_HitList), u32, u32, P(_HitList)]
+    L.vgpu_suggest.argtypes = [vp, cp, P(_Suggestions)]
+    L.vgpu_suggest_part.argtypes = [vp, cp, P(_Suggestions)]
+    L.vgpu_suggestions_free.argtypes = [P(_Suggestions)]
+    L.vgpu_suggestions_free.restype = None
     L.vgpu_launch_count.restype = u64
     L.vgpu_batch_phase_ms.argtypes = [vp, P(ctypes.c_float), u32]
     L.vgpu_batch_traffic_model.argtypes = [vp, P(u64), P(u64), P(u64), P(u64)]
@@ -312,6 +324,23 @@ class Index:
                     yield batch.results_flat(k)
                 finally:
                     batch.close()
+
+    # ---- suggest (search_field.rs:178-228): [(text, score, term id)]
+    def _suggest(self, fn, payload):
+        out = _Suggestions()
+        _check(fn(self.h, json.dumps(payload, ensure_ascii=False).encode("utf-8"), ctypes.byref(out)))
+        try:
+            return [(out.items[i].text.decode("utf-8"), np.float32(out.items[i].score), out.items[i].id) for i in range(out.n)]
+        finally:
+            self.L.vgpu_suggestions_free(ctypes.byref(out))
+
+    def suggest_multi(self, request):
+        """`request`: {"suggest": [part, ...], "top": .., "skip": ..}"""
+        return self._suggest(self.L.vgpu_suggest, request)
+
+    def suggest(self, part):
+        """One RequestSearchPart; its top/skip bound the list."""
+        return self._suggest(self.L.vgpu_suggest_part, part)
 
     # ---- step seam
     def field_search(self, part, get_scores=True, get_ids=False):

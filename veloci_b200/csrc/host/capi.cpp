@@ -328,6 +328,41 @@ int32_t vgpu_top_n(vgpu_index* idx, const vgpu_hitlist* in, uint32_t top, uint32
     return guarded([&]() { vsteps::top_n(*idx->ix, *in, top, skip, *out); });
 }
 
+static void fill_suggestions(const std::vector<vsteps::Suggestion>& v, vgpu_suggestions* out) {
+    size_t bytes = 0;
+    for (auto& sg : v) bytes += sg.text.size() + 1;
+    out->items = (vgpu_suggestion*)malloc(std::max<size_t>(1, v.size()) * sizeof(vgpu_suggestion));
+    out->text_block = (char*)malloc(std::max<size_t>(1, bytes));
+    out->n = (uint32_t)v.size();
+    size_t at = 0;
+    for (size_t i = 0; i < v.size(); ++i) {
+        memcpy(out->text_block + at, v[i].text.c_str(), v[i].text.size() + 1);
+        out->items[i] = vgpu_suggestion{out->text_block + at, v[i].score, v[i].id};
+        at += v[i].text.size() + 1;
+    }
+}
+int32_t vgpu_suggest(vgpu_index* idx, const char* request_json, vgpu_suggestions* out) {
+    if (!idx || !request_json || !out) return VGPU_ERR_INVALID_REQUEST;
+    memset(out, 0, sizeof *out);
+    return guarded([&]() { fill_suggestions(vsteps::suggest(*idx->ix, vhost::read_request_json(request_json, strlen(request_json))), out); });
+}
+int32_t vgpu_suggest_part(vgpu_index* idx, const char* part_json, vgpu_suggestions* out) {
+    if (!idx || !part_json || !out) return VGPU_ERR_INVALID_REQUEST;
+    memset(out, 0, sizeof *out);
+    return guarded([&]() {
+        vhost::Request req;
+        const vhost::SearchPart part = vsteps::parse_part(part_json);
+        req.suggest = std::vector<vhost::SearchPart>{part};
+        req.top = part.top, req.skip = part.skip;  // search_field.rs:224-225
+        fill_suggestions(vsteps::suggest(*idx->ix, req), out);
+    });
+}
+void vgpu_suggestions_free(vgpu_suggestions* s) {
+    if (!s) return;
+    free(s->items), free(s->text_block);
+    s->items = nullptr, s->text_block = nullptr, s->n = 0;
+}
+
 uint64_t vgpu_launch_count(void) { return vdev::launches_so_far(); }
 
 int32_t vgpu_batch_phase_ms(const vgpu_batch* batch, float* ms, uint32_t n_phases) {

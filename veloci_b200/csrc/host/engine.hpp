@@ -162,10 +162,13 @@ struct Batch {
     }
 
     // field search only (vgpu_field_search)
-    void prepare_parts(DeviceIndex* index, const std::vector<vhost::SearchPart>& search_parts) {
+    void prepare_parts(DeviceIndex* index, const std::vector<vhost::SearchPart>& search_parts, std::vector<uint32_t>* part_ids = nullptr) {
         ix = index;
         plan.ix = ix;
-        for (auto& p : search_parts) plan.add_part(p);
+        for (auto& p : search_parts) {
+            const uint32_t id = plan.add_part(p);  // equal parts share one id
+            if (part_ids) part_ids->push_back(id);
+        }
         n = 0;
         upload_plan();
     }

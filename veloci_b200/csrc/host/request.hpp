@@ -131,6 +131,7 @@ struct FacetRequest {
 
 struct Request {
     std::optional<SearchRequest> search_req;
+    std::optional<std::vector<SearchPart>> suggest;  // or/and/search and suggest are mutually exclusive (request/mod.rs:21-22)
     std::optional<std::vector<BoostPart>> boost;
     std::optional<std::vector<SearchPart>> boost_term;
     std::optional<std::vector<FacetRequest>> facets;
@@ -262,6 +263,12 @@ inline Request parse_request(const vjson::Value& v) {
     if (!v.is_object()) throw RequestError("request must be a JSON object");
     Request r;
     if (auto* f = field(v, "search_req")) r.search_req = parse_search_request(*f);
+    if (auto* f = field(v, "suggest")) {
+        if (!f->is_array()) throw RequestError("suggest must be an array");
+        std::vector<SearchPart> ps;
+        for (auto& e : f->arr) ps.push_back(parse_search_part(e));
+        r.suggest = std::move(ps);
+    }
     if (auto* f = field(v, "boost")) {
         if (!f->is_array()) throw RequestError("boost must be an array");
         std::vector<BoostPart> bs;
@@ -557,6 +564,14 @@ class RequestReader : private vjson::Parser {
         if (!have_path) throw RequestError("missing field `path`");
         if (!have_terms) throw RequestError("missing field `terms`");
     }
+    std::vector<SearchPart> read_part_list(const char* not_array) {
+        std::vector<SearchPart> ps;
+        elements(not_array, [&] {
+            ps.emplace_back();
+            read_search_part(ps.back());
+        });
+        return ps;
+    }
     void read_search_request(SearchRequest& r) {
         static const char* const shape = "search request must be an object with exactly one of `or`, `and`, `search`";
         uint32_t n_keys = 0;
@@ -601,15 +616,10 @@ class RequestReader : private vjson::Parser {
                 });
             } else if (is(k, "boost")) {
                 optional_field(r.boost, [&] { return read_boost_list("boost must be an array"); });
+            } else if (is(k, "suggest")) {
+                optional_field(r.suggest, [&] { return read_part_list("suggest must be an array"); });
             } else if (is(k, "boost_term")) {
-                optional_field(r.boost_term, [&] {
-                    std::vector<SearchPart> ps;
-                    elements("boost_term must be an array", [&] {
-                        ps.emplace_back();
-                        read_search_part(ps.back());
-                    });
-                    return ps;
-                });
+                optional_field(r.boost_term, [&] { return read_part_list("boost_term must be an array"); });
             } else if (is(k, "facets")) {
                 optional_field(r.facets, [&] {
                     std::vector<FacetRequest> fs;
@@ -709,6 +719,11 @@ inline std::string describe(const Request& r) {
     std::string out;
     auto u = [&](const char* name, const std::optional<uint64_t>& v) { out += name, out += v ? "=" + std::to_string(*v) : "=None", out += " "; };
     if (r.search_req) out += "search_req=", describe(*r.search_req, out), out += " ";
+    if (r.suggest) {
+        out += "suggest=[";
+        for (auto& p : *r.suggest) describe(p, out);
+        out += "] ";
+    }
     if (r.boost) {
         out += "boost=[";
         for (auto& b : *r.boost) describe(b, out);

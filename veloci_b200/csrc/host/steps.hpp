@@ -83,6 +83,93 @@ inline void field_search(vdev::DeviceIndex& ix, const char* part_json, bool get_
     out.ids = dup_array(ids), out.n_ids = (uint32_t)ids.size();
 }
 
+// suggest_multi / suggest (search_field.rs:147-228): every part's fuzzy match and scoring run on the device in one batch
+// (get_term_ids_in_field, get_scores + return_term); the per-part top/skip bound (:292-294,:322-331,:366-369), the merge of
+// equal texts and the final order are a few hundred elements of host work.
+struct Suggestion {
+    std::string text;
+    float score;
+    uint32_t id;
+};
+
+// The per-part `top` bound of get_term_ids_in_field over hits in FST order (= ascending term id): once top + skip + 200
+// hits are held, the best top + skip by (score, id) stay and a hit scoring below the worst of them is dropped from then
+// on (sort.rs:25-34); the part's boost comes after, then the best top + skip by score stay.
+inline void bound_part_hits(const vhost::SearchPart& part, std::vector<vgpu_hit>& hits) {
+    if (part.top) {
+        const size_t top_n = (size_t)(*part.top + part.skip.value_or(0));
+        float worst = -3.40282347e+38f;
+        std::vector<vgpu_hit> kept;
+        for (const vgpu_hit& h : hits) {
+            if (h.score < worst) continue;
+            if (!kept.empty() && kept.size() == top_n + 200) {
+                std::sort(kept.begin(), kept.end(), [](const vgpu_hit& a, const vgpu_hit& b) { return a.score != b.score ? a.score > b.score : a.id > b.id; });
+                kept.resize(top_n);
+                if (!kept.empty()) worst = kept.back().score;
+            }
+            kept.push_back(h);
+        }
+        hits.swap(kept);
+    }
+    if (part.boost)
+        for (vgpu_hit& h : hits) h.score *= *part.boost;
+    if (part.top) {
+        const size_t top_n = (size_t)(*part.top + part.skip.value_or(0));
+        std::stable_sort(hits.begin(), hits.end(), [](const vgpu_hit& a, const vgpu_hit& b) { return a.score > b.score; });
+        if (hits.size() > top_n) hits.resize(top_n);
+    }
+}
+
+inline std::vector<Suggestion> suggest(vdev::DeviceIndex& ix, const vhost::Request& req) {
+    if (!req.suggest) throw vplan::InvalidRequest("only suggest allowed in suggest function");
+    // the device matches and scores; bound and boost are applied to its output above
+    std::vector<vhost::SearchPart> device_parts;
+    for (const vhost::SearchPart& part : *req.suggest) {
+        if (part.token_value) throw vplan::Unsupported("token_value boost is outside the accelerated path");
+        vhost::SearchPart p = part;
+        p.top.reset(), p.skip.reset(), p.boost.reset();
+        device_parts.push_back(std::move(p));
+    }
+    std::vector<Suggestion> all;
+    if (!device_parts.empty()) {
+        vdev::Batch b;
+        std::vector<uint32_t> part_ids;
+        b.prepare_parts(&ix, device_parts, &part_ids);
+        b.run_match();
+        for (size_t i = 0; i < device_parts.size(); ++i) {
+            std::vector<uint32_t> terms;
+            std::vector<float> scores;
+            b.download_matches(part_ids[i], terms, scores);
+            std::vector<vgpu_hit> hits(terms.size());
+            for (size_t j = 0; j < terms.size(); ++j) hits[j] = vgpu_hit{terms[j], scores[j]};
+            std::sort(hits.begin(), hits.end(), [](const vgpu_hit& x, const vgpu_hit& y) { return x.id < y.id; });
+            bound_part_hits((*req.suggest)[i], hits);
+            std::string path = device_parts[i].path;
+            if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+            const vhost::TermDict& dict = ix.host->dict.at(path);
+            for (const vgpu_hit& h : hits) {
+                size_t slot = 0;
+                if (!dict.find_id(h.id, slot)) continue;
+                all.push_back(Suggestion{vfmt::to_lowercase(dict.term(slot)), h.score, h.id});  // return_term_lowercase
+            }
+        }
+    }
+    // get_text_score_id_from_result: equal texts merge into the first of them with the largest score, then by score
+    std::stable_sort(all.begin(), all.end(), [](const Suggestion& a, const Suggestion& b) { return b.text < a.text; });
+    std::vector<Suggestion> merged;
+    for (Suggestion& sg : all) {
+        if (!merged.empty() && merged.back().text == sg.text) {
+            if (sg.score > merged.back().score) merged.back().score = sg.score;
+        } else {
+            merged.push_back(std::move(sg));
+        }
+    }
+    std::stable_sort(merged.begin(), merged.end(), [](const Suggestion& a, const Suggestion& b) { return a.score > b.score; });
+    if (req.skip) merged.erase(merged.begin(), merged.begin() + (long)std::min<uint64_t>(*req.skip, merged.size()));  // apply_top_skip, search.rs:230-239
+    if (req.top && merged.size() > *req.top) merged.resize((size_t)*req.top);
+    return merged;
+}
+
 // The remaining step entry points run a one-request batch whose leaves are explicit hit lists.
 inline void run_lists(vdev::DeviceIndex& ix, const std::vector<vdev::ExplicitList>& lists, const std::vector<uint32_t>& code, const std::vector<vdev::BoostStep>& boosts, uint32_t k,
                       bool all_hits, vgpu_hitlist& out) {
