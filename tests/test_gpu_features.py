@@ -10,7 +10,7 @@ import pytest
 
 import helpers
 import ref_fixtures as fx
-from test_gpu_parity import assert_same_topk, close  # noqa: F401
+from test_gpu_parity import assert_same_topk, close, compare_batch  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 
@@ -329,3 +329,64 @@ def test_suggest_bounds_and_boosts_on_a_large_dictionary(gpu, native_libs):
         one = dict(parts[0])
         _same_suggestions(index.suggest(one), oracle.call("suggest", part=one), one)
     assert n_long >= 5, "no part matched enough terms to reach the bound"
+
+
+def test_per_part_top_and_skip_in_search_requests(gpu, native_libs):
+    """a RequestSearchPart with `top` keeps only its best top + skip term matches (with the reference's
+    200-hit slack and its drop-below-the-worst rule, search_field.rs:292-294,322-331,366-369) before they are resolved to
+    anchors.  Parts that match hundreds of terms, alone, inside or/and trees with unbounded parts, with part boosts and
+    with request boosts."""
+    synth = dict(num_docs=30000, vocab=20000, seed=11)
+    d = tempfile.mkdtemp(prefix="vb200_gpu_")
+    helpers.create_synthetic_index(d, **synth)
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    words = [json.loads(r)["search_req"]["search"]["terms"][0] for r in helpers.synthetic_requests(num_queries=60, query_kind="single", query_seed=17, **synth)]
+    P = lambda t, **kw: {"search": {"terms": [t], "path": "body", **kw}}
+    boost = [{"path": "commonness", "boost_fun": "Log10", "param": 1}]
+    reqs = []
+    for i, w in enumerate(words):
+        bounded = P(w[:1 + i % 3], starts_with=True, top=1 + i % 9, skip=i % 3)
+        fuzzy = P(w, levenshtein_distance=2, top=2 + i % 4)
+        if i % 4 == 0:
+            bounded["search"]["boost"] = 2.0 if i % 8 else -1.0
+        shape = i % 6
+        if shape == 0:
+            r = {"search_req": bounded}
+        elif shape == 1:
+            r = {"search_req": fuzzy, "boost": boost}
+        elif shape == 2:
+            r = {"search_req": {"or": {"queries": [bounded, P(words[(i + 1) % len(words)], levenshtein_distance=1), fuzzy]}}, "boost": boost}
+        elif shape == 3:
+            r = {"search_req": {"and": {"queries": [P(w[:2], starts_with=True, top=400), P(words[(i + 7) % len(words)][:1], starts_with=True)]}}}
+        elif shape == 4:
+            r = {"search_req": {"or": {"queries": [fuzzy, P(w[:3], starts_with=True, levenshtein_distance=1, top=7)]}}, "top": 3}
+        else:
+            r = {"search_req": {"or": {"queries": [bounded, bounded, P(w[:2], starts_with=True, top=5)]}}, "top": 20, "skip": 3}
+        reqs.append(json.dumps(r))
+    out, ref = compare_batch(index, oracle, reqs, k=10)
+    assert (out["num_hits"] > 0).sum() > len(reqs) // 2
+    # the bound is visible: the same part without `top` finds more
+    unbounded = index.search_batch([json.dumps({"search_req": P(words[0][:1], starts_with=True)})], k=10)
+    assert int(unbounded["num_hits"][0]) > int(out["num_hits"][0])
+    # the step seam takes bounded parts too
+    for i, w in enumerate(words[:12]):
+        part = {"terms": [w[:1 + i % 2]], "path": "body", "starts_with": True, "top": 3 + i, "skip": i % 2}
+        if i % 3 == 0:
+            part["boost"] = 1.5
+        hits, _ = index.field_search(part)
+        want = oracle.call("field_search", part=part)["hits_scores"]
+        assert sorted((h[0], round(float(h[1]), 4)) for h in hits) == sorted((h[0], round(float(h[1]), 4)) for h in want), part
+
+
+def test_per_part_top_does_not_bound_ids(test_all):
+    """Filter, boost_term and phrase parts are searched for ids, which are collected before the per-part bound
+    (search_field.rs:305-307): `top` on them changes nothing."""
+    index, oracle = test_all
+    compare(index, oracle, [
+        {"search_req": OR_MAJ_URGE, "filter": S("1587690", "ent_seq", top=1)},
+        {"search_req": OR_MAJ_URGE, "filter": {"or": {"queries": [S("15", "ent_seq", starts_with=True, top=1), S("urge", "meanings.eng[]", top=0)]}}},
+        {"search_req": S("will", "meanings.eng[]"), "boost_term": [{"terms": ["9"], "path": "ent_seq", "starts_with": True, "boost": 5.0, "top": 1}]},
+        {"search_req": S("will", "meanings.eng[]", top=1), "boost_term": [{"terms": ["9555"], "path": "ent_seq", "boost": 5.0, "top": 0}]},
+        {"search_req": S("maje", "meanings.ger[]", starts_with=True, top=1)},
+        {"search_req": {"or": {"queries": [S("maje", "meanings.ger[]", starts_with=True, top=2, skip=1), S("urge", "meanings.eng[]")]}}},
+    ])

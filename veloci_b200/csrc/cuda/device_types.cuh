@@ -133,6 +133,7 @@ enum PartFlags : uint32_t {
     kPartRawCase = 4u,        // ignore_case == false: match on raw scalars
     kPartCheckPrefix = 8u,    // starts_with || levenshtein != 0  (:302)
     kPartHasBoost = 16u,
+    kPartInjected = 128u,     // its (term id, score) hits are given by the host (per-part top/skip bound), not matched in this batch
     kPartList = 32u,          // not a search part: its tile bucket is filled by a list producer (phrase pairs, text locality, 1:n boosts)
     kPartListBoost = 64u,     // list part of a 1:n boost: entries carry 0x7FFFFFFF - value id; the tile keeps the smallest value id of an
                               // anchor plus (bit 31) whether the anchor has several

@@ -408,7 +408,7 @@ __global__ void score_scatter_kernel(ScoreScatterArgs a) {
     const PartQuery& q = a.parts[r.part];
     float score;
     uint32_t term_id;
-    if (a.inj_terms) {
+    if (a.inj_terms && (a.inj_all || (q.flags & kPartInjected))) {
         term_id = a.inj_terms[r.slot];
         score = a.inj_scores[r.slot];
     } else {

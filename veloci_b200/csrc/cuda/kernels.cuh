@@ -49,8 +49,9 @@ struct ScoreScatterArgs {
     uint32_t* g_row;
     uint32_t* g_part;
     // step seam (vgpu_resolve_to_anchor): hits are given, record.slot indexes these arrays
-    const uint32_t* inj_terms;
+    const uint32_t* inj_terms;  // hits given by the host: records of injected parts index these arrays
     const float* inj_scores;
+    uint32_t inj_all;           // every record is injected (vgpu_resolve_to_anchor); else only those of kPartInjected parts
     // head-term planes: matches of plane terms are also registered per part (zeroed before the launch)
     PartPlanes* part_planes;
     uint32_t* g_plane;  // per grouped match: plane id or kNoValue

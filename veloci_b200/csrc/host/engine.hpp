@@ -31,6 +31,39 @@ struct ExplicitList {  // a caller-provided hit list used as a leaf (step seam)
 
 static const int kPhases = 6;
 
+struct TermHit {
+    uint32_t id;
+    float score;
+};
+
+// The per-part `top` bound of get_term_ids_in_field over hits in FST order (= ascending term id): once top + skip + 200
+// hits are held, the best top + skip by (score, id) stay and a hit scoring below the worst of them is dropped from then
+// on (search_field.rs:322-331, sort.rs:25-34); the part's boost comes after (:359-364), then the best top + skip by score
+// stay (:366-369; the reference's unstable sort leaves the choice among equal scores open, a stable one is used here).
+inline void bound_part_hits(const vhost::SearchPart& part, std::vector<TermHit>& hits) {
+    const size_t top_n = part.top ? (size_t)(*part.top + part.skip.value_or(0)) : 0;
+    if (part.top) {
+        float worst = -3.40282347e+38f;
+        std::vector<TermHit> kept;
+        for (const TermHit& h : hits) {
+            if (h.score < worst) continue;
+            if (!kept.empty() && kept.size() == top_n + 200) {
+                std::sort(kept.begin(), kept.end(), [](const TermHit& a, const TermHit& b) { return a.score != b.score ? a.score > b.score : a.id > b.id; });
+                kept.resize(top_n);
+                if (!kept.empty()) worst = kept.back().score;
+            }
+            kept.push_back(h);
+        }
+        hits.swap(kept);
+    }
+    if (part.boost)
+        for (TermHit& h : hits) h.score *= *part.boost;
+    if (part.top) {
+        std::stable_sort(hits.begin(), hits.end(), [](const TermHit& a, const TermHit& b) { return a.score > b.score; });
+        if (hits.size() > top_n) hits.resize(top_n);
+    }
+}
+
 struct Batch {
     DeviceIndex* ix = nullptr;
     vplan::BatchPlan plan;
@@ -337,7 +370,7 @@ struct Batch {
         if (mode == kRequests) {
             for (uint32_t p = 0; p < n_parts; ++p) {
                 const PartQuery& pq = plan.parts[p];
-                if (pq.flags & kPartList) continue;
+                if (pq.flags & (kPartList | kPartInjected)) continue;
                 const uint32_t d = plan.part_dict[p];
                 const DictDev& dict = ix->dicts.at(plan.dict_names[d]);
                 bool probe = pq.m >= 1 && pq.d_match <= 2 && !(pq.flags & (kPartPrefix | kPartRawCase));
@@ -423,9 +456,18 @@ struct Batch {
         if (mode == kRequests) {
             const size_t n_dicts = parts_of_dict.size();
             std::vector<unsigned long long> overflow(n_dicts + 1);
+            std::vector<MatchRecord> injected;
+            if (!plan.bounded.empty()) match_bounded_parts(injected);
+            if (injected.size() > d_records.n) d_records.reserve(injected.size() + 1024);
             for (int attempt = 0; attempt < 2; ++attempt) {
                 VDEV_CUDA(cudaMemsetAsync(d_counters.p, 0, d_counters.bytes(), stream));
                 VDEV_CUDA(cudaMemsetAsync(d_overflow_count.p, 0, d_overflow_count.bytes(), stream));
+                if (!injected.empty()) {  // the given hits take the first records; the match kernels append after them
+                    const unsigned long long n_inj = injected.size();
+                    VDEV_CUDA(cudaMemcpyAsync(d_records.p, injected.data(), injected.size() * sizeof(MatchRecord), cudaMemcpyHostToDevice, stream));
+                    VDEV_CUDA(cudaMemcpyAsync(d_counters.p, &n_inj, 8, cudaMemcpyHostToDevice, stream));
+                    VDEV_CUDA(cudaStreamSynchronize(stream));
+                }
                 const uint32_t capacity = (uint32_t)std::min<size_t>(d_records.n, 0xFFFFFFFFu);
                 for (size_t d = 0; d < n_dicts; ++d) {
                     const DictView dict = ix->dicts.at(plan.dict_names[d]).view();
@@ -474,13 +516,52 @@ struct Batch {
         a.part_begin = d_part_begin.p, a.dense_cursor = d_dense_cursor.p, a.sparse_cursor = d_sparse_cursor.p, a.n_dense_rows = reinterpret_cast<uint32_t*>(d_counters.p + 3);
         a.dense_row_capacity = M, a.dense_min = dense_min(), a.row_match = d_row_match.p, a.part_est = d_part_est.p;
         a.g_term = d_g_term.p, a.g_score = d_g_score.p, a.g_begin = d_g_begin.p, a.g_df = d_g_df.p, a.g_row = d_g_row.p, a.g_part = d_g_part.p;
-        a.inj_terms = mode == kTermHits ? d_inj_terms.p : nullptr, a.inj_scores = mode == kTermHits ? d_inj_scores.p : nullptr;
+        const bool has_injected = mode == kTermHits || !plan.bounded.empty();
+        a.inj_terms = has_injected ? d_inj_terms.p : nullptr, a.inj_scores = has_injected ? d_inj_scores.p : nullptr, a.inj_all = mode == kTermHits ? 1u : 0u;
         a.part_planes = use_planes ? d_part_planes.p : nullptr, a.g_plane = use_planes ? d_g_plane.p : nullptr;
         launch_score_scatter(stream, a);
         VDEV_CUDA(cudaEventRecord(ev[2], stream));
         VDEV_CUDA(cudaStreamSynchronize(stream));
         VDEV_CUDA(cudaGetLastError());
         matched = true;
+    }
+
+    // Parts with a per-part `top` (search_field.rs:292-294): matched and scored on the device in a batch of their own, bounded on
+    // the host in FST order (bound_part_hits), and handed to this batch as given (term id, score) hits.
+    void match_bounded_parts(std::vector<MatchRecord>& records) {
+        std::vector<vhost::SearchPart> device_parts;
+        for (auto& bp : plan.bounded) {
+            vhost::SearchPart p = bp.request;
+            p.top.reset(), p.skip.reset(), p.boost.reset();
+            device_parts.push_back(std::move(p));
+        }
+        Batch own;
+        std::vector<uint32_t> ids;
+        own.prepare_parts(ix, device_parts, &ids);
+        own.run_match();
+        std::vector<uint32_t> inj_terms;
+        std::vector<float> inj_scores;
+        for (size_t i = 0; i < plan.bounded.size(); ++i) {
+            std::vector<TermHit> hits;
+            own.download_part_hits(ids[i], hits);
+            bound_part_hits(plan.bounded[i].request, hits);
+            for (const TermHit& h : hits) {
+                records.push_back(MatchRecord{plan.bounded[i].part, (uint32_t)inj_terms.size()});
+                inj_terms.push_back(h.id), inj_scores.push_back(h.score);
+            }
+        }
+        d_inj_terms.upload(inj_terms), d_inj_scores.upload(inj_scores);
+        h2d_bytes += inj_terms.size() * 8 + records.size() * sizeof(MatchRecord);
+    }
+
+    // (term id, score) hits of one part after run_match, in ascending term id order (the FST stream's)
+    void download_part_hits(uint32_t part, std::vector<TermHit>& hits) {
+        std::vector<uint32_t> terms;
+        std::vector<float> scores;
+        download_matches(part, terms, scores);
+        hits.resize(terms.size());
+        for (size_t j = 0; j < terms.size(); ++j) hits[j] = TermHit{terms[j], scores[j]};
+        std::sort(hits.begin(), hits.end(), [](const TermHit& x, const TermHit& y) { return x.id < y.id; });
     }
 
     // (term id, score) hits of one part after run_match, unordered

@@ -207,7 +207,6 @@ struct BatchPlan {
         const vhost::SearchPart& req = part_in;
         if (req.terms.empty()) throw InvalidRequest("search part without terms");
         if (req.is_regex) throw Unsupported("regex search is outside the accelerated path");
-        if (req.top || req.skip) throw Unsupported("per-part top/skip is outside the accelerated path");
         if (req.token_value) throw Unsupported("token_value boost is outside the accelerated path");
         const FieldTables& ft = field_tables(req.path);
         const uint32_t did = ft.dict_id, pid = ft.postings_id;
@@ -245,8 +244,24 @@ struct BatchPlan {
             q.match_sym[j] = code_of(case_insensitive ? vfmt::lower_scalar(raw[j]) : raw[j]);
             q.score_sym[j] = code_of(low[j]);
         }
+        if (req.top) {
+            // The per-part bound (search_field.rs:292-294,:322-331,:366-369) depends on the order the hits arrive in: the engine
+            // matches such a part on its own first, bounds its hits on the host and gives them to the batch (kPartInjected).
+            q.flags |= vdev::kPartInjected;
+            const uint32_t id = (uint32_t)parts.size();
+            parts.push_back(q);
+            part_dict.push_back(did);
+            part_hash.push_back(0);  // never shared
+            bounded.push_back(BoundedPart{id, req});
+            return id;
+        }
         return find_or_add_part(q, did, hash_part(q));
     }
+    struct BoundedPart {
+        uint32_t part;
+        vhost::SearchPart request;
+    };
+    std::vector<BoundedPart> bounded;
 
     // A part whose hits are produced by a list kernel (phrase pairs, text locality, 1:n boosts) instead of a field search.
     uint32_t add_list_part() {
@@ -284,8 +299,16 @@ struct BatchPlan {
             }
             PartQuery q = o.parts[i];
             if (q.postings != vdev::kNoValue) q.postings = post_map[q.postings];
+            if (o.part_hash[i] == 0) {  // bounded parts neither
+                part_map[i] = (uint32_t)parts.size();
+                parts.push_back(q);
+                part_dict.push_back(dict_map[o.part_dict[i]]);
+                part_hash.push_back(0);
+                continue;
+            }
             part_map[i] = find_or_add_part(q, dict_map[o.part_dict[i]], o.part_hash[i]);
         }
+        for (BoundedPart& bp : o.bounded) bounded.push_back(BoundedPart{part_map[bp.part], std::move(bp.request)});
         const uint32_t leaf_base = (uint32_t)leaf_part.size(), prog_base = (uint32_t)prog.size(), boost_base = (uint32_t)boosts.size(), facet_base = (uint32_t)facets.size();
         for (vdev::PhraseMember m : o.phrase_members) {
             m.part1 = part_map[m.part1], m.part2 = part_map[m.part2], m.list_part = part_map[m.list_part];
@@ -322,6 +345,14 @@ struct BatchPlan {
         max_k = std::max(max_k, o.max_k);
     }
 
+    // A part whose hits_ids are used: they are collected before the per-part bound (search_field.rs:305-307).
+    uint32_t add_part_for_ids(const vhost::SearchPart& part) {
+        if (!part.top) return add_part(part);
+        vhost::SearchPart unbounded = part;
+        unbounded.top.reset(), unbounded.skip.reset();
+        return add_part(unbounded);
+    }
+
     // A part searched for ids only (filter trees, boost_term): its matched term ids, taken as text ids, resolve to
     // anchors through text_id_to_anchor (search_field.rs:468-498).  Returns the list part that receives them.
     uint32_t add_ids_part(const vhost::SearchPart& part) {
@@ -329,7 +360,7 @@ struct BatchPlan {
         if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
         vdev::IdsMember m;
         memset(&m, 0, sizeof m);
-        m.part = add_part(part);
+        m.part = add_part_for_ids(part);
         m.identity = ix->host->is_anchor_identity_column(path) ? 1u : 0u;
         if (!m.identity) {
             auto it = ix->stores.find(path + ".text_id_to_anchor");
@@ -594,7 +625,7 @@ struct BatchPlan {
                 if (!vfmt::ends_with(path, ".phrase_pair_to_anchor")) path += ".phrase_pair_to_anchor";
                 auto it = ix->phrases.find(path);
                 if (it == ix->phrases.end()) ix->host->path_not_found(path);
-                entries.push_back(Entry{pb.search1.terms[0], pb.search2.terms[0], add_part(pb.search1), add_part(pb.search2), it->second.view()});
+                entries.push_back(Entry{pb.search1.terms[0], pb.search2.terms[0], add_part_for_ids(pb.search1), add_part_for_ids(pb.search2), it->second.view()});
             }
             std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return std::tie(a.t1, a.t2) < std::tie(b.t1, b.t2); });
             for (size_t i = 0; i < entries.size();) {

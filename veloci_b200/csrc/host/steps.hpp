@@ -84,41 +84,13 @@ inline void field_search(vdev::DeviceIndex& ix, const char* part_json, bool get_
 }
 
 // suggest_multi / suggest (search_field.rs:147-228): every part's fuzzy match and scoring run on the device in one batch
-// (get_term_ids_in_field, get_scores + return_term); the per-part top/skip bound (:292-294,:322-331,:366-369), the merge of
+// (get_term_ids_in_field, get_scores + return_term); the per-part top/skip bound (vdev::bound_part_hits), the merge of
 // equal texts and the final order are a few hundred elements of host work.
 struct Suggestion {
     std::string text;
     float score;
     uint32_t id;
 };
-
-// The per-part `top` bound of get_term_ids_in_field over hits in FST order (= ascending term id): once top + skip + 200
-// hits are held, the best top + skip by (score, id) stay and a hit scoring below the worst of them is dropped from then
-// on (sort.rs:25-34); the part's boost comes after, then the best top + skip by score stay.
-inline void bound_part_hits(const vhost::SearchPart& part, std::vector<vgpu_hit>& hits) {
-    if (part.top) {
-        const size_t top_n = (size_t)(*part.top + part.skip.value_or(0));
-        float worst = -3.40282347e+38f;
-        std::vector<vgpu_hit> kept;
-        for (const vgpu_hit& h : hits) {
-            if (h.score < worst) continue;
-            if (!kept.empty() && kept.size() == top_n + 200) {
-                std::sort(kept.begin(), kept.end(), [](const vgpu_hit& a, const vgpu_hit& b) { return a.score != b.score ? a.score > b.score : a.id > b.id; });
-                kept.resize(top_n);
-                if (!kept.empty()) worst = kept.back().score;
-            }
-            kept.push_back(h);
-        }
-        hits.swap(kept);
-    }
-    if (part.boost)
-        for (vgpu_hit& h : hits) h.score *= *part.boost;
-    if (part.top) {
-        const size_t top_n = (size_t)(*part.top + part.skip.value_or(0));
-        std::stable_sort(hits.begin(), hits.end(), [](const vgpu_hit& a, const vgpu_hit& b) { return a.score > b.score; });
-        if (hits.size() > top_n) hits.resize(top_n);
-    }
-}
 
 inline std::vector<Suggestion> suggest(vdev::DeviceIndex& ix, const vhost::Request& req) {
     if (!req.suggest) throw vplan::InvalidRequest("only suggest allowed in suggest function");
@@ -137,17 +109,13 @@ inline std::vector<Suggestion> suggest(vdev::DeviceIndex& ix, const vhost::Reque
         b.prepare_parts(&ix, device_parts, &part_ids);
         b.run_match();
         for (size_t i = 0; i < device_parts.size(); ++i) {
-            std::vector<uint32_t> terms;
-            std::vector<float> scores;
-            b.download_matches(part_ids[i], terms, scores);
-            std::vector<vgpu_hit> hits(terms.size());
-            for (size_t j = 0; j < terms.size(); ++j) hits[j] = vgpu_hit{terms[j], scores[j]};
-            std::sort(hits.begin(), hits.end(), [](const vgpu_hit& x, const vgpu_hit& y) { return x.id < y.id; });
-            bound_part_hits((*req.suggest)[i], hits);
+            std::vector<vdev::TermHit> hits;
+            b.download_part_hits(part_ids[i], hits);
+            vdev::bound_part_hits((*req.suggest)[i], hits);
             std::string path = device_parts[i].path;
             if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
             const vhost::TermDict& dict = ix.host->dict.at(path);
-            for (const vgpu_hit& h : hits) {
+            for (const vdev::TermHit& h : hits) {
                 size_t slot = 0;
                 if (!dict.find_id(h.id, slot)) continue;
                 all.push_back(Suggestion{vfmt::to_lowercase(dict.term(slot)), h.score, h.id});  // return_term_lowercase
