@@ -148,9 +148,17 @@ class Batch:
         self.index = index
         self.n = len(requests)
         self.h = ctypes.c_void_p()
-        if self.n >= 64 and all(isinstance(r, str) and r and "\n" not in r for r in requests):
-            # many requests: one JSON-lines buffer instead of one C string per request
-            blob = "\n".join(requests).encode("utf-8")
+        blob = None
+        if self.n >= 64:
+            # many requests: one JSON-lines buffer instead of one C string per request (when every request is a non-empty
+            # string without a line break: then the buffer has exactly n - 1 of them and no empty line)
+            try:
+                text = "\n".join(requests)
+                if text.count("\n") == self.n - 1 and "\n\n" not in text and not text.startswith("\n") and not text.endswith("\n"):
+                    blob = text.encode("utf-8")
+            except TypeError:
+                blob = None
+        if blob is not None:
             n = ctypes.c_uint32()
             _check(self.L.vgpu_batch_prepare_jsonl(index.h, blob, len(blob), ctypes.byref(n), ctypes.byref(self.h)))
             assert n.value == self.n

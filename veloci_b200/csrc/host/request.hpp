@@ -457,8 +457,8 @@ class RequestReader : private vjson::Parser {
         else field = read();
     }
 
+    // (the read_* functions fill a freshly constructed object)
     void read_boost_part(BoostPart& b) {
-        b = BoostPart();
         bool have_path = false;
         std::string fun;
         members("boost part must be an object", [&](const std::string& k) {
@@ -505,7 +505,6 @@ class RequestReader : private vjson::Parser {
         return bs;
     }
     void read_options(SearchOptions& o) {
-        o = SearchOptions();
         o.present = true;
         members("options must be an object", [&](const std::string& k) {
             if (is(k, "explain")) {
@@ -522,7 +521,6 @@ class RequestReader : private vjson::Parser {
         });
     }
     void read_search_part(SearchPart& s) {
-        s = SearchPart();
         bool have_path = false, have_terms = false;
         members("search part must be an object", [&](const std::string& k) {
             if (is(k, "path")) {
@@ -555,8 +553,8 @@ class RequestReader : private vjson::Parser {
             } else if (is(k, "skip")) {
                 optional_field(s.skip, [&] { return u64("skip"); });
             } else if (is(k, "options")) {
-                if (null_next()) s.options = SearchOptions();
-                else read_options(s.options);
+                s.options = SearchOptions();
+                if (!null_next()) read_options(s.options);
             } else {
                 skip_value();
             }
@@ -596,8 +594,8 @@ class RequestReader : private vjson::Parser {
                     });
                     have_queries = true;
                 } else if (is(k, "options")) {
-                    if (null_next()) r.options = SearchOptions();
-                    else read_options(r.options);
+                    r.options = SearchOptions();
+                    if (!null_next()) read_options(r.options);
                 } else {
                     skip_value();
                 }
@@ -643,8 +641,8 @@ class RequestReader : private vjson::Parser {
                         PhraseBoost pb;
                         bool have1 = false, have2 = false;
                         members("phrase boost needs `search1` and `search2`", [&](const std::string& pk) {
-                            if (is(pk, "search1")) read_search_part(pb.search1), have1 = true;
-                            else if (is(pk, "search2")) read_search_part(pb.search2), have2 = true;
+                            if (is(pk, "search1")) pb.search1 = SearchPart(), read_search_part(pb.search1), have1 = true;
+                            else if (is(pk, "search2")) pb.search2 = SearchPart(), read_search_part(pb.search2), have2 = true;
                             else skip_value();
                         });
                         if (!have1 || !have2) throw RequestError("phrase boost needs `search1` and `search2`");
