@@ -128,7 +128,7 @@ struct Batch {
     uint64_t stat_fast_items = 0, stat_general_items = 0, stat_plane_evaluated = 0;
     // between execute_begin and execute_finish
     unsigned long long pending_items = 0;
-    uint32_t pending_fast_items = 0, seeded_tiles = 0;
+    uint32_t pending_fast_items = 0, seeded_tiles = 0, seed_level = 5;
     bool begun = false;
     // device: per-request state and results
     DevBuf<unsigned long long> d_heap, d_tau, d_num_hits;
@@ -726,10 +726,14 @@ struct Batch {
             // Seed pass over the first tiles: only the anchors in the top 1/64 of the boost column are evaluated (and nothing
             // is counted), which gives every request a threshold close to its final one for a fraction of a tile's work.
             // Without a boost column in the batch the first tile runs in full instead.
-            seeded_tiles = lev_dev ? std::min<uint32_t>(8, n_tiles) : 0;
+            uint32_t want_tiles = 8;
+            seed_level = 5;
+            if (const char* env = getenv("VELOCI_SEED_TILES")) want_tiles = (uint32_t)std::max(0, atoi(env));
+            if (const char* env = getenv("VELOCI_SEED_LEVEL")) seed_level = (uint32_t)std::min(15, std::max(1, atoi(env)));
+            seeded_tiles = lev_dev ? std::min<uint32_t>(want_tiles, n_tiles) : 0;
             if (seeded_tiles) {
                 PlaneArgs seed = plane_stage_args(0, 0, seeded_tiles);
-                seed.pass_mode = 1, seed.seed_level = 5;
+                seed.pass_mode = 1, seed.seed_level = seed_level;
                 launch_plane_eval(stream, seed, n_sms);
             } else {
                 launch_plane_eval(stream, plane_stage_args(0, 0, std::min<uint32_t>(1, n_tiles)), n_sms);
@@ -752,7 +756,7 @@ struct Batch {
             const uint32_t first = seeded_tiles ? 0u : std::min<uint32_t>(1, n_tiles);
             if (n_tiles > first) {
                 PlaneArgs rest = plane_stage_args(2, first, n_tiles);
-                rest.pass_mode = seeded_tiles ? 2 : 0, rest.seed_level = 5, rest.seeded_tiles = seeded_tiles;
+                rest.pass_mode = seeded_tiles ? 2 : 0, rest.seed_level = seed_level, rest.seeded_tiles = seeded_tiles;
                 launch_plane_eval(stream, rest, n_sms);
             }
         }
