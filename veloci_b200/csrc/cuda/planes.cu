@@ -28,6 +28,7 @@ namespace vdev {
 static const int kPlaneThreads = 512;
 static const int kPlaneWarps = kPlaneThreads / 32;
 static const uint32_t kQueueCap = 64;      // pending candidates of a warp: evaluated 32 at a time, one anchor per lane
+static const uint32_t kMergeGroup = 8;   // keys of one request merged into its top-k under one lock round trip
 static const uint32_t kHashSlots = 256;    // >= 2 * kFastMaxEntries
 static const uint32_t kHashEmpty = 0xFFFFFFFFu;
 static const uint32_t kEntRegs = kFastMaxEntries / 32;  // entries a lane holds
@@ -41,11 +42,11 @@ struct WarpScratch {
     uint32_t hval[kHashSlots];
     // candidates waiting for their exact evaluation; self-contained, so they outlive the item that produced them
     uint32_t cand_q[kQueueCap];            // request
-    uint32_t cand_idx[kQueueCap];          // anchor index in the tile
+    uint16_t cand_idx[kQueueCap];          // anchor index in the tile (< 8192)
     float cand_e[kFastMaxLeaves][kQueueCap];  // per part: largest entry score of the anchor (0: none)
     uint16_t ent_idx[kFastMaxEntries];     // index in tile | leaf << 13 of entry r * 32 + lane
     uint32_t ent_key[kFastMaxEntries];     // its score key
-    unsigned long long merge[kFastMaxK + 1];
+    unsigned long long merge[kFastMaxK + kMergeGroup];  // a request's top-k plus the keys merged into it in one go
     // state of the item being processed (warp-uniform)
     unsigned long long tau;                // the request's k-th best so far (0: fewer than k hits)
     float tau_score;                       // score of tau when pruning is possible, else 0
@@ -235,7 +236,9 @@ __device__ __forceinline__ void compute_levels(WarpScratch& S, uint32_t lane, ui
 }
 
 // Inserts one hit into the request's heap (sorted, k slots) under its lock, if it still beats the k-th best.
-__device__ __noinline__ void merge_one(const CtaContext* C, WarpScratch* Sp, uint32_t lane, uint32_t q, unsigned long long comp) {
+__device__ __noinline__ void merge_group(const CtaContext* C, WarpScratch* Sp, uint32_t lane, uint32_t q, unsigned long long comp, uint32_t group) {
+    // Merges the order keys of the lanes in `group` (at most kMergeGroup, all of request q, each above the threshold it was
+    // compared with) into the request's top-k under its lock: one lock round trip for all of them.
     WarpScratch& S = *Sp;
     const uint32_t k = C->fast[q].k;
     unsigned long long* heap = C->heap + (size_t)q * C->heap_stride;
@@ -245,10 +248,12 @@ __device__ __noinline__ void merge_one(const CtaContext* C, WarpScratch* Sp, uin
     }
     __syncwarp();
     for (uint32_t i = lane; i < k; i += 32) S.merge[i] = __ldcg(heap + i);
-    if (lane == 0) S.merge[k] = comp;
+    const uint32_t cnt = __popc(group);
+    if (group & (1u << lane)) S.merge[k + __popc(group & ((1u << lane) - 1u))] = comp;
     __syncwarp();
-    const uint32_t n = k + 1;
-    if (comp > S.merge[k - 1]) {
+    const uint32_t n = k + cnt;
+    const unsigned long long worst = S.merge[k - 1];
+    if (__ballot_sync(0xFFFFFFFFu, (group & (1u << lane)) && comp > worst)) {
         for (uint32_t e = lane; e < n; e += 32) {
             const unsigned long long key = S.merge[e];
             if (key == 0) continue;
@@ -343,12 +348,17 @@ __device__ __noinline__ void drain(const CtaContext* C, WarpScratch* Sp, uint32_
         if (comp <= __ldcg(C->tau + q)) comp = 0;
     }
     uint32_t m = __ballot_sync(0xFFFFFFFFu, comp != 0);
-    while (m) {
+    while (m) {  // survivors of one request (an item's candidates are neighbours in the list) merge together
         const int src = __ffs((int)m) - 1;
-        m &= m - 1u;
         const uint32_t sq = __shfl_sync(0xFFFFFFFFu, q, src);
-        const unsigned long long sc = __shfl_sync(0xFFFFFFFFu, comp, src);
-        merge_one(C, Sp, lane, sq, sc);
+        uint32_t group = __ballot_sync(0xFFFFFFFFu, comp != 0 && q == sq) & m;
+        if (__popc(group) > (int)kMergeGroup) {  // the lowest kMergeGroup lanes of the group now, the others next time round
+            uint32_t rest = group;
+            for (uint32_t i = 0; i < kMergeGroup; ++i) rest &= rest - 1u;
+            group &= ~rest;
+        }
+        m &= ~group;
+        merge_group(C, Sp, lane, sq, comp, group);
     }
 }
 
@@ -360,7 +370,7 @@ __device__ __forceinline__ void enqueue(const CtaContext* C, WarpScratch& S, uin
     if (!m) return;
     if (flag) {
         const uint32_t at = qn + __popc(m & ((1u << lane) - 1u));
-        S.cand_q[at] = S.q, S.cand_idx[at] = idx;
+        S.cand_q[at] = S.q, S.cand_idx[at] = (uint16_t)idx;
         S.cand_e[0][at] = e0, S.cand_e[1][at] = e1, S.cand_e[2][at] = e2, S.cand_e[3][at] = e3;
     }
     qn += __popc(m);

@@ -597,9 +597,10 @@ struct Batch {
         // ~24 units per SM (tail balance on small shards)
         uint32_t unit = stage == 2 ? std::max<uint32_t>(256, (uint32_t)(((uint64_t)n * (t1 - t0)) / ((uint64_t)n_sms * 24) + 1))
                                    : std::max<uint32_t>(16, ((uint64_t)n * (t1 - t0) + want_units - 1) / want_units);
-        uint32_t unit_cap = 4096u;
-        if (const char* env = getenv("VELOCI_UNIT_ITEMS")) unit_cap = (uint32_t)std::max(16, atoi(env));
-        unit = (std::min<uint32_t>(unit, unit_cap) + 15u) & ~15u;
+        unit = std::min<uint32_t>(unit, 4096u);
+        if (const char* env = getenv("VELOCI_UNIT_ITEMS"))  // experiments: items per unit of the bulk pass, as given
+            if (stage == 2) unit = (uint32_t)std::min(4096, std::max(16, atoi(env)));
+        unit = (unit + 15u) & ~15u;
         a.tile_begin = t0, a.unit_items = unit;
         a.chunks_per_tile = (n + unit - 1) / unit;
         a.n_units = (t1 - t0) * a.chunks_per_tile;
@@ -754,8 +755,10 @@ struct Batch {
         if (planes_on && pending_fast_items) {
             // the normal pass: every tile (the seeded ones skip what the seed pass evaluated), or the tiles after the first
             const uint32_t first = seeded_tiles ? 0u : std::min<uint32_t>(1, n_tiles);
-            if (n_tiles > first) {
-                PlaneArgs rest = plane_stage_args(2, first, n_tiles);
+            uint32_t last = n_tiles;
+            if (const char* env = getenv("VELOCI_TILE_LIMIT")) last = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, atoi(env)));  // timing experiments only: wrong results
+            if (last > first) {
+                PlaneArgs rest = plane_stage_args(2, first, last);
                 rest.pass_mode = seeded_tiles ? 2 : 0, rest.seed_level = seed_level, rest.seeded_tiles = seeded_tiles;
                 launch_plane_eval(stream, rest, n_sms);
             }
