@@ -80,6 +80,10 @@ int32_t vgpu_batch_prepare(vgpu_index* idx, const char* const* request_json, uin
 /* The same with the requests as JSON lines in one buffer (one `search::Request` per line; empty lines are skipped):
  * what a server hands over when it drains its request queue.  *n_requests receives the number of requests found. */
 int32_t vgpu_batch_prepare_jsonl(vgpu_index* idx, const char* text, size_t len, uint32_t* n_requests, vgpu_batch** out);
+/* The same for exactly `n` requests joined by single line feeds (an empty line is an empty request, which fails like one):
+ * what a binding passes instead of n C strings.  VGPU_ERR_INVALID_REQUEST, before any work, when the buffer does not hold
+ * n - 1 line feeds (some request contains one: the caller then uses vgpu_batch_prepare). */
+int32_t vgpu_batch_prepare_lines(vgpu_index* idx, const char* text, size_t len, uint32_t n, vgpu_batch** out);
 int32_t vgpu_batch_execute(vgpu_batch* batch);
 void vgpu_batch_free(vgpu_batch* batch);
 

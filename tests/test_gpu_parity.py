@@ -402,3 +402,36 @@ def test_parts_shared_by_what_the_device_sees(small):
         {"search_req": {"and": {"queries": [P(w[1], levenshtein_distance=1, ignore_case=True), P(w[1], levenshtein_distance=1), P(w[2], starts_with=True)]}}},
     ]
     compare_batch(index, oracle, [json.dumps(r) for r in reqs] * 30, k=10)
+
+
+def test_batches_as_lines_with_line_feeds_and_empty_requests(small):
+    """Batches of 64+ request strings travel as one line-feed separated buffer (vgpu_batch_prepare_lines); a request that
+    contains a line feed (pretty-printed JSON) sends the batch down the one-string-per-request path instead, an empty
+    request fails alone.  Results are the same either way."""
+    index, oracle, _ = small
+    reqs = helpers.synthetic_requests(num_queries=100, query_kind="or3", levenshtein=1, query_seed=41, **SMALL)
+    plain = index.search_batch(reqs, k=10)
+    b = index.prepare(reqs).execute()
+    lines = b.results_flat(10)
+    b.close()
+    assert np.array_equal(lines["ids"], plain["ids"]) and np.array_equal(lines["num_hits"], plain["num_hits"])
+    pretty = list(reqs)
+    pretty[7] = json.dumps(json.loads(reqs[7]), indent=2)
+    assert "\n" in pretty[7]
+    pretty[50] = ""
+    pretty[99] = "\n"
+    b = index.prepare(pretty).execute()
+    got = b.results_flat(10)
+    assert [int(s) for s in got["status"][[7, 50, 99]]] == [0, 5, 5]
+    ok = got["status"] == 0
+    assert ok.sum() == 98
+    assert np.array_equal(got["ids"][ok], plain["ids"][ok]) and np.array_equal(got["num_hits"][ok], plain["num_hits"][ok])
+    b.close()
+    with_empty = list(reqs)
+    with_empty[0] = ""
+    with_empty[63] = ""
+    b = index.prepare(with_empty).execute()   # stays on the lines path: an empty line is an empty request
+    got = b.results_flat(10)
+    assert [int(s) for s in got["status"][[0, 63]]] == [5, 5] and (got["status"][1:63] == 0).all()
+    assert np.array_equal(got["ids"][1:63], plain["ids"][1:63])
+    b.close()

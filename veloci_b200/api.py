@@ -59,6 +59,7 @@ def load_library():
     L.vgpu_index_close.restype = None
     L.vgpu_index_info.argtypes = [vp, P(u64), P(u64), P(u64), P(u64)]
     L.vgpu_batch_prepare.argtypes = [vp, P(cp), u32, P(vp)]
+    L.vgpu_batch_prepare_lines.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, u32, P(vp)]
     L.vgpu_batch_prepare_jsonl.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, P(u32), P(vp)]
     L.vgpu_batch_execute.argtypes = [vp]
     L.vgpu_batch_execute_begin.argtypes = [vp]
@@ -148,23 +149,23 @@ class Batch:
         self.index = index
         self.n = len(requests)
         self.h = ctypes.c_void_p()
-        blob = None
-        if self.n >= 64:
-            # many requests: one JSON-lines buffer instead of one C string per request (when every request is a non-empty
-            # string without a line break: then the buffer has exactly n - 1 of them and no empty line)
-            try:
-                text = "\n".join(requests)
-                if text.count("\n") == self.n - 1 and "\n\n" not in text and not text.startswith("\n") and not text.endswith("\n"):
-                    blob = text.encode("utf-8")
-            except TypeError:
-                blob = None
-        if blob is not None:
-            n = ctypes.c_uint32()
-            _check(self.L.vgpu_batch_prepare_jsonl(index.h, blob, len(blob), ctypes.byref(n), ctypes.byref(self.h)))
-            assert n.value == self.n
-        else:
-            arr, self._keep = _encode_requests(requests)
-            _check(self.L.vgpu_batch_prepare(index.h, arr, self.n, ctypes.byref(self.h)))
+        if self.n >= 64 and self._prepare_lines(index, requests):
+            return
+        arr, self._keep = _encode_requests(requests)
+        _check(self.L.vgpu_batch_prepare(index.h, arr, self.n, ctypes.byref(self.h)))
+
+    def _prepare_lines(self, index, requests):
+        """Many requests: one buffer of line-feed separated requests instead of one C string each.  False when some request
+        is not a string or contains a line feed (the library checks the count of line feeds before doing anything)."""
+        try:
+            blob = "\n".join(requests).encode("utf-8")
+        except TypeError:
+            return False
+        rc = self.L.vgpu_batch_prepare_lines(index.h, blob, len(blob), self.n, ctypes.byref(self.h))
+        if rc == 1:  # VGPU_ERR_INVALID_REQUEST: not n - 1 line feeds
+            return False
+        _check(rc)
+        return True
 
     def execute(self):
         _check(self.L.vgpu_batch_execute(self.h))

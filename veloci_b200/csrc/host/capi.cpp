@@ -133,6 +133,38 @@ int32_t vgpu_batch_prepare(vgpu_index* idx, const char* const* request_json, uin
     });
 }
 
+int32_t vgpu_batch_prepare_lines(vgpu_index* idx, const char* text, size_t len, uint32_t n, vgpu_batch** out) {
+    if (!idx || !out || (len && !text)) {
+        t_error = "null argument";
+        return VGPU_ERR_INVALID_REQUEST;
+    }
+    *out = nullptr;
+    size_t feeds = 0;
+    for (const char* p = text; p && (p = static_cast<const char*>(memchr(p, '\n', (size_t)(text + len - p)))) != nullptr; ++p) ++feeds;
+    if (feeds + 1 != (size_t)n && !(n == 0 && len == 0)) {
+        t_error = "the buffer does not hold n requests separated by single line feeds";
+        return VGPU_ERR_INVALID_REQUEST;
+    }
+    return guarded([&]() {
+        std::unique_ptr<vgpu_batch> b(new vgpu_batch());
+        b->jsonl.assign(text, text + len);
+        b->jsonl.push_back('\0');
+        std::vector<const char*> lines;
+        lines.reserve(n);
+        char* p = b->jsonl.data();
+        char* end = p + len;
+        for (uint32_t i = 0; i < n; ++i) {
+            char* nl = static_cast<char*>(memchr(p, '\n', (size_t)(end - p)));
+            if (!nl) nl = end;
+            *nl = '\0';
+            lines.push_back(p);
+            p = nl < end ? nl + 1 : end;
+        }
+        b->b.prepare(idx->ix.get(), lines.data(), n);
+        *out = b.release();
+    });
+}
+
 int32_t vgpu_batch_prepare_jsonl(vgpu_index* idx, const char* text, size_t len, uint32_t* n_out, vgpu_batch** out) {
     if (!idx || !out || (len && !text)) {
         t_error = "null argument";
