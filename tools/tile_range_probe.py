@@ -18,4 +18,5 @@ for limit in (0, 8, 16, 32, 64, 153, 306, 612, 1221):
     t = []
     for _ in range(3):
         a = time.perf_counter(); batch.execute(); t.append(time.perf_counter() - a)
+    os.environ["VELOCI_DEBUG"] = "1"; batch.execute(); batch.results_flat(10); os.environ.pop("VELOCI_DEBUG")
     print(f"tiles {limit or 'all'}: {1000*min(t):.2f} ms plane_eval {batch.phase_ms()[3]:.2f} evaluated {batch.path_stats()['plane_evaluated']}", flush=True)

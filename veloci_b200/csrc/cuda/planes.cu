@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
     for (uint32_t i = lane; i < 256; i += 32) S.ebits[i] = 0, S.mbits[i] = 0;
     for (uint32_t i = lane; i < kHashSlots; i += 32) S.hkey[i] = kHashEmpty, S.hval[i] = 0;
     if (lane == 0) S.mult_lev = nullptr, S.mult_fun = 0xFFFFFFFFu, S.mult_param = 0.0f;
-    unsigned long long st_cand = 0, st_items = 0;  // lane 0
+    unsigned long long st_cand = 0, st_items = 0, st_general = 0, st_sweepless = 0;  // lane 0
 
     while (true) {
         __syncthreads();
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
             for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
             if (lane == 0) {
                 if (cnt && !seed_pass) atomicAdd(a.num_hits + it_cur.q, (unsigned long long)cnt);
-                st_cand += ncand, st_items += 1;
+                st_cand += ncand, st_items += 1, st_general += (!sweepless && !lower_dead) ? 1 : 0, st_sweepless += sweepless ? 1 : 0;
             }
             if (n_ent) {  // leave the entry bitmap and the hash table empty
                 __syncwarp();
@@ -773,6 +773,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
     if (lane == 0 && st_items) {
         atomicAdd(a.stats + 0, st_items);
         atomicAdd(a.stats + 1, st_cand);
+        atomicAdd(a.stats + 5, st_general);    // items swept with the exact per-anchor part count (threshold not converged)
+        atomicAdd(a.stats + 6, st_sweepless);  // items answered from the per-plane counts
     }
 }
 

@@ -807,11 +807,14 @@ struct Batch {
         if (n) {
             VDEV_CUDA(cudaMemcpyAsync(h_keys.data(), d_out_keys.p, h_keys.size() * 8, cudaMemcpyDeviceToHost, stream));
             VDEV_CUDA(cudaMemcpyAsync(h_hits.data(), d_out_hits.p, h_hits.size() * 8, cudaMemcpyDeviceToHost, stream));
-            uint64_t stats[10];
+            uint64_t stats[16];
             VDEV_CUDA(cudaMemcpyAsync(stats, d_counters.p, sizeof stats, cudaMemcpyDeviceToHost, stream));
             VDEV_CUDA(cudaStreamSynchronize(stream));
             stat_postings = stats[2];
             stat_plane_evaluated = stats[9];
+            if (getenv("VELOCI_DEBUG") && use_planes)
+                fprintf(stderr, "[veloci] plane path: %llu item evaluations (seed + bulk), %llu candidates, %llu items swept before their threshold converged, %llu answered from plane counts\n",
+                        (unsigned long long)stats[8], (unsigned long long)stats[9], (unsigned long long)stats[13], (unsigned long long)stats[14]);
             d2h_bytes += h_keys.size() * 8 + h_hits.size() * 8 + sizeof stats;
             stat_union = 0;
             for (uint64_t h : h_hits) stat_union += h;
