@@ -214,6 +214,7 @@ struct PlaneArgs {
     // counted: it gives every request a useful threshold for a fraction of a tile's evaluations.  2: the normal pass over
     // tiles that were seeded (tiles below `seeded_tiles`): the anchors the seed pass evaluated are skipped.
     uint32_t pass_mode, seed_level, seeded_tiles;
+    uint32_t force_general;  // timing experiments: never take the converged-threshold sweep
     // per-query state (shared with tile_eval_kernel)
     unsigned long long* heap;
     uint32_t heap_stride;

@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) plane_eval_kernel(PlaneArgs 
 
             // plane sweep: four 32-anchor words per lane and step
             const int lev_top = S.lev[L - 1];
-            bool lower_dead = true;
+            bool lower_dead = a.force_general == 0;
 #pragma unroll
             for (int i2 = 0; i2 < (int)kFastMaxLeaves - 1; ++i2)
                 if ((uint32_t)i2 + 1 < L && S.lev[i2] != -2) lower_dead = false;

@@ -602,6 +602,7 @@ struct Batch {
             if (stage == 2) unit = (uint32_t)std::min(4096, std::max(16, atoi(env)));
         unit = (unit + 15u) & ~15u;
         a.tile_begin = t0, a.unit_items = unit;
+        a.force_general = getenv("VELOCI_FORCE_GENERAL_SWEEP") ? 1u : 0u;
         a.chunks_per_tile = (n + unit - 1) / unit;
         a.n_units = (t1 - t0) * a.chunks_per_tile;
         a.work_counter = d_counters.p + 10 + stage;
