@@ -76,10 +76,13 @@ class ClockSampler:
     def __init__(self, device):
         self.device = device
         self.samples = []
+        self.source = "nvidia-smi"
         self.stop = threading.Event()
         self.thread = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
+        if self.run_nvml():
+            return
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.device)], capture_output=True, text=True, timeout=5).stdout.strip()
@@ -88,6 +91,32 @@ class ClockSampler:
             except Exception:
                 pass
             self.stop.wait(0.2)
+
+    def run_nvml(self):
+        """The same readings through NVML (what nvidia-smi calls), every 10 ms: a 5-step timed region lasts ~0.1 s, too short
+        for more than one nvidia-smi process.  False when NVML is not usable (the nvidia-smi loop runs instead)."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.device)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons_of = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        self.source = "nvml"
+        bits = ((0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5))  # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while not self.stop.is_set():
+            try:
+                row = [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "", "", "", ""]
+                mask = reasons_of(h)
+                for bit, col in bits:
+                    row[col] = "Active" if mask & bit else "Not Active"
+                self.samples.append(row)
+            except Exception:
+                pass
+            self.stop.wait(0.01)
+        return True
 
     def __enter__(self):
         self.thread.start()
@@ -102,7 +131,7 @@ class ClockSampler:
         mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 def run_reference(args):
