@@ -35,7 +35,7 @@ enum {
     VGPU_ERR_JSON = 5,            /* VelociError::JsonError (serde) */
     VGPU_ERR_CUDA = 6,
     VGPU_ERR_NCCL = 7,
-    VGPU_ERR_UNSUPPORTED = 8,     /* valid veloci request outside the accelerated path (regex, per-part top, ...) */
+    VGPU_ERR_UNSUPPORTED = 8,     /* valid veloci request outside the accelerated path (see DESIGN.md "Known limits") */
     VGPU_ERR_INTERNAL = 9
 };
 
@@ -61,6 +61,10 @@ int32_t vgpu_device_count(void);
  * [rank*num_docs/n_shards, (rank+1)*num_docs/n_shards): postings, anchor-keyed
  * stores and boost columns are cut to it; term-keyed structures are replicated. */
 int32_t vgpu_index_open(const char* dir, int32_t device, uint32_t shard_rank, uint32_t n_shards, vgpu_index** out);
+/* The same with build options (diagnostics and A/B tests; results never depend on them): without head-term planes every
+ * request takes the posting path, without the deletion-neighbourhood index every fuzzy part scans the dictionary. */
+enum { VGPU_OPEN_NO_PLANES = 1, VGPU_OPEN_NO_DELETION_INDEX = 2 };
+int32_t vgpu_index_open_ex(const char* dir, int32_t device, uint32_t shard_rank, uint32_t n_shards, uint32_t flags, vgpu_index** out);
 void vgpu_index_close(vgpu_index* idx);
 /* num_docs of metaData.json and the anchor range this handle owns. */
 int32_t vgpu_index_info(const vgpu_index* idx, uint64_t* num_docs, uint64_t* anchor_lo, uint64_t* anchor_hi, uint64_t* device_bytes);
@@ -87,6 +91,8 @@ int32_t vgpu_batch_prepare_lines(vgpu_index* idx, const char* text, size_t len, 
 int32_t vgpu_batch_execute(vgpu_batch* batch);
 void vgpu_batch_free(vgpu_batch* batch);
 
+/* Number of requests of the batch (a batch made from a plan never saw the request strings). */
+int32_t vgpu_batch_size(const vgpu_batch* batch, uint32_t* n);
 /* Per-request status (VGPU_OK or the error of that request) and message. */
 int32_t vgpu_batch_status(const vgpu_batch* batch, uint32_t q);
 const char* vgpu_batch_message(const vgpu_batch* batch, uint32_t q);
@@ -110,7 +116,39 @@ int32_t vgpu_batch_facet_group(const vgpu_batch* batch, uint32_t q, uint32_t fie
 /* One-call form: prepare + execute + results_flat + free.  The e2e path of bench.py. */
 int32_t vgpu_search_batch(vgpu_index* idx, const char* const* request_json, uint32_t n, uint32_t k, uint32_t* ids, float* scores, uint64_t* num_hits, int32_t* status);
 
-/* ---- multi-GPU merge (anchor-range shards) ----------------------
+/* ---- multi-GPU (anchor-range shards) ----------------------------
+ * One process per GPU.  Process r opens shard r of n (vgpu_index_open with shard_rank = r, n_shards = n), one process
+ * calls vgpu_comm_unique_id and hands the 128 bytes to the others (any channel: it is an ncclUniqueId), every process
+ * calls vgpu_comm_init.  From then on vgpu_batch_execute on that handle is a collective: every rank executes the same
+ * batch (same requests, same order) and, on the batch's stream with no host synchronisation in between,
+ *   seed pass -> ncclAllReduce(max) of the per-request thresholds -> bulk pass -> local top-k
+ *   -> ncclAllGather of the top-k rows and hit counts (+ ncclAllReduce(sum) of facet histograms) -> final merge,
+ * so every rank ends with the complete SearchResult of every request (NCCL over NVLink / NVSwitch; failures are
+ * VGPU_ERR_NCCL).  NCCL is bound at run time (libnccl.so.2); without it these calls fail and nothing else is affected. */
+#define VGPU_COMM_ID_BYTES 128
+int32_t vgpu_comm_unique_id(uint8_t id[VGPU_COMM_ID_BYTES]);
+int32_t vgpu_comm_init(vgpu_index* idx, const uint8_t id[VGPU_COMM_ID_BYTES]);
+int32_t vgpu_comm_destroy(vgpu_index* idx);
+
+/* Plan once per box.  Parsing and planning a batch is host work that does not depend on the shard: one process prepares
+ * the batch and exports its plan (a byte blob without process-local addresses, released with vgpu_free), the other
+ * processes of the box import it against their own handle of the same index directory instead of planning again
+ * (replaces N x plan_creator, src/plan_creator/execution_plan.rs:132-200, by 1 x).  VGPU_ERR_INVALID_REQUEST when the
+ * blob was made for another index. */
+int32_t vgpu_batch_export_plan(const vgpu_batch* batch, void** blob, size_t* len);
+int32_t vgpu_batch_prepare_from_plan(vgpu_index* idx, const void* blob, size_t len, vgpu_batch** out);
+
+/* The same through shared memory, for the processes of one box: a named channel (POSIX shared memory) that local rank 0
+ * publishes plans into and the other local ranks read from.  vgpu_batch_prepare_shared is a collective over the
+ * channel's ranks: rank 0 passes the requests, parses, plans and publishes; the others pass NULL / 0, wait for the plan
+ * and import it.  Two plans may be in flight (rank 0 can run one batch ahead).  `capacity` bounds the blob size. */
+typedef struct vgpu_plan_channel vgpu_plan_channel;
+int32_t vgpu_plan_channel_open(const char* name, uint32_t local_rank, uint32_t local_ranks, size_t capacity, vgpu_plan_channel** out);
+void vgpu_plan_channel_close(vgpu_plan_channel* ch);
+int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, const char* text, size_t len, uint32_t n, vgpu_batch** out);
+
+/* ---- multi-GPU merge driven by the host (the pieces vgpu_batch_execute runs by itself once vgpu_comm_init was called;
+ * kept for hosts with their own transport and for single-device tests of several shards) ----------------------
  * After execute, every shard holds the local top-(top+skip) of each request as
  * device rows of `stride` 64-bit keys ((orderable score << 32) | anchor id, 0 = no
  * hit) plus its local num_hits.  The host all-gathers those buffers (NCCL) and calls
@@ -192,6 +230,18 @@ uint64_t vgpu_launch_count(void);
 int32_t vgpu_batch_phase_ms(const vgpu_batch* batch, float* ms, uint32_t n_phases);
 int32_t vgpu_batch_traffic_model(const vgpu_batch* batch, uint64_t* posting_bytes, uint64_t* boost_bytes, uint64_t* postings, uint64_t* union_hits);
 int32_t vgpu_batch_path_stats(const vgpu_batch* batch, uint64_t* plane_items, uint64_t* general_items, uint64_t* plane_evaluated);
+/* Per-kernel device time: with profiling on, the next execute brackets every kernel launch with a pair of CUDA events on
+ * the batch's stream (a few microseconds each: not for timed runs); vgpu_batch_kernel_times_json returns
+ * {"kernel": {"launches": n, "ms": total}, ...} of that execute (owned by the batch). */
+int32_t vgpu_batch_set_profiling(vgpu_batch* batch, int32_t on);
+const char* vgpu_batch_kernel_times_json(vgpu_batch* batch);
+/* Work counters of the last execute, in this order: matched terms, postings of the matched terms (posting-list model),
+ * union hits, sparse entries (postings of non-plane terms copied into tile buckets), plane-path items, general items,
+ * anchors evaluated exactly on the plane path, plane-path item evaluations (seed + bulk), of which swept before their
+ * threshold converged, of which answered from per-plane tile counts, anchor tiles, distinct search parts, planes of the
+ * index, 32-anchor words per plane. */
+#define VGPU_WORK_STATS 14
+int32_t vgpu_batch_work_stats(const vgpu_batch* batch, uint64_t* out, uint32_t n);
 /* Bytes copied host->device by prepare (plan tables) and device->host by execute + fetch. */
 int32_t vgpu_batch_io_bytes(const vgpu_batch* batch, uint64_t* h2d, uint64_t* d2h);
 

@@ -120,3 +120,55 @@ class Oracle:
         status = np.zeros(n, dtype=np.int32)
         secs = self.lib.vo_search_batch(self.h, arr, n, threads, k, ids.ctypes.data, scores.ctypes.data, num_hits.ctypes.data, status.ctypes.data)
         return {"seconds": secs, "ids": ids, "scores": scores, "num_hits": num_hits, "status": status}
+
+
+# ---- result parity (bench.py, __graft_entry__.smoke and the GPU tests share one rule)
+REL_TOL = 1e-5  # f32 scores: relative tolerance north_star states
+
+
+def _close(a, b):
+    return abs(float(a) - float(b)) <= REL_TOL * max(abs(float(a)), abs(float(b)), 1e-30)
+
+
+def same_topk(got, ref):
+    """got / ref: lists of (id, score) in rank order.  Equal when the scores agree rank by rank within REL_TOL and every id
+    that differs is a tie: an id of `got` the reference also returned must tie with the reference's hit at that rank, an id
+    the reference did not return must tie with the reference's last (boundary) hit.  -> (ok, reason)"""
+    if len(got) != len(ref):
+        return False, f"{len(got)} hits vs {len(ref)}"
+    ref_scores = {i: s for i, s in ref}
+    for pos, ((gi, gs), (ci, cs)) in enumerate(zip(got, ref)):
+        if not _close(gs, cs):
+            return False, f"score at rank {pos}: {gs!r} vs {cs!r}"
+        if gi != ci:
+            if gi in ref_scores:
+                if not _close(ref_scores[gi], cs):
+                    return False, f"id {gi} at rank {pos} is not a tie with {ci}"
+            elif not _close(gs, ref[-1][1]):
+                return False, f"id {gi} at rank {pos} is neither in the reference's top-k nor a boundary tie"
+    return True, ""
+
+
+def batch_parity(got, ref, rows=None):
+    """got / ref: results_flat-style dicts (ids [n][k] padded with 0xFFFFFFFF, scores, num_hits, status) over the same
+    requests.  -> {"checked", "equal", "num_hits_equal", "first_mismatch"}: hit counts exact, top-k per same_topk."""
+    n = len(ref["num_hits"]) if rows is None else len(rows)
+    equal = hits_equal = 0
+    first = None
+    for j in range(n):
+        q = j if rows is None else rows[j]
+        ok = int(got["status"][q]) == int(ref["status"][j])
+        why = "status" if not ok else ""
+        if ok and int(got["num_hits"][q]) == int(ref["num_hits"][j]):
+            hits_equal += 1
+        elif ok:
+            ok, why = False, f"num_hits {int(got['num_hits'][q])} vs {int(ref['num_hits'][j])}"
+        if ok:
+            g = [(int(i), float(s)) for i, s in zip(got["ids"][q], got["scores"][q]) if int(i) != 0xFFFFFFFF]
+            c = [(int(i), float(s)) for i, s in zip(ref["ids"][j], ref["scores"][j]) if int(i) != 0xFFFFFFFF]
+            ok, why = same_topk(g, c)
+        if ok:
+            equal += 1
+        elif first is None:
+            first = {"request": int(q), "why": why}
+    return {"checked": n, "equal": equal, "num_hits_equal": hits_equal, "first_mismatch": first}

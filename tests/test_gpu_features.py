@@ -159,28 +159,6 @@ def test_config3_shape(gpu, native_libs):  # BASELINE config 3: AND + phrase + t
     assert sum(b.result(q)["num_hits"] for q in range(len(reqs))) > 0
 
 
-def test_one_to_n_boost_with_several_values_per_document(gpu, native_libs):
-    """Several boosted values of one document in one 1:n field: the reference applies the first or all of them depending on
-    the run of boosted hits before the anchor (apply_boost_values_anchor, boost.rs:255-281)."""
-    rng = np.random.default_rng(11)
-    syll = ["ka", "ki", "ku", "mi", "mo", "ra", "ri", "ru", "sa", "to"]
-    words = ["".join(rng.choice(syll, size=int(rng.integers(2, 4)))) for _ in range(120)]
-    docs = []
-    for i in range(1500):
-        n = int(rng.integers(0, 4))
-        d = {"ent_seq": str(i)}
-        if n:
-            d["kana"] = [{"text": str(rng.choice(words)), **({"commonness": int(rng.integers(1, 900))} if rng.random() < 0.75 else {})} for _ in range(n)]
-        docs.append(d)
-    index, oracle = _pair(gpu, docs, {"kana[].text": {"fulltext": {"tokenize": True}}, "kana[].commonness": dict(fx.BOOST)})
-    reqs = []
-    for t in [str(w) for w in rng.choice(words, size=12)] + ["mi", "ka", "ri"]:
-        for fun in ("Log10", "Multiply", "Add"):
-            reqs.append({"search_req": {"search": {"terms": [t], "path": "kana[].text", "levenshtein_distance": 1, "starts_with": True}},
-                         "boost": [{"path": "kana[].commonness", "boost_fun": fun, "param": 1}], "top": 50})
-    compare(index, oracle, reqs)
-
-
 def test_one_to_n_boosts(test_all):  # tests/all/tests.rs:839-931 (BoostToAnchor + ApplyAnchorBoost)
     index, oracle = test_all
     compare(index, oracle, [

@@ -235,8 +235,7 @@ def test_plane_path_equals_posting_path(gpu, native_libs, monkeypatch):
     got = b.results_flat(10)
     stats = b.path_stats()
     assert stats["plane_items"] > 0, "the plane path did not run"
-    monkeypatch.setenv("VELOCI_NO_PLANES", "1")
-    without = gpu.Index(d)
+    without = gpu.Index(d, planes=False)
     b2 = without.prepare(reqs)
     b2.execute()
     ref = b2.results_flat(10)
@@ -256,8 +255,7 @@ def test_deletion_index_equals_dictionary_scan(gpu, native_libs, monkeypatch):
     for lev, seed in ((0, 1), (1, 2), (2, 3)):
         reqs += helpers.synthetic_requests(num_queries=150, query_kind="single", levenshtein=lev, query_seed=seed, **params)
     probe = gpu.Index(d).search_batch(reqs, k=10)
-    monkeypatch.setenv("VELOCI_NO_DELINDEX", "1")
-    scan = gpu.Index(d).search_batch(reqs, k=10)
+    scan = gpu.Index(d, deletion_index=False).search_batch(reqs, k=10)
     assert (probe["status"] == 0).all() and (scan["status"] == 0).all()
     assert probe["num_hits"].sum() > 0
     assert (probe["num_hits"] == scan["num_hits"]).all()

@@ -1,0 +1,271 @@
+"""GPU tests of the round-2 boundary: many anchor-range shards, plan export / import, the shared-memory plan channel,
+the in-library NCCL exchange (needs two GPUs), open flags, load-time validation.  All through the C ABI."""
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHARDED = dict(num_docs=120000, vocab=7000, seed=33, tags=30)
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import veloci_b200
+
+    assert veloci_b200.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return veloci_b200
+
+
+@pytest.fixture(scope="module")
+def sharded_corpus(gpu, native_libs):
+    d = tempfile.mkdtemp(prefix="vb200_r2_shards_")
+    helpers.create_synthetic_index(d, **SHARDED)
+    reqs = helpers.synthetic_requests(num_queries=400, query_kind="or3", levenshtein=1, query_seed=8, **SHARDED)
+    reqs += helpers.synthetic_requests(num_queries=120, query_kind="and", levenshtein=1, query_seed=9, **SHARDED)  # with facets on tags[]
+    reqs += helpers.synthetic_requests(num_queries=80, query_kind="single", levenshtein=2, query_seed=10, **SHARDED)
+    assert "facets" in reqs[450]
+    return d, reqs
+
+
+class _DevArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def run_shards_on_one_device(gpu, d, reqs, n_shards, k=10):
+    """The host-driven exchange (execute_begin / thresholds / execute_finish / local_topk / merge_gathered) over
+    `n_shards` handles on this device: what vgpu_batch_execute does over NCCL when every shard has its own GPU."""
+    import torch
+
+    shards = [gpu.Index(d, shard_rank=r, n_shards=n_shards) for r in range(n_shards)]
+    batches = [s.prepare(reqs) for s in shards]
+    sign = -(1 << 63)
+    taus = []
+    for b in batches:
+        b.execute_begin()
+        ptr, cnt = b.thresholds()
+        taus.append(torch.as_tensor(_DevArray(ptr, cnt), device="cuda"))
+    shared = taus[0] ^ sign
+    for t in taus[1:]:
+        shared = torch.maximum(shared, t ^ sign)
+    shared = shared ^ sign
+    for t in taus:
+        t.copy_(shared)
+    torch.cuda.synchronize()
+    keys, hits, hists = [], [], []
+    for b in batches:
+        b.execute_finish()
+        kp, hp, stride = b.local_topk()
+        keys.append(torch.as_tensor(_DevArray(kp, len(reqs) * stride), device="cuda").clone())
+        hits.append(torch.as_tensor(_DevArray(hp, len(reqs)), device="cuda").clone())
+        ptr, cnt = b.facet_histograms()
+        if cnt:
+            hists.append(torch.as_tensor(_DevArray(ptr, cnt // 2), device="cuda").view(torch.int32))
+    g_keys, g_hits = torch.cat(keys), torch.cat(hits)
+    if hists:
+        total = hists[0].clone()
+        for h in hists[1:]:
+            total += h
+        for h in hists:
+            h.copy_(total)
+    torch.cuda.synchronize()
+    out = []
+    for b in batches:  # every rank merges the same gathered buffers
+        b.merge_gathered(g_keys.data_ptr(), g_hits.data_ptr(), n_shards)
+        out.append(b)
+    return shards, out
+
+
+@pytest.mark.parametrize("n_shards", [3, 8])
+def test_many_shards_equal_unsharded_and_oracle(gpu, sharded_corpus, n_shards):
+    """Eight (and three: uneven cuts) anchor-range shards of one index, merged on the device: identical, bit for bit, to
+    the unsharded index -- ids, score bits, hit counts, facet groups -- and equal to the CPU oracle."""
+    d, reqs = sharded_corpus
+    whole_batch = gpu.Index(d).prepare(reqs).execute()
+    whole = whole_batch.results_flat(10)
+    assert (whole["status"] == 0).all()
+    shards, batches = run_shards_on_one_device(gpu, d, reqs, n_shards)
+    ranges = [s.info() for s in shards]
+    assert ranges[0]["anchor_lo"] == 0 and ranges[-1]["anchor_hi"] == SHARDED["num_docs"]
+    assert all(ranges[i]["anchor_hi"] == ranges[i + 1]["anchor_lo"] for i in range(n_shards - 1))
+    for b in (batches[0], batches[-1]):
+        got = b.results_flat(10)
+        assert (got["status"] == 0).all()
+        assert (got["num_hits"] == whole["num_hits"]).all()
+        assert (got["ids"] == whole["ids"]).all()
+        assert (got["scores"].view(np.uint32) == whole["scores"].view(np.uint32)).all()
+        for q in range(400, 520, 7):
+            assert b.result(q)["facets"] == whole_batch.result(q)["facets"]
+    rows = list(range(0, len(reqs), 5))
+    ref = helpers.Oracle(d).search_batch([reqs[q] for q in rows], threads=4, k=10)
+    par = helpers.batch_parity(batches[0].results_flat(10), ref, rows)
+    assert par["equal"] == par["checked"], par
+
+
+def test_one_to_n_boost_is_refused_on_a_sharded_index(gpu, native_libs):
+    """apply_boost_values_anchor (boost.rs:255-281) depends on the run of boosted hits before an anchor, which may begin in
+    the previous shard: the sharded handle answers VGPU_ERR_UNSUPPORTED for that request shape instead of a result that
+    could differ; the unsharded handle answers it."""
+    rng = np.random.default_rng(5)
+    words = ["kami", "kumo", "kawa", "mori", "sora", "tori"]
+    docs = [{"ent_seq": str(i), "kana": [{"text": str(rng.choice(words)), "commonness": int(rng.integers(1, 90))} for _ in range(int(rng.integers(1, 3)))]} for i in range(400)]
+    d = tempfile.mkdtemp(prefix="vb200_r2_1n_")
+    helpers.create_index(d, docs, {"kana[].text": {"fulltext": {"tokenize": True}}, "kana[].commonness": {"boost": {"boost_type": "f32"}}})
+    req = {"search_req": {"search": {"terms": ["kami"], "path": "kana[].text"}}, "boost": [{"path": "kana[].commonness", "boost_fun": "Log10", "param": 1}]}
+    plain = {"search_req": {"search": {"terms": ["kami"], "path": "kana[].text"}}}
+    whole = gpu.Index(d).search_batch([json.dumps(req), json.dumps(plain)])
+    assert list(whole["status"]) == [0, 0] and whole["num_hits"][0] > 0
+    shard = gpu.Index(d, shard_rank=1, n_shards=2)
+    b = shard.prepare([json.dumps(req), json.dumps(plain)]).execute()
+    assert b.status(0) == 8 and "1:n" in b.message(0)
+    assert b.status(1) == 0
+
+
+def test_plan_export_import(gpu, sharded_corpus):
+    """A plan exported by one handle and imported by other handles of the same directory (unsharded and a shard) gives the
+    results of planning there; a plan of another index is refused."""
+    d, reqs = sharded_corpus
+    a = gpu.Index(d)
+    ba = a.prepare(reqs)
+    blob = ba.export_plan()
+    assert len(blob) > 1000
+    want = ba.execute().results_flat(10)
+    b = gpu.Index(d)
+    bb = b.prepare(len(reqs), plan=blob).execute()
+    got = bb.results_flat(10)
+    for key in ("status", "num_hits", "ids"):
+        assert (got[key] == want[key]).all(), key
+    assert (got["scores"].view(np.uint32) == want["scores"].view(np.uint32)).all()
+    for q in range(400, 520, 11):
+        assert bb.result(q)["facets"] == ba.result(q)["facets"]
+    # a shard imports the unsharded handle's plan: same local rows as planning on the shard
+    s1 = gpu.Index(d, shard_rank=1, n_shards=2)
+    own = s1.prepare(reqs).execute().results_flat(10)
+    imp = s1.prepare(len(reqs), plan=blob).execute().results_flat(10)
+    for key in ("status", "num_hits", "ids"):
+        assert (imp[key] == own[key]).all(), key
+    # failed requests travel with their status and message
+    mixed = [reqs[0], "{not json", json.dumps({"search_req": {"search": {"terms": ["x"], "path": "nosuchfield"}}}), reqs[1]]
+    bm = a.prepare(mixed)
+    bi = b.prepare(len(mixed), plan=bm.export_plan()).execute()
+    bm.execute()
+    assert [bi.status(q) for q in range(4)] == [bm.status(q) for q in range(4)] == [0, 5, 2, 0]
+    assert bi.message(2) == bm.message(2)
+    # another index: refused
+    other = tempfile.mkdtemp(prefix="vb200_r2_other_")
+    helpers.create_synthetic_index(other, num_docs=5000, vocab=500, seed=1)
+    with pytest.raises(gpu.VelociGpuError) as e:
+        gpu.Index(other).prepare(len(reqs), plan=blob)
+    assert e.value.status == 1
+    with pytest.raises(gpu.VelociGpuError):
+        b.prepare(3, plan=blob[: len(blob) // 2])
+
+
+_CHANNEL_WORKER = r"""
+import json, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import numpy as np
+import veloci_b200
+d, name, n_batches, out = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
+index = veloci_b200.Index(d)
+ch = veloci_b200.PlanChannel(name, 1, 2, capacity=32 << 20)
+res = []
+for out_flat in index.search_stream(([] for _ in range(n_batches)), k=10, channel=ch):
+    res.append(out_flat)
+np.savez(out, **{{f"{{k}}{{i}}": v for i, r in enumerate(res) for k, v in r.items()}})
+"""
+
+
+def test_plan_channel_between_two_processes(gpu, sharded_corpus):
+    """Local rank 0 (this process) plans and publishes five different batches through the shared-memory channel; a second
+    process imports each plan (it never sees the request text) and must produce the same results.  Five batches through
+    two slots exercise the slot hand-over in both directions."""
+    d, reqs = sharded_corpus
+    n_batches = 5
+    batches = [reqs[i * 100:(i + 1) * 100 + 37] for i in range(n_batches)]
+    name = f"/vb200_test_{os.getpid()}"
+    out = tempfile.mktemp(suffix=".npz")
+    child = subprocess.Popen([sys.executable, "-c", _CHANNEL_WORKER.format(root=ROOT), d, name, str(n_batches), out])
+    try:
+        index = gpu.Index(d)
+        ch = gpu.PlanChannel(name, 0, 2, capacity=32 << 20)
+        mine = list(index.search_stream(iter(batches), k=10, channel=ch))
+        assert child.wait(timeout=300) == 0
+    finally:
+        if child.poll() is None:
+            child.kill()
+    theirs = np.load(out)
+    for i, r in enumerate(mine):
+        direct = index.search_batch(batches[i], k=10)
+        for key in ("status", "num_hits", "ids"):
+            assert (r[key] == direct[key]).all(), (i, key)
+            assert (theirs[f"{key}{i}"] == direct[key]).all(), (i, key)
+        assert (theirs[f"scores{i}"].view(np.uint32) == direct["scores"].view(np.uint32)).all()
+    ch.close()
+
+
+def test_load_rejects_postings_beyond_num_docs(gpu, native_libs):
+    """Planes, level bitmaps and tile buckets are sized from metaData.json's num_docs: an index whose postings reach past it
+    (stale metadata) must fail to load (VGPU_ERR_IO), not write out of bounds."""
+    src = tempfile.mkdtemp(prefix="vb200_r2_meta_")
+    helpers.create_synthetic_index(src, num_docs=3000, vocab=300, seed=2)
+    meta_path = os.path.join(src, "metaData.json")
+    meta = json.load(open(meta_path))
+    assert meta["num_docs"] == 3000
+    gpu.Index(src).close()
+    meta["num_docs"] = 2000
+    json.dump(meta, open(meta_path, "w"))
+    with pytest.raises(gpu.VelociGpuError) as e:
+        gpu.Index(src)
+    assert e.value.status == 4 and "num_docs" in e.value.message
+    shutil.rmtree(src, ignore_errors=True)
+
+
+def test_kernel_profile_and_work_stats(gpu, sharded_corpus):
+    d, reqs = sharded_corpus
+    b = gpu.Index(d).prepare(reqs[:400])
+    b.execute()
+    base = b.results_flat(10)
+    times = b.profile_execute()
+    assert "plane_eval" in times and times["plane_eval"]["ms"] > 0 and "sparse_fill" in times
+    again = b.results_flat(10)
+    assert (again["ids"] == base["ids"]).all()
+    w = b.work_stats()
+    assert w["plane_items"] > 0 and w["tiles"] == (SHARDED["num_docs"] + 8191) // 8192 and w["sparse_entries"] > 0
+
+
+@pytest.mark.skipif("__import__('veloci_b200').device_count() < 2")
+def test_index_on_a_second_device(gpu, sharded_corpus):
+    """Kernel attributes (opt-in shared memory) are per device: an index on device 1 must work in a process that already
+    ran every kernel on device 0."""
+    d, reqs = sharded_corpus
+    first = gpu.Index(d, device=0).search_batch(reqs, k=10)
+    second = gpu.Index(d, device=1).search_batch(reqs, k=10)
+    assert (second["status"] == 0).all()
+    for key in ("num_hits", "ids"):
+        assert (first[key] == second[key]).all()
+
+
+@pytest.mark.skipif("__import__('veloci_b200').device_count() < 2")
+def test_in_library_exchange_over_nccl(gpu, sharded_corpus):
+    """Two processes, one GPU each: vgpu_comm_init, the plan channel, then vgpu_batch_execute as a collective.  Every rank
+    must end with the unsharded result (tools/sharded_worker.py checks it on both ranks)."""
+    d, reqs = sharded_corpus
+    req_path = tempfile.mktemp(suffix=".jsonl")
+    open(req_path, "w").write("\n".join(reqs))
+    port = 29500 + os.getpid() % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tools", "sharded_worker.py"), d, req_path]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "sharded_worker ok" in r.stdout

@@ -15,7 +15,9 @@ There is no CPU fallback: without the CUDA library or a CUDA device every call r
 from .api import (  # noqa: F401
     Batch,
     Index,
+    PlanChannel,
     VelociGpuError,
+    comm_unique_id,
     device_count,
     launch_count,
     lib_path,

@@ -55,6 +55,16 @@ def load_library():
     L.vgpu_last_error.restype = cp
     L.vgpu_device_count.restype = i32
     L.vgpu_index_open.argtypes = [cp, i32, u32, u32, P(vp)]
+    L.vgpu_index_open_ex.argtypes = [cp, i32, u32, u32, u32, P(vp)]
+    L.vgpu_comm_unique_id.argtypes = [vp]
+    L.vgpu_comm_init.argtypes = [vp, vp]
+    L.vgpu_comm_destroy.argtypes = [vp]
+    L.vgpu_batch_export_plan.argtypes = [vp, P(vp), P(ctypes.c_size_t)]
+    L.vgpu_batch_prepare_from_plan.argtypes = [vp, vp, ctypes.c_size_t, P(vp)]
+    L.vgpu_plan_channel_open.argtypes = [cp, u32, u32, ctypes.c_size_t, P(vp)]
+    L.vgpu_plan_channel_close.argtypes = [vp]
+    L.vgpu_plan_channel_close.restype = None
+    L.vgpu_batch_prepare_shared.argtypes = [vp, vp, ctypes.c_char_p, ctypes.c_size_t, u32, P(vp)]
     L.vgpu_index_close.argtypes = [vp]
     L.vgpu_index_close.restype = None
     L.vgpu_index_info.argtypes = [vp, P(u64), P(u64), P(u64), P(u64)]
@@ -68,6 +78,7 @@ def load_library():
     L.vgpu_batch_facet_histograms.argtypes = [vp, P(vp), P(u64)]
     L.vgpu_batch_free.argtypes = [vp]
     L.vgpu_batch_free.restype = None
+    L.vgpu_batch_size.argtypes = [vp, P(u32)]
     L.vgpu_batch_status.argtypes = [vp, u32]
     L.vgpu_batch_message.argtypes = [vp, u32]
     L.vgpu_batch_message.restype = cp
@@ -98,6 +109,10 @@ def load_library():
     L.vgpu_batch_traffic_model.argtypes = [vp, P(u64), P(u64), P(u64), P(u64)]
     L.vgpu_batch_path_stats.argtypes = [vp, P(u64), P(u64), P(u64)]
     L.vgpu_batch_io_bytes.argtypes = [vp, P(u64), P(u64)]
+    L.vgpu_batch_set_profiling.argtypes = [vp, i32]
+    L.vgpu_batch_kernel_times_json.argtypes = [vp]
+    L.vgpu_batch_kernel_times_json.restype = cp
+    L.vgpu_batch_work_stats.argtypes = [vp, P(u64), u32]
     _LIB = L
     return L
 
@@ -144,15 +159,41 @@ def _from_hitlist(L, hl):
 class Batch:
     """A prepared batch of requests (vgpu_batch_prepare / execute / fetch)."""
 
-    def __init__(self, index, requests):
+    def __init__(self, index, requests, plan=None, channel=None):
+        """`requests`: the batch.  `plan`: a blob from `export_plan()` of another handle of the same directory (the requests
+        are then not parsed again; pass their count or the list).  `channel`: a PlanChannel -- local rank 0 plans and
+        publishes, the other local ranks import (collective over the channel's ranks)."""
         self.L = load_library()
         self.index = index
-        self.n = len(requests)
+        self.n = requests if isinstance(requests, int) else len(requests)
         self.h = ctypes.c_void_p()
+        if plan is not None:
+            _check(self.L.vgpu_batch_prepare_from_plan(index.h, plan, len(plan), ctypes.byref(self.h)))
+            self.n = self._size()
+            return
+        if channel is not None:
+            blob = b"" if channel.rank != 0 else "\n".join(requests).encode("utf-8")
+            _check(self.L.vgpu_batch_prepare_shared(index.h, channel.h, blob if channel.rank == 0 else None, len(blob), self.n if channel.rank == 0 else 0, ctypes.byref(self.h)))
+            self.n = self._size()
+            return
         if self.n >= 64 and self._prepare_lines(index, requests):
             return
         arr, self._keep = _encode_requests(requests)
         _check(self.L.vgpu_batch_prepare(index.h, arr, self.n, ctypes.byref(self.h)))
+
+    def _size(self):
+        n = ctypes.c_uint32()
+        _check(self.L.vgpu_batch_size(self.h, ctypes.byref(n)))
+        return int(n.value)
+
+    def export_plan(self):
+        """The batch's plan as bytes without process-local addresses (vgpu_batch_export_plan)."""
+        blob, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(self.L.vgpu_batch_export_plan(self.h, ctypes.byref(blob), ctypes.byref(n)))
+        try:
+            return ctypes.string_at(blob.value, n.value)
+        finally:
+            self.L.vgpu_free(blob)
 
     def _prepare_lines(self, index, requests):
         """Many requests: one buffer of line-feed separated requests instead of one C string each.  False when some request
@@ -254,6 +295,23 @@ class Batch:
         _check(self.L.vgpu_batch_traffic_model(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
         return {"posting_bytes": a.value, "boost_bytes": b.value, "postings": c.value, "union_hits": d.value}
 
+    WORK_STATS = ["matched_terms", "postings", "union_hits", "sparse_entries", "plane_items", "general_items", "plane_evaluated", "plane_item_evals",
+                  "plane_unconverged_sweeps", "plane_sweepless", "tiles", "parts", "planes", "plane_words"]
+
+    def work_stats(self):
+        v = (ctypes.c_uint64 * len(self.WORK_STATS))()
+        _check(self.L.vgpu_batch_work_stats(self.h, v, len(self.WORK_STATS)))
+        return dict(zip(self.WORK_STATS, [int(x) for x in v]))
+
+    def profile_execute(self):
+        """One execute with a CUDA event pair around every kernel launch -> {"kernel": {"launches", "ms"}}."""
+        _check(self.L.vgpu_batch_set_profiling(self.h, 1))
+        try:
+            self.execute()
+            return json.loads(self.L.vgpu_batch_kernel_times_json(self.h).decode())
+        finally:
+            _check(self.L.vgpu_batch_set_profiling(self.h, 0))
+
     def io_bytes(self):
         a, b = ctypes.c_uint64(), ctypes.c_uint64()
         _check(self.L.vgpu_batch_io_bytes(self.h, ctypes.byref(a), ctypes.byref(b)))
@@ -271,21 +329,58 @@ class Batch:
             pass
 
 
+def comm_unique_id():
+    """128 bytes (an ncclUniqueId) made by one rank and handed to every rank's `Index.comm_init`."""
+    buf = ctypes.create_string_buffer(128)
+    _check(load_library().vgpu_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+    return buf.raw
+
+
+class PlanChannel:
+    """Shared-memory channel between the processes of one box: local rank 0 publishes plans, the others import them."""
+
+    def __init__(self, name, local_rank, local_ranks, capacity=64 << 20):
+        self.L = load_library()
+        self.rank = local_rank
+        self.h = ctypes.c_void_p()
+        _check(self.L.vgpu_plan_channel_open(name.encode(), local_rank, local_ranks, capacity, ctypes.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.vgpu_plan_channel_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Index:
     """An index directory loaded into the HBM of one GPU (one anchor-range shard of it)."""
 
-    def __init__(self, directory, device=0, shard_rank=0, n_shards=1):
+    def __init__(self, directory, device=0, shard_rank=0, n_shards=1, planes=True, deletion_index=True):
         self.L = load_library()
         self.h = ctypes.c_void_p()
-        _check(self.L.vgpu_index_open(os.fsencode(directory), device, shard_rank, n_shards, ctypes.byref(self.h)))
+        flags = (0 if planes else 1) | (0 if deletion_index else 2)
+        _check(self.L.vgpu_index_open_ex(os.fsencode(directory), device, shard_rank, n_shards, flags, ctypes.byref(self.h)))
+
+    def comm_init(self, unique_id):
+        """Joins the communicator of the shards (NCCL): afterwards `Batch.execute` is a collective that ends with the complete
+        result on every rank."""
+        _check(self.L.vgpu_comm_init(self.h, ctypes.cast(ctypes.create_string_buffer(unique_id, 128), ctypes.c_void_p)))
+
+    def comm_destroy(self):
+        _check(self.L.vgpu_comm_destroy(self.h))
 
     def info(self):
         a, b, c, d = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
         _check(self.L.vgpu_index_info(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
         return {"num_docs": a.value, "anchor_lo": b.value, "anchor_hi": c.value, "device_bytes": d.value}
 
-    def prepare(self, requests):
-        return Batch(self, requests)
+    def prepare(self, requests, plan=None, channel=None):
+        return Batch(self, requests, plan=plan, channel=channel)
 
     def search(self, request):
         b = Batch(self, [request]).execute()
@@ -305,7 +400,7 @@ class Index:
         _check(self.L.vgpu_search_batch(self.h, arr, n, k, ids.ctypes.data, scores.ctypes.data, num_hits.ctypes.data, status.ctypes.data))
         return {"ids": ids, "scores": scores, "num_hits": num_hits, "status": status}
 
-    def search_stream(self, batches, k=10, run=None):
+    def search_stream(self, batches, k=10, run=None, channel=None):
         """Evaluates a sequence of request batches, yielding one `results_flat(k)` dict per batch, in order.
 
         A planner thread parses, plans and uploads batch i+1 (`vgpu_batch_prepare`, host work + H2D on its own stream)
@@ -320,7 +415,7 @@ class Index:
                     reqs = next(it)
                 except StopIteration:
                     return None
-                return planner.submit(self.prepare, reqs)
+                return planner.submit(self.prepare, reqs, None, channel)
             ahead = plan_next()
             while ahead is not None:
                 batch = ahead.result()

@@ -63,14 +63,36 @@ def build_oracle(force=False):
 
 
 def build_main_lib(force=False, verbose_ptxas=False):
+    """Every source is compiled to its own object (in parallel, only when it or a header changed) and linked."""
+    from concurrent.futures import ThreadPoolExecutor
+
     os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
     out = os.path.join(LIB_DIR, "libveloci_b200.so")
     srcs = sorted(glob.glob(os.path.join(CSRC, "cuda", "*.cu"))) + sorted(glob.glob(os.path.join(CSRC, "host", "*.cpp")))
-    if force or _newer(out, srcs + _headers()):
-        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else [])
-        cmd += ["-I", os.path.join(REPO, "include"), "-shared"] + srcs + ["-o", out, "-lcudart"]
-        _run(cmd)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else [])
+    if os.environ.get("VELOCI_PROBES"):  # timing experiments (tools/*_probe.py): the library reads its probe settings from the environment
+        flags = flags + ["-DVELOCI_PROBES"]
+    stamp = os.path.join(obj_dir, ".flags")
+    flag_text = " ".join(flags)
+    if not os.path.exists(stamp) or open(stamp).read() != flag_text:
+        force = True
+    headers = _headers()
+    jobs = []
+    objs = []
+    for src in srcs:
+        obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
+        objs.append(obj)
+        if force or _newer(obj, [src] + headers):
+            jobs.append([nvcc] + flags + ["-I", os.path.join(REPO, "include"), "-c", src, "-o", obj])
+    if jobs:
+        with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+            list(pool.map(_run, jobs))
+        open(stamp, "w").write(flag_text)
+    if jobs or _newer(out, objs):
+        _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", out, "-lcudart", "-ldl", "-lrt"])
     return out
 
 

@@ -146,14 +146,14 @@ void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* 
     const unsigned gx = (dict.n_tiles + kFuzzyThreads - 1) / kFuzzyThreads;
     if (max_m <= 32) {
         const size_t smem = sizeof(PartLite<uint32_t>) * kPartChunk;
-        static bool once = false;
-        if (!once) cudaFuncSetAttribute(fuzzy_match_kernel<uint32_t, kPartChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), once = true;
+        static PerDeviceOnce once;
+        if (once.first()) cudaFuncSetAttribute(fuzzy_match_kernel<uint32_t, kPartChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid(gx, (n_parts + kPartChunk - 1) / kPartChunk);
         fuzzy_match_kernel<uint32_t, kPartChunk><<<grid, kFuzzyThreads, smem, st>>>(dict, parts, part_ids, n_parts, out, capacity, counter);
     } else {
         const size_t smem = sizeof(PartLite<uint64_t>) * (kPartChunk / 2);
-        static bool once = false;
-        if (!once) cudaFuncSetAttribute(fuzzy_match_kernel<uint64_t, kPartChunk / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), once = true;
+        static PerDeviceOnce once;
+        if (once.first()) cudaFuncSetAttribute(fuzzy_match_kernel<uint64_t, kPartChunk / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid(gx, (n_parts + kPartChunk / 2 - 1) / (kPartChunk / 2));
         fuzzy_match_kernel<uint64_t, kPartChunk / 2><<<grid, kFuzzyThreads, smem, st>>>(dict, parts, part_ids, n_parts, out, capacity, counter);
     }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 
 #include "device_types.cuh"
@@ -10,6 +11,21 @@ namespace vdev {
 
 void count_launch();          // bumps the library-wide kernel launch counter
 uint64_t launches_so_far();
+
+// Kernel attributes (opt-in dynamic shared memory) are per device: one flag per device ordinal, so a process that
+// opens indices on several GPUs configures every one of them.  first() is true exactly once per device.
+struct PerDeviceOnce {
+    static const int kMaxDevices = 64;
+    std::atomic<uint32_t> done[kMaxDevices];
+    PerDeviceOnce() {
+        for (auto& d : done) d.store(0);
+    }
+    bool first() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;  // unknown device: always configure
+        return done[dev].exchange(1u) == 0u;
+    }
+};
 
 // ---- fuzzy.cu ----
 void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* parts, const uint32_t* part_ids, uint32_t n_parts, uint32_t max_m, MatchRecord* out,

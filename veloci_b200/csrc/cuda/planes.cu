@@ -792,11 +792,8 @@ size_t plane_kernel_smem(uint32_t tile_log2, uint32_t n_planes) {
 void launch_plane_eval(cudaStream_t st, const PlaneArgs& a, int n_sms) {
     if (a.n_units == 0) return;
     const size_t smem = plane_kernel_smem(a.tile_log2, a.planes.n_planes);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(plane_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        configured = true;
-    }
+    static PerDeviceOnce configured;
+    if (configured.first()) cudaFuncSetAttribute(plane_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     unsigned blocks = (unsigned)n_sms;
     if (blocks > a.n_units) blocks = a.n_units;
     plane_eval_kernel<<<blocks, kPlaneThreads, smem, st>>>(a);

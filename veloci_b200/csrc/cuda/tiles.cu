@@ -871,11 +871,8 @@ size_t tile_kernel_smem(uint32_t tile_log2, uint32_t max_leaves) {
 void launch_tile_eval(cudaStream_t st, const TileArgs& a, int n_sms) {
     if (a.n_items == 0) return;
     const size_t smem = tile_kernel_smem(a.tile_log2, a.max_leaves);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(tile_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - kTileStaticSmem));
-        configured = true;
-    }
+    static PerDeviceOnce configured;
+    if (configured.first()) cudaFuncSetAttribute(tile_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - kTileStaticSmem));
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_eval_kernel, kTileThreads, smem);
     if (per_sm < 1) per_sm = 1;

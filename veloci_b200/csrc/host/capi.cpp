@@ -9,6 +9,7 @@
 #include <string>
 
 #include "engine.hpp"
+#include "plan_channel.hpp"
 #include "steps.hpp"
 
 namespace vdev {
@@ -20,10 +21,14 @@ uint64_t launches_so_far() { return g_launches.load(std::memory_order_relaxed); 
 struct vgpu_index {
     std::unique_ptr<vdev::DeviceIndex> ix;
 };
+struct vgpu_plan_channel {
+    std::unique_ptr<vplan::PlanChannel> ch;
+};
 struct vgpu_batch {
     vdev::Batch b;
     std::vector<std::vector<vsteps::FacetGroups>> facets;  // per request, filled on demand
     std::vector<char> jsonl;                                // vgpu_batch_prepare_jsonl: the request lines
+    std::string kernel_times;
 };
 
 static thread_local std::string t_error;
@@ -54,6 +59,12 @@ static int32_t guarded(F&& f) {
     } catch (const vdev::CudaError& e) {
         t_error = e.what();
         return VGPU_ERR_CUDA;
+    } catch (const vdev::NcclError& e) {
+        t_error = e.what();
+        return VGPU_ERR_NCCL;
+    } catch (const vplan::BlobError& e) {
+        t_error = e.what();
+        return VGPU_ERR_INVALID_REQUEST;
     } catch (const vplan::Unsupported& e) {
         t_error = e.what();
         return VGPU_ERR_UNSUPPORTED;
@@ -91,6 +102,10 @@ static void tune_allocator_once() {
 }
 
 int32_t vgpu_index_open(const char* dir, int32_t device, uint32_t shard_rank, uint32_t n_shards, vgpu_index** out) {
+    return vgpu_index_open_ex(dir, device, shard_rank, n_shards, 0, out);
+}
+
+int32_t vgpu_index_open_ex(const char* dir, int32_t device, uint32_t shard_rank, uint32_t n_shards, uint32_t flags, vgpu_index** out) {
     tune_allocator_once();
     if (!dir || !out) {
         t_error = "null argument";
@@ -99,7 +114,7 @@ int32_t vgpu_index_open(const char* dir, int32_t device, uint32_t shard_rank, ui
     *out = nullptr;
     return guarded([&]() {
         std::unique_ptr<vgpu_index> h(new vgpu_index());
-        h->ix = vdev::DeviceIndex::open(dir, device, shard_rank, n_shards);
+        h->ix = vdev::DeviceIndex::open(dir, device, shard_rank, n_shards, flags);
         *out = h.release();
     });
 }
@@ -194,6 +209,131 @@ int32_t vgpu_batch_prepare_jsonl(vgpu_index* idx, const char* text, size_t len, 
     });
 }
 
+// ---- communicator, plan export / import, plan channel
+int32_t vgpu_comm_unique_id(uint8_t id[VGPU_COMM_ID_BYTES]) {
+    if (!id) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() {
+        vdev::NcclApi& api = vdev::NcclApi::get();
+        api.require();
+        vdev::NcclUniqueId uid;
+        api.check(api.GetUniqueId(&uid), "ncclGetUniqueId");
+        static_assert(sizeof uid.internal == VGPU_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+        memcpy(id, uid.internal, VGPU_COMM_ID_BYTES);
+    });
+}
+
+int32_t vgpu_comm_init(vgpu_index* idx, const uint8_t id[VGPU_COMM_ID_BYTES]) {
+    if (!idx || !id) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() {
+        vdev::NcclApi& api = vdev::NcclApi::get();
+        api.require();
+        VDEV_CUDA(cudaSetDevice(idx->ix->device));
+        std::unique_ptr<vdev::ShardComm> c(new vdev::ShardComm());
+        c->rank = idx->ix->shard_rank, c->n_ranks = idx->ix->n_shards;
+        vdev::NcclUniqueId uid;
+        memcpy(uid.internal, id, VGPU_COMM_ID_BYTES);
+        api.check(api.CommInitRank(&c->comm, (int)c->n_ranks, uid, (int)c->rank), "ncclCommInitRank");
+        idx->ix->comm = std::move(c);
+    });
+}
+
+int32_t vgpu_comm_destroy(vgpu_index* idx) {
+    if (!idx) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() {
+        if (idx->ix->comm) VDEV_CUDA(cudaSetDevice(idx->ix->device));
+        idx->ix->comm.reset();
+    });
+}
+
+int32_t vgpu_batch_export_plan(const vgpu_batch* batch, void** blob, size_t* len) {
+    if (!batch || !blob || !len) return VGPU_ERR_INVALID_REQUEST;
+    *blob = nullptr, *len = 0;
+    return guarded([&]() {
+        if (batch->b.mode != vdev::Batch::kRequests) throw vplan::BlobError("only request batches have a plan to export");
+        const std::vector<uint8_t> bytes = vplan::export_plan(batch->b.plan);
+        void* p = malloc(std::max<size_t>(1, bytes.size()));
+        if (!p) throw std::bad_alloc();
+        memcpy(p, bytes.data(), bytes.size());
+        *blob = p, *len = bytes.size();
+    });
+}
+
+int32_t vgpu_batch_prepare_from_plan(vgpu_index* idx, const void* blob, size_t len, vgpu_batch** out) {
+    if (!idx || !blob || !out) {
+        t_error = "null argument";
+        return VGPU_ERR_INVALID_REQUEST;
+    }
+    *out = nullptr;
+    return guarded([&]() {
+        std::unique_ptr<vgpu_batch> b(new vgpu_batch());
+        b->b.prepare_from_blob(idx->ix.get(), blob, len);
+        *out = b.release();
+    });
+}
+
+int32_t vgpu_plan_channel_open(const char* name, uint32_t local_rank, uint32_t local_ranks, size_t capacity, vgpu_plan_channel** out) {
+    if (!name || !out) return VGPU_ERR_INVALID_REQUEST;
+    *out = nullptr;
+    return guarded([&]() {
+        std::unique_ptr<vgpu_plan_channel> h(new vgpu_plan_channel());
+        h->ch.reset(new vplan::PlanChannel(name, local_rank, local_ranks, capacity));
+        *out = h.release();
+    });
+}
+
+void vgpu_plan_channel_close(vgpu_plan_channel* ch) { delete ch; }
+
+int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, const char* text, size_t len, uint32_t n, vgpu_batch** out) {
+    if (!idx || !ch || !out) {
+        t_error = "null argument";
+        return VGPU_ERR_INVALID_REQUEST;
+    }
+    *out = nullptr;
+    if (ch->ch->rank() == 0) {
+        // plan here, publish the plan -- or the failure, so that the other ranks fail with it instead of waiting
+        vgpu_batch* b = nullptr;
+        int32_t rc = vgpu_batch_prepare_lines(idx, text, len, n, &b);
+        std::vector<uint8_t> bytes;
+        if (rc == VGPU_OK)
+            rc = guarded([&]() {
+                bytes = vplan::export_plan(b->b.plan);
+                if (bytes.size() > ch->ch->capacity()) throw vplan::ChannelError("the plan (" + std::to_string(bytes.size()) + " bytes) exceeds the channel capacity");
+            });
+        const std::string failure = t_error;
+        const int32_t pub = guarded([&]() {
+            if (rc == VGPU_OK) ch->ch->publish(bytes.data(), bytes.size(), 0);
+            else ch->ch->publish(failure.data(), std::min(failure.size(), ch->ch->capacity()), (uint64_t)rc);
+        });
+        if (rc == VGPU_OK) rc = pub;
+        else t_error = failure;
+        if (rc != VGPU_OK) {
+            vgpu_batch_free(b);
+            return rc;
+        }
+        *out = b;
+        return VGPU_OK;
+    }
+    int32_t remote = VGPU_OK;
+    std::string remote_msg;
+    const int32_t rc = guarded([&]() {
+        std::unique_ptr<vgpu_batch> b(new vgpu_batch());
+        ch->ch->consume([&](const uint8_t* data, size_t blob_len, uint64_t status) {
+            if (status != 0) {
+                remote = (int32_t)status, remote_msg.assign(reinterpret_cast<const char*>(data), blob_len);
+                return;
+            }
+            b->b.prepare_from_blob(idx->ix.get(), data, blob_len);
+        });
+        if (remote == VGPU_OK) *out = b.release();
+    });
+    if (rc != VGPU_OK) return rc;
+    if (remote != VGPU_OK) {
+        t_error = "local rank 0 could not plan the batch: " + remote_msg;
+        return remote;
+    }
+    return VGPU_OK;
+}
+
 int32_t vgpu_batch_execute(vgpu_batch* batch) {
     if (!batch) return VGPU_ERR_INVALID_REQUEST;
     return guarded([&]() {
@@ -233,6 +373,12 @@ void vgpu_batch_free(vgpu_batch* batch) {
     if (!batch) return;
     if (batch->b.ix) cudaSetDevice(batch->b.ix->device);
     delete batch;
+}
+
+int32_t vgpu_batch_size(const vgpu_batch* batch, uint32_t* n) {
+    if (!batch || !n) return VGPU_ERR_INVALID_REQUEST;
+    *n = batch->b.n;
+    return VGPU_OK;
 }
 
 int32_t vgpu_batch_status(const vgpu_batch* batch, uint32_t q) {
@@ -427,6 +573,35 @@ int32_t vgpu_batch_path_stats(const vgpu_batch* batch_c, uint64_t* plane_items, 
         if (plane_items) *plane_items = batch->b.stat_fast_items;
         if (general_items) *general_items = batch->b.stat_general_items;
         if (plane_evaluated) *plane_evaluated = batch->b.stat_plane_evaluated;
+    });
+}
+
+int32_t vgpu_batch_set_profiling(vgpu_batch* batch, int32_t on) {
+    if (!batch) return VGPU_ERR_INVALID_REQUEST;
+    batch->b.profiling = on != 0;
+    return VGPU_OK;
+}
+
+const char* vgpu_batch_kernel_times_json(vgpu_batch* batch) {
+    if (!batch) return "{}";
+    try {
+        batch->kernel_times = batch->b.kernel_times_json();
+    } catch (...) {
+        batch->kernel_times = "{}";
+    }
+    return batch->kernel_times.c_str();
+}
+
+int32_t vgpu_batch_work_stats(const vgpu_batch* batch_c, uint64_t* out, uint32_t n) {
+    vgpu_batch* batch = const_cast<vgpu_batch*>(batch_c);
+    if (!batch || !out) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() {
+        batch->b.fetch();
+        const vdev::Batch& b = batch->b;
+        const uint64_t v[VGPU_WORK_STATS] = {b.stat_matches,        b.stat_postings,          b.stat_union,           b.stat_sparse,          b.stat_fast_items, b.stat_general_items,
+                                             b.stat_plane_evaluated, b.stat_plane_item_evals, b.stat_plane_unconverged, b.stat_plane_sweepless, b.n_tiles,         b.n_parts,
+                                             b.ix->planes.n_planes,  b.ix->planes.words};
+        for (uint32_t i = 0; i < n; ++i) out[i] = i < VGPU_WORK_STATS ? v[i] : 0;
     });
 }
 

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstdint>
@@ -32,10 +33,12 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../cuda/device_types.cuh"
 #include "../cuda/kernels.cuh"
+#include "comm.hpp"
 #include "persistence.hpp"
 
 namespace vdev {
@@ -229,7 +232,10 @@ struct DevBuf {
         if (v.empty()) return;
         UploadScope* scope = UploadScope::current();
         if (scope && scope->copy(p, v.data(), v.size() * sizeof(T))) return;
+        // No scope (index build, step seam): a pageable cudaMemcpy may return before its DMA has landed, and the batches'
+        // non-blocking streams do not order against the legacy stream, so wait for the copy itself.
         VDEV_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        VDEV_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     }
     size_t bytes() const { return n * sizeof(T); }
 };
@@ -374,6 +380,8 @@ struct DeviceIndex {
     int device = 0;
     int n_sms = 148;
     uint32_t shard_rank = 0, n_shards = 1;
+    uint32_t open_flags = 0;  // VGPU_OPEN_* (include/veloci_b200.h)
+    static const uint32_t kOpenNoPlanes = 1u, kOpenNoDelIndex = 2u;
     uint64_t num_docs = 0, anchor_lo = 0, anchor_hi = 0;
     std::unique_ptr<vhost::Persistence> host;
     std::map<std::string, DictDev> dicts;          // "<field>.textindex"
@@ -382,6 +390,12 @@ struct DeviceIndex {
     std::map<std::string, ColumnDev> boosts;       // "<field>.boost_valid_to_value"
     std::map<std::string, PhraseDev> phrases;
     PlaneSetDev planes;
+    std::unique_ptr<ShardComm> comm;  // set by vgpu_comm_init: this handle is shard `comm->rank` of `comm->n_ranks`
+    // Base pointers of the structures plan tables refer to, in name order (the same for every handle of one directory),
+    // and a fingerprint of their names and sizes: see plan_blob.hpp.
+    std::vector<const void*> reloc_ptrs;
+    std::unordered_map<const void*, uint32_t> reloc_index;
+    uint64_t reloc_fingerprint = 0;
     uint64_t max_posting_list = 0;   // longest posting list of the shard
     uint64_t max_nonplane_list = 0;  // ... among the terms without a plane
     size_t device_bytes = 0;
@@ -467,9 +481,24 @@ struct DeviceIndex {
     void ensure_del_index(const std::string& path, int level) {
         std::lock_guard<std::mutex> g(build_mu);
         auto it = dicts.find(path);
-        if (it == dicts.end() || it->second.del[level].built || getenv("VELOCI_NO_DELINDEX")) return;
+        if (it == dicts.end() || it->second.del[level].built || (open_flags & kOpenNoDelIndex)) return;
         VDEV_CUDA(cudaSetDevice(device));
-        build_del_index(it->second, level);
+        try {
+            build_del_index(it->second, level);
+        } catch (const std::exception&) {  // no room for the two-deletion index: the dictionary scan stays responsible
+            it->second.del[level] = DelIndexDev();
+            cudaGetLastError();
+        }
+    }
+    // Views of a dictionary taken while no build is in flight (the planner thread of search_stream may be inside
+    // ensure_del_index for the same dictionary).
+    DictView dict_view(const std::string& path) {
+        std::lock_guard<std::mutex> g(build_mu);
+        return dicts.at(path).view();
+    }
+    bool del_index_built(const std::string& path, int level) {
+        std::lock_guard<std::mutex> g(build_mu);
+        return dicts.at(path).del[level].built;
     }
 
     void build_dict(const std::string& path, const vhost::TermDict& d) {
@@ -518,7 +547,7 @@ struct DeviceIndex {
                 dd.variants[1] += 1 + len + (len >= 2 ? len * (len - 1) / 2 : 0);
             }
         }
-        if (!getenv("VELOCI_NO_DELINDEX")) build_del_index(dd, 0);
+        if (!(open_flags & kOpenNoDelIndex)) build_del_index(dd, 0);
         device_bytes += dd.ids.bytes() + dd.lower_bytes.bytes() + dd.lower.sym.bytes() + dd.lower.off.bytes() + dd.lower.tiles.bytes() + dd.raw.sym.bytes() + dd.raw.off.bytes() + dd.raw.tiles.bytes();
         dicts.emplace(path, std::move(dd));
     }
@@ -527,7 +556,10 @@ struct DeviceIndex {
         const size_t n = v.num_ids();
         std::vector<uint64_t> off(n + 1, 0);
         const uint32_t lo = (uint32_t)anchor_lo, hi = (uint32_t)std::min<uint64_t>(anchor_hi, 0xFFFFFFFFull);
-        const bool all = (n_shards == 1);
+        // every structure of the shard is sized from metaData.json's num_docs: a posting outside [0, num_docs) (stale or
+        // corrupt metadata) must fail the load, not index past the planes and tile buckets
+        std::atomic<uint64_t> out_of_range{0};
+        const uint64_t docs = num_docs;
         unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
         auto parallel_terms = [&](auto&& fn) {
             std::vector<std::thread> pool;
@@ -542,10 +574,16 @@ struct DeviceIndex {
         parallel_terms([&](size_t a, size_t b) {
             for (size_t id = a; id < b; ++id) {
                 uint64_t c = 0;
-                v.for_each((uint32_t)id, [&](uint32_t anchor, uint32_t) { c += (all || (anchor >= lo && anchor < hi)) ? 1 : 0; });
+                uint64_t bad = 0;
+                v.for_each((uint32_t)id, [&](uint32_t anchor, uint32_t) {
+                    c += (anchor >= lo && anchor < hi) ? 1 : 0;
+                    bad += anchor >= docs ? 1 : 0;
+                });
                 off[id + 1] = c;
+                if (bad) out_of_range.fetch_add(bad, std::memory_order_relaxed);
             }
         });
+        if (out_of_range.load()) throw vhost::IoError(path + ": " + std::to_string(out_of_range.load()) + " postings have an anchor id >= num_docs (" + std::to_string(docs) + ") of metaData.json");
         for (size_t i = 0; i < n; ++i) off[i + 1] += off[i];
         const uint64_t total = off[n];
         std::vector<Posting> post(total);
@@ -553,7 +591,7 @@ struct DeviceIndex {
             for (size_t id = a; id < b; ++id) {
                 uint64_t at = off[id];
                 v.for_each((uint32_t)id, [&](uint32_t anchor, uint32_t raw) {
-                    if (all || (anchor >= lo && anchor < hi)) {
+                    if (anchor >= lo && anchor < hi) {
                         post[at].anchor = anchor;
                         // AnchorScore keeps the score as f16 (persistence_score/mod.rs:9-12); resolve_token_to_anchor
                         // uses `score.to_f32() / 100.0` (search_field.rs:426): divided here, once, in IEEE f32
@@ -624,7 +662,7 @@ struct DeviceIndex {
         device_bytes += c.bits.bytes();
         // level thresholds: the (1 - 2^-(j+1)) quantiles of a sample of the shard's values
         const uint64_t span = anchor_hi - anchor_lo;
-        if (c.non_negative && span > 0 && span < 0xFFFFFFFFull && !getenv("VELOCI_NO_PLANES")) {
+        if (c.non_negative && span > 0 && span < 0xFFFFFFFFull && !(open_flags & kOpenNoPlanes)) {
             std::vector<float> sample;
             const size_t lo = (size_t)std::min<uint64_t>(anchor_lo, n), hi = (size_t)std::min<uint64_t>(anchor_hi, n);
             const size_t stride = std::max<size_t>(1, (hi - lo) >> 20);
@@ -658,7 +696,7 @@ struct DeviceIndex {
     // Head-term planes: the terms with df >= span / 128 over all postings stores, at most kMaxPlanes by df.
     void build_planes() {
         const uint64_t span = anchor_hi - anchor_lo;
-        if (getenv("VELOCI_NO_PLANES") || span == 0 || span >= 0xFFFFFFFFull) return;
+        if ((open_flags & kOpenNoPlanes) || span == 0 || span >= 0xFFFFFFFFull) return;
         const uint64_t min_df = std::max<uint64_t>(1, span / 128);
         struct Cand {
             uint64_t df;
@@ -737,7 +775,7 @@ struct DeviceIndex {
         phrases.emplace(path, std::move(p));
     }
 
-    static std::unique_ptr<DeviceIndex> open(const std::string& dir, int device, uint32_t rank, uint32_t n_shards) {
+    static std::unique_ptr<DeviceIndex> open(const std::string& dir, int device, uint32_t rank, uint32_t n_shards, uint32_t flags = 0) {
         if (n_shards == 0 || rank >= n_shards) throw std::runtime_error("invalid shard rank");
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
@@ -749,6 +787,7 @@ struct DeviceIndex {
         VDEV_CUDA(cudaDeviceGetAttribute(&ix->n_sms, cudaDevAttrMultiProcessorCount, device));
         ix->shard_rank = rank;
         ix->n_shards = n_shards;
+        ix->open_flags = flags;
         ix->host = vhost::Persistence::load(dir);
         ix->num_docs = ix->host->metadata.num_docs;
         ix->anchor_lo = ix->num_docs * rank / n_shards;
@@ -763,7 +802,27 @@ struct DeviceIndex {
         for (auto& kv : ix->host->boost_valueid_to_value) ix->build_boost(kv.first, kv.second);
         for (auto& kv : ix->host->phrase_pair_to_anchor) ix->build_phrase(kv.first, kv.second);
         VDEV_CUDA(cudaDeviceSynchronize());
+        ix->build_reloc_table();
         return ix;
+    }
+
+    void build_reloc_table() {
+        uint64_t h = 0xCBF29CE484222325ull;
+        auto mix = [&](const void* p, size_t n) {
+            const uint8_t* b = static_cast<const uint8_t*>(p);
+            for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 0x100000001B3ull;
+        };
+        auto add = [&](const std::string& name, const void* p, uint64_t size) {
+            mix(name.data(), name.size()), mix(&size, 8);
+            reloc_index.emplace(p, (uint32_t)reloc_ptrs.size());
+            reloc_ptrs.push_back(p);
+        };
+        mix(&num_docs, 8);
+        for (auto& kv : boosts) add(kv.first, kv.second.bits.p, kv.second.n), add(kv.first + "#levels", kv.second.level_hdr.p, kv.second.level_hdr.p ? 1 : 0);
+        for (auto& kv : stores) add(kv.first, kv.second.off.p, kv.second.n_ids), add(kv.first + "#val", kv.second.val.p, kv.second.h_val.size());
+        for (auto& kv : phrases) add(kv.first, kv.second.keys.p, kv.second.n), add(kv.first + "#off", kv.second.off.p, kv.second.n), add(kv.first + "#anchors", kv.second.anchors.p, 0);
+        for (auto& kv : dicts) mix(kv.first.data(), kv.first.size()), mix(&kv.second.n, sizeof kv.second.n);
+        reloc_fingerprint = h;
     }
 };
 

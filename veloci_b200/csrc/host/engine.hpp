@@ -15,6 +15,7 @@
 
 #include "../cuda/bitvec.cuh"
 #include "../cuda/kernels.cuh"
+#include "plan_blob.hpp"
 #include "planner.hpp"
 
 namespace vdev {
@@ -30,6 +31,17 @@ struct ExplicitList {  // a caller-provided hit list used as a leaf (step seam)
 };
 
 static const int kPhases = 6;
+
+// Timing experiments read their settings from the environment only in a library built with -DVELOCI_PROBES
+// (tools/*_probe.py); the release library never consults them (one of them, VELOCI_TILE_LIMIT, gives wrong results).
+inline const char* probe_env(const char* name) {
+#ifdef VELOCI_PROBES
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 
 struct TermHit {
     uint32_t id;
@@ -143,8 +155,62 @@ struct Batch {
     bool matched = false, executed = false, fetched = false;
     std::vector<uint64_t> h_keys, h_hits;
     float phase_ms[kPhases] = {};
-    uint64_t stat_postings = 0, stat_matches = 0, stat_union = 0;
+    uint64_t stat_postings = 0, stat_matches = 0, stat_union = 0, stat_sparse = 0;
+    uint64_t stat_plane_item_evals = 0, stat_plane_unconverged = 0, stat_plane_sweepless = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
+
+    // Optional per-kernel timing (vgpu_batch_set_profiling): a pair of CUDA events around every launch of the next
+    // execute, on the batch's stream; read back by kernel_times_json() after the step.
+    bool profiling = false;
+    struct KernelSpan {
+        const char* name;
+        cudaEvent_t a, b;
+    };
+    std::vector<KernelSpan> spans;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> span_pool;
+    size_t spans_used = 0;
+    template <class F>
+    void timed(const char* name, F&& launch) {
+        if (!profiling) return launch();
+        if (spans_used == span_pool.size()) {
+            cudaEvent_t a, b;
+            VDEV_CUDA(cudaEventCreate(&a));
+            VDEV_CUDA(cudaEventCreate(&b));
+            span_pool.emplace_back(a, b);
+        }
+        const auto& ev2 = span_pool[spans_used++];
+        const uint64_t before = launches_so_far();
+        VDEV_CUDA(cudaEventRecord(ev2.first, stream));
+        launch();
+        if (launches_so_far() == before) {  // the wrapper had nothing to launch
+            --spans_used;
+            return;
+        }
+        VDEV_CUDA(cudaEventRecord(ev2.second, stream));
+        spans.push_back(KernelSpan{name, ev2.first, ev2.second});
+    }
+    // {"kernel": {"launches": n, "ms": total}, ...} of the last execute with profiling on
+    std::string kernel_times_json() {
+        std::vector<std::pair<std::string, std::pair<uint32_t, double>>> agg;
+        for (auto& sp : spans) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, sp.a, sp.b) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            bool found = false;
+            for (auto& kv : agg)
+                if (kv.first == sp.name) kv.second.first += 1, kv.second.second += ms, found = true;
+            if (!found) agg.push_back({sp.name, {1u, (double)ms}});
+        }
+        std::string out = "{";
+        for (size_t i = 0; i < agg.size(); ++i) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %u, \"ms\": %.6f}", i ? ", " : "", agg[i].first.c_str(), agg[i].second.first, agg[i].second.second);
+            out += buf;
+        }
+        return out + "}";
+    }
 
     Batch() = default;
     Batch(const Batch&) = delete;
@@ -152,6 +218,7 @@ struct Batch {
     ~Batch() {
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto& pr : span_pool) cudaEventDestroy(pr.first), cudaEventDestroy(pr.second);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -201,6 +268,14 @@ struct Batch {
             auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
             fprintf(stderr, "[veloci] prepare: parse + plan %.2f ms on %u threads + merge %.2f ms, upload %.2f ms\n", ms(t0, t_joined), hw, ms(t_joined, t1), ms(t2, t3));
         }
+    }
+
+    // A plan made by another handle of the same index directory (vgpu_batch_export_plan on the planning process).
+    void prepare_from_blob(DeviceIndex* index, const void* blob, size_t len) {
+        ix = index;
+        vplan::import_plan(ix, blob, len, plan);
+        n = (uint32_t)plan.requests.size();
+        upload_plan();
     }
 
     // field search only (vgpu_field_search)
@@ -298,6 +373,7 @@ struct Batch {
             slices[i].m_begin = 0, slices[i].n_match = 1, slices[i].n_dense = 0, slices[i].sparse_row = (uint32_t)i, slices[i].sparse_base = sparse.size();
             for (auto& e : entries) sparse.push_back(SparseEntry{e.first, e.second ? e.second : 1u});
         }
+        UploadScope staged(stream);
         d_bucket.upload(bucket);
         d_sparse.upload(sparse);
         d_slices.upload(slices);
@@ -330,7 +406,7 @@ struct Batch {
                 if (bs.levels && !lev_dev)
                     for (auto& kv : ix->boosts)
                         if (kv.second.level_hdr.p == bs.levels) lev_dev = bs.levels, lev_hdr = kv.second.h_levels;
-        if (const char* env = getenv("VELOCI_TILE_LOG2")) {
+        if (const char* env = probe_env("VELOCI_TILE_LOG2")) {
             int v = atoi(env);
             if (v >= 8 && v <= 13 && tile_kernel_smem((uint32_t)v, L)) tile_log2 = (uint32_t)v;
         }
@@ -381,16 +457,15 @@ struct Batch {
                 const PartQuery& pq = plan.parts[p];
                 if (pq.flags & (kPartList | kPartInjected)) continue;
                 const uint32_t d = plan.part_dict[p];
-                const DictDev& dict = ix->dicts.at(plan.dict_names[d]);
                 bool probe = pq.m >= 1 && pq.d_match <= 2 && !(pq.flags & (kPartPrefix | kPartRawCase));
-                if (probe && pq.d_match == 2 && !dict.del[1].built) ix->ensure_del_index(plan.dict_names[d], 1);
-                probe = probe && dict.del[pq.d_match == 2 ? 1 : 0].built;
+                if (probe && pq.d_match == 2 && !ix->del_index_built(plan.dict_names[d], 1)) ix->ensure_del_index(plan.dict_names[d], 1);
+                probe = probe && ix->del_index_built(plan.dict_names[d], pq.d_match == 2 ? 1 : 0);
                 (probe ? probe_of_dict : parts_of_dict)[d].push_back(p);
                 max_m_of_dict[d] = std::max(max_m_of_dict[d], pq.m);
             }
         }
         std::vector<DictView> dv;
-        for (auto& name : plan.dict_names) dv.push_back(ix->dicts.at(name).view());
+        for (auto& name : plan.dict_names) dv.push_back(ix->dict_view(name));
         d_dicts.upload(dv);
         std::vector<PostingsView> pv;
         for (auto& name : plan.postings_names) pv.push_back(ix->postings.at(name).view());
@@ -442,10 +517,10 @@ struct Batch {
 
     // count pass (la.sparse == nullptr) or fill pass of every list producer of the batch
     void run_list_producers(const ListArgs& la) {
-        launch_phrase_pairs(stream, d_phrase_members.p, (uint32_t)plan.phrase_members.size(), la);
-        launch_ids_to_anchor(stream, d_ids_members.p, (uint32_t)plan.ids_members.size(), la);
-        launch_boost_to_anchor(stream, d_boost_members.p, (uint32_t)plan.boost_members.size(), la);
-        launch_text_locality(stream, d_tl_instances.p, (uint32_t)plan.tl_instances.size(), d_tl_term_parts.p, d_req_error.p, la);
+        timed("phrase_pairs", [&] { launch_phrase_pairs(stream, d_phrase_members.p, (uint32_t)plan.phrase_members.size(), la); });
+        timed("ids_to_anchor", [&] { launch_ids_to_anchor(stream, d_ids_members.p, (uint32_t)plan.ids_members.size(), la); });
+        timed("boost_to_anchor", [&] { launch_boost_to_anchor(stream, d_boost_members.p, (uint32_t)plan.boost_members.size(), la); });
+        timed("text_locality", [&] { launch_text_locality(stream, d_tl_instances.p, (uint32_t)plan.tl_instances.size(), d_tl_term_parts.p, d_req_error.p, la); });
     }
 
     template <class T>
@@ -479,10 +554,10 @@ struct Batch {
                 }
                 const uint32_t capacity = (uint32_t)std::min<size_t>(d_records.n, 0xFFFFFFFFu);
                 for (size_t d = 0; d < n_dicts; ++d) {
-                    const DictView dict = ix->dicts.at(plan.dict_names[d]).view();
-                    launch_fuzzy_probe(stream, dict, d_parts.p, d_probe_of_dict[d].p, (uint32_t)probe_of_dict[d].size(), d_records.p, capacity, d_counters.p, d_overflow_of_dict[d].p,
-                                       d_overflow_count.p + d);
-                    launch_fuzzy_match(stream, dict, d_parts.p, d_parts_of_dict[d].p, (uint32_t)parts_of_dict[d].size(), max_m_of_dict[d], d_records.p, capacity, d_counters.p);
+                    const DictView dict = ix->dict_view(plan.dict_names[d]);
+                    timed("fuzzy_probe", [&] { launch_fuzzy_probe(stream, dict, d_parts.p, d_probe_of_dict[d].p, (uint32_t)probe_of_dict[d].size(), d_records.p, capacity, d_counters.p, d_overflow_of_dict[d].p,
+                                       d_overflow_count.p + d); });
+                    timed("fuzzy_match", [&] { launch_fuzzy_match(stream, dict, d_parts.p, d_parts_of_dict[d].p, (uint32_t)parts_of_dict[d].size(), max_m_of_dict[d], d_records.p, capacity, d_counters.p); });
                 }
                 VDEV_CUDA(cudaMemcpyAsync(overflow.data(), d_overflow_count.p, n_dicts * 8, cudaMemcpyDeviceToHost, stream));
                 n_match = read_back(d_counters.p);
@@ -490,8 +565,8 @@ struct Batch {
                 bool rescanned = false;
                 for (size_t d = 0; d < n_dicts; ++d)
                     if (overflow[d]) {  // candidate sets too large for the probe: scan the dictionary for those parts
-                        const DictView dict = ix->dicts.at(plan.dict_names[d]).view();
-                        launch_fuzzy_match(stream, dict, d_parts.p, d_overflow_of_dict[d].p, (uint32_t)overflow[d], max_m_of_dict[d], d_records.p, capacity, d_counters.p);
+                        const DictView dict = ix->dict_view(plan.dict_names[d]);
+                        timed("fuzzy_match", [&] { launch_fuzzy_match(stream, dict, d_parts.p, d_overflow_of_dict[d].p, (uint32_t)overflow[d], max_m_of_dict[d], d_records.p, capacity, d_counters.p); });
                         rescanned = true;
                     }
                 if (rescanned) n_match = read_back(d_counters.p);
@@ -503,6 +578,7 @@ struct Batch {
             VDEV_CUDA(cudaMemsetAsync(d_counters.p, 0, d_counters.bytes(), stream));
             std::vector<MatchRecord> rec(n_injected);
             for (uint32_t i = 0; i < n_injected; ++i) rec[i] = MatchRecord{0u, i};
+            UploadScope staged(stream);
             d_records.upload(rec);
             n_match = n_injected;
         }
@@ -518,8 +594,8 @@ struct Batch {
         VDEV_CUDA(cudaMemsetAsync(d_dense_cursor.p, 0, d_dense_cursor.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_sparse_cursor.p, 0, d_sparse_cursor.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_part_est.p, 0, d_part_est.bytes(), stream));
-        launch_group_count(stream, d_records.p, M, d_part_count.p);
-        launch_scan_u32(stream, d_part_count.p, d_part_begin.p, n_parts);
+        timed("group_count", [&] { launch_group_count(stream, d_records.p, M, d_part_count.p); });
+        timed("scan_u32", [&] { launch_scan_u32(stream, d_part_count.p, d_part_begin.p, n_parts); });
         ScoreScatterArgs a;
         a.records = d_records.p, a.n_records = M, a.parts = d_parts.p, a.part_dict = d_part_dict.p, a.dicts = d_dicts.p, a.postings = d_postings.p;
         a.part_begin = d_part_begin.p, a.dense_cursor = d_dense_cursor.p, a.sparse_cursor = d_sparse_cursor.p, a.n_dense_rows = reinterpret_cast<uint32_t*>(d_counters.p + 3);
@@ -528,7 +604,7 @@ struct Batch {
         const bool has_injected = mode == kTermHits || !plan.bounded.empty();
         a.inj_terms = has_injected ? d_inj_terms.p : nullptr, a.inj_scores = has_injected ? d_inj_scores.p : nullptr, a.inj_all = mode == kTermHits ? 1u : 0u;
         a.part_planes = use_planes ? d_part_planes.p : nullptr, a.g_plane = use_planes ? d_g_plane.p : nullptr;
-        launch_score_scatter(stream, a);
+        timed("score_scatter", [&] { launch_score_scatter(stream, a); });
         VDEV_CUDA(cudaEventRecord(ev[2], stream));
         VDEV_CUDA(cudaStreamSynchronize(stream));
         VDEV_CUDA(cudaGetLastError());
@@ -559,7 +635,10 @@ struct Batch {
                 inj_terms.push_back(h.id), inj_scores.push_back(h.score);
             }
         }
-        d_inj_terms.upload(inj_terms), d_inj_scores.upload(inj_scores);
+        {
+            UploadScope staged(stream);  // ordered with the kernels of this batch's stream that read them
+            d_inj_terms.upload(inj_terms), d_inj_scores.upload(inj_scores);
+        }
         h2d_bytes += inj_terms.size() * 8 + records.size() * sizeof(MatchRecord);
     }
 
@@ -587,8 +666,39 @@ struct Batch {
 
     // ------------------------------------------------------------ all phases
     void execute() {
-        execute_begin();
+        if (ix->comm && ix->comm->n_ranks > 1 && mode == kRequests) return execute_sharded();
+        execute_begin(false);  // no host round trip between the seed pass and the bulk pass
         execute_finish();
+    }
+
+    // The whole step on an anchor-range shard with a communicator (vgpu_comm_init): seed pass -> all-reduce(max) of the
+    // requests' thresholds -> bulk pass -> all-gather of the shard-local top-k rows and hit counts (all-reduce(sum) of
+    // the facet histograms) -> final merge, all on the batch's stream, no host synchronisation between them.  Every rank
+    // ends up with the complete result.  Collective: every rank of the communicator must execute the same batch.
+    DevBuf<uint64_t> d_gather_keys, d_gather_hits;
+    void execute_sharded() {
+        ShardComm& c = *ix->comm;
+        execute_begin(false);
+        try {
+            if (n) c.all_reduce_max_u64(d_tau.p, n, stream);  // the global k-th best is at least the largest local one
+            execute_finish(false);
+            const uint32_t R = c.n_ranks;
+            d_gather_keys.reserve((size_t)R * std::max<uint32_t>(n, 1) * stride), d_gather_hits.reserve((size_t)R * std::max<uint32_t>(n, 1));
+            if (n) {
+                c.group_start();
+                c.all_gather_u64(d_out_keys.p, d_gather_keys.p, (size_t)n * stride, stream);
+                c.all_gather_u64(d_out_hits.p, d_gather_hits.p, n, stream);
+                if (n_facets) c.all_reduce_sum_u32(d_facet_hist.p, d_facet_hist.n, stream);
+                c.group_end();
+                timed("merge_heaps", [&] { launch_merge_heaps(stream, d_gather_keys.p, d_gather_hits.p, R, n, stride, d_programs.p, d_out_keys.p, d_out_hits.p); });
+                if (n_facets) timed("facet_topk", [&] { launch_facet_topk(stream, d_facets.p, d_facet_top.p, n_facets, facet_stride, d_facet_ids.p, d_facet_counts.p, d_facet_n.p); });
+            }
+        } catch (const NcclError&) {
+            cudaStreamSynchronize(stream);
+            throw;
+        }
+        VDEV_CUDA(cudaEventRecord(ev[6], stream));  // the final phase now ends after the exchange and the merge
+        finish_sync();
     }
 
     // PlaneArgs of one stage of the plane evaluation: tiles [t0, t1)
@@ -607,11 +717,11 @@ struct Batch {
         uint32_t unit = stage == 2 ? std::max<uint32_t>(256, (uint32_t)(((uint64_t)n * (t1 - t0)) / ((uint64_t)n_sms * 24) + 1))
                                    : std::max<uint32_t>(16, ((uint64_t)n * (t1 - t0) + want_units - 1) / want_units);
         unit = std::min<uint32_t>(unit, 4096u);
-        if (const char* env = getenv("VELOCI_UNIT_ITEMS"))  // experiments: items per unit of the bulk pass, as given
+        if (const char* env = probe_env("VELOCI_UNIT_ITEMS"))  // experiments: items per unit of the bulk pass, as given
             if (stage == 2) unit = (uint32_t)std::min(4096, std::max(16, atoi(env)));
         unit = (unit + 15u) & ~15u;
         a.tile_begin = t0, a.unit_items = unit;
-        a.force_general = getenv("VELOCI_FORCE_GENERAL_SWEEP") ? 1u : 0u;
+        a.force_general = probe_env("VELOCI_FORCE_GENERAL_SWEEP") ? 1u : 0u;
         a.chunks_per_tile = (n + unit - 1) / unit;
         a.n_units = (t1 - t0) * a.chunks_per_tile;
         a.work_counter = d_counters.p + 10 + stage;
@@ -620,10 +730,11 @@ struct Batch {
 
     // Everything up to the point where the requests' thresholds (k-th best so far) are worth sharing between anchor-range
     // shards: match, slicing, item scan and the seed pass of the plane evaluation.  Returns with the stream idle.
-    void execute_begin() {
+    void execute_begin(bool sync_at_end = true) {
         VDEV_CUDA(cudaSetDevice(ix->device));
         executed = false, fetched = false, begun = false;
         d2h_bytes = 0;
+        spans.clear(), spans_used = 0;
         uint32_t M = 0;
         if (mode != kLists) {
             run_match();
@@ -634,29 +745,30 @@ struct Batch {
             DenseOffsetsArgs da;
             da.row_match = d_row_match.p, da.g_part = d_g_part.p, da.g_begin = d_g_begin.p, da.g_df = d_g_df.p, da.parts = d_parts.p, da.postings = d_postings.p;
             da.toff = d_toff.p, da.n_tiles = n_tiles, da.tile_log2 = tile_log2, da.anchor_lo = (uint32_t)ix->anchor_lo;
-            launch_dense_tile_offsets(stream, da, n_rows);
+            timed("dense_tile_offsets", [&] { launch_dense_tile_offsets(stream, da, n_rows); });
             VDEV_CUDA(cudaMemsetAsync(d_bucket.p, 0, d_bucket.bytes(), stream));
             SparseArgs sa;
             sa.n_matches = M, sa.g_row = d_g_row.p, sa.g_df = d_g_df.p, sa.g_part = d_g_part.p, sa.g_begin = d_g_begin.p, sa.g_score = d_g_score.p;
             sa.parts = d_parts.p, sa.postings = d_postings.p, sa.bucket = d_bucket.p, sa.sparse_base = d_sparse_base.p, sa.sparse = nullptr;
             sa.n_tiles = n_tiles, sa.tile_log2 = tile_log2, sa.anchor_lo = (uint32_t)ix->anchor_lo;
             sa.max_df = (uint32_t)std::min<uint64_t>(use_planes ? ix->max_nonplane_list : std::min<uint64_t>(dense_min(), ix->max_posting_list), 0xFFFFFFFFull);
-            launch_sparse_count(stream, sa);
+            timed("sparse_count", [&] { launch_sparse_count(stream, sa); });
             ListArgs la;
             la.part_begin = d_part_begin.p, la.g_term = d_g_term.p, la.bucket = d_bucket.p, la.sparse_base = d_sparse_base.p, la.sparse = nullptr;
             la.n_tiles = n_tiles, la.tile_log2 = tile_log2, la.anchor_lo = (uint32_t)ix->anchor_lo, la.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
             run_list_producers(la);
-            launch_sparse_scan(stream, d_bucket.p, n_tiles, d_sparse_total.p, n_parts);
-            launch_scan_u64(stream, d_sparse_total.p, d_sparse_base.p, n_parts);
+            timed("sparse_scan", [&] { launch_sparse_scan(stream, d_bucket.p, n_tiles, d_sparse_total.p, n_parts); });
+            timed("scan_u64", [&] { launch_scan_u64(stream, d_sparse_total.p, d_sparse_base.p, n_parts); });
             const uint64_t n_sparse = read_back(d_sparse_base.p + n_parts);
+            stat_sparse = n_sparse;
             d_sparse.reserve((size_t)std::max<uint64_t>(n_sparse, 1));
             sa.sparse = d_sparse.p;
-            launch_sparse_fill(stream, sa);
+            timed("sparse_fill", [&] { launch_sparse_fill(stream, sa); });
             la.sparse = d_sparse.p;
             run_list_producers(la);
-            launch_part_slices(stream, d_slices.p, d_part_begin.p, d_dense_cursor.p, d_sparse_base.p, d_parts.p, n_parts);
-            launch_finalize_programs(stream, d_programs.p, n, d_prog.p, d_leaf_part.p, d_part_est.p, d_counters.p + 2);
-            if (use_planes) launch_build_fast_desc(stream, d_programs.p, n, d_leaf_part.p, d_part_planes.p, ix->planes.wmax.p, d_fast.p);
+            timed("part_slices", [&] { launch_part_slices(stream, d_slices.p, d_part_begin.p, d_dense_cursor.p, d_sparse_base.p, d_parts.p, n_parts); });
+            timed("finalize_programs", [&] { launch_finalize_programs(stream, d_programs.p, n, d_prog.p, d_leaf_part.p, d_part_est.p, d_counters.p + 2); });
+            if (use_planes) timed("build_fast_desc", [&] { launch_build_fast_desc(stream, d_programs.p, n, d_leaf_part.p, d_part_planes.p, ix->planes.wmax.p, d_fast.p); });
             if (use_planes && getenv("VELOCI_DEBUG")) {
                 std::vector<FastDesc> fd(n);
                 std::vector<PartPlanes> pp(n_parts);
@@ -701,11 +813,11 @@ struct Batch {
                 VDEV_CUDA(cudaMemsetAsync(d_fast_item_cursor.p, 0, d_fast_item_cursor.bytes(), stream));
             }
             VDEV_CUDA(cudaMemsetAsync(d_counters.p + 5, 0, 16, stream));
-            launch_item_scan(stream, sc, false);
+            timed("item_scan", [&] { launch_item_scan(stream, sc, false); });
             unsigned long long counts[2];
             VDEV_CUDA(cudaMemcpyAsync(counts, d_counters.p + 5, 16, cudaMemcpyDeviceToHost, stream));
             if (planes_on) {
-                launch_scan_u32(stream, d_fast_item_cursor.p, d_fast_item_begin.p, n_tiles);
+                timed("scan_u32", [&] { launch_scan_u32(stream, d_fast_item_cursor.p, d_fast_item_begin.p, n_tiles); });
                 VDEV_CUDA(cudaMemcpyAsync(&n_fast_items, d_fast_item_begin.p + n_tiles, 4, cudaMemcpyDeviceToHost, stream));
                 d2h_bytes += 4;
             }
@@ -721,7 +833,7 @@ struct Batch {
                 VDEV_CUDA(cudaMemsetAsync(d_fast_item_cursor.p, 0, d_fast_item_cursor.bytes(), stream));
             }
             VDEV_CUDA(cudaMemsetAsync(d_counters.p + 5, 0, 16, stream));
-            launch_item_scan(stream, sc, true);
+            timed("item_scan", [&] { launch_item_scan(stream, sc, true); });
         }
         stat_fast_items = n_fast_items, stat_general_items = n_items;
         VDEV_CUDA(cudaEventRecord(ev[3], stream));
@@ -739,24 +851,26 @@ struct Batch {
             // Without a boost column in the batch the first tile runs in full instead.
             uint32_t want_tiles = 8;
             seed_level = 5;
-            if (const char* env = getenv("VELOCI_SEED_TILES")) want_tiles = (uint32_t)std::max(0, atoi(env));
-            if (const char* env = getenv("VELOCI_SEED_LEVEL")) seed_level = (uint32_t)std::min(15, std::max(1, atoi(env)));
+            if (const char* env = probe_env("VELOCI_SEED_TILES")) want_tiles = (uint32_t)std::max(0, atoi(env));
+            if (const char* env = probe_env("VELOCI_SEED_LEVEL")) seed_level = (uint32_t)std::min(15, std::max(1, atoi(env)));
             seeded_tiles = lev_dev ? std::min<uint32_t>(want_tiles, n_tiles) : 0;
             if (seeded_tiles) {
                 PlaneArgs seed = plane_stage_args(0, 0, seeded_tiles);
                 seed.pass_mode = 1, seed.seed_level = seed_level;
-                launch_plane_eval(stream, seed, n_sms);
+                timed("plane_eval_seed", [&] { launch_plane_eval(stream, seed, n_sms); });
             } else {
-                launch_plane_eval(stream, plane_stage_args(0, 0, std::min<uint32_t>(1, n_tiles)), n_sms);
+                timed("plane_eval", [&] { launch_plane_eval(stream, plane_stage_args(0, 0, std::min<uint32_t>(1, n_tiles)), n_sms); });
             }
         }
-        VDEV_CUDA(cudaStreamSynchronize(stream));
-        VDEV_CUDA(cudaGetLastError());
+        if (sync_at_end) {
+            VDEV_CUDA(cudaStreamSynchronize(stream));
+            VDEV_CUDA(cudaGetLastError());
+        }
         begun = true;
     }
 
     // The rest of the step: the bulk of the plane evaluation, the general items, the final order.
-    void execute_finish() {
+    void execute_finish(bool sync_at_end = true) {
         if (!begun) throw std::runtime_error("execute_finish without execute_begin");
         VDEV_CUDA(cudaSetDevice(ix->device));
         begun = false;
@@ -766,11 +880,11 @@ struct Batch {
             // the normal pass: every tile (the seeded ones skip what the seed pass evaluated), or the tiles after the first
             const uint32_t first = seeded_tiles ? 0u : std::min<uint32_t>(1, n_tiles);
             uint32_t last = n_tiles;
-            if (const char* env = getenv("VELOCI_TILE_LIMIT")) last = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, atoi(env)));  // timing experiments only: wrong results
+            if (const char* env = probe_env("VELOCI_TILE_LIMIT")) last = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, atoi(env)));  // timing experiments only: wrong results
             if (last > first) {
                 PlaneArgs rest = plane_stage_args(2, first, last);
                 rest.pass_mode = seeded_tiles ? 2 : 0, rest.seed_level = seed_level, rest.seeded_tiles = seeded_tiles;
-                launch_plane_eval(stream, rest, n_sms);
+                timed("plane_eval", [&] { launch_plane_eval(stream, rest, n_sms); });
             }
         }
         VDEV_CUDA(cudaEventRecord(ev[4], stream));
@@ -786,13 +900,17 @@ struct Batch {
             a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
             a.work_counter = d_counters.p + 1, a.n_items = n_items;
             a.emit = d_emit.p, a.emit_count = d_counters.p + 4, a.emit_capacity = emit_capacity;
-            launch_tile_eval(stream, a, n_sms);
+            timed("tile_eval", [&] { launch_tile_eval(stream, a, n_sms); });
         }
         VDEV_CUDA(cudaEventRecord(ev[5], stream));
         // ---- phase 5: final order of the local heaps, top groups of the facet histograms
-        if (n_facets) launch_facet_topk(stream, d_facets.p, d_facet_top.p, n_facets, facet_stride, d_facet_ids.p, d_facet_counts.p, d_facet_n.p);
-        launch_merge_heaps(stream, reinterpret_cast<const uint64_t*>(d_heap.p), reinterpret_cast<const uint64_t*>(d_num_hits.p), 1, n, stride, d_programs.p, d_out_keys.p, d_out_hits.p);
+        if (n_facets) timed("facet_topk", [&] { launch_facet_topk(stream, d_facets.p, d_facet_top.p, n_facets, facet_stride, d_facet_ids.p, d_facet_counts.p, d_facet_n.p); });
+        timed("merge_heaps", [&] { launch_merge_heaps(stream, reinterpret_cast<const uint64_t*>(d_heap.p), reinterpret_cast<const uint64_t*>(d_num_hits.p), 1, n, stride, d_programs.p, d_out_keys.p, d_out_hits.p); });
         VDEV_CUDA(cudaEventRecord(ev[6], stream));
+        if (sync_at_end) finish_sync();
+    }
+
+    void finish_sync() {
         VDEV_CUDA(cudaStreamSynchronize(stream));
         VDEV_CUDA(cudaGetLastError());
         for (int p = 0; p < kPhases; ++p) VDEV_CUDA(cudaEventElapsedTime(&phase_ms[p], ev[p], ev[p + 1]));
@@ -801,9 +919,9 @@ struct Batch {
 
     void merge_gathered(const uint64_t* keys_dev, const uint64_t* hits_dev, uint32_t n_shards) {
         VDEV_CUDA(cudaSetDevice(ix->device));
-        launch_merge_heaps(stream, keys_dev, hits_dev, n_shards, n, stride, d_programs.p, d_out_keys.p, d_out_hits.p);
+        timed("merge_heaps", [&] { launch_merge_heaps(stream, keys_dev, hits_dev, n_shards, n, stride, d_programs.p, d_out_keys.p, d_out_hits.p); });
         // the caller has summed the shards' facet histograms (vgpu_batch_facet_histograms) by now: pick the groups again
-        if (n_facets) launch_facet_topk(stream, d_facets.p, d_facet_top.p, n_facets, facet_stride, d_facet_ids.p, d_facet_counts.p, d_facet_n.p);
+        if (n_facets) timed("facet_topk", [&] { launch_facet_topk(stream, d_facets.p, d_facet_top.p, n_facets, facet_stride, d_facet_ids.p, d_facet_counts.p, d_facet_n.p); });
         VDEV_CUDA(cudaStreamSynchronize(stream));
         fetched = false;
     }
@@ -822,6 +940,7 @@ struct Batch {
             VDEV_CUDA(cudaStreamSynchronize(stream));
             stat_postings = stats[2];
             stat_plane_evaluated = stats[9];
+            stat_plane_item_evals = stats[8], stat_plane_unconverged = stats[13], stat_plane_sweepless = stats[14];
             if (getenv("VELOCI_DEBUG") && use_planes)
                 fprintf(stderr, "[veloci] plane path: %llu item evaluations (seed + bulk), %llu candidates, %llu items swept before their threshold converged, %llu answered from plane counts\n",
                         (unsigned long long)stats[8], (unsigned long long)stats[9], (unsigned long long)stats[13], (unsigned long long)stats[14]);

@@ -412,6 +412,9 @@ struct BatchPlan {
                         found = &b;
                     }
                     if (found) {
+                        // apply_boost_values_anchor (boost.rs:255-281) depends on the run of boosted hits before an anchor; a
+                        // run that starts in the previous anchor-range shard cannot be seen from this one
+                        if (ix->n_shards > 1) throw Unsupported("1:n boosts (a boost on the search part's own [] level) are outside the accelerated path on a sharded index");
                         vdev::BoostListMember m;
                         memset(&m, 0, sizeof m);
                         m.part = part;
@@ -775,7 +778,7 @@ struct BatchPlan {
         memset(&qp, 0, sizeof qp);
         // a failing request must not leave half-registered leaves behind
         const size_t leaf_mark = leaf_part.size(), prog_mark = prog.size(), boost_mark = boosts.size(), facet_mark = facets.size(), phrase_mark = phrase_members.size(), ids_mark = ids_members.size(), tl_mark = tl_instances.size(),
-                     tl_term_mark = tl_term_parts.size(), bm_mark = boost_members.size();
+                     tl_term_mark = tl_term_parts.size(), bm_mark = boost_members.size(), bounded_mark = bounded.size();
         try {
             if (parsed.status != 0) {
                 rp.status = parsed.status, rp.message = parsed.message;
@@ -799,6 +802,9 @@ struct BatchPlan {
             leaf_part.resize(leaf_mark), prog.resize(prog_mark), boosts.resize(boost_mark);
             facets.resize(facet_mark), facet_top.resize(facet_mark), facet_text_path.resize(facet_mark);
             phrase_members.resize(phrase_mark), ids_members.resize(ids_mark), tl_instances.resize(tl_mark), tl_term_parts.resize(tl_term_mark), boost_members.resize(bm_mark);
+            // per-part-top parts of the failed request: nothing references them any more, so they must not be matched and
+            // bounded on every execute (their PartQuery stays behind as an injected part without hits)
+            bounded.resize(bounded_mark);
             rp.facets.clear(), rp.has_facets = false;
             memset(&qp, 0, sizeof qp);
         }
