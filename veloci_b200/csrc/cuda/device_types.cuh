@@ -53,19 +53,31 @@ struct PostingsView {
     const uint32_t* term_plane;  // per term id: head-term plane of the index, kNoValue if the term has none
 };
 
-// ---- head-term planes ----
-// The most frequent terms of the index (df >= anchors / 128, at most kMaxPlanes over all
-// fields) also exist anchor-indexed: one presence bit and the f16 score per anchor of the
-// shard.  The plane path (planes.cu) evaluates them with word-wide bit operations instead
-// of scattering their postings.
-static const uint32_t kMaxPlanes = 96;
+// ---- term planes ----
+// The frequent terms of the index also exist anchor-indexed: one presence bit per anchor of the shard
+// ("plane").  The plane path (planes.cu) evaluates them with word-wide bit operations instead of
+// scattering their postings.  Two classes, by document frequency over the shard's anchors:
+//   head planes  df >= span / 128  (at most kMaxHeadPlanes): bits + the f16 score per anchor
+//   mid planes   df >= span / 1024 (at most kMaxPlanes in total): bits only; the weight of an anchor is found by
+//                binary search in the term's posting list, which only exact evaluations (rare) need
+// Planes are ordered by descending df over all fields; plane ids below n_head are head planes.
+static const uint32_t kMaxHeadPlanes = 96;
+static const uint32_t kMaxPlanes = 2048;
 static const uint32_t kPlaneTileLog2 = 13;   // planes are padded to whole tiles of 2^13 anchors
+struct PlaneInfo {           // posting list of the plane's term (this shard's part of it)
+    const struct Posting* post;
+    uint32_t df;
+    uint32_t pad;
+};
 struct PlaneSetView {
     const uint32_t* bits;    // [n_planes][words]
-    const uint16_t* score;   // [n_planes][words * 32] f16 bits of AnchorScore.score; weight = f16 / 100 (search_field.rs:426)
+    const uint16_t* score;   // [n_head][words * 32] f16 bits of AnchorScore.score; weight = f16 / 100 (search_field.rs:426)
     const float* wmax;       // [n_planes] largest weight of the plane
-    uint32_t n_planes;
+    const PlaneInfo* info;   // [n_planes]
+    const uint32_t* tcount;  // [n_planes][words / 256] anchors of the plane per tile of 2^13 anchors
+    uint32_t n_planes, n_head;
     uint32_t words;          // 32-anchor words per plane (multiple of 2^kPlaneTileLog2 / 32)
+    uint32_t pad;
 };
 
 // Nested "value >= threshold" bitmaps of a boost column (anchors without a value are set in
@@ -79,41 +91,45 @@ struct ColumnLevels {
     float thr[kBoostLevels];  // ascending
 };
 
-static const uint32_t kPartPlaneSlots = 4;
-struct PartPlanes {  // head-term matches of one search part (48 B)
+static const uint32_t kPartPlaneSlots = 8;
+struct PartPlanes {  // plane-term matches of one search part (80 B)
     uint32_t n;      // matches registered (more than kPartPlaneSlots: the part cannot take the plane path)
     uint32_t plane[kPartPlaneSlots];
     float ts[kPartPlaneSlots];  // term score of the match
     uint32_t pad[3];
 };
 
-// Everything the plane path needs to know about one request (160 B).
+// Everything the plane path needs to know about one request.
 static const uint32_t kFastMaxLeaves = 4;
 static const uint32_t kFastMaxK = 64;
-static const uint32_t kFastMaxEntries = 128;  // postings of non-plane terms in one (tile, request) item
+static const uint32_t kFastMaxTerms = 12;      // plane terms of one request, over all its parts
+static const uint32_t kGroupMaxEntries = 256;  // postings of non-plane terms in one (tile group, request) item
 enum FastFlags : uint32_t { kFastOk = 1u, kFastBoost = 2u, kFastUnion1 = 4u };
-struct alignas(16) FastDesc {
+struct alignas(16) FastDesc {  // 176 B
     uint32_t flags, n_leaves, k, fb_fun;
     float fb_param, fb_max_mult;
-    uint32_t fb_n;
-    uint8_t n_planes[kFastMaxLeaves];
+    uint32_t fb_n, n_terms;
     float bound[kFastMaxLeaves];  // bound[n-1]: no anchor with n parts present, all through planes, scores above it (before the boost)
     float ub[kFastMaxLeaves];     // per part: largest score a plane match can contribute
-    float ts[kFastMaxLeaves][kPartPlaneSlots];
-    uint8_t plane[kFastMaxLeaves][kPartPlaneSlots];
     const uint32_t* fb_col;
     const ColumnLevels* fb_lev;
+    float ts[kFastMaxTerms];       // plane terms, grouped by part in part order: term score of the match,
+    uint16_t plane[kFastMaxTerms]; // its plane,
+    uint8_t part[kFastMaxTerms];   // its part
+    uint8_t np[kFastMaxLeaves];    // plane terms per part
+    uint8_t pad[8];
 };
-static_assert(sizeof(FastDesc) == 160, "FastDesc is copied as ten 16-byte words");
+static_assert(sizeof(FastDesc) == 176, "FastDesc layout");
 
-// One (tile, request) item of the plane path: per part, the request's entries (postings of
-// non-plane terms inside the tile) are one contiguous range of the part's sparse tile bucket.
+// One (tile group, request) item of the plane path: per part, the request's entries (postings of non-plane terms
+// inside the group's tiles) are one contiguous range of the part's sparse tile buckets.
 struct alignas(16) FastItem {  // 32 B
     uint32_t q;
+    uint32_t group;
     uint16_t n[kFastMaxLeaves];
     uint32_t begin[kFastMaxLeaves];  // index into the batch's SparseEntry array
-    uint32_t pad;
 };
+static_assert(sizeof(FastItem) == 32, "FastItem layout");
 
 struct SparseEntry {  // 8 B: one posting of a sparse (rarely matched) term, already scored
     uint32_t anchor;

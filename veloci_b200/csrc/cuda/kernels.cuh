@@ -133,11 +133,11 @@ void launch_finalize_programs(cudaStream_t st, const QueryProgram* queries, uint
                               unsigned long long* stat_postings);
 
 // ---- tiles.cu ----
-// Classifies every (tile, request) pair: nothing to do / plane-path item (the request has a
-// FastDesc and at most kFastMaxEntries postings of non-plane terms in the tile, all of them in
-// sparse buckets; evaluated by plane_eval_kernel) / general item (tile_eval_kernel).  Pass 0
-// counts, pass 1 writes the records; plane-path items are grouped per tile, general items
-// form one flat tile-major list with their slice records.
+// Classifies every (tile group, request) pair.  A request with a FastDesc takes the plane path in every group of
+// `group_tiles` consecutive tiles where its non-plane terms have at most kGroupMaxEntries postings, all of them in
+// sparse buckets: one plane-path item per (group, request), evaluated by plane_eval_kernel.  Everything else becomes
+// general items, one per non-empty (tile, request), for tile_eval_kernel.  Pass 0 counts, pass 1 writes the records;
+// plane-path items are grouped per group, general items form one flat tile-major list with their slice records.
 struct ItemScanArgs {
     const QueryProgram* queries;
     uint32_t n_queries;
@@ -151,14 +151,16 @@ struct ItemScanArgs {
     const float* g_score;
     const uint32_t* toff;
     const uint32_t* bucket;
+    const uint32_t* plane_tcount;      // [n_planes][n_tiles] anchors per (plane, tile) (nullptr without planes)
     uint32_t n_tiles;
-    unsigned long long n_items_total;  // n_tiles * n_queries
+    uint32_t group_tiles, n_groups;    // tiles per group (1 when there is no plane path), ceil(n_tiles / group_tiles)
+    unsigned long long n_pairs_total;  // n_groups * n_queries
     unsigned long long* counters;      // [0] general items, [1] general slices (zeroed before each pass)
     ItemRec* items;                    // general items
     SliceRec* slice_recs;              // general slices
-    // plane-path items, per tile: pass 0 accumulates counts in the cursor, pass 1 uses it as cursor (zeroed before each pass)
-    uint32_t* fast_item_cursor;        // [n_tiles]
-    const uint32_t* fast_item_begin;   // [n_tiles + 1] (pass 1)
+    // plane-path items, per group: pass 0 accumulates counts in the cursor, pass 1 uses it as cursor (zeroed before each pass)
+    uint32_t* fast_item_cursor;        // [n_groups]
+    const uint32_t* fast_item_begin;   // [n_groups + 1] (pass 1)
     FastItem* fast_items;
 };
 void launch_item_scan(cudaStream_t st, const ItemScanArgs& a, bool fill);
@@ -206,9 +208,12 @@ size_t tile_kernel_smem(uint32_t tile_log2, uint32_t max_leaves);
 void launch_tile_eval(cudaStream_t st, const TileArgs& a, int n_sms);
 
 // ---- planes.cu ----
-// Index build: presence bits, f16 scores and the largest weight of one head-term plane from its posting list
-// (*bad is set when the list cannot be represented: unsorted anchors or a weight that is not f16 / 100).
-void launch_plane_fill(cudaStream_t st, const Posting* post, uint64_t n, uint32_t* bits_row, uint16_t* score_row, float* wmax_slot, uint32_t* bad, uint32_t anchor_lo);
+// Index build: presence bits, f16 scores (score_row == nullptr: a mid plane, bits only) and the largest weight of one
+// plane from its posting list (*bad is set when the list cannot be represented: unsorted or out-of-range anchors, or
+// a weight that is not f16 / 100).
+void launch_plane_fill(cudaStream_t st, const Posting* post, uint64_t n, uint32_t* bits_row, uint16_t* score_row, float* wmax_slot, uint32_t* bad, uint32_t anchor_lo, uint32_t span);
+// Index build: anchors per (plane, tile of 2^13 anchors).
+void launch_plane_tile_counts(cudaStream_t st, const uint32_t* bits, uint32_t n_planes, uint32_t words, uint32_t* tcount);
 // Index build: the kBoostLevels nested bitmaps of a boost column for the shard's anchors.
 void launch_level_fill(cudaStream_t st, const uint32_t* col, uint32_t col_n, uint32_t anchor_lo, uint32_t span, const float* thr, uint32_t* bits, uint32_t words);
 
@@ -216,31 +221,24 @@ void launch_level_fill(cudaStream_t st, const uint32_t* col, uint32_t col_n, uin
 void launch_build_fast_desc(cudaStream_t st, const QueryProgram* queries, uint32_t n, const uint32_t* leaf_part, const PartPlanes* part_planes, const float* wmax, FastDesc* out);
 
 struct PlaneArgs {
-    const FastItem* items;                // plane-path items, grouped per tile
-    const uint32_t* tile_item_begin;      // [n_tiles + 1]
+    const FastItem* items;                // plane-path items, group-major
+    const uint32_t* group_item_begin;     // [n_groups + 1]
     const FastDesc* fast;
     const SparseEntry* sparse;
     PlaneSetView planes;
-    const ColumnLevels* lev_dev;          // the column whose level bits are staged in shared memory (nullptr: none)
-    ColumnLevels lev_hdr;                 // host copy of *lev_dev
-    uint32_t tile_log2, anchor_lo, anchor_hi;
-    // work unit u = (tile tile_begin + u / chunks_per_tile, chunk u % chunks_per_tile of unit_items items)
-    uint32_t tile_begin, unit_items, chunks_per_tile, n_units;
-    // 0: normal.  1: seed pass -- only anchors without entries inside boost level `seed_level` are evaluated, nothing is
-    // counted: it gives every request a useful threshold for a fraction of a tile's evaluations.  2: the normal pass over
-    // tiles that were seeded (tiles below `seeded_tiles`): the anchors the seed pass evaluated are skipped.
-    uint32_t pass_mode, seed_level, seeded_tiles;
-    uint32_t force_general;  // timing experiments: never take the converged-threshold sweep
+    uint32_t anchor_lo, anchor_hi;
+    uint32_t group_tiles;                 // tiles of 2^13 anchors per item
+    uint32_t group_begin, group_end;      // this launch evaluates the items of groups [group_begin, group_end)
     // per-query state (shared with tile_eval_kernel)
     unsigned long long* heap;
     uint32_t heap_stride;
     unsigned long long* tau;
     uint32_t* lock;
     unsigned long long* num_hits;
-    unsigned long long* work_counter;
-    unsigned long long* stats;  // [0] items, [1] anchors evaluated exactly
+    unsigned long long* work_counter;     // zeroed before the launch
+    unsigned long long* stats;  // [0] items, [1] anchors evaluated exactly, [5] items swept before their threshold converged, [6] items answered from tile counts
 };
-size_t plane_kernel_smem(uint32_t tile_log2, uint32_t n_planes);
+size_t plane_kernel_smem();
 void launch_plane_eval(cudaStream_t st, const PlaneArgs& a, int n_sms);
 
 // Top groups of every facet histogram: block f writes the `top[f]` largest counts of facets[f] (count desc, value id

@@ -36,77 +36,101 @@ static const uint32_t kSurvivorCap = 512;
 static const uint32_t kSliceChunk = 64;     // slice records staged in shared memory at a time
 
 // ---------------------------------------------------------------- item scan
-// One thread per (tile, request), tile-major.  Pass 0 counts the non-empty items and
-// their slices; pass 1 writes them.  A request with a FastDesc takes the plane path in
-// every tile where its non-plane terms have at most kFastMaxEntries postings, all in the
-// parts' sparse tile buckets: those items only record the bucket ranges and are grouped
-// per tile (per-tile cursors).  Everything else becomes a general item with all its
-// slices; blocks reserve general output ranges in index order, so that list stays
-// (nearly) tile-major.
+// One thread per (tile group, request), group-major.  Pass 0 counts the items and their slices; pass 1 writes them.
+// A request with a FastDesc takes the plane path in every group where its non-plane terms have at most
+// kGroupMaxEntries postings, all in the parts' sparse tile buckets (a group's buckets of one part are contiguous):
+// such a pair is one plane-path item that only records the bucket ranges; the items are grouped per group (per-group
+// cursors).  Every other pair becomes one general item per non-empty tile of the group, with all its slices; blocks
+// reserve general output ranges in index order, so that list stays (nearly) tile-major.
+
+// Postings and non-empty slices of request `qp` in tile t.
+__device__ __forceinline__ void tile_totals(const ItemScanArgs& a, const QueryProgram& qp, uint32_t t, uint32_t& all_post, uint32_t& all_slices) {
+    all_post = 0, all_slices = 0;
+    for (uint32_t l = 0; l < qp.n_leaves; ++l) {
+        const PartSlices ps = a.slices[a.leaf_part[qp.leaf_begin + l]];
+        for (uint32_t r = 0; r < ps.n_dense; ++r) {
+            const uint32_t* trow = a.toff + (size_t)a.g_row[ps.m_begin + r] * (a.n_tiles + 1);
+            const uint32_t n = trow[t + 1] - trow[t];
+            all_post += n, all_slices += n ? 1u : 0u;
+        }
+        if (ps.n_match != ps.n_dense) {
+            const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
+            const uint32_t n = brow[t + 1] - brow[t];
+            all_post += n, all_slices += n ? 1u : 0u;
+        }
+    }
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
     __shared__ uint32_t s_warp_items[8], s_warp_slices[8];
     __shared__ unsigned long long s_base_items, s_base_slices;
     const unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t all_slices = 0, all_post = 0, ent_post = 0, t = 0, q = 0;
-    bool plane_hit = false, fastq = false, fast_fits = true;
+    uint32_t g = 0, q = 0, t0 = 0, t1 = 0;
+    bool fast_item = false, general = false;
     FastItem fi;
-    fi.q = 0, fi.pad = 0;
+    fi.q = 0, fi.group = 0;
     for (uint32_t l = 0; l < kFastMaxLeaves; ++l) fi.n[l] = 0, fi.begin[l] = 0;
     QueryProgram qp;
-    qp.active = 0;
-    if (i < a.n_items_total) {
-        t = (uint32_t)(i / a.n_queries), q = (uint32_t)(i % a.n_queries);
+    qp.active = 0, qp.n_leaves = 0;
+    if (i < a.n_pairs_total) {
+        g = (uint32_t)(i / a.n_queries), q = (uint32_t)(i % a.n_queries);
+        t0 = g * a.group_tiles, t1 = min(a.n_tiles, t0 + a.group_tiles);
         qp = a.queries[q];
-        fastq = a.fast != nullptr && (a.fast[q].flags & kFastOk) != 0;
     }
     if (qp.active && qp.n_leaves) {
-        for (uint32_t l = 0; l < qp.n_leaves; ++l) {
-            const PartSlices ps = a.slices[a.leaf_part[qp.leaf_begin + l]];
-            for (uint32_t r = 0; r < ps.n_dense; ++r) {
-                const uint32_t* trow = a.toff + (size_t)a.g_row[ps.m_begin + r] * (a.n_tiles + 1);
-                const uint32_t n = trow[t + 1] - trow[t];
-                all_post += n, all_slices += n ? 1u : 0u;
-                if (fastq) {
+        const bool fastq = a.fast != nullptr && (a.fast[q].flags & kFastOk) != 0;
+        bool fits = fastq, plane_hit = false;
+        if (fastq) {
+            uint32_t ent_post = 0;
+            for (uint32_t l = 0; l < qp.n_leaves; ++l) {
+                const PartSlices ps = a.slices[a.leaf_part[qp.leaf_begin + l]];
+                for (uint32_t r = 0; r < ps.n_dense; ++r) {
+                    const uint32_t* trow = a.toff + (size_t)a.g_row[ps.m_begin + r] * (a.n_tiles + 1);
+                    const uint32_t n = trow[t1] - trow[t0];
                     if (a.g_plane[ps.m_begin + r] != kNoValue) plane_hit = plane_hit || n != 0;
-                    else if (n) fast_fits = false;  // a frequent term without a plane: general path
+                    else if (n) fits = false;  // a frequent term without a plane: general path
+                }
+                if (ps.n_match != ps.n_dense) {
+                    const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
+                    const uint32_t s = brow[t0], n = brow[t1] - s;
+                    ent_post += n;
+                    if (l < kFastMaxLeaves) {
+                        const unsigned long long at = ps.sparse_base + s;
+                        if (at + n > 0xFFFFFFFFull) fits = false;
+                        fi.n[l] = (uint16_t)min(n, 0xFFFFu), fi.begin[l] = (uint32_t)at;
+                    }
                 }
             }
-            if (ps.n_match != ps.n_dense) {
-                const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
-                const uint32_t s = brow[t], n = brow[t + 1] - s;
-                all_post += n, all_slices += n ? 1u : 0u;
-                ent_post += n;
-                if (fastq && l < kFastMaxLeaves) {
-                    const unsigned long long at = ps.sparse_base + s;
-                    if (at + n > 0xFFFFFFFFull) fast_fits = false;
-                    fi.n[l] = (uint16_t)min(n, 0xFFFFu), fi.begin[l] = (uint32_t)at;
-                }
-            }
+            fits = fits && ent_post <= kGroupMaxEntries;
+            fast_item = fits && (plane_hit || ent_post != 0);
         }
+        general = !fits;
     }
-    fast_fits = fastq && fast_fits && ent_post <= kFastMaxEntries;
-    const bool fast_item = fast_fits && (plane_hit || ent_post != 0);
-    const bool general_item = !fast_fits && all_post != 0;
-    const uint32_t n_slices = general_item ? all_slices : 0u;
 
-    // ---- plane-path items: per-tile cursors, one atomic per (warp, tile)
+    // ---- plane-path items: per-group cursors, one atomic per (warp, group)
     {
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, fast_item ? t : 0xFFFFFFFFu);
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, fast_item ? g : 0xFFFFFFFFu);
         const int leader = __ffs((int)peers) - 1;
         uint32_t base_i = 0;
-        if (fast_item && (int)lane == leader) base_i = atomicAdd(a.fast_item_cursor + t, (uint32_t)__popc(peers));
+        if (fast_item && (int)lane == leader) base_i = atomicAdd(a.fast_item_cursor + g, (uint32_t)__popc(peers));
         base_i = __shfl_sync(0xFFFFFFFFu, base_i, leader);
         if (FILL && fast_item) {
-            fi.q = q;
-            a.fast_items[a.fast_item_begin[t] + base_i + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = fi;
+            fi.q = q, fi.group = g;
+            a.fast_items[a.fast_item_begin[g] + base_i + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = fi;
         }
     }
 
-    // ---- general items: block-ordered reservation, exclusive prefix of (items, slices) over the block
-    const uint32_t has = general_item ? 1u : 0u;
-    uint32_t xi = has, xs = n_slices;
+    // ---- general items: one per non-empty tile of the pair; block-ordered reservation, exclusive prefix of (items, slices) over the block
+    uint32_t my_items = 0, my_slices = 0;
+    if (general)
+        for (uint32_t t = t0; t < t1; ++t) {
+            uint32_t np, ns;
+            tile_totals(a, qp, t, np, ns);
+            if (np) my_items += 1, my_slices += ns;
+        }
+    uint32_t xi = my_items, xs = my_slices;
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t yi = __shfl_up_sync(0xFFFFFFFFu, xi, o), ys = __shfl_up_sync(0xFFFFFFFFu, xs, o);
         if ((int)lane >= o) xi += yi, xs += ys;
@@ -124,43 +148,48 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
     }
     if (!FILL) return;
     __syncthreads();
-    if (!has) return;
-    const unsigned long long item_at = s_base_items + wi + xi - has;
-    unsigned long long slice_at = s_base_slices + ws + xs - n_slices;
-    ItemRec rec;
-    rec.q = q, rec.t = t, rec.slice_begin = slice_at, rec.n_slices = n_slices, rec.npost = all_post;
-    a.items[item_at] = rec;
-    uint32_t task_at = 0;
-    for (uint32_t l = 0; l < qp.n_leaves; ++l) {
-        const uint32_t part = a.leaf_part[qp.leaf_begin + l];
-        const PartSlices ps = a.slices[part];
-        for (uint32_t r = 0; r < ps.n_dense; ++r) {
-            const uint32_t mi = ps.m_begin + r;
-            const uint32_t* trow = a.toff + (size_t)a.g_row[mi] * (a.n_tiles + 1);
-            const uint32_t s = trow[t], e = trow[t + 1];
-            if (e == s) continue;
-            SliceRec sr;
-            sr.begin = a.g_begin[mi] + s, sr.n = e - s, sr.term_score = a.g_score[mi], sr.task_begin = task_at;
-            sr.leaf = (uint16_t)l, sr.kind = 0, sr.single = ps.n_match == 1 ? 1 : 0, sr.postings = a.parts[part].postings, sr.pad = 0;
-            task_at += (sr.n + kTaskPostings - 1) / kTaskPostings;
-            a.slice_recs[slice_at++] = sr;
-        }
-        if (ps.n_match != ps.n_dense) {
-            const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
-            const uint32_t s = brow[t], e = brow[t + 1];
-            if (e == s) continue;
-            SliceRec sr;
-            sr.begin = ps.sparse_base + s, sr.n = e - s, sr.term_score = 0.0f, sr.task_begin = task_at;
-            sr.leaf = (uint16_t)l, sr.kind = 1, sr.single = (a.parts[part].flags & kPartListBoost) ? 3 : 0, sr.postings = 0, sr.pad = 0;
-            task_at += (sr.n + kTaskPostings - 1) / kTaskPostings;
-            a.slice_recs[slice_at++] = sr;
+    if (!my_items) return;
+    unsigned long long item_at = s_base_items + wi + xi - my_items;
+    unsigned long long slice_at = s_base_slices + ws + xs - my_slices;
+    for (uint32_t t = t0; t < t1; ++t) {
+        uint32_t all_post, n_slices;
+        tile_totals(a, qp, t, all_post, n_slices);
+        if (!all_post) continue;
+        ItemRec rec;
+        rec.q = q, rec.t = t, rec.slice_begin = slice_at, rec.n_slices = n_slices, rec.npost = all_post;
+        a.items[item_at++] = rec;
+        uint32_t task_at = 0;
+        for (uint32_t l = 0; l < qp.n_leaves; ++l) {
+            const uint32_t part = a.leaf_part[qp.leaf_begin + l];
+            const PartSlices ps = a.slices[part];
+            for (uint32_t r = 0; r < ps.n_dense; ++r) {
+                const uint32_t mi = ps.m_begin + r;
+                const uint32_t* trow = a.toff + (size_t)a.g_row[mi] * (a.n_tiles + 1);
+                const uint32_t s = trow[t], e = trow[t + 1];
+                if (e == s) continue;
+                SliceRec sr;
+                sr.begin = a.g_begin[mi] + s, sr.n = e - s, sr.term_score = a.g_score[mi], sr.task_begin = task_at;
+                sr.leaf = (uint16_t)l, sr.kind = 0, sr.single = ps.n_match == 1 ? 1 : 0, sr.postings = a.parts[part].postings, sr.pad = 0;
+                task_at += (sr.n + kTaskPostings - 1) / kTaskPostings;
+                a.slice_recs[slice_at++] = sr;
+            }
+            if (ps.n_match != ps.n_dense) {
+                const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
+                const uint32_t s = brow[t], e = brow[t + 1];
+                if (e == s) continue;
+                SliceRec sr;
+                sr.begin = ps.sparse_base + s, sr.n = e - s, sr.term_score = 0.0f, sr.task_begin = task_at;
+                sr.leaf = (uint16_t)l, sr.kind = 1, sr.single = (a.parts[part].flags & kPartListBoost) ? 3 : 0, sr.postings = 0, sr.pad = 0;
+                task_at += (sr.n + kTaskPostings - 1) / kTaskPostings;
+                a.slice_recs[slice_at++] = sr;
+            }
         }
     }
 }
 
 void launch_item_scan(cudaStream_t st, const ItemScanArgs& a, bool fill) {
-    if (!a.n_items_total) return;
-    const unsigned blocks = (unsigned)((a.n_items_total + 255) / 256);
+    if (!a.n_pairs_total) return;
+    const unsigned blocks = (unsigned)((a.n_pairs_total + 255) / 256);
     if (fill) item_scan_kernel<true><<<blocks, 256, 0, st>>>(a);
     else item_scan_kernel<false><<<blocks, 256, 0, st>>>(a);
     count_launch();

@@ -340,12 +340,14 @@ struct PostingsDev {
     PostingsView view() const { return PostingsView{post.p, off.p, (uint32_t)n_terms, term_plane.p}; }
 };
 
-struct PlaneSetDev {  // head-term planes of every postings store of the shard
-    uint32_t n_planes = 0, words = 0;
+struct PlaneSetDev {  // term planes of every postings store of the shard (head planes first, then mid planes)
+    uint32_t n_planes = 0, n_head = 0, words = 0;
     DevBuf<uint32_t> bits;
-    DevBuf<uint16_t> score;
+    DevBuf<uint16_t> score;   // head planes only
     DevBuf<float> wmax;
-    PlaneSetView view() const { return PlaneSetView{bits.p, score.p, wmax.p, n_planes, words}; }
+    DevBuf<PlaneInfo> info;
+    DevBuf<uint32_t> tcount;  // [n_planes][tiles]
+    PlaneSetView view() const { return PlaneSetView{bits.p, score.p, wmax.p, info.p, tcount.p, n_planes, n_head, words, 0u}; }
 };
 
 struct CsrDev {  // id -> list<u32>
@@ -693,11 +695,12 @@ struct DeviceIndex {
         boosts.emplace(path, std::move(c));
     }
 
-    // Head-term planes: the terms with df >= span / 128 over all postings stores, at most kMaxPlanes by df.
+    // Term planes: head planes for the terms with df >= span / 128 (at most kMaxHeadPlanes, bits + f16 scores), mid planes
+    // for the terms with df >= span / 1024 (bits only), at most kMaxPlanes in total, by descending df over all stores.
     void build_planes() {
         const uint64_t span = anchor_hi - anchor_lo;
         if ((open_flags & kOpenNoPlanes) || span == 0 || span >= 0xFFFFFFFFull) return;
-        const uint64_t min_df = std::max<uint64_t>(1, span / 128);
+        const uint64_t head_df = std::max<uint64_t>(1, span / 128), mid_df = std::max<uint64_t>(16, span / 1024);
         struct Cand {
             uint64_t df;
             PostingsDev* store;
@@ -708,16 +711,18 @@ struct DeviceIndex {
             PostingsDev& pd = kv.second;
             for (size_t t = 0; t < pd.n_terms; ++t) {
                 const uint64_t df = pd.h_off[t + 1] - pd.h_off[t];
-                if (df >= min_df) cands.push_back(Cand{df, &pd, (uint32_t)t});
+                if (df >= mid_df) cands.push_back(Cand{df, &pd, (uint32_t)t});
             }
         }
         if (cands.empty()) return;
         std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.df > b.df; });
         if (cands.size() > kMaxPlanes) cands.resize(kMaxPlanes);
+        uint32_t n_head = 0;
+        while (n_head < cands.size() && n_head < kMaxHeadPlanes && cands[n_head].df >= head_df) ++n_head;
         const uint32_t n = (uint32_t)cands.size(), words = shard_words();
-        planes.n_planes = n, planes.words = words;
+        planes.n_planes = n, planes.n_head = n_head, planes.words = words;
         planes.bits.alloc((size_t)n * words);
-        planes.score.alloc((size_t)n * words * 32);
+        planes.score.alloc((size_t)std::max<uint32_t>(n_head, 1) * words * 32);
         planes.wmax.alloc(n);
         DevBuf<uint32_t> bad;
         bad.alloc(n);
@@ -725,11 +730,16 @@ struct DeviceIndex {
         VDEV_CUDA(cudaMemset(planes.score.p, 0, planes.score.bytes()));
         VDEV_CUDA(cudaMemset(planes.wmax.p, 0, planes.wmax.bytes()));
         VDEV_CUDA(cudaMemset(bad.p, 0, bad.bytes()));
+        std::vector<PlaneInfo> info(n);
         for (uint32_t p = 0; p < n; ++p) {
             const Cand& c = cands[p];
-            launch_plane_fill(nullptr, c.store->post.p + c.store->h_off[c.term], c.df, planes.bits.p + (size_t)p * words, planes.score.p + (size_t)p * words * 32, planes.wmax.p + p,
-                              bad.p + p, (uint32_t)anchor_lo);
+            info[p] = PlaneInfo{c.store->post.p + c.store->h_off[c.term], (uint32_t)c.df, 0u};
+            launch_plane_fill(nullptr, info[p].post, c.df, planes.bits.p + (size_t)p * words, p < n_head ? planes.score.p + (size_t)p * words * 32 : nullptr, planes.wmax.p + p, bad.p + p,
+                              (uint32_t)anchor_lo, (uint32_t)span);
         }
+        planes.info.upload(info);
+        planes.tcount.alloc((size_t)n * (words >> (kPlaneTileLog2 - 5)));
+        launch_plane_tile_counts(nullptr, planes.bits.p, n, words, planes.tcount.p);
         std::vector<uint32_t> h_bad(n);
         VDEV_CUDA(cudaMemcpy(h_bad.data(), bad.p, n * 4, cudaMemcpyDeviceToHost));
         std::map<PostingsDev*, std::vector<uint32_t>> maps;
@@ -750,7 +760,7 @@ struct DeviceIndex {
             for (size_t t = 0; t < pd.n_terms; ++t)
                 if (it == maps.end() || it->second[t] == kNoValue) max_nonplane_list = std::max<uint64_t>(max_nonplane_list, pd.h_off[t + 1] - pd.h_off[t]);
         }
-        device_bytes += planes.bits.bytes() + planes.score.bytes() + planes.wmax.bytes();
+        device_bytes += planes.bits.bytes() + planes.score.bytes() + planes.wmax.bytes() + planes.info.bytes() + planes.tcount.bytes();
     }
 
     void build_phrase(const std::string& path, const vfmt::PhrasePairView& v) {

@@ -135,12 +135,10 @@ struct Batch {
     DevBuf<uint32_t> d_facet_top, d_facet_hist, d_facet_ids, d_facet_counts, d_facet_n;
     uint32_t n_facets = 0, facet_stride = 1;
     std::vector<uint32_t> h_facet_ids, h_facet_counts, h_facet_n;
-    const ColumnLevels* lev_dev = nullptr;  // boost column whose level bits the plane kernel stages in shared memory
-    ColumnLevels lev_hdr{};
     uint64_t stat_fast_items = 0, stat_general_items = 0, stat_plane_evaluated = 0;
     // between execute_begin and execute_finish
     unsigned long long pending_items = 0;
-    uint32_t pending_fast_items = 0, seeded_tiles = 0, seed_level = 5;
+    uint32_t pending_fast_items = 0;
     bool begun = false;
     // device: per-request state and results
     DevBuf<unsigned long long> d_heap, d_tau, d_num_hits;
@@ -150,7 +148,7 @@ struct Batch {
     uint64_t emit_capacity = 0;
     uint32_t stride = 1;
     // geometry
-    uint32_t tile_log2 = 13, n_tiles = 0;
+    uint32_t tile_log2 = 13, n_tiles = 0, group_tiles = 1, n_groups = 0;
     // host results
     bool matched = false, executed = false, fetched = false;
     std::vector<uint64_t> h_keys, h_hits;
@@ -391,8 +389,8 @@ struct Batch {
         const uint32_t L = std::max<uint32_t>(1, plan.max_leaves);
         tile_log2 = 13;
         while (tile_log2 > 10 && ((size_t)L << tile_log2) * 4 > 48 * 1024) --tile_log2;
-        // plane path: requests that are flat `or`s of few parts run on head-term planes, with plane-sized tiles
-        use_planes = mode == kRequests && ix->planes.n_planes > 0 && plane_kernel_smem(kPlaneTileLog2, ix->planes.n_planes) != 0;
+        // plane path: requests that are flat `or`s of few parts run on term planes, with plane-sized tiles grouped into items
+        use_planes = mode == kRequests && ix->planes.n_planes > 0;
         if (use_planes) {
             uint32_t eligible = 0;
             for (auto& qp : plan.programs)
@@ -400,18 +398,16 @@ struct Batch {
             if (eligible * 2 >= n && eligible > 0 && tile_kernel_smem(kPlaneTileLog2, L) != 0) tile_log2 = kPlaneTileLog2;
             else use_planes = false;
         }
-        lev_dev = nullptr;
-        if (use_planes)
-            for (auto& bs : plan.boosts)
-                if (bs.levels && !lev_dev)
-                    for (auto& kv : ix->boosts)
-                        if (kv.second.level_hdr.p == bs.levels) lev_dev = bs.levels, lev_hdr = kv.second.h_levels;
         if (const char* env = probe_env("VELOCI_TILE_LOG2")) {
             int v = atoi(env);
             if (v >= 8 && v <= 13 && tile_kernel_smem((uint32_t)v, L)) tile_log2 = (uint32_t)v;
         }
         const uint64_t span = ix->anchor_hi - ix->anchor_lo;
         n_tiles = (uint32_t)((span + (1ull << tile_log2) - 1) >> tile_log2);
+        // plane-path items span `group_tiles` tiles (128 Ki anchors); without a plane path every tile is its own group
+        group_tiles = use_planes ? 16u : 1u;
+        if (const char* env = probe_env("VELOCI_GROUP_TILES")) group_tiles = use_planes ? (uint32_t)std::min(32, std::max(1, atoi(env))) : 1u;
+        n_groups = (n_tiles + group_tiles - 1) / group_tiles;
         stride = std::max<uint32_t>(1, plan.max_k);
 
         d_parts.upload(plan.parts);
@@ -701,29 +697,16 @@ struct Batch {
         finish_sync();
     }
 
-    // PlaneArgs of one stage of the plane evaluation: tiles [t0, t1)
-    PlaneArgs plane_stage_args(int stage, uint32_t t0, uint32_t t1) {
+    // PlaneArgs of one stage of the plane evaluation: the items of tile groups [g0, g1)
+    PlaneArgs plane_stage_args(int stage, uint32_t g0, uint32_t g1) {
         PlaneArgs a;
         memset(&a, 0, sizeof a);
-        a.items = d_fast_items.p, a.tile_item_begin = d_fast_item_begin.p, a.fast = d_fast.p;
+        a.items = d_fast_items.p, a.group_item_begin = d_fast_item_begin.p, a.fast = d_fast.p;
         a.sparse = d_sparse.p, a.planes = ix->planes.view();
-        a.lev_dev = lev_dev, a.lev_hdr = lev_hdr;
-        a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
+        a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
+        a.group_tiles = group_tiles, a.group_begin = g0, a.group_end = g1;
         a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
         a.stats = d_counters.p + 8;
-        const uint32_t want_units = (uint32_t)n_sms * 2;
-        // items of one tile a CTA takes at a time: at most 4096 (the tile's bits are staged once per unit), and small enough for
-        // ~24 units per SM (tail balance on small shards)
-        uint32_t unit = stage == 2 ? std::max<uint32_t>(256, (uint32_t)(((uint64_t)n * (t1 - t0)) / ((uint64_t)n_sms * 24) + 1))
-                                   : std::max<uint32_t>(16, ((uint64_t)n * (t1 - t0) + want_units - 1) / want_units);
-        unit = std::min<uint32_t>(unit, 4096u);
-        if (const char* env = probe_env("VELOCI_UNIT_ITEMS"))  // experiments: items per unit of the bulk pass, as given
-            if (stage == 2) unit = (uint32_t)std::min(4096, std::max(16, atoi(env)));
-        unit = (unit + 15u) & ~15u;
-        a.tile_begin = t0, a.unit_items = unit;
-        a.force_general = probe_env("VELOCI_FORCE_GENERAL_SWEEP") ? 1u : 0u;
-        a.chunks_per_tile = (n + unit - 1) / unit;
-        a.n_units = (t1 - t0) * a.chunks_per_tile;
         a.work_counter = d_counters.p + 10 + stage;
         return a;
     }
@@ -796,7 +779,7 @@ struct Batch {
             VDEV_CUDA(cudaEventRecord(ev[1], stream));
             VDEV_CUDA(cudaEventRecord(ev[2], stream));
         }
-        // non-empty (tile, request) items and their slices: plane-path items grouped per tile, general items tile-major
+        // (tile group, request) pairs: plane-path items grouped per group, general items (one per non-empty tile) tile-major
         unsigned long long n_items = 0;
         uint32_t n_fast_items = 0;
         const bool planes_on = use_planes && mode == kRequests;
@@ -805,20 +788,19 @@ struct Batch {
             memset(&sc, 0, sizeof sc);
             sc.queries = d_programs.p, sc.n_queries = n, sc.leaf_part = d_leaf_part.p, sc.slices = d_slices.p, sc.parts = d_parts.p;
             sc.g_row = d_g_row.p, sc.g_begin = d_g_begin.p, sc.g_score = d_g_score.p, sc.toff = d_toff.p, sc.bucket = d_bucket.p;
-            sc.n_tiles = n_tiles, sc.n_items_total = (unsigned long long)n_tiles * n, sc.counters = d_counters.p + 5, sc.items = nullptr, sc.slice_recs = nullptr;
-            if (planes_on) {
-                d_fast_item_cursor.reserve(n_tiles + 1), d_fast_item_begin.reserve(n_tiles + 2);
-                sc.fast = d_fast.p, sc.g_plane = d_g_plane.p;
-                sc.fast_item_cursor = d_fast_item_cursor.p, sc.fast_item_begin = d_fast_item_begin.p;
-                VDEV_CUDA(cudaMemsetAsync(d_fast_item_cursor.p, 0, d_fast_item_cursor.bytes(), stream));
-            }
+            sc.n_tiles = n_tiles, sc.group_tiles = group_tiles, sc.n_groups = n_groups, sc.n_pairs_total = (unsigned long long)n_groups * n;
+            sc.counters = d_counters.p + 5, sc.items = nullptr, sc.slice_recs = nullptr;
+            d_fast_item_cursor.reserve(n_groups + 1), d_fast_item_begin.reserve(n_groups + 2);
+            sc.fast_item_cursor = d_fast_item_cursor.p, sc.fast_item_begin = d_fast_item_begin.p;
+            if (planes_on) sc.fast = d_fast.p, sc.g_plane = d_g_plane.p, sc.plane_tcount = ix->planes.tcount.p;
+            VDEV_CUDA(cudaMemsetAsync(d_fast_item_cursor.p, 0, d_fast_item_cursor.bytes(), stream));
             VDEV_CUDA(cudaMemsetAsync(d_counters.p + 5, 0, 16, stream));
             timed("item_scan", [&] { launch_item_scan(stream, sc, false); });
             unsigned long long counts[2];
             VDEV_CUDA(cudaMemcpyAsync(counts, d_counters.p + 5, 16, cudaMemcpyDeviceToHost, stream));
             if (planes_on) {
-                timed("scan_u32", [&] { launch_scan_u32(stream, d_fast_item_cursor.p, d_fast_item_begin.p, n_tiles); });
-                VDEV_CUDA(cudaMemcpyAsync(&n_fast_items, d_fast_item_begin.p + n_tiles, 4, cudaMemcpyDeviceToHost, stream));
+                timed("scan_u32", [&] { launch_scan_u32(stream, d_fast_item_cursor.p, d_fast_item_begin.p, n_groups); });
+                VDEV_CUDA(cudaMemcpyAsync(&n_fast_items, d_fast_item_begin.p + n_groups, 4, cudaMemcpyDeviceToHost, stream));
                 d2h_bytes += 4;
             }
             VDEV_CUDA(cudaStreamSynchronize(stream));
@@ -830,8 +812,8 @@ struct Batch {
             if (planes_on) {
                 d_fast_items.reserve(std::max<size_t>(n_fast_items, 1));
                 sc.fast_items = d_fast_items.p;
-                VDEV_CUDA(cudaMemsetAsync(d_fast_item_cursor.p, 0, d_fast_item_cursor.bytes(), stream));
             }
+            VDEV_CUDA(cudaMemsetAsync(d_fast_item_cursor.p, 0, d_fast_item_cursor.bytes(), stream));
             VDEV_CUDA(cudaMemsetAsync(d_counters.p + 5, 0, 16, stream));
             timed("item_scan", [&] { launch_item_scan(stream, sc, true); });
         }
@@ -842,26 +824,10 @@ struct Batch {
         VDEV_CUDA(cudaMemsetAsync(d_num_hits.p, 0, d_num_hits.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_lock.p, 0, d_lock.bytes(), stream));
         if (n_facets) VDEV_CUDA(cudaMemsetAsync(d_facet_hist.p, 0, d_facet_hist.bytes(), stream));
-        // ---- phase 3: plane evaluation.  Tile 0 first, its requests spread over all SMs, then a few more tiles: the
-        // requests' thresholds are then close to final when the bulk of the tiles runs and prunes against them.
+        // ---- phase 3: plane evaluation.  The first tile group of every request before the rest: afterwards the requests'
+        // thresholds are worth sharing between anchor-range shards (and the other groups prune against them from the start).
         pending_items = n_items, pending_fast_items = n_fast_items;
-        if (planes_on && n_fast_items) {
-            // Seed pass over the first tiles: only the anchors in the top 1/64 of the boost column are evaluated (and nothing
-            // is counted), which gives every request a threshold close to its final one for a fraction of a tile's work.
-            // Without a boost column in the batch the first tile runs in full instead.
-            uint32_t want_tiles = 8;
-            seed_level = 5;
-            if (const char* env = probe_env("VELOCI_SEED_TILES")) want_tiles = (uint32_t)std::max(0, atoi(env));
-            if (const char* env = probe_env("VELOCI_SEED_LEVEL")) seed_level = (uint32_t)std::min(15, std::max(1, atoi(env)));
-            seeded_tiles = lev_dev ? std::min<uint32_t>(want_tiles, n_tiles) : 0;
-            if (seeded_tiles) {
-                PlaneArgs seed = plane_stage_args(0, 0, seeded_tiles);
-                seed.pass_mode = 1, seed.seed_level = seed_level;
-                timed("plane_eval_seed", [&] { launch_plane_eval(stream, seed, n_sms); });
-            } else {
-                timed("plane_eval", [&] { launch_plane_eval(stream, plane_stage_args(0, 0, std::min<uint32_t>(1, n_tiles)), n_sms); });
-            }
-        }
+        if (planes_on && n_fast_items) timed("plane_eval_first", [&] { launch_plane_eval(stream, plane_stage_args(0, 0, std::min<uint32_t>(1, n_groups)), n_sms); });
         if (sync_at_end) {
             VDEV_CUDA(cudaStreamSynchronize(stream));
             VDEV_CUDA(cudaGetLastError());
@@ -876,17 +842,7 @@ struct Batch {
         begun = false;
         const unsigned long long n_items = pending_items;
         const bool planes_on = use_planes && mode == kRequests;
-        if (planes_on && pending_fast_items) {
-            // the normal pass: every tile (the seeded ones skip what the seed pass evaluated), or the tiles after the first
-            const uint32_t first = seeded_tiles ? 0u : std::min<uint32_t>(1, n_tiles);
-            uint32_t last = n_tiles;
-            if (const char* env = probe_env("VELOCI_TILE_LIMIT")) last = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, atoi(env)));  // timing experiments only: wrong results
-            if (last > first) {
-                PlaneArgs rest = plane_stage_args(2, first, last);
-                rest.pass_mode = seeded_tiles ? 2 : 0, rest.seed_level = seed_level, rest.seeded_tiles = seeded_tiles;
-                timed("plane_eval", [&] { launch_plane_eval(stream, rest, n_sms); });
-            }
-        }
+        if (planes_on && pending_fast_items && n_groups > 1) timed("plane_eval", [&] { launch_plane_eval(stream, plane_stage_args(2, 1, n_groups), n_sms); });
         VDEV_CUDA(cudaEventRecord(ev[4], stream));
         // ---- phase 4: tile evaluation of the general items
         {
