@@ -58,7 +58,7 @@ struct PostingsView {
 // ("plane").  The plane path (planes.cu) evaluates them with word-wide bit operations instead of
 // scattering their postings.  Two classes, by document frequency over the shard's anchors:
 //   head planes  df >= span / 128  (at most kMaxHeadPlanes): bits + the f16 score per anchor
-//   mid planes   df >= span / 1024 (at most kMaxPlanes in total): bits only; the weight of an anchor is found by
+//   mid planes   df >= span / 4096 (at most kMaxPlanes in total): bits only; the weight of an anchor is found by
 //                binary search in the term's posting list, which only exact evaluations (rare) need
 // Planes are ordered by descending df over all fields; plane ids below n_head are head planes.
 static const uint32_t kMaxHeadPlanes = 96;
@@ -75,10 +75,13 @@ struct PlaneSetView {
     const float* wmax;       // [n_planes] largest weight of the plane
     const PlaneInfo* info;   // [n_planes]
     const uint32_t* tcount;  // [n_planes][words / 256] anchors of the plane per tile of 2^13 anchors
+    const uint32_t* tprefix; // [n_planes][words / 256 + 1] its exclusive prefix sums: the plane term's posting offset at every tile
+                             // boundary (a plane's bits and its term's postings of the shard correspond one to one)
     uint32_t n_planes, n_head;
     uint32_t words;          // 32-anchor words per plane (multiple of 2^kPlaneTileLog2 / 32)
     uint32_t pad;
 };
+static const uint32_t kPlaneRow = 0xFFFFFFFEu;  // g_row of a matched plane term: its tile offsets are the plane's tprefix row
 
 // Nested "value >= threshold" bitmaps of a boost column (anchors without a value are set in
 // every level): lets the plane path restrict the exact evaluation to anchors whose boost
@@ -103,7 +106,7 @@ struct PartPlanes {  // plane-term matches of one search part (80 B)
 static const uint32_t kFastMaxLeaves = 4;
 static const uint32_t kFastMaxK = 64;
 static const uint32_t kFastMaxTerms = 12;      // plane terms of one request, over all its parts
-static const uint32_t kGroupMaxEntries = 256;  // postings of non-plane terms in one (tile group, request) item
+static const uint32_t kGroupMaxEntries = 512;  // postings of non-plane terms in one (tile group, request) item
 enum FastFlags : uint32_t { kFastOk = 1u, kFastBoost = 2u, kFastUnion1 = 4u };
 struct alignas(16) FastDesc {  // 176 B
     uint32_t flags, n_leaves, k, fb_fun;

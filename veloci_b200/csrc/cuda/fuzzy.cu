@@ -451,8 +451,12 @@ __global__ void score_scatter_kernel(ScoreScatterArgs a) {
     uint32_t pos, row = kNoValue;
     if (dense) {
         pos = seg + atomicAdd(&a.dense_cursor[r.part], 1u);
-        row = atomicAdd(a.n_dense_rows, 1u);
-        if (row < a.dense_row_capacity) a.row_match[row] = pos;
+        if (plane != kNoValue) {
+            row = kPlaneRow;  // its tile offsets are the plane's tprefix row (index build): nothing to compute per batch
+        } else {
+            row = atomicAdd(a.n_dense_rows, 1u);
+            if (row < a.dense_row_capacity) a.row_match[row] = pos;
+        }
     } else {
         pos = seg + cnt - 1u - atomicAdd(&a.sparse_cursor[r.part], 1u);
     }

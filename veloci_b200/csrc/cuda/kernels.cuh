@@ -151,7 +151,7 @@ struct ItemScanArgs {
     const float* g_score;
     const uint32_t* toff;
     const uint32_t* bucket;
-    const uint32_t* plane_tcount;      // [n_planes][n_tiles] anchors per (plane, tile) (nullptr without planes)
+    const uint32_t* plane_tprefix;     // [n_planes][n_tiles + 1] tile offsets of the plane terms' postings (nullptr without planes)
     uint32_t n_tiles;
     uint32_t group_tiles, n_groups;    // tiles per group (1 when there is no plane path), ceil(n_tiles / group_tiles)
     unsigned long long n_pairs_total;  // n_groups * n_queries
@@ -184,6 +184,8 @@ struct TileArgs {
     const uint32_t* g_row;
     const uint32_t* g_df;
     const uint32_t* toff;
+    const uint32_t* g_plane;        // per grouped match: plane or kNoValue (nullptr: no planes in this batch)
+    const uint32_t* plane_tprefix;  // tile offsets of the plane terms
     const uint32_t* bucket;
     const SparseEntry* sparse;
     // geometry
@@ -213,7 +215,7 @@ void launch_tile_eval(cudaStream_t st, const TileArgs& a, int n_sms);
 // a weight that is not f16 / 100).
 void launch_plane_fill(cudaStream_t st, const Posting* post, uint64_t n, uint32_t* bits_row, uint16_t* score_row, float* wmax_slot, uint32_t* bad, uint32_t anchor_lo, uint32_t span);
 // Index build: anchors per (plane, tile of 2^13 anchors).
-void launch_plane_tile_counts(cudaStream_t st, const uint32_t* bits, uint32_t n_planes, uint32_t words, uint32_t* tcount);
+void launch_plane_tile_counts(cudaStream_t st, const uint32_t* bits, uint32_t n_planes, uint32_t words, uint32_t* tcount, uint32_t* tprefix);
 // Index build: the kBoostLevels nested bitmaps of a boost column for the shard's anchors.
 void launch_level_fill(cudaStream_t st, const uint32_t* col, uint32_t col_n, uint32_t anchor_lo, uint32_t span, const float* thr, uint32_t* bits, uint32_t words);
 

@@ -34,7 +34,7 @@ static const int kPlaneThreads = 256;
 static const int kPlaneWarps = kPlaneThreads / 32;
 static const uint32_t kQueueCap = 64;      // pending candidates of a warp: evaluated 32 at a time, one anchor per lane
 static const uint32_t kMergeGroup = 8;     // keys of one request merged into its top-k under one lock round trip
-static const uint32_t kHashSlots = 512;    // >= 2 * kGroupMaxEntries
+static const uint32_t kHashSlots = 1024;   // >= 2 * kGroupMaxEntries
 static const uint32_t kHashEmpty = 0xFFFFFFFFu;
 static const uint32_t kPartShift = 20;     // entry code = anchor index in the group | part << 20
 static const uint32_t kItemBatch = 4;      // items a warp takes from the work counter at a time
@@ -50,10 +50,10 @@ struct alignas(16) WarpScratch {
     float cand_e[kFastMaxLeaves][kQueueCap];  // per part: largest entry score of the anchor (0: none)
     unsigned long long merge[kFastMaxK + kMergeGroup];  // a request's top-k plus the keys merged into it in one go
     const uint32_t* term_bits[kFastMaxTerms];  // the current item's plane rows, at the group's first word
-    uint32_t term_part[kFastMaxTerms];
-    // state of the item being processed (warp-uniform)
-    float tau_score;                       // score of the request's k-th best so far when pruning is possible, else 0
-    int lev[kFastMaxLeaves];               // per count of present parts: -2 no candidates, -1 every anchor, else boost level
+    uint32_t term_part[kFastMaxTerms + 4];     // (+ 4: the entry pass reads parts four at a time)
+    float term_ub[kFastMaxTerms + 4];          // largest score the term can give its part (term score x largest weight of its plane)
+    int term_lev[kFastMaxTerms + 4];           // boost level an anchor whose part takes this term must be inside (-1: any, -2: it cannot matter)
+    int count_lev[kFastMaxLeaves];             // ... an anchor with exactly n + 1 parts present must be inside
     // which (boost function, param, column) mult[] was computed for
     uint32_t mult_fun;
     float mult_param;
@@ -114,10 +114,25 @@ __global__ void plane_tile_count_kernel(const uint32_t* __restrict__ bits, uint3
     if (lane == 0) tcount[wid] = c;
 }
 
-void launch_plane_tile_counts(cudaStream_t st, const uint32_t* bits, uint32_t n_planes, uint32_t words, uint32_t* tcount) {
-    const uint64_t warps = (uint64_t)n_planes * (words >> (kPlaneTileLog2 - 5));
+// One thread per plane: exclusive prefix sums of its tile counts.
+__global__ void plane_tile_prefix_kernel(const uint32_t* __restrict__ tcount, uint32_t n_planes, uint32_t tiles, uint32_t* __restrict__ tprefix) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_planes) return;
+    uint32_t acc = 0;
+    for (uint32_t t = 0; t < tiles; ++t) {
+        tprefix[(size_t)p * (tiles + 1) + t] = acc;
+        acc += tcount[(size_t)p * tiles + t];
+    }
+    tprefix[(size_t)p * (tiles + 1) + tiles] = acc;
+}
+
+void launch_plane_tile_counts(cudaStream_t st, const uint32_t* bits, uint32_t n_planes, uint32_t words, uint32_t* tcount, uint32_t* tprefix) {
+    const uint32_t tiles = words >> (kPlaneTileLog2 - 5);
+    const uint64_t warps = (uint64_t)n_planes * tiles;
     if (!warps) return;
     plane_tile_count_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(bits, n_planes, words, tcount);
+    count_launch();
+    plane_tile_prefix_kernel<<<(n_planes + 63) / 64, 64, 0, st>>>(tcount, n_planes, tiles, tprefix);
     count_launch();
 }
 
@@ -237,31 +252,64 @@ __device__ __forceinline__ int deepest_level(const WarpScratch& S, float B, floa
     return lo;
 }
 
-// Which anchors still have to be evaluated, per number of parts present (see the file comment): lane n - 1 decides
-// for n parts present.  `tau` is the request's current k-th best key (0: fewer than k hits).
-__device__ __forceinline__ void compute_levels(WarpScratch& S, const FastDesc* __restrict__ D, uint32_t flags, uint32_t n_leaves, unsigned long long tau, uint32_t lane) {
-    float tau_score = 0.0f;
+// What the sweep needs to know about a request's threshold (warp-uniform).  A sweep anchor has no entries, so only parts
+// with plane terms can be present in it; with P such parts its score is at most
+// (sum over present parts of the strongest present term's bound) * n^2 * boost multiplier, n <= P.  Hence, against the
+// current k-th best:
+//   term_lev[t]  boost level an anchor must be inside when term t is the strongest term of its part, even with every
+//                other part at its best (-1: any anchor, -2: such an anchor cannot matter) -- a fuzzy neighbour next to
+//                the exact term only matters deep inside the boost column, if at all
+//   allow        bit t: term_lev[t] != -2
+//   optional     bit l: part l may be absent from an anchor that still matters (always set for parts without plane terms)
+struct Prune {
+    float tau_score;   // score of the request's k-th best so far when pruning is possible, else 0
+    uint32_t allow, optional;
+    bool possible;     // some sweep anchor may still matter
+    bool by_count;     // some part with plane terms may be absent: anchors are also held against the bound of their part count (count_lev)
+};
+
+// Static (per item) inputs of the pruning state: lane t holds term t's bound, lane l part l's `opt_need`.
+struct PruneInputs {
+    float bound;       // lane < nt: best bound (before the multiplier) of an anchor whose part takes this term
+    float opt_need;    // lane < 4: best bound of an anchor without this part, times the largest multiplier
+    float count_bound; // lane < 4: best bound (before the multiplier) of an anchor with exactly lane + 1 parts present
+    float max_mult;    // largest boost multiplier (1 without a boost)
+    uint32_t part_terms[kFastMaxLeaves];  // per part: mask of its terms
+    uint32_t nt;
+};
+
+__device__ __forceinline__ Prune compute_prune(WarpScratch& S, const PruneInputs& in, uint32_t flags, unsigned long long tau, uint32_t lane) {
+    Prune p;
+    p.tau_score = 0.0f;
     if (tau != 0) {
         const float ts = vbit::key_score((uint32_t)(tau >> 32));
-        if (ts > 1e-30f) tau_score = ts;
+        if (ts > 1e-30f) p.tau_score = ts;
+    }
+    int lv = -1;
+    if (lane < in.nt && p.tau_score > 0.0f) {
+        if (in.bound * in.max_mult < p.tau_score) lv = -2;
+        else if (flags & kFastBoost) lv = deepest_level(S, in.bound, p.tau_score);
+    }
+    int cl = -1;
+    if (lane < kFastMaxLeaves && p.tau_score > 0.0f) {
+        if (in.count_bound * in.max_mult < p.tau_score) cl = -2;
+        else if (flags & kFastBoost) cl = deepest_level(S, in.count_bound, p.tau_score);
     }
     __syncwarp();
-    if (lane < kFastMaxLeaves) {
-        int lev = -1;
-        if (lane >= n_leaves) lev = -2;
-        else if (tau_score > 0.0f) {
-            const float B = D->bound[lane];
-            if (flags & kFastBoost) {
-                if (B * D->fb_max_mult * 1.00001f < tau_score) lev = -2;
-                else lev = deepest_level(S, B, tau_score);
-            } else if (B * 1.00001f < tau_score) {
-                lev = -2;
-            }
+    if (lane < in.nt) S.term_lev[lane] = lv;
+    if (lane < kFastMaxLeaves) S.count_lev[lane] = cl;
+    p.allow = __ballot_sync(0xFFFFFFFFu, lane < in.nt && lv != -2);
+    p.optional = __ballot_sync(0xFFFFFFFFu, lane < kFastMaxLeaves && (in.part_terms[lane & 3u] == 0u || in.opt_need >= p.tau_score));
+    p.possible = p.allow != 0u;
+    p.by_count = false;
+#pragma unroll
+    for (uint32_t l = 0; l < kFastMaxLeaves; ++l)
+        if (in.part_terms[l] != 0u) {
+            if ((p.optional >> l) & 1u) p.by_count = p.tau_score > 0.0f;
+            else if ((p.allow & in.part_terms[l]) == 0u) p.possible = false;  // a part that must be there, and none of its terms can
         }
-        S.lev[lane] = lev;
-    }
-    if (lane == 0) S.tau_score = tau_score;
     __syncwarp();
+    return p;
 }
 
 // Merges the order keys of the lanes in `group` (at most kMergeGroup, all of request q, each above the threshold it was
@@ -297,7 +345,7 @@ __device__ __noinline__ void merge_group(const CtaContext* C, WarpScratch* Sp, u
     __syncwarp();
 }
 
-__device__ __forceinline__ uint32_t hash_slot(uint32_t code) { return (code * 0x9E3779B1u) >> 23; }  // 9 bits: kHashSlots
+__device__ __forceinline__ uint32_t hash_slot(uint32_t code) { return (code * 0x9E3779B1u) >> 22; }  // 10 bits: kHashSlots
 
 // Files `key` under `code` (keeping the maximum); true when this call created the code's slot.
 __device__ __forceinline__ bool hash_insert(WarpScratch& S, uint32_t code, uint32_t key) {
@@ -324,15 +372,19 @@ __device__ __forceinline__ uint32_t hash_lookup(const WarpScratch& S, uint32_t c
     }
 }
 
-// Weight of `anchor` in the posting list of a mid plane's term (the anchor is in the list: its plane bit is set).
-__device__ __forceinline__ float posting_weight(const PlaneInfo pi, uint32_t anchor) {
-    uint32_t lo = 0, hi = pi.df;
+// Weight of `anchor` in the posting list of a mid plane's term (the anchor is in the list: its plane bit is set).  The
+// plane's tile prefix row narrows the search to the postings of the anchor's tile.
+__device__ __forceinline__ float posting_weight(const PlaneSetView& P, uint32_t plane, uint32_t rel, uint32_t anchor) {
+    const uint32_t tiles = P.words >> (kPlaneTileLog2 - 5), t = rel >> kPlaneTileLog2;
+    const uint32_t* row = P.tprefix + (size_t)plane * (tiles + 1) + t;
+    uint32_t lo = __ldg(row), hi = __ldg(row + 1);
+    const Posting* post = P.info[plane].post;
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(&pi.post[mid].anchor) < anchor) lo = mid + 1;
+        if (__ldg(&post[mid].anchor) < anchor) lo = mid + 1;
         else hi = mid;
     }
-    return __ldg(&pi.post[lo].weight);
+    return __ldg(&post[lo].weight);
 }
 
 // Exact score of candidate `c` of the warp's list: its order key.
@@ -356,7 +408,7 @@ __device__ __forceinline__ unsigned long long eval_candidate(const CtaContext& C
                     const unsigned short h = __ldg(C.planes.score + (size_t)p * ((size_t)C.planes.words * 32u) + rel);
                     wgt = __fdiv_rn(__half2float(__ushort_as_half(h)), 100.0f);  // el.score.to_f32() / 100.0 (search_field.rs:426)
                 } else {
-                    wgt = posting_weight(C.planes.info[p], anchor);  // the same value, kept in the posting (checked at index build)
+                    wgt = posting_weight(C.planes, p, rel, anchor);  // the same value, kept in the posting (checked at index build)
                 }
                 v = fmaxf(v, D->ts[t] * wgt);
             }
@@ -494,8 +546,28 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
             if (lane < nt) {
                 S.term_bits[lane] = a.planes.bits + (size_t)D->plane[lane] * words + w0;
                 S.term_part[lane] = D->part[lane];
+                S.term_ub[lane] = D->ts[lane] * __ldg(a.planes.wmax + D->plane[lane]) * 1.00001f;
             }
-            compute_levels(S, D, flags, L, tau, lane);
+            __syncwarp();
+            PruneInputs pin;
+            {
+                // P parts have plane terms; a sweep anchor with n of them present scores at most (sum of their bounds) * n^2
+                const float u0 = D->ub[0], u1 = D->ub[1], u2 = D->ub[2], u3 = D->ub[3];
+                const uint32_t P = (D->np[0] != 0) + (D->np[1] != 0) + (D->np[2] != 0) + (D->np[3] != 0);
+                const float sum_all = u0 + u1 + u2 + u3;
+                const float f_all = L == 1 ? 1.0f : (float)(P * P), f_less = L == 1 ? 1.0f : (float)((P - 1u) * (P - 1u));
+                pin.nt = nt;
+                pin.max_mult = (flags & kFastBoost) ? D->fb_max_mult * 1.00001f : 1.0f;
+                const uint32_t my_part = lane < nt ? S.term_part[lane] : 0u;
+                const float my_best = my_part == 0 ? u0 : my_part == 1 ? u1 : my_part == 2 ? u2 : u3;
+                pin.bound = lane < nt ? (sum_all - my_best + S.term_ub[lane]) * f_all * 1.0001f : 0.0f;
+                const float mine = (lane & 3u) == 0 ? u0 : (lane & 3u) == 1 ? u1 : (lane & 3u) == 2 ? u2 : u3;
+                pin.opt_need = (sum_all - mine) * f_less * pin.max_mult * 1.0001f;
+                pin.count_bound = D->bound[lane & 3u];  // (0 beyond the request's parts: such a count does not occur)
+#pragma unroll
+                for (uint32_t l = 0; l < kFastMaxLeaves; ++l) pin.part_terms[l] = __ballot_sync(0xFFFFFFFFu, lane < nt && my_part == l);
+            }
+            Prune pr = compute_prune(S, pin, flags, tau, lane);
             uint32_t cnt = 0, ncand = 0;
 
             // ---- anchors with entries: bounded one by one (entry scores are known exactly, plane parts by their bound)
@@ -533,26 +605,43 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
                             e0 = ev0 ? __uint_as_float(ev0 & 0x7FFFFFFFu) : 0.0f, e1 = ev1 ? __uint_as_float(ev1 & 0x7FFFFFFFu) : 0.0f;
                             e2 = ev2 ? __uint_as_float(ev2 & 0x7FFFFFFFu) : 0.0f, e3 = ev3 ? __uint_as_float(ev3 & 0x7FFFFFFFu) : 0.0f;
                             uint32_t by_plane = 0;  // bit l: part l is present through one of its planes
+                            float pub0 = 0.0f, pub1 = 0.0f, pub2 = 0.0f, pub3 = 0.0f;  // ... and the most such a plane can give it
+                            auto present = [&](uint32_t t) {
+                                const uint32_t l = S.term_part[t];
+                                const float ub = S.term_ub[t];
+                                by_plane |= 1u << l;
+                                if (l == 0) pub0 = fmaxf(pub0, ub);
+                                else if (l == 1) pub1 = fmaxf(pub1, ub);
+                                else if (l == 2) pub2 = fmaxf(pub2, ub);
+                                else pub3 = fmaxf(pub3, ub);
+                            };
                             const uint32_t w = idx >> 5, bit = 1u << (idx & 31u);
 #pragma unroll 1
-                            for (uint32_t t = 0; t < nt; ++t)
-                                if (__ldg(S.term_bits[t] + w) & bit) by_plane |= 1u << S.term_part[t];
+                            for (uint32_t t = 0; t < nt; t += 4) {  // four independent loads at a time
+                                const uint32_t x0 = __ldg(S.term_bits[t] + w);
+                                const uint32_t x1 = t + 1 < nt ? __ldg(S.term_bits[t + 1] + w) : 0u;
+                                const uint32_t x2 = t + 2 < nt ? __ldg(S.term_bits[t + 2] + w) : 0u;
+                                const uint32_t x3 = t + 3 < nt ? __ldg(S.term_bits[t + 3] + w) : 0u;
+                                if (x0 & bit) present(t);
+                                if (x1 & bit) present(t + 1);
+                                if (x2 & bit) present(t + 2);
+                                if (x3 & bit) present(t + 3);
+                            }
                             if (!by_plane) cnt += 1;  // a hit the plane sweep does not count
                             float sum_ub = 0.0f;
                             uint32_t n = 0;
-                            auto part = [&](uint32_t l, uint32_t ev, float e) {
-                                const bool bp = (by_plane >> l) & 1u;
-                                if (ev || bp) {
+                            auto part = [&](uint32_t l, uint32_t ev, float e, float pub) {
+                                if (ev || ((by_plane >> l) & 1u)) {
                                     n += 1;
-                                    sum_ub += fmaxf(e, bp ? D->ub[l] : 0.0f);
+                                    sum_ub += fmaxf(e, pub);
                                 }
                             };
-                            part(0, ev0, e0);
-                            if (L > 1) part(1, ev1, e1);
-                            if (L > 2) part(2, ev2, e2);
-                            if (L > 3) part(3, ev3, e3);
+                            part(0, ev0, e0, pub0);
+                            if (L > 1) part(1, ev1, e1, pub1);
+                            if (L > 2) part(2, ev2, e2, pub2);
+                            if (L > 3) part(3, ev3, e3, pub3);
                             const float B = (L == 1 ? sum_ub : sum_ub * (float)(n * n)) * 1.00001f;
-                            const float tau_score = S.tau_score;
+                            const float tau_score = pr.tau_score;
                             cand = true;
                             if (tau_score > 0.0f) {
                                 if (flags & kFastBoost) {
@@ -569,84 +658,63 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
                     }
                     if (enqueue(C, S, lane, q, cand, rel, e0, e1, e2, e3, qn, ncand)) {
                         tau = __ldcg(a.tau + q);
-                        compute_levels(S, D, flags, L, tau, lane);
+                        pr = compute_prune(S, pin, flags, tau, lane);
                     }
                 }
             }
 
             // ---- anchors without entries: the plane sweep, four 32-anchor words per lane and step
-            bool swept_general = false;
-            const bool one_plane_done = nt == 1 && S.lev[0] == -2;  // single-part anchors cannot reach the threshold any more
+            bool swept_cold = false;
+            const bool count_from_table = nt == 1 && !pr.possible;  // one plane term and no anchor of it can matter any more
             if (nt == 0) {
                 // nothing but entries
-            } else if (one_plane_done) {
+            } else if (count_from_table) {
                 // the hit count is the plane's count of the group's tiles (+ the entry anchors outside it, counted above)
                 const uint32_t tiles_total = words >> (kPlaneTileLog2 - 5), t0 = g * a.group_tiles;
                 if (lane < a.group_tiles && t0 + lane < tiles_total) cnt += __ldg(a.planes.tcount + (size_t)D->plane[0] * tiles_total + t0 + lane);
             } else {
-#pragma unroll 1
-                for (uint32_t w4 = lane; w4 < (nw >> 2); w4 += 32) {
-                    // presence words of every part (OR over the part's planes)
-                    uint4 pw0 = make_uint4(0u, 0u, 0u, 0u), pw1 = pw0, pw2 = pw0, pw3 = pw0;
-#pragma unroll 1
-                    for (uint32_t t = 0; t < nt; ++t) {
-                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(S.term_bits[t]) + w4);
-                        const uint32_t p = S.term_part[t];
-                        if (p == 0) or4(pw0, v);
-                        else if (p == 1) or4(pw1, v);
-                        else if (p == 2) or4(pw2, v);
-                        else or4(pw3, v);
-                    }
-                    const int lv0 = S.lev[0], lv1 = S.lev[1], lv2 = S.lev[2], lv3 = S.lev[3];
-                    const int lev_top = L == 1 ? lv0 : L == 2 ? lv1 : L == 3 ? lv2 : lv3;
-                    const bool lower_dead = (L < 2 || lv0 == -2) && (L < 3 || lv1 == -2) && (L < 4 || lv2 == -2);
-                    uint4 cm = make_uint4(0u, 0u, 0u, 0u);
-                    if (lower_dead) {
-                        // converged threshold: only anchors with every part present can still matter -> OR for the count, AND for the candidates
-                        uint4 any = pw0, all = pw0;
-                        if (L > 1) or4(any, pw1), and4(all, pw1);
-                        if (L > 2) or4(any, pw2), and4(all, pw2);
-                        if (L > 3) or4(any, pw3), and4(all, pw3);
-                        cnt += popc4(any);
-                        if (lev_top != -2 && any4(all)) {
-                            if (lev_top >= 0) and4(all, __ldg(reinterpret_cast<const uint4*>(lev_bits + (size_t)lev_top * lev_words) + w4));
-                            cm = all;
-                        }
-                    } else {
-                        swept_general = true;
-                        uint4 ones = pw0, twos = make_uint4(0u, 0u, 0u, 0u), fours = twos;
-                        auto add_part = [&](const uint4& x) {
-                            uint32_t cy, cy2;
-                            cy = ones.x & x.x, ones.x ^= x.x, cy2 = twos.x & cy, twos.x ^= cy, fours.x |= cy2;
-                            cy = ones.y & x.y, ones.y ^= x.y, cy2 = twos.y & cy, twos.y ^= cy, fours.y |= cy2;
-                            cy = ones.z & x.z, ones.z ^= x.z, cy2 = twos.z & cy, twos.z ^= cy, fours.z |= cy2;
-                            cy = ones.w & x.w, ones.w ^= x.w, cy2 = twos.w & cy, twos.w ^= cy, fours.w |= cy2;
-                        };
-                        if (L > 1) add_part(pw1);
-                        if (L > 2) add_part(pw2);
-                        if (L > 3) add_part(pw3);
-                        cnt += __popc(ones.x | twos.x | fours.x) + __popc(ones.y | twos.y | fours.y) + __popc(ones.z | twos.z | fours.z) + __popc(ones.w | twos.w | fours.w);
-#pragma unroll
-                        for (int i2 = 0; i2 < (int)kFastMaxLeaves; ++i2) {
-                            const int lv = i2 == 0 ? lv0 : i2 == 1 ? lv1 : i2 == 2 ? lv2 : lv3;
-                            if (lv == -2) continue;
-                            uint4 ex;  // anchors with exactly i2 + 1 parts present
-                            if (i2 == 0) ex = make_uint4(ones.x & ~twos.x & ~fours.x, ones.y & ~twos.y & ~fours.y, ones.z & ~twos.z & ~fours.z, ones.w & ~twos.w & ~fours.w);
-                            else if (i2 == 1) ex = make_uint4(twos.x & ~ones.x & ~fours.x, twos.y & ~ones.y & ~fours.y, twos.z & ~ones.z & ~fours.z, twos.w & ~ones.w & ~fours.w);
-                            else if (i2 == 2) ex = make_uint4(ones.x & twos.x, ones.y & twos.y, ones.z & twos.z, ones.w & twos.w);
-                            else ex = fours;
-                            if (lv >= 0 && any4(ex)) and4(ex, __ldg(reinterpret_cast<const uint4*>(lev_bits + (size_t)lv * lev_words) + w4));
-                            or4(cm, ex);
-                        }
-                    }
-                    if (__ballot_sync(0xFFFFFFFFu, any4(cm)) == 0) continue;
+                const uint4* tp0 = reinterpret_cast<const uint4*>(S.term_bits[0]);
+                const uint4* tp1 = reinterpret_cast<const uint4*>(S.term_bits[nt > 1 ? 1 : 0]);
+                const uint4* tp2 = reinterpret_cast<const uint4*>(S.term_bits[nt > 2 ? 2 : 0]);
+                const uint4* tp3 = reinterpret_cast<const uint4*>(S.term_bits[nt > 3 ? 3 : 0]);
+                const uint32_t tq0 = S.term_part[0], tq1 = S.term_part[nt > 1 ? 1 : 0], tq2 = S.term_part[nt > 2 ? 2 : 0], tq3 = S.term_part[nt > 3 ? 3 : 0];
+                // candidates of one step: `cm` = anchors that pass the word-parallel tests
+                auto candidates = [&](uint32_t w4, const uint4& cm) {
+                    if (__ballot_sync(0xFFFFFFFFu, any4(cm)) == 0) return;
 #pragma unroll 1
                     for (int c4 = 0; c4 < 4; ++c4) {
                         uint32_t m = c4 == 0 ? cm.x : c4 == 1 ? cm.y : c4 == 2 ? cm.z : cm.w;
                         while (__ballot_sync(0xFFFFFFFFu, m != 0)) {
                             bool flag = m != 0;
-                            const uint32_t idx = (w4 * 4u + (uint32_t)c4) * 32u + (uint32_t)__ffs((int)m) - 1u;
+                            const uint32_t bp = flag ? (uint32_t)__ffs((int)m) - 1u : 0u;
+                            const uint32_t idx = (w4 * 4u + (uint32_t)c4) * 32u + bp;
                             m &= m - 1u;
+                            // Second stage: this anchor's bound from the terms it really has (their words come from L1 now).
+                            if (flag && pr.tau_score > 0.0f) {
+                                float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+#pragma unroll 1
+                                for (uint32_t t = 0; t < nt; ++t)
+                                    if ((__ldg(S.term_bits[t] + (idx >> 5)) >> bp) & 1u) {
+                                        const uint32_t part = S.term_part[t];
+                                        const float ub = S.term_ub[t];
+                                        if (part == 0) v0 = fmaxf(v0, ub);
+                                        else if (part == 1) v1 = fmaxf(v1, ub);
+                                        else if (part == 2) v2 = fmaxf(v2, ub);
+                                        else v3 = fmaxf(v3, ub);
+                                    }
+                                const uint32_t np = (v0 > 0.0f) + (v1 > 0.0f) + (v2 > 0.0f) + (v3 > 0.0f);
+                                const float sum = v0 + v1 + v2 + v3;
+                                const float B = (L == 1 ? sum : sum * (float)(np * np)) * 1.00001f;
+                                if (flags & kFastBoost) {
+                                    if (B * pin.max_mult < pr.tau_score) flag = false;
+                                    else {
+                                        const int lo = deepest_level(S, B, pr.tau_score);
+                                        if (lo >= 0) flag = (__ldg(lev_bits + (size_t)lo * lev_words + (idx >> 5)) >> bp) & 1u;
+                                    }
+                                } else if (B * 1.00001f < pr.tau_score) {
+                                    flag = false;
+                                }
+                            }
                             // anchors with entries belong to the entry pass above (it knows their entry scores)
                             if (flag && n_ent) {
                                 bool has = hash_lookup(S, idx) != 0u;
@@ -657,16 +725,115 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
                             }
                             if (enqueue(C, S, lane, q, flag, rel0 + idx, 0.0f, 0.0f, 0.0f, 0.0f, qn, ncand)) {
                                 tau = __ldcg(a.tau + q);
-                                compute_levels(S, D, flags, L, tau, lane);  // the rest of the sweep prunes against the tightened threshold
+                                pr = compute_prune(S, pin, flags, tau, lane);  // the rest of the sweep prunes against the tightened threshold
                             }
                         }
+                    }
+                };
+                const uint4 ones4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                auto level_row = [&](int lv) { return reinterpret_cast<const uint4*>(lev_bits + (size_t)(lv > 0 ? lv : 0) * lev_words); };
+                // `v`: the word of term t, `lw` the word of the boost level the term's anchors must be inside.  The word joins
+                // its part's presence word (r*) and, restricted to that level, the part's word of anchors that can matter (p*).
+                auto place = [&](uint32_t t, uint32_t part, const uint4& v, const uint4& lw, uint4& r0, uint4& r1, uint4& r2, uint4& r3, uint4& p0, uint4& p1, uint4& p2, uint4& p3) {
+                    const bool ok = (pr.allow >> t) & 1u;
+                    const uint4 x = make_uint4(v.x & lw.x, v.y & lw.y, v.z & lw.z, v.w & lw.w);
+                    if (part == 0) {
+                        or4(r0, v);
+                        if (ok) or4(p0, x);
+                    } else if (part == 1) {
+                        or4(r1, v);
+                        if (ok) or4(p1, x);
+                    } else if (part == 2) {
+                        or4(r2, v);
+                        if (ok) or4(p2, x);
+                    } else {
+                        or4(r3, v);
+                        if (ok) or4(p3, x);
+                    }
+                };
+                // Anchors that can matter by their number of present parts: exactly n parts -> inside count_lev[n - 1].
+                auto by_count = [&](uint32_t w4, const uint4& r0, const uint4& r1, const uint4& r2, const uint4& r3) {
+                    uint4 ones = r0, twos = make_uint4(0u, 0u, 0u, 0u), fours = twos;
+                    auto add_part = [&](const uint4& x) {
+                        uint32_t cy, cy2;
+                        cy = ones.x & x.x, ones.x ^= x.x, cy2 = twos.x & cy, twos.x ^= cy, fours.x |= cy2;
+                        cy = ones.y & x.y, ones.y ^= x.y, cy2 = twos.y & cy, twos.y ^= cy, fours.y |= cy2;
+                        cy = ones.z & x.z, ones.z ^= x.z, cy2 = twos.z & cy, twos.z ^= cy, fours.z |= cy2;
+                        cy = ones.w & x.w, ones.w ^= x.w, cy2 = twos.w & cy, twos.w ^= cy, fours.w |= cy2;
+                    };
+                    add_part(r1), add_part(r2), add_part(r3);
+                    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int i2 = 0; i2 < (int)kFastMaxLeaves; ++i2) {
+                        const int lv = S.count_lev[i2];
+                        if (lv == -2) continue;
+                        uint4 ex;  // anchors with exactly i2 + 1 parts present
+                        if (i2 == 0) ex = make_uint4(ones.x & ~twos.x & ~fours.x, ones.y & ~twos.y & ~fours.y, ones.z & ~twos.z & ~fours.z, ones.w & ~twos.w & ~fours.w);
+                        else if (i2 == 1) ex = make_uint4(twos.x & ~ones.x & ~fours.x, twos.y & ~ones.y & ~fours.y, twos.z & ~ones.z & ~fours.z, twos.w & ~ones.w & ~fours.w);
+                        else if (i2 == 2) ex = make_uint4(ones.x & twos.x, ones.y & twos.y, ones.z & twos.z, ones.w & twos.w);
+                        else ex = fours;
+                        if (lv >= 0 && any4(ex)) and4(ex, __ldg(level_row(lv) + w4));
+                        or4(out, ex);
+                    }
+                    return out;
+                };
+                auto required = [&](uint4 cm, const uint4& p0, const uint4& p1, const uint4& p2, const uint4& p3) {
+                    if (!(pr.optional & 1u)) and4(cm, p0);
+                    if (!(pr.optional & 2u)) and4(cm, p1);
+                    if (!(pr.optional & 4u)) and4(cm, p2);
+                    if (!(pr.optional & 8u)) and4(cm, p3);
+                    return cm;
+                };
+                // One step per iteration: the plane words of up to four terms and the boost level words they are restricted to
+                // are requested before any is used, so up to eight independent 128-bit loads are in flight per lane (a load-use
+                // chain per term would expose the L2 latency once per term).
+                const uint32_t nw4 = nw >> 2;  // a multiple of 64
+                swept_cold = pr.tau_score == 0.0f;
+#pragma unroll 1
+                for (uint32_t w4 = lane; w4 < nw4; w4 += 32) {
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                    const int tl0 = S.term_lev[0], tl1 = S.term_lev[1], tl2 = S.term_lev[2], tl3 = S.term_lev[3];  // (they move with the threshold)
+                    const uint4 a0 = __ldg(tp0 + w4);
+                    uint4 a1 = z, a2 = z, a3 = z;
+                    if (nt > 1) a1 = __ldg(tp1 + w4);
+                    if (nt > 2) a2 = __ldg(tp2 + w4);
+                    if (nt > 3) a3 = __ldg(tp3 + w4);
+                    uint4 la0 = ones4, la1 = ones4, la2 = ones4, la3 = ones4;
+                    if (pr.possible) {
+                        if (tl0 >= 0) la0 = __ldg(level_row(tl0) + w4);
+                        if (nt > 1 && tl1 >= 0) la1 = __ldg(level_row(tl1) + w4);
+                        if (nt > 2 && tl2 >= 0) la2 = __ldg(level_row(tl2) + w4);
+                        if (nt > 3 && tl3 >= 0) la3 = __ldg(level_row(tl3) + w4);
+                    }
+                    uint4 ra0 = z, ra1 = z, ra2 = z, ra3 = z, pa0 = z, pa1 = z, pa2 = z, pa3 = z;
+                    place(0, tq0, a0, la0, ra0, ra1, ra2, ra3, pa0, pa1, pa2, pa3);
+                    if (nt > 1) place(1, tq1, a1, la1, ra0, ra1, ra2, ra3, pa0, pa1, pa2, pa3);
+                    if (nt > 2) place(2, tq2, a2, la2, ra0, ra1, ra2, ra3, pa0, pa1, pa2, pa3);
+                    if (nt > 3) place(3, tq3, a3, la3, ra0, ra1, ra2, ra3, pa0, pa1, pa2, pa3);
+#pragma unroll 1
+                    for (uint32_t t = 4; t < nt; ++t) {  // requests with more than four plane terms
+                        const int tl = S.term_lev[t];
+                        const uint4 va = __ldg(reinterpret_cast<const uint4*>(S.term_bits[t]) + w4);
+                        uint4 la = ones4;
+                        if (pr.possible && tl >= 0) la = __ldg(level_row(tl) + w4);
+                        place(t, S.term_part[t], va, la, ra0, ra1, ra2, ra3, pa0, pa1, pa2, pa3);
+                    }
+                    const uint4 any = make_uint4(ra0.x | ra1.x | ra2.x | ra3.x, ra0.y | ra1.y | ra2.y | ra3.y, ra0.z | ra1.z | ra2.z | ra3.z, ra0.w | ra1.w | ra2.w | ra3.w);
+                    cnt += popc4(any);
+                    if (pr.possible) {
+                        // some allowed term present, every part that must be present present through such a term ...
+                        uint4 cm = make_uint4(pa0.x | pa1.x | pa2.x | pa3.x, pa0.y | pa1.y | pa2.y | pa3.y, pa0.z | pa1.z | pa2.z | pa3.z, pa0.w | pa1.w | pa2.w | pa3.w);
+                        cm = required(cm, pa0, pa1, pa2, pa3);
+                        // ... and, when parts may be absent, inside the level its part count needs
+                        if (pr.by_count && any4(cm)) and4(cm, by_count(w4, ra0, ra1, ra2, ra3));
+                        candidates(w4, cm);
                     }
                 }
             }
             for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
             if (lane == 0) {
                 if (cnt) atomicAdd(a.num_hits + q, (unsigned long long)cnt);
-                st_cand += ncand, st_items += 1, st_general += swept_general ? 1 : 0, st_sweepless += (nt == 0 || one_plane_done) ? 1 : 0;
+                st_cand += ncand, st_items += 1, st_general += swept_cold ? 1 : 0, st_sweepless += (nt == 0 || count_from_table) ? 1 : 0;
             }
             if (n_ent) {  // leave the hash table empty
                 __syncwarp();
@@ -682,7 +849,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
     if (lane == 0 && st_items) {
         atomicAdd(a.stats + 0, st_items);
         atomicAdd(a.stats + 1, st_cand);
-        atomicAdd(a.stats + 5, st_general);    // items swept (at least partly) with the exact per-anchor part count (threshold not converged)
+        atomicAdd(a.stats + 5, st_general);    // items swept without a threshold (the request had fewer than k hits so far)
         atomicAdd(a.stats + 6, st_sweepless);  // items answered from the per-plane tile counts
     }
 }

@@ -43,13 +43,22 @@ static const uint32_t kSliceChunk = 64;     // slice records staged in shared me
 // cursors).  Every other pair becomes one general item per non-empty tile of the group, with all its slices; blocks
 // reserve general output ranges in index order, so that list stays (nearly) tile-major.
 
+// Tile offsets of the postings of dense match `mi`: the plane's prefix row for a plane term, else its row of the batch's table.
+__device__ __forceinline__ const uint32_t* dense_row(const uint32_t* toff, const uint32_t* tprefix, const uint32_t* g_row, const uint32_t* g_plane, uint32_t mi, uint32_t n_tiles) {
+    if (g_plane != nullptr) {
+        const uint32_t p = g_plane[mi];
+        if (p != kNoValue) return tprefix + (size_t)p * (n_tiles + 1);
+    }
+    return toff + (size_t)g_row[mi] * (n_tiles + 1);
+}
+
 // Postings and non-empty slices of request `qp` in tile t.
 __device__ __forceinline__ void tile_totals(const ItemScanArgs& a, const QueryProgram& qp, uint32_t t, uint32_t& all_post, uint32_t& all_slices) {
     all_post = 0, all_slices = 0;
     for (uint32_t l = 0; l < qp.n_leaves; ++l) {
         const PartSlices ps = a.slices[a.leaf_part[qp.leaf_begin + l]];
         for (uint32_t r = 0; r < ps.n_dense; ++r) {
-            const uint32_t* trow = a.toff + (size_t)a.g_row[ps.m_begin + r] * (a.n_tiles + 1);
+            const uint32_t* trow = dense_row(a.toff, a.plane_tprefix, a.g_row, a.g_plane, ps.m_begin + r, a.n_tiles);
             const uint32_t n = trow[t + 1] - trow[t];
             all_post += n, all_slices += n ? 1u : 0u;
         }
@@ -87,7 +96,7 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
             for (uint32_t l = 0; l < qp.n_leaves; ++l) {
                 const PartSlices ps = a.slices[a.leaf_part[qp.leaf_begin + l]];
                 for (uint32_t r = 0; r < ps.n_dense; ++r) {
-                    const uint32_t* trow = a.toff + (size_t)a.g_row[ps.m_begin + r] * (a.n_tiles + 1);
+                    const uint32_t* trow = dense_row(a.toff, a.plane_tprefix, a.g_row, a.g_plane, ps.m_begin + r, a.n_tiles);
                     const uint32_t n = trow[t1] - trow[t0];
                     if (a.g_plane[ps.m_begin + r] != kNoValue) plane_hit = plane_hit || n != 0;
                     else if (n) fits = false;  // a frequent term without a plane: general path
@@ -164,7 +173,7 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
             const PartSlices ps = a.slices[part];
             for (uint32_t r = 0; r < ps.n_dense; ++r) {
                 const uint32_t mi = ps.m_begin + r;
-                const uint32_t* trow = a.toff + (size_t)a.g_row[mi] * (a.n_tiles + 1);
+                const uint32_t* trow = dense_row(a.toff, a.plane_tprefix, a.g_row, a.g_plane, mi, a.n_tiles);
                 const uint32_t s = trow[t], e = trow[t + 1];
                 if (e == s) continue;
                 SliceRec sr;
@@ -237,6 +246,8 @@ struct LeafBoostGlobals {  // the batch tables the rule needs; one copy per CTA 
     const uint32_t* leaf_part;
     const uint32_t* toff;
     const uint32_t* g_row;
+    const uint32_t* g_plane;
+    const uint32_t* plane_tprefix;
     uint32_t n_tiles, tile_log2, anchor_lo, pad;
 };
 struct LeafBoostCtx {
@@ -288,7 +299,7 @@ __device__ __noinline__ float apply_leaf_boost(const LeafBoostGlobals* gp, LeafB
                 for (uint32_t i = prow[tt]; i < prow[tt + 1]; ++i)
                     if (pent[i].anchor < cur && (!found || pent[i].anchor > pred)) pred = pent[i].anchor, found = true;
             for (uint32_t r = 0; r < ps.n_dense; ++r) {
-                const uint32_t* trow = a.toff + (size_t)a.g_row[ps.m_begin + r] * (a.n_tiles + 1);
+                const uint32_t* trow = dense_row(a.toff, a.plane_tprefix, a.g_row, a.g_plane, ps.m_begin + r, a.n_tiles);
                 const Posting* post = pv.post + a.g_begin[ps.m_begin + r];
                 uint32_t lo = trow[tt], hi = trow[tt + 1];
                 const uint32_t first = lo;
@@ -676,7 +687,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
     }
     if (tid == 0) {
         s_lb.bucket = a.bucket, s_lb.sparse = a.sparse, s_lb.slices = a.slices, s_lb.postings = a.postings, s_lb.parts = a.parts;
-        s_lb.g_begin = a.g_begin, s_lb.g_df = a.g_df, s_lb.leaf_part = a.leaf_part, s_lb.toff = a.toff, s_lb.g_row = a.g_row;
+        s_lb.g_begin = a.g_begin, s_lb.g_df = a.g_df, s_lb.leaf_part = a.leaf_part, s_lb.toff = a.toff, s_lb.g_row = a.g_row, s_lb.g_plane = a.g_plane, s_lb.plane_tprefix = a.plane_tprefix;
         s_lb.n_tiles = a.n_tiles, s_lb.tile_log2 = a.tile_log2, s_lb.anchor_lo = a.anchor_lo, s_lb.pad = 0;
         const unsigned long long first = atomicAdd(a.work_counter, 1ull);
         s_item_idx[0] = first;

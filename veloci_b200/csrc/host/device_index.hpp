@@ -347,7 +347,8 @@ struct PlaneSetDev {  // term planes of every postings store of the shard (head 
     DevBuf<float> wmax;
     DevBuf<PlaneInfo> info;
     DevBuf<uint32_t> tcount;  // [n_planes][tiles]
-    PlaneSetView view() const { return PlaneSetView{bits.p, score.p, wmax.p, info.p, tcount.p, n_planes, n_head, words, 0u}; }
+    DevBuf<uint32_t> tprefix; // [n_planes][tiles + 1]
+    PlaneSetView view() const { return PlaneSetView{bits.p, score.p, wmax.p, info.p, tcount.p, tprefix.p, n_planes, n_head, words, 0u}; }
 };
 
 struct CsrDev {  // id -> list<u32>
@@ -696,11 +697,11 @@ struct DeviceIndex {
     }
 
     // Term planes: head planes for the terms with df >= span / 128 (at most kMaxHeadPlanes, bits + f16 scores), mid planes
-    // for the terms with df >= span / 1024 (bits only), at most kMaxPlanes in total, by descending df over all stores.
+    // for the terms with df >= span / 4096 (bits only), at most kMaxPlanes in total, by descending df over all stores.
     void build_planes() {
         const uint64_t span = anchor_hi - anchor_lo;
         if ((open_flags & kOpenNoPlanes) || span == 0 || span >= 0xFFFFFFFFull) return;
-        const uint64_t head_df = std::max<uint64_t>(1, span / 128), mid_df = std::max<uint64_t>(16, span / 1024);
+        const uint64_t head_df = std::max<uint64_t>(1, span / 128), mid_df = std::max<uint64_t>(16, span / 4096);
         struct Cand {
             uint64_t df;
             PostingsDev* store;
@@ -739,7 +740,8 @@ struct DeviceIndex {
         }
         planes.info.upload(info);
         planes.tcount.alloc((size_t)n * (words >> (kPlaneTileLog2 - 5)));
-        launch_plane_tile_counts(nullptr, planes.bits.p, n, words, planes.tcount.p);
+        planes.tprefix.alloc((size_t)n * ((words >> (kPlaneTileLog2 - 5)) + 1));
+        launch_plane_tile_counts(nullptr, planes.bits.p, n, words, planes.tcount.p, planes.tprefix.p);
         std::vector<uint32_t> h_bad(n);
         VDEV_CUDA(cudaMemcpy(h_bad.data(), bad.p, n * 4, cudaMemcpyDeviceToHost));
         std::map<PostingsDev*, std::vector<uint32_t>> maps;
@@ -760,7 +762,7 @@ struct DeviceIndex {
             for (size_t t = 0; t < pd.n_terms; ++t)
                 if (it == maps.end() || it->second[t] == kNoValue) max_nonplane_list = std::max<uint64_t>(max_nonplane_list, pd.h_off[t + 1] - pd.h_off[t]);
         }
-        device_bytes += planes.bits.bytes() + planes.score.bytes() + planes.wmax.bytes() + planes.info.bytes() + planes.tcount.bytes();
+        device_bytes += planes.bits.bytes() + planes.score.bytes() + planes.wmax.bytes() + planes.info.bytes() + planes.tcount.bytes() + planes.tprefix.bytes();
     }
 
     void build_phrase(const std::string& path, const vfmt::PhrasePairView& v) {

@@ -792,7 +792,7 @@ struct Batch {
             sc.counters = d_counters.p + 5, sc.items = nullptr, sc.slice_recs = nullptr;
             d_fast_item_cursor.reserve(n_groups + 1), d_fast_item_begin.reserve(n_groups + 2);
             sc.fast_item_cursor = d_fast_item_cursor.p, sc.fast_item_begin = d_fast_item_begin.p;
-            if (planes_on) sc.fast = d_fast.p, sc.g_plane = d_g_plane.p, sc.plane_tcount = ix->planes.tcount.p;
+            if (planes_on) sc.fast = d_fast.p, sc.g_plane = d_g_plane.p, sc.plane_tprefix = ix->planes.tprefix.p;
             VDEV_CUDA(cudaMemsetAsync(d_fast_item_cursor.p, 0, d_fast_item_cursor.bytes(), stream));
             VDEV_CUDA(cudaMemsetAsync(d_counters.p + 5, 0, 16, stream));
             timed("item_scan", [&] { launch_item_scan(stream, sc, false); });
@@ -851,6 +851,7 @@ struct Batch {
             a.queries = d_programs.p, a.n_queries = n, a.leaf_part = d_leaf_part.p, a.prog = d_prog.p, a.boosts = d_boosts.p, a.facets = d_facets.p;
             a.parts = d_parts.p, a.slices = d_slices.p, a.postings = d_postings.p, a.g_score = d_g_score.p, a.g_begin = d_g_begin.p, a.g_row = d_g_row.p, a.g_df = d_g_df.p;
             a.toff = d_toff.p, a.bucket = d_bucket.p, a.sparse = d_sparse.p;
+            a.g_plane = use_planes ? d_g_plane.p : nullptr, a.plane_tprefix = use_planes ? ix->planes.tprefix.p : nullptr;
             a.n_tiles = n_tiles, a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
             a.max_leaves = std::max<uint32_t>(1, plan.max_leaves);
             a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
