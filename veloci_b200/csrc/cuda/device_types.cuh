@@ -58,7 +58,7 @@ struct PostingsView {
 // ("plane").  The plane path (planes.cu) evaluates them with word-wide bit operations instead of
 // scattering their postings.  Two classes, by document frequency over the shard's anchors:
 //   head planes  df >= span / 128  (at most kMaxHeadPlanes): bits + the f16 score per anchor
-//   mid planes   df >= span / 4096 (at most kMaxPlanes in total): bits only; the weight of an anchor is found by
+//   mid planes   df >= span / 1024 (at most kMaxPlanes in total): bits only; the weight of an anchor is found by
 //                binary search in the term's posting list, which only exact evaluations (rare) need
 // Planes are ordered by descending df over all fields; plane ids below n_head are head planes.
 static const uint32_t kMaxHeadPlanes = 96;
@@ -128,7 +128,7 @@ static_assert(sizeof(FastDesc) == 176, "FastDesc layout");
 // inside the group's tiles) are one contiguous range of the part's sparse tile buckets.
 struct alignas(16) FastItem {  // 32 B
     uint32_t q;
-    uint32_t group;
+    uint32_t tiles;                  // first tile | number of tiles << 24 (at most the group size; fewer where the entries of a whole group exceed kGroupMaxEntries)
     uint16_t n[kFastMaxLeaves];
     uint32_t begin[kFastMaxLeaves];  // index into the batch's SparseEntry array
 };

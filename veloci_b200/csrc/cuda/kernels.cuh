@@ -231,6 +231,8 @@ struct PlaneArgs {
     uint32_t anchor_lo, anchor_hi;
     uint32_t group_tiles;                 // tiles of 2^13 anchors per item
     uint32_t group_begin, group_end;      // this launch evaluates the items of groups [group_begin, group_end)
+    const uint32_t* ones_row;             // constant rows of at least group_tiles * 256 words: all ones, all zeros
+    const uint32_t* zeros_row;
     // per-query state (shared with tile_eval_kernel)
     unsigned long long* heap;
     uint32_t heap_stride;

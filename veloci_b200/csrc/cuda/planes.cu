@@ -54,6 +54,7 @@ struct alignas(16) WarpScratch {
     float term_ub[kFastMaxTerms + 4];          // largest score the term can give its part (term score x largest weight of its plane)
     int term_lev[kFastMaxTerms + 4];           // boost level an anchor whose part takes this term must be inside (-1: any, -2: it cannot matter)
     int count_lev[kFastMaxLeaves];             // ... an anchor with exactly n + 1 parts present must be inside
+    const uint32_t* term_lw[kFastMaxTerms + 4]; // row the term's words are AND-ed with: its boost level's, all ones (any anchor) or all zeros (cannot matter)
     // which (boost function, param, column) mult[] was computed for
     uint32_t mult_fun;
     float mult_param;
@@ -276,6 +277,10 @@ struct PruneInputs {
     float max_mult;    // largest boost multiplier (1 without a boost)
     uint32_t part_terms[kFastMaxLeaves];  // per part: mask of its terms
     uint32_t nt;
+    const uint32_t* lev_bits;             // the boost column's level rows at the item's first word (nullptr without a boost)
+    uint32_t lev_words;
+    const uint32_t* ones_row;
+    const uint32_t* zeros_row;
 };
 
 __device__ __forceinline__ Prune compute_prune(WarpScratch& S, const PruneInputs& in, uint32_t flags, unsigned long long tau, uint32_t lane) {
@@ -296,7 +301,10 @@ __device__ __forceinline__ Prune compute_prune(WarpScratch& S, const PruneInputs
         else if (flags & kFastBoost) cl = deepest_level(S, in.count_bound, p.tau_score);
     }
     __syncwarp();
-    if (lane < in.nt) S.term_lev[lane] = lv;
+    if (lane < in.nt) {
+        S.term_lev[lane] = lv;
+        S.term_lw[lane] = lv == -2 ? in.zeros_row : lv == -1 ? in.ones_row : in.lev_bits + (size_t)lv * in.lev_words;
+    }
     if (lane < kFastMaxLeaves) S.count_lev[lane] = cl;
     p.allow = __ballot_sync(0xFFFFFFFFu, lane < in.nt && lv != -2);
     p.optional = __ballot_sync(0xFFFFFFFFu, lane < kFastMaxLeaves && (in.part_terms[lane & 3u] == 0u || in.opt_need >= p.tau_score));
@@ -324,6 +332,12 @@ __device__ __noinline__ void merge_group(const CtaContext* C, WarpScratch* Sp, u
     }
     __syncwarp();
     for (uint32_t i = lane; i < k; i += 32) S.merge[i] = __ldcg(heap + i);
+    __syncwarp();
+    // a key that is in the top-k already (its anchor was evaluated before: the seed pass and the sweep may both reach it) is dropped
+    if (group & (1u << lane))
+        for (uint32_t i = 0; i < k; ++i)
+            if (S.merge[i] == comp) comp = 0;
+    group = __ballot_sync(0xFFFFFFFFu, (group & (1u << lane)) && comp != 0);
     const uint32_t cnt = __popc(group);
     if (group & (1u << lane)) S.merge[k + __popc(group & ((1u << lane) - 1u))] = comp;
     __syncwarp();
@@ -503,7 +517,6 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
     __syncthreads();
     unsigned long long st_cand = 0, st_items = 0, st_general = 0, st_sweepless = 0;  // lane 0
     const uint32_t ibeg = a.group_item_begin[a.group_begin], iend = a.group_item_begin[a.group_end];
-    const uint32_t group_words = a.group_tiles << (kPlaneTileLog2 - 5);
     const uint32_t words = a.planes.words;
     uint32_t qn = 0;  // candidates of this warp waiting for their exact evaluation
 
@@ -515,17 +528,17 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
         const uint32_t last = min(iend, first + kItemBatch);
 #pragma unroll 1
         for (uint32_t ii = first; ii < last; ++ii) {
-            // ---- item (group g, request q)
+            // ---- item (tiles [t0, t0 + n), request q)
             const uint4* rp = reinterpret_cast<const uint4*>(a.items + ii);
             const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-            const uint32_t q = r0.x, g = r0.y;
+            const uint32_t q = r0.x, t0 = r0.y & 0xFFFFFFu, n_item_tiles = r0.y >> 24;  // the item's tiles: [t0, t0 + n_item_tiles)
             const uint32_t c0 = r0.z & 0xFFFFu, c1 = c0 + (r0.z >> 16), c2 = c1 + (r0.w & 0xFFFFu), n_ent = c2 + (r0.w >> 16);  // entry prefix sums over the parts
             const FastDesc* __restrict__ D = a.fast + q;
             const uint32_t flags = D->flags, L = D->n_leaves, nt = D->n_terms;
             unsigned long long tau = __ldcg(a.tau + q);
-            const uint32_t w0 = g * group_words;                 // first word of the group in every plane
-            const uint32_t nw = min(group_words, words - w0);    // words of this group (the last group may be short)
-            const uint32_t rel0 = w0 << 5;                       // first anchor of the group, relative to the shard
+            const uint32_t w0 = t0 << (kPlaneTileLog2 - 5);                              // first word of the item in every plane
+            const uint32_t nw = min(n_item_tiles << (kPlaneTileLog2 - 5), words - w0);   // its words
+            const uint32_t rel0 = w0 << 5;                                               // its first anchor, relative to the shard
             const ColumnLevels* __restrict__ lev = (flags & kFastBoost) ? D->fb_lev : nullptr;
             const uint32_t* lev_bits = nullptr;
             uint32_t lev_words = 0;
@@ -564,15 +577,71 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
                 const float mine = (lane & 3u) == 0 ? u0 : (lane & 3u) == 1 ? u1 : (lane & 3u) == 2 ? u2 : u3;
                 pin.opt_need = (sum_all - mine) * f_less * pin.max_mult * 1.0001f;
                 pin.count_bound = D->bound[lane & 3u];  // (0 beyond the request's parts: such a count does not occur)
+                pin.lev_bits = lev_bits, pin.lev_words = lev_words, pin.ones_row = a.ones_row, pin.zeros_row = a.zeros_row;
 #pragma unroll
                 for (uint32_t l = 0; l < kFastMaxLeaves; ++l) pin.part_terms[l] = __ballot_sync(0xFFFFFFFFu, lane < nt && my_part == l);
             }
+            // terms are grouped by part: bit t = term t is the last term of its part
+            const uint32_t last_mask = __ballot_sync(0xFFFFFFFFu, lane < nt && (lane + 1u == nt || S.term_part[lane + 1u] != S.term_part[lane]));
             Prune pr = compute_prune(S, pin, flags, tau, lane);
             uint32_t cnt = 0, ncand = 0;
+            bool seeding = false;
+            // candidates of one step: `cm` = anchors that pass the word-parallel tests
+            auto candidates = [&](uint32_t w4, const uint4& cm) {
+                if (__ballot_sync(0xFFFFFFFFu, any4(cm)) == 0) return;
+#pragma unroll 1
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    uint32_t m = c4 == 0 ? cm.x : c4 == 1 ? cm.y : c4 == 2 ? cm.z : cm.w;
+                    while (__ballot_sync(0xFFFFFFFFu, m != 0)) {
+                        bool flag = m != 0;
+                        const uint32_t bp = flag ? (uint32_t)__ffs((int)m) - 1u : 0u;
+                        const uint32_t idx = (w4 * 4u + (uint32_t)c4) * 32u + bp;
+                        m &= m - 1u;
+                        // Second stage: this anchor's bound from the terms it really has (their words come from L1 now).
+                        if (flag && pr.tau_score > 0.0f) {
+                            float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+#pragma unroll 1
+                            for (uint32_t t = 0; t < nt; ++t)
+                                if ((__ldg(S.term_bits[t] + (idx >> 5)) >> bp) & 1u) {
+                                    const uint32_t part = S.term_part[t];
+                                    const float ub = S.term_ub[t];
+                                    if (part == 0) v0 = fmaxf(v0, ub);
+                                    else if (part == 1) v1 = fmaxf(v1, ub);
+                                    else if (part == 2) v2 = fmaxf(v2, ub);
+                                    else v3 = fmaxf(v3, ub);
+                                }
+                            const uint32_t np = (v0 > 0.0f) + (v1 > 0.0f) + (v2 > 0.0f) + (v3 > 0.0f);
+                            const float sum = v0 + v1 + v2 + v3;
+                            const float B = (L == 1 ? sum : sum * (float)(np * np)) * 1.00001f;
+                            if (flags & kFastBoost) {
+                                if (B * pin.max_mult < pr.tau_score) flag = false;
+                                else {
+                                    const int lo = deepest_level(S, B, pr.tau_score);
+                                    if (lo >= 0) flag = (__ldg(lev_bits + (size_t)lo * lev_words + (idx >> 5)) >> bp) & 1u;
+                                }
+                            } else if (B * 1.00001f < pr.tau_score) {
+                                flag = false;
+                            }
+                        }
+                        // anchors with entries belong to the entry pass above (it knows their entry scores)
+                        if (flag && n_ent) {
+                            bool has = hash_lookup(S, idx) != 0u;
+                            if (L > 1) has = has || hash_lookup(S, idx | (1u << kPartShift)) != 0u;
+                            if (L > 2) has = has || hash_lookup(S, idx | (2u << kPartShift)) != 0u;
+                            if (L > 3) has = has || hash_lookup(S, idx | (3u << kPartShift)) != 0u;
+                            flag = !has;
+                        }
+                        if (enqueue(C, S, lane, q, flag, rel0 + idx, 0.0f, 0.0f, 0.0f, 0.0f, qn, ncand)) {
+                            tau = __ldcg(a.tau + q);
+                            if (!seeding) pr = compute_prune(S, pin, flags, tau, lane);  // the rest of the sweep prunes against the tightened threshold
+                        }
+                    }
+                }
+            };
 
             // ---- anchors with entries: bounded one by one (entry scores are known exactly, plane parts by their bound)
+            uint32_t own = 0;  // bit r: this lane's entry of round r is the first of its (anchor, part)
             if (n_ent) {
-                uint32_t own = 0;  // bit r: this lane's entry of round r is the first of its (anchor, part)
 #pragma unroll 1
                 for (uint32_t r = 0; r * 32u < n_ent; ++r) {
                     const uint32_t j = r * 32u + lane;
@@ -584,6 +653,37 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
                     }
                 }
                 __syncwarp();
+            }
+
+            // ---- a request without a threshold yet (its first item): seed pass.  Evaluating anchors in anchor order until the
+            // threshold has converged costs hundreds of evaluations; the anchors that have every part with plane terms present
+            // (for a single such part: its anchors in the top 1/64 of the boost column) are few and contain good hits, so they
+            // go first, until a first batch of them has given the request a threshold.  Nothing is counted here, and the sweep
+            // below reaches the same anchors again: merging is idempotent.
+            const uint32_t n_planed = (pin.part_terms[0] != 0u) + (pin.part_terms[1] != 0u) + (pin.part_terms[2] != 0u) + (pin.part_terms[3] != 0u);
+            if (pr.tau_score == 0.0f && nt > 0 && (n_planed >= 2 || (flags & kFastBoost))) {
+                seeding = true;
+                const uint4* seed_lw = n_planed >= 2 ? nullptr : reinterpret_cast<const uint4*>(lev_bits + (size_t)5 * lev_words);
+                const uint32_t nw4 = nw >> 2;
+#pragma unroll 1
+                for (uint32_t w4 = lane; w4 < nw4; w4 += 32) {
+                    uint4 cm = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), cur = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+                    for (uint32_t t = 0; t < nt; ++t) {
+                        or4(cur, __ldg(reinterpret_cast<const uint4*>(S.term_bits[t]) + w4));
+                        if ((last_mask >> t) & 1u) and4(cm, cur), cur = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    if (seed_lw && any4(cm)) and4(cm, __ldg(seed_lw + w4));
+                    candidates(w4, cm);
+                    if (tau != 0) break;  // a first batch has been evaluated and the request has a threshold: enough
+                }
+                if (qn) drain(C, &S, lane, 0, qn), qn = 0;
+                seeding = false;
+                tau = __ldcg(a.tau + q);
+                pr = compute_prune(S, pin, flags, tau, lane);
+            }
+
+            if (n_ent) {
 #pragma unroll 1
                 for (uint32_t r = 0; r * 32u < n_ent; ++r) {
                     const uint32_t j = r * 32u + lane;
@@ -670,164 +770,88 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
                 // nothing but entries
             } else if (count_from_table) {
                 // the hit count is the plane's count of the group's tiles (+ the entry anchors outside it, counted above)
-                const uint32_t tiles_total = words >> (kPlaneTileLog2 - 5), t0 = g * a.group_tiles;
-                if (lane < a.group_tiles && t0 + lane < tiles_total) cnt += __ldg(a.planes.tcount + (size_t)D->plane[0] * tiles_total + t0 + lane);
+                const uint32_t tiles_total = words >> (kPlaneTileLog2 - 5);
+                if (lane < n_item_tiles && t0 + lane < tiles_total) cnt += __ldg(a.planes.tcount + (size_t)D->plane[0] * tiles_total + t0 + lane);
             } else {
                 const uint4* tp0 = reinterpret_cast<const uint4*>(S.term_bits[0]);
                 const uint4* tp1 = reinterpret_cast<const uint4*>(S.term_bits[nt > 1 ? 1 : 0]);
                 const uint4* tp2 = reinterpret_cast<const uint4*>(S.term_bits[nt > 2 ? 2 : 0]);
                 const uint4* tp3 = reinterpret_cast<const uint4*>(S.term_bits[nt > 3 ? 3 : 0]);
-                const uint32_t tq0 = S.term_part[0], tq1 = S.term_part[nt > 1 ? 1 : 0], tq2 = S.term_part[nt > 2 ? 2 : 0], tq3 = S.term_part[nt > 3 ? 3 : 0];
-                // candidates of one step: `cm` = anchors that pass the word-parallel tests
-                auto candidates = [&](uint32_t w4, const uint4& cm) {
-                    if (__ballot_sync(0xFFFFFFFFu, any4(cm)) == 0) return;
-#pragma unroll 1
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        uint32_t m = c4 == 0 ? cm.x : c4 == 1 ? cm.y : c4 == 2 ? cm.z : cm.w;
-                        while (__ballot_sync(0xFFFFFFFFu, m != 0)) {
-                            bool flag = m != 0;
-                            const uint32_t bp = flag ? (uint32_t)__ffs((int)m) - 1u : 0u;
-                            const uint32_t idx = (w4 * 4u + (uint32_t)c4) * 32u + bp;
-                            m &= m - 1u;
-                            // Second stage: this anchor's bound from the terms it really has (their words come from L1 now).
-                            if (flag && pr.tau_score > 0.0f) {
-                                float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
-#pragma unroll 1
-                                for (uint32_t t = 0; t < nt; ++t)
-                                    if ((__ldg(S.term_bits[t] + (idx >> 5)) >> bp) & 1u) {
-                                        const uint32_t part = S.term_part[t];
-                                        const float ub = S.term_ub[t];
-                                        if (part == 0) v0 = fmaxf(v0, ub);
-                                        else if (part == 1) v1 = fmaxf(v1, ub);
-                                        else if (part == 2) v2 = fmaxf(v2, ub);
-                                        else v3 = fmaxf(v3, ub);
-                                    }
-                                const uint32_t np = (v0 > 0.0f) + (v1 > 0.0f) + (v2 > 0.0f) + (v3 > 0.0f);
-                                const float sum = v0 + v1 + v2 + v3;
-                                const float B = (L == 1 ? sum : sum * (float)(np * np)) * 1.00001f;
-                                if (flags & kFastBoost) {
-                                    if (B * pin.max_mult < pr.tau_score) flag = false;
-                                    else {
-                                        const int lo = deepest_level(S, B, pr.tau_score);
-                                        if (lo >= 0) flag = (__ldg(lev_bits + (size_t)lo * lev_words + (idx >> 5)) >> bp) & 1u;
-                                    }
-                                } else if (B * 1.00001f < pr.tau_score) {
-                                    flag = false;
-                                }
-                            }
-                            // anchors with entries belong to the entry pass above (it knows their entry scores)
-                            if (flag && n_ent) {
-                                bool has = hash_lookup(S, idx) != 0u;
-                                if (L > 1) has = has || hash_lookup(S, idx | (1u << kPartShift)) != 0u;
-                                if (L > 2) has = has || hash_lookup(S, idx | (2u << kPartShift)) != 0u;
-                                if (L > 3) has = has || hash_lookup(S, idx | (3u << kPartShift)) != 0u;
-                                flag = !has;
-                            }
-                            if (enqueue(C, S, lane, q, flag, rel0 + idx, 0.0f, 0.0f, 0.0f, 0.0f, qn, ncand)) {
-                                tau = __ldcg(a.tau + q);
-                                pr = compute_prune(S, pin, flags, tau, lane);  // the rest of the sweep prunes against the tightened threshold
-                            }
-                        }
-                    }
-                };
                 const uint4 ones4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-                auto level_row = [&](int lv) { return reinterpret_cast<const uint4*>(lev_bits + (size_t)(lv > 0 ? lv : 0) * lev_words); };
-                // `v`: the word of term t, `lw` the word of the boost level the term's anchors must be inside.  The word joins
-                // its part's presence word (r*) and, restricted to that level, the part's word of anchors that can matter (p*).
-                auto place = [&](uint32_t t, uint32_t part, const uint4& v, const uint4& lw, uint4& r0, uint4& r1, uint4& r2, uint4& r3, uint4& p0, uint4& p1, uint4& p2, uint4& p3) {
-                    const bool ok = (pr.allow >> t) & 1u;
-                    const uint4 x = make_uint4(v.x & lw.x, v.y & lw.y, v.z & lw.z, v.w & lw.w);
-                    if (part == 0) {
-                        or4(r0, v);
-                        if (ok) or4(p0, x);
-                    } else if (part == 1) {
-                        or4(r1, v);
-                        if (ok) or4(p1, x);
-                    } else if (part == 2) {
-                        or4(r2, v);
-                        if (ok) or4(p2, x);
-                    } else {
-                        or4(r3, v);
-                        if (ok) or4(p3, x);
-                    }
-                };
-                // Anchors that can matter by their number of present parts: exactly n parts -> inside count_lev[n - 1].
-                auto by_count = [&](uint32_t w4, const uint4& r0, const uint4& r1, const uint4& r2, const uint4& r3) {
-                    uint4 ones = r0, twos = make_uint4(0u, 0u, 0u, 0u), fours = twos;
-                    auto add_part = [&](const uint4& x) {
-                        uint32_t cy, cy2;
-                        cy = ones.x & x.x, ones.x ^= x.x, cy2 = twos.x & cy, twos.x ^= cy, fours.x |= cy2;
-                        cy = ones.y & x.y, ones.y ^= x.y, cy2 = twos.y & cy, twos.y ^= cy, fours.y |= cy2;
-                        cy = ones.z & x.z, ones.z ^= x.z, cy2 = twos.z & cy, twos.z ^= cy, fours.z |= cy2;
-                        cy = ones.w & x.w, ones.w ^= x.w, cy2 = twos.w & cy, twos.w ^= cy, fours.w |= cy2;
-                    };
-                    add_part(r1), add_part(r2), add_part(r3);
-                    uint4 out = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                    for (int i2 = 0; i2 < (int)kFastMaxLeaves; ++i2) {
-                        const int lv = S.count_lev[i2];
-                        if (lv == -2) continue;
-                        uint4 ex;  // anchors with exactly i2 + 1 parts present
-                        if (i2 == 0) ex = make_uint4(ones.x & ~twos.x & ~fours.x, ones.y & ~twos.y & ~fours.y, ones.z & ~twos.z & ~fours.z, ones.w & ~twos.w & ~fours.w);
-                        else if (i2 == 1) ex = make_uint4(twos.x & ~ones.x & ~fours.x, twos.y & ~ones.y & ~fours.y, twos.z & ~ones.z & ~fours.z, twos.w & ~ones.w & ~fours.w);
-                        else if (i2 == 2) ex = make_uint4(ones.x & twos.x, ones.y & twos.y, ones.z & twos.z, ones.w & twos.w);
-                        else ex = fours;
-                        if (lv >= 0 && any4(ex)) and4(ex, __ldg(level_row(lv) + w4));
-                        or4(out, ex);
-                    }
-                    return out;
-                };
-                auto required = [&](uint4 cm, const uint4& p0, const uint4& p1, const uint4& p2, const uint4& p3) {
-                    if (!(pr.optional & 1u)) and4(cm, p0);
-                    if (!(pr.optional & 2u)) and4(cm, p1);
-                    if (!(pr.optional & 4u)) and4(cm, p2);
-                    if (!(pr.optional & 8u)) and4(cm, p3);
-                    return cm;
-                };
-                // One step per iteration: the plane words of up to four terms and the boost level words they are restricted to
-                // are requested before any is used, so up to eight independent 128-bit loads are in flight per lane (a load-use
-                // chain per term would expose the L2 latency once per term).
+                // One step per iteration: the plane words of up to four terms and the rows they are restricted to (a boost level,
+                // all ones, or all zeros for a term that cannot matter: no branches) are requested before any is used, so up to
+                // eight independent 128-bit loads are in flight per lane.  Terms are grouped by part: a running OR over a part's
+                // restricted words is AND-ed into the candidate word when the part's last term has been seen (if the part must
+                // be present), and -- when parts may be absent -- the part's presence word goes into a bit-sliced counter, so
+                // that anchors are also held against the boost level their number of present parts needs.
                 const uint32_t nw4 = nw >> 2;  // a multiple of 64
                 swept_cold = pr.tau_score == 0.0f;
 #pragma unroll 1
                 for (uint32_t w4 = lane; w4 < nw4; w4 += 32) {
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                    const int tl0 = S.term_lev[0], tl1 = S.term_lev[1], tl2 = S.term_lev[2], tl3 = S.term_lev[3];  // (they move with the threshold)
                     const uint4 a0 = __ldg(tp0 + w4);
                     uint4 a1 = z, a2 = z, a3 = z;
                     if (nt > 1) a1 = __ldg(tp1 + w4);
                     if (nt > 2) a2 = __ldg(tp2 + w4);
                     if (nt > 3) a3 = __ldg(tp3 + w4);
-                    uint4 la0 = ones4, la1 = ones4, la2 = ones4, la3 = ones4;
-                    if (pr.possible) {
-                        if (tl0 >= 0) la0 = __ldg(level_row(tl0) + w4);
-                        if (nt > 1 && tl1 >= 0) la1 = __ldg(level_row(tl1) + w4);
-                        if (nt > 2 && tl2 >= 0) la2 = __ldg(level_row(tl2) + w4);
-                        if (nt > 3 && tl3 >= 0) la3 = __ldg(level_row(tl3) + w4);
-                    }
-                    uint4 ra0 = z, ra1 = z, ra2 = z, ra3 = z, pa0 = z, pa1 = z, pa2 = z, pa3 = z;
-                    place(0, tq0, a0, la0, ra0, ra1, ra2, ra3, pa0, pa1, pa2, pa3);
-                    if (nt > 1) place(1, tq1, a1, la1, ra0, ra1, ra2, ra3, pa0, pa1, pa2, pa3);
-                    if (nt > 2) place(2, tq2, a2, la2, ra0, ra1, ra2, ra3, pa0, pa1, pa2, pa3);
-                    if (nt > 3) place(3, tq3, a3, la3, ra0, ra1, ra2, ra3, pa0, pa1, pa2, pa3);
+                    if (!pr.possible) {  // nothing can matter any more: count only
+                        uint4 any = make_uint4(a0.x | a1.x | a2.x | a3.x, a0.y | a1.y | a2.y | a3.y, a0.z | a1.z | a2.z | a3.z, a0.w | a1.w | a2.w | a3.w);
 #pragma unroll 1
-                    for (uint32_t t = 4; t < nt; ++t) {  // requests with more than four plane terms
-                        const int tl = S.term_lev[t];
-                        const uint4 va = __ldg(reinterpret_cast<const uint4*>(S.term_bits[t]) + w4);
-                        uint4 la = ones4;
-                        if (pr.possible && tl >= 0) la = __ldg(level_row(tl) + w4);
-                        place(t, S.term_part[t], va, la, ra0, ra1, ra2, ra3, pa0, pa1, pa2, pa3);
+                        for (uint32_t t = 4; t < nt; ++t) or4(any, __ldg(reinterpret_cast<const uint4*>(S.term_bits[t]) + w4));
+                        cnt += popc4(any);
+                        continue;
                     }
-                    const uint4 any = make_uint4(ra0.x | ra1.x | ra2.x | ra3.x, ra0.y | ra1.y | ra2.y | ra3.y, ra0.z | ra1.z | ra2.z | ra3.z, ra0.w | ra1.w | ra2.w | ra3.w);
+                    const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(S.term_lw[0]) + w4);
+                    uint4 l1 = z, l2 = z, l3 = z;
+                    if (nt > 1) l1 = __ldg(reinterpret_cast<const uint4*>(S.term_lw[1]) + w4);
+                    if (nt > 2) l2 = __ldg(reinterpret_cast<const uint4*>(S.term_lw[2]) + w4);
+                    if (nt > 3) l3 = __ldg(reinterpret_cast<const uint4*>(S.term_lw[3]) + w4);
+                    const uint32_t req_mask = (pr.optional & 1u ? 0u : pin.part_terms[0]) | (pr.optional & 2u ? 0u : pin.part_terms[1]) | (pr.optional & 4u ? 0u : pin.part_terms[2]) |
+                                              (pr.optional & 8u ? 0u : pin.part_terms[3]);  // bit t: term t's part must be present
+                    uint4 any = z, anyx = z, cur = z, craw = z, cm = ones4, ones = z, twos = z, fours = z;
+                    auto combine = [&](uint32_t t, const uint4& v, const uint4& lw) {
+                        const uint4 x = make_uint4(v.x & lw.x, v.y & lw.y, v.z & lw.z, v.w & lw.w);
+                        or4(any, v), or4(cur, x), or4(anyx, x);
+                        if (pr.by_count) or4(craw, v);
+                        if ((last_mask >> t) & 1u) {
+                            if ((req_mask >> t) & 1u) and4(cm, cur);
+                            cur = z;
+                            if (pr.by_count) {  // one more part present: ones / twos / fours count the parts per anchor
+                                uint32_t cy, cy2;
+                                cy = ones.x & craw.x, ones.x ^= craw.x, cy2 = twos.x & cy, twos.x ^= cy, fours.x |= cy2;
+                                cy = ones.y & craw.y, ones.y ^= craw.y, cy2 = twos.y & cy, twos.y ^= cy, fours.y |= cy2;
+                                cy = ones.z & craw.z, ones.z ^= craw.z, cy2 = twos.z & cy, twos.z ^= cy, fours.z |= cy2;
+                                cy = ones.w & craw.w, ones.w ^= craw.w, cy2 = twos.w & cy, twos.w ^= cy, fours.w |= cy2;
+                                craw = z;
+                            }
+                        }
+                    };
+                    combine(0, a0, l0);
+                    if (nt > 1) combine(1, a1, l1);
+                    if (nt > 2) combine(2, a2, l2);
+                    if (nt > 3) combine(3, a3, l3);
+#pragma unroll 1
+                    for (uint32_t t = 4; t < nt; ++t)  // requests with more than four plane terms
+                        combine(t, __ldg(reinterpret_cast<const uint4*>(S.term_bits[t]) + w4), __ldg(reinterpret_cast<const uint4*>(S.term_lw[t]) + w4));
                     cnt += popc4(any);
-                    if (pr.possible) {
-                        // some allowed term present, every part that must be present present through such a term ...
-                        uint4 cm = make_uint4(pa0.x | pa1.x | pa2.x | pa3.x, pa0.y | pa1.y | pa2.y | pa3.y, pa0.z | pa1.z | pa2.z | pa3.z, pa0.w | pa1.w | pa2.w | pa3.w);
-                        cm = required(cm, pa0, pa1, pa2, pa3);
-                        // ... and, when parts may be absent, inside the level its part count needs
-                        if (pr.by_count && any4(cm)) and4(cm, by_count(w4, ra0, ra1, ra2, ra3));
-                        candidates(w4, cm);
+                    and4(cm, anyx);  // some term that can matter is present, every part that must be present is present through such a term ...
+                    if (pr.by_count && any4(cm)) {  // ... and the anchor is inside the level its number of present parts needs
+                        uint4 ok = z;
+#pragma unroll
+                        for (int i2 = 0; i2 < (int)kFastMaxLeaves; ++i2) {
+                            const int lv = S.count_lev[i2];
+                            if (lv == -2) continue;
+                            uint4 ex;  // anchors with exactly i2 + 1 parts present
+                            if (i2 == 0) ex = make_uint4(ones.x & ~twos.x & ~fours.x, ones.y & ~twos.y & ~fours.y, ones.z & ~twos.z & ~fours.z, ones.w & ~twos.w & ~fours.w);
+                            else if (i2 == 1) ex = make_uint4(twos.x & ~ones.x & ~fours.x, twos.y & ~ones.y & ~fours.y, twos.z & ~ones.z & ~fours.z, twos.w & ~ones.w & ~fours.w);
+                            else if (i2 == 2) ex = make_uint4(ones.x & twos.x, ones.y & twos.y, ones.z & twos.z, ones.w & twos.w);
+                            else ex = fours;
+                            if (lv >= 0 && any4(ex)) and4(ex, __ldg(reinterpret_cast<const uint4*>(lev_bits + (size_t)lv * lev_words) + w4));
+                            or4(ok, ex);
+                        }
+                        and4(cm, ok);
                     }
+                    candidates(w4, cm);
                 }
             }
             for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);

@@ -70,17 +70,49 @@ __device__ __forceinline__ void tile_totals(const ItemScanArgs& a, const QueryPr
     }
 }
 
+// Entries (postings of non-plane terms) of request `qp` in tile t, over its parts; false when the tile cannot take the
+// plane path (a frequent term without a plane, or entries beyond the 32-bit index).
+__device__ __forceinline__ bool tile_entries(const ItemScanArgs& a, const QueryProgram& qp, uint32_t t, uint32_t& n_ent) {
+    n_ent = 0;
+    bool ok = true;
+    for (uint32_t l = 0; l < qp.n_leaves; ++l) {
+        const PartSlices ps = a.slices[a.leaf_part[qp.leaf_begin + l]];
+        for (uint32_t r = 0; r < ps.n_dense; ++r)
+            if (a.g_plane[ps.m_begin + r] == kNoValue) {
+                const uint32_t* trow = dense_row(a.toff, a.plane_tprefix, a.g_row, a.g_plane, ps.m_begin + r, a.n_tiles);
+                if (trow[t + 1] != trow[t]) ok = false;
+            }
+        if (ps.n_match != ps.n_dense) {
+            const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
+            n_ent += brow[t + 1] - brow[t];
+            if (ps.sparse_base + brow[t + 1] > 0xFFFFFFFFull) ok = false;
+        }
+    }
+    return ok;
+}
+
+// The plane-path item of request `qp` over tiles [t0, t1): the bucket ranges of its parts.
+__device__ __forceinline__ FastItem make_fast_item(const ItemScanArgs& a, const QueryProgram& qp, uint32_t q, uint32_t t0, uint32_t t1) {
+    FastItem fi;
+    fi.q = q, fi.tiles = t0 | ((t1 - t0) << 24);
+    for (uint32_t l = 0; l < kFastMaxLeaves; ++l) fi.n[l] = 0, fi.begin[l] = 0;
+    for (uint32_t l = 0; l < qp.n_leaves && l < kFastMaxLeaves; ++l) {
+        const PartSlices ps = a.slices[a.leaf_part[qp.leaf_begin + l]];
+        if (ps.n_match != ps.n_dense) {
+            const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
+            fi.n[l] = (uint16_t)(brow[t1] - brow[t0]), fi.begin[l] = (uint32_t)(ps.sparse_base + brow[t0]);
+        }
+    }
+    return fi;
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
     __shared__ uint32_t s_warp_items[8], s_warp_slices[8];
     __shared__ unsigned long long s_base_items, s_base_slices;
     const unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t g = 0, q = 0, t0 = 0, t1 = 0;
-    bool fast_item = false, general = false;
-    FastItem fi;
-    fi.q = 0, fi.group = 0;
-    for (uint32_t l = 0; l < kFastMaxLeaves; ++l) fi.n[l] = 0, fi.begin[l] = 0;
+    uint32_t g = 0xFFFFFFFFu, q = 0, t0 = 0, t1 = 0;
     QueryProgram qp;
     qp.active = 0, qp.n_leaves = 0;
     if (i < a.n_pairs_total) {
@@ -88,53 +120,102 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
         t0 = g * a.group_tiles, t1 = min(a.n_tiles, t0 + a.group_tiles);
         qp = a.queries[q];
     }
-    if (qp.active && qp.n_leaves) {
-        const bool fastq = a.fast != nullptr && (a.fast[q].flags & kFastOk) != 0;
-        bool fits = fastq, plane_hit = false;
-        if (fastq) {
-            uint32_t ent_post = 0;
-            for (uint32_t l = 0; l < qp.n_leaves; ++l) {
-                const PartSlices ps = a.slices[a.leaf_part[qp.leaf_begin + l]];
-                for (uint32_t r = 0; r < ps.n_dense; ++r) {
-                    const uint32_t* trow = dense_row(a.toff, a.plane_tprefix, a.g_row, a.g_plane, ps.m_begin + r, a.n_tiles);
-                    const uint32_t n = trow[t1] - trow[t0];
-                    if (a.g_plane[ps.m_begin + r] != kNoValue) plane_hit = plane_hit || n != 0;
-                    else if (n) fits = false;  // a frequent term without a plane: general path
-                }
-                if (ps.n_match != ps.n_dense) {
-                    const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
-                    const uint32_t s = brow[t0], n = brow[t1] - s;
-                    ent_post += n;
-                    if (l < kFastMaxLeaves) {
-                        const unsigned long long at = ps.sparse_base + s;
-                        if (at + n > 0xFFFFFFFFull) fits = false;
-                        fi.n[l] = (uint16_t)min(n, 0xFFFFu), fi.begin[l] = (uint32_t)at;
-                    }
+    const bool live = qp.active && qp.n_leaves;
+    const bool fastq = live && a.fast != nullptr && (a.fast[q].flags & kFastOk) != 0;
+    FastItem whole_item;
+    whole_item.q = 0, whole_item.tiles = 0;
+    bool cut_any_plane = false;
+
+    // ---- plane-path items.  The pair is one item when the entries of the whole group fit; otherwise the group is cut
+    // greedily into runs of tiles that fit (a single tile that does not fit, or cannot take the plane path at all,
+    // becomes a general item).  Both passes make the same cuts.
+    uint32_t my_fast = 0;
+    unsigned long long general_tiles = 0;  // bit (t - t0): tile t goes to the general path
+    bool whole = false;                    // the pair is a single item over the whole group (the common case)
+    if (fastq) {
+        bool any_plane = false, ok = true;
+        uint32_t group_ent = 0;
+        for (uint32_t l = 0; l < qp.n_leaves; ++l) {
+            const PartSlices ps = a.slices[a.leaf_part[qp.leaf_begin + l]];
+            for (uint32_t r = 0; r < ps.n_dense; ++r) {
+                const uint32_t* trow = dense_row(a.toff, a.plane_tprefix, a.g_row, a.g_plane, ps.m_begin + r, a.n_tiles);
+                if (trow[t1] != trow[t0]) {
+                    if (a.g_plane[ps.m_begin + r] != kNoValue) any_plane = true;
+                    else ok = false;  // a frequent term without a plane
                 }
             }
-            fits = fits && ent_post <= kGroupMaxEntries;
-            fast_item = fits && (plane_hit || ent_post != 0);
+            if (ps.n_match != ps.n_dense) {
+                const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
+                group_ent += brow[t1] - brow[t0];
+                if (ps.sparse_base + brow[t1] > 0xFFFFFFFFull) ok = false;
+            }
         }
-        general = !fits;
+        if (ok && group_ent <= kGroupMaxEntries) {
+            whole = true;
+            my_fast = (any_plane || group_ent != 0) ? 1u : 0u;
+            if (FILL && my_fast) whole_item = make_fast_item(a, qp, q, t0, t1);
+        } else {
+            // cut the group greedily into runs of tiles whose entries fit (both passes make the same cuts)
+            uint32_t run_begin = t0, run_ent = 0;
+            for (uint32_t t = t0; t <= t1; ++t) {
+                uint32_t ne = 0;
+                bool tile_ok = true;
+                if (t < t1) tile_ok = tile_entries(a, qp, t, ne);
+                const bool bad = t < t1 && (!tile_ok || ne > kGroupMaxEntries);
+                if (t == t1 || bad || run_ent + ne > kGroupMaxEntries) {  // close the run [run_begin, t)
+                    if (t > run_begin && (any_plane || run_ent != 0)) my_fast += 1;
+                    run_begin = t, run_ent = 0;
+                }
+                if (bad) general_tiles |= 1ull << (t - t0), run_begin = t + 1;
+                else run_ent += ne;
+            }
+            cut_any_plane = any_plane;
+        }
+    } else if (live) {
+        general_tiles = ~0ull;
     }
-
-    // ---- plane-path items: per-group cursors, one atomic per (warp, group)
     {
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, fast_item ? g : 0xFFFFFFFFu);
-        const int leader = __ffs((int)peers) - 1;
+        // per-group cursors, one atomic per (warp, group): lanes are group-major, so the lanes of a group are a contiguous run
+        uint32_t incl = my_fast;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((int)lane >= o) incl += y;
+        }
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, g);
+        const int leader = __ffs((int)peers) - 1, tail = 31 - __clz((int)peers);
+        const uint32_t before_leader = __shfl_sync(0xFFFFFFFFu, incl - my_fast, leader);
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, tail) - before_leader;
         uint32_t base_i = 0;
-        if (fast_item && (int)lane == leader) base_i = atomicAdd(a.fast_item_cursor + g, (uint32_t)__popc(peers));
+        if ((int)lane == leader && total && g != 0xFFFFFFFFu) base_i = atomicAdd(a.fast_item_cursor + g, total);
         base_i = __shfl_sync(0xFFFFFFFFu, base_i, leader);
-        if (FILL && fast_item) {
-            fi.q = q, fi.group = g;
-            a.fast_items[a.fast_item_begin[g] + base_i + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = fi;
+        if (FILL && my_fast) {
+            FastItem* out = a.fast_items + a.fast_item_begin[g] + base_i + (incl - my_fast - before_leader);
+            if (whole) {
+                *out = whole_item;
+            } else {
+                uint32_t run_begin = t0, run_ent = 0;
+                for (uint32_t t = t0; t <= t1; ++t) {
+                    uint32_t ne = 0;
+                    bool tile_ok = true;
+                    if (t < t1) tile_ok = tile_entries(a, qp, t, ne);
+                    const bool bad = t < t1 && (!tile_ok || ne > kGroupMaxEntries);
+                    if (t == t1 || bad || run_ent + ne > kGroupMaxEntries) {
+                        if (t > run_begin && (cut_any_plane || run_ent != 0)) *out++ = make_fast_item(a, qp, q, run_begin, t);
+                        run_begin = t, run_ent = 0;
+                    }
+                    if (bad) run_begin = t + 1;
+                    else run_ent += ne;
+                }
+            }
         }
     }
 
-    // ---- general items: one per non-empty tile of the pair; block-ordered reservation, exclusive prefix of (items, slices) over the block
+    // ---- general items: one per non-empty tile that does not take the plane path; block-ordered reservation, exclusive
+    // prefix of (items, slices) over the block
     uint32_t my_items = 0, my_slices = 0;
-    if (general)
+    if (general_tiles)
         for (uint32_t t = t0; t < t1; ++t) {
+            if (!((general_tiles >> (t - t0)) & 1ull)) continue;
             uint32_t np, ns;
             tile_totals(a, qp, t, np, ns);
             if (np) my_items += 1, my_slices += ns;
@@ -161,6 +242,7 @@ __global__ void __launch_bounds__(256) item_scan_kernel(ItemScanArgs a) {
     unsigned long long item_at = s_base_items + wi + xi - my_items;
     unsigned long long slice_at = s_base_slices + ws + xs - my_slices;
     for (uint32_t t = t0; t < t1; ++t) {
+        if (!((general_tiles >> (t - t0)) & 1ull)) continue;
         uint32_t all_post, n_slices;
         tile_totals(a, qp, t, all_post, n_slices);
         if (!all_post) continue;

@@ -348,6 +348,8 @@ struct PlaneSetDev {  // term planes of every postings store of the shard (head 
     DevBuf<PlaneInfo> info;
     DevBuf<uint32_t> tcount;  // [n_planes][tiles]
     DevBuf<uint32_t> tprefix; // [n_planes][tiles + 1]
+    DevBuf<uint32_t> const_rows;  // kConstRowWords ones, then as many zeros (rows the sweep ANDs unrestricted / excluded terms with)
+    static const uint32_t kConstRowWords = 32u << (kPlaneTileLog2 - 5);
     PlaneSetView view() const { return PlaneSetView{bits.p, score.p, wmax.p, info.p, tcount.p, tprefix.p, n_planes, n_head, words, 0u}; }
 };
 
@@ -697,11 +699,15 @@ struct DeviceIndex {
     }
 
     // Term planes: head planes for the terms with df >= span / 128 (at most kMaxHeadPlanes, bits + f16 scores), mid planes
-    // for the terms with df >= span / 4096 (bits only), at most kMaxPlanes in total, by descending df over all stores.
+    // for the terms with df >= span / 1024 (bits only), at most kMaxPlanes in total, by descending df over all stores.
     void build_planes() {
         const uint64_t span = anchor_hi - anchor_lo;
         if ((open_flags & kOpenNoPlanes) || span == 0 || span >= 0xFFFFFFFFull) return;
-        const uint64_t head_df = std::max<uint64_t>(1, span / 128), mid_df = std::max<uint64_t>(16, span / 4096);
+        uint64_t mid_div = 1024;
+#ifdef VELOCI_PROBES
+        if (const char* env = getenv("VELOCI_MID_DIV")) mid_div = (uint64_t)std::max(128, atoi(env));
+#endif
+        const uint64_t head_df = std::max<uint64_t>(1, span / 128), mid_df = std::max<uint64_t>(16, span / mid_div);
         struct Cand {
             uint64_t df;
             PostingsDev* store;
@@ -742,6 +748,9 @@ struct DeviceIndex {
         planes.tcount.alloc((size_t)n * (words >> (kPlaneTileLog2 - 5)));
         planes.tprefix.alloc((size_t)n * ((words >> (kPlaneTileLog2 - 5)) + 1));
         launch_plane_tile_counts(nullptr, planes.bits.p, n, words, planes.tcount.p, planes.tprefix.p);
+        planes.const_rows.alloc((size_t)2 * PlaneSetDev::kConstRowWords);
+        VDEV_CUDA(cudaMemset(planes.const_rows.p, 0xFF, (size_t)PlaneSetDev::kConstRowWords * 4));
+        VDEV_CUDA(cudaMemset(planes.const_rows.p + PlaneSetDev::kConstRowWords, 0, (size_t)PlaneSetDev::kConstRowWords * 4));
         std::vector<uint32_t> h_bad(n);
         VDEV_CUDA(cudaMemcpy(h_bad.data(), bad.p, n * 4, cudaMemcpyDeviceToHost));
         std::map<PostingsDev*, std::vector<uint32_t>> maps;

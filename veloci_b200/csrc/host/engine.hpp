@@ -404,8 +404,8 @@ struct Batch {
         }
         const uint64_t span = ix->anchor_hi - ix->anchor_lo;
         n_tiles = (uint32_t)((span + (1ull << tile_log2) - 1) >> tile_log2);
-        // plane-path items span `group_tiles` tiles (128 Ki anchors); without a plane path every tile is its own group
-        group_tiles = use_planes ? 16u : 1u;
+        // plane-path items span `group_tiles` tiles (256 Ki anchors); without a plane path every tile is its own group
+        group_tiles = use_planes ? 32u : 1u;
         if (const char* env = probe_env("VELOCI_GROUP_TILES")) group_tiles = use_planes ? (uint32_t)std::min(32, std::max(1, atoi(env))) : 1u;
         n_groups = (n_tiles + group_tiles - 1) / group_tiles;
         stride = std::max<uint32_t>(1, plan.max_k);
@@ -705,6 +705,7 @@ struct Batch {
         a.sparse = d_sparse.p, a.planes = ix->planes.view();
         a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
         a.group_tiles = group_tiles, a.group_begin = g0, a.group_end = g1;
+        a.ones_row = ix->planes.const_rows.p, a.zeros_row = ix->planes.const_rows.p + PlaneSetDev::kConstRowWords;
         a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
         a.stats = d_counters.p + 8;
         a.work_counter = d_counters.p + 10 + stage;
