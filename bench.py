@@ -421,6 +421,11 @@ def run_ours(args):
     import veloci_b200
     from veloci_b200 import build
 
+    # The one JSON line is the only thing that may reach stdout: native libraries (NCCL prints its version banner there)
+    # write to file descriptor 1 directly, so descriptor 1 is pointed at stderr for the run and the line goes to a saved copy.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     job = Job()
     if job.rank == 0:
         build.build_all()
@@ -451,7 +456,7 @@ def run_ours(args):
                 c5["roofline"] = roofline_of(c5, args.config5_docs, args.queries, job.world)
                 c5.pop("traffic_model", None), c5.pop("kernels_ms", None)
             line["config5"] = c5
-        print(json.dumps(line), flush=True)
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     job.close()
 
 

@@ -237,7 +237,7 @@ def test_kernel_profile_and_work_stats(gpu, sharded_corpus):
     b.execute()
     base = b.results_flat(10)
     times = b.profile_execute()
-    assert "plane_eval_first" in times and times["plane_eval_first"]["ms"] > 0 and "sparse_fill" in times
+    assert "plane_eval" in times and times["plane_eval"]["ms"] > 0 and "plane_seed" in times and "sparse_fill" in times
     again = b.results_flat(10)
     assert (again["ids"] == base["ids"]).all()
     w = b.work_stats()

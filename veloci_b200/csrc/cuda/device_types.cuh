@@ -92,7 +92,15 @@ struct ColumnLevels {
     uint32_t words;
     uint32_t pad;
     float thr[kBoostLevels];  // ascending
+    // Seed set: the shard's anchors whose value is in the top 1/8 of the column (>= thr[kSeedLevel]), by descending value, and every
+    // plane restricted to them (bit i of a plane's row = seed_anchor[i] is in the plane).  One pass over these rows -- an
+    // eighth of a plane sweep -- finds, for the whole shard, the well-boosted anchors that have every plane part of a
+    // request: their scores seed the request's threshold before the sweep starts (plane_seed_kernel).
+    const uint32_t* seed_anchor;  // relative to the shard
+    const uint32_t* seed_bits;    // [n_planes][seed_words]
+    uint32_t seed_n, seed_words;  // seed_words: 32-anchor words per row, a multiple of 128
 };
+static const uint32_t kSeedLevel = 2;
 
 static const uint32_t kPartPlaneSlots = 8;
 struct PartPlanes {  // plane-term matches of one search part (80 B)

@@ -244,6 +244,12 @@ struct PlaneArgs {
 };
 size_t plane_kernel_smem();
 void launch_plane_eval(cudaStream_t st, const PlaneArgs& a, int n_sms);
+// Index build: the planes restricted to a boost column's seed set (ColumnLevels::seed_bits).
+void launch_seed_compact(cudaStream_t st, const uint32_t* plane_bits, uint32_t n_planes, uint32_t words, const uint32_t* seed_anchor, uint32_t seed_n, uint32_t seed_words, uint32_t* out);
+// Threshold seeds: one warp per plane-path request sweeps the seed rows of its planes over the whole shard, scores the
+// anchors that have all its plane parts (plane contributions only: a lower bound of their score) and raises the
+// request's threshold to just below the k-th best of them.  Uses PlaneArgs' fast / planes / anchor_lo / tau.
+void launch_plane_seed(cudaStream_t st, const PlaneArgs& a, uint32_t n_queries, int n_sms);
 
 // Top groups of every facet histogram: block f writes the `top[f]` largest counts of facets[f] (count desc, value id
 // asc; zero counts never) to out_ids / out_counts [f * stride ...] and the number written to out_n[f].

@@ -878,7 +878,151 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
     }
 }
 
+// ---------------------------------------------------------------- threshold seeds
+__global__ void seed_compact_kernel(const uint32_t* __restrict__ plane_bits, uint32_t n_planes, uint32_t words, const uint32_t* __restrict__ seed_anchor, uint32_t seed_n,
+                                    uint32_t seed_words, uint32_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)n_planes * seed_words) return;
+    const uint32_t p = (uint32_t)(i / seed_words), cw = (uint32_t)(i % seed_words);
+    const uint32_t* row = plane_bits + (size_t)p * words;
+    uint32_t v = 0;
+    for (uint32_t b = 0; b < 32; ++b) {
+        const uint32_t j = cw * 32u + b;
+        if (j >= seed_n) break;
+        const uint32_t rel = seed_anchor[j];
+        v |= ((row[rel >> 5] >> (rel & 31u)) & 1u) << b;
+    }
+    out[i] = v;
+}
+
+void launch_seed_compact(cudaStream_t st, const uint32_t* plane_bits, uint32_t n_planes, uint32_t words, const uint32_t* seed_anchor, uint32_t seed_n, uint32_t seed_words, uint32_t* out) {
+    const uint64_t n = (uint64_t)n_planes * seed_words;
+    if (!n) return;
+    seed_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(plane_bits, n_planes, words, seed_anchor, seed_n, seed_words, out);
+    count_launch();
+}
+
+// Inserts the keys of the lanes in `mask` (at most kMergeGroup) into the warp's private top-k (S.merge[0, k), descending).
+__device__ __forceinline__ void seed_insert(WarpScratch& S, uint32_t lane, uint32_t k, unsigned long long key, uint32_t mask) {
+    const uint32_t cnt = __popc(mask);
+    if (mask & (1u << lane)) S.merge[k + __popc(mask & ((1u << lane) - 1u))] = key;
+    __syncwarp();
+    const uint32_t n = k + cnt;
+    unsigned long long mine[3];
+    uint32_t rank[3];
+#pragma unroll
+    for (uint32_t i = 0; i < 3; ++i) {
+        const uint32_t e = lane + 32u * i;
+        mine[i] = e < n ? S.merge[e] : 0ull, rank[i] = 0xFFFFFFFFu;
+        if (mine[i] != 0ull) {
+            uint32_t r = 0;
+            for (uint32_t j = 0; j < n; ++j) r += (S.merge[j] > mine[i]) || (S.merge[j] == mine[i] && j < e);
+            rank[i] = r;
+        }
+    }
+    __syncwarp();
+    for (uint32_t e = lane; e < k + kMergeGroup; e += 32) S.merge[e] = 0ull;
+    __syncwarp();
+#pragma unroll
+    for (uint32_t i = 0; i < 3; ++i)
+        if (rank[i] < k) S.merge[rank[i]] = mine[i];
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kPlaneThreads, 2) plane_seed_kernel(PlaneArgs a, uint32_t n_queries) {
+    extern __shared__ __align__(16) unsigned char plane_smem[];
+    __shared__ CtaContext s_ctx;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    WarpScratch& S = reinterpret_cast<WarpScratch*>(plane_smem)[warp];
+    const CtaContext* C = &s_ctx;
+    if (tid == 0) {
+        s_ctx.fast = a.fast, s_ctx.planes = a.planes;
+        s_ctx.heap = a.heap, s_ctx.tau = a.tau, s_ctx.lock = a.lock, s_ctx.heap_stride = a.heap_stride, s_ctx.anchor_lo = a.anchor_lo;
+    }
+    __syncthreads();
+    for (uint32_t q = blockIdx.x * kPlaneWarps + warp; q < n_queries; q += gridDim.x * kPlaneWarps) {
+        const FastDesc* __restrict__ D = a.fast + q;
+        const uint32_t flags = D->flags, nt = D->n_terms, k = D->k;
+        if (!(flags & kFastOk) || !(flags & kFastBoost) || nt == 0) continue;
+        const ColumnLevels* __restrict__ lev = D->fb_lev;
+        const uint32_t seed_n = lev->seed_n, seed_words = lev->seed_words;
+        if (seed_n == 0) continue;
+        __syncwarp();
+        for (uint32_t e = lane; e < k + kMergeGroup; e += 32) S.merge[e] = 0ull;
+        if (lane < nt) {
+            S.term_bits[lane] = lev->seed_bits + (size_t)D->plane[lane] * seed_words;
+            S.term_part[lane] = D->part[lane];
+        }
+        __syncwarp();
+        const uint32_t last_mask = __ballot_sync(0xFFFFFFFFu, lane < nt && (lane + 1u == nt || S.term_part[lane + 1u] != S.term_part[lane]));
+        uint32_t qn = 0, n_eval = 0;
+        const uint32_t max_eval = max(96u, 4u * k);  // the seed set is in descending boost order: the first anchors found are the best boosted
+        // evaluates the queued anchors (plane contributions only) and keeps the best k
+        auto flush = [&]() {
+            n_eval += qn;
+            unsigned long long key = 0;
+            if (lane < qn) key = eval_candidate(*C, S, lane, q);
+            uint32_t m = __ballot_sync(0xFFFFFFFFu, key != 0);
+            while (m) {
+                uint32_t part = m;
+                if (__popc(part) > (int)kMergeGroup) {
+                    uint32_t rest = part;
+                    for (uint32_t i = 0; i < kMergeGroup; ++i) rest &= rest - 1u;
+                    part &= ~rest;
+                }
+                m &= ~part;
+                seed_insert(S, lane, k, key, part);
+            }
+            qn = 0;
+        };
+#pragma unroll 1
+        for (uint32_t cw4 = lane; cw4 < (seed_words >> 2); cw4 += 32) {
+            uint4 cm = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), cur = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+            for (uint32_t t = 0; t < nt; ++t) {
+                or4(cur, __ldg(reinterpret_cast<const uint4*>(S.term_bits[t]) + cw4));
+                if ((last_mask >> t) & 1u) and4(cm, cur), cur = make_uint4(0u, 0u, 0u, 0u);
+            }
+            if (__ballot_sync(0xFFFFFFFFu, any4(cm)) == 0) continue;
+#pragma unroll 1
+            for (int c4 = 0; c4 < 4; ++c4) {
+                uint32_t m = c4 == 0 ? cm.x : c4 == 1 ? cm.y : c4 == 2 ? cm.z : cm.w;
+                while (__ballot_sync(0xFFFFFFFFu, m != 0)) {
+                    bool flag = m != 0;
+                    const uint32_t j = (cw4 * 4u + (uint32_t)c4) * 32u + (flag ? (uint32_t)__ffs((int)m) - 1u : 0u);
+                    m &= m - 1u;
+                    flag = flag && j < seed_n;
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, flag);
+                    if (qn + __popc(bal) > 32) flush();
+                    if (flag) {
+                        const uint32_t at = qn + __popc(bal & ((1u << lane) - 1u));
+                        S.cand_q[at] = q, S.cand_rel[at] = __ldg(lev->seed_anchor + j);
+                        S.cand_e[0][at] = 0.0f, S.cand_e[1][at] = 0.0f, S.cand_e[2][at] = 0.0f, S.cand_e[3][at] = 0.0f;
+                    }
+                    qn += __popc(bal);
+                    __syncwarp();
+                }
+            }
+            if (n_eval + qn >= max_eval) break;
+        }
+        if (qn) flush();
+        __syncwarp();
+        // the k-th best lower bound: every true score is at least its plane-only score, so the request's k-th best is at least
+        // this; the key just below it lets that very anchor through when the sweep evaluates it
+        if (lane == 0 && S.merge[k - 1] != 0ull) atomicMax(a.tau + q, S.merge[k - 1] - 1ull);
+        __syncwarp();
+    }
+}
+
 size_t plane_kernel_smem() { return sizeof(WarpScratch) * kPlaneWarps; }
+
+void launch_plane_seed(cudaStream_t st, const PlaneArgs& a, uint32_t n_queries, int n_sms) {
+    if (!n_queries) return;
+    static PerDeviceOnce configured;
+    if (configured.first()) cudaFuncSetAttribute(plane_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_kernel_smem());
+    plane_seed_kernel<<<(unsigned)n_sms * 2u, kPlaneThreads, plane_kernel_smem(), st>>>(a, n_queries);
+    count_launch();
+}
 
 void launch_plane_eval(cudaStream_t st, const PlaneArgs& a, int n_sms) {
     if (a.group_end <= a.group_begin) return;

@@ -292,7 +292,9 @@ int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, const 
     if (ch->ch->rank() == 0) {
         // plan here, publish the plan -- or the failure, so that the other ranks fail with it instead of waiting
         vgpu_batch* b = nullptr;
+        vdev::plan_for_all_ranks() = true;
         int32_t rc = vgpu_batch_prepare_lines(idx, text, len, n, &b);
+        vdev::plan_for_all_ranks() = false;
         std::vector<uint8_t> bytes;
         if (rc == VGPU_OK)
             rc = guarded([&]() {

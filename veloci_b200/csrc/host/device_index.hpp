@@ -369,6 +369,7 @@ struct ColumnDev {  // boost column
     float vmax = 0.0f;
     // nested "value >= threshold" bitmaps over the shard's anchors (plane path)
     DevBuf<uint32_t> level_bits;
+    DevBuf<uint32_t> seed_anchor, seed_bits;  // the column's seed set and the planes restricted to it (ColumnLevels)
     DevBuf<ColumnLevels> level_hdr;
     ColumnLevels h_levels{};
 };
@@ -692,6 +693,35 @@ struct DeviceIndex {
             c.level_bits.alloc((size_t)kBoostLevels * words);
             launch_level_fill(nullptr, c.bits.p, (uint32_t)n, (uint32_t)anchor_lo, (uint32_t)span, c.h_levels.thr, c.level_bits.p, words);
             c.h_levels.bits = c.level_bits.p;
+            // seed set: the shard's anchors with a value in the top 1/8 of the column, and every plane restricted to them
+            c.h_levels.seed_anchor = nullptr, c.h_levels.seed_bits = nullptr, c.h_levels.seed_n = 0, c.h_levels.seed_words = 0;
+            if (planes.n_planes > 0 && !sample.empty()) {
+                std::vector<uint32_t> seed;
+                const float thr = c.h_levels.thr[kSeedLevel];
+                {
+                    // in descending value order: the seed pass meets the best-boosted anchors first and may stop early
+                    std::vector<std::pair<uint32_t, uint32_t>> by_value;  // (value bits: non-negative floats order like their bits, anchor)
+                    for (size_t id = lo; id < hi; ++id)
+                        if (bits[id] != kNoValue) {
+                            float f;
+                            memcpy(&f, &bits[id], 4);
+                            if (f >= thr) by_value.emplace_back(bits[id], (uint32_t)(id - anchor_lo));
+                        }
+                    std::sort(by_value.begin(), by_value.end(), [](const std::pair<uint32_t, uint32_t>& x, const std::pair<uint32_t, uint32_t>& y) {
+                        return x.first != y.first ? x.first > y.first : x.second < y.second;
+                    });
+                    seed.reserve(by_value.size());
+                    for (auto& v : by_value) seed.push_back(v.second);
+                }
+                if (!seed.empty() && seed.size() <= (size_t)(span / 4 + 1024)) {  // (a column of few distinct values can put most anchors at its top: no use as a seed set)
+                    const uint32_t seed_words = (uint32_t)(((seed.size() + 31) / 32 + 127) / 128 * 128);
+                    c.seed_anchor.upload(seed);
+                    c.seed_bits.alloc((size_t)planes.n_planes * seed_words);
+                    launch_seed_compact(nullptr, planes.bits.p, planes.n_planes, planes.words, c.seed_anchor.p, (uint32_t)seed.size(), seed_words, c.seed_bits.p);
+                    c.h_levels.seed_anchor = c.seed_anchor.p, c.h_levels.seed_bits = c.seed_bits.p, c.h_levels.seed_n = (uint32_t)seed.size(), c.h_levels.seed_words = seed_words;
+                    device_bytes += c.seed_anchor.bytes() + c.seed_bits.bytes();
+                }
+            }
             c.level_hdr.upload(std::vector<ColumnLevels>{c.h_levels});
             device_bytes += c.level_bits.bytes();
         }

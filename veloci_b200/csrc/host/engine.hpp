@@ -76,6 +76,12 @@ inline void bound_part_hits(const vhost::SearchPart& part, std::vector<TermHit>&
     }
 }
 
+// Set (per thread) around a prepare whose plan is published to the other ranks of the box.
+inline bool& plan_for_all_ranks() {
+    static thread_local bool flag = false;
+    return flag;
+}
+
 struct Batch {
     DeviceIndex* ix = nullptr;
     vplan::BatchPlan plan;
@@ -233,7 +239,10 @@ struct Batch {
         // share of the cores but at least 8: at N = 4 on 32 cores, 8 threads per rank plan a batch in 10.5 ms where 16
         // (128 runnable threads with the ranks' other threads) take 12.4 ms and 4 cannot keep up with the GPU.
         unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-        if (const char* env = getenv("LOCAL_WORLD_SIZE")) {
+        if (plan_for_all_ranks()) {
+            // this process plans for every rank of the box (vgpu_batch_prepare_shared): the other ranks' cores are its to use
+            hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        } else if (const char* env = getenv("LOCAL_WORLD_SIZE")) {
             const unsigned ranks = (unsigned)std::max(1, atoi(env));
             hw = std::min(hw, std::max(8u, std::thread::hardware_concurrency() / ranks));
         }
@@ -825,10 +834,11 @@ struct Batch {
         VDEV_CUDA(cudaMemsetAsync(d_num_hits.p, 0, d_num_hits.bytes(), stream));
         VDEV_CUDA(cudaMemsetAsync(d_lock.p, 0, d_lock.bytes(), stream));
         if (n_facets) VDEV_CUDA(cudaMemsetAsync(d_facet_hist.p, 0, d_facet_hist.bytes(), stream));
-        // ---- phase 3: plane evaluation.  The first tile group of every request before the rest: afterwards the requests'
-        // thresholds are worth sharing between anchor-range shards (and the other groups prune against them from the start).
+        // ---- phase 3: plane evaluation.  First the threshold seeds: one pass over the boost column's seed set (the shard's
+        // best-boosted eighth) gives every request a threshold near its final one.  The seeds are what anchor-range shards
+        // share (all-reduce MAX) before any of them sweeps.
         pending_items = n_items, pending_fast_items = n_fast_items;
-        if (planes_on && n_fast_items) timed("plane_eval_first", [&] { launch_plane_eval(stream, plane_stage_args(0, 0, std::min<uint32_t>(1, n_groups)), n_sms); });
+        if (planes_on && n_fast_items) timed("plane_seed", [&] { launch_plane_seed(stream, plane_stage_args(0, 0, 0), n, n_sms); });
         if (sync_at_end) {
             VDEV_CUDA(cudaStreamSynchronize(stream));
             VDEV_CUDA(cudaGetLastError());
@@ -843,7 +853,7 @@ struct Batch {
         begun = false;
         const unsigned long long n_items = pending_items;
         const bool planes_on = use_planes && mode == kRequests;
-        if (planes_on && pending_fast_items && n_groups > 1) timed("plane_eval", [&] { launch_plane_eval(stream, plane_stage_args(2, 1, n_groups), n_sms); });
+        if (planes_on && pending_fast_items) timed("plane_eval", [&] { launch_plane_eval(stream, plane_stage_args(2, 0, n_groups), n_sms); });
         VDEV_CUDA(cudaEventRecord(ev[4], stream));
         // ---- phase 4: tile evaluation of the general items
         {
