@@ -292,20 +292,27 @@ int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, const 
     if (ch->ch->rank() == 0) {
         // plan here, publish the plan -- or the failure, so that the other ranks fail with it instead of waiting
         vgpu_batch* b = nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
         vdev::plan_for_all_ranks() = true;
         int32_t rc = vgpu_batch_prepare_lines(idx, text, len, n, &b);
         vdev::plan_for_all_ranks() = false;
+        const auto t1 = std::chrono::steady_clock::now();
         std::vector<uint8_t> bytes;
         if (rc == VGPU_OK)
             rc = guarded([&]() {
                 bytes = vplan::export_plan(b->b.plan);
                 if (bytes.size() > ch->ch->capacity()) throw vplan::ChannelError("the plan (" + std::to_string(bytes.size()) + " bytes) exceeds the channel capacity");
             });
+        const auto t2 = std::chrono::steady_clock::now();
         const std::string failure = t_error;
         const int32_t pub = guarded([&]() {
             if (rc == VGPU_OK) ch->ch->publish(bytes.data(), bytes.size(), 0);
             else ch->ch->publish(failure.data(), std::min(failure.size(), ch->ch->capacity()), (uint64_t)rc);
         });
+        if (getenv("VELOCI_DEBUG")) {
+            auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
+            fprintf(stderr, "[veloci] prepare_shared rank 0: prepare %.2f ms, export %.2f ms (%zu bytes), publish %.2f ms\n", ms(t0, t1), ms(t1, t2), bytes.size(), ms(t2, std::chrono::steady_clock::now()));
+        }
         if (rc == VGPU_OK) rc = pub;
         else t_error = failure;
         if (rc != VGPU_OK) {
@@ -317,9 +324,12 @@ int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, const 
     }
     int32_t remote = VGPU_OK;
     std::string remote_msg;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto t1 = t0;
     const int32_t rc = guarded([&]() {
         std::unique_ptr<vgpu_batch> b(new vgpu_batch());
         ch->ch->consume([&](const uint8_t* data, size_t blob_len, uint64_t status) {
+            t1 = std::chrono::steady_clock::now();
             if (status != 0) {
                 remote = (int32_t)status, remote_msg.assign(reinterpret_cast<const char*>(data), blob_len);
                 return;
@@ -328,6 +338,10 @@ int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, const 
         });
         if (remote == VGPU_OK) *out = b.release();
     });
+    if (getenv("VELOCI_DEBUG")) {
+        auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
+        fprintf(stderr, "[veloci] prepare_shared rank %u: waited %.2f ms, import + upload %.2f ms\n", ch->ch->rank(), ms(t0, t1), ms(t1, std::chrono::steady_clock::now()));
+    }
     if (rc != VGPU_OK) return rc;
     if (remote != VGPU_OK) {
         t_error = "local rank 0 could not plan the batch: " + remote_msg;
