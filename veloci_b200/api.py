@@ -135,6 +135,14 @@ def _encode_requests(requests):
     return (ctypes.c_char_p * len(enc))(*enc), enc
 
 
+def _join_lines(requests):
+    """The requests as one line-feed separated buffer.  Requests that are already bytes (what a server holds) are joined without
+    another pass over their text; str requests are encoded."""
+    if requests and isinstance(requests[0], bytes):
+        return b"\n".join(requests)
+    return "\n".join(requests).encode("utf-8")
+
+
 def _to_hitlist(hits=None, ids=None):
     hits = list(hits or [])
     ids = list(ids or [])
@@ -172,7 +180,7 @@ class Batch:
             self.n = self._size()
             return
         if channel is not None:
-            blob = b"" if channel.rank != 0 else "\n".join(requests).encode("utf-8")
+            blob = b"" if channel.rank != 0 else _join_lines(requests)
             _check(self.L.vgpu_batch_prepare_shared(index.h, channel.h, blob if channel.rank == 0 else None, len(blob), self.n if channel.rank == 0 else 0, ctypes.byref(self.h)))
             self.n = self._size()
             return
@@ -199,7 +207,7 @@ class Batch:
         """Many requests: one buffer of line-feed separated requests instead of one C string each.  False when some request
         is not a string or contains a line feed (the library checks the count of line feeds before doing anything)."""
         try:
-            blob = "\n".join(requests).encode("utf-8")
+            blob = _join_lines(requests)
         except TypeError:
             return False
         rc = self.L.vgpu_batch_prepare_lines(index.h, blob, len(blob), self.n, ctypes.byref(self.h))

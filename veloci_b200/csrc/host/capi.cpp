@@ -148,7 +148,11 @@ int32_t vgpu_batch_prepare(vgpu_index* idx, const char* const* request_json, uin
     });
 }
 
-int32_t vgpu_batch_prepare_lines(vgpu_index* idx, const char* text, size_t len, uint32_t n, vgpu_batch** out) {
+static int32_t prepare_lines(vgpu_index* idx, const char* text, size_t len, uint32_t n, bool upload, vgpu_batch** out);
+
+int32_t vgpu_batch_prepare_lines(vgpu_index* idx, const char* text, size_t len, uint32_t n, vgpu_batch** out) { return prepare_lines(idx, text, len, n, true, out); }
+
+static int32_t prepare_lines(vgpu_index* idx, const char* text, size_t len, uint32_t n, bool upload, vgpu_batch** out) {
     if (!idx || !out || (len && !text)) {
         t_error = "null argument";
         return VGPU_ERR_INVALID_REQUEST;
@@ -175,7 +179,7 @@ int32_t vgpu_batch_prepare_lines(vgpu_index* idx, const char* text, size_t len, 
             lines.push_back(p);
             p = nl < end ? nl + 1 : end;
         }
-        b->b.prepare(idx->ix.get(), lines.data(), n);
+        b->b.prepare(idx->ix.get(), lines.data(), n, upload);
         *out = b.release();
     });
 }
@@ -294,7 +298,7 @@ int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, const 
         vgpu_batch* b = nullptr;
         const auto t0 = std::chrono::steady_clock::now();
         vdev::plan_for_all_ranks() = true;
-        int32_t rc = vgpu_batch_prepare_lines(idx, text, len, n, &b);
+        int32_t rc = prepare_lines(idx, text, len, n, false, &b);  // the other ranks get the plan before this one uploads its own copy
         vdev::plan_for_all_ranks() = false;
         const auto t1 = std::chrono::steady_clock::now();
         std::vector<uint8_t> bytes;
@@ -315,6 +319,7 @@ int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, const 
         }
         if (rc == VGPU_OK) rc = pub;
         else t_error = failure;
+        if (rc == VGPU_OK) rc = guarded([&]() { b->b.upload_plan(); });
         if (rc != VGPU_OK) {
             vgpu_batch_free(b);
             return rc;

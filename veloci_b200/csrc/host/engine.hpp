@@ -227,7 +227,8 @@ struct Batch {
     }
 
     // ------------------------------------------------------------ preparation
-    void prepare(DeviceIndex* index, const char* const* request_json, uint32_t count) {
+    // `upload` false: the plan tables stay on the host until upload_plan() (the caller publishes the plan first)
+    void prepare(DeviceIndex* index, const char* const* request_json, uint32_t count, bool upload = true) {
         ix = index;
         n = count;
         plan.ix = ix;
@@ -269,7 +270,7 @@ struct Batch {
         }
         const auto t1 = std::chrono::steady_clock::now();
         const auto t2 = std::chrono::steady_clock::now();
-        upload_plan();
+        if (upload) upload_plan();
         if (getenv("VELOCI_DEBUG")) {
             const auto t3 = std::chrono::steady_clock::now();
             auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
