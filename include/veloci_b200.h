@@ -213,6 +213,19 @@ int32_t vgpu_resolve_to_anchor(vgpu_index* idx, const char* part_json, const vgp
 int32_t vgpu_union_hits_score(vgpu_index* idx, const vgpu_hitlist* inputs, const char* const* terms, uint32_t n, vgpu_hitlist* out);
 /* intersect_hits_score (src/search/set_op.rs:368-446). */
 int32_t vgpu_intersect_hits_score(vgpu_index* idx, const vgpu_hitlist* inputs, uint32_t n, vgpu_hitlist* out);
+/* resolve_token_to_anchor with the FilterResult of the request's filter tree (ResolveTokenIdToAnchor with a filter channel,
+ * src/plan_creator/plan_steps.rs:98-131; search_field.rs:423, 540-548): anchors outside `filter_ids` are skipped. */
+int32_t vgpu_resolve_to_anchor_filtered(vgpu_index* idx, const char* part_json, const vgpu_hitlist* in, const uint32_t* filter_ids, uint32_t n_filter, vgpu_hitlist* out);
+/* union_hits_ids (src/search/set_op.rs:222-258) and intersect_hits_ids (:468-510) over the inputs' hits_ids (the Union /
+ * Intersect steps of an ids-only filter sub-plan, plan_steps.rs:295-328). */
+int32_t vgpu_union_hits_ids(vgpu_index* idx, const vgpu_hitlist* inputs, uint32_t n, vgpu_hitlist* out);
+int32_t vgpu_intersect_hits_ids(vgpu_index* idx, const vgpu_hitlist* inputs, uint32_t n, vgpu_hitlist* out);
+/* IntersectScoresWithIds (plan_steps.rs:330-345; intersect_score_hits_with_ids, set_op.rs:311-326): the scored hits of
+ * `scores` whose id is among `ids->ids`. */
+int32_t vgpu_intersect_scores_with_ids(vgpu_index* idx, const vgpu_hitlist* scores, const vgpu_hitlist* ids, vgpu_hitlist* out);
+/* get_facet (src/facet.rs:31-73): `facet_json` is one FacetRequest, `ids` the hit ids; groups come back through the
+ * suggestion list type: text = the group's text, id = its value id, score = its count (exact below 2^24). */
+int32_t vgpu_facet(vgpu_index* idx, const char* facet_json, const uint32_t* ids, uint32_t n_ids, vgpu_suggestions* out);
 /* add_boost (src/search/boost.rs:470-504): `boost_json` is one RequestBoostPart. */
 int32_t vgpu_add_boost(vgpu_index* idx, const char* boost_json, vgpu_hitlist* inout);
 /* top_n_sort + apply_top_skip (src/search/sort.rs:5-22, src/search.rs:230-239). */

@@ -1222,6 +1222,26 @@ static std::string call(const Persistence* p, const std::string& fn, const vjson
         auto rs = results_from(*a.get("inputs"));
         return hits_to_json(intersect_score_hits_with_ids(rs[0], rs[1]).hits_scores);
     }
+    if (fn == "get_facet") {  // facet.rs:31-73 over the given hit ids -> [[text, count, value id]]
+        vhost::FacetRequest fr;
+        fr.field = a.get("field")->str;
+        if (auto* t = a.get("top")) {
+            if (t->is_null()) fr.top.reset();
+            else fr.top = (uint64_t)t->num;
+        }
+        std::vector<uint32_t> ids;
+        for (auto& x : a.get("ids")->arr) ids.push_back((uint32_t)x.num);
+        std::string out = "[";
+        bool first = true;
+        for (auto& g : get_facet(*p, fr, ids)) {
+            out += first ? "" : ",";
+            first = false;
+            out += "[";
+            vjson::write_string(out, g.text);
+            out += "," + std::to_string(g.count) + "," + std::to_string(g.id) + "]";
+        }
+        return out + "]";
+    }
     if (fn == "apply_boost_values_anchor") {
         SearchFieldResult r;
         r.hits_scores = hits_from_json(*a.get("hits_scores"));

@@ -269,3 +269,56 @@ def test_in_library_exchange_over_nccl(gpu, sharded_corpus):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "sharded_worker ok" in r.stdout
+
+
+def test_ids_set_ops_and_filter_steps(gpu, sharded_corpus):
+    """union_hits_ids, intersect_hits_ids, IntersectScoresWithIds and the filtered ResolveTokenIdToAnchor as step entry points,
+    against the oracle's restatement of set_op.rs (with its quirks: one input passes through unsorted, empty other inputs of
+    an intersection are skipped, an empty id list keeps every scored hit)."""
+    d, _ = sharded_corpus
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    rng = np.random.default_rng(12)
+    N = SHARDED["num_docs"]
+    lists = [[int(x) for x in rng.choice(N, size=n, replace=False)] for n in (900, 300, 1500, 40)]
+    lists[1] = lists[1] + lists[0][:200]  # overlaps
+    lists[2] = lists[2] + lists[0][100:400] + lists[1][:120]
+    lists[3] = lists[3] + lists[0][150:260]
+    as_inputs = lambda ls: [{"hits_ids": l} for l in ls]
+    for pick in ([0, 1], [0, 1, 2], [0, 1, 2, 3], [2], [1, 3]):
+        ls = [lists[i] for i in pick]
+        assert index.union_hits_ids(ls) == oracle.call("union_hits_ids", inputs=as_inputs(ls)), pick
+        assert index.intersect_hits_ids(ls) == oracle.call("intersect_hits_ids", inputs=as_inputs(ls)), pick
+    with_empty = [lists[0], [], lists[2]]
+    assert index.intersect_hits_ids(with_empty) == oracle.call("intersect_hits_ids", inputs=as_inputs(with_empty))
+    assert index.intersect_hits_ids([[], lists[2]]) == oracle.call("intersect_hits_ids", inputs=as_inputs([[], lists[2]])) == []
+    assert index.union_hits_ids([]) == [] and index.intersect_hits_ids([]) == []
+    hits = [(i, float(np.float32(rng.random() * 7))) for i in lists[0]]
+    for ids in (lists[2], []):
+        ref = oracle.call("intersect_score_hits_with_ids", inputs=[{"hits_scores": [[i, s] for i, s in hits]}, {"hits_ids": ids}])
+        got = index.intersect_scores_with_ids(hits, ids)
+        assert [(g[0], float(g[1])) for g in got] == [(r[0], float(np.float32(r[1]))) for r in ref]
+    # the filtered resolve: the oracle's resolve, cut to the filter
+    part = {"terms": ["abcd"], "path": "body", "levenshtein_distance": 2}
+    term_hits, _ = index.field_search(part)
+    full = oracle.call("resolve_token_to_anchor", part=part)["hits_scores"]
+    assert len(full) > 20
+    keep = sorted(r[0] for r in full[::3]) + [N - 1]
+    got = index.resolve_to_anchor_filtered(part, term_hits, keep)
+    want = [r for r in full if r[0] in set(keep)]
+    assert [g[0] for g in got] == [r[0] for r in want]
+    assert all(abs(float(g[1]) - r[1]) <= 1e-5 * abs(r[1]) for g, r in zip(got, want))
+    assert index.resolve_to_anchor_filtered(part, term_hits, []) == []
+
+
+def test_facet_step(gpu, sharded_corpus):
+    """get_facet as a step entry point: groups of a facet field over an explicit id list (facet.rs:31-73)."""
+    d, reqs = sharded_corpus
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    field = json.loads(reqs[450])["facets"][0]["field"]
+    rng = np.random.default_rng(4)
+    ids = sorted(int(x) for x in rng.choice(SHARDED["num_docs"], size=5000, replace=False))
+    for top in (3, 10, None):
+        ref = oracle.call("get_facet", field=field, top=top, ids=ids)
+        got = index.facet({"field": field, "top": top}, ids)
+        assert [(t, c, i) for t, c, i in got] == [(r[0], r[1], r[2]) for r in ref], top
+    assert index.facet({"field": field}, []) == []

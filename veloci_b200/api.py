@@ -98,6 +98,11 @@ def load_library():
     L.vgpu_resolve_to_anchor.argtypes = [vp, cp, P(_HitList), P(_HitList)]
     L.vgpu_union_hits_score.argtypes = [vp, P(_HitList), P(cp), u32, P(_HitList)]
     L.vgpu_intersect_hits_score.argtypes = [vp, P(_HitList), u32, P(_HitList)]
+    L.vgpu_resolve_to_anchor_filtered.argtypes = [vp, cp, P(_HitList), P(u32), u32, P(_HitList)]
+    L.vgpu_union_hits_ids.argtypes = [vp, P(_HitList), u32, P(_HitList)]
+    L.vgpu_intersect_hits_ids.argtypes = [vp, P(_HitList), u32, P(_HitList)]
+    L.vgpu_intersect_scores_with_ids.argtypes = [vp, P(_HitList), P(_HitList), P(_HitList)]
+    L.vgpu_facet.argtypes = [vp, cp, P(u32), u32, P(_Suggestions)]
     L.vgpu_add_boost.argtypes = [vp, cp, P(_HitList)]
     L.vgpu_top_n.argtypes = [vp, P(_HitList), u32, u32, P(_HitList)]
     L.vgpu_suggest.argtypes = [vp, cp, P(_Suggestions)]
@@ -481,6 +486,41 @@ class Index:
         out = _HitList()
         _check(self.L.vgpu_intersect_hits_score(self.h, arr, n, ctypes.byref(out)))
         return _from_hitlist(self.L, out)[0]
+
+    def resolve_to_anchor_filtered(self, part, hits, filter_ids):
+        inp, out = _to_hitlist(hits), _HitList()
+        arr = (ctypes.c_uint32 * max(1, len(filter_ids)))(*filter_ids)
+        _check(self.L.vgpu_resolve_to_anchor_filtered(self.h, json.dumps(part, ensure_ascii=False).encode("utf-8"), ctypes.byref(inp), arr, len(filter_ids), ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[0]
+
+    def _ids_op(self, fn, id_lists):
+        n = len(id_lists)
+        keep = [_to_hitlist(None, l) for l in id_lists]
+        arr = (_HitList * max(1, n))(*keep)
+        out = _HitList()
+        _check(fn(self.h, arr, n, ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[1]
+
+    def union_hits_ids(self, id_lists):
+        return self._ids_op(self.L.vgpu_union_hits_ids, id_lists)
+
+    def intersect_hits_ids(self, id_lists):
+        return self._ids_op(self.L.vgpu_intersect_hits_ids, id_lists)
+
+    def intersect_scores_with_ids(self, hits, ids):
+        a, b, out = _to_hitlist(hits), _to_hitlist(None, ids), _HitList()
+        _check(self.L.vgpu_intersect_scores_with_ids(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[0]
+
+    def facet(self, facet_request, ids):
+        """get_facet over `ids` -> [(text, count, value id)]"""
+        out = _Suggestions()
+        arr = (ctypes.c_uint32 * max(1, len(ids)))(*ids)
+        _check(self.L.vgpu_facet(self.h, json.dumps(facet_request).encode("utf-8"), arr, len(ids), ctypes.byref(out)))
+        try:
+            return [(out.items[i].text.decode("utf-8"), int(out.items[i].score), out.items[i].id) for i in range(out.n)]
+        finally:
+            self.L.vgpu_suggestions_free(ctypes.byref(out))
 
     def add_boost(self, boost, hits):
         inp = _to_hitlist(hits)

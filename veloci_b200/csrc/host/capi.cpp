@@ -518,6 +518,32 @@ int32_t vgpu_intersect_hits_score(vgpu_index* idx, const vgpu_hitlist* inputs, u
     if (!idx || (n && !inputs) || !out) return VGPU_ERR_INVALID_REQUEST;
     return guarded([&]() { vsteps::set_op(*idx->ix, inputs, nullptr, n, false, *out); });
 }
+int32_t vgpu_resolve_to_anchor_filtered(vgpu_index* idx, const char* part_json, const vgpu_hitlist* in, const uint32_t* filter_ids, uint32_t n_filter, vgpu_hitlist* out) {
+    if (!idx || !part_json || !in || !out || (n_filter && !filter_ids)) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() { vsteps::resolve_to_anchor_filtered(*idx->ix, part_json, *in, filter_ids, n_filter, *out); });
+}
+int32_t vgpu_union_hits_ids(vgpu_index* idx, const vgpu_hitlist* inputs, uint32_t n, vgpu_hitlist* out) {
+    if (!idx || (n && !inputs) || !out) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() { vsteps::set_op_ids(*idx->ix, inputs, n, true, *out); });
+}
+int32_t vgpu_intersect_hits_ids(vgpu_index* idx, const vgpu_hitlist* inputs, uint32_t n, vgpu_hitlist* out) {
+    if (!idx || (n && !inputs) || !out) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() { vsteps::set_op_ids(*idx->ix, inputs, n, false, *out); });
+}
+int32_t vgpu_intersect_scores_with_ids(vgpu_index* idx, const vgpu_hitlist* scores, const vgpu_hitlist* ids, vgpu_hitlist* out) {
+    if (!idx || !scores || !ids || !out) return VGPU_ERR_INVALID_REQUEST;
+    return guarded([&]() { vsteps::intersect_scores_with_ids(*idx->ix, *scores, *ids, *out); });
+}
+static void fill_suggestions(const std::vector<vsteps::Suggestion>& v, vgpu_suggestions* out);
+int32_t vgpu_facet(vgpu_index* idx, const char* facet_json, const uint32_t* ids, uint32_t n_ids, vgpu_suggestions* out) {
+    if (!idx || !facet_json || !out || (n_ids && !ids)) return VGPU_ERR_INVALID_REQUEST;
+    memset(out, 0, sizeof *out);
+    return guarded([&]() {
+        std::vector<vsteps::Suggestion> groups;
+        for (auto& g : vsteps::facet(*idx->ix, facet_json, ids, n_ids)) groups.push_back(vsteps::Suggestion{g.text, (float)g.count, g.id});
+        fill_suggestions(groups, out);
+    });
+}
 int32_t vgpu_add_boost(vgpu_index* idx, const char* boost_json, vgpu_hitlist* inout) {
     if (!idx || !boost_json || !inout) return VGPU_ERR_INVALID_REQUEST;
     return guarded([&]() { vsteps::add_boost(*idx->ix, boost_json, *inout); });

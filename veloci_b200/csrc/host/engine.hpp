@@ -331,7 +331,8 @@ struct Batch {
     }
 
     // one request over explicit hit lists (union / intersect / add_boost / top_n step entry points)
-    void prepare_lists(DeviceIndex* index, const std::vector<ExplicitList>& lists, const std::vector<uint32_t>& code, const std::vector<BoostStep>& boost_steps, uint32_t k, bool all_hits) {
+    void prepare_lists(DeviceIndex* index, const std::vector<ExplicitList>& lists, const std::vector<uint32_t>& code, const std::vector<BoostStep>& boost_steps, uint32_t k, bool all_hits,
+                       const vhost::FacetRequest* facet = nullptr) {
         ix = index;
         plan.ix = ix;
         mode = kLists;
@@ -342,7 +343,7 @@ struct Batch {
         for (auto& l : lists)
             for (float sc : l.scores)
                 if (!(sc >= 0.0f)) qp.nonneg = 0;
-        const bool trivial = lists.size() == 1 && code.size() == 2;
+        const bool trivial = lists.size() == 1 && code.size() == 2 && !facet;  // (facets are counted on the program path)
         qp.prog_begin = 0, qp.prog_len = trivial ? 0u : (uint32_t)code.size();
         if (!trivial) plan.prog = code;
         qp.boost_begin = 0, qp.n_boosts = (uint32_t)boost_steps.size();
@@ -358,8 +359,14 @@ struct Batch {
             plan.leaf_part.push_back((uint32_t)i);
             total += lists[i].anchors.size();
         }
+        vplan::RequestPlan rp;
+        if (facet) {  // get_facet over the list's ids (facet.rs:31-73)
+            plan.add_facet(*facet);
+            qp.facet_begin = 0, qp.n_facets = 1;
+            rp.facets.push_back(*facet), rp.has_facets = true, rp.facet_begin = 0;
+        }
         plan.programs.push_back(qp);
-        plan.requests.emplace_back();
+        plan.requests.push_back(std::move(rp));
         plan.max_leaves = std::max<uint32_t>(1, (uint32_t)lists.size());
         plan.max_k = std::max<uint32_t>(1, k);
         n = 1;

@@ -221,6 +221,133 @@ inline void set_op(vdev::DeviceIndex& ix, const vgpu_hitlist* inputs, const char
     run_lists(ix, lists, code, {}, 0, true, out);
 }
 
+inline std::vector<vdev::ExplicitList> ids_to_lists(const vgpu_hitlist* inputs, uint32_t n) {
+    std::vector<vdev::ExplicitList> lists(n);
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t j = 0; j < inputs[i].n_ids; ++j) {
+            lists[i].anchors.push_back(inputs[i].ids[j]);
+            lists[i].scores.push_back(1.0f);
+        }
+    return lists;
+}
+
+inline void ids_out(const std::vector<uint32_t>& ids, vgpu_hitlist& out) {
+    memset(&out, 0, sizeof out);
+    out.hits = dup_array(std::vector<vgpu_hit>()), out.n_hits = 0;
+    out.ids = dup_array(ids), out.n_ids = (uint32_t)ids.size();
+}
+
+// union_hits_ids (set_op.rs:222-258): one input passes through as given; otherwise the distinct ids, ascending.
+// intersect_hits_ids (set_op.rs:468-510): one input passes through; otherwise the ids of the shortest input (sorted, duplicates
+// kept) that every other non-empty input contains (an empty other input is skipped by the reference's iterator filter).
+inline void set_op_ids(vdev::DeviceIndex& ix, const vgpu_hitlist* inputs, uint32_t n, bool is_union, vgpu_hitlist& out) {
+    if (n == 0) return ids_out({}, out);
+    if (n == 1) return ids_out(std::vector<uint32_t>(inputs[0].ids, inputs[0].ids + inputs[0].n_ids), out);
+    if (n > vdev::kMaxLeaves) throw vplan::Unsupported("more than 12 inputs");
+    std::vector<uint32_t> pick(n);
+    uint32_t shortest = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        pick[i] = i;
+        if (inputs[i].n_ids < inputs[shortest].n_ids) shortest = i;
+    }
+    if (!is_union) {
+        if (inputs[shortest].n_ids == 0) return ids_out({}, out);
+        pick.clear();
+        for (uint32_t i = 0; i < n; ++i)
+            if (i == shortest || inputs[i].n_ids != 0) pick.push_back(i);
+    }
+    std::vector<vgpu_hitlist> chosen;
+    for (uint32_t i : pick) chosen.push_back(inputs[i]);
+    const uint32_t m = (uint32_t)chosen.size();
+    std::vector<vdev::ExplicitList> lists = ids_to_lists(chosen.data(), m);
+    std::vector<uint32_t> code;
+    for (uint32_t i = 0; i < m; ++i) code.push_back(vdev::kOpLeaf), code.push_back(i);
+    if (m > 1) {
+        if (is_union) {
+            code.push_back(vdev::kOpUnion), code.push_back(m), code.push_back(m);
+            for (uint32_t i = 0; i < m; ++i) code.push_back(i);
+        } else {
+            code.push_back(vdev::kOpIntersect), code.push_back(m);
+            for (uint32_t i = 0; i < m; ++i) code.push_back(i);
+            for (uint32_t i = 0; i < m; ++i) code.push_back(vdev::kNoValue - 1);
+        }
+    }
+    vgpu_hitlist all;
+    run_lists(ix, lists, code, {}, 0, true, all);  // the device's hits come back by ascending anchor id
+    std::vector<uint32_t> ids;
+    if (is_union) {
+        for (uint32_t i = 0; i < all.n_hits; ++i) ids.push_back(all.hits[i].id);
+    } else {
+        std::vector<uint32_t> base(inputs[shortest].ids, inputs[shortest].ids + inputs[shortest].n_ids);
+        std::sort(base.begin(), base.end());
+        for (uint32_t id : base) {
+            const vgpu_hit* b0 = all.hits;
+            const vgpu_hit* e = all.hits + all.n_hits;
+            const vgpu_hit* it = std::lower_bound(b0, e, id, [](const vgpu_hit& h, uint32_t v) { return h.id < v; });
+            if (it != e && it->id == id) ids.push_back(id);
+        }
+    }
+    vgpu_hitlist_free(&all);
+    ids_out(ids, out);
+}
+
+// intersect_score_hits_with_ids (set_op.rs:311-326, the IntersectScoresWithIds step plan_steps.rs:330-345): the scored hits
+// whose id is in `ids`, by ascending id; with no ids at all the reference keeps every hit.
+inline void intersect_scores_with_ids(vdev::DeviceIndex& ix, const vgpu_hitlist& scores, const vgpu_hitlist& ids, vgpu_hitlist& out) {
+    std::vector<vdev::ExplicitList> lists = to_lists(&scores, 1);
+    if (ids.n_ids == 0) return run_lists(ix, lists, {vdev::kOpLeaf, 0u}, {}, 0, true, out);
+    lists.push_back(ids_to_lists(&ids, 1)[0]);
+    run_lists(ix, lists, {vdev::kOpLeaf, 0u, vdev::kOpLeaf, 1u, vdev::kOpFilter}, {}, 0, true, out);
+}
+
+// resolve_token_to_anchor with a FilterResult::Set (search_field.rs:423, 540-548): anchors outside the filter are skipped.
+inline void resolve_to_anchor_filtered(vdev::DeviceIndex& ix, const char* part_json, const vgpu_hitlist& in, const uint32_t* filter, uint32_t n_filter, vgpu_hitlist& out) {
+    vgpu_hitlist all;
+    resolve_to_anchor(ix, part_json, in, all);
+    vgpu_hitlist f;
+    memset(&f, 0, sizeof f);
+    f.ids = const_cast<uint32_t*>(filter), f.n_ids = n_filter;
+    memset(&out, 0, sizeof out);
+    if (n_filter == 0) {  // an empty set contains nothing
+        out.hits = dup_array(std::vector<vgpu_hit>()), out.ids = all.ids, out.n_ids = all.n_ids;
+        all.ids = nullptr;
+    } else {
+        intersect_scores_with_ids(ix, all, f, out);
+        free(out.ids);
+        out.ids = all.ids, out.n_ids = all.n_ids, all.ids = nullptr;
+    }
+    vgpu_hitlist_free(&all);
+}
+
+// get_facet (facet.rs:31-73) over the given hit ids: (text, count, value id) groups, count desc then value id asc.
+inline std::vector<FacetGroup> facet(vdev::DeviceIndex& ix, const char* facet_json, const uint32_t* ids, uint32_t n_ids) {
+    vjson::Value v;
+    try {
+        v = vjson::parse(facet_json, strlen(facet_json));
+    } catch (const vjson::ParseError& e) {
+        throw vhost::RequestError(e.what());
+    }
+    if (!v.is_object()) throw vhost::RequestError("facet must be an object");
+    vhost::FacetRequest fr;
+    const vjson::Value* fld = v.get("field");
+    if (!fld || !fld->is_string()) throw vhost::RequestError("missing field `field`");
+    fr.field = fld->str;
+    if (const vjson::Value* t = v.get("top")) {
+        if (t->is_null()) fr.top.reset();
+        else if (t->is_number() && t->num >= 0) fr.top = (uint64_t)t->num;
+        else throw vhost::RequestError("top must be an unsigned integer");
+    }
+    vdev::Batch b;
+    vdev::ExplicitList l;
+    l.anchors.assign(ids, ids + n_ids);
+    l.scores.assign(n_ids, 1.0f);
+    b.prepare_lists(&ix, {l}, {vdev::kOpLeaf, 0u}, {}, 0, false, &fr);
+    b.execute();
+    std::vector<std::vector<FacetGroups>> groups;
+    materialize_facets(b, groups);
+    return groups.at(0).at(0).groups;
+}
+
 inline void add_boost(vdev::DeviceIndex& ix, const char* boost_json, vgpu_hitlist& inout) {
     vjson::Value v;
     try {
