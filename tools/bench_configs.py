@@ -111,13 +111,14 @@ def run(name, corpus, queries, cpu_sample=32, jmdict=None):
     r = oracle.search_batch(reqs[:cpu_sample], threads=cores, k=10)
     ok = int((flat["status"] == 0).sum())
     same = int((r["num_hits"] == flat["num_hits"][:cpu_sample]).sum())
+    parity = helpers.batch_parity(flat, r, list(range(cpu_sample)))  # ids + scores (1e-5 rel, ties) + num_hits
     line = {
         "config": name, "corpus": corpus, "queries": queries, "requests": len(reqs), "requests_ok": ok,
         "resident_requests_per_s": len(reqs) / min(times), "e2e_requests_per_s": len(reqs) / min(e2e[1:]),
         "phase_ms": dict(zip(["fuzzy_match", "group_score", "slice", "plane_eval", "tile_eval", "final_topk"], phase)),
         "paths": batch.path_stats(),
         "cpu_oracle_requests_per_s": cpu_sample / r["seconds"], "cpu_cores": cores, "cpu_sample": cpu_sample,
-        "num_hits_equal_on_sample": f"{same}/{cpu_sample}", "index_generation_s": gen_s,
+        "num_hits_equal_on_sample": f"{same}/{cpu_sample}", "parity": parity, "work": batch.work_stats(), "index_generation_s": gen_s,
     }
     print(json.dumps(line), flush=True)
 
@@ -125,15 +126,22 @@ def run(name, corpus, queries, cpu_sample=32, jmdict=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--full", action="store_true", help="BASELINE.json sizes: config 3 on 10M docs / 10k requests, config 4 on a 5M-term dictionary / 10k requests")
+    ap.add_argument("--configs", default="1,3,4")
     a = ap.parse_args()
     s = a.scale
-    run("config1_jmdict_shape_5way_or_lev1", {"docs": int(166_600 * s)}, {"requests": int(2000 * s)}, jmdict={"docs": int(166_600 * s), "requests": int(2000 * s)})
-    run("config3_and_phrase_locality_facets",
-        dict(num_docs=int(2_000_000 * s), vocab=int(200_000 * s), seed=42, tokens_per_doc=8, zipf_s=1.07, tags=1000, text_locality=True, phrase=True),
-        dict(num_queries=int(2000 * s), query_kind="and", levenshtein=1, query_seed=44, top=10))
-    run("config4_large_dictionary_lev2",
-        dict(num_docs=int(5_000_000 * s), vocab=int(5_000_000 * s), seed=42, tokens_per_doc=8, zipf_s=1.07, len_min=4, len_max=16),
-        dict(num_queries=int(2000 * s), query_kind="single", levenshtein=2, query_seed=45, edit_prob=0.5, top=10))
+    which = set(a.configs.split(","))
+    if "1" in which:
+        run("config1_jmdict_shape_5way_or_lev1", {"docs": int(166_600 * s)}, {"requests": int(2000 * s)}, jmdict={"docs": int(166_600 * s), "requests": int(2000 * s)})
+    s3 = 5.0 if a.full else s
+    if "3" in which:
+        run("config3_and_phrase_locality_facets",
+            dict(num_docs=int(2_000_000 * s3), vocab=int(200_000 * s3), seed=42, tokens_per_doc=8, zipf_s=1.07, tags=1000, text_locality=True, phrase=True),
+            dict(num_queries=int(2000 * s3), query_kind="and", levenshtein=1, query_seed=44, top=10), cpu_sample=64)
+    if "4" in which:
+        run("config4_large_dictionary_lev2",
+            dict(num_docs=int(5_000_000 * s), vocab=int(5_000_000 * s), seed=42, tokens_per_doc=8, zipf_s=1.07, len_min=4, len_max=16),
+            dict(num_queries=10_000 if a.full else int(2000 * s), query_kind="single", levenshtein=2, query_seed=45, edit_prob=0.5, top=10), cpu_sample=64)
 
 
 if __name__ == "__main__":

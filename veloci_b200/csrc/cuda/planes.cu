@@ -38,6 +38,7 @@ static const uint32_t kHashSlots = 1024;   // >= 2 * kGroupMaxEntries
 static const uint32_t kHashEmpty = 0xFFFFFFFFu;
 static const uint32_t kPartShift = 20;     // entry code = anchor index in the group | part << 20
 static const uint32_t kItemBatch = 4;      // items a warp takes from the work counter at a time
+static const uint32_t kSeedSweepWords = 16384;  // 32-anchor words of a seed row the seed pass looks at (a multiple of 128)
 static_assert(kHashSlots >= 2 * kGroupMaxEntries, "hash load factor");
 
 struct alignas(16) WarpScratch {
@@ -975,8 +976,11 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_seed_kernel(PlaneArgs 
             }
             qn = 0;
         };
+        // the set is in descending boost order: its first kSeedSweepWords words (the shard's best-boosted half million anchors)
+        // hold the seeds that matter, and bound the pass however large the shard is
+        const uint32_t sweep_w4 = min(seed_words, kSeedSweepWords) >> 2;
 #pragma unroll 1
-        for (uint32_t cw4 = lane; cw4 < (seed_words >> 2); cw4 += 32) {
+        for (uint32_t cw4 = lane; cw4 < sweep_w4; cw4 += 32) {
             uint4 cm = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), cur = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
             for (uint32_t t = 0; t < nt; ++t) {

@@ -33,10 +33,19 @@ struct vgpu_batch {
 
 static thread_local std::string t_error;
 
+// An unchecked runtime call that failed harmlessly leaves its code in the thread's "last error" slot, where the next
+// cudaGetLastError() of an unrelated call would find it: every entry point starts and ends with the slot empty.
+static void clear_stale_cuda_error(const char* where) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && getenv("VELOCI_DEBUG")) fprintf(stderr, "[veloci] stale CUDA error %s: %s\n", where, cudaGetErrorString(e));
+}
+
 template <class F>
 static int32_t guarded(F&& f) {
     try {
+        clear_stale_cuda_error("found at entry");
         f();
+        clear_stale_cuda_error("left by this call");
         return VGPU_OK;
     } catch (const vplan::InvalidRequest& e) {
         t_error = e.what();
@@ -124,6 +133,7 @@ void vgpu_index_close(vgpu_index* idx) {
     if (idx->ix) cudaSetDevice(idx->ix->device);
     delete idx;
     vdev::ScratchPool::instance().trim();
+    clear_stale_cuda_error("left by vgpu_index_close");
 }
 
 int32_t vgpu_index_info(const vgpu_index* idx, uint64_t* num_docs, uint64_t* anchor_lo, uint64_t* anchor_hi, uint64_t* device_bytes) {
@@ -392,8 +402,9 @@ int32_t vgpu_batch_execute_finish(vgpu_batch* batch) {
 
 void vgpu_batch_free(vgpu_batch* batch) {
     if (!batch) return;
-    if (batch->b.ix) cudaSetDevice(batch->b.ix->device);
+    if (batch->b.device >= 0) cudaSetDevice(batch->b.device);  // (the batch's own copy: its index may be closed already)
     delete batch;
+    clear_stale_cuda_error("left by vgpu_batch_free");
 }
 
 int32_t vgpu_batch_size(const vgpu_batch* batch, uint32_t* n) {

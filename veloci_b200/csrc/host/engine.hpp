@@ -84,6 +84,7 @@ inline bool& plan_for_all_ranks() {
 
 struct Batch {
     DeviceIndex* ix = nullptr;
+    int device = -1;  // ix->device, kept for the batch's destruction
     vplan::BatchPlan plan;
     uint32_t n = 0, n_parts = 0;
     cudaStream_t stream = nullptr;
@@ -396,6 +397,7 @@ struct Batch {
 
     void upload_plan() {
         VDEV_CUDA(cudaSetDevice(ix->device));
+        device = ix->device;
         n_parts = (uint32_t)plan.parts.size();
         VDEV_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (auto& e : ev) VDEV_CUDA(cudaEventCreate(&e));
