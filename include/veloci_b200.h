@@ -141,11 +141,15 @@ int32_t vgpu_batch_prepare_from_plan(vgpu_index* idx, const void* blob, size_t l
 /* The same through shared memory, for the processes of one box: a named channel (POSIX shared memory) that local rank 0
  * publishes plans into and the other local ranks read from.  vgpu_batch_prepare_shared is a collective over the
  * channel's ranks: rank 0 passes the requests, parses, plans and publishes; the others pass NULL / 0, wait for the plan
- * and import it.  Two plans may be in flight (rank 0 can run one batch ahead).  `capacity` bounds the blob size. */
+ * and import it.  Batches are numbered by tickets: every rank calls vgpu_plan_channel_ticket once per batch, in the order
+ * the batches will be executed (1, 2, ...), and passes the ticket to the prepare; prepares of consecutive tickets may
+ * then run concurrently on different threads (two plans can be in the making or in flight at once).  `capacity`
+ * bounds the blob size. */
 typedef struct vgpu_plan_channel vgpu_plan_channel;
 int32_t vgpu_plan_channel_open(const char* name, uint32_t local_rank, uint32_t local_ranks, size_t capacity, vgpu_plan_channel** out);
 void vgpu_plan_channel_close(vgpu_plan_channel* ch);
-int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, const char* text, size_t len, uint32_t n, vgpu_batch** out);
+uint64_t vgpu_plan_channel_ticket(vgpu_plan_channel* ch);
+int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, uint64_t ticket, const char* text, size_t len, uint32_t n, vgpu_batch** out);
 
 /* ---- multi-GPU merge driven by the host (the pieces vgpu_batch_execute runs by itself once vgpu_comm_init was called;
  * kept for hosts with their own transport and for single-device tests of several shards) ----------------------

@@ -64,7 +64,9 @@ def load_library():
     L.vgpu_plan_channel_open.argtypes = [cp, u32, u32, ctypes.c_size_t, P(vp)]
     L.vgpu_plan_channel_close.argtypes = [vp]
     L.vgpu_plan_channel_close.restype = None
-    L.vgpu_batch_prepare_shared.argtypes = [vp, vp, ctypes.c_char_p, ctypes.c_size_t, u32, P(vp)]
+    L.vgpu_batch_prepare_shared.argtypes = [vp, vp, u64, ctypes.c_char_p, ctypes.c_size_t, u32, P(vp)]
+    L.vgpu_plan_channel_ticket.argtypes = [vp]
+    L.vgpu_plan_channel_ticket.restype = u64
     L.vgpu_index_close.argtypes = [vp]
     L.vgpu_index_close.restype = None
     L.vgpu_index_info.argtypes = [vp, P(u64), P(u64), P(u64), P(u64)]
@@ -172,7 +174,7 @@ def _from_hitlist(L, hl):
 class Batch:
     """A prepared batch of requests (vgpu_batch_prepare / execute / fetch)."""
 
-    def __init__(self, index, requests, plan=None, channel=None):
+    def __init__(self, index, requests, plan=None, channel=None, ticket=None):
         """`requests`: the batch.  `plan`: a blob from `export_plan()` of another handle of the same directory (the requests
         are then not parsed again; pass their count or the list).  `channel`: a PlanChannel -- local rank 0 plans and
         publishes, the other local ranks import (collective over the channel's ranks)."""
@@ -186,7 +188,9 @@ class Batch:
             return
         if channel is not None:
             blob = b"" if channel.rank != 0 else _join_lines(requests)
-            _check(self.L.vgpu_batch_prepare_shared(index.h, channel.h, blob if channel.rank == 0 else None, len(blob), self.n if channel.rank == 0 else 0, ctypes.byref(self.h)))
+            if ticket is None:
+                ticket = channel.ticket()
+            _check(self.L.vgpu_batch_prepare_shared(index.h, channel.h, ticket, blob if channel.rank == 0 else None, len(blob), self.n if channel.rank == 0 else 0, ctypes.byref(self.h)))
             self.n = self._size()
             return
         if self.n >= 64 and self._prepare_lines(index, requests):
@@ -358,6 +362,10 @@ class PlanChannel:
         self.h = ctypes.c_void_p()
         _check(self.L.vgpu_plan_channel_open(name.encode(), local_rank, local_ranks, capacity, ctypes.byref(self.h)))
 
+    def ticket(self):
+        """Number of the caller's next batch; taken once per batch in execution order (by every rank alike)."""
+        return int(self.L.vgpu_plan_channel_ticket(self.h))
+
     def close(self):
         if self.h:
             self.L.vgpu_plan_channel_close(self.h)
@@ -392,8 +400,8 @@ class Index:
         _check(self.L.vgpu_index_info(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
         return {"num_docs": a.value, "anchor_lo": b.value, "anchor_hi": c.value, "device_bytes": d.value}
 
-    def prepare(self, requests, plan=None, channel=None):
-        return Batch(self, requests, plan=plan, channel=channel)
+    def prepare(self, requests, plan=None, channel=None, ticket=None):
+        return Batch(self, requests, plan=plan, channel=channel, ticket=ticket)
 
     def search(self, request):
         b = Batch(self, [request]).execute()
@@ -413,26 +421,36 @@ class Index:
         _check(self.L.vgpu_search_batch(self.h, arr, n, k, ids.ctypes.data, scores.ctypes.data, num_hits.ctypes.data, status.ctypes.data))
         return {"ids": ids, "scores": scores, "num_hits": num_hits, "status": status}
 
-    def search_stream(self, batches, k=10, run=None, channel=None):
+    def search_stream(self, batches, k=10, run=None, channel=None, depth=None):
         """Evaluates a sequence of request batches, yielding one `results_flat(k)` dict per batch, in order.
 
-        A planner thread parses, plans and uploads batch i+1 (`vgpu_batch_prepare`, host work + H2D on its own stream)
-        while the calling thread has batch i on the GPU and reads its rows back: the steady-state time per batch is
-        max(prepare, execute + fetch) instead of their sum.  `run(batch)` replaces the plain `batch.execute()` when
-        the caller has more to do per batch (the sharded path: threshold exchange, all-gather, merge)."""
+        Planner threads parse, plan and upload the next batches (`vgpu_batch_prepare`, host work + H2D on the batch's own
+        stream) while the calling thread has batch i on the GPU and reads its rows back: the steady-state time per batch
+        is max(prepare / depth, execute + fetch) instead of their sum.  `depth` batches are prepared ahead, each on its own
+        thread (default: 1; 2 with a plan channel, where one process plans for every rank of the box and planning, not the
+        GPUs, bounds the rate).  `run(batch)` replaces the plain `batch.execute()` when the caller has more to do per batch."""
+        from collections import deque
         from concurrent.futures import ThreadPoolExecutor
+        if depth is None:
+            depth = 2 if channel is not None else 1
         it = iter(batches)
-        with ThreadPoolExecutor(max_workers=1, thread_name_prefix="veloci-plan") as planner:
+        with ThreadPoolExecutor(max_workers=depth, thread_name_prefix="veloci-plan") as planner:
+            ahead = deque()
+
             def plan_next():
                 try:
                     reqs = next(it)
                 except StopIteration:
-                    return None
-                return planner.submit(self.prepare, reqs, None, channel)
-            ahead = plan_next()
-            while ahead is not None:
-                batch = ahead.result()
-                ahead = plan_next()
+                    return False
+                ticket = channel.ticket() if channel is not None else None  # in execution order, on this thread
+                ahead.append(planner.submit(self.prepare, reqs, None, channel, ticket))
+                return True
+
+            while len(ahead) < depth and plan_next():
+                pass
+            while ahead:
+                batch = ahead.popleft().result()
+                plan_next()
                 try:
                     if run is None:
                         batch.execute()

@@ -297,8 +297,10 @@ int32_t vgpu_plan_channel_open(const char* name, uint32_t local_rank, uint32_t l
 
 void vgpu_plan_channel_close(vgpu_plan_channel* ch) { delete ch; }
 
-int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, const char* text, size_t len, uint32_t n, vgpu_batch** out) {
-    if (!idx || !ch || !out) {
+uint64_t vgpu_plan_channel_ticket(vgpu_plan_channel* ch) { return ch ? ch->ch->ticket() : 0; }
+
+int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, uint64_t ticket, const char* text, size_t len, uint32_t n, vgpu_batch** out) {
+    if (!idx || !ch || !out || ticket == 0) {
         t_error = "null argument";
         return VGPU_ERR_INVALID_REQUEST;
     }
@@ -320,8 +322,8 @@ int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, const 
         const auto t2 = std::chrono::steady_clock::now();
         const std::string failure = t_error;
         const int32_t pub = guarded([&]() {
-            if (rc == VGPU_OK) ch->ch->publish(bytes.data(), bytes.size(), 0);
-            else ch->ch->publish(failure.data(), std::min(failure.size(), ch->ch->capacity()), (uint64_t)rc);
+            if (rc == VGPU_OK) ch->ch->publish(ticket, bytes.data(), bytes.size(), 0);
+            else ch->ch->publish(ticket, failure.data(), std::min(failure.size(), ch->ch->capacity()), (uint64_t)rc);
         });
         if (getenv("VELOCI_DEBUG")) {
             auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
@@ -343,7 +345,7 @@ int32_t vgpu_batch_prepare_shared(vgpu_index* idx, vgpu_plan_channel* ch, const 
     auto t1 = t0;
     const int32_t rc = guarded([&]() {
         std::unique_ptr<vgpu_batch> b(new vgpu_batch());
-        ch->ch->consume([&](const uint8_t* data, size_t blob_len, uint64_t status) {
+        ch->ch->consume(ticket, [&](const uint8_t* data, size_t blob_len, uint64_t status) {
             t1 = std::chrono::steady_clock::now();
             if (status != 0) {
                 remote = (int32_t)status, remote_msg.assign(reinterpret_cast<const char*>(data), blob_len);

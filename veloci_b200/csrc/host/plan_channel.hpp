@@ -1,7 +1,7 @@
 // Plans through POSIX shared memory between the processes of one box (vgpu_plan_channel_*): local rank 0 publishes
 // the plan blob of each batch (plan_blob.hpp), the other local ranks import it.  Two slots, so the publisher may be one
-// batch ahead of the slowest consumer (the planner thread of Index.search_stream works on batch k + 1 while batch k is
-// on the GPUs).  Synchronisation is a sequence number per slot (release / acquire on lock-free 64-bit atomics in the
+// batch ahead of the slowest consumer, and two plans may be in the making at once (Index.search_stream keeps two
+// planner threads busy while a batch is on the GPUs: batches are numbered by tickets taken in execution order).  Synchronisation is a sequence number per slot (release / acquire on lock-free 64-bit atomics in the
 // mapping) and one "consumed up to" counter per (slot, rank); waiting is a bounded spin, then short sleeps.
 #pragma once
 #include <fcntl.h>
@@ -93,9 +93,12 @@ class PlanChannel {
     uint32_t rank() const { return rank_; }
     size_t capacity() const { return capacity_; }
 
-    // rank 0: the next plan (status 0) or the failure the consumers must see instead of waiting for ever
-    void publish(const void* data, size_t len, uint64_t status) {
-        const uint64_t seq = ++seq_;
+    // Sequence number of the caller's next batch (1, 2, ...).  Every rank takes its tickets in the same order (the order
+    // the batches will be executed in); the prepares themselves may then run concurrently, two at a time.
+    uint64_t ticket() { return next_ticket_.fetch_add(1, std::memory_order_relaxed) + 1; }
+
+    // rank 0: plan number `seq` (status 0) or the failure the consumers must see instead of waiting for ever
+    void publish(uint64_t seq, const void* data, size_t len, uint64_t status) {
         const uint32_t slot = (uint32_t)(seq & 1u);
         if (len > capacity_) throw ChannelError("plan channel: blob of " + std::to_string(len) + " bytes exceeds the capacity of " + std::to_string(capacity_));
         for (uint32_t r = 1; r < n_ranks_; ++r)  // the slot's previous plan (seq - 2) must have been taken by everyone
@@ -106,10 +109,9 @@ class PlanChannel {
         hdr_->ready_seq[slot].store(seq, std::memory_order_release);
     }
 
-    // ranks > 0: waits for the next plan; `use(data, len, status)` runs while the slot is held
+    // ranks > 0: waits for plan number `seq`; `use(data, len, status)` runs while the slot is held
     template <class F>
-    void consume(F&& use) {
-        const uint64_t seq = ++seq_;
+    void consume(uint64_t seq, F&& use) {
         const uint32_t slot = (uint32_t)(seq & 1u);
         wait_until([&]() { return hdr_->ready_seq[slot].load(std::memory_order_acquire) == seq; }, "local rank 0 to publish the plan");
         const size_t len = (size_t)hdr_->len[slot].load(std::memory_order_relaxed);
@@ -141,7 +143,7 @@ class PlanChannel {
     size_t capacity_ = 0, map_len_ = 0;
     uint8_t* base_ = nullptr;
     Header* hdr_ = nullptr;
-    uint64_t seq_ = 0;
+    std::atomic<uint64_t> next_ticket_{0};
 };
 
 }  // namespace vplan
