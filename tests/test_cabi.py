@@ -78,3 +78,32 @@ def test_python_loader_has_no_fallback(monkeypatch):
     with pytest.raises(veloci_b200.api.VelociGpuError) as e:
         api.load_library()
     assert e.value.status == 6
+
+
+def test_plan_channel_opens_between_ranks_without_a_device(lib):
+    """The shared-memory plan channel is host-only: rank 0 creates it, another rank (here: a thread) attaches, tickets
+    count batches from 1, a rank count that disagrees with rank 0's is refused."""
+    import threading
+
+    vp, u32, u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64
+    lib.vgpu_plan_channel_open.argtypes = [ctypes.c_char_p, u32, u32, ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.vgpu_plan_channel_close.argtypes = [vp]
+    lib.vgpu_plan_channel_close.restype = None
+    lib.vgpu_plan_channel_ticket.argtypes = [vp]
+    lib.vgpu_plan_channel_ticket.restype = u64
+    lib.vgpu_last_error.restype = ctypes.c_char_p
+    name = f"/vb200_cabi_{os.getpid()}".encode()
+    other, rc_other = vp(), []
+    t = threading.Thread(target=lambda: rc_other.append(lib.vgpu_plan_channel_open(name, 1, 2, 1 << 20, ctypes.byref(other))))
+    t.start()  # waits until rank 0 has created the segment
+    mine = vp()
+    assert lib.vgpu_plan_channel_open(name, 0, 2, 1 << 20, ctypes.byref(mine)) == 0, lib.vgpu_last_error()
+    t.join(timeout=30)
+    assert rc_other == [0] and other.value
+    assert [lib.vgpu_plan_channel_ticket(mine) for _ in range(3)] == [1, 2, 3]
+    assert lib.vgpu_plan_channel_ticket(other) == 1
+    wrong = vp()
+    assert lib.vgpu_plan_channel_open(name, 1, 3, 1 << 20, ctypes.byref(wrong)) != 0  # rank count differs from rank 0's
+    assert lib.vgpu_plan_channel_open(name, 5, 2, 1 << 20, ctypes.byref(wrong)) != 0  # rank out of range
+    lib.vgpu_plan_channel_close(other)
+    lib.vgpu_plan_channel_close(mine)
