@@ -1,4 +1,4 @@
-"""One-off stress: the plane path against the posting path (VELOCI_NO_PLANES) on a mid-size corpus, bit for bit,
+"""One-off stress: the plane path against the posting path (`Index(..., planes=False)`) on a mid-size corpus, bit for bit,
 over several request shapes (with / without boost, k from 1 to 64, skips, single terms, levenshtein 0-2)."""
 import json, os, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -26,8 +26,7 @@ for i, r in enumerate(reqs):
         j["skip"] = int(rng.integers(0, 64 - min(63, j["top"]) + 1))
     out.append(json.dumps(j))
 a = veloci_b200.Index(d); ba = a.prepare(out); ba.execute(); ra = ba.results_flat(64); sa = ba.path_stats()
-os.environ["VELOCI_NO_PLANES"] = "1"
-b = veloci_b200.Index(d); bb = b.prepare(out); bb.execute(); rb = bb.results_flat(64); sb = bb.path_stats()
+b = veloci_b200.Index(d, planes=False); bb = b.prepare(out); bb.execute(); rb = bb.results_flat(64); sb = bb.path_stats()
 print("paths", sa, sb)
 assert sa["plane_items"] > 0 and sb["plane_items"] == 0
 ok = (ra["status"] == 0).all() and (rb["status"] == 0).all()
