@@ -319,7 +319,8 @@ struct alignas(16) QueryProgram {  // 112 B
     uint32_t post_begin, post_len;  // post ops, into the program words
     uint32_t facet_begin, n_facets; // into the FacetStep table
     uint32_t n_leaf_boosts;         // kOpLeafBoost ops in the program (at most kMaxLeafBoosts)
-    uint32_t pad2[3];
+    uint32_t must_mask;             // bit l: leaf l is a direct search-part child of a root `and`: a tile where it has no posting has no hit
+    uint32_t pad2[2];
 };
 static_assert(sizeof(QueryProgram) == 112, "QueryProgram layout");
 static const uint32_t kMaxLeafBoosts = 4;

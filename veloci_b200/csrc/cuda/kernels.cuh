@@ -233,6 +233,8 @@ struct PlaneArgs {
     uint32_t group_begin, group_end;      // this launch evaluates the items of groups [group_begin, group_end)
     const uint32_t* ones_row;             // constant rows of at least group_tiles * 256 words: all ones, all zeros
     const uint32_t* zeros_row;
+    uint32_t item_batch;                  // items a warp takes from the work counter at a time
+    uint32_t seed_sweep_words;            // 32-anchor words of a seed row the seed pass looks at (a multiple of 128)
     // per-query state (shared with tile_eval_kernel)
     unsigned long long* heap;
     uint32_t heap_stride;

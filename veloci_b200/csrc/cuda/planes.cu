@@ -37,8 +37,6 @@ static const uint32_t kMergeGroup = 8;     // keys of one request merged into it
 static const uint32_t kHashSlots = 1024;   // >= 2 * kGroupMaxEntries
 static const uint32_t kHashEmpty = 0xFFFFFFFFu;
 static const uint32_t kPartShift = 20;     // entry code = anchor index in the group | part << 20
-static const uint32_t kItemBatch = 4;      // items a warp takes from the work counter at a time
-static const uint32_t kSeedSweepWords = 16384;  // 32-anchor words of a seed row the seed pass looks at (a multiple of 128)
 static_assert(kHashSlots >= 2 * kGroupMaxEntries, "hash load factor");
 
 struct alignas(16) WarpScratch {
@@ -523,10 +521,10 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
 
     while (true) {
         uint32_t first = 0;
-        if (lane == 0) first = (uint32_t)atomicAdd(a.work_counter, (unsigned long long)kItemBatch);
+        if (lane == 0) first = (uint32_t)atomicAdd(a.work_counter, (unsigned long long)a.item_batch);
         first = ibeg + __shfl_sync(0xFFFFFFFFu, first, 0);
         if (first >= iend) break;
-        const uint32_t last = min(iend, first + kItemBatch);
+        const uint32_t last = min(iend, first + a.item_batch);
 #pragma unroll 1
         for (uint32_t ii = first; ii < last; ++ii) {
             // ---- item (tiles [t0, t0 + n), request q)
@@ -976,9 +974,9 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_seed_kernel(PlaneArgs 
             }
             qn = 0;
         };
-        // the set is in descending boost order: its first kSeedSweepWords words (the shard's best-boosted half million anchors)
+        // the set is in descending boost order: its first seed_sweep_words words (the shard's best-boosted half million anchors)
         // hold the seeds that matter, and bound the pass however large the shard is
-        const uint32_t sweep_w4 = min(seed_words, kSeedSweepWords) >> 2;
+        const uint32_t sweep_w4 = min(seed_words, a.seed_sweep_words) >> 2;
 #pragma unroll 1
         for (uint32_t cw4 = lane; cw4 < sweep_w4; cw4 += 32) {
             uint4 cm = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), cur = make_uint4(0u, 0u, 0u, 0u);

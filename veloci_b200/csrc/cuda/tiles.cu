@@ -55,19 +55,24 @@ __device__ __forceinline__ const uint32_t* dense_row(const uint32_t* toff, const
 // Postings and non-empty slices of request `qp` in tile t.
 __device__ __forceinline__ void tile_totals(const ItemScanArgs& a, const QueryProgram& qp, uint32_t t, uint32_t& all_post, uint32_t& all_slices) {
     all_post = 0, all_slices = 0;
+    bool dead = false;  // a part the root `and` needs has no posting in the tile: no hit, nothing to evaluate (set_op.rs:368-446)
     for (uint32_t l = 0; l < qp.n_leaves; ++l) {
         const PartSlices ps = a.slices[a.leaf_part[qp.leaf_begin + l]];
+        uint32_t leaf_post = 0;
         for (uint32_t r = 0; r < ps.n_dense; ++r) {
             const uint32_t* trow = dense_row(a.toff, a.plane_tprefix, a.g_row, a.g_plane, ps.m_begin + r, a.n_tiles);
             const uint32_t n = trow[t + 1] - trow[t];
-            all_post += n, all_slices += n ? 1u : 0u;
+            leaf_post += n, all_slices += n ? 1u : 0u;
         }
         if (ps.n_match != ps.n_dense) {
             const uint32_t* brow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
             const uint32_t n = brow[t + 1] - brow[t];
-            all_post += n, all_slices += n ? 1u : 0u;
+            leaf_post += n, all_slices += n ? 1u : 0u;
         }
+        all_post += leaf_post;
+        if (leaf_post == 0 && l < 32 && ((qp.must_mask >> l) & 1u)) dead = true;
     }
+    if (dead) all_post = 0, all_slices = 0;
 }
 
 // Entries (postings of non-plane terms) of request `qp` in tile t, over its parts; false when the tile cannot take the

@@ -387,6 +387,8 @@ struct BatchPlan {
     std::vector<std::string> cur_ids_keys;             // parts that are also searched for ids (filter, phrase boosts)
     bool cur_leaf_boost = false;
     uint32_t cur_n_leaf_boosts = 0;
+    const vhost::SearchRequest* cur_root = nullptr;    // the request's root node
+    uint32_t cur_must_mask = 0;                        // leaves that are direct search-part children of a root `and`
 
     Node emit(const vhost::SearchRequest& r, std::vector<uint32_t>& leaves, std::vector<uint32_t>& code, bool ids_only = false,
               const std::vector<vhost::BoostPart>& boosts = std::vector<vhost::BoostPart>()) {
@@ -486,6 +488,9 @@ struct BatchPlan {
             code.push_back((uint32_t)n_terms);
             for (auto& k : kids) code.push_back((uint32_t)(std::lower_bound(terms, terms + n_terms, &k.term, less) - terms));
         } else {
+            if (&r == cur_root && !ids_only)
+                for (auto& k : kids)
+                    if (k.leaf >= 0 && k.leaf < 32) cur_must_mask |= 1u << k.leaf;
             code.push_back(vdev::kOpIntersect);
             code.push_back((uint32_t)kids.size());
             for (size_t i = 0; i < kids.size(); ++i) code.push_back((uint32_t)i);  // sum order, patched on the device
@@ -593,6 +598,7 @@ struct BatchPlan {
         std::vector<BoostStep>& steps = scratch_steps;
         steps.clear();
         cur_steps = &steps, cur_leaf_boost = false, cur_n_leaf_boosts = 0;
+        cur_root = &root, cur_must_mask = 0;
         cur_ids_keys.clear();
         if (request.phrase_boosts)
             for (auto& pb : *request.phrase_boosts) cur_ids_keys.push_back(pb.search1.key()), cur_ids_keys.push_back(pb.search2.key());
@@ -735,6 +741,7 @@ struct BatchPlan {
         qp.post_len = (uint32_t)post.size();
         prog.insert(prog.end(), post.begin(), post.end());
         qp.n_leaf_boosts = cur_n_leaf_boosts;
+        qp.must_mask = cur_must_mask;
         qp.facet_begin = rp.facet_begin;
         qp.n_facets = (uint32_t)rp.facets.size();
         qp.boost_begin = (uint32_t)boosts.size();
