@@ -974,7 +974,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_seed_kernel(PlaneArgs 
             }
             qn = 0;
         };
-        // the set is in descending boost order: its first seed_sweep_words words (the shard's best-boosted half million anchors)
+        // the set is in descending boost order: its first seed_sweep_words words (the shard's best-boosted 128 Ki anchors)
         // hold the seeds that matter, and bound the pass however large the shard is
         const uint32_t sweep_w4 = min(seed_words, a.seed_sweep_words) >> 2;
 #pragma unroll 1

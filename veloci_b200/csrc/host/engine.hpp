@@ -727,9 +727,10 @@ struct Batch {
         a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
         a.group_tiles = group_tiles, a.group_begin = g0, a.group_end = g1;
         a.ones_row = ix->planes.const_rows.p, a.zeros_row = ix->planes.const_rows.p + PlaneSetDev::kConstRowWords;
-        // items per trip to the work counter: four when every warp gets dozens of items, one on small shards (tail balance)
-        a.item_batch = pending_fast_items > (uint32_t)n_sms * 16u * 32u ? 4u : 1u;
-        a.seed_sweep_words = 16384;
+        // one item per trip to the work counter (batches of four: +0.1 ms at N = 1, +0.2 ms on a 1/8 shard: tail imbalance) and
+        // the best-boosted 128 Ki anchors of the seed set (`tools/seed_probe.py`, profiles/r02x_seed_probe.jsonl)
+        a.item_batch = 1;
+        a.seed_sweep_words = 4096;
         if (const char* env = probe_env("VELOCI_ITEM_BATCH")) a.item_batch = (uint32_t)std::max(1, atoi(env));
         if (const char* env = probe_env("VELOCI_SEED_WORDS")) a.seed_sweep_words = (uint32_t)std::max(128, atoi(env) / 128 * 128);
         a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
