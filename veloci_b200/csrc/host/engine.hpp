@@ -240,7 +240,9 @@ struct Batch {
         // Up to 16 planner threads; when several ranks share the host (LOCAL_WORLD_SIZE, set by torchrun) each takes its
         // share of the cores but at least 8: at N = 4 on 32 cores, 8 threads per rank plan a batch in 10.5 ms where 16
         // (128 runnable threads with the ranks' other threads) take 12.4 ms and 4 cannot keep up with the GPU.
-        unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        // at most 16 threads and three quarters of the cores: the thread that launches the previous batch's kernels needs one
+        // (N = 1 on 16 cores, end to end: 12 threads 656k requests/s, 16 threads 547k-631k; `VELOCI_PLAN_THREADS` overrides)
+        unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency() * 3 / 4));
         if (plan_for_all_ranks()) {
             // This process plans for every rank of the box (vgpu_batch_prepare_shared): the other ranks' cores are its to use,
             // but two batches are planned at a time (Index.search_stream, plan channel tickets), so each takes half of them.
