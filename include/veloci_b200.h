@@ -195,6 +195,26 @@ int32_t vgpu_suggest(vgpu_index* idx, const char* request_json, vgpu_suggestions
 int32_t vgpu_suggest_part(vgpu_index* idx, const char* part_json, vgpu_suggestions* out);
 void vgpu_suggestions_free(vgpu_suggestions* s);
 
+/* ---- request generation (host side, no kernel) ------------------------------
+ * query_generator::search_query (src/query_generator.rs:175-257) with the query language of the `query_parser` crate
+ * (query_parser/src/lexer.rs:107-195, parser.rs:141-190): `params_json` is a SearchQueryGeneratorParameters
+ * (src/query_generator.rs:44-83: search_term, parser_options, top, skip, ignore_case, levenshtein,
+ * levenshtein_auto_limit, facetlimit, why_found, text_locality, boost_queries, facets, fields, boost_fields, boost_terms,
+ * phrase_pairs, explain, filter, filter_parser_options); `*request_json` receives the search::Request as the reference's
+ * serde derive would write it (NUL-terminated, released with vgpu_free), ready for vgpu_batch_prepare.  Field fan-out
+ * (query_parser_to_veloci_request.rs:85-114), automatic edit distance (src/query_generator.rs:85-99,129-132), "term*"
+ * prefix and "a*b" regex parts (query_parser_to_veloci_request.rs:44-65), phrase pairs (src/query_generator.rs:268-295)
+ * and the simplification of nested or/and (src/search/request/search_request.rs:27-76) are the reference's.  Errors: a
+ * query that does not parse -> VGPU_ERR_INVALID_REQUEST with the ParseError text; FieldNotFound -> VGPU_ERR_FIELD_NOT_FOUND;
+ * AllFieldsFiltered -> VGPU_ERR_INVALID_REQUEST; parameters that do not deserialize -> VGPU_ERR_JSON.
+ * vgpu_suggest_query is suggest_query (src/query_generator.rs:297-322); `params_json` = {"request": text, "top", "skip",
+ * "levenshtein", "fields", "levenshtein_auto_limit"}; the result goes to vgpu_suggest.
+ * vgpu_query_parse is query_parser::parse_with_opt alone: the Debug text of the tree (query_parser/src/ast.rs:51-59);
+ * `options` bit 0 no_attributes, bit 1 no_parentheses, bit 2 no_levensthein (query_parser/src/lib.rs:43-54). */
+int32_t vgpu_search_query(vgpu_index* idx, const char* params_json, char** request_json);
+int32_t vgpu_suggest_query(vgpu_index* idx, const char* params_json, char** request_json);
+int32_t vgpu_query_parse(const char* text, uint32_t options, char** tree_debug);
+
 /* ---- step seam -------------------------------------------------------------
  * One symbol per PlanStep kind (src/plan_creator/plan_steps.rs:18-74), each over host
  * hit lists; used by the step-level parity tests.  Outputs are malloc'd by the

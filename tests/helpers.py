@@ -63,6 +63,37 @@ def synthetic_requests(**params):
         os.unlink(path)
 
 
+def query_parse(text, what=0, no_attributes=False, no_parentheses=False, no_levensthein=False):
+    """The product's query parser (csrc/host/query_parser.hpp) through the host-only helper library.
+    what: 0 Debug text of the tree, 1 phrase pairs, 2 terms, 3 tokens.  Returns (ok, text-or-JSON)."""
+    lib = _index_lib()
+    lib.vidx_query_parse.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
+    out = ctypes.create_string_buffer(1 << 16)
+    rc = lib.vidx_query_parse(text.encode("utf-8"), int(no_attributes) | int(no_parentheses) << 1 | int(no_levensthein) << 2, what, out, len(out))
+    s = out.value.decode("utf-8")
+    return rc == 0, (json.loads(s) if rc == 0 and what else s)
+
+
+def query_filter_stopwords(text, stopwords):
+    lib = _index_lib()
+    lib.vidx_query_filter_stopwords.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+    out = ctypes.create_string_buffer(1 << 16)
+    rc = lib.vidx_query_filter_stopwords(text.encode("utf-8"), json.dumps(sorted(stopwords), ensure_ascii=False).encode("utf-8"), out, len(out))
+    assert rc == 0, out.value
+    return out.value.decode("utf-8")
+
+
+def generate_request(directory, params, suggest=False):
+    """search_query / suggest_query of the product's host code over the index in `directory` (no device).
+    Returns (status, request dict or message, raw text)."""
+    lib = _index_lib()
+    lib.vidx_generate_request.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
+    out = ctypes.create_string_buffer(1 << 20)
+    rc = lib.vidx_generate_request(directory.encode(), json.dumps(params, ensure_ascii=False).encode("utf-8"), int(suggest), out, len(out))
+    s = out.value.decode("utf-8")
+    return rc, (json.loads(s) if rc == 0 else s), s
+
+
 class Oracle:
     def __init__(self, directory=None):
         self.lib = ctypes.CDLL(build.build_oracle())

@@ -152,3 +152,44 @@ TEST_FACET_DOCS = [
     {"meanings": {"eng": ["test1"], "ger": ["der test", "das ist ein guter Treffer"]}},
     {"commonness": 20, "tags": ["Eis", "cool"]},
 ]
+
+# ---- tests/all/test_query_generator.rs:10-137 (the corpus of the query-generator tests)
+TEST_QG_CONFIG = {
+    "*GLOBAL*": {"features": ["All"]},
+    "commonness": {"facet": True, **BOOST},
+    "ent_seq": {"fulltext": {"tokenize": True}},
+    "nofulltext": {"fulltext": {"tokenize": False}},
+    "tags[]": {"facet": True},
+    "field1[].rank": dict(BOOST),
+    "field1[].text": {"tokenize": True},
+    "kanji[].text": {"tokenize": True},
+    "meanings.ger[]": {"stopwords": ["stopword"], "fulltext": {"tokenize": True}},
+    "meanings.eng[]": {"fulltext": {"tokenize": True}},
+    "kanji[].commonness": dict(BOOST),
+    "kana[].commonness": dict(BOOST),
+}
+TEST_QG_DOCS = [
+    {"commonness": 123456, "ent_seq": "99999", "tags": ["nice", "cool"]},
+    {
+        "ent_seq": "1337",
+        "commonness": 20,
+        "tags": ["nice", "cool", "ent_seq:99999"],
+        "kanji": [{"text": "偉容", "commonness": 0}, {"text": "威容", "commonness": 5}],
+        "kana": [{"text": "いよう", "romaji": "Iyou", "commonness": 5}],
+        "meanings": {"eng": ["will testo"], "ger": ["majestätischer Anblick (m)", "majestätisches Aussehen (n)", "Majestät (f)"]},
+    },
+    {
+        "ent_seq": "1587690",
+        "commonness": 20,
+        "tags": ["nice"],
+        "kanji": [{"text": "意欲", "commonness": 40}, {"text": "意慾", "commonness": 0}],
+        "kana": [{"text": "いよく", "romaji": "Iyoku", "commonness": 40}],
+        "meanings": {"eng": ["will", "urge", "having a long torso"], "ger": ["Wollen (n)", "Wille (m)", "Begeisterung (f)", "begeistern"]},
+    },
+    {"id": 1234566, "tags": ["awesome", "cool"], "commonness": 500, "kanji": [{"text": "意慾", "commonness": 20}], "kana": [{"text": "いよく"}], "ent_seq": "1587700"},
+    {"commonness": 515151, "ent_seq": "25", "tags": ["nice", "cool"]},
+    {"commonness": 30, "title": "COllectif", "meanings": {"ger": ["boostemich"]}},
+    {"commonness": 30, "float_value": 5.123, "ent_seq": "26", "tags": ["nice", "coolo"]},
+    {"commonness": 20, "ent_seq": "27", "my_bool": True, "tags": ["Eis", "cool"]},
+    {"commonness": 20, "ent_seq": "28", "tags": ["nice", "cool"]},
+]

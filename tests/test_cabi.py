@@ -107,3 +107,14 @@ def test_plan_channel_opens_between_ranks_without_a_device(lib):
     assert lib.vgpu_plan_channel_open(name, 5, 2, 1 << 20, ctypes.byref(wrong)) != 0  # rank out of range
     lib.vgpu_plan_channel_close(other)
     lib.vgpu_plan_channel_close(mine)
+
+
+def test_query_parse_needs_no_device(lib):
+    """vgpu_query_parse is host code only (query_parser/src/parser.rs:26-28): it answers on a box without a GPU."""
+    from veloci_b200 import api
+
+    assert api.query_parse("a AND b:(c d~2)") == '("a" AND b:("c" OR "d"~2))'
+    assert api.query_parse("(cool)", no_parentheses=True) == '"(cool)"'
+    with pytest.raises(api.VelociGpuError) as e:
+        api.query_parse("fancy~")
+    assert e.value.status == 1 and "Expecting a levenshtein number" in str(e.value)

@@ -322,3 +322,61 @@ def test_facet_step(gpu, sharded_corpus):
         got = index.facet({"field": field, "top": top}, ids)
         assert [(t, c, i) for t, c, i in got] == [(r[0], r[1], r[2]) for r in ref], top
     assert index.facet({"field": field}, []) == []
+
+
+def test_generated_requests_on_the_reference_corpus(gpu, native_libs):
+    """Request generation through the C ABI (vgpu_search_query, vgpu_suggest_query) on the corpus of
+    tests/all/test_query_generator.rs: the text the library generates equals the plain-Python oracle's request, the batch
+    planner takes it as is, and the hits are the CPU oracle's (and the ones the reference's tests assert)."""
+    import ref_fixtures as fx
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import query_generator as qg  # test infrastructure
+
+    d = tempfile.mkdtemp(prefix="vb200_r2_qg_")
+    helpers.create_index(d, fx.TEST_QG_DOCS, fx.TEST_QG_CONFIG)
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    meta = json.load(open(os.path.join(d, "metaData.json")))
+    cat = qg.Catalog(list(meta["columns"]), [f for f, c in meta["columns"].items() if any(i["path"] == f + ".textindex.to_anchor_id_score" for i in c["indices"])])
+    cases = [
+        ({"search_term": "urge"}, 1, "1587690"),                                            # test_query_generator.rs:170-179
+        ({"search_term": "ent_seq:99999"}, 1, "99999"),                                     # :182-189
+        ({"search_term": "ent_seq:99999", "parser_options": {"no_attributes": True}}, 1, "1337"),  # :192-204
+        ({"search_term": "urge OR いよく"}, 3, "1587690"),                                   # :207-216
+        ({"search_term": "urge AND いよく"}, 1, "1587690"),                                  # :219-228
+        ({"search_term": "urge AND いよく AND awesome"}, 0, None),                            # :296-303
+        ({"search_term": "awes*"}, 1, None), ({"search_term": "いよ*"}, 3, None), ({"search_term": "awesam*"}, 1, None),  # :306-326
+        ({"search_term": "will", "top": 10, "facets": ["commonness", "kanji[].commonness"], "levenshtein": 0, "boost_fields": {"meanings.eng[]": 1.5}}, 2, None),  # :270-280
+        ({"search_term": "will", "top": 10, "levenshtein": 0, "boost_fields": {"meanings.eng[]": 1.5}, "boost_terms": {"meanings.ger[]:majestätisches Aussehen (n)": 20.0}}, 2, "1337"),  # :282-294
+        ({"search_term": "will urge", "phrase_pairs": True, "fields": ["meanings.eng[]", "meanings.ger[]"], "text_locality": True,
+          "boost_queries": [{"path": "commonness", "boost_fun": "Log10", "param": 1}], "filter": "commonness:20 OR ent_seq:(25 26)"}, None, None),
+    ]
+    texts = []
+    for params, _, _ in cases:
+        text = index.search_query(params)
+        want = json.loads(json.dumps(qg.search_query(cat, params)))
+        assert json.loads(text).keys() == want.keys() and json.loads(text)["search_req"] == want["search_req"], params
+        texts.append(text)
+    b = index.prepare(texts).execute()
+    for q, (params, n, first) in enumerate(cases):
+        assert b.status(q) == 0, (params, b.message(q))
+        g, c = b.result(q), oracle.search(texts[q])
+        assert g["num_hits"] == c["num_hits"], params
+        ok, why = helpers.same_topk([(i, float(s)) for i, s in g["data"]], [(h[0], float(np.float32(h[1]))) for h in c["data"]])
+        assert ok, (params, why)
+        if n is not None:
+            assert len(g["data"]) == n, params
+        if first is not None:
+            assert fx.TEST_QG_DOCS[g["data"][0][0]]["ent_seq"] == first, params
+    with pytest.raises(gpu.VelociGpuError) as e:
+        index.search_query(search_term="notexistingfield:awes*")                              # :369-378
+    assert e.value.status == 2 and "Field notexistingfield not found in" in str(e.value)
+    with pytest.raises(gpu.VelociGpuError) as e:
+        index.search_query(search_term="awes*", fields=["notexistingfield"])                  # :358-367
+    assert e.value.status == 1 and "All fields filtered" in str(e.value)
+    # suggest_query feeds vgpu_suggest
+    text = index.suggest_query("Begeisteru", top=10, levenshtein=1, fields=["meanings.ger[]"])
+    assert json.loads(text) == qg.suggest_query(cat, "Begeisteru", top=10, levenshtein=1, fields=["meanings.ger[]"])
+    got = index.suggest_multi(json.loads(text))
+    ref = oracle.call("suggest_multi", request=json.loads(text))
+    assert [g[0] for g in got] == [r[0] for r in ref] and "begeisterung" in [g[0] for g in got]

@@ -109,6 +109,9 @@ def load_library():
     L.vgpu_top_n.argtypes = [vp, P(_HitList), u32, u32, P(_HitList)]
     L.vgpu_suggest.argtypes = [vp, cp, P(_Suggestions)]
     L.vgpu_suggest_part.argtypes = [vp, cp, P(_Suggestions)]
+    L.vgpu_search_query.argtypes = [vp, cp, P(vp)]
+    L.vgpu_suggest_query.argtypes = [vp, cp, P(vp)]
+    L.vgpu_query_parse.argtypes = [cp, ctypes.c_uint32, P(vp)]
     L.vgpu_suggestions_free.argtypes = [P(_Suggestions)]
     L.vgpu_suggestions_free.restype = None
     L.vgpu_launch_count.restype = u64
@@ -127,6 +130,21 @@ def load_library():
 def _check(rc):
     if rc != 0:
         raise VelociGpuError(rc, load_library().vgpu_last_error().decode("utf-8", "replace"))
+
+
+def _take_string(L, rc, out):
+    _check(rc)
+    try:
+        return ctypes.string_at(out.value).decode("utf-8")
+    finally:
+        L.vgpu_free(out)
+
+
+def query_parse(text, no_attributes=False, no_parentheses=False, no_levensthein=False):
+    """query_parser::parse_with_opt: the Debug text of the parsed query tree."""
+    L = load_library()
+    out = ctypes.c_void_p()
+    return _take_string(L, L.vgpu_query_parse(text.encode("utf-8"), int(no_attributes) | int(no_parentheses) << 1 | int(no_levensthein) << 2, ctypes.byref(out)), out)
 
 
 def device_count():
@@ -476,6 +494,20 @@ class Index:
     def suggest(self, part):
         """One RequestSearchPart; its top/skip bound the list."""
         return self._suggest(self.L.vgpu_suggest_part, part)
+
+    # ---- request generation (query_generator::search_query / suggest_query)
+    def search_query(self, params=None, **kw):
+        """SearchQueryGeneratorParameters (dict and/or keywords, e.g. search_term="nice AND cool~1") -> the request's JSON text,
+        ready for Batch / search_batch."""
+        out = ctypes.c_void_p()
+        text = json.dumps({**(params or {}), **kw}, ensure_ascii=False).encode("utf-8")
+        return _take_string(self.L, self.L.vgpu_search_query(self.h, text, ctypes.byref(out)), out)
+
+    def suggest_query(self, request, **kw):
+        """suggest_query(request, top, skip, levenshtein, fields, levenshtein_auto_limit) -> JSON text for suggest_multi."""
+        out = ctypes.c_void_p()
+        text = json.dumps({"request": request, **kw}, ensure_ascii=False).encode("utf-8")
+        return _take_string(self.L, self.L.vgpu_suggest_query(self.h, text, ctypes.byref(out)), out)
 
     # ---- step seam
     def field_search(self, part, get_scores=True, get_ids=False):

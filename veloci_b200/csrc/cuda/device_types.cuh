@@ -7,7 +7,7 @@ namespace vdev {
 static const uint32_t kDictTile = 32;       // terms per dictionary tile: one warp, one term per lane
 static const uint32_t kTilePrefixMax = 8;   // symbols of the tile's common prefix that are kept
 static const uint32_t kNoValue = 0xFFFFFFFFu;
-static const uint32_t kMaxLeaves = 12;      // search parts per request tree on the tile path
+static const uint32_t kMaxLeaves = 64;      // search parts per request tree on the tile path (one shared-memory array of a tile's anchors each)
 static const uint32_t kMaxK = 256;          // top + skip on the tile path
 
 struct TilePrefix {  // 20 bytes

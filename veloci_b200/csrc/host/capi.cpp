@@ -10,6 +10,7 @@
 
 #include "engine.hpp"
 #include "plan_channel.hpp"
+#include "query_generator.hpp"
 #include "steps.hpp"
 
 namespace vdev {
@@ -77,6 +78,15 @@ static int32_t guarded(F&& f) {
     } catch (const vplan::Unsupported& e) {
         t_error = e.what();
         return VGPU_ERR_UNSUPPORTED;
+    } catch (const vquery::ParseError& e) {
+        t_error = e.what();
+        return VGPU_ERR_INVALID_REQUEST;
+    } catch (const vquery::GeneratorError& e) {
+        t_error = e.what();
+        return t_error.compare(0, 6, "Field ") == 0 ? VGPU_ERR_FIELD_NOT_FOUND : VGPU_ERR_INVALID_REQUEST;
+    } catch (const vquery::ParamsError& e) {
+        t_error = e.what();
+        return VGPU_ERR_JSON;
     } catch (const std::exception& e) {
         t_error = e.what();
         return VGPU_ERR_INTERNAL;
@@ -599,6 +609,32 @@ void vgpu_suggestions_free(vgpu_suggestions* s) {
     if (!s) return;
     free(s->items), free(s->text_block);
     s->items = nullptr, s->text_block = nullptr, s->n = 0;
+}
+
+static char* c_string(const std::string& s) {
+    char* p = static_cast<char*>(malloc(s.size() + 1));
+    if (!p) throw std::bad_alloc();
+    memcpy(p, s.c_str(), s.size() + 1);
+    return p;
+}
+int32_t vgpu_search_query(vgpu_index* idx, const char* params_json, char** request_json) {
+    if (!idx || !params_json || !request_json) return VGPU_ERR_INVALID_REQUEST;
+    *request_json = nullptr;
+    return guarded([&]() { *request_json = c_string(vquery::search_query_json(vquery::FieldCatalog::of(*idx->ix->host), params_json, strlen(params_json))); });
+}
+int32_t vgpu_suggest_query(vgpu_index* idx, const char* params_json, char** request_json) {
+    if (!idx || !params_json || !request_json) return VGPU_ERR_INVALID_REQUEST;
+    *request_json = nullptr;
+    return guarded([&]() { *request_json = c_string(vquery::suggest_query_json(vquery::FieldCatalog::of(*idx->ix->host), params_json, strlen(params_json))); });
+}
+int32_t vgpu_query_parse(const char* text, uint32_t options, char** tree_debug) {
+    if (!text || !tree_debug) return VGPU_ERR_INVALID_REQUEST;
+    *tree_debug = nullptr;
+    return guarded([&]() {
+        vquery::ParserOptions o;
+        o.no_attributes = options & 1u, o.no_parentheses = options & 2u, o.no_levensthein = options & 4u;
+        *tree_debug = c_string(vquery::parse(text, o).debug());
+    });
 }
 
 uint64_t vgpu_launch_count(void) { return vdev::launches_so_far(); }

@@ -412,6 +412,7 @@ struct Batch {
         const uint32_t L = std::max<uint32_t>(1, plan.max_leaves);
         tile_log2 = 13;
         while (tile_log2 > 10 && ((size_t)L << tile_log2) * 4 > 48 * 1024) --tile_log2;
+        while (tile_log2 > 8 && tile_kernel_smem(tile_log2, L) == 0) --tile_log2;  // (requests fanned out over many fields: up to 64 parts at 512 anchors per tile)
         // plane path: requests that are flat `or`s of few parts run on term planes, with plane-sized tiles grouped into items
         use_planes = mode == kRequests && ix->planes.n_planes > 0;
         if (use_planes) {

@@ -471,7 +471,7 @@ struct BatchPlan {
             }
         }
         if (kids.size() == 1) return kids[0];  // passthrough (set_op.rs:93-96, :371-374)
-        if (kids.size() > vdev::kMaxLeaves) throw Unsupported("more than 12 sub-queries in one or/and");
+        if (kids.size() > vdev::kMaxLeaves) throw Unsupported("more than " + std::to_string(vdev::kMaxLeaves) + " sub-queries in one or/and");
         Node out;
         out.term = kids[0].term;
         if (r.kind == vhost::SearchRequest::Or) {
@@ -695,7 +695,7 @@ struct BatchPlan {
                 extras = true;
             }
         }
-        if (leaves.size() > vdev::kMaxLeaves) throw Unsupported("more than 12 search parts in one request");
+        if (leaves.size() > vdev::kMaxLeaves) throw Unsupported("more than " + std::to_string(vdev::kMaxLeaves) + " search parts in one request");
         if (request.facets && !request.facets->empty()) {
             rp.facets = *request.facets;
             rp.has_facets = true;

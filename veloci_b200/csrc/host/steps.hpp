@@ -194,7 +194,7 @@ inline void set_op(vdev::DeviceIndex& ix, const vgpu_hitlist* inputs, const char
         out.hits = dup_array(std::vector<vgpu_hit>()), out.ids = dup_array(std::vector<uint32_t>());
         return;
     }
-    if (n > vdev::kMaxLeaves) throw vplan::Unsupported("more than 12 inputs");
+    if (n > vdev::kMaxLeaves) throw vplan::Unsupported("more than " + std::to_string(vdev::kMaxLeaves) + " inputs");
     std::vector<vdev::ExplicitList> lists = to_lists(inputs, n);
     std::vector<uint32_t> code;
     for (uint32_t i = 0; i < n; ++i) code.push_back(vdev::kOpLeaf), code.push_back(i);
@@ -243,7 +243,7 @@ inline void ids_out(const std::vector<uint32_t>& ids, vgpu_hitlist& out) {
 inline void set_op_ids(vdev::DeviceIndex& ix, const vgpu_hitlist* inputs, uint32_t n, bool is_union, vgpu_hitlist& out) {
     if (n == 0) return ids_out({}, out);
     if (n == 1) return ids_out(std::vector<uint32_t>(inputs[0].ids, inputs[0].ids + inputs[0].n_ids), out);
-    if (n > vdev::kMaxLeaves) throw vplan::Unsupported("more than 12 inputs");
+    if (n > vdev::kMaxLeaves) throw vplan::Unsupported("more than " + std::to_string(vdev::kMaxLeaves) + " inputs");
     std::vector<uint32_t> pick(n);
     uint32_t shortest = 0;
     for (uint32_t i = 0; i < n; ++i) {

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <sstream>
 
+#include "../host/query_generator.hpp"
 #include "../host/request.hpp"
 #include "indexer.hpp"
 #include "synth.hpp"
@@ -70,6 +71,105 @@ int vidx_describe_request(const char* json, int reader, char* out, size_t outlen
         set_err(out, outlen, vhost::describe(r).c_str());
         return 0;
     } catch (const vhost::RequestError& e) {
+        set_err(out, outlen, e.what());
+        return 5;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
+        return 9;
+    }
+}
+
+// The query language and the request generator (host/query_parser.hpp, host/query_generator.hpp), for the CPU tests:
+// `what` 0 = Debug text of the parsed tree, 1 = its phrase pairs as a JSON list, 2 = its terms as a JSON list, 3 = the tokens.
+// `options`: bit 0 no_attributes, bit 1 no_parentheses, bit 2 no_levensthein.  Returns 0, or 1 with the ParseError text.
+int vidx_query_parse(const char* text, int options, int what, char* out, size_t outlen) {
+    try {
+        vquery::ParserOptions o;
+        o.no_attributes = options & 1, o.no_parentheses = options & 2, o.no_levensthein = options & 4;
+        std::string s;
+        if (what == 3) {  // the tokens alone: [[text, type], ...]
+            const std::string query(text);
+            s = "[";
+            for (auto& t : vquery::Lexer(query, o).tokens()) {
+                if (s.size() > 1) s += ',';
+                s += '[';
+                vjson::write_string(s, query.substr(t.begin, t.end - t.begin));
+                s += ",\"" + std::string(vquery::token_type_name(t.type)) + "\"]";
+            }
+            s += ']';
+            set_err(out, outlen, s.c_str());
+            return 0;
+        }
+        const vquery::Ast ast = vquery::parse(text, o);
+        if (what == 0) {
+            s = ast.debug();
+        } else if (what == 1) {
+            s = "[";
+            for (auto& p : ast.phrase_pairs()) {
+                if (s.size() > 1) s += ',';
+                s += '[';
+                vjson::write_string(s, p.first);
+                s += ',';
+                vjson::write_string(s, p.second);
+                s += ']';
+            }
+            s += ']';
+        } else {
+            s = "[";
+            ast.walk_terms(ast.root, [&](const std::string& t) {
+                if (s.size() > 1) s += ',';
+                vjson::write_string(s, t);
+            });
+            s += ']';
+        }
+        set_err(out, outlen, s.c_str());
+        return 0;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
+        return 1;
+    }
+}
+
+// UserAST::filter_ast with "drop the leaves whose lower-cased phrase is in `stopwords_json`" (the predicate of
+// query_parser_to_veloci_request.rs:117-133): Debug text of what is left, "None" when nothing is.
+int vidx_query_filter_stopwords(const char* text, const char* stopwords_json, char* out, size_t outlen) {
+    try {
+        vquery::Ast ast = vquery::parse(text);
+        const vjson::Value words = vjson::parse(stopwords_json, strlen(stopwords_json));
+        const int32_t kept = ast.filter(ast.root, [&](const vquery::Ast& a, int32_t i, const std::string*) {
+            if (a.nodes[i].kind != vquery::Node::Leaf) return false;
+            const std::string low = vfmt::to_lowercase(a.nodes[i].text);
+            for (auto& w : words.arr)
+                if (w.str == low) return true;
+            return false;
+        });
+        std::string s = "None";
+        if (kept >= 0) s.clear(), ast.debug(kept, s);
+        set_err(out, outlen, s.c_str());
+        return 0;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
+        return 1;
+    }
+}
+
+// search_query (what = 0) / suggest_query (what = 1) over the index in `dir` (host only: metaData.json and the index
+// files, no device).  Returns 0 with the request JSON, 1 with the message of a parse error, 2 of a generator error
+// (FieldNotFound / AllFieldsFiltered), 5 for parameters that do not deserialize.
+int vidx_generate_request(const char* dir, const char* params_json, int what, char* out, size_t outlen) {
+    try {
+        const auto p = vhost::Persistence::load(dir);
+        const vquery::FieldCatalog cat = vquery::FieldCatalog::of(*p);
+        const std::string s = what ? vquery::suggest_query_json(cat, params_json, strlen(params_json)) : vquery::search_query_json(cat, params_json, strlen(params_json));
+        set_err(out, outlen, s.c_str());
+        return 0;
+    } catch (const vquery::ParseError& e) {
+        set_err(out, outlen, e.what());
+        return 1;
+    } catch (const vquery::GeneratorError& e) {
+        set_err(out, outlen, e.what());
+        return 2;
+    } catch (const vquery::ParamsError& e) {
         set_err(out, outlen, e.what());
         return 5;
     } catch (const std::exception& e) {
