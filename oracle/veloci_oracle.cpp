@@ -34,6 +34,7 @@
 #include "../veloci_b200/csrc/host/request.hpp"
 #include "../veloci_b200/csrc/index/indexer.hpp"
 #include "../veloci_b200/csrc/vjson.hpp"
+#include "regex_sim.hpp"
 
 using vhost::BoostFun;
 using vhost::BoostPart;
@@ -250,7 +251,6 @@ static SearchFieldResult get_term_ids_in_field(const Persistence& p, PlanRequest
     SearchFieldResult result;
     result.request = req;
     if (req.terms.empty()) throw InvalidRequest("search part without terms");
-    if (req.is_regex) throw InvalidRequest("regex search is not supported on this path");
     std::string lower_term = vfmt::to_lowercase(req.terms[0]);
     if (req.levenshtein_distance) {
         uint32_t chars = (uint32_t)vfmt::utf8_count(lower_term);
@@ -267,7 +267,7 @@ static SearchFieldResult get_term_ids_in_field(const Persistence& p, PlanRequest
     const uint32_t d_match = std::min<uint32_t>(req.levenshtein_distance.value_or(0), 4);
     const bool transposition = req.ignore_case.value_or(false);   // search_field.rs:87 (sic)
     const bool case_insensitive = req.ignore_case.value_or(true);  // :88
-    levenshtein_search(dict, req.terms[0], d_match, transposition, case_insensitive, req.starts_with, [&](size_t slot) {
+    const std::function<void(size_t)> on_match = [&](size_t slot) {
         uint32_t token_text_id = dict.ids[slot];
         if (options.get_ids) result.hits_ids.push_back(token_text_id);
         if (options.get_scores) {
@@ -285,7 +285,25 @@ static SearchFieldResult get_term_ids_in_field(const Persistence& p, PlanRequest
             result.hits_scores.push_back(Hit{token_text_id, score});
         }
         if (options.return_term) result.terms[token_text_id] = options.return_term_lowercase ? vfmt::to_lowercase(dict.term(slot)) : dict.term(slot);  // :331-337
-    });
+    };
+    if (req.is_regex) {  // search_field.rs:72-83: the pattern's DFA instead of the Levenshtein automaton, same stream order
+        std::unique_ptr<oracle_regex::Program> program;
+        try {
+            program.reset(new oracle_regex::Program(req.terms[0], case_insensitive));
+        } catch (const oracle_regex::BadPattern& e) {
+            throw InvalidRequest(std::string("regex \"") + req.terms[0] + "\": " + e.what());
+        } catch (const oracle_regex::OutsideSubset& e) {
+            throw InvalidRequest(std::string("regex \"") + req.terms[0] + "\" outside the oracle's subset: " + e.what());
+        }
+        std::vector<uint32_t> scalars;
+        for (size_t slot = 0; slot < dict.size(); ++slot) {
+            scalars.clear();
+            vfmt::utf8_decode(dict.term(slot), scalars);
+            if (program->accepts(scalars, req.starts_with)) on_match(slot);
+        }
+    } else {
+        levenshtein_search(dict, req.terms[0], d_match, transposition, case_insensitive, req.starts_with, on_match);
+    }
     if (req.boost)
         for (auto& h : result.hits_scores) h.score *= *req.boost;
     if (limit_result) {
@@ -1255,6 +1273,23 @@ static std::string call(const Persistence* p, const std::string& fn, const vjson
         auto bs = results_from(*a.get("boosts"));
         boost_hits_ids_vec_multi(r, bs);
         return hits_to_json(r.hits_scores);
+    }
+    if (fn == "regex_accepts") {  // regex_sim.hpp: '0' / '1' per term; "bad: .." / "outside: .." when the pattern does not compile
+        try {
+            oracle_regex::Program prog(a.get("pattern")->str, a.get("case_insensitive")->b);
+            std::string bits = "\"";
+            std::vector<uint32_t> scalars;
+            for (auto& t : a.get("terms")->arr) {
+                scalars.clear();
+                vfmt::utf8_decode(t.str, scalars);
+                bits += prog.accepts(scalars, a.get("starts_with")->b) ? '1' : '0';
+            }
+            return bits + "\"";
+        } catch (const oracle_regex::BadPattern& e) {
+            return std::string("\"bad\"");
+        } catch (const oracle_regex::OutsideSubset& e) {
+            return std::string("\"outside\"");
+        }
     }
     if (fn == "distance") return std::to_string((int)distance(a.get("a")->str, a.get("b")->str));
     if (fn == "distance_dfa") return std::to_string((int)distance_dfa(a.get("hit")->str, a.get("term")->str, (uint32_t)a.get("d")->num));

@@ -94,6 +94,17 @@ def generate_request(directory, params, suggest=False):
     return rc, (json.loads(s) if rc == 0 else s), s
 
 
+def regex_match(pattern, terms, case_insensitive=True, starts_with=False):
+    """The product's regex DFA (csrc/host/regex_dfa.hpp) on the host: (status, [bool per term] or message, (states, classes))."""
+    lib = _index_lib()
+    lib.vidx_regex_match.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)]
+    out = ctypes.create_string_buffer(max(4096, len(terms) + 16))
+    stats = (ctypes.c_uint32 * 2)()
+    rc = lib.vidx_regex_match(pattern.encode("utf-8"), int(case_insensitive), int(starts_with), json.dumps(terms, ensure_ascii=False).encode("utf-8"), out, len(out), stats)
+    s = out.value.decode("utf-8")
+    return rc, ([c == "1" for c in s] if rc == 0 else s), (stats[0], stats[1])
+
+
 class Oracle:
     def __init__(self, directory=None):
         self.lib = ctypes.CDLL(build.build_oracle())

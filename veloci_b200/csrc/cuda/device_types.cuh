@@ -164,6 +164,17 @@ enum PartFlags : uint32_t {
     kPartList = 32u,          // not a search part: its tile bucket is filled by a list producer (phrase pairs, text locality, 1:n boosts)
     kPartListBoost = 64u,     // list part of a 1:n boost: entries carry 0x7FFFFFFF - value id; the tile keeps the smallest value id of an
                               // anchor plus (bit 31) whether the anchor has several
+    kPartRegex = 256u,        // is_regex (search_field.rs:72-83): matched by regex_match_kernel with the part's DFA, scored like any other part
+};
+
+// One regex search part on the device: its DFA over the alphabet codes of the part's dictionary (host/regex_dfa.hpp).
+struct RegexPartDev {
+    const uint16_t* class_of_code;  // [alphabet size] scalar class of every alphabet code
+    const uint16_t* trans;          // [n_states * n_classes] next state, bit 15 set when that state is a match state; state 0 is dead
+    uint32_t n_classes;
+    uint32_t start;                 // start state (bit 15: it matches the empty string)
+    uint32_t part;
+    uint32_t sticky;                // starts_with: a match after any prefix of the term counts (fst::automaton::StartsWith)
 };
 
 struct PartQuery {  // one distinct RequestSearchPart of the batch (272 B)

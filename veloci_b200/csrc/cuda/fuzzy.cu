@@ -160,6 +160,50 @@ void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* 
     count_launch();
 }
 
+// ---------------------------------------------------------------- regex parts
+// get_text_lines_from_fst with `is_regex` (search_field.rs:72-83): the reference walks the FST with the pattern's DFA; a
+// term matches when the DFA is in a match state after the term's last symbol, or -- starts_with -- after any prefix.
+// Here every thread runs the DFA over one term's raw-case symbols (case-insensitivity is in the DFA's classes): two
+// dependent loads per symbol (class of the symbol, transition), tables small enough to stay in L1/L2.
+__global__ void __launch_bounds__(256) regex_match_kernel(DictView dict, const RegexPartDev* __restrict__ parts, MatchRecord* __restrict__ out, uint32_t capacity,
+                                                          unsigned long long* __restrict__ counter) {
+    const RegexPartDev p = parts[blockIdx.y];
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    bool match = false;
+    if (slot < dict.n) {
+        const uint32_t o = dict.off[1][slot];
+        const uint16_t* ts = dict.sym[1] + o;
+        const uint32_t n = dict.off[1][slot + 1] - o;
+        uint32_t st = p.start;
+        bool hit = p.sticky && (st & 0x8000u);
+        uint32_t i = 0;
+        for (; i < n && !hit; ++i) {
+            st = __ldg(p.trans + (size_t)(st & 0x7FFFu) * p.n_classes + __ldg(p.class_of_code + ts[i]));
+            if ((st & 0x7FFFu) == 0) break;  // dead: no extension matches
+            hit = p.sticky && (st & 0x8000u);
+        }
+        match = hit || (!p.sticky && i == n && (st & 0x8000u));
+    }
+    const uint32_t mm = __ballot_sync(0xFFFFFFFFu, match);
+    if (mm) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(mm));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (match) {
+            const unsigned long long at = base + __popc(mm & ((1u << lane) - 1u));
+            if (at < capacity) out[at] = MatchRecord{p.part, slot};
+        }
+    }
+}
+
+void launch_regex_match(cudaStream_t st, const DictView& dict, const RegexPartDev* parts, uint32_t n_parts, MatchRecord* out, uint32_t capacity, unsigned long long* counter) {
+    if (n_parts == 0 || dict.n == 0) return;
+    dim3 grid((dict.n + 255u) / 256u, n_parts);
+    regex_match_kernel<<<grid, 256, 0, st>>>(dict, parts, out, capacity, counter);
+    count_launch();
+}
+
 // ---------------------------------------------------------------- deletion-neighbourhood index
 __device__ __forceinline__ uint64_t variant_hash(const uint16_t* __restrict__ sym, uint32_t n, uint32_t skip_a, uint32_t skip_b) {
     uint64_t h = 0x9E3779B97F4A7C15ull;

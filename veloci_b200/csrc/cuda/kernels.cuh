@@ -30,6 +30,8 @@ struct PerDeviceOnce {
 // ---- fuzzy.cu ----
 void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* parts, const uint32_t* part_ids, uint32_t n_parts, uint32_t max_m, MatchRecord* out,
                         uint32_t capacity, unsigned long long* counter);
+// one launch per dictionary: grid.y = the regex parts on it, one thread per dictionary term
+void launch_regex_match(cudaStream_t st, const DictView& dict, const RegexPartDev* parts, uint32_t n_parts, MatchRecord* out, uint32_t capacity, unsigned long long* counter);
 // Deletion-neighbourhood index build: pass 0 counts the variants per hash bucket, pass 1 (after an exclusive scan of
 // the counts into `off`, cursor zeroed) files the terms.
 void launch_del_index_pass(cudaStream_t st, const DictView& dict, uint32_t max_del, uint32_t mask, uint32_t* count_or_cursor, const uint32_t* off, DelEntry* ent);

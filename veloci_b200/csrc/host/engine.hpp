@@ -105,6 +105,9 @@ struct Batch {
     std::vector<DevBuf<uint32_t>> d_probe_of_dict, d_overflow_of_dict;
     DevBuf<unsigned long long> d_overflow_count;
     std::vector<uint32_t> max_m_of_dict;
+    std::vector<std::vector<RegexPartDev>> regex_of_dict;  // is_regex parts: their DFAs over each dictionary's alphabet codes
+    std::vector<DevBuf<RegexPartDev>> d_regex_of_dict;
+    DevBuf<uint16_t> d_regex_tables;                       // class maps and transition tables of all of them, back to back
     // device: match phase
     DevBuf<MatchRecord> d_records;
     DevBuf<unsigned long long> d_counters;  // [0] matches, [1] work counter, [2] stat postings, [3] dense rows, [4] emitted hits
@@ -475,7 +478,7 @@ struct Batch {
         if (mode == kRequests) {
             for (uint32_t p = 0; p < n_parts; ++p) {
                 const PartQuery& pq = plan.parts[p];
-                if (pq.flags & (kPartList | kPartInjected)) continue;
+                if (pq.flags & (kPartList | kPartInjected | kPartRegex)) continue;
                 const uint32_t d = plan.part_dict[p];
                 bool probe = pq.m >= 1 && pq.d_match <= 2 && !(pq.flags & (kPartPrefix | kPartRawCase));
                 if (probe && pq.d_match == 2 && !ix->del_index_built(plan.dict_names[d], 1)) ix->ensure_del_index(plan.dict_names[d], 1);
@@ -484,6 +487,7 @@ struct Batch {
                 max_m_of_dict[d] = std::max(max_m_of_dict[d], pq.m);
             }
         }
+        build_regex_tables();
         std::vector<DictView> dv;
         for (auto& name : plan.dict_names) dv.push_back(ix->dict_view(name));
         d_dicts.upload(dv);
@@ -524,6 +528,43 @@ struct Batch {
         d_emit.alloc((size_t)emit_capacity + 1);
         if (mode == kRequests) d_records.reserve(std::max<size_t>(1u << 20, (size_t)n_parts * 64));
         VDEV_CUDA(cudaMemsetAsync(d_counters.p, 0, d_counters.bytes(), stream));
+    }
+
+    // The DFA of every regex part (host/regex_dfa.hpp), re-expressed over the alphabet codes of the part's dictionary:
+    // per part a class map [alphabet size] and the transition table [states x classes], all in one device array.
+    void build_regex_tables() {
+        regex_of_dict.assign(plan.dict_names.size(), {});
+        d_regex_of_dict.clear();
+        d_regex_of_dict.resize(plan.dict_names.size());
+        if (plan.regex_parts.empty() || mode != kRequests) return;
+        std::vector<uint16_t> tables;
+        struct Placed {
+            uint32_t dict;
+            size_t class_at, trans_at;
+            RegexPartDev dev;
+        };
+        std::vector<Placed> placed;
+        for (auto& rp : plan.regex_parts) {
+            const vregex::Dfa dfa = vregex::compile(rp.pattern, rp.case_insensitive);  // (validated by the planner: does not throw here)
+            const uint32_t d = plan.part_dict[rp.part];
+            const DictDev& dict = ix->dicts.at(plan.dict_names[d]);
+            Placed pl;
+            pl.dict = d, pl.class_at = tables.size();
+            for (uint32_t scalar : dict.alphabet) tables.push_back(dfa.class_of(scalar));
+            if (dict.alphabet.empty()) tables.push_back(0);
+            pl.trans_at = tables.size();
+            tables.insert(tables.end(), dfa.trans.begin(), dfa.trans.end());
+            pl.dev.class_of_code = nullptr, pl.dev.trans = nullptr;
+            pl.dev.n_classes = dfa.n_classes, pl.dev.start = dfa.start, pl.dev.part = rp.part, pl.dev.sticky = rp.starts_with ? 1u : 0u;
+            placed.push_back(pl);
+        }
+        d_regex_tables.upload(tables);
+        for (auto& pl : placed) {
+            pl.dev.class_of_code = d_regex_tables.p + pl.class_at, pl.dev.trans = d_regex_tables.p + pl.trans_at;
+            regex_of_dict[pl.dict].push_back(pl.dev);
+        }
+        for (size_t d = 0; d < regex_of_dict.size(); ++d) d_regex_of_dict[d].upload(regex_of_dict[d]);
+        h2d_bytes += tables.size() * 2 + placed.size() * sizeof(RegexPartDev);
     }
 
     // Matched terms with at least this many postings get a tile-offset row, the others are copied into their part's
@@ -578,6 +619,8 @@ struct Batch {
                     timed("fuzzy_probe", [&] { launch_fuzzy_probe(stream, dict, d_parts.p, d_probe_of_dict[d].p, (uint32_t)probe_of_dict[d].size(), d_records.p, capacity, d_counters.p, d_overflow_of_dict[d].p,
                                        d_overflow_count.p + d); });
                     timed("fuzzy_match", [&] { launch_fuzzy_match(stream, dict, d_parts.p, d_parts_of_dict[d].p, (uint32_t)parts_of_dict[d].size(), max_m_of_dict[d], d_records.p, capacity, d_counters.p); });
+                    if (!regex_of_dict[d].empty())
+                        timed("regex_match", [&] { launch_regex_match(stream, dict, d_regex_of_dict[d].p, (uint32_t)regex_of_dict[d].size(), d_records.p, capacity, d_counters.p); });
                 }
                 VDEV_CUDA(cudaMemcpyAsync(overflow.data(), d_overflow_count.p, n_dicts * 8, cudaMemcpyDeviceToHost, stream));
                 n_match = read_back(d_counters.p);

@@ -152,11 +152,12 @@ inline void visit_all(std::vector<T>& v, F&& f) {
     for (auto& x : v) visit_ptrs(x, f);
 }
 
-static const uint64_t kBlobMagic = 0x31424c504f4c4556ull;  // "VELOPLB1"
+static const uint64_t kBlobMagic = 0x32424c504f4c4556ull;  // "VELOPLB2"
 
 inline void write_search_part(BlobWriter& w, const vhost::SearchPart& p) {
-    if (p.is_regex || p.token_value || p.options.present) throw BlobError("search part with regex / token_value / options cannot be exported");
+    if (p.token_value || p.options.present) throw BlobError("search part with token_value / options cannot be exported");
     w.str(p.path);
+    w.u32(p.is_regex ? 1u : 0u);
     w.str_vec(p.terms);
     w.opt(p.levenshtein_distance);
     w.u32(p.starts_with ? 1u : 0u);
@@ -167,6 +168,7 @@ inline void write_search_part(BlobWriter& w, const vhost::SearchPart& p) {
 }
 inline void read_search_part(BlobReader& r, vhost::SearchPart& p) {
     p.path = r.str();
+    p.is_regex = r.u32() != 0;
     r.str_vec(p.terms);
     r.opt(p.levenshtein_distance);
     p.starts_with = r.u32() != 0;
@@ -225,6 +227,8 @@ inline std::vector<uint8_t> export_plan(const BatchPlan& plan_in) {
     w.u32(plan_in.max_leaves), w.u32(plan_in.max_k);
     w.u64(plan_in.bounded.size());
     for (auto& b : plan_in.bounded) w.u32(b.part), write_search_part(w, b.request);
+    w.u64(plan_in.regex_parts.size());
+    for (auto& g : plan_in.regex_parts) w.u32(g.part), w.str(g.pattern), w.u32((g.case_insensitive ? 1u : 0u) | (g.starts_with ? 2u : 0u));
     return std::move(w.out);
 }
 
@@ -289,6 +293,17 @@ inline void import_plan(const vdev::DeviceIndex* ix, const void* blob, size_t le
         b.part = r.u32();
         read_search_part(r, b.request);
         plan.bounded.push_back(std::move(b));
+    }
+    const uint64_t ng = r.u64();
+    plan.regex_parts.clear();
+    for (uint64_t i = 0; i < ng; ++i) {
+        BatchPlan::RegexPart g;
+        g.part = r.u32();
+        g.pattern = r.str();
+        const uint32_t f = r.u32();
+        g.case_insensitive = f & 1u, g.starts_with = f & 2u;
+        if (g.part >= plan.parts.size()) throw BlobError("plan blob is inconsistent (regex part)");
+        plan.regex_parts.push_back(std::move(g));
     }
     if (plan.programs.size() != plan.requests.size() || plan.part_dict.size() != plan.parts.size()) throw BlobError("plan blob is inconsistent");
 }

@@ -13,6 +13,7 @@
 
 #include "../cuda/device_types.cuh"
 #include "device_index.hpp"
+#include "regex_dfa.hpp"
 #include "request.hpp"
 
 namespace vplan {
@@ -206,7 +207,6 @@ struct BatchPlan {
     uint32_t add_part(const vhost::SearchPart& part_in) {
         const vhost::SearchPart& req = part_in;
         if (req.terms.empty()) throw InvalidRequest("search part without terms");
-        if (req.is_regex) throw Unsupported("regex search is outside the accelerated path");
         if (req.token_value) throw Unsupported("token_value boost is outside the accelerated path");
         const FieldTables& ft = field_tables(req.path);
         const uint32_t did = ft.dict_id, pid = ft.postings_id;
@@ -225,6 +225,17 @@ struct BatchPlan {
             lower_bytes = lower_term.size();
         }
         if (raw.size() > 64) throw Unsupported("search terms longer than 64 characters are outside the accelerated path");
+        if (req.is_regex) {
+            // search_field.rs:72-78: the pattern must compile (the reference unwraps the build); the tables for the
+            // dictionary's alphabet are made when the plan is uploaded (Batch::prepare_tables), so the plan stays exportable
+            try {
+                vregex::compile(term, req.ignore_case.value_or(true));
+            } catch (const vregex::RegexError& e) {
+                throw InvalidRequest(std::string("regex \"") + term + "\": " + e.what());
+            } catch (const vregex::RegexUnsupported& e) {
+                throw Unsupported(std::string("regex \"") + term + "\": " + e.what() + " is outside the accelerated path");
+            }
+        }
         PartQuery q;
         memset(&q, 0, sizeof q);
         q.m = (uint32_t)raw.size();
@@ -244,6 +255,15 @@ struct BatchPlan {
             q.match_sym[j] = code_of(case_insensitive ? vfmt::lower_scalar(raw[j]) : raw[j]);
             q.score_sym[j] = code_of(low[j]);
         }
+        if (req.is_regex && !req.top) {  // never shared: its matches come from its own DFA, which PartQuery does not describe
+            q.flags |= vdev::kPartRegex;
+            const uint32_t id = (uint32_t)parts.size();
+            parts.push_back(q);
+            part_dict.push_back(did);
+            part_hash.push_back(0);
+            regex_parts.push_back(RegexPart{id, term, req.ignore_case.value_or(true), req.starts_with});
+            return id;
+        }
         if (req.top) {
             // The per-part bound (search_field.rs:292-294,:322-331,:366-369) depends on the order the hits arrive in: the engine
             // matches such a part on its own first, bounds its hits on the host and gives them to the batch (kPartInjected).
@@ -262,6 +282,12 @@ struct BatchPlan {
         vhost::SearchPart request;
     };
     std::vector<BoundedPart> bounded;
+    struct RegexPart {  // a kPartRegex part and what its DFA is built from
+        uint32_t part;
+        std::string pattern;
+        bool case_insensitive, starts_with;
+    };
+    std::vector<RegexPart> regex_parts;
 
     // A part whose hits are produced by a list kernel (phrase pairs, text locality, 1:n boosts) instead of a field search.
     uint32_t add_list_part() {
@@ -309,6 +335,7 @@ struct BatchPlan {
             part_map[i] = find_or_add_part(q, dict_map[o.part_dict[i]], o.part_hash[i]);
         }
         for (BoundedPart& bp : o.bounded) bounded.push_back(BoundedPart{part_map[bp.part], std::move(bp.request)});
+        for (RegexPart& rp : o.regex_parts) regex_parts.push_back(RegexPart{part_map[rp.part], std::move(rp.pattern), rp.case_insensitive, rp.starts_with});
         const uint32_t leaf_base = (uint32_t)leaf_part.size(), prog_base = (uint32_t)prog.size(), boost_base = (uint32_t)boosts.size(), facet_base = (uint32_t)facets.size();
         for (vdev::PhraseMember m : o.phrase_members) {
             m.part1 = part_map[m.part1], m.part2 = part_map[m.part2], m.list_part = part_map[m.list_part];
@@ -785,7 +812,7 @@ struct BatchPlan {
         memset(&qp, 0, sizeof qp);
         // a failing request must not leave half-registered leaves behind
         const size_t leaf_mark = leaf_part.size(), prog_mark = prog.size(), boost_mark = boosts.size(), facet_mark = facets.size(), phrase_mark = phrase_members.size(), ids_mark = ids_members.size(), tl_mark = tl_instances.size(),
-                     tl_term_mark = tl_term_parts.size(), bm_mark = boost_members.size(), bounded_mark = bounded.size();
+                     tl_term_mark = tl_term_parts.size(), bm_mark = boost_members.size(), bounded_mark = bounded.size(), regex_mark = regex_parts.size();
         try {
             if (parsed.status != 0) {
                 rp.status = parsed.status, rp.message = parsed.message;
@@ -812,6 +839,7 @@ struct BatchPlan {
             // per-part-top parts of the failed request: nothing references them any more, so they must not be matched and
             // bounded on every execute (their PartQuery stays behind as an injected part without hits)
             bounded.resize(bounded_mark);
+            regex_parts.resize(regex_mark);
             rp.facets.clear(), rp.has_facets = false;
             memset(&qp, 0, sizeof qp);
         }

@@ -5,6 +5,7 @@
 #include <sstream>
 
 #include "../host/query_generator.hpp"
+#include "../host/regex_dfa.hpp"
 #include "../host/request.hpp"
 #include "indexer.hpp"
 #include "synth.hpp"
@@ -172,6 +173,35 @@ int vidx_generate_request(const char* dir, const char* params_json, int what, ch
     } catch (const vquery::ParamsError& e) {
         set_err(out, outlen, e.what());
         return 5;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
+        return 9;
+    }
+}
+
+// The product's regex DFA (host/regex_dfa.hpp) on the host: which of `terms_json` (a JSON list of strings) the DFA of
+// `pattern` accepts, as a string of '0' / '1'.  Returns 0; 1 = RegexError (the reference could not build it either);
+// 8 = syntax outside the implemented subset.  `stats` (optional, 2 words) receives the DFA's states and classes.
+int vidx_regex_match(const char* pattern, int case_insensitive, int starts_with, const char* terms_json, char* out, size_t outlen, uint32_t* stats) {
+    try {
+        const vregex::Dfa dfa = vregex::compile(pattern, case_insensitive != 0);
+        if (stats) stats[0] = dfa.n_states, stats[1] = dfa.n_classes;
+        const vjson::Value terms = vjson::parse(terms_json, strlen(terms_json));
+        std::string bits;
+        std::vector<uint32_t> scalars;
+        for (auto& t : terms.arr) {
+            scalars.clear();
+            vfmt::utf8_decode(t.str, scalars);
+            bits += dfa.matches(scalars, starts_with != 0) ? '1' : '0';
+        }
+        set_err(out, outlen, bits.c_str());
+        return 0;
+    } catch (const vregex::RegexError& e) {
+        set_err(out, outlen, e.what());
+        return 1;
+    } catch (const vregex::RegexUnsupported& e) {
+        set_err(out, outlen, e.what());
+        return 8;
     } catch (const std::exception& e) {
         set_err(out, outlen, e.what());
         return 9;
