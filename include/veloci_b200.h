@@ -215,6 +215,21 @@ int32_t vgpu_search_query(vgpu_index* idx, const char* params_json, char** reque
 int32_t vgpu_suggest_query(vgpu_index* idx, const char* params_json, char** request_json);
 int32_t vgpu_query_parse(const char* text, uint32_t options, char** tree_debug);
 
+/* ---- documents (host side, no kernel) ----------------------------------------
+ * DocLoader::get_doc (doc_store/src/lib.rs:26-62) over the index directory's compressed document store `data`
+ * (lz4 blocks + block index, written by src/create/write_docs.rs:11-34): the stored JSON text of document `doc_id`
+ * (= the anchor id of a hit), NUL-terminated, released with vgpu_free.  What search::to_documents does per hit when the
+ * request has no `select` (src/search.rs:89-98).  VGPU_ERR_IO when the store is missing, damaged, or has no such document. */
+int32_t vgpu_get_doc(vgpu_index* idx, uint32_t doc_id, char** doc_json);
+/* search::to_search_result for a request without `select` (src/search.rs:65-110): after execute, the hits of request q
+ * as documents, `{"num_hits": n, "data": [{"doc": {..}, "hit": {"id", "score"}, "why_found": {"<field>": ["..<b>term</b>.."]}}]}`.
+ * `why_found` is filled when the request set `"why_found": true`: the texts of the terms its parts matched
+ * (SearchResult::why_found_terms, src/search.rs:186) highlight the stored document, field by field
+ * (highlight_on_original_document / highlight_text, src/highlight_field.rs:98-186: windows of five words around the hits,
+ * " ... " between and around them).  Released with vgpu_free.  Not for sharded batches (a shard holds its own anchors only):
+ * fetch the merged hits' documents with vgpu_get_doc there. */
+int32_t vgpu_batch_result_docs(vgpu_batch* batch, uint32_t q, char** result_json);
+
 /* ---- step seam -------------------------------------------------------------
  * One symbol per PlanStep kind (src/plan_creator/plan_steps.rs:18-74), each over host
  * hit lists; used by the step-level parity tests.  Outputs are malloc'd by the

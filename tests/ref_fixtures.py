@@ -193,3 +193,25 @@ TEST_QG_DOCS = [
     {"commonness": 20, "ent_seq": "27", "my_bool": True, "tags": ["Eis", "cool"]},
     {"commonness": 20, "ent_seq": "28", "tags": ["nice", "cool"]},
 ]
+
+# ---- tests/all/test_why_found.rs:7-64 (the corpus of the why_found tests)
+TEST_WHYFOUND_CONFIG = {
+    "*GLOBAL*": {"features": ["All"]},
+    "richtig": {"fulltext": {"tokenize": True}},
+    "not_tokenized": {"fulltext": {"tokenize": False}},
+    "not_tokenized_1_n[]": {"fulltext": {"tokenize": False}},
+    "custom_tokenized": {"fulltext": {"tokenize": True, "tokenize_on_chars": ["§", "<"]}},
+    "url": {"fulltext": {"tokenize": True, "tokenize_on_chars": ["/", ":", "."]}},
+}
+TEST_WHYFOUND_DOCS = [
+    {"url": "https://github.com/PSeitz/veloci", "richtig": "schön super", "viele": ["nette", "leute"]},
+    {"not_tokenized": "ID1000", "not_tokenized_1_n": ["ID1000"], "custom_tokenized": "test§_ cool _", "richtig": "hajoe genau"},
+    {
+        "not_tokenized": "ID2000",
+        "not_tokenized_1_n": ["ID2000"],
+        "richtig": "shön",
+        "custom_tokenized": "<<cool>>",
+        "viele": ["treffers", "und so", "super treffers", "ein längerer Text, um zu checken, dass da nicht umsortiert wird"],
+    },
+    {"buch": "Taschenbuch (kartoniert)", "viele": ["super treffers"]},
+]

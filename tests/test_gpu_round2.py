@@ -371,6 +371,7 @@ def test_generated_requests_on_the_reference_corpus(gpu, native_libs):
             assert len(g["data"]) == n, params
         if first is not None:
             assert fx.TEST_QG_DOCS[g["data"][0][0]]["ent_seq"] == first, params
+            assert index.get_doc(g["data"][0][0]) == fx.TEST_QG_DOCS[g["data"][0][0]]  # hits[0].doc of the reference's tests
     with pytest.raises(gpu.VelociGpuError) as e:
         index.search_query(search_term="notexistingfield:awes*")                              # :369-378
     assert e.value.status == 2 and "Field notexistingfield not found in" in str(e.value)
@@ -435,3 +436,56 @@ def test_regex_parts(gpu, sharded_corpus):
     for q in range(3):
         assert b2.result(q)["num_hits"] == b.result(q)["num_hits"]
         assert [i for i, _ in b2.result(q)["data"]] == [i for i, _ in b.result(q)["data"]]
+
+
+def test_result_docs_and_why_found(gpu, native_libs):
+    """search::to_search_result through the C ABI (vgpu_batch_result_docs): documents from the compressed store, why_found
+    highlights from the terms the GPU matched; the reference's expected strings (tests/all/test_why_found.rs) and the
+    plain-Python oracle (oracle/highlight.py) on the same matched terms."""
+    import ref_fixtures as fx
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import highlight as ohl  # test infrastructure
+
+    d = tempfile.mkdtemp(prefix="vb200_r2_wf_")
+    helpers.create_index(d, fx.TEST_WHYFOUND_DOCS, fx.TEST_WHYFOUND_CONFIG)
+    columns = json.load(open(os.path.join(d, "metaData.json")))["columns"]
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    S = lambda term, path, **kw: {"search_req": {"search": {"terms": [term], "path": path, **kw}}, "why_found": True}
+    cases = [
+        (S("veloci", "url"), "url", [["https://github.com/PSeitz/<b>veloci</b>"]]),                                   # :73-92
+        (S("test", "custom_tokenized"), "custom_tokenized", [["<b>test</b>§_ cool _"]]),                               # :94-105
+        (S("_ cool _", "custom_tokenized"), "custom_tokenized", [["test§<b>_ cool _</b>"]]),                           # :118-129
+        (S("<<cool>>", "custom_tokenized"), "custom_tokenized", [["<b><<cool>></b>"]]),                                # :149-161
+        (S("ID1000", "not_tokenized"), "not_tokenized", [["<b>ID1000</b>"]]),                                          # :163-175
+        (S("ID1000", "not_tokenized_1_n[]"), "not_tokenized_1_n[]", [["<b>ID1000</b>"]]),                              # :193-205
+        (S("schön", "richtig", levenshtein_distance=1), "richtig", [["<b>schön</b> super"], ["<b>shön</b>"]]),         # :237-251
+        (S("treffers", "viele[]", levenshtein_distance=1), "viele[]", [["<b>treffers</b>", "super <b>treffers</b>"]]), # :253-266 (first hit)
+        (S("umsortiert", "viele[]", levenshtein_distance=0), "viele[]", [[" ... zu checken, dass da nicht <b>umsortiert</b> wird"]]),  # :285-299
+        ({"search_req": {"or": {"queries": [{"search": {"terms": ["Taschenbuch"], "path": "buch", "levenshtein_distance": 1}},
+                                            {"search": {"terms": ["kartoniert"], "path": "buch", "levenshtein_distance": 1}}]}}, "why_found": True},
+         "buch", [["<b>Taschenbuch</b> (<b>kartoniert</b>)"]]),                                                        # :318-350
+        ({"search_req": {"search": {"terms": ["schön"], "path": "richtig"}}}, "richtig", None),                        # why_found not asked for
+    ]
+    texts = [json.dumps(c[0], ensure_ascii=False) for c in cases]
+    b = index.prepare(texts).execute()
+    for q, (req, field, expected) in enumerate(cases):
+        res = b.result_docs(q)
+        ref = oracle.search(texts[q])
+        assert res["num_hits"] == ref["num_hits"] and [h["hit"]["id"] for h in res["data"]] == [h[0] for h in ref["data"]], req
+        for h in res["data"]:
+            assert h["doc"] == fx.TEST_WHYFOUND_DOCS[h["hit"]["id"]]
+        if expected is None:
+            assert all(h["why_found"] == {} for h in res["data"])
+            continue
+        for h, want in zip(res["data"], expected):
+            assert h["why_found"][field] == want, (req, h)
+        # and the whole map equals the oracle's highlight over the oracle's matched terms
+        parts = [req["search_req"]["search"]] if "search" in req["search_req"] else [p["search"] for p in req["search_req"]["or"]["queries"]]
+        terms = {}
+        for part in parts:
+            terms.setdefault(part["path"] + ".textindex", set()).update(oracle.call("field_search", part=part)["terms"])
+        for h in res["data"]:
+            assert h["why_found"] == ohl.highlight_on_original_document(columns, h["doc"], terms), req
+    with pytest.raises(gpu.VelociGpuError):
+        index.get_doc(len(fx.TEST_WHYFOUND_DOCS))

@@ -109,6 +109,8 @@ def load_library():
     L.vgpu_top_n.argtypes = [vp, P(_HitList), u32, u32, P(_HitList)]
     L.vgpu_suggest.argtypes = [vp, cp, P(_Suggestions)]
     L.vgpu_suggest_part.argtypes = [vp, cp, P(_Suggestions)]
+    L.vgpu_get_doc.argtypes = [vp, ctypes.c_uint32, P(vp)]
+    L.vgpu_batch_result_docs.argtypes = [vp, ctypes.c_uint32, P(vp)]
     L.vgpu_search_query.argtypes = [vp, cp, P(vp)]
     L.vgpu_suggest_query.argtypes = [vp, cp, P(vp)]
     L.vgpu_query_parse.argtypes = [cp, ctypes.c_uint32, P(vp)]
@@ -220,6 +222,11 @@ class Batch:
         n = ctypes.c_uint32()
         _check(self.L.vgpu_batch_size(self.h, ctypes.byref(n)))
         return int(n.value)
+
+    def result_docs(self, q):
+        """The hits of request q as documents with why_found highlights (search::to_search_result)."""
+        out = ctypes.c_void_p()
+        return json.loads(_take_string(self.L, self.L.vgpu_batch_result_docs(self.h, q, ctypes.byref(out)), out))
 
     def export_plan(self):
         """The batch's plan as bytes without process-local addresses (vgpu_batch_export_plan)."""
@@ -494,6 +501,12 @@ class Index:
     def suggest(self, part):
         """One RequestSearchPart; its top/skip bound the list."""
         return self._suggest(self.L.vgpu_suggest_part, part)
+
+    # ---- documents
+    def get_doc(self, doc_id):
+        """The stored document of a hit (DocLoader::get_doc), parsed."""
+        out = ctypes.c_void_p()
+        return json.loads(_take_string(self.L, self.L.vgpu_get_doc(self.h, int(doc_id), ctypes.byref(out)), out))
 
     # ---- request generation (query_generator::search_query / suggest_query)
     def search_query(self, params=None, **kw):

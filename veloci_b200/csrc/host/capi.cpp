@@ -627,6 +627,20 @@ int32_t vgpu_suggest_query(vgpu_index* idx, const char* params_json, char** requ
     *request_json = nullptr;
     return guarded([&]() { *request_json = c_string(vquery::suggest_query_json(vquery::FieldCatalog::of(*idx->ix->host), params_json, strlen(params_json))); });
 }
+int32_t vgpu_get_doc(vgpu_index* idx, uint32_t doc_id, char** doc_json) {
+    if (!idx || !doc_json) return VGPU_ERR_INVALID_REQUEST;
+    *doc_json = nullptr;
+    return guarded([&]() { *doc_json = c_string(idx->ix->host->get_doc(doc_id)); });
+}
+int32_t vgpu_batch_result_docs(vgpu_batch* batch, uint32_t q, char** result_json) {
+    if (!batch || !result_json || q >= batch->b.n) return VGPU_ERR_INVALID_REQUEST;
+    *result_json = nullptr;
+    if (batch->b.plan.requests[q].status != 0) {
+        t_error = batch->b.plan.requests[q].message;
+        return batch->b.plan.requests[q].status;
+    }
+    return guarded([&]() { *result_json = c_string(vsteps::result_docs(batch->b, q)); });
+}
 int32_t vgpu_query_parse(const char* text, uint32_t options, char** tree_debug) {
     if (!text || !tree_debug) return VGPU_ERR_INVALID_REQUEST;
     *tree_debug = nullptr;

@@ -13,9 +13,11 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 
+#include "doc_store.hpp"
 #include "../format/codecs.hpp"
 #include "../format/fst.hpp"
 #include "../format/unicode.hpp"
@@ -251,6 +253,29 @@ struct Persistence {
     std::unordered_map<std::string, KeyValueStore> boost_valueid_to_value;
     std::unordered_map<std::string, vfmt::FstReader> fst;
     std::unordered_map<std::string, TermDict> dict;  // same keys as `fst`
+
+    // The document store (`data`, src/search.rs:78-79), opened on first use.
+    std::mutex doc_mu;
+    DocLoader docs;
+    const DocLoader& doc_store() {
+        std::lock_guard<std::mutex> lock(doc_mu);
+        if (!docs.is_open()) {
+            const std::vector<uint8_t>& f = file("data");
+            try {
+                docs = DocLoader(f.data(), f.size());
+            } catch (const DocStoreError& e) {
+                throw IoError(e.what());
+            }
+        }
+        return docs;
+    }
+    std::string get_doc(uint32_t doc_id) {
+        try {
+            return doc_store().get_doc(doc_id);
+        } catch (const DocStoreError& e) {
+            throw IoError(e.what());
+        }
+    }
 
     const std::vector<uint8_t>& file(const std::string& name) {
         auto it = files.find(name);

@@ -36,6 +36,7 @@ struct RequestPlan {
     std::vector<vhost::FacetRequest> facets;
     bool has_facets = false;
     uint32_t facet_begin = 0;  // first of the request's entries in BatchPlan::facets
+    bool why_found = false;    // Request::why_found: the matched term texts are kept for highlighting (execution_plan.rs:416)
 };
 
 // `x op y` boost expression (src/expression.rs:25-100)
@@ -614,6 +615,7 @@ struct BatchPlan {
     void plan_request(const vhost::Request& request, RequestPlan& rp, QueryProgram& qp) {
         rp.top = request.top.value_or(10);  // search.rs:146
         rp.skip = request.skip.value_or(0);
+        rp.why_found = request.why_found;
         if (!request.search_req) throw InvalidRequest("search_req is None, but is required in search");
         if (rp.top + rp.skip > vdev::kMaxK) throw Unsupported("top + skip above 256 is outside the accelerated path");
 

@@ -6,6 +6,7 @@
 
 #include "../../../include/veloci_b200.h"
 #include "engine.hpp"
+#include "highlight.hpp"
 
 namespace vsteps {
 
@@ -40,6 +41,53 @@ inline void materialize_facets(vdev::Batch& b, std::vector<std::vector<FacetGrou
             out[q].push_back(std::move(fg));
         }
     }
+}
+
+// SearchResult::why_found_terms of request q (src/search.rs:186): per dictionary path ("<field>.textindex") the texts of the
+// terms its search parts matched (term_text_in_field, search_field.rs:386-389; merged over the parts, set_op.rs:49-64).
+inline vhost::TermSets why_found_terms(vdev::Batch& b, uint32_t q) {
+    vhost::TermSets out;
+    const vdev::QueryProgram& qp = b.plan.programs[q];
+    for (uint32_t l = 0; l < qp.n_leaves; ++l) {
+        const uint32_t part = b.plan.leaf_part[qp.leaf_begin + l];
+        if (b.plan.parts[part].flags & vdev::kPartList) continue;  // phrase / locality / boost lists are not search parts
+        const std::string& path = b.plan.dict_names[b.plan.part_dict[part]];
+        const vhost::TermDict& dict = b.ix->host->dict.at(path);
+        std::vector<uint32_t> terms;
+        std::vector<float> scores;
+        b.download_matches(part, terms, scores);
+        for (uint32_t id : terms) {
+            size_t slot = 0;
+            if (dict.find_id(id, slot)) out[path].insert(dict.term(slot));
+        }
+    }
+    return out;
+}
+
+// search::to_search_result without `select` (src/search.rs:65-110): the documents of request q's hits from the document
+// store, each with its hit and -- when the request asked for why_found -- the highlighted texts of the matched terms.
+// {"num_hits": n, "data": [{"doc": {..}, "hit": {"id": .., "score": ..}, "why_found": {"field": ["<b>..</b>"]}}]}
+inline std::string result_docs(vdev::Batch& b, uint32_t q) {
+    const vplan::RequestPlan& rp = b.plan.requests[q];
+    uint64_t num_hits = 0;
+    const uint32_t cap = (uint32_t)std::min<uint64_t>(rp.top, vdev::kMaxK);
+    std::vector<vdev::vgpu_hit_pod> hits((size_t)cap + 1);
+    const uint32_t n = b.result(q, &num_hits, hits.data(), cap);
+    vhost::TermSets terms;
+    if (rp.why_found && n) terms = why_found_terms(b, q);
+    std::string out = "{\"num_hits\":" + std::to_string(num_hits) + ",\"data\":[";
+    for (uint32_t i = 0; i < n; ++i) {
+        const std::string doc = b.ix->host->get_doc(hits[i].id);
+        if (i) out += ',';
+        out += "{\"doc\":" + doc + ",\"hit\":{\"id\":" + std::to_string(hits[i].id) + ",\"score\":";
+        char buf[48];
+        snprintf(buf, sizeof buf, "%.9g", (double)hits[i].score);
+        out += buf;
+        out += "},\"why_found\":";
+        vhost::write_highlights(out, vhost::highlight_document(b.ix->host->metadata, doc, terms));
+        out += '}';
+    }
+    return out + "]}";
 }
 
 inline vhost::SearchPart parse_part(const char* json) {

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <sstream>
 
+#include "../host/highlight.hpp"
 #include "../host/query_generator.hpp"
 #include "../host/regex_dfa.hpp"
 #include "../host/request.hpp"
@@ -205,6 +206,74 @@ int vidx_regex_match(const char* pattern, int case_insensitive, int starts_with,
     } catch (const std::exception& e) {
         set_err(out, outlen, e.what());
         return 9;
+    }
+}
+
+// DocLoader::get_doc over the `data` file of `dir` (host/doc_store.hpp, the product's reader): the document text.
+int vidx_get_doc(const char* dir, uint32_t doc_id, char* out, size_t outlen) {
+    try {
+        const std::vector<uint8_t> bytes = vhost::read_file(std::string(dir) + "/data");
+        const vhost::DocLoader loader(bytes.data(), bytes.size());
+        const std::string doc = loader.get_doc(doc_id);
+        if (doc.size() + 1 > outlen) throw std::runtime_error("document larger than the output buffer");
+        set_err(out, outlen, doc.c_str());
+        return 0;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
+        return 1;
+    }
+}
+
+// DocStoreWriter over the given documents (a JSON list of strings) into `path`; lz4_block_decompress over a hex block.
+int vidx_write_doc_store(const char* path, const char* docs_json, char* err, size_t errlen) {
+    try {
+        const vjson::Value docs = vjson::parse(docs_json, strlen(docs_json));
+        vhost::DocStoreWriter w;
+        std::vector<uint8_t> bytes;
+        for (auto& d : docs.arr) w.add_doc(d.str, bytes);
+        w.finish(bytes);
+        vhost::write_file(path, bytes.data(), bytes.size());
+        return 0;
+    } catch (const std::exception& e) {
+        set_err(err, errlen, e.what());
+        return 1;
+    }
+}
+int vidx_lz4_decompress(const uint8_t* block, size_t n, uint8_t* out, size_t out_len, char* err, size_t errlen) {
+    try {
+        vfmt::lz4_block_decompress(block, n, out, out_len);
+        return 0;
+    } catch (const std::exception& e) {
+        set_err(err, errlen, e.what());
+        return 1;
+    }
+}
+int vidx_lz4_compress(const uint8_t* src, size_t n, uint8_t* out, size_t cap, size_t* out_len) {
+    std::vector<uint8_t> bytes;
+    vfmt::lz4_compress_prepend_size(src, n, bytes);
+    if (bytes.size() > cap) return 1;
+    memcpy(out, bytes.data(), bytes.size());
+    *out_len = bytes.size();
+    return 0;
+}
+
+// highlight_on_original_document (host/highlight.hpp) with the field options of `dir`'s metaData.json: `terms_json` is
+// {"<field>.textindex": ["term", ...]}; writes {"<field>": ["<b>..</b> ..", ...]}.
+int vidx_highlight_doc(const char* dir, const char* doc_json, const char* terms_json, char* out, size_t outlen) {
+    try {
+        const std::vector<uint8_t> mj = vhost::read_file(std::string(dir) + "/metaData.json");
+        const vhost::Metadata meta = vhost::metadata_from_json(vjson::parse((const char*)mj.data(), mj.size()));
+        const vjson::Value terms = vjson::parse(terms_json, strlen(terms_json));
+        vhost::TermSets sets;
+        for (auto& kv : terms.obj)
+            for (auto& t : kv.second.arr) sets[kv.first].insert(t.str);
+        std::string s;
+        vhost::write_highlights(s, vhost::highlight_document(meta, doc_json, sets));
+        set_err(out, outlen, s.c_str());
+        return 0;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
+        return 1;
     }
 }
 

@@ -22,6 +22,7 @@
 #include "../format/codecs.hpp"
 #include "../format/fst.hpp"
 #include "../format/unicode.hpp"
+#include "../host/doc_store.hpp"
 #include "../host/persistence.hpp"
 #include "../vjson.hpp"
 
@@ -225,6 +226,19 @@ class Indexer {
             walk(d, root, h1, root, path, "", /*pass=*/1);
         }
         meta_.num_docs = docs_.size();
+        {  // write_docs (src/create/write_docs.rs:11-34): the documents as JSON text, in the compressed store `data`
+            vhost::DocStoreWriter store;
+            std::vector<uint8_t> bytes;
+            uint64_t indexed = 0;
+            for (auto& d : docs_) {
+                const std::string text = vjson::to_string(d);
+                indexed += text.size();
+                store.add_doc(text, bytes);
+            }
+            store.finish(bytes);
+            vhost::write_file(dir_ + "/data", bytes.data(), bytes.size());
+            meta_.bytes_indexed = indexed;
+        }
         for (auto& kv : terms_in_path_) {
             const std::string& path = kv.first;
             TermDataInPath& td = kv.second;
