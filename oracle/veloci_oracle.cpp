@@ -35,6 +35,7 @@
 #include "../veloci_b200/csrc/index/indexer.hpp"
 #include "../veloci_b200/csrc/vjson.hpp"
 #include "regex_sim.hpp"
+#include "rust_lower.hpp"
 
 using vhost::BoostFun;
 using vhost::BoostPart;
@@ -169,7 +170,7 @@ static void levenshtein_search(const vhost::TermDict& dict, const std::string& q
     std::vector<uint32_t> q;
     vfmt::utf8_decode(query, q);
     if (case_insensitive)
-        for (auto& c : q) c = vfmt::lower_scalar(c);
+        for (auto& c : q) c = olow::lower_one(c);  // (the matching automaton folds scalar by scalar: no context, no expansion)
     const size_t m = q.size();
     std::vector<std::vector<uint32_t>> rows(1, std::vector<uint32_t>(m + 1));
     for (size_t j = 0; j <= m; ++j) rows[0][j] = (uint32_t)j;
@@ -198,7 +199,7 @@ static void levenshtein_search(const vhost::TermDict& dict, const std::string& q
         while (pos < klen && !accepted) {
             size_t next = pos;
             uint32_t cp = vfmt::utf8_next(key, klen, next);
-            if (case_insensitive) cp = vfmt::lower_scalar(cp);
+            if (case_insensitive) cp = olow::lower_one(cp);
             const size_t k = chars.size();
             std::vector<uint32_t> row(m + 1);
             row[0] = (uint32_t)k + 1;
@@ -251,7 +252,7 @@ static SearchFieldResult get_term_ids_in_field(const Persistence& p, PlanRequest
     SearchFieldResult result;
     result.request = req;
     if (req.terms.empty()) throw InvalidRequest("search part without terms");
-    std::string lower_term = vfmt::to_lowercase(req.terms[0]);
+    std::string lower_term = olow::to_lowercase(req.terms[0]);
     if (req.levenshtein_distance) {
         uint32_t chars = (uint32_t)vfmt::utf8_count(lower_term);
         req.levenshtein_distance = std::min(*req.levenshtein_distance, chars - 1u);  // wraps for the empty term like release Rust
@@ -271,7 +272,7 @@ static SearchFieldResult get_term_ids_in_field(const Persistence& p, PlanRequest
         uint32_t token_text_id = dict.ids[slot];
         if (options.get_ids) result.hits_ids.push_back(token_text_id);
         if (options.get_scores) {
-            std::string line_lower = vfmt::to_lowercase(dict.term(slot));
+            std::string line_lower = olow::to_lowercase(dict.term(slot));
             bool prefix_matches = should_check_prefix_match && line_lower.compare(0, lower_term.size(), lower_term) == 0 && line_lower.size() >= lower_term.size();
             float score = get_default_score_for_distance(distance_dfa(line_lower, lower_term, d_score), prefix_matches);
             if (limit_result) {
@@ -284,7 +285,7 @@ static SearchFieldResult get_term_ids_in_field(const Persistence& p, PlanRequest
             }
             result.hits_scores.push_back(Hit{token_text_id, score});
         }
-        if (options.return_term) result.terms[token_text_id] = options.return_term_lowercase ? vfmt::to_lowercase(dict.term(slot)) : dict.term(slot);  // :331-337
+        if (options.return_term) result.terms[token_text_id] = options.return_term_lowercase ? olow::to_lowercase(dict.term(slot)) : dict.term(slot);  // :331-337
     };
     if (req.is_regex) {  // search_field.rs:72-83: the pattern's DFA instead of the Levenshtein automaton, same stream order
         std::unique_ptr<oracle_regex::Program> program;
@@ -1290,6 +1291,11 @@ static std::string call(const Persistence* p, const std::string& fn, const vjson
         } catch (const oracle_regex::OutsideSubset& e) {
             return std::string("\"outside\"");
         }
+    }
+    if (fn == "to_lowercase") {
+        std::string out;
+        vjson::write_string(out, olow::to_lowercase(a.get("text")->str));
+        return out;
     }
     if (fn == "distance") return std::to_string((int)distance(a.get("a")->str, a.get("b")->str));
     if (fn == "distance_dfa") return std::to_string((int)distance_dfa(a.get("hit")->str, a.get("term")->str, (uint32_t)a.get("d")->num));

@@ -489,3 +489,37 @@ def test_result_docs_and_why_found(gpu, native_libs):
             assert h["why_found"] == ohl.highlight_on_original_document(columns, h["doc"], terms), req
     with pytest.raises(gpu.VelociGpuError):
         index.get_doc(len(fx.TEST_WHYFOUND_DOCS))
+
+
+def test_lowercase_with_expansion_and_final_sigma(gpu, native_libs):
+    """Scoring runs on Rust-lowercased text (search_field.rs:284,312): U+0130 lower-cases to two scalars, a word-final capital
+    sigma to U+03C2.  Terms and queries with them, fuzzy and exact, case-folding and not: hits and scores equal the oracle's
+    (whose lower-casing is pinned against CPython's in tests/test_lowercase.py)."""
+    docs = [{"title": t} for t in ("İstanbul", "istanbul", "ΟΔΟΣ ΑΘΗΝΑΣ", "οδος", "οδοσ", "Straße", "STRASSE", "ΣΟΦΙΑ", "ISTANBUL ΟΔΟΣ", "İİ", "ΑΣ")]
+    d = tempfile.mkdtemp(prefix="vb200_r2_lower_")
+    helpers.create_index(d, docs, {"title": {"fulltext": {"tokenize": True}}})
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    reqs = []
+    for term in ("istanbul", "İstanbul", "i̇stanbul", "ISTANBUL", "οδος", "οδοσ", "ΟΔΟΣ", "αθηνας", "strasse", "straße", "σοφια", "İİ", "ας", "ασ"):
+        for lev in (0, 1, 2):
+            for extra in ({}, {"ignore_case": False}, {"starts_with": True}):
+                reqs.append({"search_req": {"search": {"terms": [term], "path": "title", "levenshtein_distance": lev, **extra}}, "top": 20})
+    texts = [json.dumps(r, ensure_ascii=False) for r in reqs]
+    b = index.prepare(texts).execute()
+    n_hits = 0
+    for q, r in enumerate(reqs):
+        try:
+            c = oracle.search(texts[q])
+        except helpers.OracleError:
+            assert b.status(q) != 0, r
+            continue
+        if b.status(q) == 8:  # case-sensitive search for a term whose lower-case form has another length: declared outside the path
+            assert r["search_req"]["search"].get("ignore_case") is False and "İ" in r["search_req"]["search"]["terms"][0], (r, b.message(q))
+            continue
+        assert b.status(q) == 0, (r, b.message(q))
+        g = b.result(q)
+        assert g["num_hits"] == c["num_hits"], r
+        ok, why = helpers.same_topk([(i, float(s)) for i, s in g["data"]], [(h[0], float(np.float32(h[1]))) for h in c["data"]])
+        assert ok, (r, why)
+        n_hits += g["num_hits"]
+    assert n_hits > 100

@@ -39,6 +39,12 @@ struct DictView {
     const uint16_t* sym[2];  // [0] lower-cased, [1] raw
     const uint32_t* off[2];
     const TilePrefix* tiles[2];
+    // The few terms whose Rust `to_lowercase` differs from the scalar-by-scalar lowering of sym[0] (U+0130 expands, a
+    // word-final capital sigma becomes U+03C2): their exact lower-cased symbols, for scoring (search_field.rs:312).
+    const uint32_t* exc_slot;  // sorted dictionary slots
+    const uint32_t* exc_off;   // [n_exc + 1] into exc_sym
+    const uint16_t* exc_sym;
+    uint32_t n_exc, exc_pad;
 };
 
 struct Posting {  // 8 B, one 64-bit load
@@ -187,7 +193,7 @@ struct PartQuery {  // one distinct RequestSearchPart of the batch (272 B)
     float boost;             // per-part scalar boost (:359-364)
     uint32_t lower_bytes;    // byte length of the lower-cased query (distance() 255 rule, :706)
     uint32_t postings;       // index into the batch's PostingsView table, kNoValue if absent
-    uint32_t pad;
+    uint32_t m_score;        // scalars of the lower-cased query (differs from m only where to_lowercase changes the length)
 };
 
 struct MatchRecord {  // fuzzy_match output, unordered

@@ -458,8 +458,17 @@ __global__ void score_scatter_kernel(ScoreScatterArgs a) {
     } else {
         const DictView& dict = a.dicts[a.part_dict[r.part]];
         const uint16_t* ts = dict.sym[0] + dict.off[0][r.slot];
-        const uint32_t n = dict.off[0][r.slot + 1] - dict.off[0][r.slot];
-        const uint32_t m = q.m;
+        uint32_t n = dict.off[0][r.slot + 1] - dict.off[0][r.slot];
+        if (dict.n_exc) {  // a term whose exact lower-case text is kept aside (U+0130 / final sigma)
+            uint32_t lo = 0, hi = dict.n_exc;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (dict.exc_slot[mid] < r.slot) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo < dict.n_exc && dict.exc_slot[lo] == r.slot) ts = dict.exc_sym + dict.exc_off[lo], n = dict.exc_off[lo + 1] - dict.exc_off[lo];
+        }
+        const uint32_t m = q.m_score;
         bool prefix_matches = false;
         if ((q.flags & kPartCheckPrefix) && n >= m) {
             prefix_matches = true;

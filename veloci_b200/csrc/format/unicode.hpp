@@ -3,13 +3,16 @@
 // The reference lower-cases with Rust's `str::to_lowercase()`
 // (src/search/search_field.rs:284,312).  This table holds every scalar whose
 // lowercase form is a single scalar (generated from the Unicode database by
-// tools/gen_lower_table.py); the handful of scalars that expand to several
-// (U+0130) and the context rule for final sigma are NOT reproduced -- they map
-// to themselves / to U+03C3.  ASCII is handled inline.
+// tools/gen_lower_table.py); `to_lowercase` adds the one scalar that expands
+// (U+0130 -> "i" + U+0307) and the context rule for final sigma, with the Cased /
+// Case_Ignorable tables of case_props.hpp.  `lower_scalar` alone stays context
+// free.  ASCII is handled inline.
 #pragma once
 #include <cstdint>
 #include <string>
 #include <vector>
+
+#include "case_props.hpp"
 
 namespace vfmt {
 
@@ -251,11 +254,56 @@ inline void utf8_append(std::string& out, uint32_t cp) {
     }
 }
 
+inline bool in_ranges(const uint32_t (*ranges)[2], int n, uint32_t cp) {
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) / 2;
+        if (cp < ranges[mid][0]) hi = mid - 1;
+        else if (cp > ranges[mid][1]) lo = mid + 1;
+        else return true;
+    }
+    return false;
+}
+
+// Rust's `str::to_lowercase` on scalars: every scalar's lowercase mapping, U+0130 expanding to "i" + U+0307, and a capital
+// sigma becoming the final form when a cased letter precedes it and none follows (case-ignorable scalars skipped on both
+// sides: alloc::str::to_lowercase / map_uppercase_sigma).
+inline void lowercase_scalars(const std::vector<uint32_t>& in, std::vector<uint32_t>& out) {
+    out.clear();
+    out.reserve(in.size());
+    for (size_t i = 0; i < in.size(); ++i) {
+        const uint32_t cp = in[i];
+        if (cp < 0x80) {
+            out.push_back((cp >= 'A' && cp <= 'Z') ? cp + 32 : cp);
+        } else if (cp == 0x3A3) {
+            auto cased_after_ignorables = [&](long from, long step) {
+                for (long j = from; j >= 0 && j < (long)in.size(); j += step)
+                    if (!in_ranges(kCaseIgnorableRanges, kNumCaseIgnorableRanges, in[(size_t)j])) return in_ranges(kCasedRanges, kNumCasedRanges, in[(size_t)j]);
+                return false;
+            };
+            const bool word_final = cased_after_ignorables((long)i - 1, -1) && !cased_after_ignorables((long)i + 1, 1);
+            out.push_back(word_final ? 0x3C2u : 0x3C3u);
+        } else if (cp == 0x130) {
+            out.push_back(0x69), out.push_back(0x307);
+        } else {
+            out.push_back(lower_scalar(cp));
+        }
+    }
+}
+
 inline std::string to_lowercase(const std::string& s) {
+    bool ascii = true;
+    for (unsigned char c : s) ascii = ascii && c < 0x80;
     std::string out;
     out.reserve(s.size());
-    size_t i = 0;
-    while (i < s.size()) utf8_append(out, lower_scalar(utf8_next((const uint8_t*)s.data(), s.size(), i)));
+    if (ascii) {
+        for (char c : s) out.push_back((c >= 'A' && c <= 'Z') ? (char)(c + 32) : c);
+        return out;
+    }
+    std::vector<uint32_t> in, low;
+    utf8_decode(s, in);
+    lowercase_scalars(in, low);
+    for (uint32_t cp : low) utf8_append(out, cp);
     return out;
 }
 

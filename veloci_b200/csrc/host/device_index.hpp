@@ -309,6 +309,9 @@ struct DictDev {
     SymbolSet lower;
     SymbolSet raw;  // empty when identical to `lower`
     bool has_raw = false;
+    DevBuf<uint32_t> exc_slot, exc_off;  // terms whose to_lowercase is not the scalar-by-scalar lowering (DictView::exc_*)
+    DevBuf<uint16_t> exc_sym;
+    uint32_t n_exc = 0;
     uint32_t n_tiles = 0;
 
     uint16_t code_of(uint32_t scalar) const {
@@ -326,6 +329,7 @@ struct DictDev {
         v.sym[0] = lower.sym.p, v.off[0] = lower.off.p, v.tiles[0] = lower.tiles.p;
         const SymbolSet& r = has_raw ? raw : lower;
         v.sym[1] = r.sym.p, v.off[1] = r.off.p, v.tiles[1] = r.tiles.p;
+        v.exc_slot = exc_slot.p, v.exc_off = exc_off.p, v.exc_sym = exc_sym.p, v.n_exc = n_exc, v.exc_pad = 0;
         return v;
     }
 };
@@ -511,7 +515,7 @@ struct DeviceIndex {
         DictDev dd;
         dd.n = d.size();
         dd.n_tiles = (uint32_t)((dd.n + kDictTile - 1) / kDictTile);
-        bool any_upper = false;
+        bool any_upper = false, context_case = false;
         std::vector<uint32_t> scalars;
         {
             std::vector<uint8_t> seen_small(0x10000 / 8, 0);
@@ -529,6 +533,8 @@ struct DeviceIndex {
                 if (lc != cp) any_upper = true;
                 mark(cp);
                 mark(lc);
+                if (cp == 0x130) mark(0x69), mark(0x307), context_case = true;  // to_lowercase expands it
+                if (cp == 0x3A3) mark(0x3C2), context_case = true;             // ... and may give the final sigma
             }
             for (uint32_t cp = 0; cp < 0x10000; ++cp)
                 if (seen_small[cp >> 3] & (1u << (cp & 7))) scalars.push_back(cp);
@@ -541,6 +547,32 @@ struct DeviceIndex {
         dd.ids.upload(d.ids);
         std::vector<uint16_t> lower_bytes;
         build_symbol_set(d, dd.alphabet, true, dd.lower, &lower_bytes);
+        if (context_case) {  // Rust's to_lowercase of these terms, kept beside the scalar-wise lowering the matching runs on
+            std::vector<uint32_t> slots, offs{0}, scalars, exact;
+            std::vector<uint16_t> syms;
+            for (size_t i = 0; i < d.size(); ++i) {
+                const uint8_t* key = &d.bytes[d.offsets[i]];
+                const size_t klen = d.offsets[i + 1] - d.offsets[i];
+                bool candidate = false;
+                for (size_t b = 0; b + 1 < klen; ++b) candidate = candidate || (key[b] == 0xC4 && key[b + 1] == 0xB0) || (key[b] == 0xCE && key[b + 1] == 0xA3);
+                if (!candidate) continue;
+                scalars.clear();
+                for (size_t pos = 0; pos < klen;) scalars.push_back(vfmt::utf8_next(key, klen, pos));
+                vfmt::lowercase_scalars(scalars, exact);
+                bool same = exact.size() == scalars.size();
+                for (size_t j = 0; same && j < exact.size(); ++j) same = exact[j] == vfmt::lower_scalar(scalars[j]);
+                if (same) continue;
+                size_t bytes = 0;
+                for (uint32_t cp : exact) {
+                    syms.push_back(dd.code_of(cp));
+                    bytes += cp < 0x80 ? 1 : cp < 0x800 ? 2 : cp < 0x10000 ? 3 : 4;
+                }
+                lower_bytes[i] = (uint16_t)std::min<size_t>(bytes, 65535);
+                slots.push_back((uint32_t)i), offs.push_back((uint32_t)syms.size());
+            }
+            dd.n_exc = (uint32_t)slots.size();
+            if (dd.n_exc) dd.exc_slot.upload(slots), dd.exc_off.upload(offs), dd.exc_sym.upload(syms);
+        }
         dd.lower_bytes.upload(lower_bytes);
         dd.has_raw = any_upper;
         if (any_upper) build_symbol_set(d, dd.alphabet, false, dd.raw, nullptr);

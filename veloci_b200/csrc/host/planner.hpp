@@ -101,8 +101,9 @@ struct BatchPlan {
             h *= 0xFF51AFD7ED558CCDull;
             h ^= h >> 32;
         };
-        const uint32_t m = std::min<uint32_t>(q.m, 64);
+        const uint32_t m = std::min<uint32_t>(std::max(q.m, q.m_score), 64);
         for (uint32_t j = 0; j < m; ++j) mix(((uint64_t)q.match_sym[j] << 16) | q.score_sym[j]);
+        mix(q.m_score);
         uint32_t boost_bits;
         memcpy(&boost_bits, &q.boost, 4);
         mix(((uint64_t)q.m << 32) | q.d_score);
@@ -225,7 +226,7 @@ struct BatchPlan {
             vfmt::utf8_decode(lower_term, low);
             lower_bytes = lower_term.size();
         }
-        if (raw.size() > 64) throw Unsupported("search terms longer than 64 characters are outside the accelerated path");
+        if (raw.size() > 64 || low.size() > 64) throw Unsupported("search terms longer than 64 characters are outside the accelerated path");
         if (req.is_regex) {
             // search_field.rs:72-78: the pattern must compile (the reference unwraps the build); the tables for the
             // dictionary's alphabet are made when the plan is uploaded (Batch::prepare_tables), so the plan stays exportable
@@ -240,6 +241,7 @@ struct BatchPlan {
         PartQuery q;
         memset(&q, 0, sizeof q);
         q.m = (uint32_t)raw.size();
+        q.m_score = (uint32_t)low.size();  // (Rust's to_lowercase: U+0130 becomes two scalars)
         uint32_t d = 0;
         if (req.levenshtein_distance) d = std::min<uint32_t>(*req.levenshtein_distance, (uint32_t)low.size() - 1u);  // wraps for "" like release Rust
         q.d_score = d;
@@ -252,10 +254,8 @@ struct BatchPlan {
         q.lower_bytes = (uint32_t)lower_bytes;
         q.postings = pid;
         auto code_of = [&](uint32_t scalar) { return scalar < 128 ? ft.ascii_code[scalar] : ft.dict->code_of(scalar); };
-        for (size_t j = 0; j < raw.size(); ++j) {
-            q.match_sym[j] = code_of(case_insensitive ? vfmt::lower_scalar(raw[j]) : raw[j]);
-            q.score_sym[j] = code_of(low[j]);
-        }
+        for (size_t j = 0; j < raw.size(); ++j) q.match_sym[j] = code_of(case_insensitive ? vfmt::lower_scalar(raw[j]) : raw[j]);
+        for (size_t j = 0; j < low.size(); ++j) q.score_sym[j] = code_of(low[j]);
         if (req.is_regex && !req.top) {  // never shared: its matches come from its own DFA, which PartQuery does not describe
             q.flags |= vdev::kPartRegex;
             const uint32_t id = (uint32_t)parts.size();

@@ -277,4 +277,12 @@ int vidx_highlight_doc(const char* dir, const char* doc_json, const char* terms_
     }
 }
 
+// vfmt::to_lowercase (format/unicode.hpp: the product's restatement of Rust's str::to_lowercase)
+int vidx_to_lowercase(const char* text, char* out, size_t outlen) {
+    const std::string low = vfmt::to_lowercase(text);
+    if (low.size() + 1 > outlen) return 1;
+    memcpy(out, low.c_str(), low.size() + 1);
+    return 0;
+}
+
 }  // extern "C"
