@@ -285,4 +285,32 @@ int vidx_to_lowercase(const char* text, char* out, size_t outlen) {
     return 0;
 }
 
+// vfmt::FstReader (format/fst.hpp, the product's dictionary reader) over the file `path`: every "hex(key)<TAB>value" line in key
+// order, then get() and ord_to_term() of every key as a self check ("ok" / the first disagreement) in the last line.
+int vidx_fst_dump(const char* path, char* out, size_t outlen) {
+    try {
+        const std::vector<uint8_t> bytes = vhost::read_file(path);
+        const vfmt::FstReader r(bytes.data(), bytes.size());
+        std::string s;
+        std::vector<std::pair<std::string, uint64_t>> items;
+        r.for_each([&](const std::string& k, uint64_t v) { items.emplace_back(k, v); });
+        std::string check = "ok";
+        for (auto& kv : items) {
+            static const char* hex = "0123456789abcdef";
+            for (unsigned char c : kv.first) s += hex[c >> 4], s += hex[c & 15];
+            s += "\t" + std::to_string(kv.second) + "\n";
+            uint64_t v = 0;
+            if (!r.get(kv.first, v) || v != kv.second) check = "get(" + kv.first + ") disagrees";
+        }
+        if (items.size() != r.len()) check = "key count differs from the footer";
+        s += check;
+        if (s.size() + 1 > outlen) throw std::runtime_error("output buffer too small");
+        set_err(out, outlen, s.c_str());
+        return 0;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
+        return 1;
+    }
+}
+
 }  // extern "C"
