@@ -523,3 +523,65 @@ def test_lowercase_with_expansion_and_final_sigma(gpu, native_libs):
         assert ok, (r, why)
         n_hits += g["num_hits"]
     assert n_hits > 100
+
+
+def test_large_top_and_skip(gpu, sharded_corpus):
+    """top + skip beyond 256 (the reference sorts any `top`, src/search.rs:210-218): up to 4096 keys per request the heap is
+    merged in global memory on the tile path.  Ids, scores and counts against the oracle; mixed with small-k requests in one
+    batch; refused above the limit and on sharded handles."""
+    d, reqs = sharded_corpus
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    picks = []
+    for i, (top, skip) in enumerate([(1000, 0), (300, 700), (4096, 0), (10, 4000), (257, 0), (10, 0), (2000, 100), (64, 0)]):
+        r = json.loads(reqs[i * 7 if i % 2 == 0 else 400 + i])  # or3 requests and `and` requests (with facets)
+        r["top"], r["skip"] = top, skip
+        picks.append(r)
+    single = {"search_req": {"search": {"terms": ["ab"], "path": "body", "starts_with": True}}, "top": 3000}
+    picks.append(single)
+    # more skip_when_score values than the old limit of four (boost.rs:283-377 takes any number)
+    picks.append({"search_req": {"search": {"terms": ["ab"], "path": "body", "starts_with": True}}, "top": 50,
+                  "boost": [{"path": "commonness", "boost_fun": "Multiply", "skip_when_score": [1.5, 2.5, 3.0, 4.0, 5.0, 6.5, 7.0]}]})
+    texts = [json.dumps(r) for r in picks]
+    b = index.prepare(texts).execute()
+    total = 0
+    for q, r in enumerate(picks):
+        assert b.status(q) == 0, (r["top"], b.message(q))
+        g, c = b.result(q), oracle.search(texts[q])
+        assert g["num_hits"] == c["num_hits"], (q, r["top"], r["skip"])
+        assert len(g["data"]) == len(c["data"]), (q, r["top"], r["skip"], len(g["data"]), len(c["data"]))
+        ok, why = helpers.same_topk([(i, float(s)) for i, s in g["data"]], [(h[0], float(np.float32(h[1]))) for h in c["data"]])
+        assert ok, (q, r["top"], r["skip"], why)
+        total += len(g["data"])
+    assert total > 3000
+    too_many = dict(picks[0], top=4097)
+    b = index.prepare([json.dumps(too_many)]).execute()
+    assert b.status(0) == 8 and "4096" in b.message(0)
+    shard = gpu.Index(d, shard_rank=0, n_shards=2)
+    b = shard.prepare([texts[0]])
+    assert b.status(0) == 8 and "sharded" in b.message(0)
+    # the top_n step takes the same sizes
+    rng = np.random.default_rng(2)
+    hits = [(int(i), float(np.float32(rng.random() * 9))) for i in rng.choice(SHARDED["num_docs"], size=6000, replace=False)]
+    got = index.top_n(hits, 1500, 20)
+    ref = sorted(hits, key=lambda h: (-h[1], -h[0]))[20:1520]
+    assert [g[0] for g in got] == [r[0] for r in ref]
+
+
+def test_facets_with_many_groups(gpu, native_libs):
+    """A facet field with more groups than the old 1024 limit (src/facet.rs:31-73 takes any number): `top: null` returns them
+    all, `top: 2000` the first 2000 in (count desc, value id asc) order."""
+    rng = np.random.default_rng(6)
+    docs = [{"body": "hit" if i % 3 else "miss", "tags": ["t%04d" % int(x) for x in rng.integers(0, 3000, size=3)]} for i in range(9000)]
+    d = tempfile.mkdtemp(prefix="vb200_r2_facets_")
+    helpers.create_index(d, docs, {"*GLOBAL*": {"features": ["All"]}, "tags[]": {"facet": True}})
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    reqs = [{"search_req": {"search": {"terms": ["hit"], "path": "body"}}, "facets": [{"field": "tags[]", "top": top}]} for top in (None, 2000, 1025, 5)]
+    texts = [json.dumps(r) for r in reqs]
+    b = index.prepare(texts).execute()
+    for q, r in enumerate(reqs):
+        assert b.status(q) == 0, b.message(q)
+        got = b.result(q)["facets"]["tags[]"]
+        ref = oracle.search(texts[q])["facets"]["tags[]"]
+        assert len(got) == len(ref) and len(got) == (r["facets"][0]["top"] or len(ref))
+        assert [(g[0], g[1]) for g in got] == [(x[0], x[1]) for x in ref], q
+    assert len(b.result(0)["facets"]["tags[]"]) > 2500

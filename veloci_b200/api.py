@@ -260,7 +260,7 @@ class Batch:
     def message(self, q):
         return self.L.vgpu_batch_message(self.h, q).decode("utf-8", "replace")
 
-    def result(self, q, cap=256):
+    def result(self, q, cap=4096):
         """-> {"num_hits", "data": [(id, score)], "facets": {...}} of request q (raises for a failed request)."""
         st = self.status(q)
         if st != 0:

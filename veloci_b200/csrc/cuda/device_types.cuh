@@ -8,7 +8,9 @@ static const uint32_t kDictTile = 32;       // terms per dictionary tile: one wa
 static const uint32_t kTilePrefixMax = 8;   // symbols of the tile's common prefix that are kept
 static const uint32_t kNoValue = 0xFFFFFFFFu;
 static const uint32_t kMaxLeaves = 64;      // search parts per request tree on the tile path (one shared-memory array of a tile's anchors each)
-static const uint32_t kMaxK = 256;          // top + skip on the tile path
+static const uint32_t kMaxK = 256;          // top + skip whose heap is merged in shared memory (and the limit on sharded handles)
+static const uint32_t kMaxKLarge = 4096;    // top + skip on one device: beyond kMaxK the heap is merged in global memory (tile path only)
+static const uint32_t kTileBlocksPerSm = 16;  // upper bound of resident tile_eval CTAs per SM (sizes the large-k merge scratch)
 
 struct TilePrefix {  // 20 bytes
     uint16_t sym[kTilePrefixMax];
@@ -233,13 +235,14 @@ static const uint32_t kTaskPostings = 128;  // postings one warp takes from a sl
 enum BoostFunDev : uint32_t { kBoostNone = 0, kBoostLog2 = 1, kBoostLog10 = 2, kBoostMultiply = 3, kBoostAdd = 4, kBoostReplace = 5 };
 enum ExprOp : uint32_t { kExprNone = 0, kExprDiv = 1, kExprMul = 2, kExprAdd = 3, kExprSub = 4 };
 
+static const uint32_t kMaxSkipWhenScore = 16;  // values of RequestBoostPart::skip_when_score a step carries
 struct BoostStep {  // add_boost on anchor ids (boost.rs:470-504, apply_boost :283-377)
     const uint32_t* column;
     uint32_t n;
     uint32_t fun;
     float param;
     uint32_t n_skip;
-    float skip[4];
+    float skip[kMaxSkipWhenScore];
     uint32_t expr_op;       // `x op y` expression, operands: $SCORE (= boost value) or a float
     uint32_t expr_left_is_score, expr_right_is_score;
     float expr_left, expr_right;

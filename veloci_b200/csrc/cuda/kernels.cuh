@@ -196,6 +196,7 @@ struct TileArgs {
     // per-query state
     unsigned long long* heap;  // [n_queries][heap_stride] keys, sorted descending, 0 = empty
     uint32_t heap_stride;
+    unsigned long long* merge_scratch;  // [n_sms * kTileBlocksPerSm][heap_stride]: merge buffer of requests with k > kMaxK (nullptr when none)
     unsigned long long* tau;   // current k-th best key (0 until k hits were seen)
     uint32_t* lock;
     unsigned long long* num_hits;

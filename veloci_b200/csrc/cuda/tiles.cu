@@ -940,23 +940,55 @@ __global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
                 __threadfence();
             }
             __syncthreads();
-            for (uint32_t i = tid; i < k; i += kTileThreads) {
-                s_heap[i] = __ldcg(heap + i);
-                s_out[i] = 0;
+            unsigned long long new_tau;
+            if (k <= kMaxK) {
+                for (uint32_t i = tid; i < k; i += kTileThreads) {
+                    s_heap[i] = __ldcg(heap + i);
+                    s_out[i] = 0;
+                }
+                __syncthreads();
+                const uint32_t n = k + n_list;
+                for (uint32_t e = tid; e < n; e += kTileThreads) {
+                    const unsigned long long key = e < k ? s_heap[e] : s_list[e - k];
+                    if (key == 0) continue;
+                    uint32_t rank = 0;
+                    for (uint32_t j = 0; j < k; ++j) rank += s_heap[j] > key;
+                    for (uint32_t j = 0; j < n_list; ++j) rank += s_list[j] > key;
+                    if (rank < k) s_out[rank] = key;
+                }
+                __syncthreads();
+                for (uint32_t i = tid; i < k; i += kTileThreads) __stcg(heap + i, s_out[i]);
+                new_tau = s_out[k - 1];
+            } else {
+                // large k: the heap stays in global memory.  It is sorted descending with the empty slots at its end, so a heap
+                // key's rank is its index plus the survivors above it, a survivor's rank the heap keys above it (binary search)
+                // plus the survivors above it; keys are distinct (the anchor is part of the key).
+                unsigned long long* scratch = a.merge_scratch + (size_t)blockIdx.x * a.heap_stride;
+                for (uint32_t i = tid; i < k; i += kTileThreads) scratch[i] = 0;
+                __syncthreads();
+                for (uint32_t e = tid; e < k; e += kTileThreads) {
+                    const unsigned long long key = __ldcg(heap + e);
+                    if (key == 0) continue;
+                    uint32_t rank = e;
+                    for (uint32_t j = 0; j < n_list; ++j) rank += s_list[j] > key;
+                    if (rank < k) scratch[rank] = key;
+                }
+                for (uint32_t e = tid; e < n_list; e += kTileThreads) {
+                    const unsigned long long key = s_list[e];
+                    uint32_t lo = 0, hi = k;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (__ldcg(heap + mid) > key) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    uint32_t rank = lo;
+                    for (uint32_t j = 0; j < n_list; ++j) rank += s_list[j] > key;
+                    if (rank < k) scratch[rank] = key;
+                }
+                __syncthreads();
+                for (uint32_t i = tid; i < k; i += kTileThreads) __stcg(heap + i, scratch[i]);
+                new_tau = scratch[k - 1];
             }
-            __syncthreads();
-            const uint32_t n = k + n_list;
-            for (uint32_t e = tid; e < n; e += kTileThreads) {
-                const unsigned long long key = e < k ? s_heap[e] : s_list[e - k];
-                if (key == 0) continue;
-                uint32_t rank = 0;
-                for (uint32_t j = 0; j < k; ++j) rank += s_heap[j] > key;
-                for (uint32_t j = 0; j < n_list; ++j) rank += s_list[j] > key;
-                if (rank < k) s_out[rank] = key;
-            }
-            __syncthreads();
-            for (uint32_t i = tid; i < k; i += kTileThreads) __stcg(heap + i, s_out[i]);
-            const unsigned long long new_tau = s_out[k - 1];
             __syncthreads();
             if (tid == 0) {
                 atomicMax(a.tau + q, new_tau);  // never below a threshold shared by the other shards
@@ -1003,6 +1035,7 @@ void launch_tile_eval(cudaStream_t st, const TileArgs& a, int n_sms) {
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_eval_kernel, kTileThreads, smem);
     if (per_sm < 1) per_sm = 1;
+    if (per_sm > (int)kTileBlocksPerSm) per_sm = (int)kTileBlocksPerSm;
     unsigned long long blocks = (unsigned long long)n_sms * (unsigned)per_sm;
     if (blocks > a.n_items) blocks = a.n_items;
     tile_eval_kernel<<<(unsigned)blocks, kTileThreads, smem, st>>>(a);
@@ -1092,6 +1125,10 @@ void launch_merge_heaps(cudaStream_t st, const uint64_t* src_keys, const uint64_
                         uint64_t* out_keys, uint64_t* out_hits) {
     if (!n_queries) return;
     const size_t smem = (size_t)n_src * stride * sizeof(uint64_t);
+    if (smem > 48 * 1024) {  // (requests with a large top on one device: up to kMaxKLarge keys per request)
+        static PerDeviceOnce configured;
+        if (configured.first()) cudaFuncSetAttribute(merge_heaps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    }
     merge_heaps_kernel<<<n_queries, 256, smem, st>>>(src_keys, src_hits, n_src, n_queries, stride, queries, out_keys, out_hits);
     count_launch();
 }

@@ -151,7 +151,7 @@ struct Batch {
     uint32_t pending_fast_items = 0;
     bool begun = false;
     // device: per-request state and results
-    DevBuf<unsigned long long> d_heap, d_tau, d_num_hits;
+    DevBuf<unsigned long long> d_heap, d_tau, d_num_hits, d_merge_scratch;
     DevBuf<uint32_t> d_lock;
     DevBuf<uint64_t> d_out_keys, d_out_hits;
     DevBuf<unsigned long long> d_emit;  // all hits of request 0 (step seam): (score key << 32) | anchor
@@ -930,6 +930,8 @@ struct Batch {
             a.n_tiles = n_tiles, a.tile_log2 = tile_log2, a.anchor_lo = (uint32_t)ix->anchor_lo, a.anchor_hi = (uint32_t)std::min<uint64_t>(ix->anchor_hi, 0xFFFFFFFFull);
             a.max_leaves = std::max<uint32_t>(1, plan.max_leaves);
             a.heap = d_heap.p, a.heap_stride = stride, a.tau = d_tau.p, a.lock = d_lock.p, a.num_hits = d_num_hits.p;
+            if (stride > kMaxK) d_merge_scratch.reserve((size_t)n_sms * kTileBlocksPerSm * stride);
+            a.merge_scratch = stride > kMaxK ? d_merge_scratch.p : nullptr;
             a.work_counter = d_counters.p + 1, a.n_items = n_items;
             a.emit = d_emit.p, a.emit_count = d_counters.p + 4, a.emit_capacity = emit_capacity;
             timed("tile_eval", [&] { launch_tile_eval(stream, a, n_sms); });

@@ -548,7 +548,7 @@ struct BatchPlan {
         s.fun = (uint32_t)b.boost_fun;
         s.param = b.param.value_or(0.0f);
         if (b.skip_when_score) {
-            if (b.skip_when_score->size() > 4) throw Unsupported("more than 4 skip_when_score values");
+            if (b.skip_when_score->size() > vdev::kMaxSkipWhenScore) throw Unsupported("more than " + std::to_string(vdev::kMaxSkipWhenScore) + " skip_when_score values");
             s.n_skip = (uint32_t)b.skip_when_score->size();
             for (size_t i = 0; i < b.skip_when_score->size(); ++i) s.skip[i] = (*b.skip_when_score)[i];
         }
@@ -592,7 +592,8 @@ struct BatchPlan {
             fs.hist_size = it->second.n_values;
         }
         const uint64_t top = fr.top ? *fr.top : (uint64_t)fs.hist_size;
-        if (std::min<uint64_t>(top, fs.hist_size) > 1024) throw Unsupported("facets with more than 1024 groups are outside the accelerated path");
+        // the groups are picked one arg-max round each (facet_topk_kernel): fine for the usual handful, seconds beyond this
+        if (std::min<uint64_t>(top, fs.hist_size) > 65536) throw Unsupported("facets with more than 65536 groups are outside the accelerated path");
         facets.push_back(fs);
         facet_top.push_back((uint32_t)std::min<uint64_t>(top, fs.hist_size));
         facet_text_path.push_back(steps.back());
@@ -617,7 +618,11 @@ struct BatchPlan {
         rp.skip = request.skip.value_or(0);
         rp.why_found = request.why_found;
         if (!request.search_req) throw InvalidRequest("search_req is None, but is required in search");
-        if (rp.top + rp.skip > vdev::kMaxK) throw Unsupported("top + skip above 256 is outside the accelerated path");
+        {  // the top-k heap: merged in shared memory up to 256 keys, in global memory up to 4096 (one device only: shards gather every heap)
+            const uint64_t limit = ix->n_shards > 1 ? vdev::kMaxK : vdev::kMaxKLarge;
+            if (rp.top > limit || rp.skip > limit || rp.top + rp.skip > limit)
+                throw Unsupported("top + skip above " + std::to_string(limit) + (ix->n_shards > 1 ? " on a sharded index" : "") + " is outside the accelerated path");
+        }
 
         std::vector<uint32_t>&leaves = scratch_leaves, &code = scratch_code, &post = scratch_post;
         leaves.clear(), code.clear(), post.clear();

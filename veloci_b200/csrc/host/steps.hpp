@@ -70,7 +70,7 @@ inline vhost::TermSets why_found_terms(vdev::Batch& b, uint32_t q) {
 inline std::string result_docs(vdev::Batch& b, uint32_t q) {
     const vplan::RequestPlan& rp = b.plan.requests[q];
     uint64_t num_hits = 0;
-    const uint32_t cap = (uint32_t)std::min<uint64_t>(rp.top, vdev::kMaxK);
+    const uint32_t cap = (uint32_t)std::min<uint64_t>(rp.top, vdev::kMaxKLarge);
     std::vector<vdev::vgpu_hit_pod> hits((size_t)cap + 1);
     const uint32_t n = b.result(q, &num_hits, hits.data(), cap);
     vhost::TermSets terms;
@@ -422,7 +422,7 @@ inline void add_boost(vdev::DeviceIndex& ix, const char* boost_json, vgpu_hitlis
 
 // top_n_sort + apply_top_skip (sort.rs:5-22, search.rs:230-239)
 inline void top_n(vdev::DeviceIndex& ix, const vgpu_hitlist& in, uint32_t top, uint32_t skip, vgpu_hitlist& out) {
-    if ((uint64_t)top + skip > vdev::kMaxK) throw vplan::Unsupported("top + skip above 256");
+    if ((uint64_t)top + skip > (ix.n_shards > 1 ? vdev::kMaxK : vdev::kMaxKLarge)) throw vplan::Unsupported("top + skip above " + std::to_string(ix.n_shards > 1 ? vdev::kMaxK : vdev::kMaxKLarge));
     std::vector<vdev::ExplicitList> lists = to_lists(&in, 1);
     vgpu_hitlist all;
     run_lists(ix, lists, {vdev::kOpLeaf, 0u}, {}, top + skip, false, all);
