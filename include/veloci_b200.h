@@ -262,6 +262,27 @@ int32_t vgpu_intersect_hits_ids(vgpu_index* idx, const vgpu_hitlist* inputs, uin
 /* IntersectScoresWithIds (plan_steps.rs:330-345; intersect_score_hits_with_ids, set_op.rs:311-326): the scored hits of
  * `scores` whose id is among `ids->ids`. */
 int32_t vgpu_intersect_scores_with_ids(vgpu_index* idx, const vgpu_hitlist* scores, const vgpu_hitlist* ids, vgpu_hitlist* out);
+/* PlanStepPhrasePairToAnchorId (src/plan_creator/plan_steps.rs:279-293) = get_anchor_for_phrases_in_field
+ * (src/search/search_field.rs:263-275): the anchors of every (id of `ids1`, id of `ids2`) term pair in the phrase-pair store of
+ * `path` ("<field>" or "<field>.textindex[.phrase_pair_to_anchor]"), sorted, duplicates kept, in out->ids. */
+int32_t vgpu_phrase_pairs_to_anchor(vgpu_index* idx, const char* path, const uint32_t* ids1, uint32_t n1, const uint32_t* ids2, uint32_t n2, vgpu_hitlist* out);
+/* BoostAnchorFromPhraseResults (src/plan_creator/plan_steps.rs:260-277): `phrase_results[i].ids` are the anchors one phrase
+ * step produced, `group[i]` numbers the phrase (the (search1.terms[0], search2.terms[0]) pair) it belongs to; the results of
+ * one phrase are merged and deduplicated (:230-257), every phrase multiplies the hits it contains by 5.0
+ * (boost_hits_ids_vec_multi, src/search/boost.rs:149-195).  out->hits: the hits by ascending id. */
+int32_t vgpu_boost_anchor_from_phrase_results(vgpu_index* idx, const vgpu_hitlist* hits, const vgpu_hitlist* phrase_results, const uint32_t* group, uint32_t n, vgpu_hitlist* out);
+/* BoostToAnchor (src/plan_creator/plan_steps.rs:174-196): `part_json` is the search part, `in` its term hits (hits: the term
+ * ids of a tokenized field; ids: the text ids of an untokenized one), `boost_json` the RequestBoostPart on the part's own 1:n
+ * level.  out->hits = SearchFieldResult::boost_ids: (anchor, boost value) in value-id order. */
+int32_t vgpu_boost_to_anchor(vgpu_index* idx, const char* part_json, const vgpu_hitlist* in, const char* boost_json, vgpu_hitlist* out);
+/* ApplyAnchorBoost (src/plan_creator/plan_steps.rs:198-217) = apply_boost_values_anchor (src/search/boost.rs:255-281): `hits`
+ * by ascending anchor, `boost_ids->hits` the (anchor, value) list vgpu_boost_to_anchor returned for the same part.  out->hits:
+ * the hits with the boost function / expression of `boost_json` applied the way the reference's merge walk applies it. */
+int32_t vgpu_apply_anchor_boost(vgpu_index* idx, const char* boost_json, const vgpu_hitlist* hits, const vgpu_hitlist* boost_ids, vgpu_hitlist* out);
+/* boost_text_locality (src/search/boost.rs:34-87) of one field, reduced per anchor like boost_text_locality_all (:11-32):
+ * `term_hits[t].ids` = the token ids query term t matched in `path`; out->hits = (anchor, boost 2 c c) by ascending anchor for
+ * the texts reached by c > 1 of those tokens (the smallest boost per anchor, as the reference keeps it). */
+int32_t vgpu_text_locality(vgpu_index* idx, const char* path, const vgpu_hitlist* term_hits, uint32_t n_terms, vgpu_hitlist* out);
 /* get_facet (src/facet.rs:31-73): `facet_json` is one FacetRequest, `ids` the hit ids; groups come back through the
  * suggestion list type: text = the group's text, id = its value id, score = its count (exact below 2^24). */
 int32_t vgpu_facet(vgpu_index* idx, const char* facet_json, const uint32_t* ids, uint32_t n_ids, vgpu_suggestions* out);

@@ -1268,6 +1268,59 @@ static std::string call(const Persistence* p, const std::string& fn, const vjson
         apply_boost_values_anchor(r, b, hits_from_json(*a.get("boost_ids")));
         return hits_to_json(r.hits_scores);
     }
+    if (fn == "boost_text_locality") {  // boost.rs:11-87 for one field: terms = {"term": [token ids]}
+        std::string path = a.get("path")->str;
+        if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+        std::map<std::string, std::map<std::string, std::vector<uint32_t>>> in;
+        for (auto& kv : a.get("terms")->obj)
+            for (auto& x : kv.second.arr) in[path][kv.first].push_back((uint32_t)x.num);
+        return hits_to_json(boost_text_locality_all(*p, in));
+    }
+    if (fn == "boost_to_anchor") {  // the BoostToAnchor step, plan_steps.rs:174-196
+        SearchFieldResult r;
+        SearchPart part = vhost::parse_search_part(*a.get("part"));
+        if (auto* h = a.get("hits_scores")) r.hits_scores = hits_from_json(*h);
+        if (auto* h = a.get("hits_ids"))
+            for (auto& x : h->arr) r.hits_ids.push_back((uint32_t)x.num);
+        resolve_token_hits_to_text_id_ids_only(*p, part, r);
+        r = join_to_parent_ids(*p, r, part.path + ".textindex" + ".value_id_to_parent");
+        get_boost_ids_and_resolve_to_anchor(*p, vhost::parse_boost_part(*a.get("boost")).path, r);
+        return hits_to_json(r.boost_ids);
+    }
+    if (fn == "get_anchor_for_phrases_in_field") {  // search_field.rs:247-275
+        std::string path = a.get("path")->str;
+        if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+        if (!vfmt::ends_with(path, ".phrase_pair_to_anchor")) path += ".phrase_pair_to_anchor";
+        const vfmt::PhrasePairView& store = p->get_phrase_pair_to_anchor(path);
+        std::vector<uint32_t> out;
+        for (auto& t1 : a.get("ids1")->arr)
+            for (auto& t2 : a.get("ids2")->arr) store.get_values((uint32_t)t1.num, (uint32_t)t2.num, out);
+        std::sort(out.begin(), out.end());
+        return ids_to_json(out);
+    }
+    if (fn == "boost_anchor_from_phrase_results") {  // plan_steps.rs:230-277; boosts: [{"hits_ids": [...], "phrase": ["a", "b"]}]
+        SearchFieldResult r;
+        r.hits_scores = hits_from_json(*a.get("hits_scores"));
+        std::map<std::pair<std::string, std::string>, std::vector<std::vector<uint32_t>>> by_phrase;  // sort_unstable_by_key + group_by on the term pair
+        for (auto& e : a.get("boosts")->arr) {
+            std::vector<uint32_t> ids;
+            for (auto& x : e.get("hits_ids")->arr) ids.push_back((uint32_t)x.num);
+            by_phrase[{e.get("phrase")->arr[0].str, e.get("phrase")->arr[1].str}].push_back(std::move(ids));
+        }
+        std::vector<SearchFieldResult> boosts;
+        for (auto& kv : by_phrase) {
+            std::vector<uint32_t> merged;  // kmerge of the (sorted) lists, then dedup of neighbours
+            for (auto& l : kv.second) merged.insert(merged.end(), l.begin(), l.end());
+            std::stable_sort(merged.begin(), merged.end());
+            merged.erase(std::unique(merged.begin(), merged.end()), merged.end());
+            SearchFieldResult b;
+            b.hits_ids = std::move(merged);
+            b.request.boost = 5.0f;
+            boosts.push_back(std::move(b));
+        }
+        boost_hits_ids_vec_multi(r, boosts);
+        return hits_to_json(r.hits_scores);
+    }
     if (fn == "boost_hits_ids_vec_multi") {
         SearchFieldResult r;
         r.hits_scores = hits_from_json(*a.get("hits_scores"));

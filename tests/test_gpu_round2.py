@@ -585,3 +585,94 @@ def test_facets_with_many_groups(gpu, native_libs):
         assert len(got) == len(ref) and len(got) == (r["facets"][0]["top"] or len(ref))
         assert [(g[0], g[1]) for g in got] == [(x[0], x[1]) for x in ref], q
     assert len(b.result(0)["facets"]["tags[]"]) > 2500
+
+
+def test_boost_and_phrase_step_symbols(gpu, native_libs):
+    """The remaining PlanStep kinds as step entry points (plan_steps.rs:174-217, 260-293): BoostToAnchor, ApplyAnchorBoost,
+    PlanStepPhrasePairToAnchorId, BoostAnchorFromPhraseResults -- each against the oracle's restatement of the step, and chained
+    (FieldSearch -> ResolveTokenIdToAnchor / BoostToAnchor -> ApplyAnchorBoost) against the whole request."""
+    import ref_fixtures as fx
+
+    rng = np.random.default_rng(11)
+    syll = ["ka", "ki", "ku", "mi", "mo", "ra", "ri", "ru", "sa", "to"]
+    words = ["".join(rng.choice(syll, size=int(rng.integers(2, 4)))) for _ in range(120)]
+    docs = []
+    for i in range(1500):
+        n = int(rng.integers(0, 4))
+        d = {"ent_seq": str(i), "title": " ".join(str(w) for w in rng.choice(words[:25], size=4))}
+        if n:  # several boosted values per document: the position-dependent case of apply_boost_values_anchor
+            d["kana"] = [{"text": str(rng.choice(words)), **({"commonness": int(rng.integers(1, 900))} if rng.random() < 0.75 else {})} for _ in range(n)]
+        docs.append(d)
+    d = tempfile.mkdtemp(prefix="vb200_r2_steps_")
+    helpers.create_index(d, docs, {"kana[].text": {"fulltext": {"tokenize": True}}, "kana[].commonness": dict(fx.BOOST),
+                                   "title": {"features": ["Search", "PhraseBoost", "BoostTextLocality"], "fulltext": {"tokenize": True}}})
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    close = lambda a, b: abs(float(a) - float(b)) <= 1e-5 * max(abs(float(b)), 1e-30)
+    n_boosted = n_multi = 0
+    for term in [str(w) for w in rng.choice(words, size=10)] + ["mi", "ka", "ri"]:
+        part = {"terms": [term], "path": "kana[].text", "levenshtein_distance": 1, "starts_with": True}
+        term_hits, _ = index.field_search(part)
+        hits, _ = index.resolve_to_anchor(part, term_hits)
+        for fun in ("Log10", "Multiply", "Add"):
+            boost = {"path": "kana[].commonness", "boost_fun": fun, "param": 1}
+            # BoostToAnchor
+            got_ids = index.boost_to_anchor(part, boost, term_hits=term_hits)
+            ref_ids = oracle.call("boost_to_anchor", part=part, boost=boost, hits_scores=[[i, float(s)] for i, s in term_hits])
+            assert [g[0] for g in got_ids] == [r[0] for r in ref_ids], (term, fun)
+            assert all(float(g[1]) == float(np.float32(r[1])) for g, r in zip(got_ids, ref_ids))
+            # ApplyAnchorBoost
+            got = index.apply_anchor_boost(boost, hits, got_ids)
+            ref = oracle.call("apply_boost_values_anchor", hits_scores=[[i, float(s)] for i, s in hits], boost=boost, boost_ids=[[i, float(v)] for i, v in got_ids])
+            assert [g[0] for g in got] == [r[0] for r in ref], (term, fun)
+            assert all(close(g[1], r[1]) for g, r in zip(got, ref)), (term, fun)
+            n_boosted += len(got_ids)
+            n_multi += len(got_ids) - len({g[0] for g in got_ids})
+        # the chain equals the request with the boost on the part's own 1:n level
+        req = {"search_req": {"search": part}, "boost": [{"path": "kana[].commonness", "boost_fun": "Log10", "param": 1}], "top": 4000}
+        whole = oracle.search(json.dumps(req))
+        chained = index.apply_anchor_boost({"path": "kana[].commonness", "boost_fun": "Log10", "param": 1}, hits, index.boost_to_anchor(part, req["boost"][0], term_hits=term_hits))
+        by_id = {h[0]: h[1] for h in whole["data"]}
+        assert len(chained) == whole["num_hits"] and all(close(s, by_id[i]) for i, s in chained), term
+    assert n_boosted > 300 and n_multi > 20
+    assert index.apply_anchor_boost({"path": "kana[].commonness", "boost_fun": "Add"}, [(3, 1.0), (9, 2.0)], []) == [(3, np.float32(1.0)), (9, np.float32(2.0))]
+    with pytest.raises(gpu.VelociGpuError) as e:
+        index.apply_anchor_boost({"path": "kana[].commonness", "boost_fun": "Add"}, [(3, 1.0)], [(4, 2.0)])
+    assert e.value.status == 8
+
+    # PlanStepPhrasePairToAnchorId, BoostAnchorFromPhraseResults
+    n_pairs = 0
+    phrase_results, phrase_names = [], []
+    for w1, w2 in [(str(a), str(b)) for a, b in zip(rng.choice(words[:25], size=12), rng.choice(words[:25], size=12))]:
+        p1 = {"terms": [w1], "path": "title", "levenshtein_distance": 1}
+        p2 = {"terms": [w2], "path": "title", "levenshtein_distance": 1}
+        ids1 = [i for i, _ in index.field_search(p1)[0]]
+        ids2 = [i for i, _ in index.field_search(p2)[0]]
+        got = index.phrase_pairs_to_anchor("title", ids1, ids2)
+        assert got == oracle.call("get_anchor_for_phrases_in_field", path="title", ids1=ids1, ids2=ids2), (w1, w2)
+        n_pairs += len(got)
+        phrase_results.append(got), phrase_names.append([w1, w2])
+    assert n_pairs > 50
+    assert index.phrase_pairs_to_anchor("title.textindex", [], [1, 2]) == []
+    with pytest.raises(gpu.VelociGpuError) as e:
+        index.phrase_pairs_to_anchor("no_such_field", [1], [2])
+    assert e.value.status == 3
+    hits = [(int(i), float(np.float32(rng.random() * 9 + 0.5))) for i in sorted(rng.choice(1500, size=700, replace=False))]
+    names = sorted({tuple(n) for n in phrase_names})
+    groups = [names.index(tuple(n)) for n in phrase_names]
+    got = index.boost_anchor_from_phrase_results(hits, phrase_results, groups)
+    ref = oracle.call("boost_anchor_from_phrase_results", hits_scores=[[i, s] for i, s in hits], boosts=[{"hits_ids": r, "phrase": n} for r, n in zip(phrase_results, phrase_names)])
+    assert [g[0] for g in got] == [r[0] for r in ref] and all(close(g[1], r[1]) for g, r in zip(got, ref))
+    assert sum(1 for (i, s), g in zip(hits, got) if not close(g[1], s)) > 10  # some hits were boosted
+    # the same phrase twice is one boost (merged and deduplicated), two phrases hitting one anchor are two
+    twice = index.boost_anchor_from_phrase_results([(5, 2.0), (7, 1.0)], [[5], [5, 7], [5]], [0, 0, 1])
+    assert twice == [(5, np.float32(50.0)), (7, np.float32(5.0))]
+
+    # boost_text_locality as a step: the tokens several query terms matched in one text
+    n_loc = 0
+    for ws in ([words[0], words[1]], [words[2], words[3], words[4]], [words[5], words[5]], [words[6]], [words[7], words[8], words[9], words[10]]):
+        token_ids = [[i for i, _ in index.field_search({"terms": [str(w)], "path": "title", "levenshtein_distance": 1})[0]] for w in ws]
+        got = index.text_locality("title", token_ids)
+        ref = oracle.call("boost_text_locality", path="title", terms={"t%d" % k: ids for k, ids in enumerate(token_ids)})
+        assert [(g[0], float(g[1])) for g in got] == [(r[0], float(r[1])) for r in ref], ws
+        n_loc += len(got)
+    assert n_loc > 20

@@ -104,6 +104,11 @@ def load_library():
     L.vgpu_union_hits_ids.argtypes = [vp, P(_HitList), u32, P(_HitList)]
     L.vgpu_intersect_hits_ids.argtypes = [vp, P(_HitList), u32, P(_HitList)]
     L.vgpu_intersect_scores_with_ids.argtypes = [vp, P(_HitList), P(_HitList), P(_HitList)]
+    L.vgpu_phrase_pairs_to_anchor.argtypes = [vp, cp, P(ctypes.c_uint32), ctypes.c_uint32, P(ctypes.c_uint32), ctypes.c_uint32, P(_HitList)]
+    L.vgpu_boost_anchor_from_phrase_results.argtypes = [vp, P(_HitList), P(_HitList), P(ctypes.c_uint32), ctypes.c_uint32, P(_HitList)]
+    L.vgpu_boost_to_anchor.argtypes = [vp, cp, P(_HitList), cp, P(_HitList)]
+    L.vgpu_apply_anchor_boost.argtypes = [vp, cp, P(_HitList), P(_HitList), P(_HitList)]
+    L.vgpu_text_locality.argtypes = [vp, cp, P(_HitList), ctypes.c_uint32, P(_HitList)]
     L.vgpu_facet.argtypes = [vp, cp, P(u32), u32, P(_Suggestions)]
     L.vgpu_add_boost.argtypes = [vp, cp, P(_HitList)]
     L.vgpu_top_n.argtypes = [vp, P(_HitList), u32, u32, P(_HitList)]
@@ -589,6 +594,42 @@ class Index:
         inp = _to_hitlist(hits)
         _check(self.L.vgpu_add_boost(self.h, json.dumps(boost).encode("utf-8"), ctypes.byref(inp)))
         return [(inp.hits[i].id, np.float32(inp.hits[i].score)) for i in range(inp.n_hits)]
+
+    def phrase_pairs_to_anchor(self, path, ids1, ids2):
+        """PlanStepPhrasePairToAnchorId: sorted anchors of every (id1, id2) pair."""
+        a1, a2 = (ctypes.c_uint32 * max(1, len(ids1)))(*ids1), (ctypes.c_uint32 * max(1, len(ids2)))(*ids2)
+        out = _HitList()
+        _check(self.L.vgpu_phrase_pairs_to_anchor(self.h, path.encode("utf-8"), a1, len(ids1), a2, len(ids2), ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[1]
+
+    def boost_anchor_from_phrase_results(self, hits, phrase_results, groups):
+        """BoostAnchorFromPhraseResults: `phrase_results` id lists, `groups` the phrase each belongs to."""
+        inp, out = _to_hitlist(hits), _HitList()
+        keep = [_to_hitlist([], ids) for ids in phrase_results]
+        arr = (_HitList * max(1, len(keep)))(*keep)
+        g = (ctypes.c_uint32 * max(1, len(groups)))(*groups)
+        _check(self.L.vgpu_boost_anchor_from_phrase_results(self.h, ctypes.byref(inp), arr, g, len(keep), ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[0]
+
+    def boost_to_anchor(self, part, boost, term_hits=None, text_ids=None):
+        """BoostToAnchor: (anchor, boost value) pairs in value-id order."""
+        inp, out = _to_hitlist(term_hits, text_ids), _HitList()
+        _check(self.L.vgpu_boost_to_anchor(self.h, json.dumps(part, ensure_ascii=False).encode("utf-8"), ctypes.byref(inp), json.dumps(boost).encode("utf-8"), ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[0]
+
+    def apply_anchor_boost(self, boost, hits, boost_ids):
+        """ApplyAnchorBoost: `hits` with the boost values of `boost_ids` applied."""
+        inp, vals, out = _to_hitlist(hits), _to_hitlist(boost_ids), _HitList()
+        _check(self.L.vgpu_apply_anchor_boost(self.h, json.dumps(boost).encode("utf-8"), ctypes.byref(inp), ctypes.byref(vals), ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[0]
+
+    def text_locality(self, path, term_token_ids):
+        """boost_text_locality: `term_token_ids` = per query term the token ids it matched -> [(anchor, boost)]."""
+        keep = [_to_hitlist([], ids) for ids in term_token_ids]
+        arr = (_HitList * max(1, len(keep)))(*keep)
+        out = _HitList()
+        _check(self.L.vgpu_text_locality(self.h, path.encode("utf-8"), arr, len(keep), ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[0]
 
     def top_n(self, hits, top, skip=0):
         inp, out = _to_hitlist(hits), _HitList()

@@ -666,6 +666,79 @@ __global__ void __launch_bounds__(128) phrase_pairs_kernel(const PhraseMember* _
     }
 }
 
+// The phrase-pair step on its own (PlanStepPhrasePairToAnchorId, plan_steps.rs:279-293): every pair of the two term id lists.
+__global__ void __launch_bounds__(128) phrase_lookup_kernel(PhraseView store, const uint32_t* __restrict__ ids1, uint32_t n1, const uint32_t* __restrict__ ids2, uint32_t n2,
+                                                            uint32_t* __restrict__ pair_count, const uint32_t* __restrict__ pair_off, uint32_t* __restrict__ out) {
+    const unsigned long long pairs = (unsigned long long)n1 * n2;
+    for (unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < pairs; x += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint64_t key = ((uint64_t)ids1[(uint32_t)(x / n2)] << 32) | ids2[(uint32_t)(x % n2)];
+        uint32_t lo = 0, hi = store.n;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (store.keys[mid] < key) lo = mid + 1;
+            else hi = mid;
+        }
+        const bool found = lo < store.n && store.keys[lo] == key;
+        const uint32_t begin = found ? store.off[lo] : 0u, n = found ? store.off[lo + 1] - begin : 0u;
+        if (out == nullptr) {
+            pair_count[x] = n;
+        } else {
+            for (uint32_t i = 0; i < n; ++i) out[pair_off[x] + i] = store.anchors[begin + i];
+        }
+    }
+}
+
+void launch_phrase_lookup(cudaStream_t st, const PhraseView& store, const uint32_t* ids1, uint32_t n1, const uint32_t* ids2, uint32_t n2, uint32_t* pair_count, const uint32_t* pair_off,
+                          uint32_t* out) {
+    const unsigned long long pairs = (unsigned long long)n1 * n2;
+    if (pairs == 0) return;
+    const unsigned blocks = (unsigned)std::min<unsigned long long>((pairs + 127) / 128, 65535ull);
+    phrase_lookup_kernel<<<blocks, 128, 0, st>>>(store, ids1, n1, ids2, n2, pair_count, pair_off, out);
+    count_launch();
+}
+
+// BoostToAnchor on its own (plan_steps.rs:174-196): the joins run one store at a time over explicit id lists.
+__global__ void __launch_bounds__(128) csr_expand_kernel(CsrView store, const uint32_t* __restrict__ ids, uint32_t n, uint32_t self_if_empty, uint32_t* __restrict__ count,
+                                                         const uint32_t* __restrict__ off, uint32_t* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t id = ids[i];
+        uint32_t b = 0, e = 0;
+        if (id < store.n_ids) b = store.off[id], e = store.off[id + 1];
+        const bool self = e == b && self_if_empty;  // a token without an entry is its own text id (search_field.rs:676-678)
+        if (out == nullptr) {
+            count[i] = self ? 1u : e - b;
+        } else if (self) {
+            out[off[i]] = id;
+        } else {
+            for (uint32_t k = b; k < e; ++k) out[off[i] + (k - b)] = store.val[k];
+        }
+    }
+}
+
+void launch_csr_expand(cudaStream_t st, const CsrView& store, const uint32_t* ids, uint32_t n, uint32_t self_if_empty, uint32_t* count, const uint32_t* off, uint32_t* out) {
+    if (!n) return;
+    csr_expand_kernel<<<std::min<unsigned>((n + 127) / 128, 65535u), 128, 0, st>>>(store, ids, n, self_if_empty, count, off, out);
+    count_launch();
+}
+
+__global__ void __launch_bounds__(128) boost_values_kernel(const uint32_t* __restrict__ column, uint32_t column_n, CsrView v2a, const uint32_t* __restrict__ value_ids, uint32_t n,
+                                                           uint32_t* __restrict__ out_anchor, uint32_t* __restrict__ out_bits) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t v = value_ids[i];
+        uint32_t anchor = kNoValue, bits = kNoValue;
+        if (v < column_n) bits = column[v];
+        if (bits != kNoValue && v < v2a.n_ids && v2a.off[v + 1] > v2a.off[v]) anchor = v2a.val[v2a.off[v]];
+        out_anchor[i] = anchor, out_bits[i] = bits;
+    }
+}
+
+void launch_boost_values(cudaStream_t st, const uint32_t* column, uint32_t column_n, const CsrView& value_id_to_anchor, const uint32_t* value_ids, uint32_t n, uint32_t* out_anchor,
+                         uint32_t* out_bits) {
+    if (!n) return;
+    boost_values_kernel<<<std::min<unsigned>((n + 127) / 128, 65535u), 128, 0, st>>>(column, column_n, value_id_to_anchor, value_ids, n, out_anchor, out_bits);
+    count_launch();
+}
+
 // One block per member: the matched term ids of the part, as text ids, to their anchors.
 __global__ void __launch_bounds__(128) ids_to_anchor_kernel(const IdsMember* __restrict__ members, ListArgs a) {
     const IdsMember m = members[blockIdx.x];

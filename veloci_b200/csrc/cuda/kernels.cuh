@@ -31,6 +31,16 @@ struct PerDeviceOnce {
 void launch_fuzzy_match(cudaStream_t st, const DictView& dict, const PartQuery* parts, const uint32_t* part_ids, uint32_t n_parts, uint32_t max_m, MatchRecord* out,
                         uint32_t capacity, unsigned long long* counter);
 // one launch per dictionary: grid.y = the regex parts on it, one thread per dictionary term
+// get_anchor_for_phrases_in_field (search_field.rs:263-275) over explicit term id lists: thread x takes the pair
+// (ids1[x / n2], ids2[x % n2]); `out` == nullptr counts the pair's anchors into pair_count[x], else copies them to out + pair_off[x]
+void launch_phrase_lookup(cudaStream_t st, const PhraseView& store, const uint32_t* ids1, uint32_t n1, const uint32_t* ids2, uint32_t n2, uint32_t* pair_count, const uint32_t* pair_off,
+                          uint32_t* out);
+// One step of BoostToAnchor (plan_steps.rs:174-196) over explicit id lists: the values of every id in `store` (the id itself
+// when it has none and `self_if_empty`); `out` == nullptr counts into count[i], else copies to out + off[i].
+void launch_csr_expand(cudaStream_t st, const CsrView& store, const uint32_t* ids, uint32_t n, uint32_t self_if_empty, uint32_t* count, const uint32_t* off, uint32_t* out);
+// get_boost_ids_and_resolve_to_anchor (boost.rs:432-468): per value id its boost value bits and (first) anchor, kNoValue anchor when it has no value
+void launch_boost_values(cudaStream_t st, const uint32_t* column, uint32_t column_n, const CsrView& value_id_to_anchor, const uint32_t* value_ids, uint32_t n, uint32_t* out_anchor,
+                         uint32_t* out_bits);
 void launch_regex_match(cudaStream_t st, const DictView& dict, const RegexPartDev* parts, uint32_t n_parts, MatchRecord* out, uint32_t capacity, unsigned long long* counter);
 // Deletion-neighbourhood index build: pass 0 counts the variants per hash bucket, pass 1 (after an exclusive scan of
 // the counts into `off`, cursor zeroed) files the terms.

@@ -373,7 +373,9 @@ __device__ __noinline__ float apply_leaf_boost(const LeafBoostGlobals* gp, LeafB
     if (open_at_tile_start) {  // ... and across the tile start from the part's postings of the tiles before (bucket + offset rows)
         const uint32_t tile_base = x.anchor - x.idx;
         const PartSlices ps = a.slices[x.part];
-        const PostingsView pv = a.postings[a.parts[x.part].postings];
+        PostingsView pv;
+        pv.post = nullptr, pv.off = nullptr, pv.n_terms = 0, pv.term_plane = nullptr;
+        if (ps.n_dense) pv = a.postings[a.parts[x.part].postings];  // (explicit hit lists of the step seam have no posting store)
         const uint32_t* prow = a.bucket + (size_t)ps.sparse_row * (a.n_tiles + 1);
         const SparseEntry* pent = a.sparse + ps.sparse_base;
         uint32_t cur = tile_base;

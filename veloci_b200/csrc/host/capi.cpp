@@ -558,6 +558,31 @@ int32_t vgpu_intersect_scores_with_ids(vgpu_index* idx, const vgpu_hitlist* scor
     return guarded([&]() { vsteps::intersect_scores_with_ids(*idx->ix, *scores, *ids, *out); });
 }
 static void fill_suggestions(const std::vector<vsteps::Suggestion>& v, vgpu_suggestions* out);
+int32_t vgpu_phrase_pairs_to_anchor(vgpu_index* idx, const char* path, const uint32_t* ids1, uint32_t n1, const uint32_t* ids2, uint32_t n2, vgpu_hitlist* out) {
+    if (!idx || !path || !out || (n1 && !ids1) || (n2 && !ids2)) return VGPU_ERR_INVALID_REQUEST;
+    memset(out, 0, sizeof *out);
+    return guarded([&]() { vsteps::phrase_pairs_to_anchor(*idx->ix, path, ids1, n1, ids2, n2, *out); });
+}
+int32_t vgpu_boost_anchor_from_phrase_results(vgpu_index* idx, const vgpu_hitlist* hits, const vgpu_hitlist* phrase_results, const uint32_t* group, uint32_t n, vgpu_hitlist* out) {
+    if (!idx || !hits || !out || (n && (!phrase_results || !group))) return VGPU_ERR_INVALID_REQUEST;
+    memset(out, 0, sizeof *out);
+    return guarded([&]() { vsteps::boost_anchor_from_phrase_results(*idx->ix, *hits, phrase_results, group, n, *out); });
+}
+int32_t vgpu_boost_to_anchor(vgpu_index* idx, const char* part_json, const vgpu_hitlist* in, const char* boost_json, vgpu_hitlist* out) {
+    if (!idx || !part_json || !in || !boost_json || !out) return VGPU_ERR_INVALID_REQUEST;
+    memset(out, 0, sizeof *out);
+    return guarded([&]() { vsteps::boost_to_anchor(*idx->ix, part_json, *in, boost_json, *out); });
+}
+int32_t vgpu_apply_anchor_boost(vgpu_index* idx, const char* boost_json, const vgpu_hitlist* hits, const vgpu_hitlist* boost_ids, vgpu_hitlist* out) {
+    if (!idx || !boost_json || !hits || !boost_ids || !out) return VGPU_ERR_INVALID_REQUEST;
+    memset(out, 0, sizeof *out);
+    return guarded([&]() { vsteps::apply_anchor_boost(*idx->ix, boost_json, *hits, *boost_ids, *out); });
+}
+int32_t vgpu_text_locality(vgpu_index* idx, const char* path, const vgpu_hitlist* term_hits, uint32_t n_terms, vgpu_hitlist* out) {
+    if (!idx || !path || !out || (n_terms && !term_hits)) return VGPU_ERR_INVALID_REQUEST;
+    memset(out, 0, sizeof *out);
+    return guarded([&]() { vsteps::text_locality(*idx->ix, path, term_hits, n_terms, *out); });
+}
 int32_t vgpu_facet(vgpu_index* idx, const char* facet_json, const uint32_t* ids, uint32_t n_ids, vgpu_suggestions* out) {
     if (!idx || !facet_json || !out || (n_ids && !ids)) return VGPU_ERR_INVALID_REQUEST;
     memset(out, 0, sizeof *out);

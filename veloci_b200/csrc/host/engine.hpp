@@ -28,6 +28,8 @@ struct vgpu_hit_pod {  // same layout as vgpu_hit
 struct ExplicitList {  // a caller-provided hit list used as a leaf (step seam)
     std::vector<uint32_t> anchors;
     std::vector<float> scores;
+    std::vector<uint32_t> raw_keys;  // when given: the entries' keys as they are (a 1:n boost list: 0x7FFFFFFF - value id) instead of score keys
+    uint32_t part_flags = 0;         // PartFlags of the leaf's part (kPartList | kPartListBoost for such a list)
 };
 
 static const int kPhases = 6;
@@ -339,8 +341,9 @@ struct Batch {
     }
 
     // one request over explicit hit lists (union / intersect / add_boost / top_n step entry points)
+    // `post`: post ops over the leaves (kPostMulIfPresent / kPostMulValue), applied to the root's score after the boost steps
     void prepare_lists(DeviceIndex* index, const std::vector<ExplicitList>& lists, const std::vector<uint32_t>& code, const std::vector<BoostStep>& boost_steps, uint32_t k, bool all_hits,
-                       const vhost::FacetRequest* facet = nullptr) {
+                       const vhost::FacetRequest* facet = nullptr, const std::vector<uint32_t>& post = {}) {
         ix = index;
         plan.ix = ix;
         mode = kLists;
@@ -351,9 +354,16 @@ struct Batch {
         for (auto& l : lists)
             for (float sc : l.scores)
                 if (!(sc >= 0.0f)) qp.nonneg = 0;
-        const bool trivial = lists.size() == 1 && code.size() == 2 && !facet;  // (facets are counted on the program path)
+        for (size_t pc = 0; pc < code.size();) {  // (the 1:n boost ops of the program: the tile kernel keeps hit bitmaps for them)
+            const uint32_t op = code[pc];
+            if (op == kOpLeafBoost) ++qp.n_leaf_boosts;
+            pc += op == kOpLeaf ? 2 : op == kOpUnion ? 3 + code[pc + 1] : op == kOpFilter ? 1 : op == kOpLeafBoost ? 4 : 2 + 2 * code[pc + 1];
+        }
+        const bool trivial = lists.size() == 1 && code.size() == 2 && !facet && post.empty();  // (facets and post ops run on the program path)
         qp.prog_begin = 0, qp.prog_len = trivial ? 0u : (uint32_t)code.size();
         if (!trivial) plan.prog = code;
+        qp.post_begin = (uint32_t)plan.prog.size(), qp.post_len = (uint32_t)post.size();
+        plan.prog.insert(plan.prog.end(), post.begin(), post.end());
         qp.boost_begin = 0, qp.n_boosts = (uint32_t)boost_steps.size();
         plan.boosts = boost_steps;
         vplan::BatchPlan::set_fast_boost(qp, boost_steps);
@@ -362,6 +372,7 @@ struct Batch {
             PartQuery pq;
             memset(&pq, 0, sizeof pq);
             pq.postings = kNoValue;
+            pq.flags = lists[i].part_flags;
             plan.parts.push_back(pq);
             plan.part_dict.push_back(0);
             plan.leaf_part.push_back((uint32_t)i);
@@ -388,7 +399,7 @@ struct Batch {
             const ExplicitList& l = lists[i];
             std::vector<std::pair<uint32_t, uint32_t>> entries;  // dedup keeps the max like resolve_token_to_anchor; inputs are normally unique
             for (size_t j = 0; j < l.anchors.size(); ++j)
-                if (l.anchors[j] >= ix->anchor_lo && l.anchors[j] < ix->anchor_hi) entries.emplace_back(l.anchors[j], vbit::score_key(l.scores[j]));
+                if (l.anchors[j] >= ix->anchor_lo && l.anchors[j] < ix->anchor_hi) entries.emplace_back(l.anchors[j], l.raw_keys.empty() ? vbit::score_key(l.scores[j]) : l.raw_keys[j]);
             std::stable_sort(entries.begin(), entries.end(), [](auto& a, auto& b) { return a.first < b.first; });
             uint32_t* row = &bucket[i * (n_tiles + 1)];
             for (auto& e : entries) row[((e.first - (uint32_t)ix->anchor_lo) >> tile_log2) + 1]++;

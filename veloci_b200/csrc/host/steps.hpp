@@ -188,10 +188,10 @@ inline std::vector<Suggestion> suggest(vdev::DeviceIndex& ix, const vhost::Reque
 
 // The remaining step entry points run a one-request batch whose leaves are explicit hit lists.
 inline void run_lists(vdev::DeviceIndex& ix, const std::vector<vdev::ExplicitList>& lists, const std::vector<uint32_t>& code, const std::vector<vdev::BoostStep>& boosts, uint32_t k,
-                      bool all_hits, vgpu_hitlist& out) {
+                      bool all_hits, vgpu_hitlist& out, const std::vector<uint32_t>& post = {}) {
     memset(&out, 0, sizeof out);
     vdev::Batch b;
-    b.prepare_lists(&ix, lists, code, boosts, k, all_hits);
+    b.prepare_lists(&ix, lists, code, boosts, k, all_hits, nullptr, post);
     b.execute();
     std::vector<vgpu_hit> hits;
     b.download_hits(0, all_hits, hits);
@@ -394,6 +394,250 @@ inline std::vector<FacetGroup> facet(vdev::DeviceIndex& ix, const char* facet_js
     std::vector<std::vector<FacetGroups>> groups;
     materialize_facets(b, groups);
     return groups.at(0).at(0).groups;
+}
+
+// PlanStepPhrasePairToAnchorId (plan_steps.rs:279-293) = get_anchor_for_phrases_in_field (search_field.rs:263-275): the anchors
+// of every (term id of the first part, term id of the second part) pair of the field's phrase-pair store, concatenated and
+// sorted (duplicates stay).  The lookups and the gather run on the device; the final sort of the (small) list is host work.
+inline void phrase_pairs_to_anchor(vdev::DeviceIndex& ix, const char* path_c, const uint32_t* ids1, uint32_t n1, const uint32_t* ids2, uint32_t n2, vgpu_hitlist& out) {
+    std::string path = path_c;
+    if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+    if (!vfmt::ends_with(path, ".phrase_pair_to_anchor")) path += ".phrase_pair_to_anchor";
+    auto it = ix.phrases.find(path);
+    if (it == ix.phrases.end()) ix.host->path_not_found(path);
+    std::vector<uint32_t> anchors;
+    const uint64_t pairs = (uint64_t)n1 * n2;
+    if (pairs > (1ull << 26)) throw vplan::Unsupported("more than 2^26 term pairs in one phrase step");
+    if (pairs) {
+        VDEV_CUDA(cudaSetDevice(ix.device));
+        vdev::DevBuf<uint32_t> d1, d2, d_count, d_off, d_out;
+        d1.upload(std::vector<uint32_t>(ids1, ids1 + n1)), d2.upload(std::vector<uint32_t>(ids2, ids2 + n2));
+        d_count.alloc((size_t)pairs);
+        const vdev::PhraseView store = it->second.view();
+        vdev::launch_phrase_lookup(cudaStreamLegacy, store, d1.p, n1, d2.p, n2, d_count.p, nullptr, nullptr);
+        std::vector<uint32_t> count((size_t)pairs), off((size_t)pairs);
+        VDEV_CUDA(cudaMemcpy(count.data(), d_count.p, (size_t)pairs * 4, cudaMemcpyDeviceToHost));
+        uint64_t total = 0;
+        for (size_t x = 0; x < count.size(); ++x) off[x] = (uint32_t)total, total += count[x];
+        if (total > 0xFFFFFFF0ull) throw vplan::Unsupported("more than 2^32 anchors in one phrase step");
+        if (total) {
+            d_off.upload(off);
+            d_out.alloc((size_t)total);
+            vdev::launch_phrase_lookup(cudaStreamLegacy, store, d1.p, n1, d2.p, n2, nullptr, d_off.p, d_out.p);
+            anchors.resize((size_t)total);
+            VDEV_CUDA(cudaMemcpy(anchors.data(), d_out.p, (size_t)total * 4, cudaMemcpyDeviceToHost));
+        }
+        VDEV_CUDA(cudaGetLastError());
+        std::sort(anchors.begin(), anchors.end());
+    }
+    ids_out(anchors, out);
+}
+
+// BoostAnchorFromPhraseResults (plan_steps.rs:260-277): the phrase results of one phrase (same `group`) are merged into one id
+// set (kmerge + dedup, sort_and_group_boosts_by_phrase_terms :230-257), every set boosts the hits it contains by 5.0
+// (boost_hits_ids_vec_multi, boost.rs:149-195: a hit in two sets is multiplied twice); the hits come back by ascending id.
+inline void boost_anchor_from_phrase_results(vdev::DeviceIndex& ix, const vgpu_hitlist& hits, const vgpu_hitlist* phrase_results, const uint32_t* group, uint32_t n, vgpu_hitlist& out) {
+    std::vector<uint32_t> groups(group, group + n);
+    std::sort(groups.begin(), groups.end());
+    groups.erase(std::unique(groups.begin(), groups.end()), groups.end());
+    if (groups.size() + 1 > vdev::kMaxLeaves) throw vplan::Unsupported("more than " + std::to_string(vdev::kMaxLeaves - 1) + " phrases in one boost step");
+    std::vector<vdev::ExplicitList> lists = to_lists(&hits, 1);
+    std::vector<uint32_t> post;
+    const float boost = 5.0f;  // plan_steps.rs:270
+    uint32_t boost_bits;
+    memcpy(&boost_bits, &boost, 4);
+    for (uint32_t g : groups) {
+        std::vector<uint32_t> ids;
+        for (uint32_t i = 0; i < n; ++i)
+            if (group[i] == g) ids.insert(ids.end(), phrase_results[i].ids, phrase_results[i].ids + phrase_results[i].n_ids);
+        std::sort(ids.begin(), ids.end());
+        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        vdev::ExplicitList l;
+        l.anchors = std::move(ids);
+        l.scores.assign(l.anchors.size(), 1.0f);
+        post.push_back(vdev::kPostMulIfPresent), post.push_back((uint32_t)lists.size()), post.push_back(boost_bits);
+        lists.push_back(std::move(l));
+    }
+    run_lists(ix, lists, {vdev::kOpLeaf, 0u}, {}, 0, true, out, post);
+}
+
+// The values of every id in a CSR store, by two launches of csr_expand_kernel (count, then fill); out[off[i] .. off[i + 1])
+// belong to ids[i].  Step-seam helper: small lists, legacy stream, synchronous copies.
+inline std::vector<uint32_t> expand_on_device(vdev::DeviceIndex& ix, const vdev::CsrDev& csr, const std::vector<uint32_t>& ids, bool self_if_empty, std::vector<uint32_t>* off_out = nullptr) {
+    std::vector<uint32_t> result, off(ids.size() + 1, 0);
+    if (!ids.empty()) {
+        if (ids.size() > 0x7FFFFFFFull) throw vplan::Unsupported("too many ids in one step");
+        VDEV_CUDA(cudaSetDevice(ix.device));
+        const uint32_t n = (uint32_t)ids.size();
+        vdev::DevBuf<uint32_t> d_ids, d_count, d_off, d_out;
+        d_ids.upload(ids);
+        d_count.alloc(n);
+        vdev::launch_csr_expand(cudaStreamLegacy, csr.view(), d_ids.p, n, self_if_empty ? 1u : 0u, d_count.p, nullptr, nullptr);
+        std::vector<uint32_t> count(n);
+        VDEV_CUDA(cudaMemcpy(count.data(), d_count.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < n; ++i) off[i] = (uint32_t)total, total += count[i];
+        if (total > 0xFFFFFFF0ull) throw vplan::Unsupported("more than 2^32 values in one step");
+        off[n] = (uint32_t)total;
+        if (total) {
+            d_off.upload(off);
+            d_out.alloc((size_t)total);
+            vdev::launch_csr_expand(cudaStreamLegacy, csr.view(), d_ids.p, n, self_if_empty ? 1u : 0u, nullptr, d_off.p, d_out.p);
+            result.resize((size_t)total);
+            VDEV_CUDA(cudaMemcpy(result.data(), d_out.p, (size_t)total * 4, cudaMemcpyDeviceToHost));
+        }
+        VDEV_CUDA(cudaGetLastError());
+    }
+    if (off_out) *off_out = std::move(off);
+    return result;
+}
+
+// boost_text_locality (boost.rs:34-87) of one field, reduced like boost_text_locality_all (boost.rs:11-32): `term_hits[t].ids`
+// are the token ids query term t matched in the field.  Every token's text ids (tokens_to_text_id), all terms together; a
+// text reached c > 1 times boosts its anchors by 2 c c; an anchor reached through several texts keeps the SMALLEST boost
+// (the reference's max_by has its comparator reversed).  out->hits: (anchor, boost) by ascending anchor.  Nothing for a
+// single term.
+inline void text_locality(vdev::DeviceIndex& ix, const char* path_c, const vgpu_hitlist* term_hits, uint32_t n_terms, vgpu_hitlist& out) {
+    std::string path = path_c;
+    if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+    std::vector<vgpu_hit> boosts;
+    if (n_terms > 1) {
+        auto store = [&](const std::string& p) -> const vdev::CsrDev& {
+            auto it = ix.stores.find(p);
+            if (it == ix.stores.end()) ix.host->path_not_found(p);
+            return it->second;
+        };
+        std::vector<uint32_t> tokens;
+        for (uint32_t t = 0; t < n_terms; ++t) tokens.insert(tokens.end(), term_hits[t].ids, term_hits[t].ids + term_hits[t].n_ids);
+        std::vector<uint32_t> texts = expand_on_device(ix, store(path + ".tokens_to_text_id"), tokens, false);
+        std::sort(texts.begin(), texts.end());
+        std::vector<uint32_t> boosted_texts;
+        std::vector<float> boost_of;
+        for (size_t i = 0; i < texts.size();) {
+            size_t j = i;
+            while (j < texts.size() && texts[j] == texts[i]) ++j;
+            if (j - i > 1) boosted_texts.push_back(texts[i]), boost_of.push_back(2.0f * (float)(j - i) * (float)(j - i));
+            i = j;
+        }
+        if (ix.host->is_anchor_identity_column(path)) {
+            for (size_t i = 0; i < boosted_texts.size(); ++i) boosts.push_back(vgpu_hit{boosted_texts[i], boost_of[i]});
+        } else {
+            std::vector<uint32_t> off;
+            const std::vector<uint32_t> anchors = expand_on_device(ix, store(path + ".text_id_to_anchor"), boosted_texts, false, &off);
+            for (size_t i = 0; i < boosted_texts.size(); ++i)
+                for (uint32_t k = off[i]; k < off[i + 1]; ++k) boosts.push_back(vgpu_hit{anchors[k], boost_of[i]});
+        }
+        std::sort(boosts.begin(), boosts.end(), [](const vgpu_hit& a, const vgpu_hit& b) { return a.id != b.id ? a.id < b.id : a.score < b.score; });
+        boosts.erase(std::unique(boosts.begin(), boosts.end(), [](const vgpu_hit& a, const vgpu_hit& b) { return a.id == b.id; }), boosts.end());  // the smallest per anchor
+    }
+    memset(&out, 0, sizeof out);
+    out.hits = dup_array(boosts), out.n_hits = (uint32_t)boosts.size();
+    out.ids = dup_array(std::vector<uint32_t>()), out.n_ids = 0;
+}
+
+inline vhost::BoostPart parse_boost(const char* boost_json) {
+    vjson::Value v;
+    try {
+        v = vjson::parse(boost_json, strlen(boost_json));
+    } catch (const vjson::ParseError& e) {
+        throw vhost::RequestError(e.what());
+    }
+    return vhost::parse_boost_part(v);
+}
+
+// BoostToAnchor (plan_steps.rs:174-196): the part's term hits -> text ids (resolve_token_hits_to_text_id_ids_only,
+// search_field.rs:640-687: tokenized fields only; untokenized ones pass the hits_ids through) -> the value ids those texts
+// belong to (join_to_parent_ids, search.rs:281-315) -> the ones with a boost value, as (anchor, value) in value-id order
+// (get_boost_ids_and_resolve_to_anchor, boost.rs:432-468).  Every join and the value lookup is a kernel over the id list;
+// the sort + dedup between them is host work on the (small) lists.  out->hits = boost_ids.
+inline void boost_to_anchor(vdev::DeviceIndex& ix, const char* part_json, const vgpu_hitlist& in, const char* boost_json, vgpu_hitlist& out) {
+    const vhost::SearchPart part = parse_part(part_json);
+    const vhost::BoostPart boost = parse_boost(boost_json);
+    std::string path = part.path;
+    if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+    auto store = [&](const std::string& p) -> const vdev::CsrDev& {
+        auto it = ix.stores.find(p);
+        if (it == ix.stores.end()) ix.host->path_not_found(p);
+        return it->second;
+    };
+    VDEV_CUDA(cudaSetDevice(ix.device));
+    auto expand = [&](const vdev::CsrDev& csr, const std::vector<uint32_t>& ids, bool self_if_empty) {
+        std::vector<uint32_t> result = expand_on_device(ix, csr, ids, self_if_empty);
+        std::sort(result.begin(), result.end());
+        result.erase(std::unique(result.begin(), result.end()), result.end());
+        return result;
+    };
+    std::vector<uint32_t> text_ids;
+    if (ix.host->is_tokenized(path)) {
+        std::vector<uint32_t> tokens;
+        for (uint32_t i = 0; i < in.n_hits; ++i) tokens.push_back(in.hits[i].id);
+        text_ids = expand(store(path + ".tokens_to_text_id"), tokens, true);
+    } else {
+        text_ids.assign(in.ids, in.ids + in.n_ids);
+    }
+    std::vector<uint32_t> value_ids = expand(store(path + ".value_id_to_parent"), text_ids, false);
+    auto col = ix.boosts.find(boost.path + ".boost_valid_to_value");
+    if (col == ix.boosts.end()) ix.host->path_not_found(boost.path + ".boost_valid_to_value");
+    const vdev::CsrDev& v2a = store(boost.path + ".value_id_to_anchor");
+    std::vector<vgpu_hit> pairs;
+    if (!value_ids.empty()) {
+        const uint32_t n = (uint32_t)value_ids.size();
+        vdev::DevBuf<uint32_t> d_ids, d_anchor, d_bits;
+        d_ids.upload(value_ids);
+        d_anchor.alloc(n), d_bits.alloc(n);
+        vdev::launch_boost_values(cudaStreamLegacy, col->second.bits.p, (uint32_t)col->second.n, v2a.view(), d_ids.p, n, d_anchor.p, d_bits.p);
+        std::vector<uint32_t> anchor(n), bits(n);
+        VDEV_CUDA(cudaMemcpy(anchor.data(), d_anchor.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        VDEV_CUDA(cudaMemcpy(bits.data(), d_bits.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < n; ++i) {
+            if (anchor[i] == vdev::kNoValue) continue;
+            float v;
+            memcpy(&v, &bits[i], 4);
+            pairs.push_back(vgpu_hit{anchor[i], v});
+        }
+    }
+    VDEV_CUDA(cudaGetLastError());
+    memset(&out, 0, sizeof out);
+    out.hits = dup_array(pairs), out.n_hits = (uint32_t)pairs.size();
+    out.ids = dup_array(std::vector<uint32_t>()), out.n_ids = 0;
+}
+
+// ApplyAnchorBoost (plan_steps.rs:198-217) = apply_boost_values_anchor (boost.rs:255-281): the hits of a part (ascending
+// anchors) and the (anchor, value) list BoostToAnchor made for the same part (ascending anchors, an anchor may have several
+// values).  The reference's merge walk makes the number of values a hit takes depend on the run of boosted hits before it;
+// the tile kernel's kOpLeafBoost reproduces that (apply_leaf_boost, tiles.cu).  The values are given, not looked up: they
+// travel as a temporary column indexed by their position in the list.  out->hits: the hits by ascending anchor.
+inline void apply_anchor_boost(vdev::DeviceIndex& ix, const char* boost_json, const vgpu_hitlist& hits, const vgpu_hitlist& boost_ids, vgpu_hitlist& out) {
+    const vhost::BoostPart boost = parse_boost(boost_json);
+    std::vector<vdev::ExplicitList> lists = to_lists(&hits, 1);
+    if (boost_ids.n_hits == 0) return run_lists(ix, lists, {vdev::kOpLeaf, 0u}, {}, 0, true, out);
+    if (boost_ids.n_hits >= 0x7FFFFFF0u) throw vplan::Unsupported("too many boost values in one ApplyAnchorBoost step");
+    std::vector<uint32_t> sorted_hits = lists[0].anchors;
+    std::sort(sorted_hits.begin(), sorted_hits.end());
+    vdev::ExplicitList values;
+    values.part_flags = vdev::kPartList | vdev::kPartListBoost;
+    std::vector<uint32_t> column(boost_ids.n_hits);
+    for (uint32_t i = 0; i < boost_ids.n_hits; ++i) {
+        if (i && boost_ids.hits[i].id < boost_ids.hits[i - 1].id) throw vplan::Unsupported("ApplyAnchorBoost: the boost values must come by ascending anchor (as BoostToAnchor returns them)");
+        if (!std::binary_search(sorted_hits.begin(), sorted_hits.end(), boost_ids.hits[i].id))
+            throw vplan::Unsupported("ApplyAnchorBoost: a boost value for an anchor that is not among the hits (BoostToAnchor of the same part never returns one)");
+        values.anchors.push_back(boost_ids.hits[i].id);
+        values.scores.push_back(1.0f);
+        values.raw_keys.push_back(0x7FFFFFFFu - i);
+        memcpy(&column[i], &boost_ids.hits[i].score, 4);
+    }
+    lists.push_back(std::move(values));
+    VDEV_CUDA(cudaSetDevice(ix.device));
+    vdev::DevBuf<uint32_t> d_column;
+    d_column.upload(column);
+    vdev::BoostStep step;
+    memset(&step, 0, sizeof step);
+    step.column = d_column.p, step.n = (uint32_t)column.size();
+    step.fun = (uint32_t)boost.boost_fun;
+    step.param = boost.param.value_or(0.0f);
+    step.list_only = 1;
+    if (boost.expression) vplan::parse_expression(*boost.expression, step);
+    run_lists(ix, lists, {vdev::kOpLeafBoost, 0u, 1u, 0u}, {step}, 0, true, out);
 }
 
 inline void add_boost(vdev::DeviceIndex& ix, const char* boost_json, vgpu_hitlist& inout) {
