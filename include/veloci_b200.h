@@ -221,14 +221,21 @@ int32_t vgpu_query_parse(const char* text, uint32_t options, char** tree_debug);
  * (= the anchor id of a hit), NUL-terminated, released with vgpu_free.  What search::to_documents does per hit when the
  * request has no `select` (src/search.rs:89-98).  VGPU_ERR_IO when the store is missing, damaged, or has no such document. */
 int32_t vgpu_get_doc(vgpu_index* idx, uint32_t doc_id, char** doc_json);
-/* search::to_search_result for a request without `select` (src/search.rs:65-110): after execute, the hits of request q
+/* search::to_search_result (src/search.rs:65-110): after execute, the hits of request q
  * as documents, `{"num_hits": n, "data": [{"doc": {..}, "hit": {"id", "score"}, "why_found": {"<field>": ["..<b>term</b>.."]}}]}`.
  * `why_found` is filled when the request set `"why_found": true`: the texts of the terms its parts matched
  * (SearchResult::why_found_terms, src/search.rs:186) highlight the stored document, field by field
  * (highlight_on_original_document / highlight_text, src/highlight_field.rs:98-186: windows of five words around the hits,
- * " ... " between and around them).  Released with vgpu_free.  Not for sharded batches (a shard holds its own anchors only):
+ * " ... " between and around them).  A request with `select` gets its documents from vgpu_read_doc's path instead of the
+ * store.  Released with vgpu_free.  Not for sharded batches (a shard holds its own anchors only):
  * fetch the merged hits' documents with vgpu_get_doc there. */
 int32_t vgpu_batch_result_docs(vgpu_batch* batch, uint32_t q, char** result_json);
+/* read_data (src/search/read_document.rs:8-59): document `doc_id` rebuilt from the indices, only the fields of `fields_json`
+ * (a JSON list of field paths, the request's `select`): 1:n levels through `<level>.parent_to_value_id`, texts through
+ * `<field>.textindex.parent_to_value_id` and the dictionary, long texts from their token ids (src/search.rs:242-269).
+ * vgpu_batch_result_docs uses it for requests with `select`, together with the token-id based why_found
+ * (src/search/why_found.rs:11-49, highlight_document src/highlight_field.rs:187-271). */
+int32_t vgpu_read_doc(vgpu_index* idx, uint32_t doc_id, const char* fields_json, char** doc_json);
 
 /* ---- step seam -------------------------------------------------------------
  * One symbol per PlanStep kind (src/plan_creator/plan_steps.rs:18-74), each over host

@@ -489,6 +489,18 @@ def test_result_docs_and_why_found(gpu, native_libs):
             assert h["why_found"] == ohl.highlight_on_original_document(columns, h["doc"], terms), req
     with pytest.raises(gpu.VelociGpuError):
         index.get_doc(len(fx.TEST_WHYFOUND_DOCS))
+    # requests with `select`: documents rebuilt from the indices, why_found by token ids (test_why_found.rs:177-221, :267-284)
+    sel = [
+        ({**S("ID1000", "not_tokenized"), "select": ["not_tokenized"]}, {"not_tokenized": "ID1000"}, {"not_tokenized": ["<b>ID1000</b>"]}),
+        ({**S("ID1000", "not_tokenized_1_n[]"), "select": ["not_tokenized_1_n[]"]}, {"not_tokenized_1_n": ["ID1000"]}, {"not_tokenized_1_n[]": ["<b>ID1000</b>"]}),
+        ({**S("umsortiert", "viele[]", levenshtein_distance=0), "select": ["richtig"]}, {"richtig": "shön"}, {"viele[]": [" ... zu checken, dass da nicht <b>umsortiert</b> wird"]}),
+        ({"search_req": {"search": {"terms": ["schön"], "path": "richtig"}}, "select": ["richtig", "viele[]", "nofield"]}, {"richtig": "schön super", "viele": ["nette", "leute"]}, {}),
+    ]
+    b = index.prepare([json.dumps(r, ensure_ascii=False) for r, _, _ in sel]).execute()
+    for q, (req, doc, why) in enumerate(sel):
+        res = b.result_docs(q)
+        assert res["data"][0]["doc"] == doc and res["data"][0]["why_found"] == why, (req, res)
+    assert index.read_doc(2, ["custom_tokenized", "viele[]"]) == {"custom_tokenized": "<<cool>>", "viele": fx.TEST_WHYFOUND_DOCS[2]["viele"]}
 
 
 def test_lowercase_with_expansion_and_final_sigma(gpu, native_libs):

@@ -116,6 +116,7 @@ def load_library():
     L.vgpu_suggest_part.argtypes = [vp, cp, P(_Suggestions)]
     L.vgpu_get_doc.argtypes = [vp, ctypes.c_uint32, P(vp)]
     L.vgpu_batch_result_docs.argtypes = [vp, ctypes.c_uint32, P(vp)]
+    L.vgpu_read_doc.argtypes = [vp, ctypes.c_uint32, cp, P(vp)]
     L.vgpu_search_query.argtypes = [vp, cp, P(vp)]
     L.vgpu_suggest_query.argtypes = [vp, cp, P(vp)]
     L.vgpu_query_parse.argtypes = [cp, ctypes.c_uint32, P(vp)]
@@ -512,6 +513,11 @@ class Index:
         """The stored document of a hit (DocLoader::get_doc), parsed."""
         out = ctypes.c_void_p()
         return json.loads(_take_string(self.L, self.L.vgpu_get_doc(self.h, int(doc_id), ctypes.byref(out)), out))
+
+    def read_doc(self, doc_id, fields):
+        """The document rebuilt from the indices, `fields` only (read_data, the request's `select`)."""
+        out = ctypes.c_void_p()
+        return json.loads(_take_string(self.L, self.L.vgpu_read_doc(self.h, int(doc_id), json.dumps(list(fields)).encode("utf-8"), ctypes.byref(out)), out))
 
     # ---- request generation (query_generator::search_query / suggest_query)
     def search_query(self, params=None, **kw):

@@ -60,6 +60,9 @@ static int32_t guarded(F&& f) {
     } catch (const vhost::IoError& e) {
         t_error = e.what();
         return VGPU_ERR_IO;
+    } catch (const vhost::MissingTextId& e) {
+        t_error = e.what();
+        return VGPU_ERR_IO;
     } catch (const vhost::RequestError& e) {
         t_error = e.what();
         return VGPU_ERR_JSON;
@@ -656,6 +659,20 @@ int32_t vgpu_get_doc(vgpu_index* idx, uint32_t doc_id, char** doc_json) {
     if (!idx || !doc_json) return VGPU_ERR_INVALID_REQUEST;
     *doc_json = nullptr;
     return guarded([&]() { *doc_json = c_string(idx->ix->host->get_doc(doc_id)); });
+}
+int32_t vgpu_read_doc(vgpu_index* idx, uint32_t doc_id, const char* fields_json, char** doc_json) {
+    if (!idx || !fields_json || !doc_json) return VGPU_ERR_INVALID_REQUEST;
+    *doc_json = nullptr;
+    return guarded([&]() {
+        const vjson::Value f = vjson::parse(fields_json, strlen(fields_json));
+        if (!f.is_array()) throw vhost::RequestError("select must be an array");
+        std::vector<std::string> fields;
+        for (auto& e : f.arr) {
+            if (!e.is_string()) throw vhost::RequestError("select must be an array of strings");
+            fields.push_back(e.str);
+        }
+        *doc_json = c_string(vjson::to_string(vhost::read_data(*idx->ix->host, doc_id, fields)));
+    });
 }
 int32_t vgpu_batch_result_docs(vgpu_batch* batch, uint32_t q, char** result_json) {
     if (!batch || !result_json || q >= batch->b.n) return VGPU_ERR_INVALID_REQUEST;

@@ -202,6 +202,8 @@ inline std::vector<uint8_t> export_plan(const BatchPlan& plan_in) {
         w.u32((rq.has_facets ? 1u : 0u) | (rq.why_found ? 2u : 0u)), w.u32(rq.facet_begin);
         w.u64(rq.facets.size());
         for (auto& f : rq.facets) w.str(f.field), w.opt(f.top);
+        w.u32(rq.select ? 1u : 0u);
+        if (rq.select) w.str_vec(*rq.select);
     }
     w.pod_vec(plan_in.parts);
     w.pod_vec(plan_in.part_dict);
@@ -263,6 +265,11 @@ inline void import_plan(const vdev::DeviceIndex* ix, const void* blob, size_t le
             f.field = r.str();
             r.opt(f.top);
             rq.facets.push_back(std::move(f));
+        }
+        if (r.u32()) {
+            std::vector<std::string> fields;
+            r.str_vec(fields);
+            rq.select = std::move(fields);
         }
         plan.requests.push_back(std::move(rq));
     }

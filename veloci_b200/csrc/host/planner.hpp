@@ -37,6 +37,7 @@ struct RequestPlan {
     bool has_facets = false;
     uint32_t facet_begin = 0;  // first of the request's entries in BatchPlan::facets
     bool why_found = false;    // Request::why_found: the matched term texts are kept for highlighting (execution_plan.rs:416)
+    std::optional<std::vector<std::string>> select;  // Request::select: the hits' documents are rebuilt from the indices (search.rs:82-88)
 };
 
 // `x op y` boost expression (src/expression.rs:25-100)
@@ -617,6 +618,7 @@ struct BatchPlan {
         rp.top = request.top.value_or(10);  // search.rs:146
         rp.skip = request.skip.value_or(0);
         rp.why_found = request.why_found;
+        rp.select = request.select;
         if (!request.search_req) throw InvalidRequest("search_req is None, but is required in search");
         {  // the top-k heap: merged in shared memory up to 256 keys, in global memory up to 4096 (one device only: shards gather every heap)
             const uint64_t limit = ix->n_shards > 1 ? vdev::kMaxK : vdev::kMaxKLarge;

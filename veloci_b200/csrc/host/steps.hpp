@@ -7,6 +7,7 @@
 #include "../../../include/veloci_b200.h"
 #include "engine.hpp"
 #include "highlight.hpp"
+#include "read_document.hpp"
 
 namespace vsteps {
 
@@ -64,8 +65,25 @@ inline vhost::TermSets why_found_terms(vdev::Batch& b, uint32_t q) {
     return out;
 }
 
-// search::to_search_result without `select` (src/search.rs:65-110): the documents of request q's hits from the document
-// store, each with its hit and -- when the request asked for why_found -- the highlighted texts of the matched terms.
+// term_id_hits_in_field of request q (search_field.rs:375-380, merged over the parts: set_op.rs:29-47): per dictionary path
+// the ids of the terms its search parts matched -- what get_why_found highlights by when the request has `select`.
+inline std::map<std::string, std::set<uint32_t>> why_found_term_ids(vdev::Batch& b, uint32_t q) {
+    std::map<std::string, std::set<uint32_t>> out;
+    const vdev::QueryProgram& qp = b.plan.programs[q];
+    for (uint32_t l = 0; l < qp.n_leaves; ++l) {
+        const uint32_t part = b.plan.leaf_part[qp.leaf_begin + l];
+        if (b.plan.parts[part].flags & vdev::kPartList) continue;
+        std::vector<uint32_t> terms;
+        std::vector<float> scores;
+        b.download_matches(part, terms, scores);
+        out[b.plan.dict_names[b.plan.part_dict[part]]].insert(terms.begin(), terms.end());
+    }
+    return out;
+}
+
+// search::to_search_result (src/search.rs:65-110): the documents of request q's hits -- from the document store, or rebuilt
+// from the indices when the request has `select` -- each with its hit and, when the request asked for why_found, the
+// highlighted texts of the matched terms.
 // {"num_hits": n, "data": [{"doc": {..}, "hit": {"id": .., "score": ..}, "why_found": {"field": ["<b>..</b>"]}}]}
 inline std::string result_docs(vdev::Batch& b, uint32_t q) {
     const vplan::RequestPlan& rp = b.plan.requests[q];
@@ -74,17 +92,22 @@ inline std::string result_docs(vdev::Batch& b, uint32_t q) {
     std::vector<vdev::vgpu_hit_pod> hits((size_t)cap + 1);
     const uint32_t n = b.result(q, &num_hits, hits.data(), cap);
     vhost::TermSets terms;
-    if (rp.why_found && n) terms = why_found_terms(b, q);
+    std::map<std::string, std::set<uint32_t>> term_ids;
+    if (rp.why_found && n) {
+        if (rp.select) term_ids = why_found_term_ids(b, q);  // with `select` the texts are highlighted by token ids (why_found.rs:11-49)
+        else terms = why_found_terms(b, q);
+    }
     std::string out = "{\"num_hits\":" + std::to_string(num_hits) + ",\"data\":[";
     for (uint32_t i = 0; i < n; ++i) {
-        const std::string doc = b.ix->host->get_doc(hits[i].id);
+        const std::string doc = rp.select ? vjson::to_string(vhost::read_data(*b.ix->host, hits[i].id, *rp.select)) : b.ix->host->get_doc(hits[i].id);
         if (i) out += ',';
         out += "{\"doc\":" + doc + ",\"hit\":{\"id\":" + std::to_string(hits[i].id) + ",\"score\":";
         char buf[48];
         snprintf(buf, sizeof buf, "%.9g", (double)hits[i].score);
         out += buf;
         out += "},\"why_found\":";
-        vhost::write_highlights(out, vhost::highlight_document(b.ix->host->metadata, doc, terms));
+        if (rp.select) vhost::write_highlights(out, vhost::why_found_by_ids(*b.ix->host, hits[i].id, term_ids));
+        else vhost::write_highlights(out, vhost::highlight_document(b.ix->host->metadata, doc, terms));
         out += '}';
     }
     return out + "]}";

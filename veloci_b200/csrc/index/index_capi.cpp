@@ -6,6 +6,7 @@
 
 #include "../host/highlight.hpp"
 #include "../host/query_generator.hpp"
+#include "../host/read_document.hpp"
 #include "../host/regex_dfa.hpp"
 #include "../host/request.hpp"
 #include "indexer.hpp"
@@ -304,6 +305,33 @@ int vidx_fst_dump(const char* path, char* out, size_t outlen) {
         }
         if (items.size() != r.len()) check = "key count differs from the footer";
         s += check;
+        if (s.size() + 1 > outlen) throw std::runtime_error("output buffer too small");
+        set_err(out, outlen, s.c_str());
+        return 0;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
+        return 1;
+    }
+}
+
+// read_data (host/read_document.hpp) over the index in `dir`: `fields_json` = the request's `select`; with `term_ids_json`
+// ({"<field>.textindex": [term ids]}) instead the token-id based why_found of anchor `id` (why_found_by_ids).
+int vidx_read_doc(const char* dir, uint32_t id, const char* fields_json, const char* term_ids_json, char* out, size_t outlen) {
+    try {
+        const auto p = vhost::Persistence::load(dir);
+        std::string s;
+        if (term_ids_json) {
+            const vjson::Value t = vjson::parse(term_ids_json, strlen(term_ids_json));
+            std::map<std::string, std::set<uint32_t>> ids;
+            for (auto& kv : t.obj)
+                for (auto& x : kv.second.arr) ids[kv.first].insert((uint32_t)x.num);
+            vhost::write_highlights(s, vhost::why_found_by_ids(*p, id, ids));
+        } else {
+            const vjson::Value f = vjson::parse(fields_json, strlen(fields_json));
+            std::vector<std::string> fields;
+            for (auto& e : f.arr) fields.push_back(e.str);
+            s = vjson::to_string(vhost::read_data(*p, id, fields));
+        }
         if (s.size() + 1 > outlen) throw std::runtime_error("output buffer too small");
         set_err(out, outlen, s.c_str());
         return 0;
