@@ -51,6 +51,7 @@ struct alignas(16) WarpScratch {
     const uint32_t* term_bits[kFastMaxTerms];  // the current item's plane rows, at the group's first word
     uint32_t term_part[kFastMaxTerms + 4];     // (+ 4: the entry pass reads parts four at a time)
     float term_ub[kFastMaxTerms + 4];          // largest score the term can give its part (term score x largest weight of its plane)
+    uint32_t term_xkey[kFastMaxTerms + 4];     // ... as the exact order key of that product, without slack (PruneInputs: tie rule)
     int term_lev[kFastMaxTerms + 4];           // boost level an anchor whose part takes this term must be inside (-1: any, -2: it cannot matter)
     int count_lev[kFastMaxLeaves];             // ... an anchor with exactly n + 1 parts present must be inside
     const uint32_t* term_lw[kFastMaxTerms + 4]; // row the term's words are AND-ed with: its boost level's, all ones (any anchor) or all zeros (cannot matter)
@@ -276,13 +277,19 @@ struct PruneInputs {
     float max_mult;    // largest boost multiplier (1 without a boost)
     uint32_t part_terms[kFastMaxLeaves];  // per part: mask of its terms
     uint32_t nt;
+    // Requests of one part without a boost: a sweep anchor's score is exactly ts * weight of its strongest plane term, so
+    // term t gives at most exact_key = key(ts[t] * wmax[plane t]), the very product eval_candidate forms for an anchor of
+    // that weight.  Against a threshold of the same score the anchor id decides (larger wins, search.rs:123-130): when every
+    // anchor of the item lies below the threshold's anchor, the term cannot matter in this item.  Items are taken from the
+    // highest anchors down, so the ties of a frequent term are settled by its first group instead of evaluated everywhere.
+    // (exact_key lives in WarpScratch::term_xkey, the item's last anchor is passed to compute_prune)
     const uint32_t* lev_bits;             // the boost column's level rows at the item's first word (nullptr without a boost)
     uint32_t lev_words;
     const uint32_t* ones_row;
     const uint32_t* zeros_row;
 };
 
-__device__ __forceinline__ Prune compute_prune(WarpScratch& S, const PruneInputs& in, uint32_t flags, unsigned long long tau, uint32_t lane) {
+__device__ __forceinline__ Prune compute_prune(WarpScratch& S, const PruneInputs& in, uint32_t flags, unsigned long long tau, uint32_t lane, bool tie_rule, uint32_t item_hi) {
     Prune p;
     p.tau_score = 0.0f;
     if (tau != 0) {
@@ -293,6 +300,10 @@ __device__ __forceinline__ Prune compute_prune(WarpScratch& S, const PruneInputs
     if (lane < in.nt && p.tau_score > 0.0f) {
         if (in.bound * in.max_mult < p.tau_score) lv = -2;
         else if (flags & kFastBoost) lv = deepest_level(S, in.bound, p.tau_score);
+        else if (tie_rule) {
+            const uint32_t tau_key = (uint32_t)(tau >> 32), exact_key = S.term_xkey[lane];
+            if (exact_key < tau_key || (exact_key == tau_key && item_hi < (uint32_t)tau)) lv = -2;
+        }
     }
     int cl = -1;
     if (lane < kFastMaxLeaves && p.tau_score > 0.0f) {
@@ -526,8 +537,10 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
         if (first >= iend) break;
         const uint32_t last = min(iend, first + a.item_batch);
 #pragma unroll 1
-        for (uint32_t ii = first; ii < last; ++ii) {
-            // ---- item (tiles [t0, t0 + n), request q)
+        for (uint32_t it = first; it < last; ++it) {
+            // ---- item (tiles [t0, t0 + n), request q); the list is group-major ascending and is taken from its end: the groups
+            // of the highest anchors first (see PruneInputs::tie_rule)
+            const uint32_t ii = ibeg + (iend - 1u - it);
             const uint4* rp = reinterpret_cast<const uint4*>(a.items + ii);
             const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
             const uint32_t q = r0.x, t0 = r0.y & 0xFFFFFFu, n_item_tiles = r0.y >> 24;  // the item's tiles: [t0, t0 + n_item_tiles)
@@ -559,7 +572,11 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
                 S.term_bits[lane] = a.planes.bits + (size_t)D->plane[lane] * words + w0;
                 S.term_part[lane] = D->part[lane];
                 S.term_ub[lane] = D->ts[lane] * __ldg(a.planes.wmax + D->plane[lane]) * 1.00001f;
+                const uint32_t xkey = vbit::score_key(D->ts[lane] * __ldg(a.planes.wmax + D->plane[lane]));
+                S.term_xkey[lane] = xkey ? xkey : 1u;  // (eval_candidate never returns key 0)
             }
+            const bool tie_rule = L == 1 && !(flags & (kFastBoost | kFastUnion1));
+            const uint32_t item_hi = a.anchor_lo + rel0 + (nw << 5) - 1u;
             __syncwarp();
             PruneInputs pin;
             {
@@ -577,12 +594,13 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
                 pin.opt_need = (sum_all - mine) * f_less * pin.max_mult * 1.0001f;
                 pin.count_bound = D->bound[lane & 3u];  // (0 beyond the request's parts: such a count does not occur)
                 pin.lev_bits = lev_bits, pin.lev_words = lev_words, pin.ones_row = a.ones_row, pin.zeros_row = a.zeros_row;
+
 #pragma unroll
                 for (uint32_t l = 0; l < kFastMaxLeaves; ++l) pin.part_terms[l] = __ballot_sync(0xFFFFFFFFu, lane < nt && my_part == l);
             }
             // terms are grouped by part: bit t = term t is the last term of its part
             const uint32_t last_mask = __ballot_sync(0xFFFFFFFFu, lane < nt && (lane + 1u == nt || S.term_part[lane + 1u] != S.term_part[lane]));
-            Prune pr = compute_prune(S, pin, flags, tau, lane);
+            Prune pr = compute_prune(S, pin, flags, tau, lane, tie_rule, item_hi);
             uint32_t cnt = 0, ncand = 0;
             bool seeding = false;
             // candidates of one step: `cm` = anchors that pass the word-parallel tests
@@ -632,7 +650,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
                         }
                         if (enqueue(C, S, lane, q, flag, rel0 + idx, 0.0f, 0.0f, 0.0f, 0.0f, qn, ncand)) {
                             tau = __ldcg(a.tau + q);
-                            if (!seeding) pr = compute_prune(S, pin, flags, tau, lane);  // the rest of the sweep prunes against the tightened threshold
+                            if (!seeding) pr = compute_prune(S, pin, flags, tau, lane, tie_rule, item_hi);  // the rest of the sweep prunes against the tightened threshold
                         }
                     }
                 }
@@ -679,7 +697,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
                 if (qn) drain(C, &S, lane, 0, qn), qn = 0;
                 seeding = false;
                 tau = __ldcg(a.tau + q);
-                pr = compute_prune(S, pin, flags, tau, lane);
+                pr = compute_prune(S, pin, flags, tau, lane, tie_rule, item_hi);
             }
 
             if (n_ent) {
@@ -757,7 +775,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 2) plane_eval_kernel(PlaneArgs 
                     }
                     if (enqueue(C, S, lane, q, cand, rel, e0, e1, e2, e3, qn, ncand)) {
                         tau = __ldcg(a.tau + q);
-                        pr = compute_prune(S, pin, flags, tau, lane);
+                        pr = compute_prune(S, pin, flags, tau, lane, tie_rule, item_hi);
                     }
                 }
             }
