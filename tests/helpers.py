@@ -23,6 +23,8 @@ class OracleError(RuntimeError):
 def _index_lib():
     lib = ctypes.CDLL(build.build_index_lib())
     lib.vidx_create_from_jsonl.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+    lib.vidx_add_token_values.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+    lib.vidx_bound_part_hits.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_create_synthetic.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_write_synthetic_requests.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     return lib
@@ -37,6 +39,27 @@ def create_index(directory, docs, config=None):
     if rc != 0:
         raise RuntimeError(err.value.decode())
     return directory
+
+
+def add_token_values(directory, data, config):
+    """create/token_values_to_tokens.rs:26-82 on an index directory: data = [{"text", "value"}], config = {"path": field}."""
+    lib = _index_lib()
+    err = ctypes.create_string_buffer(_ERRLEN)
+    rc = lib.vidx_add_token_values(directory.encode(), json.dumps(data, ensure_ascii=False).encode("utf-8"), json.dumps(config).encode(), err, _ERRLEN)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return directory
+
+
+def bound_part_hits(directory, part, hits):
+    """The product's host arithmetic on a part's term hits (csrc/host/part_hits.hpp; no device): per-part top / skip bound,
+    part boost, token_value boost.  `hits` = [(term id, score)] of the part without those; returns its final hits."""
+    lib = _index_lib()
+    out = ctypes.create_string_buffer(1 << 22)
+    rc = lib.vidx_bound_part_hits(directory.encode(), json.dumps(part, ensure_ascii=False).encode("utf-8"), json.dumps([[int(i), float(s)] for i, s in hits]).encode(), out, len(out))
+    if rc != 0:
+        raise RuntimeError(out.value.decode())
+    return [(int(i), float(s)) for i, s in json.loads(out.value.decode())]
 
 
 def create_synthetic_index(directory, **params):

@@ -28,6 +28,9 @@ TEST_ALL_CONFIG = {
 
 LONG = "Prolog:\nthis is a story of a guy who went out to rule the world, but then died. the end"
 
+# tests/all/tests.rs:41: token values added to the test index after its creation
+TEST_ALL_TOKEN_VALUES = ([{"text": "Begeisterung", "value": 20}], {"path": "meanings.ger[]"})
+
 TEST_ALL_DOCS = [
     {"ignore_field": "", "commonness": 123456, "ent_seq": "99999", "tags": ["nice", "cool"]},
     {

@@ -281,6 +281,60 @@ def test_suggest_on_the_reference_corpus(gpu, native_libs):
         index.suggest({"terms": ["a"], "path": "nope"})
 
 
+def test_token_value_boosts(gpu, native_libs):
+    """`token_value` of a search part (search_field.rs:391-395): add_boost over the part's term hits with the
+    1:1 store create/token_values_to_tokens.rs writes.  The reference's own case (tests.rs:1134-1158) on its corpus, then a
+    20k-term dictionary where a third of the terms carry values: every boost function, an expression, skip_when_score,
+    together with the per-part top bound and the part boost, in suggest, in the FieldSearch step and inside whole
+    requests (alone, in or / and trees, with a request boost), from an exported plan too."""
+    d = tempfile.mkdtemp(prefix="vb200_gpu_")
+    helpers.create_index(d, fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG)
+    helpers.add_token_values(d, *fx.TEST_ALL_TOKEN_VALUES)
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    tv = {"path": "meanings.ger[]", "boost_fun": "Log10", "param": 1}
+    part = {"terms": ["begeist"], "path": "meanings.ger[]", "levenshtein_distance": 0, "starts_with": True, "token_value": tv, "top": 10, "skip": 0}
+    got = index.suggest(part)
+    assert [t for t, _, _ in got] == ["begeisterung", "begeistern", "begeisterung (f)"]
+    _same_suggestions(got, oracle.call("suggest", part=part), part)
+    compare(index, oracle, [{"search_req": {"search": {k: v for k, v in part.items() if k not in ("top", "skip")}}},
+                            {"search_req": {"search": part}},
+                            {"search_req": {"or": {"queries": [{"search": part}, S("urge", "meanings.eng[]")]}}}])
+    with pytest.raises(Exception):  # no token values on this field: "Did not found path in indices"
+        index.suggest({"terms": ["will"], "path": "meanings.eng[]", "token_value": {"path": "meanings.eng[]", "boost_fun": "Log10"}})
+    b = index.prepare([json.dumps({"search_req": {"search": {"terms": ["will"], "path": "meanings.eng[]", "token_value": {"path": "meanings.eng[]"}}}}),
+                       json.dumps({"search_req": S("urge", "meanings.eng[]")})]).execute()
+    assert b.status(0) == 3 and b.status(1) == 0, (b.status(0), b.message(0))
+
+    from test_part_hits import make_valued_index, token_value_parts
+    d, oracle, words, _ = make_valued_index()
+    index = gpu.Index(d)
+    P = lambda t, **kw: {"search": {"terms": [t], "path": "body", **kw}}
+    reqs = []
+    for i, part in enumerate(token_value_parts(words)):
+        w = words[i]
+        _same_suggestions(index.suggest(part), oracle.call("suggest", part=part), part)
+        hits, _ = index.field_search(part)
+        ref = sorted(oracle.call("field_search", part=part)["hits_scores"])
+        assert [h[0] for h in sorted(hits)] == [h[0] for h in ref], part
+        for (_, gs), (_, cs) in zip(sorted(hits), ref):
+            assert abs(float(gs) - float(cs)) <= 1e-5 * max(abs(float(cs)), 1e-30), part
+        shape = i % 4
+        other = P(words[(i + 5) % len(words)], levenshtein_distance=1)
+        if shape == 0:
+            reqs.append({"search_req": {"search": part}})
+        elif shape == 1:
+            reqs.append({"search_req": {"or": {"queries": [{"search": part}, other]}}, "boost": [{"path": "commonness", "boost_fun": "Log10", "param": 1}]})
+        elif shape == 2:
+            reqs.append({"search_req": {"and": {"queries": [{"search": part}, P(w[:1], starts_with=True)]}}})
+        else:
+            reqs.append({"search_req": {"or": {"queries": [{"search": part}, {"search": {**part, "token_value": {"path": "body", "boost_fun": "Multiply"}}}]}}, "top": 5})
+    batch = compare(index, oracle, reqs)
+    texts = [json.dumps(r) for r in reqs]
+    again = index.prepare(len(texts), plan=batch.export_plan()).execute()
+    for q in range(len(texts)):
+        assert again.status(q) == 0 and again.result(q) == batch.result(q), texts[q]
+
+
 def test_suggest_bounds_and_boosts_on_a_large_dictionary(gpu, native_libs):
     """Prefix and fuzzy suggestions over a 20k-term dictionary: hundreds of matches per part, so the per-part top bound
     (keep top + skip + 200, cut, drop what scores below the worst kept) is exercised, with part boosts (also negative),

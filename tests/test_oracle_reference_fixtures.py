@@ -13,15 +13,17 @@ import helpers
 import ref_fixtures as fx
 
 
-def _make(docs, config):
+def _make(docs, config, token_values=None):
     d = tempfile.mkdtemp(prefix="vb200_idx_")
     helpers.create_index(d, docs, config)
+    if token_values:
+        helpers.add_token_values(d, *token_values)
     return helpers.Oracle(d)
 
 
 @pytest.fixture(scope="module")
 def test_all(native_libs):
-    return _make(fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG)
+    return _make(fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG, fx.TEST_ALL_TOKEN_VALUES)  # tests.rs:38-44
 
 
 @pytest.fixture(scope="module")
@@ -415,3 +417,20 @@ def test_multi_real_suggest_with_score(test_all):  # tests.rs:1115-1132
 def test_suggest_terms_of_field_search(test_all):  # tests.rs:960-993 (return_term, not lower-cased)
     got = test_all.call("suggest", part={"terms": ["majes"], "path": "meanings.ger[]", "levenshtein_distance": 0, "starts_with": True})
     assert sorted(t for t, _, _ in got) == sorted(s.lower() for s in ["Majestät", "Majestät (f)", "majestätischer", "majestätischer Anblick (m)", "majestätisches", "majestätisches Aussehen (n)"])
+
+
+def test_suggest_with_token_value(test_all):  # tests.rs:1134-1158
+    part = {"terms": ["begeist"], "path": "meanings.ger[]", "levenshtein_distance": 0, "starts_with": True,
+            "token_value": {"path": "meanings.ger[]", "boost_fun": "Log10", "param": 1}, "top": 10, "skip": 0}
+    got = test_all.call("suggest", part=part)
+    assert [t for t, _, _ in got] == ["begeisterung", "begeistern", "begeisterung (f)"]
+    plain = {t: s for t, s, _ in test_all.call("suggest", part={k: v for k, v in part.items() if k != "token_value"})}
+    boosted = {t: s for t, s, _ in got}
+    # only "Begeisterung" carries a value (20): score * log10(20 + 1); the other terms keep their scores
+    assert abs(boosted["begeisterung"] - plain["begeisterung"] * 1.3222193) < 1e-4
+    assert boosted["begeistern"] == plain["begeistern"] and boosted["begeisterung (f)"] == plain["begeisterung (f)"]
+
+
+def test_token_value_errors(test_all):  # persistence.rs:454-458: a field without token values
+    with pytest.raises(helpers.OracleError):
+        test_all.call("suggest", part={"terms": ["will"], "path": "meanings.eng[]", "token_value": {"path": "meanings.eng[]", "boost_fun": "Log10"}})

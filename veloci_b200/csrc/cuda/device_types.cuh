@@ -172,6 +172,7 @@ enum PartFlags : uint32_t {
     kPartList = 32u,          // not a search part: its tile bucket is filled by a list producer (phrase pairs, text locality, 1:n boosts)
     kPartListBoost = 64u,     // list part of a 1:n boost: entries carry 0x7FFFFFFF - value id; the tile keeps the smallest value id of an
                               // anchor plus (bit 31) whether the anchor has several
+    kPartAnySign = 512u,      // a token_value boost follows the match (search_field.rs:391-395): the given scores may be negative
     kPartRegex = 256u,        // is_regex (search_field.rs:72-83): matched by regex_match_kernel with the part's DFA, scored like any other part
 };
 

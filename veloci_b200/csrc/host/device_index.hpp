@@ -882,7 +882,11 @@ struct DeviceIndex {
         ix->max_nonplane_list = ix->max_posting_list;
         ix->build_planes();
         for (auto& kv : ix->host->key_value_stores) ix->build_store(kv.first, kv.second);
-        for (auto& kv : ix->host->boost_valueid_to_value) ix->build_boost(kv.first, kv.second);
+        for (auto& kv : ix->host->boost_valueid_to_value) {
+            // token values are keyed by term id and applied to a part's few term hits on the host (engine.hpp: apply_token_value)
+            if (vfmt::ends_with(kv.first, ".token_values.boost_valid_to_value")) continue;
+            ix->build_boost(kv.first, kv.second);
+        }
         for (auto& kv : ix->host->phrase_pair_to_anchor) ix->build_phrase(kv.first, kv.second);
         VDEV_CUDA(cudaDeviceSynchronize());
         ix->build_reloc_table();

@@ -45,39 +45,6 @@ inline const char* probe_env(const char* name) {
 #endif
 }
 
-struct TermHit {
-    uint32_t id;
-    float score;
-};
-
-// The per-part `top` bound of get_term_ids_in_field over hits in FST order (= ascending term id): once top + skip + 200
-// hits are held, the best top + skip by (score, id) stay and a hit scoring below the worst of them is dropped from then
-// on (search_field.rs:322-331, sort.rs:25-34); the part's boost comes after (:359-364), then the best top + skip by score
-// stay (:366-369; the reference's unstable sort leaves the choice among equal scores open, a stable one is used here).
-inline void bound_part_hits(const vhost::SearchPart& part, std::vector<TermHit>& hits) {
-    const size_t top_n = part.top ? (size_t)(*part.top + part.skip.value_or(0)) : 0;
-    if (part.top) {
-        float worst = -3.40282347e+38f;
-        std::vector<TermHit> kept;
-        for (const TermHit& h : hits) {
-            if (h.score < worst) continue;
-            if (!kept.empty() && kept.size() == top_n + 200) {
-                std::sort(kept.begin(), kept.end(), [](const TermHit& a, const TermHit& b) { return a.score != b.score ? a.score > b.score : a.id > b.id; });
-                kept.resize(top_n);
-                if (!kept.empty()) worst = kept.back().score;
-            }
-            kept.push_back(h);
-        }
-        hits.swap(kept);
-    }
-    if (part.boost)
-        for (TermHit& h : hits) h.score *= *part.boost;
-    if (part.top) {
-        std::stable_sort(hits.begin(), hits.end(), [](const TermHit& a, const TermHit& b) { return a.score > b.score; });
-        if (hits.size() > top_n) hits.resize(top_n);
-    }
-}
-
 // Set (per thread) around a prepare whose plan is published to the other ranks of the box.
 inline bool& plan_for_all_ranks() {
     static thread_local bool flag = false;
@@ -685,13 +652,14 @@ struct Batch {
         matched = true;
     }
 
-    // Parts with a per-part `top` (search_field.rs:292-294): matched and scored on the device in a batch of their own, bounded on
-    // the host in FST order (bound_part_hits), and handed to this batch as given (term id, score) hits.
+    // Parts with a per-part `top` (search_field.rs:292-294) or a `token_value` boost (:391-395): matched and scored on the device in
+    // a batch of their own, bounded on the host in FST order (bound_part_hits), boosted by their token values, and handed to
+    // this batch as given (term id, score) hits.
     void match_bounded_parts(std::vector<MatchRecord>& records) {
         std::vector<vhost::SearchPart> device_parts;
         for (auto& bp : plan.bounded) {
             vhost::SearchPart p = bp.request;
-            p.top.reset(), p.skip.reset(), p.boost.reset();
+            p.top.reset(), p.skip.reset(), p.boost.reset(), p.token_value.reset();
             device_parts.push_back(std::move(p));
         }
         Batch own;
@@ -704,6 +672,7 @@ struct Batch {
             std::vector<TermHit> hits;
             own.download_part_hits(ids[i], hits);
             bound_part_hits(plan.bounded[i].request, hits);
+            apply_token_value(*ix->host, plan.bounded[i].request, hits);
             for (const TermHit& h : hits) {
                 records.push_back(MatchRecord{plan.bounded[i].part, (uint32_t)inj_terms.size()});
                 inj_terms.push_back(h.id), inj_scores.push_back(h.score);

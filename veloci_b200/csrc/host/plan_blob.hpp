@@ -152,10 +152,10 @@ inline void visit_all(std::vector<T>& v, F&& f) {
     for (auto& x : v) visit_ptrs(x, f);
 }
 
-static const uint64_t kBlobMagic = 0x32424c504f4c4556ull;  // "VELOPLB2"
+static const uint64_t kBlobMagic = 0x33424c504f4c4556ull;  // "VELOPLB3"
 
 inline void write_search_part(BlobWriter& w, const vhost::SearchPart& p) {
-    if (p.token_value || p.options.present) throw BlobError("search part with token_value / options cannot be exported");
+    if (p.options.present) throw BlobError("search part with options cannot be exported");
     w.str(p.path);
     w.u32(p.is_regex ? 1u : 0u);
     w.str_vec(p.terms);
@@ -165,6 +165,18 @@ inline void write_search_part(BlobWriter& w, const vhost::SearchPart& p) {
     w.opt(p.ignore_case);
     w.opt(p.top);
     w.opt(p.skip);
+    w.u32(p.token_value ? 1u : 0u);
+    if (p.token_value) {
+        const vhost::BoostPart& b = *p.token_value;
+        w.str(b.path);
+        w.u32((uint32_t)b.boost_fun);
+        w.opt(b.param);
+        w.u32(b.skip_when_score ? (uint32_t)b.skip_when_score->size() + 1u : 0u);
+        if (b.skip_when_score)
+            for (float f : *b.skip_when_score) w.raw(&f, 4);
+        w.u32(b.expression ? 1u : 0u);
+        if (b.expression) w.str(*b.expression);
+    }
 }
 inline void read_search_part(BlobReader& r, vhost::SearchPart& p) {
     p.path = r.str();
@@ -176,6 +188,26 @@ inline void read_search_part(BlobReader& r, vhost::SearchPart& p) {
     r.opt(p.ignore_case);
     r.opt(p.top);
     r.opt(p.skip);
+    p.token_value.reset();
+    if (r.u32() != 0) {
+        vhost::BoostPart b;
+        b.path = r.str();
+        const uint32_t fun = r.u32();
+        if (fun > (uint32_t)vhost::BoostFun::Replace) throw BlobError("plan blob is inconsistent (boost function)");
+        b.boost_fun = (vhost::BoostFun)fun;
+        r.opt(b.param);
+        const uint32_t n_skip = r.u32();
+        if (n_skip) {
+            b.skip_when_score.emplace();
+            for (uint32_t i = 1; i < n_skip; ++i) {
+                float f;
+                r.raw(&f, 4);
+                b.skip_when_score->push_back(f);
+            }
+        }
+        if (r.u32() != 0) b.expression = r.str();
+        p.token_value = std::move(b);
+    }
 }
 
 // The plan as bytes without process-local addresses.  `plan` is not modified.

@@ -13,6 +13,7 @@
 
 #include "../cuda/device_types.cuh"
 #include "device_index.hpp"
+#include "part_hits.hpp"
 #include "regex_dfa.hpp"
 #include "request.hpp"
 
@@ -21,13 +22,6 @@ namespace vplan {
 using vdev::BoostStep;
 using vdev::PartQuery;
 using vdev::QueryProgram;
-
-struct Unsupported : std::runtime_error {
-    using std::runtime_error::runtime_error;
-};
-struct InvalidRequest : std::runtime_error {
-    using std::runtime_error::runtime_error;
-};
 
 struct RequestPlan {
     int32_t status = 0;
@@ -39,48 +33,6 @@ struct RequestPlan {
     bool why_found = false;    // Request::why_found: the matched term texts are kept for highlighting (execution_plan.rs:416)
     std::optional<std::vector<std::string>> select;  // Request::select: the hits' documents are rebuilt from the indices (search.rs:82-88)
 };
-
-// `x op y` boost expression (src/expression.rs:25-100)
-inline void parse_expression(const std::string& expression, BoostStep& b) {
-    enum Kind { Division, Mul, Add, Sub, Score, Float };
-    std::vector<std::pair<Kind, float>> ops;
-    std::string current;
-    auto try_float = [&](const std::string& s) {
-        if (s.empty()) return;
-        char* end = nullptr;
-        float v = strtof(s.c_str(), &end);
-        if (end && *end == 0 && end != s.c_str()) ops.emplace_back(Float, v);
-    };
-    for (char c : expression) {
-        if (c == ' ') {
-            try_float(current);
-            current.clear();
-        } else {
-            current.push_back(c);
-        }
-        if (current == "+") ops.emplace_back(Add, 0.f), current.clear();
-        else if (current == "-") ops.emplace_back(Sub, 0.f), current.clear();
-        else if (current == "/") ops.emplace_back(Division, 0.f), current.clear();
-        else if (current == "*") ops.emplace_back(Mul, 0.f), current.clear();
-        else if (current == "$SCORE") ops.emplace_back(Score, 0.f), current.clear();
-    }
-    try_float(current);
-    if (ops.size() < 3) throw InvalidRequest("boost expression must be `x op y`");
-    auto operand = [&](const std::pair<Kind, float>& o, uint32_t& is_score, float& val) {
-        if (o.first == Score) is_score = 1, val = 0.f;
-        else if (o.first == Float) is_score = 0, val = o.second;
-        else throw InvalidRequest("boost expression operand must be a float or $SCORE");
-    };
-    operand(ops[0], b.expr_left_is_score, b.expr_left);
-    operand(ops[2], b.expr_right_is_score, b.expr_right);
-    switch (ops[1].first) {
-        case Division: b.expr_op = vdev::kExprDiv; break;
-        case Mul: b.expr_op = vdev::kExprMul; break;
-        case Add: b.expr_op = vdev::kExprAdd; break;
-        case Sub: b.expr_op = vdev::kExprSub; break;
-        default: throw InvalidRequest("boost expression operator must be one of * + - /");
-    }
-}
 
 struct BatchPlan {
     const vdev::DeviceIndex* ix = nullptr;
@@ -210,7 +162,12 @@ struct BatchPlan {
     uint32_t add_part(const vhost::SearchPart& part_in) {
         const vhost::SearchPart& req = part_in;
         if (req.terms.empty()) throw InvalidRequest("search part without terms");
-        if (req.token_value) throw Unsupported("token_value boost is outside the accelerated path");
+        if (req.token_value) {  // search_field.rs:391-395: the store must exist (persistence.rs:454-458), the expression parse
+            ix->host->get_boost(req.token_value->path + ".textindex.token_values.boost_valid_to_value");
+            BoostStep probe;
+            memset(&probe, 0, sizeof probe);
+            if (req.token_value->expression) parse_expression(*req.token_value->expression, probe);
+        }
         const FieldTables& ft = field_tables(req.path);
         const uint32_t did = ft.dict_id, pid = ft.postings_id;
         const std::string& term = req.terms[0];
@@ -266,10 +223,11 @@ struct BatchPlan {
             regex_parts.push_back(RegexPart{id, term, req.ignore_case.value_or(true), req.starts_with});
             return id;
         }
-        if (req.top) {
-            // The per-part bound (search_field.rs:292-294,:322-331,:366-369) depends on the order the hits arrive in: the engine
-            // matches such a part on its own first, bounds its hits on the host and gives them to the batch (kPartInjected).
-            q.flags |= vdev::kPartInjected;
+        if (req.top || req.token_value) {
+            // The per-part bound (search_field.rs:292-294,:322-331,:366-369) depends on the order the hits arrive in, and the
+            // token_value boost (:391-395) comes after it: the engine matches such a part on its own first, bounds and boosts
+            // its hits on the host and gives them to the batch (kPartInjected).
+            q.flags |= vdev::kPartInjected | (req.token_value ? vdev::kPartAnySign : 0u);
             const uint32_t id = (uint32_t)parts.size();
             parts.push_back(q);
             part_dict.push_back(did);
@@ -788,7 +746,7 @@ struct BatchPlan {
         qp.active = 1;
         qp.nonneg = 1;
         for (uint32_t part : leaves)
-            if (!(parts[part].boost >= 0.0f)) qp.nonneg = 0;
+            if (!(parts[part].boost >= 0.0f) || (parts[part].flags & vdev::kPartAnySign)) qp.nonneg = 0;
         max_leaves = std::max<uint32_t>(max_leaves, qp.n_leaves);
         max_k = std::max<uint32_t>(max_k, std::max<uint32_t>(qp.k, 1));
     }

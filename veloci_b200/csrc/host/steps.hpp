@@ -165,12 +165,11 @@ struct Suggestion {
 
 inline std::vector<Suggestion> suggest(vdev::DeviceIndex& ix, const vhost::Request& req) {
     if (!req.suggest) throw vplan::InvalidRequest("only suggest allowed in suggest function");
-    // the device matches and scores; bound and boost are applied to its output above
+    // the device matches and scores; bound, boost and token_value are applied to its output above
     std::vector<vhost::SearchPart> device_parts;
     for (const vhost::SearchPart& part : *req.suggest) {
-        if (part.token_value) throw vplan::Unsupported("token_value boost is outside the accelerated path");
         vhost::SearchPart p = part;
-        p.top.reset(), p.skip.reset(), p.boost.reset();
+        p.top.reset(), p.skip.reset(), p.boost.reset(), p.token_value.reset();
         device_parts.push_back(std::move(p));
     }
     std::vector<Suggestion> all;
@@ -183,6 +182,7 @@ inline std::vector<Suggestion> suggest(vdev::DeviceIndex& ix, const vhost::Reque
             std::vector<vdev::TermHit> hits;
             b.download_part_hits(part_ids[i], hits);
             vdev::bound_part_hits((*req.suggest)[i], hits);
+            vdev::apply_token_value(*ix.host, (*req.suggest)[i], hits);  // search_field.rs:391-395
             std::string path = device_parts[i].path;
             if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
             const vhost::TermDict& dict = ix.host->dict.at(path);

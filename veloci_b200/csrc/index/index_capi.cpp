@@ -5,6 +5,7 @@
 #include <sstream>
 
 #include "../host/highlight.hpp"
+#include "../host/part_hits.hpp"
 #include "../host/query_generator.hpp"
 #include "../host/read_document.hpp"
 #include "../host/regex_dfa.hpp"
@@ -37,6 +38,92 @@ int vidx_create_from_jsonl(const char* dir, const char* jsonl, const char* confi
         return 0;
     } catch (const std::exception& e) {
         set_err(err, errlen, e.what());
+        return 1;
+    }
+}
+
+// add_token_values_to_tokens (src/create/token_values_to_tokens.rs:26-82): `data_json` = [{"text": ..., "value": f32 | null}],
+// `config_json` = {"path": <field>}.  Every text is looked up exactly (levenshtein 0, case-sensitive) in the field's
+// dictionary; the found term ids get `value.to_bits()` in the 1:1 packed store
+// `<path>.textindex.token_values.boost_valid_to_value` (Boost, SingleValue, U32), appended to the column's indices.
+int vidx_add_token_values(const char* dir, const char* data_json, const char* config_json, char* err, size_t errlen) {
+    try {
+        std::unique_ptr<vhost::Persistence> p = vhost::Persistence::load(dir);
+        const vjson::Value data = vjson::parse(data_json, strlen(data_json));
+        const vjson::Value config = vjson::parse(config_json, strlen(config_json));
+        const vjson::Value* path_v = config.get("path");
+        if (!data.is_array() || !path_v || !path_v->is_string()) throw std::runtime_error("token values: expected an array of {text, value} and a config {path}");
+        const std::string field = path_v->str;
+        auto fst = p->fst.find(field + ".textindex");
+        if (fst == p->fst.end()) throw std::runtime_error("field does not exist " + field + ".textindex (fst not found)");
+        vfmt::PackedWriter w;
+        std::vector<std::pair<uint32_t, uint32_t>> entries;
+        for (const vjson::Value& el : data.arr) {
+            const vjson::Value* text = el.get("text");
+            const vjson::Value* value = el.get("value");
+            if (!text || !text->is_string()) throw std::runtime_error("token values: entry without text");
+            if (!value || value->is_null()) continue;
+            if (!value->is_number()) throw std::runtime_error("token values: value must be a number");
+            uint64_t id = 0;
+            if (!fst->second.get(text->str, id)) continue;
+            const float f = (float)value->num;
+            uint32_t bits;
+            memcpy(&bits, &f, 4);
+            entries.emplace_back((uint32_t)id, bits);
+        }
+        std::stable_sort(entries.begin(), entries.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+        for (auto& e : entries) w.add(e.first, e.second);
+        const std::string path = field + ".textindex.token_values.boost_valid_to_value";
+        const std::vector<uint8_t> bytes = w.encode();
+        vhost::write_file(std::string(dir) + "/" + path, bytes.data(), bytes.size());
+        vhost::IndexMetadata im;
+        im.path = path;
+        im.category = vhost::IndexCategory::Boost;
+        im.cardinality = vhost::IndexCardinality::SingleValue;
+        im.is_empty = w.cache.empty();
+        im.meta = w.meta;
+        vhost::Metadata meta = p->metadata;
+        auto col = meta.columns.find(field);
+        if (col == meta.columns.end()) {
+            vhost::FieldInfo fi;
+            fi.has_fst = false;
+            col = meta.columns.emplace(field, fi).first;
+        }
+        col->second.indices.push_back(im);
+        const std::string mj = vjson::to_string(vhost::metadata_to_json(meta), 2);
+        vhost::write_file(std::string(dir) + "/metaData.json", mj.data(), mj.size());
+        return 0;
+    } catch (const std::exception& e) {
+        set_err(err, errlen, e.what());
+        return 1;
+    }
+}
+
+// The product's host arithmetic on a part's term hits (host/part_hits.hpp: bound_part_hits, apply_token_value), for the CPU
+// tests that hold it against the oracle's get_term_ids_in_field: `hits_json` = [[term id, score], ...] as the device match
+// delivers them for the part without top / skip / boost / token_value; writes the part's final hits in the same form.
+int vidx_bound_part_hits(const char* dir, const char* part_json, const char* hits_json, char* out, size_t outlen) {
+    try {
+        std::unique_ptr<vhost::Persistence> p = vhost::Persistence::load(dir);
+        const vhost::SearchPart part = vhost::parse_search_part(vjson::parse(part_json, strlen(part_json)));
+        const vjson::Value hv = vjson::parse(hits_json, strlen(hits_json));
+        std::vector<vdev::TermHit> hits;
+        for (const vjson::Value& h : hv.arr) hits.push_back(vdev::TermHit{(uint32_t)h.arr.at(0).num, (float)h.arr.at(1).num});
+        std::sort(hits.begin(), hits.end(), [](const vdev::TermHit& a, const vdev::TermHit& b) { return a.id < b.id; });
+        vdev::bound_part_hits(part, hits);
+        vdev::apply_token_value(*p, part, hits);
+        std::string text = "[";
+        for (size_t i = 0; i < hits.size(); ++i) {
+            char buf[64];
+            snprintf(buf, sizeof buf, "%s[%u,%.9g]", i ? "," : "", hits[i].id, (double)hits[i].score);
+            text += buf;
+        }
+        text += "]";
+        if (text.size() + 1 > outlen) throw std::runtime_error("output buffer too small");
+        set_err(out, outlen, text.c_str());
+        return 0;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
         return 1;
     }
 }
