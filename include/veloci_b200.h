@@ -230,6 +230,15 @@ int32_t vgpu_get_doc(vgpu_index* idx, uint32_t doc_id, char** doc_json);
  * store.  Released with vgpu_free.  Not for sharded batches (a shard holds its own anchors only):
  * fetch the merged hits' documents with vgpu_get_doc there. */
 int32_t vgpu_batch_result_docs(vgpu_batch* batch, uint32_t q, char** result_json);
+/* SearchResult::explain of the hits request q returns (src/search.rs:174, read per hit by to_documents :86,96;
+ * src/search/result/explain.rs:1-21): `{"<anchor id>": [Explain, ...]}` in serde's form of the enum --
+ * {"LevenshteinScore": {"score", "text_or_token_id", "term_id"}} (search_field.rs:334-344),
+ * {"TermToAnchor": {"term_score", "anchor_score", "final_score", "term_id"}} (:429-441),
+ * {"OrSumOverDistinctTerms": f32} (set_op.rs:187-190), {"Boost": f32} (boost.rs:297-300,371-374) -- in the order the
+ * reference's plan steps push them.  For requests with `"explain": true` (or a part with `"options": {"explain": true}`);
+ * vgpu_batch_result_docs carries the same lists as each hit's "explain".  VGPU_ERR_UNSUPPORTED for the explanation (never for
+ * the search) when the request has phrase boosts or 1:n boosts, on sharded handles and on imported plans.  Released with vgpu_free. */
+int32_t vgpu_batch_explain(vgpu_batch* batch, uint32_t q, char** explain_json);
 /* read_data (src/search/read_document.rs:8-59): document `doc_id` rebuilt from the indices, only the fields of `fields_json`
  * (a JSON list of field paths, the request's `select`): 1:n levels through `<level>.parent_to_value_id`, texts through
  * `<field>.textindex.parent_to_value_id` and the dictionary, long texts from their token ids (src/search.rs:242-269).

@@ -55,7 +55,21 @@ struct Hit {  // search.rs:53-57
     float score;
 };
 
+struct Explain {  // result/explain.rs:1-21
+    enum Kind { Boost, MaxTokenToTextId, TermToAnchor, LevenshteinScore, OrSumOverDistinctTerms } kind;
+    float a = 0.f, b = 0.f, c = 0.f;  // Boost / MaxTokenToTextId / OrSum: a.  TermToAnchor: term_score, anchor_score, final_score.  LevenshteinScore: score
+    uint32_t term_id = 0;
+    std::string text;  // LevenshteinScore::text_or_token_id
+    explicit Explain(Kind k, float value = 0.f) : kind(k), a(value) {}
+};
+typedef std::map<uint32_t, std::vector<Explain>> ExplainMap;
+
+static bool is_explain(const SearchPart& part) {  // search_request.rs:182-184
+    return part.options.present && part.options.explain;
+}
+
 struct SearchFieldResult {  // result/field_result.rs:6-30 (hit-bearing fields only)
+    ExplainMap explain;
     std::vector<Hit> hits_scores;
     std::vector<uint32_t> hits_ids;
     std::vector<Hit> boost_ids;
@@ -242,8 +256,8 @@ static void levenshtein_search(const vhost::TermDict& dict, const std::string& q
     }
 }
 
-// search_field.rs:277-398 get_term_ids_in_field (token_value boost and per-part top/skip
-// pruning included; explain/terms maps omitted)
+// search_field.rs:277-398 get_term_ids_in_field (token_value boost, per-part top/skip
+// pruning and the explain map included)
 static void add_boost(const Persistence& p, const BoostPart& boost, SearchFieldResult& hits);
 
 static SearchFieldResult get_term_ids_in_field(const Persistence& p, PlanRequestSearchPart& options) {
@@ -284,6 +298,11 @@ static SearchFieldResult get_term_ids_in_field(const Persistence& p, PlanRequest
                 }
             }
             result.hits_scores.push_back(Hit{token_text_id, score});
+            if (is_explain(req)) {  // :334-344
+                Explain e(Explain::LevenshteinScore);
+                e.a = score, e.term_id = token_text_id, e.text = dict.term(slot);
+                result.explain[token_text_id] = {e};
+            }
         }
         if (options.return_term) result.terms[token_text_id] = options.return_term_lowercase ? olow::to_lowercase(dict.term(slot)) : dict.term(slot);  // :331-337
     };
@@ -384,6 +403,14 @@ static SearchFieldResult resolve_token_to_anchor(const Persistence& p, const Sea
             if (f && f->is_set && !f->set.count(anchor)) return;  // should_filter :540-548
             float el_score = f16_roundtrip((float)raw);
             float final_score = hit.score * (el_score / 100.0f);
+            if (is_explain(options_in)) {  // :429-441
+                std::vector<Explain>& vecco = res.explain[anchor];
+                Explain e(Explain::TermToAnchor);
+                e.term_id = hit.id, e.a = hit.score, e.b = el_score / 100.0f, e.c = final_score;
+                vecco.push_back(e);
+                auto exp = result.explain.find(hit.id);
+                if (exp != result.explain.end()) vecco.insert(vecco.end(), exp->second.begin(), exp->second.end());
+            }
             anchor_ids_hits.push_back(Hit{anchor, final_score});
         });
     }
@@ -488,7 +515,8 @@ struct ScoreExpression {
 };
 
 // boost.rs:283-377
-static void apply_boost(Hit& hit, float boost_value, float boost_param, BoostFun fun, const std::optional<ScoreExpression>& expre) {
+static void apply_boost(Hit& hit, float boost_value, float boost_param, BoostFun fun, const std::optional<ScoreExpression>& expre, ExplainMap* explain = nullptr) {
+    if (explain && fun == BoostFun::Log10) (*explain)[hit.id].push_back(Explain(Explain::Boost, log10f(boost_value + boost_param)));  // :297-300 (Log10 only)
     switch (fun) {
         case BoostFun::Log10: hit.score *= log10f(boost_value + boost_param); break;
         case BoostFun::Log2: hit.score *= log2f(boost_value + boost_param); break;
@@ -498,6 +526,7 @@ static void apply_boost(Hit& hit, float boost_value, float boost_param, BoostFun
         case BoostFun::None: break;
     }
     if (expre) hit.score += expre->get_score(boost_value);
+    if (explain) (*explain)[hit.id].push_back(Explain(Explain::Boost, hit.score));  // :371-374
 }
 
 // boost.rs:470-504
@@ -516,7 +545,7 @@ static void add_boost(const Persistence& p, const BoostPart& boost, SearchFieldR
         if (store.get_value(hit.id, bits)) {
             float v;
             memcpy(&v, &bits, 4);
-            apply_boost(hit, v, boost_param, boost.boost_fun, expre);
+            apply_boost(hit, v, boost_param, boost.boost_fun, expre, is_explain(hits.request) ? &hits.explain : nullptr);  // :484
         }
     }
 }
@@ -528,6 +557,7 @@ static void apply_boost_values_anchor(SearchFieldResult& results, const BoostPar
     if (boost.expression) expre.emplace(*boost.expression);
     size_t bi = 0;
     if (bi >= boosts.size()) return;
+    ExplainMap* explain = is_explain(results.request) ? &results.explain : nullptr;  // :258
     Hit hit_curr = boosts[bi++];
     for (Hit& hit : results.hits_scores) {
         if (hit_curr.id < hit.id) {
@@ -538,11 +568,11 @@ static void apply_boost_values_anchor(SearchFieldResult& results, const BoostPar
                     break;
                 } else if (b_hit.id == hit.id) {
                     hit_curr = b_hit;
-                    apply_boost(hit, b_hit.score, boost_param, boost.boost_fun, expre);
+                    apply_boost(hit, b_hit.score, boost_param, boost.boost_fun, expre, explain);
                 }
             }
         } else if (hit_curr.id == hit.id) {
-            apply_boost(hit, hit_curr.score, boost_param, boost.boost_fun, expre);
+            apply_boost(hit, hit_curr.score, boost_param, boost.boost_fun, expre, explain);
         }
     }
 }
@@ -559,6 +589,7 @@ static void apply_boost_from_iter(SearchFieldResult& results, const std::vector<
             } else if (b_hit.id == hit.id) {
                 hit_curr = b_hit;
                 hit.score *= b_hit.score;
+                if (is_explain(results.request)) results.explain[hit.id].push_back(Explain(Explain::Boost, b_hit.score));  // :213-217 (only here, not for the first match below)
             }
         }
     };
@@ -644,6 +675,10 @@ static SearchFieldResult union_hits_score(std::vector<SearchFieldResult> or_resu
         const std::string t = or_results[i].request.terms.empty() ? std::string() : or_results[i].request.terms[0];
         term_id[i] = (uint8_t)(std::find(terms.begin(), terms.end(), t) - terms.begin());
     }
+    const bool should_explain = is_explain(or_results[0].request);  // :120
+    if (should_explain)  // :133-137: a later input's explanations replace an earlier one's for the same anchor
+        for (auto& r : or_results)
+            for (auto& kv : r.explain) res.explain[kv.first] = kv.second;
     std::vector<size_t> pos(or_results.size(), 0);
     std::vector<float> max_scores_per_term(terms.size(), 0.0f);
     while (true) {
@@ -670,7 +705,17 @@ static SearchFieldResult union_hits_score(std::vector<SearchFieldResult> or_resu
         float sum = 0.0f;
         for (float m : max_scores_per_term) sum += m;
         res.hits_scores.push_back(Hit{id, sum * num_distinct_terms * num_distinct_terms});
+        if (should_explain) res.explain[id].push_back(Explain(Explain::OrSumOverDistinctTerms, sum));  // :187-190
     }
+    if (should_explain)  // :199-208
+        for (const Hit& hit : res.hits_scores)
+            for (auto& r : or_results) {
+                auto exp = r.explain.find(hit.id);
+                if (exp != r.explain.end()) {
+                    std::vector<Explain>& e = res.explain[hit.id];
+                    e.insert(e.end(), exp->second.begin(), exp->second.end());
+                }
+            }
     res.request = or_results[0].request;
     return res;
 }
@@ -714,6 +759,7 @@ static SearchFieldResult intersect_hits_score(std::vector<SearchFieldResult> and
     for (auto& el : and_results)
         for (auto& attr : el.term_id_hits_in_field)
             for (auto& th : attr.second) res.term_id_hits_in_field[attr.first][th.first] = th.second;
+    const bool should_explain = is_explain(and_results[0].request);  // :384 (before the shortest input is removed)
     size_t index_shortest = 0;
     uint64_t shortest = UINT64_MAX;
     for (size_t i = 0; i < and_results.size(); ++i)
@@ -759,6 +805,15 @@ static SearchFieldResult intersect_hits_score(std::vector<SearchFieldResult> and
             res.hits_scores.push_back(Hit{cur.id, score});
         }
     }
+    if (should_explain)  // :421-432: the explanations of the remaining inputs (the shortest one has been removed)
+        for (const Hit& hit : res.hits_scores)
+            for (auto& r : and_results) {
+                auto exp = r.explain.find(hit.id);
+                if (exp != r.explain.end()) {
+                    std::vector<Explain>& e = res.explain[hit.id];
+                    e.insert(e.end(), exp->second.begin(), exp->second.end());
+                }
+            }
     res.request = and_results[0].request;
     return res;
 }
@@ -915,6 +970,7 @@ struct SearchResult {  // result/search_result.rs:8-26
     std::vector<Hit> data;
     std::vector<std::pair<std::string, std::vector<FacetGroup>>> facets;
     bool has_facets = false;
+    ExplainMap explain;  // of the returned hits (search.rs:174 keeps the plan result's whole map; to_documents :86 reads it per hit)
 };
 
 // plan_creator + execute_steps, evaluated as a tree walk with the same dataflow.
@@ -926,6 +982,12 @@ class Executor {
         Request request = header_;
         request.top = request.top ? request.top : std::optional<uint64_t>(10);  // search.rs:146
         if (!request.search_req) throw InvalidRequest("search_req is None, but is required in search");
+        if (request.explain) {  // get_all_field_request_parts_and_propagate_settings (execution_plan.rs:46-90)
+            if (request.phrase_boosts)
+                for (auto& pb : *request.phrase_boosts) set_explain(pb.search1), set_explain(pb.search2);
+            propagate_explain(*request.search_req);
+            if (request.filter) propagate_explain(*request.filter);
+        }
         // collect_all_field_request_into_cache (execution_plan.rs:91-130)
         if (request.phrase_boosts)
             for (auto& pb : *request.phrase_boosts) {
@@ -991,6 +1053,7 @@ class Executor {
             }
             boost_hits_ids_vec_multi(res, grouped);
         }
+        ExplainMap plan_explain = res.explain;  // search.rs:174: taken before boost_term and text locality
         // search.rs:176-228
         if (request.boost_term) {
             std::vector<SearchFieldResult> data;
@@ -1021,6 +1084,10 @@ class Executor {
         // apply_top_skip :230-239
         if (request.skip) out.data.erase(out.data.begin(), out.data.begin() + (long)std::min<uint64_t>(skip, out.data.size()));
         if (out.data.size() > *request.top) out.data.resize(*request.top);
+        for (const Hit& h : out.data) {
+            auto e = plan_explain.find(h.id);
+            if (e != plan_explain.end()) out.explain[h.id] = e->second;
+        }
         return out;
     }
 
@@ -1034,6 +1101,12 @@ class Executor {
     const Request& header_;
     std::map<std::string, FieldSearch> cache_;
 
+    static void set_explain(SearchPart& part) { part.options.present = true, part.options.explain = true; }
+    static void propagate_explain(SearchRequest& r) {
+        if (r.kind == SearchRequest::Search) set_explain(r.part);
+        else
+            for (auto& q : r.queries) propagate_explain(q);
+    }
     void add_to_cache(const SearchPart& part, bool ids_only) {
         auto it = cache_.find(part.key());
         if (it != cache_.end()) {
@@ -1110,6 +1183,26 @@ class Executor {
     }
 };
 
+// serde's externally tagged form of result/explain.rs:1-21 (floats with 9 significant digits)
+static void write_explain(std::string& s, const Explain& e) {
+    char buf[160];
+    switch (e.kind) {
+        case Explain::Boost: snprintf(buf, sizeof buf, "{\"Boost\":%.9g}", (double)e.a), s += buf; break;
+        case Explain::MaxTokenToTextId: snprintf(buf, sizeof buf, "{\"MaxTokenToTextId\":%.9g}", (double)e.a), s += buf; break;
+        case Explain::OrSumOverDistinctTerms: snprintf(buf, sizeof buf, "{\"OrSumOverDistinctTerms\":%.9g}", (double)e.a), s += buf; break;
+        case Explain::TermToAnchor:
+            snprintf(buf, sizeof buf, "{\"TermToAnchor\":{\"term_score\":%.9g,\"anchor_score\":%.9g,\"final_score\":%.9g,\"term_id\":%u}}", (double)e.a, (double)e.b, (double)e.c, e.term_id);
+            s += buf;
+            break;
+        case Explain::LevenshteinScore:
+            snprintf(buf, sizeof buf, "{\"LevenshteinScore\":{\"score\":%.9g,\"text_or_token_id\":", (double)e.a);
+            s += buf;
+            vjson::write_string(s, e.text);
+            s += ",\"term_id\":" + std::to_string(e.term_id) + "}}";
+            break;
+    }
+}
+
 static std::string result_to_json(const SearchResult& r) {
     std::string s = "{\"num_hits\":" + std::to_string(r.num_hits) + ",\"data\":[";
     char buf[64];
@@ -1132,6 +1225,20 @@ static std::string result_to_json(const SearchResult& r) {
                 s += "[";
                 vjson::write_string(s, r.facets[i].second[j].text);
                 s += "," + std::to_string(r.facets[i].second[j].count) + "," + std::to_string(r.facets[i].second[j].id) + "]";
+            }
+            s += "]";
+        }
+        s += "}";
+    }
+    if (!r.explain.empty()) {
+        s += ",\"explain\":{";
+        bool first = true;
+        for (auto& kv : r.explain) {
+            s += (first ? "\"" : ",\"") + std::to_string(kv.first) + "\":[";
+            first = false;
+            for (size_t j = 0; j < kv.second.size(); ++j) {
+                if (j) s += ",";
+                write_explain(s, kv.second[j]);
             }
             s += "]";
         }

@@ -25,6 +25,7 @@ def _index_lib():
     lib.vidx_create_from_jsonl.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_add_token_values.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_bound_part_hits.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+    lib.vidx_explain_walk.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_create_synthetic.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_write_synthetic_requests.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     return lib
@@ -60,6 +61,41 @@ def bound_part_hits(directory, part, hits):
     if rc != 0:
         raise RuntimeError(out.value.decode())
     return [(int(i), float(s)) for i, s in json.loads(out.value.decode())]
+
+
+def explain_walk(directory, request, anchors, leaves):
+    """The product's explain walk (csrc/host/explain_walk.hpp; no device) for the returned `anchors` of `request`, given per
+    search part of the tree (tree order) the (term id, score) hits of the bare part.  -> {anchor: [Explain, ...]}"""
+    lib = _index_lib()
+    out = ctypes.create_string_buffer(1 << 22)
+    rc = lib.vidx_explain_walk(directory.encode(), json.dumps(request, ensure_ascii=False).encode("utf-8"), json.dumps([int(a) for a in anchors]).encode(),
+                               json.dumps([[[int(i), float(s)] for i, s in hits] for hits in leaves]).encode(), out, len(out))
+    if rc != 0:
+        raise OracleError(rc, out.value.decode())
+    return {int(k): v for k, v in json.loads(out.value.decode()).items()}
+
+
+def tree_parts(search_request):
+    """The search parts of a request tree in tree order."""
+    if "search" in search_request:
+        return [search_request["search"]]
+    node = search_request.get("or") or search_request.get("and")
+    return [p for q in node["queries"] for p in tree_parts(q)]
+
+
+def bare_part(part):
+    return {k: v for k, v in part.items() if k not in ("top", "skip", "boost", "token_value", "options")}
+
+
+def same_explain(got, want, rel=1e-5):
+    """Two explain values ({anchor: [Explain]} or parts of them): same structure, texts and ids, floats within `rel`."""
+    if isinstance(want, dict):
+        return isinstance(got, dict) and set(map(str, got)) == set(map(str, want)) and all(same_explain(got[k] if k in got else got[str(k)], v, rel) for k, v in want.items())
+    if isinstance(want, list):
+        return isinstance(got, list) and len(got) == len(want) and all(same_explain(g, w, rel) for g, w in zip(got, want))
+    if isinstance(want, float) or isinstance(got, float):
+        return abs(float(got) - float(want)) <= rel * max(abs(float(want)), 1e-30)
+    return got == want
 
 
 def create_synthetic_index(directory, **params):

@@ -688,3 +688,78 @@ def test_boost_and_phrase_step_symbols(gpu, native_libs):
         assert [(g[0], float(g[1])) for g in got] == [(r[0], float(r[1])) for r in ref], ws
         n_loc += len(got)
     assert n_loc > 20
+
+
+def test_explain(gpu, native_libs):
+    """`explain` (result/explain.rs): vgpu_batch_explain and the "explain" of vgpu_batch_result_docs against the
+    oracle's explain maps -- the reference's two explain tests (tests.rs:347-391), every shape of tests/test_explain.py on
+    the reference corpus and on a 20k-term dictionary with token values.  The walk itself is also checked on the CPU
+    (tests/test_explain.py); this test adds the device match of the bare parts and posting_lookup_kernel."""
+    import ref_fixtures as fx
+    from test_explain import UNSUPPORTED_REQUESTS, large_dictionary_requests, reference_corpus_requests
+    from test_part_hits import make_valued_index
+
+    d = tempfile.mkdtemp(prefix="vb200_gpu_explain_")
+    helpers.create_index(d, fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG)
+    helpers.add_token_values(d, *fx.TEST_ALL_TOKEN_VALUES)
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+
+    def check(index, oracle, requests):
+        texts = [json.dumps(r, ensure_ascii=False) for r in requests]
+        b = index.prepare(texts).execute()
+        n_items = 0
+        for q, r in enumerate(requests):
+            assert b.status(q) == 0, (texts[q], b.message(q))
+            want_res = oracle.search(r)
+            got_ids, want_ids = [h[0] for h in b.result(q)["data"]], [h[0] for h in want_res["data"]]
+            common = set(got_ids) & set(want_ids)  # (hits that tie at the end of the top-k may differ: helpers.same_topk)
+            assert len(got_ids) == len(want_ids) and len(common) + 2 >= len(want_ids), texts[q]
+            got = b.explain(q)
+            assert set(got) == set(got_ids), texts[q]
+            for a in common:  # an anchor nothing was recorded for has no entry in the reference's map
+                want = want_res.get("explain", {}).get(str(a), [])
+                assert helpers.same_explain(got[a], want), (texts[q], a, got[a], want)
+                n_items += len(want)
+        return b, n_items
+
+    requests = reference_corpus_requests()
+    b, n_items = check(index, oracle, requests)
+    assert n_items > 60
+    assert len(b.explain(0)[b.result(0)["data"][0][0]]) == 2  # tests.rs:363
+    assert len(b.explain(1)[b.result(1)["data"][0][0]]) == 5  # tests.rs:390
+    # DocWithHit::explain (search.rs:86,96)
+    docs = b.result_docs(1)["data"]
+    assert [len(h["explain"]) for h in docs] == [5, 5] and docs[0]["doc"]["ent_seq"] == "1587690"
+    assert helpers.same_explain({h["hit"]["id"]: h["explain"] for h in docs}, b.explain(1))
+    plain = index.prepare([json.dumps({"search_req": {"search": {"terms": ["urge"], "path": "meanings.eng[]"}}})]).execute()
+    assert "explain" not in plain.result_docs(0)["data"][0]
+    with pytest.raises(gpu.VelociGpuError) as e:
+        plain.explain(0)
+    assert e.value.status == 8
+    # outside the reconstruction: the search answers, the explanation is refused
+    unsupported = UNSUPPORTED_REQUESTS[:1]  # the 1:n boost (the phrase boost case needs another corpus: CPU test only)
+    bu = index.prepare([json.dumps(r, ensure_ascii=False) for r in unsupported]).execute()
+    for q in range(len(unsupported)):
+        assert bu.status(q) == 0, bu.message(q)
+        with pytest.raises(gpu.VelociGpuError) as e:
+            bu.explain(q)
+        assert e.value.status == 8, (q, e.value)
+        assert all(h["explain"] is None for h in bu.result_docs(q)["data"])
+    # an imported plan does not carry the request; a shard does not hold every anchor's postings
+    imported = index.prepare(len(requests), plan=b.export_plan()).execute()
+    assert imported.result(1) == b.result(1)
+    with pytest.raises(gpu.VelociGpuError) as e:
+        imported.explain(1)
+    assert e.value.status == 8
+
+    d, oracle, words, _ = make_valued_index()
+    index = gpu.Index(d)
+    large = list(large_dictionary_requests(words))
+    _, n_items = check(index, oracle, large)
+    assert n_items > 500
+    shard = gpu.Index(d, shard_rank=0, n_shards=2)
+    bs = shard.prepare([json.dumps(large[0])]).execute()
+    assert bs.status(0) == 0
+    with pytest.raises(gpu.VelociGpuError) as e:
+        bs.explain(0)
+    assert e.value.status == 8

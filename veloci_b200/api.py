@@ -116,6 +116,7 @@ def load_library():
     L.vgpu_suggest_part.argtypes = [vp, cp, P(_Suggestions)]
     L.vgpu_get_doc.argtypes = [vp, ctypes.c_uint32, P(vp)]
     L.vgpu_batch_result_docs.argtypes = [vp, ctypes.c_uint32, P(vp)]
+    L.vgpu_batch_explain.argtypes = [vp, ctypes.c_uint32, P(vp)]
     L.vgpu_read_doc.argtypes = [vp, ctypes.c_uint32, cp, P(vp)]
     L.vgpu_search_query.argtypes = [vp, cp, P(vp)]
     L.vgpu_suggest_query.argtypes = [vp, cp, P(vp)]
@@ -233,6 +234,12 @@ class Batch:
         """The hits of request q as documents with why_found highlights (search::to_search_result)."""
         out = ctypes.c_void_p()
         return json.loads(_take_string(self.L, self.L.vgpu_batch_result_docs(self.h, q, ctypes.byref(out)), out))
+
+    def explain(self, q):
+        """{anchor id: [Explain, ...]} of the hits request q returns (a request with "explain": true)."""
+        out = ctypes.c_void_p()
+        text = _take_string(self.L, self.L.vgpu_batch_explain(self.h, q, ctypes.byref(out)), out)
+        return {int(k): v for k, v in json.loads(text).items()}
 
     def export_plan(self):
         """The batch's plan as bytes without process-local addresses (vgpu_batch_export_plan)."""

@@ -974,6 +974,31 @@ void launch_scan_u64(cudaStream_t st, const uint64_t* in, uint64_t* out, uint32_
     scan_u64_kernel<<<1, 1024, 0, st>>>(in, out, n);
     count_launch();
 }
+// explain (search_field.rs:429-441): the posting weight of every (matched term, result anchor) pair, by binary search in the
+// term's posting list (anchors ascending); -1 where the term has no posting on the anchor.  One thread per pair.
+__global__ void posting_lookup_kernel(PostingsView pv, const uint32_t* __restrict__ terms, uint32_t n_terms, const uint32_t* __restrict__ anchors, uint32_t n_anchors,
+                                      float* __restrict__ weight) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_terms * n_anchors) return;
+    const uint32_t term = terms[i / n_anchors], anchor = anchors[i % n_anchors];
+    float w = -1.0f;
+    if (term < pv.n_terms) {
+        uint64_t lo = pv.off[term], hi = pv.off[term + 1];
+        while (lo < hi) {
+            const uint64_t mid = lo + ((hi - lo) >> 1);
+            if (pv.post[mid].anchor < anchor) lo = mid + 1;
+            else hi = mid;
+        }
+        if (lo < pv.off[term + 1] && pv.post[lo].anchor == anchor) w = pv.post[lo].weight;
+    }
+    weight[i] = w;
+}
+void launch_posting_lookup(cudaStream_t st, const PostingsView& pv, const uint32_t* terms, uint32_t n_terms, const uint32_t* anchors, uint32_t n_anchors, float* weight) {
+    const uint64_t n = (uint64_t)n_terms * n_anchors;
+    if (!n) return;
+    posting_lookup_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pv, terms, n_terms, anchors, n_anchors, weight);
+    count_launch();
+}
 void launch_score_scatter(cudaStream_t st, const ScoreScatterArgs& a) {
     if (!a.n_records) return;
     score_scatter_kernel<<<(a.n_records + 127) / 128, 128, 0, st>>>(a);

@@ -138,6 +138,9 @@ void launch_boost_to_anchor(cudaStream_t st, const BoostListMember* members, uin
 // the ids half of resolve_token_to_anchor (search_field.rs:468-498): one block per member
 void launch_ids_to_anchor(cudaStream_t st, const IdsMember* members, uint32_t n_members, const ListArgs& a);
 
+// explain: weight[t * n_anchors + a] = posting weight of term t on anchor a, -1 without a posting (one thread per pair)
+void launch_posting_lookup(cudaStream_t st, const PostingsView& pv, const uint32_t* terms, uint32_t n_terms, const uint32_t* anchors, uint32_t n_anchors, float* weight);
+
 // Patches the sum order of every `and` node (set_op.rs:388-417: the shortest input is
 // swap_remove'd and added last); input lengths are estimated by part_est.
 // Also sums, over all requests, the postings of their matched terms into *stat_postings (traffic model).

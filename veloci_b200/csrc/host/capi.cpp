@@ -683,6 +683,15 @@ int32_t vgpu_batch_result_docs(vgpu_batch* batch, uint32_t q, char** result_json
     }
     return guarded([&]() { *result_json = c_string(vsteps::result_docs(batch->b, q)); });
 }
+int32_t vgpu_batch_explain(vgpu_batch* batch, uint32_t q, char** explain_json) {
+    if (!batch || !explain_json || q >= batch->b.n) return VGPU_ERR_INVALID_REQUEST;
+    *explain_json = nullptr;
+    if (batch->b.plan.requests[q].status != 0) {
+        t_error = batch->b.plan.requests[q].message;
+        return batch->b.plan.requests[q].status;
+    }
+    return guarded([&]() { *explain_json = c_string(vexplain::Explainer(batch->b, q).walk().to_json()); });
+}
 int32_t vgpu_query_parse(const char* text, uint32_t options, char** tree_debug) {
     if (!text || !tree_debug) return VGPU_ERR_INVALID_REQUEST;
     *tree_debug = nullptr;

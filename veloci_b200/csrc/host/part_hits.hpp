@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -108,15 +109,33 @@ inline void bound_part_hits(const vhost::SearchPart& part, std::vector<TermHit>&
 // values of `<path>.textindex.token_values.boost_valid_to_value`, a 1:1 store keyed by term id (written by
 // create/token_values_to_tokens.rs:26-82).  skip_when_score, boost function and `x op y` expression as boost.rs:470-504 /
 // :283-377; a few hundred hits of host arithmetic on the output of the device match.
-inline void apply_token_value(const vhost::Persistence& host, const vhost::SearchPart& part, std::vector<TermHit>& hits) {
+// apply_boost (boost.rs:283-377) on one score with the boost value `v`: boost function, then the `x op y` expression.  `log`
+// receives what the reference's explain records on the way: the logarithm factor (Log10 only, :297-300) and the new score (:371-374).
+inline void apply_boost_value(const vhost::BoostPart& boost, float v, float& score, std::vector<float>* log = nullptr) {
+    const float param = boost.param.value_or(0.0f);
+    if (log && boost.boost_fun == vhost::BoostFun::Log10) log->push_back(log10f(v + param));
+    switch (boost.boost_fun) {
+        case vhost::BoostFun::Log10: score *= log10f(v + param); break;
+        case vhost::BoostFun::Log2: score *= log2f(v + param); break;
+        case vhost::BoostFun::Multiply: score *= v + param; break;
+        case vhost::BoostFun::Add: score += v + param; break;
+        case vhost::BoostFun::Replace: score = v + param; break;
+        case vhost::BoostFun::None: break;
+    }
+    if (boost.expression) {
+        BoostStep expr;
+        memset(&expr, 0, sizeof expr);
+        vplan::parse_expression(*boost.expression, expr);
+        const float l = expr.expr_left_is_score ? v : expr.expr_left, r = expr.expr_right_is_score ? v : expr.expr_right;
+        score += expr.expr_op == vdev::kExprDiv ? l / r : expr.expr_op == vdev::kExprMul ? l * r : expr.expr_op == vdev::kExprAdd ? l + r : l - r;
+    }
+    if (log) log->push_back(score);
+}
+
+inline void apply_token_value(const vhost::Persistence& host, const vhost::SearchPart& part, std::vector<TermHit>& hits, std::map<uint32_t, std::vector<float>>* explain_log = nullptr) {
     if (!part.token_value) return;
     const vhost::BoostPart& tb = *part.token_value;
     const vhost::KeyValueStore& store = host.get_boost(tb.path + ".textindex.token_values.boost_valid_to_value");
-    const float param = tb.param.value_or(0.0f);
-    BoostStep expr;
-    memset(&expr, 0, sizeof expr);
-    if (tb.expression) vplan::parse_expression(*tb.expression, expr);
-    auto operand = [](uint32_t is_score, float constant, float value) { return is_score ? value : constant; };
     for (TermHit& h : hits) {
         bool skip = false;
         if (tb.skip_when_score)
@@ -125,18 +144,7 @@ inline void apply_token_value(const vhost::Persistence& host, const vhost::Searc
         if (skip || !store.get_value(h.id, bits)) continue;
         float v;
         memcpy(&v, &bits, 4);
-        switch (tb.boost_fun) {
-            case vhost::BoostFun::Log10: h.score *= log10f(v + param); break;
-            case vhost::BoostFun::Log2: h.score *= log2f(v + param); break;
-            case vhost::BoostFun::Multiply: h.score *= v + param; break;
-            case vhost::BoostFun::Add: h.score += v + param; break;
-            case vhost::BoostFun::Replace: h.score = v + param; break;
-            case vhost::BoostFun::None: break;
-        }
-        if (tb.expression) {
-            const float l = operand(expr.expr_left_is_score, expr.expr_left, v), r = operand(expr.expr_right_is_score, expr.expr_right, v);
-            h.score += expr.expr_op == vdev::kExprDiv ? l / r : expr.expr_op == vdev::kExprMul ? l * r : expr.expr_op == vdev::kExprAdd ? l + r : l - r;
-        }
+        apply_boost_value(tb, v, h.score, explain_log ? &(*explain_log)[h.id] : nullptr);
     }
 }
 

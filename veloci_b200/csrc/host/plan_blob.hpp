@@ -231,7 +231,7 @@ inline std::vector<uint8_t> export_plan(const BatchPlan& plan_in) {
         w.u32((uint32_t)rq.status);
         w.str(rq.message);
         w.u64(rq.top), w.u64(rq.skip);
-        w.u32((rq.has_facets ? 1u : 0u) | (rq.why_found ? 2u : 0u)), w.u32(rq.facet_begin);
+        w.u32((rq.has_facets ? 1u : 0u) | (rq.why_found ? 2u : 0u) | (rq.explain_asked ? 4u : 0u)), w.u32(rq.facet_begin);
         w.u64(rq.facets.size());
         for (auto& f : rq.facets) w.str(f.field), w.opt(f.top);
         w.u32(rq.select ? 1u : 0u);
@@ -290,7 +290,7 @@ inline void import_plan(const vdev::DeviceIndex* ix, const void* blob, size_t le
         rq.message = r.str();
         rq.top = r.u64(), rq.skip = r.u64();
         const uint32_t request_flags = r.u32();
-        rq.has_facets = request_flags & 1u, rq.why_found = request_flags & 2u, rq.facet_begin = r.u32();
+        rq.has_facets = request_flags & 1u, rq.why_found = request_flags & 2u, rq.explain_asked = request_flags & 4u, rq.facet_begin = r.u32();
         const uint64_t nf = r.u64();
         for (uint64_t j = 0; j < nf; ++j) {
             vhost::FacetRequest f;

@@ -6,6 +6,7 @@
 #pragma once
 #include <cmath>
 #include <map>
+#include <memory>
 #include <string>
 #include <tuple>
 #include <unordered_map>
@@ -30,6 +31,8 @@ struct RequestPlan {
     std::vector<vhost::FacetRequest> facets;
     bool has_facets = false;
     uint32_t facet_begin = 0;  // first of the request's entries in BatchPlan::facets
+    std::shared_ptr<const vhost::Request> explain;  // the request itself when it asks for explain (host/explain.hpp rebuilds the explanations of its hits)
+    bool explain_asked = false;  // ... it did (an imported plan carries only this)
     bool why_found = false;    // Request::why_found: the matched term texts are kept for highlighting (execution_plan.rs:416)
     std::optional<std::vector<std::string>> select;  // Request::select: the hits' documents are rebuilt from the indices (search.rs:82-88)
 };
@@ -577,6 +580,7 @@ struct BatchPlan {
         rp.skip = request.skip.value_or(0);
         rp.why_found = request.why_found;
         rp.select = request.select;
+        if (vhost::request_explains(request)) rp.explain = std::make_shared<const vhost::Request>(request), rp.explain_asked = true;
         if (!request.search_req) throw InvalidRequest("search_req is None, but is required in search");
         {  // the top-k heap: merged in shared memory up to 256 keys, in global memory up to 4096 (one device only: shards gather every heap)
             const uint64_t limit = ix->n_shards > 1 ? vdev::kMaxK : vdev::kMaxKLarge;

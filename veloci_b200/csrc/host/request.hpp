@@ -145,6 +145,17 @@ struct Request {
     bool explain = false;
 };
 
+// RequestSearchPart::is_explain (search_request.rs:182-184), and whether a request asks for explanations anywhere: its own
+// `explain` (merged into every part, execution_plan.rs:46-90) or a part's own options.
+inline bool part_explains(const SearchPart& p) { return p.options.present && p.options.explain; }
+inline bool tree_explains(const SearchRequest& r) {
+    if (r.kind == SearchRequest::Search) return part_explains(r.part);
+    for (auto& q : r.queries)
+        if (tree_explains(q)) return true;
+    return false;
+}
+inline bool request_explains(const Request& r) { return r.explain || (r.search_req && tree_explains(*r.search_req)); }
+
 // ------------------------------------------------------------- parsing ------
 namespace detail {
 inline const vjson::Value* field(const vjson::Value& o, const char* k) {

@@ -6,6 +6,7 @@
 
 #include "../../../include/veloci_b200.h"
 #include "engine.hpp"
+#include "explain.hpp"
 #include "highlight.hpp"
 #include "read_document.hpp"
 
@@ -97,6 +98,14 @@ inline std::string result_docs(vdev::Batch& b, uint32_t q) {
         if (rp.select) term_ids = why_found_term_ids(b, q);  // with `select` the texts are highlighted by token ids (why_found.rs:11-49)
         else terms = why_found_terms(b, q);
     }
+    // DocWithHit::explain (search.rs:86,96): the hit's explanations, null when the request did not ask or they cannot be rebuilt
+    std::unique_ptr<vexplain::Explainer> explainer;
+    if (rp.explain && n) {
+        try {
+            explainer.reset(new vexplain::Explainer(b, q));
+        } catch (const vplan::Unsupported&) {
+        }
+    }
     std::string out = "{\"num_hits\":" + std::to_string(num_hits) + ",\"data\":[";
     for (uint32_t i = 0; i < n; ++i) {
         const std::string doc = rp.select ? vjson::to_string(vhost::read_data(*b.ix->host, hits[i].id, *rp.select)) : b.ix->host->get_doc(hits[i].id);
@@ -108,6 +117,11 @@ inline std::string result_docs(vdev::Batch& b, uint32_t q) {
         out += "},\"why_found\":";
         if (rp.select) vhost::write_highlights(out, vhost::why_found_by_ids(*b.ix->host, hits[i].id, term_ids));
         else vhost::write_highlights(out, vhost::highlight_document(b.ix->host->metadata, doc, terms));
+        if (rp.explain_asked) {
+            out += ",\"explain\":";
+            if (explainer && i < explainer->walk().n_anchors() && explainer->walk().anchor(i) == hits[i].id) vexplain::Walk::write_items(out, explainer->walk().explain_anchor(i));
+            else out += "null";
+        }
         out += '}';
     }
     return out + "]}";

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <sstream>
 
+#include "../host/explain_walk.hpp"
 #include "../host/highlight.hpp"
 #include "../host/part_hits.hpp"
 #include "../host/query_generator.hpp"
@@ -122,6 +123,51 @@ int vidx_bound_part_hits(const char* dir, const char* part_json, const char* hit
         if (text.size() + 1 > outlen) throw std::runtime_error("output buffer too small");
         set_err(out, outlen, text.c_str());
         return 0;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
+        return 1;
+    }
+}
+
+// The product's explain walk (host/explain_walk.hpp) without a device, for the CPU tests that hold it against the oracle's
+// explain: `anchors_json` = the ids of the request's returned hits, `leaves_json` = per search part of the tree (tree order)
+// the [[term id, score], ...] hits of the bare part, which the device match delivers in the product; the posting weights
+// come from the index files here (the product looks them up on the device).  Writes {"<anchor>": [Explain, ...]}.
+int vidx_explain_walk(const char* dir, const char* request_json, const char* anchors_json, const char* leaves_json, char* out, size_t outlen) {
+    try {
+        std::unique_ptr<vhost::Persistence> p = vhost::Persistence::load(dir);
+        const vhost::Request request = vhost::read_request_json(request_json, strlen(request_json));
+        const vjson::Value av = vjson::parse(anchors_json, strlen(anchors_json));
+        const vjson::Value lv = vjson::parse(leaves_json, strlen(leaves_json));
+        std::vector<uint32_t> anchors;
+        for (const vjson::Value& a : av.arr) anchors.push_back((uint32_t)a.num);
+        vexplain::Walk walk(*p, request, anchors);
+        if (lv.arr.size() != walk.n_parts()) throw std::runtime_error("explain walk: one hit list per search part expected");
+        for (size_t i = 0; i < walk.n_parts(); ++i) {
+            std::vector<vdev::TermHit> raw;
+            for (const vjson::Value& h : lv.arr[i].arr) raw.push_back(vdev::TermHit{(uint32_t)h.arr.at(0).num, (float)h.arr.at(1).num});
+            std::sort(raw.begin(), raw.end(), [](const vdev::TermHit& a, const vdev::TermHit& b) { return a.id < b.id; });
+            const std::vector<vdev::TermHit>& hits = walk.set_hits(i, std::move(raw));
+            std::string path = walk.part(i).path;
+            if (!vfmt::ends_with(path, ".textindex")) path += ".textindex";
+            const vfmt::AnchorScoreView& store = p->get_token_to_anchor(path);
+            std::vector<float> weight(hits.size() * anchors.size(), -1.0f);
+            uint64_t postings = 0;
+            for (size_t t = 0; t < hits.size(); ++t)
+                store.for_each(hits[t].id, [&](uint32_t anchor, uint32_t raw_score) {
+                    ++postings;
+                    for (size_t a = 0; a < anchors.size(); ++a)
+                        if (anchors[a] == anchor) weight[t * anchors.size() + a] = (float)(_Float16)(float)raw_score / 100.0f;  // AnchorScore keeps an f16 (search_field.rs:426)
+                });
+            walk.set_weights(i, std::move(weight), postings);
+        }
+        const std::string text = walk.to_json();
+        if (text.size() + 1 > outlen) throw std::runtime_error("output buffer too small");
+        set_err(out, outlen, text.c_str());
+        return 0;
+    } catch (const vplan::Unsupported& e) {
+        set_err(out, outlen, e.what());
+        return 8;
     } catch (const std::exception& e) {
         set_err(out, outlen, e.what());
         return 1;
