@@ -136,6 +136,11 @@ inline void apply_token_value(const vhost::Persistence& host, const vhost::Searc
     if (!part.token_value) return;
     const vhost::BoostPart& tb = *part.token_value;
     const vhost::KeyValueStore& store = host.get_boost(tb.path + ".textindex.token_values.boost_valid_to_value");
+    if (tb.expression) {  // a malformed expression fails the part whether or not a hit carries a value
+        BoostStep probe;
+        memset(&probe, 0, sizeof probe);
+        vplan::parse_expression(*tb.expression, probe);
+    }
     for (TermHit& h : hits) {
         bool skip = false;
         if (tb.skip_when_score)
