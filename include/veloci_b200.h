@@ -307,6 +307,31 @@ int32_t vgpu_add_boost(vgpu_index* idx, const char* boost_json, vgpu_hitlist* in
 /* top_n_sort + apply_top_skip (src/search/sort.rs:5-22, src/search.rs:230-239). */
 int32_t vgpu_top_n(vgpu_index* idx, const vgpu_hitlist* in, uint32_t top, uint32_t skip, vgpu_hitlist* out);
 
+/* ---- step seam, device-resident -------------------------------------------
+ * The same steps over hit lists that stay in HBM between them ("device-resident handles between steps"; the
+ * reference passes owned SearchFieldResults from step to step over channels, src/plan_creator/plan_steps.rs:357-376).
+ * A vgpu_hitlist_dev holds the hits_scores of a SearchFieldResult on the index's device, by ascending anchor id; between
+ * two steps only the handles and the lists' lengths cross the bus.  ResolveTokenIdToAnchor starts from the (few) term hits
+ * of vgpu_field_search on the host; Union / Intersect / BoostPlanStepFromBoostRequest go from handles to a handle;
+ * vgpu_dev_top_n brings the k best hits back.  Handles belong to the index they were made on, which must outlive them;
+ * a sharded handle's lists hold the shard's anchors.  Whole requests should still go through vgpu_batch_execute, which
+ * fuses these steps into one pass per tile; the step symbols serve hosts that drive the reference's plan themselves. */
+typedef struct vgpu_hitlist_dev vgpu_hitlist_dev;
+int32_t vgpu_dev_upload(vgpu_index* idx, const vgpu_hitlist* in, vgpu_hitlist_dev** out);      /* hits of a host list (a repeated anchor keeps its largest score) */
+int32_t vgpu_dev_download(const vgpu_hitlist_dev* list, vgpu_hitlist* out);                     /* by ascending anchor id; released with vgpu_hitlist_free */
+uint32_t vgpu_dev_len(const vgpu_hitlist_dev* list);
+void vgpu_dev_free(vgpu_hitlist_dev* list);
+/* ResolveTokenIdToAnchor (src/search/search_field.rs:400-464; plan_steps.rs:155-167) */
+int32_t vgpu_dev_resolve_to_anchor(vgpu_index* idx, const char* part_json, const vgpu_hitlist* term_hits, vgpu_hitlist_dev** out);
+/* Union (src/search/set_op.rs:87-220): terms[i] = request.terms[0] of input i */
+int32_t vgpu_dev_union_hits_score(vgpu_index* idx, const vgpu_hitlist_dev* const* inputs, const char* const* terms, uint32_t n, vgpu_hitlist_dev** out);
+/* Intersect (src/search/set_op.rs:368-446) */
+int32_t vgpu_dev_intersect_hits_score(vgpu_index* idx, const vgpu_hitlist_dev* const* inputs, uint32_t n, vgpu_hitlist_dev** out);
+/* BoostPlanStepFromBoostRequest (add_boost, src/search/boost.rs:470-504) */
+int32_t vgpu_dev_add_boost(vgpu_index* idx, const char* boost_json, const vgpu_hitlist_dev* in, vgpu_hitlist_dev** out);
+/* top_n_sort + apply_top_skip (src/search/sort.rs:5-22, src/search.rs:230-239) */
+int32_t vgpu_dev_top_n(vgpu_index* idx, const vgpu_hitlist_dev* in, uint32_t top, uint32_t skip, vgpu_hitlist* out);
+
 /* ---- instrumentation ---------------------------------------------------------
  * Kernel launches issued by this library since process start, and per-phase device
  * time (CUDA events on the library's stream) of the last vgpu_batch_execute:

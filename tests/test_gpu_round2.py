@@ -763,3 +763,70 @@ def test_explain(gpu, native_libs):
     with pytest.raises(gpu.VelociGpuError) as e:
         bs.explain(0)
     assert e.value.status == 8
+
+
+def test_device_resident_step_chain(gpu, sharded_corpus):
+    """the step seam over hit lists that stay on the device (vgpu_dev_*).  FieldSearch's term hits ->
+    ResolveTokenIdToAnchor per part -> Union / Intersect -> BoostPlanStepFromBoostRequest -> top_n, every intermediate
+    list a handle: each step against the same step over host lists (ids and score bits identical), the chain's top-k
+    against the whole request through vgpu_batch_execute and against the oracle."""
+    from test_gpu_parity import assert_same_topk
+
+    d, _ = sharded_corpus
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    bits = lambda hits: [(int(a), int(np.float32(s).view(np.uint32))) for a, s in hits]
+    boost = {"path": "commonness", "boost_fun": "Log10", "param": 1}
+    reqs = helpers.synthetic_requests(num_queries=12, query_kind="or3", levenshtein=1, query_seed=61, **SHARDED)
+    reqs += helpers.synthetic_requests(num_queries=12, query_kind="and", levenshtein=1, query_seed=62, **SHARDED)
+    n_hits_seen = 0
+    for text in reqs:
+        r = json.loads(text)
+        is_or = "or" in r["search_req"]
+        parts = [q["search"] for q in r["search_req"]["or" if is_or else "and"]["queries"]]
+        dev_lists, host_lists = [], []
+        for part in parts:
+            term_hits, _ = index.field_search(part)
+            dl = index.dev_resolve_to_anchor(part, term_hits)
+            hl, _ = index.resolve_to_anchor(part, term_hits)
+            assert len(dl) == len(hl) and bits(dl.download()) == bits(hl), part
+            dev_lists.append(dl), host_lists.append(hl)
+        terms = [p["terms"][0] for p in parts]
+        if is_or:
+            merged = index.dev_union_hits_score(dev_lists, terms)
+            assert bits(merged.download()) == bits(index.union_hits_score(host_lists, terms)), text
+        else:
+            merged = index.dev_intersect_hits_score(dev_lists)
+            assert bits(merged.download()) == bits(index.intersect_hits_score(host_lists)), text
+        n_hits_seen += len(merged)
+        if "boost" in r:
+            boosted = index.dev_add_boost(r["boost"][0], merged)
+            assert bits(boosted.download()) == bits(index.add_boost(r["boost"][0], merged.download())), text
+            merged = boosted
+        top = index.dev_top_n(merged, 10)
+        whole = index.search(json.dumps({k: v for k, v in r.items() if k != "facets"}))
+        assert_same_topk(top, whole["data"], ctx=text)
+        ref = oracle.search({k: v for k, v in r.items() if k != "facets"})
+        assert len(merged) == ref["num_hits"] == whole["num_hits"], text
+        assert_same_topk(top, [(h[0], np.float32(h[1])) for h in ref["data"]], ctx=text)
+        assert bits(index.dev_top_n(merged, 4, 3)) == bits(index.top_n(merged.download(), 4, 3)), text
+    assert n_hits_seen > 10000
+    # host lists in and out: a repeated anchor keeps its largest score, order is by anchor id, negative scores survive
+    ups = [(70, 2.5), (3, 1.0), (70, 4.0), (119999, 0.0), (5, -3.0)]
+    up = index.dev_upload(ups)
+    assert up.download() == [(3, 1.0), (5, -3.0), (70, 4.0), (119999, 0.0)] and len(up) == 4
+    other = index.dev_upload([(5, 2.0), (9, 1.0)])
+    assert bits(index.dev_union_hits_score([up, other], ["a", "b"]).download()) == bits(index.union_hits_score([up.download(), other.download()], ["a", "b"]))
+    assert bits(index.dev_intersect_hits_score([up, other]).download()) == bits(index.intersect_hits_score([up.download(), other.download()]))
+    assert index.dev_union_hits_score([], []).download() == [] and len(index.dev_upload([])) == 0
+    assert bits(index.dev_union_hits_score([other], ["a"]).download()) == bits(other.download())  # one input passes through
+    # a handle belongs to its index; a shard's lists hold the shard's anchors
+    second = gpu.Index(d, shard_rank=1, n_shards=2)
+    with pytest.raises(gpu.VelociGpuError) as e:
+        second.dev_union_hits_score([up, other], ["a", "b"])
+    assert e.value.status == 1
+    part = json.loads(reqs[0])["search_req"]["or"]["queries"][0]["search"]
+    term_hits, _ = index.field_search(part)
+    first = gpu.Index(d, shard_rank=0, n_shards=2)
+    halves = [s.dev_resolve_to_anchor(part, term_hits).download() for s in (first, second)]
+    assert bits(halves[0] + halves[1]) == bits(index.resolve_to_anchor(part, term_hits)[0])
+    assert all(a < SHARDED["num_docs"] // 2 for a, _ in halves[0]) and all(a >= SHARDED["num_docs"] // 2 for a, _ in halves[1])

@@ -112,6 +112,17 @@ def load_library():
     L.vgpu_facet.argtypes = [vp, cp, P(u32), u32, P(_Suggestions)]
     L.vgpu_add_boost.argtypes = [vp, cp, P(_HitList)]
     L.vgpu_top_n.argtypes = [vp, P(_HitList), u32, u32, P(_HitList)]
+    L.vgpu_dev_upload.argtypes = [vp, P(_HitList), P(vp)]
+    L.vgpu_dev_download.argtypes = [vp, P(_HitList)]
+    L.vgpu_dev_len.argtypes = [vp]
+    L.vgpu_dev_len.restype = ctypes.c_uint32
+    L.vgpu_dev_free.argtypes = [vp]
+    L.vgpu_dev_free.restype = None
+    L.vgpu_dev_resolve_to_anchor.argtypes = [vp, cp, P(_HitList), P(vp)]
+    L.vgpu_dev_union_hits_score.argtypes = [vp, P(vp), P(cp), u32, P(vp)]
+    L.vgpu_dev_intersect_hits_score.argtypes = [vp, P(vp), u32, P(vp)]
+    L.vgpu_dev_add_boost.argtypes = [vp, cp, vp, P(vp)]
+    L.vgpu_dev_top_n.argtypes = [vp, vp, u32, u32, P(_HitList)]
     L.vgpu_suggest.argtypes = [vp, cp, P(_Suggestions)]
     L.vgpu_suggest_part.argtypes = [vp, cp, P(_Suggestions)]
     L.vgpu_get_doc.argtypes = [vp, ctypes.c_uint32, P(vp)]
@@ -196,6 +207,33 @@ def _from_hitlist(L, hl):
     ids = [hl.ids[i] for i in range(hl.n_ids)]
     L.vgpu_hitlist_free(ctypes.byref(hl))
     return hits, ids
+
+
+class DeviceHitList:
+    """hits_scores of a plan step kept on the index's device for the next step (vgpu_hitlist_dev)."""
+
+    def __init__(self, index, handle):
+        self.index, self.L, self.h = index, index.L, handle
+
+    def __len__(self):
+        return int(self.L.vgpu_dev_len(self.h))
+
+    def download(self):
+        """[(anchor id, score)] by ascending anchor id."""
+        out = _HitList()
+        _check(self.L.vgpu_dev_download(self.h, ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[0]
+
+    def close(self):
+        if self.h:
+            self.L.vgpu_dev_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Batch:
@@ -642,6 +680,41 @@ class Index:
         arr = (_HitList * max(1, len(keep)))(*keep)
         out = _HitList()
         _check(self.L.vgpu_text_locality(self.h, path.encode("utf-8"), arr, len(keep), ctypes.byref(out)))
+        return _from_hitlist(self.L, out)[0]
+
+    # ---- step seam, device-resident: lists stay in HBM between the steps
+    def _dev(self, call):
+        out = ctypes.c_void_p()
+        _check(call(ctypes.byref(out)))
+        return DeviceHitList(self, out)
+
+    def dev_upload(self, hits):
+        inp = _to_hitlist(hits)
+        return self._dev(lambda out: self.L.vgpu_dev_upload(self.h, ctypes.byref(inp), out))
+
+    def dev_resolve_to_anchor(self, part, term_hits):
+        inp = _to_hitlist(term_hits)
+        text = json.dumps(part, ensure_ascii=False).encode("utf-8")
+        return self._dev(lambda out: self.L.vgpu_dev_resolve_to_anchor(self.h, text, ctypes.byref(inp), out))
+
+    def dev_union_hits_score(self, lists, terms):
+        n = len(lists)
+        arr = (ctypes.c_void_p * max(1, n))(*[l.h for l in lists])
+        tarr = (ctypes.c_char_p * max(1, n))(*[t.encode("utf-8") for t in terms])
+        return self._dev(lambda out: self.L.vgpu_dev_union_hits_score(self.h, arr, tarr, n, out))
+
+    def dev_intersect_hits_score(self, lists):
+        n = len(lists)
+        arr = (ctypes.c_void_p * max(1, n))(*[l.h for l in lists])
+        return self._dev(lambda out: self.L.vgpu_dev_intersect_hits_score(self.h, arr, n, out))
+
+    def dev_add_boost(self, boost, hits):
+        text = json.dumps(boost).encode("utf-8")
+        return self._dev(lambda out: self.L.vgpu_dev_add_boost(self.h, text, hits.h, out))
+
+    def dev_top_n(self, hits, top, skip=0):
+        out = _HitList()
+        _check(self.L.vgpu_dev_top_n(self.h, hits.h, top, skip, ctypes.byref(out)))
         return _from_hitlist(self.L, out)[0]
 
     def top_n(self, hits, top, skip=0):

@@ -138,6 +138,13 @@ void launch_boost_to_anchor(cudaStream_t st, const BoostListMember* members, uin
 // the ids half of resolve_token_to_anchor (search_field.rs:468-498): one block per member
 void launch_ids_to_anchor(cudaStream_t st, const IdsMember* members, uint32_t n_members, const ListArgs& a);
 
+// ---- lists.cu: device-resident hit lists of the step seam ----
+// per-tile offsets of an anchor-sorted list (row[0 .. n_tiles]), as prepare_lists builds them on the host for host lists
+void launch_list_bucket(cudaStream_t st, const SparseEntry* entries, uint32_t n, uint32_t anchor_lo, uint32_t tile_log2, uint32_t n_tiles, uint32_t* row);
+// the hits a step emitted ((key << 32) | anchor, unordered) as an anchor-sorted SparseEntry list in `out`; `buf` is overwritten, `alt` scratch
+size_t emitted_sort_temp_bytes(uint32_t n);
+cudaError_t launch_emitted_to_list(cudaStream_t st, unsigned long long* buf, unsigned long long* alt, unsigned long long* out, uint32_t n, void* temp, size_t temp_bytes);
+
 // explain: weight[t * n_anchors + a] = posting weight of term t on anchor a, -1 without a posting (one thread per pair)
 void launch_posting_lookup(cudaStream_t st, const PostingsView& pv, const uint32_t* terms, uint32_t n_terms, const uint32_t* anchors, uint32_t n_anchors, float* weight);
 

@@ -30,6 +30,20 @@ struct ExplicitList {  // a caller-provided hit list used as a leaf (step seam)
     std::vector<float> scores;
     std::vector<uint32_t> raw_keys;  // when given: the entries' keys as they are (a 1:n boost list: 0x7FFFFFFF - value id) instead of score keys
     uint32_t part_flags = 0;         // PartFlags of the leaf's part (kPartList | kPartListBoost for such a list)
+    // a list that is resident on the device (DeviceHitList): anchor-sorted SparseEntry array; the host vectors stay empty
+    const SparseEntry* dev = nullptr;
+    uint32_t dev_n = 0;
+    bool dev_nonneg = true;
+};
+
+// Hits of a plan step kept on the device for the next step (vgpu_hitlist_dev): anchor-sorted (anchor, score key) entries,
+// the form the tile path reads sparse postings in.
+struct DeviceHitList {
+    DeviceIndex* ix = nullptr;
+    DevBuf<unsigned long long> entries;  // SparseEntry {anchor, key}, anchors ascending and unique
+    uint32_t n = 0;
+    bool nonneg = true;  // no entry has a negative score (cheap key decode downstream)
+    const SparseEntry* data() const { return reinterpret_cast<const SparseEntry*>(entries.p); }
 };
 
 static const int kPhases = 6;
@@ -318,9 +332,16 @@ struct Batch {
         memset(&qp, 0, sizeof qp);
         qp.leaf_begin = 0, qp.n_leaves = (uint32_t)lists.size(), qp.k = k, qp.active = 1, qp.emit_all = all_hits ? 1 : 0;
         qp.nonneg = 1;
-        for (auto& l : lists)
+        bool on_device = false;
+        for (auto& l : lists) {
             for (float sc : l.scores)
                 if (!(sc >= 0.0f)) qp.nonneg = 0;
+            if (l.dev || l.dev_n) on_device = true;
+            if (!l.dev_nonneg) qp.nonneg = 0;
+        }
+        if (on_device)
+            for (auto& l : lists)
+                if (!l.anchors.empty()) throw std::runtime_error("a step takes its lists either from the host or from the device");
         for (size_t pc = 0; pc < code.size();) {  // (the 1:n boost ops of the program: the tile kernel keeps hit bitmaps for them)
             const uint32_t op = code[pc];
             if (op == kOpLeafBoost) ++qp.n_leaf_boosts;
@@ -343,7 +364,7 @@ struct Batch {
             plan.parts.push_back(pq);
             plan.part_dict.push_back(0);
             plan.leaf_part.push_back((uint32_t)i);
-            total += lists[i].anchors.size();
+            total += lists[i].anchors.size() + lists[i].dev_n;
         }
         vplan::RequestPlan rp;
         if (facet) {  // get_facet over the list's ids (facet.rs:31-73)
@@ -358,6 +379,23 @@ struct Batch {
         n = 1;
         emit_capacity = total;
         upload_plan();
+        if (on_device) {
+            // device-resident lists: their entries are gathered device to device, their tile offsets found by list_bucket_kernel
+            std::vector<PartSlices> slices(lists.size());
+            d_bucket.alloc((size_t)lists.size() * (n_tiles + 1));
+            d_sparse.alloc((size_t)total + 1);
+            uint64_t base = 0;
+            for (size_t i = 0; i < lists.size(); ++i) {
+                const ExplicitList& l = lists[i];
+                slices[i].m_begin = 0, slices[i].n_match = 1, slices[i].n_dense = 0, slices[i].sparse_row = (uint32_t)i, slices[i].sparse_base = base;
+                if (l.dev_n) VDEV_CUDA(cudaMemcpyAsync(d_sparse.p + base, l.dev, (size_t)l.dev_n * sizeof(SparseEntry), cudaMemcpyDeviceToDevice, stream));
+                launch_list_bucket(stream, d_sparse.p + base, l.dev_n, (uint32_t)ix->anchor_lo, tile_log2, n_tiles, d_bucket.p + i * (n_tiles + 1));
+                base += l.dev_n;
+            }
+            UploadScope staged(stream);
+            d_slices.upload(slices);
+            return;
+        }
         // tile buckets of the lists, built on the host (step seam inputs are small)
         std::vector<uint32_t> bucket((size_t)lists.size() * (n_tiles + 1), 0);
         std::vector<SparseEntry> sparse;
@@ -1019,6 +1057,26 @@ struct Batch {
         if (cnt) VDEV_CUDA(cudaMemcpy(buf.data(), d_emit.p, cnt * 8, cudaMemcpyDeviceToHost));
         std::sort(buf.begin(), buf.end(), [](unsigned long long a, unsigned long long b) { return (uint32_t)a < (uint32_t)b; });
         for (auto v : buf) hits.push_back(Hit{(uint32_t)(v & 0xFFFFFFFFull), vbit::key_score((uint32_t)(v >> 32))});
+    }
+
+    // Step seam, device-resident: every hit of request 0 stays on the device as an anchor-sorted list (only the count is read back).
+    void take_emitted(DeviceHitList& out) {
+        unsigned long long cnt = 0;
+        VDEV_CUDA(cudaMemcpy(&cnt, d_counters.p + 4, 8, cudaMemcpyDeviceToHost));
+        if (cnt > emit_capacity) throw std::runtime_error("emit buffer overflow");
+        if (cnt >= (1ull << 31)) throw vplan::Unsupported("hit lists of 2^31 entries or more");
+        out.ix = ix;
+        out.n = (uint32_t)cnt;
+        out.nonneg = plan.programs[0].nonneg != 0 && plan.programs[0].n_boosts == 0;  // (a boost may turn a score negative)
+        out.entries.alloc((size_t)cnt + 1);
+        if (!cnt) return;
+        DevBuf<unsigned long long> alt;
+        DevBuf<unsigned char> temp;
+        alt.alloc((size_t)cnt);
+        const size_t temp_bytes = emitted_sort_temp_bytes((uint32_t)cnt);
+        temp.alloc(temp_bytes + 1);
+        VDEV_CUDA(launch_emitted_to_list(stream, d_emit.p, alt.p, out.entries.p, (uint32_t)cnt, temp.p, temp_bytes));
+        VDEV_CUDA(cudaStreamSynchronize(stream));
     }
 };
 

@@ -715,4 +715,130 @@ inline void top_n(vdev::DeviceIndex& ix, const vgpu_hitlist& in, uint32_t top, u
     out.ids = dup_array(std::vector<uint32_t>()), out.n_ids = 0;
 }
 
+// ---- device-resident step seam ("device-resident handles between steps") -------------------------------
+// The same steps over hit lists that stay on the device between them (vdev::DeviceHitList: anchor-sorted (anchor, score
+// key) entries, consumed by the tile path like the postings of a rarely matched term).  Only sizes cross the bus between
+// two steps; the chain ResolveTokenIdToAnchor -> Union / Intersect -> BoostPlanStepFromBoostRequest -> top_n runs from
+// the matched terms to the k best hits without its intermediate lists leaving HBM.
+
+inline vdev::ExplicitList dev_leaf(vdev::DeviceIndex& ix, const vdev::DeviceHitList& h) {
+    if (h.ix != &ix) throw vplan::InvalidRequest("hit list handle of another index");
+    vdev::ExplicitList l;
+    l.dev = h.data(), l.dev_n = h.n, l.dev_nonneg = h.nonneg;
+    return l;
+}
+
+inline void run_lists_dev(vdev::DeviceIndex& ix, const std::vector<vdev::ExplicitList>& lists, const std::vector<uint32_t>& code, const std::vector<vdev::BoostStep>& boosts, vdev::DeviceHitList& out) {
+    vdev::Batch b;
+    b.prepare_lists(&ix, lists, code, boosts, 0, true);
+    b.execute();
+    b.take_emitted(out);
+}
+
+// host list -> handle: by anchor id, a repeated anchor keeps its largest score (resolve_token_to_anchor's dedup), anchors
+// outside the handle's shard are dropped
+inline void dev_upload(vdev::DeviceIndex& ix, const vgpu_hitlist& in, vdev::DeviceHitList& out) {
+    std::vector<std::pair<uint32_t, float>> hits;
+    for (uint32_t i = 0; i < in.n_hits; ++i)
+        if (in.hits[i].id >= ix.anchor_lo && in.hits[i].id < ix.anchor_hi) hits.emplace_back(in.hits[i].id, in.hits[i].score);
+    std::stable_sort(hits.begin(), hits.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    std::vector<unsigned long long> entries;
+    out.nonneg = true;
+    for (size_t i = 0; i < hits.size(); ++i) {
+        float score = hits[i].second;
+        while (i + 1 < hits.size() && hits[i + 1].first == hits[i].first) score = std::max(score, hits[++i].second);
+        if (!(score >= 0.0f)) out.nonneg = false;
+        uint32_t key = vbit::score_key(score);
+        if (key == 0) key = 1;
+        entries.push_back(((unsigned long long)key << 32) | hits[i].first);  // SparseEntry {anchor, key}, little endian
+    }
+    VDEV_CUDA(cudaSetDevice(ix.device));
+    out.ix = &ix;
+    out.n = (uint32_t)entries.size();
+    out.entries.upload(entries);
+}
+
+inline void dev_download(const vdev::DeviceHitList& h, vgpu_hitlist& out) {
+    memset(&out, 0, sizeof out);
+    std::vector<unsigned long long> entries(h.n);
+    if (h.n) {
+        VDEV_CUDA(cudaSetDevice(h.ix->device));
+        VDEV_CUDA(cudaMemcpy(entries.data(), h.entries.p, (size_t)h.n * 8, cudaMemcpyDeviceToHost));
+    }
+    std::vector<vgpu_hit> hits;
+    for (unsigned long long v : entries) hits.push_back(vgpu_hit{(uint32_t)(v & 0xFFFFFFFFull), vbit::key_score((uint32_t)(v >> 32))});
+    out.hits = dup_array(hits), out.n_hits = (uint32_t)hits.size();
+    out.ids = dup_array(std::vector<uint32_t>()), out.n_ids = 0;
+}
+
+// ResolveTokenIdToAnchor (search_field.rs:400-464) from the few (term id, score) hits of a part to a list on the device
+inline void dev_resolve_to_anchor(vdev::DeviceIndex& ix, const char* part_json, const vgpu_hitlist& in, vdev::DeviceHitList& out) {
+    vhost::SearchPart part = parse_part(part_json);
+    std::vector<uint32_t> terms(in.n_hits);
+    std::vector<float> scores(in.n_hits);
+    for (uint32_t i = 0; i < in.n_hits; ++i) terms[i] = in.hits[i].id, scores[i] = in.hits[i].score;
+    vdev::Batch b;
+    b.prepare_term_hits(&ix, part, terms, scores);
+    b.execute();
+    b.take_emitted(out);
+}
+
+// Union / Intersect (set_op.rs:87-220, :368-446) over handles; the inputs' lengths decide the intersect's order as in the reference
+inline void dev_set_op(vdev::DeviceIndex& ix, const vdev::DeviceHitList* const* inputs, const char* const* terms, uint32_t n, bool is_union, vdev::DeviceHitList& out) {
+    if (n == 0) {
+        VDEV_CUDA(cudaSetDevice(ix.device));
+        out.ix = &ix, out.n = 0, out.nonneg = true;
+        out.entries.alloc(1);
+        return;
+    }
+    if (n > vdev::kMaxLeaves) throw vplan::Unsupported("more than " + std::to_string(vdev::kMaxLeaves) + " inputs");
+    std::vector<vdev::ExplicitList> lists;
+    for (uint32_t i = 0; i < n; ++i) lists.push_back(dev_leaf(ix, *inputs[i]));
+    std::vector<uint32_t> code;
+    for (uint32_t i = 0; i < n; ++i) code.push_back(vdev::kOpLeaf), code.push_back(i);
+    if (n > 1) {
+        if (is_union) {
+            std::vector<std::string> ts;
+            for (uint32_t i = 0; i < n; ++i) ts.push_back(terms && terms[i] ? terms[i] : "");
+            std::vector<std::string> sorted = ts;
+            std::sort(sorted.begin(), sorted.end());
+            sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+            code.push_back(vdev::kOpUnion), code.push_back(n), code.push_back((uint32_t)sorted.size());
+            for (uint32_t i = 0; i < n; ++i) code.push_back((uint32_t)(std::find(sorted.begin(), sorted.end(), ts[i]) - sorted.begin()));
+        } else {
+            uint32_t shortest = 0;
+            for (uint32_t i = 1; i < n; ++i)
+                if (inputs[i]->n < inputs[shortest]->n) shortest = i;
+            code.push_back(vdev::kOpIntersect), code.push_back(n);
+            for (uint32_t i = 0; i + 1 < n; ++i) code.push_back(i == shortest ? n - 1 : i);
+            code.push_back(shortest);
+            for (uint32_t i = 0; i < n; ++i) code.push_back(vdev::kNoValue - 1);  // order is final: not a leaf reference
+        }
+    }
+    run_lists_dev(ix, lists, code, {}, out);
+}
+
+// BoostPlanStepFromBoostRequest (add_boost, boost.rs:470-504)
+inline void dev_add_boost(vdev::DeviceIndex& ix, const char* boost_json, const vdev::DeviceHitList& in, vdev::DeviceHitList& out) {
+    vhost::BoostPart bp = parse_boost(boost_json);
+    vplan::BatchPlan plan;
+    plan.ix = &ix;
+    vdev::BoostStep step = plan.make_boost(bp);
+    run_lists_dev(ix, {dev_leaf(ix, in)}, {vdev::kOpLeaf, 0u}, {step}, out);
+}
+
+// top_n_sort + apply_top_skip (sort.rs:5-22, search.rs:230-239): the k best hits of a handle, to the host
+inline void dev_top_n(vdev::DeviceIndex& ix, const vdev::DeviceHitList& in, uint32_t top, uint32_t skip, vgpu_hitlist& out) {
+    if ((uint64_t)top + skip > (ix.n_shards > 1 ? vdev::kMaxK : vdev::kMaxKLarge)) throw vplan::Unsupported("top + skip above " + std::to_string(ix.n_shards > 1 ? vdev::kMaxK : vdev::kMaxKLarge));
+    vdev::Batch b;
+    b.prepare_lists(&ix, {dev_leaf(ix, in)}, {vdev::kOpLeaf, 0u}, {}, top + skip, false);
+    b.execute();
+    std::vector<vgpu_hit> all, hits;
+    b.download_hits(0, false, all);
+    for (uint32_t i = skip; i < all.size() && hits.size() < top; ++i) hits.push_back(all[i]);
+    memset(&out, 0, sizeof out);
+    out.hits = dup_array(hits), out.n_hits = (uint32_t)hits.size();
+    out.ids = dup_array(std::vector<uint32_t>()), out.n_ids = 0;
+}
+
 }  // namespace vsteps
