@@ -647,22 +647,39 @@ __device__ __forceinline__ void list_emit(const ListArgs& a, uint32_t list_part,
     if (a.sparse) a.sparse[a.sparse_base[list_part] + at] = SparseEntry{anchor, key};
 }
 
-// One block per phrase_boosts entry: for every (t1, t2) of the two parts' matched terms, the anchors of the pair.
+// One block per phrase_boosts entry: for every (t1, t2) of the two parts' matched terms, the anchors of the pair.  The
+// threads look the pairs up, one each; the anchor lists of the pairs that exist are then emitted by the whole block (a
+// pair of two head terms has tens of thousands of anchors: emitted by the thread that found it, it alone set the time
+// of the launch -- 48.7 ms of a 74 ms step on the config-3 shape, profiles/r02ac_config3_summary.md).
 __global__ void __launch_bounds__(128) phrase_pairs_kernel(const PhraseMember* __restrict__ members, ListArgs a) {
+    __shared__ uint32_t s_begin[128], s_end[128];
+    __shared__ uint32_t s_found;
     const PhraseMember m = members[blockIdx.x];
     const uint32_t b1 = a.part_begin[m.part1], n1 = a.part_begin[m.part1 + 1] - b1;
     const uint32_t b2 = a.part_begin[m.part2], n2 = a.part_begin[m.part2 + 1] - b2;
     const unsigned long long pairs = (unsigned long long)n1 * n2;
-    for (unsigned long long x = threadIdx.x; x < pairs; x += blockDim.x) {
-        const uint64_t key = ((uint64_t)a.g_term[b1 + (uint32_t)(x / n2)] << 32) | a.g_term[b2 + (uint32_t)(x % n2)];
-        uint32_t lo = 0, hi = m.store.n;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (m.store.keys[mid] < key) lo = mid + 1;
-            else hi = mid;
+    for (unsigned long long base = 0; base < pairs; base += blockDim.x) {
+        if (threadIdx.x == 0) s_found = 0;
+        __syncthreads();
+        const unsigned long long x = base + threadIdx.x;
+        if (x < pairs) {
+            const uint64_t key = ((uint64_t)a.g_term[b1 + (uint32_t)(x / n2)] << 32) | a.g_term[b2 + (uint32_t)(x % n2)];
+            uint32_t lo = 0, hi = m.store.n;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (m.store.keys[mid] < key) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo < m.store.n && m.store.keys[lo] == key && m.store.off[lo + 1] > m.store.off[lo]) {
+                const uint32_t slot = atomicAdd(&s_found, 1u);
+                s_begin[slot] = m.store.off[lo], s_end[slot] = m.store.off[lo + 1];
+            }
         }
-        if (lo >= m.store.n || m.store.keys[lo] != key) continue;
-        for (uint32_t i = m.store.off[lo]; i < m.store.off[lo + 1]; ++i) list_emit(a, m.list_part, m.store.anchors[i], 0x80000000u);
+        __syncthreads();
+        const uint32_t found = s_found;
+        for (uint32_t r = 0; r < found; ++r)
+            for (uint32_t i = s_begin[r] + threadIdx.x; i < s_end[r]; i += blockDim.x) list_emit(a, m.list_part, m.store.anchors[i], 0x80000000u);
+        __syncthreads();
     }
 }
 
