@@ -752,7 +752,7 @@ __device__ __forceinline__ uint32_t run_task(const TileArgs& a, const ItemCtx& c
     return present;
 }
 
-__global__ void __launch_bounds__(kTileThreads, 1) tile_eval_kernel(TileArgs a) {
+__global__ void __launch_bounds__(kTileThreads) tile_eval_kernel(TileArgs a) {
     extern __shared__ __align__(16) uint32_t arr[];  // [max_leaves][tile], all zero between items
     __shared__ ItemRec s_item[2];
     __shared__ unsigned long long s_item_idx[2];
