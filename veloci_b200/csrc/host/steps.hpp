@@ -85,7 +85,7 @@ inline std::map<std::string, std::set<uint32_t>> why_found_term_ids(vdev::Batch&
 // search::to_search_result (src/search.rs:65-110): the documents of request q's hits -- from the document store, or rebuilt
 // from the indices when the request has `select` -- each with its hit and, when the request asked for why_found, the
 // highlighted texts of the matched terms.
-// {"num_hits": n, "data": [{"doc": {..}, "hit": {"id": .., "score": ..}, "why_found": {"field": ["<b>..</b>"]}}]}
+// {"num_hits": n, "execution_time_ns": t, "data": [{"doc": {..}, "hit": {"id": .., "score": ..}, "why_found": {"field": ["<b>..</b>"]}, "explain": [..]}]}
 inline std::string result_docs(vdev::Batch& b, uint32_t q) {
     const vplan::RequestPlan& rp = b.plan.requests[q];
     uint64_t num_hits = 0;
@@ -106,7 +106,11 @@ inline std::string result_docs(vdev::Batch& b, uint32_t q) {
         } catch (const vplan::Unsupported&) {
         }
     }
-    std::string out = "{\"num_hits\":" + std::to_string(num_hits) + ",\"data\":[";
+    // SearchResultWithDoc::execution_time_ns (search.rs:226, search_result_with_doc.rs): the requests of a batch are answered
+    // together, so every one of them reports the device time of the batch's last execute
+    double batch_ms = 0.0;
+    for (int p = 0; p < vdev::kPhases; ++p) batch_ms += b.phase_ms[p];
+    std::string out = "{\"num_hits\":" + std::to_string(num_hits) + ",\"execution_time_ns\":" + std::to_string((uint64_t)(batch_ms * 1.0e6)) + ",\"data\":[";
     for (uint32_t i = 0; i < n; ++i) {
         const std::string doc = rp.select ? vjson::to_string(vhost::read_data(*b.ix->host, hits[i].id, *rp.select)) : b.ix->host->get_doc(hits[i].id);
         if (i) out += ',';
