@@ -218,3 +218,14 @@ TEST_WHYFOUND_DOCS = [
     },
     {"buch": "Taschenbuch (kartoniert)", "viele": ["super treffers"]},
 ]
+
+
+# ---- tests/all/test_code_search.rs:11-41
+TEST_CODE_CONFIG = {
+    "*GLOBAL*": {"features": ["All"]},
+    "filepath": {"fulltext": {"tokenize": True, "tokenize_on_chars": ["/", "\\"]}},
+    "filename": {"fulltext": {"tokenize": True}},
+    "line": {"fulltext": {"tokenize": True}},
+    "line_number": dict(BOOST),
+}
+TEST_CODE_DOCS = [{"line_number": 1, "line": "function myfun(param1: Type1)", "filename": "cool.ts", "filepath": "all/the/path"}]

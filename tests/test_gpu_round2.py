@@ -830,3 +830,24 @@ def test_device_resident_step_chain(gpu, sharded_corpus):
     halves = [s.dev_resolve_to_anchor(part, term_hits).download() for s in (first, second)]
     assert bits(halves[0] + halves[1]) == bits(index.resolve_to_anchor(part, term_hits)[0])
     assert all(a < SHARDED["num_docs"] // 2 for a, _ in halves[0]) and all(a >= SHARDED["num_docs"] // 2 for a, _ in halves[1])
+
+
+def test_code_search_on_the_gpu(gpu, native_libs):
+    """tests/all/test_code_search.rs on the device: regex parts given directly and `*` patterns through the query generator
+    (four-field `or`s of regex parts), on the reference's one-line corpus; hits, scores and the document against the oracle
+    (tests/test_code_search.py holds the same requests against the oracle alone)."""
+    from test_code_search import API_CASES, GENERATOR_CASES, LINE, generated_request, make_code_index
+    from test_gpu_parity import assert_same_topk
+
+    d, cat = make_code_index()
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    reqs = [r for r, _ in API_CASES] + [generated_request(d, cat, p) for p, _ in GENERATOR_CASES]
+    want = [n for _, n in API_CASES] + [n for _, n in GENERATOR_CASES]
+    b = index.prepare([json.dumps(r, ensure_ascii=False) for r in reqs]).execute()
+    for q, (r, n) in enumerate(zip(reqs, want)):
+        assert b.status(q) == 0, (r, b.message(q))
+        got, ref = b.result(q), oracle.search(r)
+        assert got["num_hits"] == ref["num_hits"] and len(got["data"]) == n, r
+        assert_same_topk(got["data"], [(h[0], np.float32(h[1])) for h in ref["data"]], ctx=r)
+        if n:
+            assert b.result_docs(q)["data"][0]["doc"]["line"] == LINE
