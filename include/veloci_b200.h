@@ -193,6 +193,12 @@ typedef struct vgpu_suggestions {
 } vgpu_suggestions;
 int32_t vgpu_suggest(vgpu_index* idx, const char* request_json, vgpu_suggestions* out);
 int32_t vgpu_suggest_part(vgpu_index* idx, const char* part_json, vgpu_suggestions* out);
+/* search_field::highlight (src/search/search_field.rs:232-245): the texts of the part's field that it hits, the hit tokens
+ * tagged (`snippet: true`; `snippet_info` = {num_words_around_snippet, snippet_start_tag, snippet_end_tag, snippet_connector,
+ * max_snippets}, src/search/request/snippet_info.rs), best score first, the part's skip / top applied.  The part's terms are
+ * normalised first (util::normalize_text, src/util.rs:11-30).  `out->items[i]`: text = the highlighted text, id = its text id.
+ * Released with vgpu_suggestions_free. */
+int32_t vgpu_highlight(vgpu_index* idx, const char* part_json, vgpu_suggestions* out);
 void vgpu_suggestions_free(vgpu_suggestions* s);
 
 /* ---- request generation (host side, no kernel) ------------------------------

@@ -26,6 +26,7 @@ def _index_lib():
     lib.vidx_add_token_values.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_bound_part_hits.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_explain_walk.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+    lib.vidx_field_highlight.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_create_synthetic.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_write_synthetic_requests.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     return lib
@@ -96,6 +97,27 @@ def same_explain(got, want, rel=1e-5):
     if isinstance(want, float) or isinstance(got, float):
         return abs(float(got) - float(want)) <= rel * max(abs(float(want)), 1e-30)
     return got == want
+
+
+def field_highlight(directory, part, hits):
+    """The host half of the product's search_field::highlight (csrc/host/field_highlight.hpp; no device) over the bare
+    part's (term id, score) hits -> [(highlighted text, score, text id)]."""
+    lib = _index_lib()
+    out = ctypes.create_string_buffer(1 << 22)
+    rc = lib.vidx_field_highlight(directory.encode(), json.dumps(part, ensure_ascii=False).encode("utf-8"), json.dumps([[int(i), float(s)] for i, s in hits]).encode(), 0, out, len(out))
+    if rc != 0:
+        raise OracleError(rc, out.value.decode())
+    return [(t, float(s), int(i)) for t, s, i in json.loads(out.value.decode("utf-8"))]
+
+
+def normalize_text(text):
+    """util::normalize_text of the product's host code."""
+    lib = _index_lib()
+    out = ctypes.create_string_buffer(1 << 16)
+    rc = lib.vidx_field_highlight(b"", json.dumps(text, ensure_ascii=False).encode("utf-8"), b"[]", 1, out, len(out))
+    if rc != 0:
+        raise RuntimeError(out.value.decode())
+    return json.loads(out.value.decode("utf-8"))
 
 
 def create_synthetic_index(directory, **params):

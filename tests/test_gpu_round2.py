@@ -851,3 +851,23 @@ def test_code_search_on_the_gpu(gpu, native_libs):
         assert_same_topk(got["data"], [(h[0], np.float32(h[1])) for h in ref["data"]], ctx=r)
         if n:
             assert b.result_docs(q)["data"][0]["doc"]["line"] == LINE
+
+
+def test_field_highlight_on_the_gpu(gpu, native_libs):
+    """search_field::highlight through the C ABI (vgpu_highlight): the part's terms matched and scored on the device, texts and
+    snippets against the Python oracle (tests/test_field_highlight.py: its parts, the reference's tests.rs:1009-1045 first)."""
+    from test_field_highlight import PARTS, STORY, make_index, oracle_highlight, same
+
+    d = make_index()
+    index, oracle = gpu.Index(d), helpers.Oracle(d)
+    assert [t for t, _, _ in index.highlight(PARTS[0])] == [STORY] and [t for t, _, _ in index.highlight(PARTS[1])] == [STORY]
+    for part in PARTS:
+        got = [(t, float(s), i) for t, s, i in index.highlight(part)]
+        assert same(got, oracle_highlight(d, oracle, part)), (part, got)
+    for part in ({"terms": ["story"], "path": "mylongtext"}, {"terms": ["1587690"], "path": "nofulltext", "snippet": True}):
+        with pytest.raises(gpu.VelociGpuError) as e:
+            index.highlight(part)
+        assert e.value.status == 1
+    with pytest.raises(gpu.VelociGpuError) as e:
+        index.highlight({"terms": ["story"], "path": "nope", "snippet": True})
+    assert e.value.status == 2  # FstNotFound

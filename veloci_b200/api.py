@@ -125,6 +125,7 @@ def load_library():
     L.vgpu_dev_top_n.argtypes = [vp, vp, u32, u32, P(_HitList)]
     L.vgpu_suggest.argtypes = [vp, cp, P(_Suggestions)]
     L.vgpu_suggest_part.argtypes = [vp, cp, P(_Suggestions)]
+    L.vgpu_highlight.argtypes = [vp, cp, P(_Suggestions)]
     L.vgpu_get_doc.argtypes = [vp, ctypes.c_uint32, P(vp)]
     L.vgpu_batch_result_docs.argtypes = [vp, ctypes.c_uint32, P(vp)]
     L.vgpu_batch_explain.argtypes = [vp, ctypes.c_uint32, P(vp)]
@@ -552,6 +553,10 @@ class Index:
     def suggest(self, part):
         """One RequestSearchPart; its top/skip bound the list."""
         return self._suggest(self.L.vgpu_suggest_part, part)
+
+    def highlight(self, part):
+        """search_field::highlight: [(highlighted text, score, text id)] of a part with "snippet": true."""
+        return self._suggest(self.L.vgpu_highlight, part)
 
     # ---- documents
     def get_doc(self, doc_id):

@@ -715,6 +715,11 @@ int32_t vgpu_suggest_query(vgpu_index* idx, const char* params_json, char** requ
     *request_json = nullptr;
     return guarded([&]() { *request_json = c_string(vquery::suggest_query_json(vquery::FieldCatalog::of(*idx->ix->host), params_json, strlen(params_json))); });
 }
+int32_t vgpu_highlight(vgpu_index* idx, const char* part_json, vgpu_suggestions* out) {
+    if (!idx || !part_json || !out) return VGPU_ERR_INVALID_REQUEST;
+    memset(out, 0, sizeof *out);
+    return guarded([&]() { fill_suggestions(vsteps::highlight(*idx->ix, part_json), out); });
+}
 int32_t vgpu_get_doc(vgpu_index* idx, uint32_t doc_id, char** doc_json) {
     if (!idx || !doc_json) return VGPU_ERR_INVALID_REQUEST;
     *doc_json = nullptr;

@@ -7,6 +7,7 @@
 #include "../../../include/veloci_b200.h"
 #include "engine.hpp"
 #include "explain.hpp"
+#include "field_highlight.hpp"
 #include "highlight.hpp"
 #include "read_document.hpp"
 
@@ -225,6 +226,31 @@ inline std::vector<Suggestion> suggest(vdev::DeviceIndex& ix, const vhost::Reque
     if (req.skip) merged.erase(merged.begin(), merged.begin() + (long)std::min<uint64_t>(*req.skip, merged.size()));  // apply_top_skip, search.rs:230-239
     if (req.top && merged.size() > *req.top) merged.resize((size_t)*req.top);
     return merged;
+}
+
+// search_field::highlight (search_field.rs:232-245): the part's terms are matched and scored on the device; the bound, the
+// boost, the token values and resolve_token_hits_to_text_id with snippets follow on the host (host/field_highlight.hpp).
+inline std::vector<Suggestion> highlight(vdev::DeviceIndex& ix, const char* part_json) {
+    vjson::Value v;
+    try {
+        v = vjson::parse(part_json, strlen(part_json));
+    } catch (const vjson::ParseError& e) {
+        throw vhost::RequestError(e.what());
+    }
+    const vhost::HighlightRequest req = vhost::parse_highlight_request(v);
+    vhost::SearchPart bare = req.part;
+    bare.top.reset(), bare.skip.reset(), bare.boost.reset(), bare.token_value.reset();
+    vdev::Batch b;
+    std::vector<uint32_t> part_ids;
+    b.prepare_parts(&ix, {bare}, &part_ids);
+    b.run_match();
+    std::vector<vdev::TermHit> hits;
+    b.download_part_hits(part_ids[0], hits);
+    vdev::bound_part_hits(req.part, hits);
+    vdev::apply_token_value(*ix.host, req.part, hits);
+    std::vector<Suggestion> out;
+    for (vhost::FieldHighlight& h : vhost::highlight_field(*ix.host, req, hits)) out.push_back(Suggestion{std::move(h.text), h.score, h.id});
+    return out;
 }
 
 // The remaining step entry points run a one-request batch whose leaves are explicit hit lists.

@@ -5,6 +5,7 @@
 #include <sstream>
 
 #include "../host/explain_walk.hpp"
+#include "../host/field_highlight.hpp"
 #include "../host/highlight.hpp"
 #include "../host/part_hits.hpp"
 #include "../host/query_generator.hpp"
@@ -168,6 +169,48 @@ int vidx_explain_walk(const char* dir, const char* request_json, const char* anc
     } catch (const vplan::Unsupported& e) {
         set_err(out, outlen, e.what());
         return 8;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
+        return 1;
+    }
+}
+
+// The host half of search_field::highlight (host/field_highlight.hpp) without a device: `hits_json` = the part's
+// [[term id, score], ...] as the device match delivers them for the bare part (terms normalised); writes
+// [[highlighted text, score, text id], ...].  what = 1: only normalize_text of `part_json` (a JSON string).
+int vidx_field_highlight(const char* dir, const char* part_json, const char* hits_json, int what, char* out, size_t outlen) {
+    try {
+        std::string text;
+        if (what == 1) {
+            const vjson::Value v = vjson::parse(part_json, strlen(part_json));
+            vjson::write_string(text, vhost::normalize_text(v.str));
+        } else {
+            std::unique_ptr<vhost::Persistence> p = vhost::Persistence::load(dir);
+            const vhost::HighlightRequest req = vhost::parse_highlight_request(vjson::parse(part_json, strlen(part_json)));
+            const vjson::Value hv = vjson::parse(hits_json, strlen(hits_json));
+            std::vector<vdev::TermHit> hits;
+            for (const vjson::Value& h : hv.arr) hits.push_back(vdev::TermHit{(uint32_t)h.arr.at(0).num, (float)h.arr.at(1).num});
+            std::sort(hits.begin(), hits.end(), [](const vdev::TermHit& a, const vdev::TermHit& b) { return a.id < b.id; });
+            vdev::bound_part_hits(req.part, hits);
+            vdev::apply_token_value(*p, req.part, hits);
+            text = "[";
+            bool first = true;
+            for (const vhost::FieldHighlight& h : vhost::highlight_field(*p, req, hits)) {
+                text += first ? "[" : ",[";
+                first = false;
+                vjson::write_string(text, h.text);
+                char buf[64];
+                snprintf(buf, sizeof buf, ",%.9g,%u]", (double)h.score, h.id);
+                text += buf;
+            }
+            text += "]";
+        }
+        if (text.size() + 1 > outlen) throw std::runtime_error("output buffer too small");
+        set_err(out, outlen, text.c_str());
+        return 0;
+    } catch (const vplan::InvalidRequest& e) {
+        set_err(out, outlen, e.what());
+        return 2;
     } catch (const std::exception& e) {
         set_err(out, outlen, e.what());
         return 1;
