@@ -245,6 +245,11 @@ int32_t vgpu_batch_result_docs(vgpu_batch* batch, uint32_t q, char** result_json
  * vgpu_batch_result_docs carries the same lists as each hit's "explain".  VGPU_ERR_UNSUPPORTED for the explanation (never for
  * the search) when the request has phrase boosts or 1:n boosts, on sharded handles and on imported plans.  Released with vgpu_free. */
 int32_t vgpu_batch_explain(vgpu_batch* batch, uint32_t q, char** explain_json);
+/* search::explain_plan (src/search.rs:132-141): the request's execution plan as a Graphviz dot graph -- the steps
+ * plan_creator lays out (src/plan_creator/execution_plan.rs:132-200), labelled like the reference's steps
+ * (plan_steps.rs:76-135: "search <path> <term>", "token to anchor", "Union", "BoostPlanStepFromBoostRequest", ...), one
+ * edge per dependency.  Needs no index.  Released with vgpu_free. */
+int32_t vgpu_explain_plan(const char* request_json, char** dot);
 /* read_data (src/search/read_document.rs:8-59): document `doc_id` rebuilt from the indices, only the fields of `fields_json`
  * (a JSON list of field paths, the request's `select`): 1:n levels through `<level>.parent_to_value_id`, texts through
  * `<field>.textindex.parent_to_value_id` and the dictionary, long texts from their token ids (src/search.rs:242-269).

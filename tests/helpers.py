@@ -27,6 +27,7 @@ def _index_lib():
     lib.vidx_bound_part_hits.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_explain_walk.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_field_highlight.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
+    lib.vidx_explain_plan.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_create_synthetic.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.vidx_write_synthetic_requests.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     return lib
@@ -118,6 +119,16 @@ def normalize_text(text):
     if rc != 0:
         raise RuntimeError(out.value.decode())
     return json.loads(out.value.decode("utf-8"))
+
+
+def explain_plan(request):
+    """search::explain_plan of the product's host code (csrc/host/explain_plan.hpp): a Graphviz dot text."""
+    lib = _index_lib()
+    out = ctypes.create_string_buffer(1 << 20)
+    rc = lib.vidx_explain_plan(json.dumps(request, ensure_ascii=False).encode("utf-8"), out, len(out))
+    if rc != 0:
+        raise RuntimeError(out.value.decode())
+    return out.value.decode("utf-8")
 
 
 def create_synthetic_index(directory, **params):

@@ -129,6 +129,7 @@ def load_library():
     L.vgpu_get_doc.argtypes = [vp, ctypes.c_uint32, P(vp)]
     L.vgpu_batch_result_docs.argtypes = [vp, ctypes.c_uint32, P(vp)]
     L.vgpu_batch_explain.argtypes = [vp, ctypes.c_uint32, P(vp)]
+    L.vgpu_explain_plan.argtypes = [cp, P(vp)]
     L.vgpu_read_doc.argtypes = [vp, ctypes.c_uint32, cp, P(vp)]
     L.vgpu_search_query.argtypes = [vp, cp, P(vp)]
     L.vgpu_suggest_query.argtypes = [vp, cp, P(vp)]
@@ -166,6 +167,14 @@ def query_parse(text, no_attributes=False, no_parentheses=False, no_levensthein=
     L = load_library()
     out = ctypes.c_void_p()
     return _take_string(L, L.vgpu_query_parse(text.encode("utf-8"), int(no_attributes) | int(no_parentheses) << 1 | int(no_levensthein) << 2, ctypes.byref(out)), out)
+
+
+def explain_plan(request):
+    """search::explain_plan: the request's plan steps as a Graphviz dot graph."""
+    L = load_library()
+    out = ctypes.c_void_p()
+    text = request if isinstance(request, (str, bytes)) else json.dumps(request, ensure_ascii=False)
+    return _take_string(L, L.vgpu_explain_plan(text.encode("utf-8") if isinstance(text, str) else text, ctypes.byref(out)), out)
 
 
 def device_count():

@@ -757,6 +757,11 @@ int32_t vgpu_batch_explain(vgpu_batch* batch, uint32_t q, char** explain_json) {
     }
     return guarded([&]() { *explain_json = c_string(vexplain::Explainer(batch->b, q).walk().to_json()); });
 }
+int32_t vgpu_explain_plan(const char* request_json, char** dot) {
+    if (!request_json || !dot) return VGPU_ERR_INVALID_REQUEST;
+    *dot = nullptr;
+    return guarded([&]() { *dot = c_string(vhost::explain_plan(vhost::read_request_json(request_json, strlen(request_json)))); });
+}
 int32_t vgpu_query_parse(const char* text, uint32_t options, char** tree_debug) {
     if (!text || !tree_debug) return VGPU_ERR_INVALID_REQUEST;
     *tree_debug = nullptr;

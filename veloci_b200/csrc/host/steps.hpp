@@ -7,6 +7,7 @@
 #include "../../../include/veloci_b200.h"
 #include "engine.hpp"
 #include "explain.hpp"
+#include "explain_plan.hpp"
 #include "field_highlight.hpp"
 #include "highlight.hpp"
 #include "read_document.hpp"

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <sstream>
 
+#include "../host/explain_plan.hpp"
 #include "../host/explain_walk.hpp"
 #include "../host/field_highlight.hpp"
 #include "../host/highlight.hpp"
@@ -211,6 +212,19 @@ int vidx_field_highlight(const char* dir, const char* part_json, const char* hit
     } catch (const vplan::InvalidRequest& e) {
         set_err(out, outlen, e.what());
         return 2;
+    } catch (const std::exception& e) {
+        set_err(out, outlen, e.what());
+        return 1;
+    }
+}
+
+// search::explain_plan of the product's host code (host/explain_plan.hpp), for the CPU tests.
+int vidx_explain_plan(const char* request_json, char* out, size_t outlen) {
+    try {
+        const std::string text = vhost::explain_plan(vhost::read_request_json(request_json, strlen(request_json)));
+        if (text.size() + 1 > outlen) throw std::runtime_error("output buffer too small");
+        set_err(out, outlen, text.c_str());
+        return 0;
     } catch (const std::exception& e) {
         set_err(out, outlen, e.what());
         return 1;
