@@ -129,3 +129,19 @@ def test_walk_on_a_large_dictionary(native_libs):
         n_items += sum(len(v) for v in want.values())
         n_multi += sum(1 for v in want.values() if sum(1 for e in v if "TermToAnchor" in e) > 2)
     assert n_items > 500 and n_multi > 5
+
+
+def test_reference_explain_tests_through_the_query_generator(native_libs):
+    """test_query_generator.rs:139-152 (5 entries) and :154-168 (3 hits, 7 entries for the first): requests made by the
+    product's query generator over every field of the reference's query-generator corpus; the oracle's explain lengths as
+    the reference asserts them, and the product's walk against the oracle on these many-part `or`s."""
+    d = tempfile.mkdtemp(prefix="vb200_explain_qg_")
+    helpers.create_index(d, fx.TEST_QG_DOCS, fx.TEST_QG_CONFIG)
+    o = helpers.Oracle(d)
+    for params, n_hits, n_explain in (({"search_term": "urge", "explain": True}, 1, 5), ({"search_term": "urge OR いよく", "explain": True}, 3, 7)):
+        rc, req, raw = helpers.generate_request(d, params)
+        assert rc == 0 and req["explain"] is True, raw
+        res = o.search(req)
+        assert len(res["data"]) == n_hits and fx.TEST_QG_DOCS[res["data"][0][0]]["ent_seq"] == "1587690"
+        assert len(res["explain"][str(res["data"][0][0])]) == n_explain
+        walk_against_oracle(d, o, req)

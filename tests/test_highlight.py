@@ -126,3 +126,13 @@ def test_random_texts_product_equals_oracle(corpus):
         assert product_highlight(d, doc, sets) == ref, (text, terms)
         n_some += bool(ref)
     assert n_some > 400
+
+
+def test_regex_why_found(corpus):  # test_why_found.rs:345-360: the pattern spans the tokens, only the whole text matches: all of it is marked
+    hits = why_found(corpus, S(".*github.com.*", "url", is_regex=True))
+    assert len(hits) == 1 and hits[0][1]["url"] == ["<b>https://github.com/PSeitz/veloci</b>"]
+
+
+def test_regex_why_found_token(corpus):  # test_why_found.rs:362-377: a token and the whole text match: the token is what gets marked
+    hits = why_found(corpus, S(".*PSeitz.*", "url", is_regex=True))
+    assert len(hits) == 1 and hits[0][1]["url"] == ["https://github.com/<b>PSeitz</b>/veloci"]

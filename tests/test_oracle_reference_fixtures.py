@@ -434,3 +434,41 @@ def test_suggest_with_token_value(test_all):  # tests.rs:1134-1158
 def test_token_value_errors(test_all):  # persistence.rs:454-458: a field without token values
     with pytest.raises(helpers.OracleError):
         test_all.call("suggest", part={"terms": ["will"], "path": "meanings.eng[]", "token_value": {"path": "meanings.eng[]", "boost_fun": "Log10"}})
+
+
+# ---- the rest of tests/all/test_phrase.rs: requests made by the query generator, several phrases per request
+def _tags(*terms):
+    return [{"search": {"terms": [t], "path": "tags[]"}} for t in terms]
+
+
+def _pbt(path, t1, t2):
+    return {"path": path, "search1": {"terms": [t1], "path": path}, "search2": {"terms": [t2], "path": path}}
+
+
+def test_phrase_requests_from_the_query_generator(test_phrase, native_libs):  # test_phrase.rs:100-127
+    import json
+    import os
+    import tempfile
+    d = tempfile.mkdtemp(prefix="vb200_idx_")
+    helpers.create_index(d, fx.TEST_PHRASE_DOCS, fx.TEST_PHRASE_CONFIG)
+    for params in ({"search_term": "die AND erbin", "phrase_pairs": True},                     # :100-107
+                   {"search_term": "die erbin", "phrase_pairs": True, "explain": True},        # :109-118
+                   {"search_term": "die erbin", "phrase_pairs": True}):                         # :120-127
+        rc, req, raw = helpers.generate_request(d, params)
+        assert rc == 0 and req.get("phrase_boosts"), raw
+        assert docs_of(test_phrase.search(req), P)[0]["title"] == "die erbin", params
+
+
+def test_should_double_boost_from_multiphrases(test_phrase):  # test_phrase.rs:129-176
+    for kind in ("or", "and"):  # :178-219 the same with `and`
+        single = {"search_req": {kind: {"queries": _tags("greg", "tagebuch", "05")}}, "phrase_boosts": [_pbt("tags[]", "greg", "tagebuch")]}
+        hit = docs_of(test_phrase.search(single), P)[0]
+        assert hit["tags"][0] == "greg tagebuch" and (kind == "and" or hit["tags"][1] == "05")
+        multi = {"search_req": {kind: {"queries": _tags("greg", "tagebuch", "05")}}, "phrase_boosts": [_pbt("tags[]", "greg", "tagebuch"), _pbt("tags[]", "tagebuch", "05")]}
+        assert docs_of(test_phrase.search(multi), P)[0]["tags"][0] == "greg tagebuch 05"
+
+
+def test_should_prefer_different_phrases_from_same_phrase_multiple_times(test_phrase):  # test_phrase.rs:220-258
+    req = {"search_req": {"or": {"queries": _tags("greg", "tagebuch", "05") + [{"search": {"terms": [t], "path": "title"}} for t in ("greg", "tagebuch", "05")]}},
+           "phrase_boosts": [_pbt("tags[]", "greg", "tagebuch"), _pbt("title", "greg", "tagebuch"), _pbt("tags[]", "tagebuch", "05"), _pbt("title", "tagebuch", "05")]}
+    assert docs_of(test_phrase.search(req), P)[0]["tags"][0] == "greg tagebuch 05"
