@@ -1581,6 +1581,12 @@ static std::string call(const Persistence* p, const std::string& fn, const vjson
         }
         std::vector<uint8_t> sp = w.encode_start_pos();
         vfmt::AnchorScoreView v;
+        if (a.get("wide") && a.get("wide")->b) {  // data_type U64 (token_to_anchor_score_vint.rs:242-248): 8-byte start positions
+            std::vector<uint8_t> wide(sp.size() * 2, 0);
+            for (size_t i = 0; i < sp.size() / 4; ++i) memcpy(&wide[i * 8], &sp[i * 4], 4);
+            sp.swap(wide);
+            v.wide = true;
+        }
         v.start_pos = sp.data();
         v.start_len = sp.size();
         v.data = w.data.data();

@@ -136,3 +136,12 @@ def test_regex_why_found(corpus):  # test_why_found.rs:345-360: the pattern span
 def test_regex_why_found_token(corpus):  # test_why_found.rs:362-377: a token and the whole text match: the token is what gets marked
     hits = why_found(corpus, S(".*PSeitz.*", "url", is_regex=True))
     assert len(hits) == 1 and hits[0][1]["url"] == ["https://github.com/<b>PSeitz</b>/veloci"]
+
+
+def test_highlight_text_unit_vectors(corpus):  # highlight_field.rs:279-300 (the default tokenizer)
+    d, _, _ = corpus
+    assert ohl.highlight_text("mein treffer", {"treffer"}, ohl.DEFAULT_SEPERATORS) == "mein <b>treffer</b>"
+    assert ohl.highlight_text("mein treffer treffers", {"treffers", "treffer"}, ohl.DEFAULT_SEPERATORS) == "mein <b>treffer</b> <b>treffers</b>"
+    # the product through a document of one tokenized field
+    for text, terms, want in (("mein treffer", {"treffer"}, "mein <b>treffer</b>"), ("mein treffer treffers", {"treffers", "treffer"}, "mein <b>treffer</b> <b>treffers</b>")):
+        assert product_highlight(d, {"richtig": text}, {"richtig.textindex": terms}) == {"richtig": [want]}

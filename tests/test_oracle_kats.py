@@ -161,6 +161,9 @@ def test_anchor_score_codec(o):  # token_to_anchor_score_vint.rs:212-232
     assert r[0] == [] and r[1] == [[1, 1], [2, 3]] and all(x == [] for x in r[2:])
     big = [[0, [0, 395, 7, 148, 100000, 148, 100001, 70000]]]
     assert o.call("codec_anchor_score", adds=big, queries=[0]) == [[[0, 395], [7, 148], [100000, 148], [100001, 70000]]]
+    # the same store with 8-byte start positions (data_type U64, token_to_anchor_score_vint.rs:242-248)
+    r = o.call("codec_anchor_score", adds=[[1, [1, 1]], [5, [1, 1, 2, 3]]], queries=[0, 1, 4, 5, 6], wide=True)
+    assert r == [[], [[1, 1]], [], [[1, 1], [2, 3]], []]
 
 
 def test_fst_roundtrip(o):  # search_field.rs:36-51,101-141 (fst::Map::from_iter + ord_to_term)
