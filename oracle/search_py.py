@@ -1,0 +1,281 @@
+"""CPU oracle (TEST INFRASTRUCTURE, never imported by the product): a second, independent restatement of the hot path in
+plain Python + numpy float32 -- request JSON -> get_term_ids_in_field -> resolve_token_to_anchor -> union / intersect ->
+add_boost -> top_n -- over the oracle's own decoder of the index files (oracle/index_files.py).  It shares no code with the
+product and none with oracle/veloci_oracle.cpp (which reads index directories through the product's reader and parses
+requests with the product's DOM parser): tests/test_python_search_oracle.py holds the two oracles against each other.
+
+Covers SURVEY 8 rows a1, a4-a7, a9, a11, a12, a17 (search / or / and trees of search parts with levenshtein_distance,
+starts_with, ignore_case, boost; request boosts on the anchor level with every boost function, expression and
+skip_when_score; top / skip).  Not covered (raises): filters, phrase boosts, text locality, facets, 1:n boosts,
+boost_term, regex parts, per-part top, token values.
+
+Each function cites the reference file:line it follows.
+"""
+import numpy as np
+
+import index_files as oif
+
+F = np.float32
+
+
+def _lower_one(ch):  # the matching automaton folds scalar by scalar (no expansion, no context)
+    low = ch.lower()
+    return low if len(low) == 1 else ch
+
+
+def _prefix_distances(a, b, transposition):
+    """Levenshtein distance (adjacent transposition at cost one when asked) of every prefix of `a` to `b`: [d(a[:i], b)]."""
+    n, m = len(a), len(b)
+    pp, p = None, list(range(m + 1))
+    out = [p[m]]
+    for i in range(1, n + 1):
+        c = [i] + [0] * m
+        for j in range(1, m + 1):
+            v = min(p[j] + 1, c[j - 1] + 1, p[j - 1] + (a[i - 1] != b[j - 1]))
+            if transposition and i >= 2 and j >= 2 and a[i - 1] == b[j - 2] and a[i - 2] == b[j - 1]:
+                v = min(v, pp[j - 2] + 1)
+            c[j] = v
+        pp, p = p, c
+        out.append(p[m])
+    return out
+
+
+def _edit_distance(a, b, transposition):
+    return _prefix_distances(a, b, transposition)[-1]
+
+
+def _distance_u8(s1, s2):  # search_field.rs:705-732: plain DP in u8 cells, 255 when a string has 255 bytes or more
+    if len(s1.encode("utf-8")) >= 255 or len(s2.encode("utf-8")) >= 255:
+        return 255
+    column = list(range(len(s1) + 1))
+    for x, cx in enumerate(s2):
+        column[0] = (x + 1) & 0xFF
+        lastdiag = x & 0xFF
+        for y, cy in enumerate(s1):
+            if cy != cx:
+                lastdiag = (lastdiag + 1) & 0xFF
+            olddiag = column[y + 1]
+            column[y + 1] = min((column[y + 1] + 1) & 0xFF, (column[y] + 1) & 0xFF, lastdiag)
+            lastdiag = olddiag
+    return column[len(s1)]
+
+
+def _default_score(distance, prefix_matches):  # search_field.rs:27-33
+    if prefix_matches:
+        return F(2.0) / (np.log2(F(distance) + F(1.0)) + F(0.2))
+    return F(2.0) / (F(distance) + F(0.2))
+
+
+class Unsupported(Exception):
+    pass
+
+
+class PySearch:
+    def __init__(self, directory):
+        self.ix = oif.IndexDirectory(directory)
+        self.meta = {ix["path"]: ix for _field, ix in self.ix.indices()}
+        self._dicts, self._files = {}, {}
+
+    def _file(self, name):
+        if name not in self._files:
+            self._files[name] = self.ix.read(name)
+        return self._files[name]
+
+    def _dictionary(self, path):  # [(text, term id)] in key order: the FST stream's order
+        if path not in self._dicts:
+            if not any(f + ".textindex" == path and c.get("has_fst") for f, c in self.ix.meta["columns"].items()):
+                raise KeyError("field does not exist %s (fst not found)" % path)
+            self._dicts[path] = [(k.decode("utf-8"), v) for k, v in oif.Fst(self._file(path + ".fst")).items()]
+        return self._dicts[path]
+
+    # ---- search_field.rs:277-398
+    def field_search(self, part):
+        for key in ("top", "skip", "token_value", "is_regex"):
+            if part.get(key):
+                raise Unsupported(key)
+        path = part["path"] if part["path"].endswith(".textindex") else part["path"] + ".textindex"
+        term = part["terms"][0]
+        lower_term = term.lower()
+        d = part.get("levenshtein_distance")
+        if d is not None:
+            d = min(d, len(lower_term) - 1)  # :286 (the empty term is not exercised here)
+        d_score = d or 0
+        d_match = min(d_score, 4)                              # :87-88
+        ignore_case = part.get("ignore_case")
+        transposition = bool(ignore_case) if ignore_case is not None else False  # :87 (sic)
+        case_insensitive = ignore_case if ignore_case is not None else True
+        starts_with = bool(part.get("starts_with"))
+        check_prefix = starts_with or d_score != 0             # :302
+        query = [(_lower_one(c) if case_insensitive else c) for c in term]
+        hits = []
+        for text, term_id in self._dictionary(path):
+            cand = [(_lower_one(c) if case_insensitive else c) for c in text]
+            if starts_with:  # the automaton's prefix closure: some prefix of the key is within distance
+                ok = min(_prefix_distances(cand, query, transposition)) <= d_match
+            else:
+                ok = abs(len(cand) - len(query)) <= d_match and _edit_distance(cand, query, transposition) <= d_match
+            if not ok:
+                continue
+            line_lower = text.lower()
+            prefix_matches = check_prefix and line_lower.startswith(lower_term)
+            k = _edit_distance(list(line_lower), list(lower_term), True)   # distance_dfa :691-702
+            dist = k if k <= d_score else _distance_u8(line_lower, lower_term)
+            hits.append((term_id, _default_score(dist, prefix_matches)))
+        hits.sort(key=lambda h: h[0])
+        if part.get("boost") is not None:                      # :359-364
+            hits = [(i, s * F(part["boost"])) for i, s in hits]
+        return path, hits
+
+    # ---- search_field.rs:400-464
+    def resolve(self, path, hits):
+        name = path + ".to_anchor_id_score"
+        meta = self.meta[name]
+        start_pos, data = self._file(name + ".indirect"), self._file(name + ".data")
+        best = {}
+        for term_id, score in hits:
+            for anchor, raw in oif.anchor_scores(start_pos, data, term_id, wide=meta.get("data_type") == "U64"):
+                final = score * (F(np.float16(F(raw))) / F(100.0))  # :426: the stored score passes through f16
+                if anchor not in best or final > best[anchor]:
+                    best[anchor] = final
+        return best
+
+    # ---- set_op.rs:87-220
+    @staticmethod
+    def union(results):
+        if len(results) == 1:
+            return results[0]
+        slots = sorted({term for term, _ in results})
+        out = {}
+        for anchor in sorted(set().union(*[hits.keys() for _, hits in results])):
+            mx = [F(0.0)] * len(slots)
+            for term, hits in results:
+                if anchor in hits:
+                    i = slots.index(term)
+                    mx[i] = max(mx[i], hits[anchor])
+            n = F(sum(1 for m in mx if m >= F(0.00001)))
+            total = F(0.0)
+            for m in mx:
+                total = total + m
+            out[anchor] = total * n * n
+        return (results[0][0], out)
+
+    # ---- set_op.rs:368-446
+    @staticmethod
+    def intersect(results):
+        if len(results) == 1:
+            return results[0]
+        lists = list(results)
+        shortest = min(range(len(lists)), key=lambda i: (len(lists[i][1]), i))   # the first shortest
+        short = lists[shortest][1]
+        lists[shortest] = lists[-1]                                              # swap_remove
+        lists.pop()
+        out = {}
+        for anchor in sorted(short):
+            if all(anchor in hits for _, hits in lists):
+                score = F(0.0)
+                for _, hits in lists:
+                    score = score + hits[anchor]
+                out[anchor] = score + short[anchor]
+        return (lists[0][0], out)
+
+    def _tree(self, node):
+        if "search" in node:
+            part = node["search"]
+            if (part.get("options") or {}).get("boost"):
+                raise Unsupported("boosts in a part's options")
+            path, hits = self.field_search(part)
+            return (part["terms"][0], self.resolve(path, hits))
+        kind = "or" if "or" in node else "and"
+        if (node[kind].get("options") or {}).get("boost"):
+            raise Unsupported("boosts in a sub-query's options")
+        inputs = [self._tree(q) for q in node[kind]["queries"]]
+        return self.union(inputs) if kind == "or" else self.intersect(inputs)
+
+    # ---- boost.rs:470-504, 283-377; expression.rs:25-100
+    def _boost_value(self, path, anchor):
+        name = path + ".boost_valid_to_value"
+        meta = self.meta.get(name)
+        if meta is None:
+            raise KeyError("Did not found path in indices " + name)
+        if meta["index_cardinality"] == "MultiValue":
+            vals = oif.indirect_get_values(self._file(name + ".indirect"), self._file(name + ".data"), anchor)
+            bits = vals[0] if vals else None
+        else:
+            bits = oif.packed_get_value(self._file(name), oif.packed_width(meta["metadata"]["max_value_id"]), anchor)
+        return None if bits is None else np.array([bits], dtype=np.uint32).view(np.float32)[0]
+
+    @staticmethod
+    def _expression(text, v):
+        ops, current = [], ""
+
+        def flush(s):
+            try:
+                ops.append(("f", F(float(s))))
+            except ValueError:
+                pass
+
+        for c in text:
+            if c == " ":
+                if current:
+                    flush(current)
+                current = ""
+            else:
+                current += c
+            if current in ("+", "-", "/", "*"):
+                ops.append((current, None))
+                current = ""
+            elif current == "$SCORE":
+                ops.append(("$", None))
+                current = ""
+        if current:
+            flush(current)
+        left = v if ops[0][0] == "$" else ops[0][1]
+        right = v if ops[2][0] == "$" else ops[2][1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            op = ops[1][0]
+            return left / right if op == "/" else left * right if op == "*" else left + right if op == "+" else left - right
+
+    def add_boost(self, boost, hits):
+        if "[]" in boost["path"]:
+            raise Unsupported("1:n boost")
+        param = F(boost.get("param") or 0.0)
+        skip = [F(x) for x in boost.get("skip_when_score") or []]
+        fun = boost.get("boost_fun")
+        for anchor in list(hits):
+            score = hits[anchor]
+            if any(abs(x - score) < F(0.00001) for x in skip):
+                continue
+            v = self._boost_value(boost["path"], anchor)
+            if v is None:
+                continue
+            with np.errstate(divide="ignore", invalid="ignore"):
+                if fun == "Log10":
+                    score = score * np.log10(v + param)
+                elif fun == "Log2":
+                    score = score * np.log2(v + param)
+                elif fun == "Multiply":
+                    score = score * (v + param)
+                elif fun == "Add":
+                    score = score + (v + param)
+                elif fun == "Replace":
+                    score = v + param
+                if boost.get("expression"):
+                    score = score + self._expression(boost["expression"], v)
+            hits[anchor] = F(score)
+
+    # ---- search.rs:143-228
+    def search(self, request):
+        for key in ("filter", "phrase_boosts", "boost_term", "facets", "suggest", "select"):
+            if request.get(key):
+                raise Unsupported(key)
+        if request.get("text_locality"):
+            raise Unsupported("text_locality")
+        top = request.get("top", 10)
+        top = 10 if top is None else top
+        skip = request.get("skip") or 0
+        _, hits = self._tree(request["search_req"])
+        hits = dict(hits)
+        for boost in request.get("boost") or []:
+            self.add_boost(boost, hits)
+        ordered = sorted(hits.items(), key=lambda h: (-float(h[1]), -h[0]))  # sort.rs:5-22 / search.rs:123-130: score desc, id desc
+        return {"num_hits": len(hits), "data": [(a, float(s)) for a, s in ordered[skip:skip + top]]}

@@ -1,0 +1,71 @@
+"""Two oracles against each other on the hot path: oracle/veloci_oracle.cpp (C++, reads index directories through the
+product's reader and parses requests with the product's DOM parser) and oracle/search_py.py (plain Python + numpy float32
+over the oracle's own decoder of the index files, its own reading of the request JSON, its own matching and scoring).
+They share no code; agreement on hit counts, ids and scores means the shared headers under the C++ oracle are not hiding a
+common mistake on this path."""
+import json
+import os
+import sys
+import tempfile
+
+import pytest
+
+import helpers
+import ref_fixtures as fx
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+import search_py  # noqa: E402  (test infrastructure)
+
+S = lambda term, path, **kw: {"search": {"terms": [term], "path": path, **kw}}
+GER, ENG = "meanings.ger[]", "meanings.eng[]"
+
+
+def agree(cpp, py, request):
+    a, b = cpp.search(request), py.search(request)
+    assert a["num_hits"] == b["num_hits"], (request, a["num_hits"], b["num_hits"])
+    assert helpers.same_topk([(h[0], h[1]) for h in a["data"]], b["data"]), (request, a["data"], b["data"])
+    return a["num_hits"]
+
+
+def test_reference_corpus(native_libs):
+    d = tempfile.mkdtemp(prefix="vb200_py_")
+    helpers.create_index(d, fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG)
+    cpp, py = helpers.Oracle(d), search_py.PySearch(d)
+    c1 = {"path": "commonness", "boost_fun": "Log10", "param": 1}
+    requests = [
+        {"search_req": S("urge", ENG)},
+        {"search_req": S("Urge", ENG, ignore_case=False)},
+        {"search_req": S("majestätischer", GER, levenshtein_distance=1)},
+        {"search_req": S("majestät", GER, levenshtein_distance=2), "top": 3, "skip": 1},
+        {"search_req": S("will", GER, starts_with=True), "top": None},
+        {"search_req": S("wil", GER, starts_with=True, levenshtein_distance=1, boost=2.5)},
+        {"search_req": S("ewsome", "field1[].text", levenshtein_distance=1, ignore_case=True)},   # transposition only with ignore_case (search_field.rs:87)
+        {"search_req": S("awesoem", "field1[].text", levenshtein_distance=1, ignore_case=True)},
+        {"search_req": S("awesoem", "field1[].text", levenshtein_distance=1)},
+        {"search_req": {"or": {"queries": [S("majestät", GER), S("urge", ENG)]}}},
+        {"search_req": {"or": {"queries": [S("majestät", GER, levenshtein_distance=1), S("majestät", ENG, levenshtein_distance=1), S("urge", ENG), S("weich", GER, levenshtein_distance=1)]}}, "boost": [c1]},
+        {"search_req": {"and": {"queries": [S("majestät", GER, levenshtein_distance=2), S("majestätisches", GER, levenshtein_distance=3)]}}},
+        {"search_req": {"or": {"queries": [{"and": {"queries": [S("will", GER, starts_with=True), S("will", ENG, starts_with=True)]}}, S("urge", ENG)]}}, "boost": [c1]},
+        {"search_req": S("weich", GER, levenshtein_distance=1), "boost": [{"path": "commonness", "boost_fun": "Log2", "param": 2}]},
+        {"search_req": S("weich", GER, levenshtein_distance=1), "boost": [{"path": "commonness", "boost_fun": "Multiply", "expression": "$SCORE * 2", "skip_when_score": [7.5]}, {"path": "commonness", "boost_fun": "Add", "param": 3}]},
+        {"search_req": S("weich", GER, levenshtein_distance=1), "boost": [{"path": "commonness", "boost_fun": "Replace"}, {"path": "commonness", "expression": "10 / $SCORE"}]},
+        {"search_req": S("nothing matches this", GER)},
+    ]
+    total = sum(agree(cpp, py, r) for r in requests)
+    assert total > 25
+    with pytest.raises(KeyError):
+        py.search({"search_req": S("a", "notexisting")})
+
+
+def test_synthetic_config2_shape(native_libs):
+    """A seeded Zipfian corpus in the shape of BASELINE config 2 (3-term `or`, levenshtein 1, Log10 boost) and its `and` /
+    single-term relatives, small enough for the Python oracle (500-term dictionary)."""
+    params = dict(num_docs=4000, vocab=500, seed=7)
+    d = tempfile.mkdtemp(prefix="vb200_py_")
+    helpers.create_synthetic_index(d, **params)
+    cpp, py = helpers.Oracle(d), search_py.PySearch(d)
+    reqs = helpers.synthetic_requests(num_queries=40, query_kind="or3", levenshtein=1, query_seed=3, **params)
+    reqs += helpers.synthetic_requests(num_queries=15, query_kind="single", levenshtein=2, query_seed=4, **params)
+    reqs += [json.dumps({k: v for k, v in json.loads(r).items() if k != "facets"}) for r in helpers.synthetic_requests(num_queries=15, query_kind="and", levenshtein=1, query_seed=5, **params)]
+    total = sum(agree(cpp, py, json.loads(r)) for r in reqs)
+    assert total > 20000
