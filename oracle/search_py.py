@@ -6,14 +6,15 @@ requests with the product's DOM parser): tests/test_python_search_oracle.py hold
 
 Covers SURVEY 8 rows a1, a4-a7, a9, a11, a12, a17 (search / or / and trees of search parts with levenshtein_distance,
 starts_with, ignore_case, boost; request boosts on the anchor level with every boost function, expression and
-skip_when_score; top / skip).  Not covered (raises): filters, phrase boosts, text locality, facets, 1:n boosts,
-boost_term, regex parts, per-part top, token values.
+skip_when_score; top / skip), and a10 / a16: `filter` trees and facets.  Not covered (raises): phrase boosts, text
+locality, 1:n boosts, boost_term, regex parts, per-part top, token values.
 
 Each function cites the reference file:line it follows.
 """
 import numpy as np
 
 import index_files as oif
+import read_document as ord_
 
 F = np.float32
 
@@ -75,6 +76,7 @@ class PySearch:
         self.ix = oif.IndexDirectory(directory)
         self.meta = {ix["path"]: ix for _field, ix in self.ix.indices()}
         self._dicts, self._files = {}, {}
+        self.reader = ord_.Reader(directory)  # key-value stores (oracle/read_document.py, over the same decoder)
 
     def _file(self, name):
         if name not in self._files:
@@ -191,6 +193,46 @@ class PySearch:
         inputs = [self._tree(q) for q in node[kind]["queries"]]
         return self.union(inputs) if kind == "or" else self.intersect(inputs)
 
+    # ---- the ids-only sub-plan of a filter (execution_plan.rs:289-292,513-516; search_field.rs:466-498; set_op.rs:222-258,468-509)
+    def _ids_tree(self, node):
+        if "search" in node:
+            path, hits = self.field_search(node["search"])
+            field = path[:-len(".textindex")]
+            if self.ix.meta["columns"].get(field, {}).get("is_anchor_identity_column"):
+                return {term_id for term_id, _ in hits}
+            anchors = set()
+            for term_id, _ in hits:
+                anchors.update(self.reader.get_values(path + ".text_id_to_anchor", term_id) or [])
+            return anchors
+        kind = "or" if "or" in node else "and"
+        sets = [self._ids_tree(q) for q in node[kind]["queries"]]
+        return set().union(*sets) if kind == "or" else set.intersection(*sets)
+
+    # ---- facet.rs:31-83
+    def facet(self, field, top, anchors):
+        steps, cur = [], ""
+        for piece in field.split("."):
+            cur = cur + "." + piece if cur else piece
+            if piece.endswith("[]"):
+                steps.append(cur)
+        steps.append(field + ".textindex")  # util.rs:173-188 get_steps_to_anchor
+        counts = {}
+        if len(steps) == 1 or self.reader.has_index(steps[-1] + ".anchor_to_text_id"):
+            path = steps[0] + ".parent_to_value_id" if len(steps) == 1 else steps[-1] + ".anchor_to_text_id"
+            for a in anchors:
+                for v in self.reader.get_values(path, a) or []:
+                    counts[v] = counts.get(v, 0) + 1
+        else:
+            ids = list(anchors)
+            for step in steps:  # join_anchor_to_leaf
+                ids = [v for i in ids for v in (self.reader.get_values(step + ".parent_to_value_id", i) or [])]
+            for v in ids:
+                counts[v] = counts.get(v, 0) + 1
+        groups = sorted(counts.items(), key=lambda g: -g[1])  # ties: unspecified in the reference (unstable sort)
+        if top is not None:
+            groups = groups[:top]
+        return [(self.reader.text_for_id(steps[-1], v), n, v) for v, n in groups]
+
     # ---- boost.rs:470-504, 283-377; expression.rs:25-100
     def _boost_value(self, path, anchor):
         name = path + ".boost_valid_to_value"
@@ -265,7 +307,7 @@ class PySearch:
 
     # ---- search.rs:143-228
     def search(self, request):
-        for key in ("filter", "phrase_boosts", "boost_term", "facets", "suggest", "select"):
+        for key in ("phrase_boosts", "boost_term", "suggest", "select"):
             if request.get(key):
                 raise Unsupported(key)
         if request.get("text_locality"):
@@ -275,7 +317,13 @@ class PySearch:
         skip = request.get("skip") or 0
         _, hits = self._tree(request["search_req"])
         hits = dict(hits)
+        if request.get("filter"):  # intersect_score_hits_with_ids (set_op.rs:311-326)
+            allowed = self._ids_tree(request["filter"])
+            hits = {a: s for a, s in hits.items() if a in allowed}
         for boost in request.get("boost") or []:
             self.add_boost(boost, hits)
         ordered = sorted(hits.items(), key=lambda h: (-float(h[1]), -h[0]))  # sort.rs:5-22 / search.rs:123-130: score desc, id desc
-        return {"num_hits": len(hits), "data": [(a, float(s)) for a, s in ordered[skip:skip + top]]}
+        out = {"num_hits": len(hits), "data": [(a, float(s)) for a, s in ordered[skip:skip + top]]}
+        if request.get("facets"):  # search.rs:188-206: over the sorted hit ids
+            out["facets"] = {f["field"]: self.facet(f["field"], f.get("top", 10), sorted(hits)) for f in request["facets"]}
+        return out

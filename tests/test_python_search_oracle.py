@@ -24,6 +24,9 @@ def agree(cpp, py, request):
     a, b = cpp.search(request), py.search(request)
     assert a["num_hits"] == b["num_hits"], (request, a["num_hits"], b["num_hits"])
     assert helpers.same_topk([(h[0], h[1]) for h in a["data"]], b["data"]), (request, a["data"], b["data"])
+    if request.get("facets"):  # (every group asked for: the order among equal counts is open in the reference)
+        for field, groups in a["facets"].items():
+            assert sorted((t, n, i) for t, n, i in groups) == sorted(b["facets"][field]), (request, field)
     return a["num_hits"]
 
 
@@ -50,6 +53,12 @@ def test_reference_corpus(native_libs):
         {"search_req": S("weich", GER, levenshtein_distance=1), "boost": [{"path": "commonness", "boost_fun": "Multiply", "expression": "$SCORE * 2", "skip_when_score": [7.5]}, {"path": "commonness", "boost_fun": "Add", "param": 3}]},
         {"search_req": S("weich", GER, levenshtein_distance=1), "boost": [{"path": "commonness", "boost_fun": "Replace"}, {"path": "commonness", "expression": "10 / $SCORE"}]},
         {"search_req": S("nothing matches this", GER)},
+        # filters (tests.rs:753-824) and facets (tests_facet.rs:60-117 run on their own corpus below)
+        {"search_req": S("majestät", GER, levenshtein_distance=1), "filter": S("20", "commonness")},
+        {"search_req": {"or": {"queries": [S("majestät", GER, levenshtein_distance=2), S("urge", ENG), S("will", GER, starts_with=True)]}},
+         "filter": {"or": {"queries": [S("20", "commonness"), S("1587690", "ent_seq")]}}, "boost": [c1]},
+        {"search_req": S("will", GER, starts_with=True), "filter": {"and": {"queries": [S("will", ENG, starts_with=True), S("will", GER, starts_with=True)]}}},
+        {"search_req": {"or": {"queries": [S("majestät", GER, levenshtein_distance=2), S("will", GER, starts_with=True)]}}, "facets": [{"field": "tags[]", "top": 100}, {"field": "commonness", "top": 100}]},
     ]
     total = sum(agree(cpp, py, r) for r in requests)
     assert total > 25
@@ -66,6 +75,12 @@ def test_synthetic_config2_shape(native_libs):
     cpp, py = helpers.Oracle(d), search_py.PySearch(d)
     reqs = helpers.synthetic_requests(num_queries=40, query_kind="or3", levenshtein=1, query_seed=3, **params)
     reqs += helpers.synthetic_requests(num_queries=15, query_kind="single", levenshtein=2, query_seed=4, **params)
-    reqs += [json.dumps({k: v for k, v in json.loads(r).items() if k != "facets"}) for r in helpers.synthetic_requests(num_queries=15, query_kind="and", levenshtein=1, query_seed=5, **params)]
+    params["tags"] = 30  # the `and` requests count facets on tags[]
+    helpers.create_synthetic_index(d, **params)
+    cpp, py = helpers.Oracle(d), search_py.PySearch(d)
+    for r in helpers.synthetic_requests(num_queries=15, query_kind="and", levenshtein=1, query_seed=5, **params):
+        r = json.loads(r)
+        r["facets"][0]["top"] = 1000
+        reqs.append(json.dumps(r))
     total = sum(agree(cpp, py, json.loads(r)) for r in reqs)
     assert total > 20000
