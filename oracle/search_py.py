@@ -6,8 +6,8 @@ requests with the product's DOM parser): tests/test_python_search_oracle.py hold
 
 Covers SURVEY 8 rows a1, a4-a7, a9, a11, a12, a17 (search / or / and trees of search parts with levenshtein_distance,
 starts_with, ignore_case, boost; request boosts on the anchor level with every boost function, expression and
-skip_when_score; top / skip), and a10 / a16: `filter` trees and facets.  Not covered (raises): phrase boosts, text
-locality, 1:n boosts, boost_term, regex parts, per-part top, token values.
+skip_when_score; top / skip), and a10 / a13 / a14 / a16: `filter` trees, phrase boosts, text locality, facets -- the
+shape of BASELINE config 3.  Not covered (raises): 1:n boosts, boost_term, regex parts, per-part top, token values.
 
 Each function cites the reference file:line it follows.
 """
@@ -208,6 +208,60 @@ class PySearch:
         sets = [self._ids_tree(q) for q in node[kind]["queries"]]
         return set().union(*sets) if kind == "or" else set.intersection(*sets)
 
+    # ---- phrase boosts (execution_plan.rs:202-262, plan_steps.rs:235-293, search_field.rs:263-275, boost.rs:380-402)
+    def _phrase_boosts(self, phrase_boosts, hits):
+        groups = {}
+        for pb in phrase_boosts:
+            p1, p2 = pb["search1"], pb["search2"]
+            assert p1["path"] == p2["path"]
+            path, h1 = self.field_search(p1)
+            _, h2 = self.field_search(p2)
+            name = path + ".phrase_pair_to_anchor"
+            store = oif.phrase_pair_records(self._file(name + ".indirect"), self._file(name + ".data"))
+            anchors = groups.setdefault((p1["terms"][0], p2["terms"][0]), set())  # the same two terms in several fields: one group
+            for t1, _ in h1:
+                for t2, _ in h2:
+                    anchors.update(store.get((t1, t2), []))
+        for anchors in groups.values():  # every group multiplies the hits it contains by 5.0 (plan_steps.rs:271)
+            for a in anchors:
+                if a in hits:
+                    hits[a] = hits[a] * F(5.0)
+
+    # ---- text locality (boost.rs:11-87, search.rs:113-120,180-184)
+    def _term_ids_in_field(self, node, out):
+        if "search" in node:
+            path, hits = self.field_search(node["search"])
+            if hits:  # search_field.rs:379-383
+                out.setdefault(path, {})[node["search"]["terms"][0]] = [i for i, _ in hits]
+            return
+        for q in node["or" if "or" in node else "and"]["queries"]:
+            self._term_ids_in_field(q, out)
+
+    def _text_locality(self, search_req, hits):
+        per_field = {}
+        self._term_ids_in_field(search_req, per_field)
+        best = {}
+        for path, term_to_ids in per_field.items():
+            if len(term_to_ids) <= 1:
+                continue
+            counts = {}
+            for ids in term_to_ids.values():
+                for token in ids:
+                    for text_id in self.reader.get_values(path + ".tokens_to_text_id", token) or []:
+                        counts[text_id] = counts.get(text_id, 0) + 1
+            identity = self.ix.meta["columns"].get(path[:-len(".textindex")], {}).get("is_anchor_identity_column")
+            for text_id, c in counts.items():
+                if c <= 1:
+                    continue
+                boost = F(2.0) * F(c) * F(c)
+                anchors = [text_id] if identity else (self.reader.get_values(path + ".text_id_to_anchor", text_id) or [])
+                for a in anchors:
+                    if a not in best or boost < best[a]:  # the reversed comparator keeps the minimum (boost.rs:23-28)
+                        best[a] = boost
+        for a, boost in best.items():
+            if a in hits:
+                hits[a] = hits[a] * boost
+
     # ---- facet.rs:31-83
     def facet(self, field, top, anchors):
         steps, cur = [], ""
@@ -307,11 +361,9 @@ class PySearch:
 
     # ---- search.rs:143-228
     def search(self, request):
-        for key in ("phrase_boosts", "boost_term", "suggest", "select"):
+        for key in ("boost_term", "suggest", "select"):
             if request.get(key):
                 raise Unsupported(key)
-        if request.get("text_locality"):
-            raise Unsupported("text_locality")
         top = request.get("top", 10)
         top = 10 if top is None else top
         skip = request.get("skip") or 0
@@ -322,6 +374,10 @@ class PySearch:
             hits = {a: s for a, s in hits.items() if a in allowed}
         for boost in request.get("boost") or []:
             self.add_boost(boost, hits)
+        if request.get("phrase_boosts"):
+            self._phrase_boosts(request["phrase_boosts"], hits)
+        if request.get("text_locality"):
+            self._text_locality(request["search_req"], hits)
         ordered = sorted(hits.items(), key=lambda h: (-float(h[1]), -h[0]))  # sort.rs:5-22 / search.rs:123-130: score desc, id desc
         out = {"num_hits": len(hits), "data": [(a, float(s)) for a, s in ordered[skip:skip + top]]}
         if request.get("facets"):  # search.rs:188-206: over the sorted hit ids

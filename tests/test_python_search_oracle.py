@@ -84,3 +84,45 @@ def test_synthetic_config2_shape(native_libs):
         reqs.append(json.dumps(r))
     total = sum(agree(cpp, py, json.loads(r)) for r in reqs)
     assert total > 20000
+
+
+def test_phrase_and_text_locality_corpora(native_libs):
+    """The reference's phrase tests (test_phrase.rs) and its text locality test (tests.rs:1296-1313) through both oracles."""
+    d = tempfile.mkdtemp(prefix="vb200_py_")
+    helpers.create_index(d, fx.TEST_PHRASE_DOCS, fx.TEST_PHRASE_CONFIG)
+    cpp, py = helpers.Oracle(d), search_py.PySearch(d)
+    T = lambda *terms: [S(t, "tags[]") for t in terms]
+    pb = lambda path, a, b: {"path": path, "search1": {"terms": [a], "path": path}, "search2": {"terms": [b], "path": path}}
+    requests = [
+        {"search_req": S("erbin", "title"), "phrase_boosts": [pb("title", "die", "erbin")]},
+        {"search_req": {"or": {"queries": [S(t, p) for p in ("title", "tags[]") for t in ("die", "erbin")]}}, "phrase_boosts": [pb("title", "die", "erbin"), pb("tags[]", "die", "erbin")]},
+        {"search_req": {"or": {"queries": T("greg", "tagebuch", "05")}}, "phrase_boosts": [pb("tags[]", "greg", "tagebuch"), pb("tags[]", "tagebuch", "05")]},
+        {"search_req": {"and": {"queries": T("greg", "tagebuch", "05")}}, "phrase_boosts": [pb("tags[]", "greg", "tagebuch")]},
+        {"search_req": {"or": {"queries": T("greg", "tagebuch", "05") + [S(t, "title") for t in ("greg", "tagebuch", "05")]}}, "text_locality": True,
+         "phrase_boosts": [pb("tags[]", "greg", "tagebuch"), pb("title", "greg", "tagebuch"), pb("tags[]", "tagebuch", "05"), pb("title", "tagebuch", "05")]},
+        {"search_req": {"or": {"queries": T("greg", "tagebuch", "05")}}, "text_locality": True},
+    ]
+    assert sum(agree(cpp, py, r) for r in requests) > 10
+    d = tempfile.mkdtemp(prefix="vb200_py_")
+    helpers.create_index(d, fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG)
+    cpp, py = helpers.Oracle(d), search_py.PySearch(d)
+    req = {"search_req": {"or": {"queries": [S("text", GER), S("localität", GER), S("text", ENG)]}}, "text_locality": True}
+    assert agree(cpp, py, req) >= 2
+
+
+def test_synthetic_config3_shape(native_libs):
+    """BASELINE config 3 in small: `and` of 2-3 parts (levenshtein 0 / 1), phrase boosts for adjacent parts, text locality,
+    facets on tags[] -- every piece of that request through both oracles."""
+    params = dict(num_docs=3000, vocab=400, seed=9, tags=25, text_locality=True, phrase=True)
+    d = tempfile.mkdtemp(prefix="vb200_py_")
+    helpers.create_synthetic_index(d, **params)
+    cpp, py = helpers.Oracle(d), search_py.PySearch(d)
+    total = boosted = 0
+    for r in helpers.synthetic_requests(num_queries=40, query_kind="and", levenshtein=1, query_seed=6, **params):
+        r = json.loads(r)
+        assert r.get("phrase_boosts") and r.get("text_locality") and r.get("facets")
+        r["facets"][0]["top"] = 1000
+        total += agree(cpp, py, r)
+        plain = {k: v for k, v in r.items() if k not in ("phrase_boosts", "text_locality")}
+        boosted += [h[1] for h in cpp.search(r)["data"]] != [h[1] for h in cpp.search(plain)["data"]]
+    assert total > 300 and boosted >= 5, (total, boosted)
