@@ -4,6 +4,8 @@ usage: ncu -i prof.ncu-rep --page source --print-source sass,cuda --csv | python
 import csv
 import sys
 
+if sys.stdin.isatty() or (len(sys.argv) > 1 and sys.argv[1] in ("-h", "--help")):
+    sys.exit(__doc__)
 rows = list(csv.reader(sys.stdin))
 top = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 data, cur, hdr = [], None, None
