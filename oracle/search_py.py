@@ -7,7 +7,8 @@ requests with the product's DOM parser): tests/test_python_search_oracle.py hold
 Covers SURVEY 8 rows a1, a4-a7, a9, a11, a12, a17 (search / or / and trees of search parts with levenshtein_distance,
 starts_with, ignore_case, boost; request boosts on the anchor level with every boost function, expression and
 skip_when_score; top / skip), and a10 / a13 / a14 / a16: `filter` trees, phrase boosts, text locality, facets -- the
-shape of BASELINE config 3.  Not covered (raises): 1:n boosts, boost_term, regex parts, per-part top, token values.
+shape of BASELINE config 3 -- plus a15 (boost_term), the per-part top / skip bound and token values of a4.  Not covered
+(raises): 1:n boosts, regex parts.
 
 Each function cites the reference file:line it follows.
 """
@@ -92,9 +93,8 @@ class PySearch:
 
     # ---- search_field.rs:277-398
     def field_search(self, part):
-        for key in ("top", "skip", "token_value", "is_regex"):
-            if part.get(key):
-                raise Unsupported(key)
+        if part.get("is_regex"):
+            raise Unsupported("is_regex")
         path = part["path"] if part["path"].endswith(".textindex") else part["path"] + ".textindex"
         term = part["terms"][0]
         lower_term = term.lower()
@@ -108,9 +108,13 @@ class PySearch:
         case_insensitive = ignore_case if ignore_case is not None else True
         starts_with = bool(part.get("starts_with"))
         check_prefix = starts_with or d_score != 0             # :302
+        limit = part.get("top") is not None                    # :292-294
+        top_n = (part.get("top") if limit else 10) + (part.get("skip") or 0)
+        worst = F(-3.40282347e+38)
+        order = lambda h: (-float(h[1]), -h[0])                # search.rs:123-130: score desc, id desc
         query = [(_lower_one(c) if case_insensitive else c) for c in term]
         hits = []
-        for text, term_id in self._dictionary(path):
+        for text, term_id in self._dictionary(path):           # the FST stream: ascending key = ascending term id
             cand = [(_lower_one(c) if case_insensitive else c) for c in text]
             if starts_with:  # the automaton's prefix closure: some prefix of the key is within distance
                 ok = min(_prefix_distances(cand, query, transposition)) <= d_match
@@ -122,10 +126,27 @@ class PySearch:
             prefix_matches = check_prefix and line_lower.startswith(lower_term)
             k = _edit_distance(list(line_lower), list(lower_term), True)   # distance_dfa :691-702
             dist = k if k <= d_score else _distance_u8(line_lower, lower_term)
-            hits.append((term_id, _default_score(dist, prefix_matches)))
-        hits.sort(key=lambda h: h[0])
+            score = _default_score(dist, prefix_matches)
+            if limit:                                          # :322-331, sort.rs:25-34
+                if score < worst:
+                    continue
+                if hits and len(hits) == top_n + 200:
+                    hits.sort(key=order)
+                    del hits[top_n:]
+                    if hits:
+                        worst = hits[-1][1]
+            hits.append((term_id, score))
         if part.get("boost") is not None:                      # :359-364
             hits = [(i, s * F(part["boost"])) for i, s in hits]
+        if limit:                                              # :366-369 (the reference's sort is unstable: ties at the cut are open)
+            hits.sort(key=lambda h: -float(h[1]))
+            del hits[top_n:]
+        if part.get("token_value"):                            # :391-395: add_boost over the term hits
+            tv = dict(part["token_value"])
+            tv["path"] = tv["path"] + ".textindex.token_values"
+            scored = dict(hits)
+            self.add_boost(tv, scored)
+            hits = [(i, scored[i]) for i, _ in hits]
         return path, hits
 
     # ---- search_field.rs:400-464
@@ -194,16 +215,19 @@ class PySearch:
         return self.union(inputs) if kind == "or" else self.intersect(inputs)
 
     # ---- the ids-only sub-plan of a filter (execution_plan.rs:289-292,513-516; search_field.rs:466-498; set_op.rs:222-258,468-509)
+    def _ids_of_part(self, part):  # hits_ids of a part resolved to anchors, one entry per (matched text id, anchor) (search_field.rs:466-498)
+        path, hits = self.field_search(part)
+        field = path[:-len(".textindex")]
+        if self.ix.meta["columns"].get(field, {}).get("is_anchor_identity_column"):
+            return [term_id for term_id, _ in hits]
+        anchors = []
+        for term_id, _ in hits:
+            anchors.extend(self.reader.get_values(path + ".text_id_to_anchor", term_id) or [])
+        return anchors
+
     def _ids_tree(self, node):
         if "search" in node:
-            path, hits = self.field_search(node["search"])
-            field = path[:-len(".textindex")]
-            if self.ix.meta["columns"].get(field, {}).get("is_anchor_identity_column"):
-                return {term_id for term_id, _ in hits}
-            anchors = set()
-            for term_id, _ in hits:
-                anchors.update(self.reader.get_values(path + ".text_id_to_anchor", term_id) or [])
-            return anchors
+            return set(self._ids_of_part(node["search"]))
         kind = "or" if "or" in node else "and"
         sets = [self._ids_tree(q) for q in node[kind]["queries"]]
         return set().union(*sets) if kind == "or" else set.intersection(*sets)
@@ -332,8 +356,6 @@ class PySearch:
             return left / right if op == "/" else left * right if op == "*" else left + right if op == "+" else left - right
 
     def add_boost(self, boost, hits):
-        if "[]" in boost["path"]:
-            raise Unsupported("1:n boost")
         param = F(boost.get("param") or 0.0)
         skip = [F(x) for x in boost.get("skip_when_score") or []]
         fun = boost.get("boost_fun")
@@ -361,9 +383,12 @@ class PySearch:
 
     # ---- search.rs:143-228
     def search(self, request):
-        for key in ("boost_term", "suggest", "select"):
+        for key in ("suggest", "select"):
             if request.get(key):
                 raise Unsupported(key)
+        for boost in request.get("boost") or []:
+            if "[]" in boost["path"]:
+                raise Unsupported("1:n boost")
         top = request.get("top", 10)
         top = 10 if top is None else top
         skip = request.get("skip") or 0
@@ -376,6 +401,11 @@ class PySearch:
             self.add_boost(boost, hits)
         if request.get("phrase_boosts"):
             self._phrase_boosts(request["phrase_boosts"], hits)
+        for part in request.get("boost_term") or []:  # search.rs:176, boost.rs:89-195: hits the part also finds, times its boost (2.0)
+            factor = F(part["boost"] if part.get("boost") is not None else 2.0)
+            for a in self._ids_of_part(part):  # an anchor reached from two matched texts is boosted twice (boost.rs:222-231)
+                if a in hits:
+                    hits[a] = hits[a] * factor
         if request.get("text_locality"):
             self._text_locality(request["search_req"], hits)
         ordered = sorted(hits.items(), key=lambda h: (-float(h[1]), -h[0]))  # sort.rs:5-22 / search.rs:123-130: score desc, id desc

@@ -53,6 +53,10 @@ def test_reference_corpus(native_libs):
         {"search_req": S("weich", GER, levenshtein_distance=1), "boost": [{"path": "commonness", "boost_fun": "Multiply", "expression": "$SCORE * 2", "skip_when_score": [7.5]}, {"path": "commonness", "boost_fun": "Add", "param": 3}]},
         {"search_req": S("weich", GER, levenshtein_distance=1), "boost": [{"path": "commonness", "boost_fun": "Replace"}, {"path": "commonness", "expression": "10 / $SCORE"}]},
         {"search_req": S("nothing matches this", GER)},
+        # boost_term (tests.rs:1232-1256), per-part top / skip and part boosts (tests.rs:1276-1288)
+        {"search_req": S("majestät", GER, levenshtein_distance=2), "boost_term": [{"terms": ["9555"], "path": "ent_seq", "boost": 5.0}, {"terms": ["majestät"], "path": GER, "levenshtein_distance": 1}]},
+        {"search_req": S("will", GER, starts_with=True, top=2, skip=1, boost=0.5)},
+        {"search_req": {"or": {"queries": [S("majestät", GER, levenshtein_distance=2, top=1), S("will", GER, starts_with=True, top=3)]}}},
         # filters (tests.rs:753-824) and facets (tests_facet.rs:60-117 run on their own corpus below)
         {"search_req": S("majestät", GER, levenshtein_distance=1), "filter": S("20", "commonness")},
         {"search_req": {"or": {"queries": [S("majestät", GER, levenshtein_distance=2), S("urge", ENG), S("will", GER, starts_with=True)]}},
@@ -126,3 +130,24 @@ def test_synthetic_config3_shape(native_libs):
         plain = {k: v for k, v in r.items() if k not in ("phrase_boosts", "text_locality")}
         boosted += [h[1] for h in cpp.search(r)["data"]] != [h[1] for h in cpp.search(plain)["data"]]
     assert total > 300 and boosted >= 5, (total, boosted)
+
+
+def test_per_part_top_and_token_values(native_libs):
+    """The per-part bound (keep top + skip + 200, cut, drop below the worst kept: search_field.rs:292-294,322-331,366-369) on
+    parts that match hundreds of terms, and token values (:391-395), through both oracles as term hit lists and as whole requests."""
+    from test_part_hits import make_valued_index, token_value_parts
+    d, cpp, words, _ = make_valued_index()
+    py = search_py.PySearch(d)
+    parts = list(token_value_parts(words[:8]))
+    # one-letter prefixes match hundreds of terms: the bound's cut at top + skip + 200 hits is reached
+    parts += [{"terms": [w[:1]], "path": "body", "starts_with": True, "levenshtein_distance": i % 2, "top": 2 + 3 * i, "skip": i % 3,
+               **({"boost": -1.5} if i == 2 else {}), **({"token_value": {"path": "body", "boost_fun": "Multiply"}} if i % 2 else {})} for i, w in enumerate(words[8:13])]
+    n_long = 0
+    for part in parts:
+        a = sorted(cpp.call("field_search", part=part)["hits_scores"])
+        b = sorted((t, float(s)) for t, s in py.field_search(part)[1])
+        assert [t for t, _ in a] == [t for t, _ in b], part
+        assert all(abs(x[1] - y[1]) <= 1e-5 * max(abs(x[1]), 1e-30) for x, y in zip(a, b)), part
+        agree(cpp, py, {"search_req": {"search": part}, "top": 20})
+        n_long += len(cpp.call("field_search", part={k: v for k, v in part.items() if k not in ("top", "skip", "token_value")})["hits_scores"]) > 210
+    assert n_long >= 3, "no part reached the bound"
