@@ -7,8 +7,8 @@ requests with the product's DOM parser): tests/test_python_search_oracle.py hold
 Covers SURVEY 8 rows a1, a4-a7, a9, a11, a12, a17 (search / or / and trees of search parts with levenshtein_distance,
 starts_with, ignore_case, boost; request boosts on the anchor level with every boost function, expression and
 skip_when_score; top / skip), and a10 / a13 / a14 / a16: `filter` trees, phrase boosts, text locality, facets -- the
-shape of BASELINE config 3 -- plus a15 (boost_term), the per-part top / skip bound and token values of a4.  Not covered
-(raises): 1:n boosts, regex parts.
+shape of BASELINE config 3 -- plus a8 (boosts on a 1:n level), a15 (boost_term), the per-part top / skip bound and token
+values of a4.  Not covered (raises): regex parts.
 
 Each function cites the reference file:line it follows.
 """
@@ -201,20 +201,67 @@ class PySearch:
                 out[anchor] = score + short[anchor]
         return (lists[0][0], out)
 
-    def _tree(self, node):
+    def _tree(self, node, boosts=()):
         if "search" in node:
             part = node["search"]
-            if (part.get("options") or {}).get("boost"):
-                raise Unsupported("boosts in a part's options")
-            path, hits = self.field_search(part)
-            return (part["terms"][0], self.resolve(path, hits))
+            path, term_hits = self.field_search(part)
+            hits = self.resolve(path, term_hits)
+            pos = part["path"].rfind("[]")
+            if pos >= 0:  # plan_creator_search_part (execution_plan.rs:422-509): a boost on the part's own 1:n level
+                level = part["path"][:pos]
+                on_level = [b for b in boosts if b["path"].rfind("[]") >= 0 and b["path"][:b["path"].rfind("[]")] == level]
+                if len(on_level) > 1:
+                    raise ValueError("more than one boost on the same 1:n level")
+                if on_level:
+                    self._apply_anchor_boost(hits, on_level[0], self._boost_to_anchor(part, path, term_hits, on_level[0]))
+            return (part["terms"][0], hits)
         kind = "or" if "or" in node else "and"
-        if (node[kind].get("options") or {}).get("boost"):
-            raise Unsupported("boosts in a sub-query's options")
-        inputs = [self._tree(q) for q in node[kind]["queries"]]
+        inputs = []
+        for q in node[kind]["queries"]:
+            own = ((q.get("search") or q.get("or") or q.get("and")).get("options") or {}).get("boost") or []  # merge_vec :263-270
+            inputs.append(self._tree(q, tuple(boosts) + tuple(own)))
         return self.union(inputs) if kind == "or" else self.intersect(inputs)
 
-    # ---- the ids-only sub-plan of a filter (execution_plan.rs:289-292,513-516; search_field.rs:466-498; set_op.rs:222-258,468-509)
+    # ---- BoostToAnchor (plan_steps.rs:174-196): term hits -> text ids -> value ids -> (anchor, boost value) in value id order
+    def _boost_to_anchor(self, part, path, term_hits, boost):
+        field = path[:-len(".textindex")]
+        tokenized = (((self.ix.meta["columns"].get(field) or {}).get("textindex_metadata") or {}).get("options") or {}).get("tokenize")
+        ids = [i for i, _ in term_hits]
+        if tokenized:  # resolve_token_hits_to_text_id_ids_only (search_field.rs:640-689): a token without an entry is itself a text id
+            text_ids = []
+            for i in ids:
+                vals = self.reader.get_values(path + ".tokens_to_text_id", i)
+                text_ids.extend(vals if vals is not None else [i])
+            ids = sorted(set(text_ids))
+        value_ids = sorted({v for i in ids for v in (self.reader.get_values(path + ".value_id_to_parent", i) or [])})  # join_to_parent_ids (search.rs:281-315)
+        out = []
+        for value_id in value_ids:  # get_boost_ids_and_resolve_to_anchor (boost.rs:432-468)
+            v = self._boost_value(boost["path"], value_id)
+            if v is None:
+                continue
+            anchor = self.reader.get_value(boost["path"] + ".value_id_to_anchor", value_id)
+            if anchor is not None:
+                out.append((anchor, v))
+        return out
+
+    # ---- ApplyAnchorBoost: apply_boost_values_anchor (boost.rs:255-281), the merge walk as it is written
+    def _apply_anchor_boost(self, hits, boost, boost_ids):
+        if not boost_ids:
+            return
+        it = iter(boost_ids)
+        cur = next(it)
+        for anchor in sorted(hits):
+            if cur[0] < anchor:
+                for b in it:
+                    if b[0] > anchor:
+                        cur = b
+                        break
+                    if b[0] == anchor:
+                        cur = b
+                        hits[anchor] = self._apply_boost(boost, hits[anchor], b[1])
+            elif cur[0] == anchor:
+                hits[anchor] = self._apply_boost(boost, hits[anchor], cur[1])
+
     def _ids_of_part(self, part):  # hits_ids of a part resolved to anchors, one entry per (matched text id, anchor) (search_field.rs:466-498)
         path, hits = self.field_search(part)
         field = path[:-len(".textindex")]
@@ -355,50 +402,50 @@ class PySearch:
             op = ops[1][0]
             return left / right if op == "/" else left * right if op == "*" else left + right if op == "+" else left - right
 
-    def add_boost(self, boost, hits):
+    def _apply_boost(self, boost, score, v):  # apply_boost (boost.rs:283-377)
         param = F(boost.get("param") or 0.0)
-        skip = [F(x) for x in boost.get("skip_when_score") or []]
         fun = boost.get("boost_fun")
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if fun == "Log10":
+                score = score * np.log10(v + param)
+            elif fun == "Log2":
+                score = score * np.log2(v + param)
+            elif fun == "Multiply":
+                score = score * (v + param)
+            elif fun == "Add":
+                score = score + (v + param)
+            elif fun == "Replace":
+                score = v + param
+            if boost.get("expression"):
+                score = score + self._expression(boost["expression"], v)
+        return F(score)
+
+    def add_boost(self, boost, hits):  # boost.rs:470-504
+        skip = [F(x) for x in boost.get("skip_when_score") or []]
         for anchor in list(hits):
             score = hits[anchor]
             if any(abs(x - score) < F(0.00001) for x in skip):
                 continue
             v = self._boost_value(boost["path"], anchor)
-            if v is None:
-                continue
-            with np.errstate(divide="ignore", invalid="ignore"):
-                if fun == "Log10":
-                    score = score * np.log10(v + param)
-                elif fun == "Log2":
-                    score = score * np.log2(v + param)
-                elif fun == "Multiply":
-                    score = score * (v + param)
-                elif fun == "Add":
-                    score = score + (v + param)
-                elif fun == "Replace":
-                    score = v + param
-                if boost.get("expression"):
-                    score = score + self._expression(boost["expression"], v)
-            hits[anchor] = F(score)
+            if v is not None:
+                hits[anchor] = self._apply_boost(boost, score, v)
 
     # ---- search.rs:143-228
     def search(self, request):
         for key in ("suggest", "select"):
             if request.get(key):
                 raise Unsupported(key)
-        for boost in request.get("boost") or []:
-            if "[]" in boost["path"]:
-                raise Unsupported("1:n boost")
         top = request.get("top", 10)
         top = 10 if top is None else top
         skip = request.get("skip") or 0
-        _, hits = self._tree(request["search_req"])
+        _, hits = self._tree(request["search_req"], tuple(request.get("boost") or []))
         hits = dict(hits)
         if request.get("filter"):  # intersect_score_hits_with_ids (set_op.rs:311-326)
             allowed = self._ids_tree(request["filter"])
             hits = {a: s for a, s in hits.items() if a in allowed}
         for boost in request.get("boost") or []:
-            self.add_boost(boost, hits)
+            if "[]" not in boost["path"]:  # execution_plan.rs:175-189: boosts on the anchor level follow the tree
+                self.add_boost(boost, hits)
         if request.get("phrase_boosts"):
             self._phrase_boosts(request["phrase_boosts"], hits)
         for part in request.get("boost_term") or []:  # search.rs:176, boost.rs:89-195: hits the part also finds, times its boost (2.0)

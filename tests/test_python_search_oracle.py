@@ -151,3 +151,41 @@ def test_per_part_top_and_token_values(native_libs):
         agree(cpp, py, {"search_req": {"search": part}, "top": 20})
         n_long += len(cpp.call("field_search", part={k: v for k, v in part.items() if k not in ("top", "skip", "token_value")})["hits_scores"]) > 210
     assert n_long >= 3, "no part reached the bound"
+
+
+def test_one_to_n_boosts(native_libs):
+    """Boosts on a 1:n level (tests.rs:839-931): BoostToAnchor's joins and ApplyAnchorBoost's merge walk, with its
+    position dependence when a document has several boosted values, through both oracles."""
+    import numpy as np
+    d = tempfile.mkdtemp(prefix="vb200_py_")
+    helpers.create_index(d, fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG)
+    cpp, py = helpers.Oracle(d), search_py.PySearch(d)
+    c1 = {"path": "commonness", "boost_fun": "Log10", "param": 1}
+    requests = [
+        {"search_req": S("意慾", "kanji[].text"), "boost": [{"path": "kanji[].commonness", "boost_fun": "Log10", "param": 1}]},
+        {"search_req": S("awesome", "field1[].text"), "boost": [c1, {"path": "field1[].rank", "expression": "10 / $SCORE", "skip_when_score": [0]}]},
+        {"search_req": {"or": {"queries": [
+            {"search": {"terms": ["awesome"], "path": "field1[].text", "options": {"boost": [{"path": "field1[].rank", "boost_fun": "Log10", "param": 1}]}}},
+            {"search": {"terms": ["urge"], "path": ENG, "options": {"boost": [c1]}}}]}}},
+        {"search_req": {"or": {"queries": [S("awesome", "field1[].text"), S("意慾", "kanji[].text", levenshtein_distance=1)]}},
+         "boost": [{"path": "field1[].rank", "boost_fun": "Multiply"}, {"path": "kanji[].commonness", "boost_fun": "Add", "param": 2}, {"path": "commonness", "boost_fun": "Log2", "param": 2}]},
+    ]
+    assert sum(agree(cpp, py, r) for r in requests) >= 4
+    rng = np.random.default_rng(11)
+    syll = ["ka", "ki", "ku", "mi", "mo", "ra", "ri", "ru", "sa", "to"]
+    words = ["".join(rng.choice(syll, size=int(rng.integers(2, 4)))) for _ in range(120)]
+    docs = []
+    for i in range(1500):
+        n = int(rng.integers(0, 4))
+        doc = {"ent_seq": str(i)}
+        if n:
+            doc["kana"] = [{"text": str(rng.choice(words)), **({"commonness": int(rng.integers(1, 900))} if rng.random() < 0.75 else {})} for _ in range(n)]
+        docs.append(doc)
+    d = tempfile.mkdtemp(prefix="vb200_py_")
+    helpers.create_index(d, docs, {"kana[].text": {"fulltext": {"tokenize": True}}, "kana[].commonness": dict(fx.BOOST)})
+    cpp, py = helpers.Oracle(d), search_py.PySearch(d)
+    total = 0
+    for t in [str(w) for w in rng.choice(words, size=8)] + ["mi", "ka"]:
+        for fun in ("Log10", "Multiply", "Add"):
+            total += agree(cpp, py, {"search_req": S(t, "kana[].text", levenshtein_distance=1, starts_with=True), "boost": [{"path": "kana[].commonness", "boost_fun": fun, "param": 1}], "top": 50})
+    assert total > 1000
