@@ -205,6 +205,26 @@ class Fst:
                 stack.append((target, key + bytes([inp]), acc + o))
         return out
 
+    def ord_to_term(self, ord_):
+        """search_field.rs:36-51: the key whose value is `ord_` when the values are the keys' ranks.  -> (found, bytes); for a
+        value no key carries (ids of texts too long to be stored, create_fulltext.rs:60-64) the walk ends somewhere and
+        get_text_for_id (:520-526) takes the bytes gathered so far all the same."""
+        out = bytearray()
+        is_final, _, trans = self.node(self.root)
+        while ord_ != 0 or not is_final:
+            pick = None
+            for t in trans:
+                if t[1] <= ord_:
+                    pick = t
+                else:
+                    break
+            if pick is None:
+                return False, bytes(out)
+            ord_ -= pick[1]
+            out.append(pick[0])
+            is_final, _, trans = self.node(pick[2])
+        return True, bytes(out)
+
     def get(self, key):
         addr, acc = self.root, 0
         for b in key:

@@ -39,10 +39,10 @@ class Reader:
         vals = self.get_values(path, value_id)
         return vals[0] if vals else None
 
-    def text_for_id(self, field, term_id):  # get_text_for_id (search_field.rs:520-526): ord_to_term on the field's FST
+    def text_for_id(self, field, term_id):  # get_text_for_id (search_field.rs:520-526): ord_to_term on the field's FST, its result ignored
         if field not in self._terms:
-            self._terms[field] = {v: k.decode("utf-8") for k, v in oif.Fst(self._file(field + ".fst")).items()}
-        return self._terms[field].get(term_id, "")
+            self._terms[field] = oif.Fst(self._file(field + ".fst"))
+        return self._terms[field].ord_to_term(term_id)[1].decode("utf-8", "replace")
 
     def join_and_get_text_for_ids(self, value_id, prop):  # src/search.rs:242-269
         field = prop + ".textindex"

@@ -189,3 +189,62 @@ def test_one_to_n_boosts(native_libs):
         for fun in ("Log10", "Multiply", "Add"):
             total += agree(cpp, py, {"search_req": S(t, "kana[].text", levenshtein_distance=1, starts_with=True), "boost": [{"path": "kana[].commonness", "boost_fun": fun, "param": 1}], "top": 50})
     assert total > 1000
+
+
+def test_random_request_trees(native_libs):
+    """300 seeded random requests on the reference corpus -- nested or / and trees of fuzzy, prefix and exact parts over
+    several fields, optional filter tree, anchor and 1:n boosts, boost_term, text locality, facets, top / skip -- through both oracles."""
+    import random
+    rng = random.Random(20261019)
+    d = tempfile.mkdtemp(prefix="vb200_py_")
+    helpers.create_index(d, fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG)
+    cpp, py = helpers.Oracle(d), search_py.PySearch(d)
+    terms = {GER: ["majestät", "majestätischer", "will", "wille", "weich", "welch", "text", "localität", "begeisterung", "der", "test", "treffer"],
+             ENG: ["urge", "will", "majesty", "test1", "text", "awesome"], "field1[].text": ["awesome", "nice"], "kanji[].text": ["意慾", "偉容"],
+             "ent_seq": ["1587690", "1587700", "9555"], "tags[]": ["nice", "cool", "awesome"]}
+
+    def part():
+        path = rng.choice(list(terms))
+        t = rng.choice(terms[path])
+        p = {"terms": [t[:rng.randrange(2, len(t) + 1)] if rng.random() < 0.3 else t], "path": path}
+        if rng.random() < 0.5:
+            p["levenshtein_distance"] = rng.randrange(0, 3)
+        if rng.random() < 0.3:
+            p["starts_with"] = True
+        if rng.random() < 0.15:
+            p["ignore_case"] = rng.random() < 0.5
+        if rng.random() < 0.15:
+            p["boost"] = rng.choice([0.5, 2.0, 3.5])
+        if rng.random() < 0.1:
+            p["top"], p["skip"] = rng.randrange(1, 4), rng.randrange(0, 2)
+        return {"search": p}
+
+    def tree(depth):
+        if depth == 0 or rng.random() < 0.35:
+            return part()
+        return {rng.choice(["or", "and"]): {"queries": [tree(depth - 1) for _ in range(rng.randrange(1, 4))]}}
+
+    total = 0
+    for _ in range(300):
+        r = {"search_req": tree(2)}
+        if rng.random() < 0.2:
+            r["filter"] = tree(1)
+        boosts = []
+        if rng.random() < 0.4:
+            boosts.append({"path": "commonness", "boost_fun": rng.choice(["Log10", "Log2", "Multiply", "Add", "Replace"]), "param": rng.choice([1, 2, 0.5])})
+        if rng.random() < 0.15:
+            boosts.append({"path": rng.choice(["kanji[].commonness", "field1[].rank"]), "boost_fun": rng.choice(["Log10", "Multiply", "Add"]), "param": 1})
+        if rng.random() < 0.1:
+            boosts.append({"path": "commonness", "expression": rng.choice(["$SCORE * 2", "10 / $SCORE", "$SCORE + 1.5"]), "skip_when_score": [10.0]})
+        if boosts:
+            r["boost"] = boosts
+        if rng.random() < 0.15:
+            r["boost_term"] = [part()["search"]]
+        if rng.random() < 0.2:
+            r["text_locality"] = True
+        if rng.random() < 0.2:
+            r["facets"] = [{"field": rng.choice(["tags[]", "commonness"]), "top": 100}]
+        if rng.random() < 0.3:
+            r["top"], r["skip"] = rng.randrange(1, 6), rng.randrange(0, 3)
+        total += agree(cpp, py, r)
+    assert total > 300
