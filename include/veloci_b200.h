@@ -324,7 +324,8 @@ int32_t vgpu_top_n(vgpu_index* idx, const vgpu_hitlist* in, uint32_t top, uint32
  * A vgpu_hitlist_dev holds the hits_scores of a SearchFieldResult on the index's device, by ascending anchor id; between
  * two steps only the handles and the lists' lengths cross the bus.  ResolveTokenIdToAnchor starts from the (few) term hits
  * of vgpu_field_search on the host; Union / Intersect / BoostPlanStepFromBoostRequest go from handles to a handle;
- * vgpu_dev_top_n brings the k best hits back.  Handles belong to the index they were made on, which must outlive them;
+ * vgpu_dev_top_n brings the k best hits back.  Handles belong to the index they were made on (steps refuse foreign handles);
+ * a handle may be freed after its index was closed, but not used;
  * a sharded handle's lists hold the shard's anchors.  Whole requests should still go through vgpu_batch_execute, which
  * fuses these steps into one pass per tile; the step symbols serve hosts that drive the reference's plan themselves. */
 typedef struct vgpu_hitlist_dev vgpu_hitlist_dev;

@@ -101,14 +101,16 @@ static int32_t guarded(F&& f) {
 
 struct vgpu_hitlist_dev {
     vdev::DeviceHitList list;
+    int device = -1;  // where its buffer lives: kept apart from the index, which may already be closed when the handle is freed
 };
 template <class F>
-static int32_t make_dev_list(vgpu_hitlist_dev** out, F&& fill) {
+static int32_t make_dev_list(vgpu_index* idx, vgpu_hitlist_dev** out, F&& fill) {
     *out = nullptr;
     std::unique_ptr<vgpu_hitlist_dev> h(new vgpu_hitlist_dev());
+    h->device = idx->ix->device;
     const int32_t rc = guarded([&]() { fill(h->list); });
     if (rc == VGPU_OK) *out = h.release();
-    else if (h->list.ix) cudaSetDevice(h->list.ix->device);  // (its buffers go back to that device's pool)
+    else cudaSetDevice(h->device);  // (its buffers go back to that device's pool)
     return rc;
 }
 
@@ -620,7 +622,7 @@ int32_t vgpu_top_n(vgpu_index* idx, const vgpu_hitlist* in, uint32_t top, uint32
 // ---- device-resident step seam
 int32_t vgpu_dev_upload(vgpu_index* idx, const vgpu_hitlist* in, vgpu_hitlist_dev** out) {
     if (!idx || !in || !out) return VGPU_ERR_INVALID_REQUEST;
-    return make_dev_list(out, [&](vdev::DeviceHitList& l) { vsteps::dev_upload(*idx->ix, *in, l); });
+    return make_dev_list(idx, out, [&](vdev::DeviceHitList& l) { vsteps::dev_upload(*idx->ix, *in, l); });
 }
 int32_t vgpu_dev_download(const vgpu_hitlist_dev* list, vgpu_hitlist* out) {
     if (!list || !out) return VGPU_ERR_INVALID_REQUEST;
@@ -629,12 +631,12 @@ int32_t vgpu_dev_download(const vgpu_hitlist_dev* list, vgpu_hitlist* out) {
 uint32_t vgpu_dev_len(const vgpu_hitlist_dev* list) { return list ? list->list.n : 0u; }
 void vgpu_dev_free(vgpu_hitlist_dev* list) {
     if (!list) return;
-    if (list->list.ix) cudaSetDevice(list->list.ix->device);
+    if (list->device >= 0) cudaSetDevice(list->device);
     delete list;
 }
 int32_t vgpu_dev_resolve_to_anchor(vgpu_index* idx, const char* part_json, const vgpu_hitlist* term_hits, vgpu_hitlist_dev** out) {
     if (!idx || !part_json || !term_hits || !out) return VGPU_ERR_INVALID_REQUEST;
-    return make_dev_list(out, [&](vdev::DeviceHitList& l) { vsteps::dev_resolve_to_anchor(*idx->ix, part_json, *term_hits, l); });
+    return make_dev_list(idx, out, [&](vdev::DeviceHitList& l) { vsteps::dev_resolve_to_anchor(*idx->ix, part_json, *term_hits, l); });
 }
 static bool all_lists_given(const vgpu_hitlist_dev* const* inputs, uint32_t n) {
     if (n && !inputs) return false;
@@ -645,7 +647,7 @@ static bool all_lists_given(const vgpu_hitlist_dev* const* inputs, uint32_t n) {
 static int32_t dev_set_op(vgpu_index* idx, const vgpu_hitlist_dev* const* inputs, const char* const* terms, uint32_t n, bool is_union, vgpu_hitlist_dev** out) {
     std::vector<const vdev::DeviceHitList*> lists;
     for (uint32_t i = 0; i < n; ++i) lists.push_back(&inputs[i]->list);
-    return make_dev_list(out, [&](vdev::DeviceHitList& l) { vsteps::dev_set_op(*idx->ix, lists.data(), terms, n, is_union, l); });
+    return make_dev_list(idx, out, [&](vdev::DeviceHitList& l) { vsteps::dev_set_op(*idx->ix, lists.data(), terms, n, is_union, l); });
 }
 int32_t vgpu_dev_union_hits_score(vgpu_index* idx, const vgpu_hitlist_dev* const* inputs, const char* const* terms, uint32_t n, vgpu_hitlist_dev** out) {
     if (!idx || !out || !all_lists_given(inputs, n) || (n && !terms)) return VGPU_ERR_INVALID_REQUEST;
@@ -657,7 +659,7 @@ int32_t vgpu_dev_intersect_hits_score(vgpu_index* idx, const vgpu_hitlist_dev* c
 }
 int32_t vgpu_dev_add_boost(vgpu_index* idx, const char* boost_json, const vgpu_hitlist_dev* in, vgpu_hitlist_dev** out) {
     if (!idx || !boost_json || !in || !out) return VGPU_ERR_INVALID_REQUEST;
-    return make_dev_list(out, [&](vdev::DeviceHitList& l) { vsteps::dev_add_boost(*idx->ix, boost_json, in->list, l); });
+    return make_dev_list(idx, out, [&](vdev::DeviceHitList& l) { vsteps::dev_add_boost(*idx->ix, boost_json, in->list, l); });
 }
 int32_t vgpu_dev_top_n(vgpu_index* idx, const vgpu_hitlist_dev* in, uint32_t top, uint32_t skip, vgpu_hitlist* out) {
     if (!idx || !in || !out) return VGPU_ERR_INVALID_REQUEST;
