@@ -54,6 +54,28 @@ def test_oracle_reproduces_golden(native_libs, name, build):
         check_hits(res["num_hits"], [(h[0], h[1]) for h in res["data"]], case, case["request"])
 
 
+@pytest.mark.parametrize("name,build", [("reference_corpus", golden.build_reference_index), ("synthetic_small", golden.build_synthetic_index)])
+def test_python_oracle_reproduces_golden(native_libs, name, build):
+    """The goldens were written by the C++ oracle; the independent Python restatement (oracle/search_py.py: its own index
+    decoder, request reading, matching and scoring) must arrive at the same hits: what the CUDA path is held to in the
+    GPU test below does not rest on one implementation."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "..", "oracle"))
+    import search_py  # noqa: E402  (test infrastructure)
+    py = search_py.PySearch(build())
+    checked = 0
+    for case in load(name):
+        if "suggest" in case:
+            continue
+        try:
+            res = py.search(case["request"])
+        except search_py.Unsupported:  # regex parts
+            continue
+        check_hits(res["num_hits"], res["data"], case, case["request"])
+        checked += 1
+    assert checked >= 10, checked
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,build", [("reference_corpus", golden.build_reference_index), ("synthetic_small", golden.build_synthetic_index)])
 def test_cuda_path_matches_golden(native_libs, name, build):
