@@ -8,7 +8,7 @@ Covers SURVEY 8 rows a1, a4-a7, a9, a11, a12, a17 (search / or / and trees of se
 starts_with, ignore_case, boost; request boosts on the anchor level with every boost function, expression and
 skip_when_score; top / skip), and a10 / a13 / a14 / a16: `filter` trees, phrase boosts, text locality, facets -- the
 shape of BASELINE config 3 -- plus a8 (boosts on a 1:n level), a15 (boost_term), the per-part top / skip bound and token
-values of a4.  Not covered (raises): regex parts.
+values of a4, and suggest / suggest_multi (f.2).  Not covered (raises): regex parts.
 
 Each function cites the reference file:line it follows.
 """
@@ -429,6 +429,29 @@ class PySearch:
             v = self._boost_value(boost["path"], anchor)
             if v is not None:
                 hits[anchor] = self._apply_boost(boost, score, v)
+
+    # ---- search_field.rs:160-228: suggest_multi / suggest
+    def suggest_multi(self, request):
+        items = []
+        for part in request["suggest"]:
+            path, hits = self.field_search(part)
+            texts = {term_id: text for text, term_id in self._dictionary(path)}
+            items.extend((texts[term_id].lower(), score, term_id) for term_id, score in hits)  # return_term_lowercase
+        items.sort(key=lambda it: it[0], reverse=True)  # (stable where the reference's sort is not: equal texts keep their order)
+        merged = []
+        for text, score, term_id in items:  # dedup_by: equal texts merge into the first, which takes the larger score
+            if merged and merged[-1][0] == text:
+                if score > merged[-1][1]:
+                    merged[-1] = (text, score, merged[-1][2])
+            else:
+                merged.append((text, score, term_id))
+        merged.sort(key=lambda it: -float(it[1]))
+        skip, top = request.get("skip") or 0, request.get("top")
+        merged = merged[skip:]
+        return [(t, float(s), i) for t, s, i in (merged if top is None else merged[:top])]
+
+    def suggest(self, part):  # :219-228: the part's own top / skip also bound the merged list
+        return self.suggest_multi({"suggest": [part], "top": part.get("top"), "skip": part.get("skip")})
 
     # ---- search.rs:143-228
     def search(self, request):

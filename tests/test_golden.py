@@ -66,6 +66,8 @@ def test_python_oracle_reproduces_golden(native_libs, name, build):
     checked = 0
     for case in load(name):
         if "suggest" in case:
+            check_suggestions(py.suggest_multi(case["suggest"]), case, case["suggest"])
+            checked += 1
             continue
         try:
             res = py.search(case["request"])

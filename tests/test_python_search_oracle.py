@@ -248,3 +248,27 @@ def test_random_request_trees(native_libs):
             r["top"], r["skip"] = rng.randrange(1, 6), rng.randrange(0, 3)
         total += agree(cpp, py, r)
     assert total > 300
+
+
+def test_suggest(native_libs):  # tests.rs:1087-1158 and the shapes of tests/test_gpu_features.py::test_suggest_*
+    d = tempfile.mkdtemp(prefix="vb200_py_")
+    helpers.create_index(d, fx.TEST_ALL_DOCS, fx.TEST_ALL_CONFIG)
+    helpers.add_token_values(d, *fx.TEST_ALL_TOKEN_VALUES)
+    cpp, py = helpers.Oracle(d), search_py.PySearch(d)
+
+    def same(a, b, ctx):
+        assert [(t, i) for t, _, i in a] == [(t, i) for t, _, i in b], (ctx, a, b)
+        assert all(abs(x[1] - y[1]) <= 1e-5 * max(abs(x[1]), 1e-30) for x, y in zip(a, b)), ctx
+
+    part = {"terms": ["majes"], "path": GER, "levenshtein_distance": 0, "starts_with": True, "top": 10, "skip": 0}
+    got = py.suggest(part)
+    assert sorted(t for t, _, _ in got) == sorted(["majestät", "majestät (f)", "majestätisches", "majestätischer", "majestätischer anblick (m)", "majestätisches aussehen (n)"])
+    same(cpp.call("suggest", part=part), got, part)
+    tv = {"terms": ["begeist"], "path": GER, "levenshtein_distance": 0, "starts_with": True, "token_value": {"path": GER, "boost_fun": "Log10", "param": 1}, "top": 10, "skip": 0}
+    assert [t for t, _, _ in py.suggest(tv)] == ["begeisterung", "begeistern", "begeisterung (f)"]  # tests.rs:1134-1158
+    for req in ({"suggest": [{"terms": ["will"], "path": GER, "levenshtein_distance": 0, "starts_with": True}, {"terms": ["will"], "path": ENG, "levenshtein_distance": 0, "starts_with": True}], "top": 10, "skip": 0},
+                {"suggest": [{"terms": ["majes"], "path": GER, "starts_with": True}], "top": 2, "skip": 1},
+                {"suggest": [{"terms": ["Majestat"], "path": GER, "levenshtein_distance": 2}], "top": None},
+                {"suggest": [{"terms": ["will"], "path": GER, "starts_with": True, "boost": 3.0, "top": 2}, {"terms": ["wille"], "path": GER, "levenshtein_distance": 1}]},
+                {"suggest": [], "top": 10}):
+        same(cpp.call("suggest_multi", request=req), py.suggest_multi(req), req)
