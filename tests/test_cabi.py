@@ -42,6 +42,14 @@ def test_library_exports_every_declared_symbol(lib):
     assert not missing, f"declared in include/veloci_b200.h but not exported: {missing}"
 
 
+def test_every_symbol_appears_in_the_integration_notes():
+    """INTEGRATION.md shows the reference-side binding (the `-sys` crate's extern block and the Rust call sites): a symbol
+    added to the header without its binding there would be a seam nobody can use."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in declared_symbols() if n not in doc]
+    assert not missing, missing
+
+
 def test_python_binding_binds_only_declared_symbols():
     src = open(os.path.join(ROOT, "veloci_b200", "api.py")).read()
     used = set(re.findall(r"\bL\.(vgpu_[a-z0-9_]+)", src))
